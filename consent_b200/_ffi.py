@@ -1,0 +1,193 @@
+"""ctypes mirror of include/consent_b200.h and consent_b200/host/synth.h.
+
+Only plain C structs live here; nothing in this module computes anything.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+REPO_DIR = os.path.dirname(PKG_DIR)
+
+CG_OK = 0
+CG_WINDOW_CONSENSUS = 0
+CG_WINDOW_TEMPLATE = 1
+CG_N_STAGES = 7
+STAGE_NAMES = ("pack", "index", "chain", "split", "poa", "stitch", "polish")
+STATUS_NAMES = {
+    0: "CG_OK", -1: "CG_ERR_INVALID_ARG", -2: "CG_ERR_NO_DEVICE", -3: "CG_ERR_CUDA",
+    -4: "CG_ERR_OUT_OF_MEMORY", -5: "CG_ERR_BAD_BASE", -6: "CG_ERR_CAPACITY", -7: "CG_ERR_STATE",
+}
+
+
+class cg_params(C.Structure):
+    _fields_ = [("mer_size", C.c_uint32), ("solid_thresh", C.c_uint32),
+                ("common_kmers", C.c_uint32), ("min_anchors", C.c_uint32)]
+
+
+class cg_batch(C.Structure):
+    _fields_ = [("n_windows", C.c_uint32),
+                ("win_seq_begin", C.POINTER(C.c_uint32)),
+                ("seq_off", C.POINTER(C.c_uint64)),
+                ("bases", C.c_char_p)]
+
+
+class cg_results(C.Structure):
+    _fields_ = [("n_windows", C.c_uint32),
+                ("cons_off", C.POINTER(C.c_uint64)),
+                ("cons", C.POINTER(C.c_char)),
+                ("status", C.POINTER(C.c_uint8)),
+                ("solid_off", C.POINTER(C.c_uint64)),
+                ("solid_kmer", C.POINTER(C.c_uint32)),
+                ("solid_count", C.POINTER(C.c_uint32)),
+                ("owner_", C.c_void_p)]
+
+
+class cg_counters(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in (
+        "windows", "sequences", "bases", "anchors", "regions", "poa_graphs", "alignments",
+        "dp_cells", "dp_pred_cells", "solid_kmers", "consensus_bytes", "fallback_windows")]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+class cg_synth_spec(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("first_window", C.c_uint32), ("n_windows", C.c_uint32),
+                ("n_seqs", C.c_uint32), ("truth_len", C.c_uint32),
+                ("err", C.c_double), ("p_sub", C.c_double), ("p_ins", C.c_double)]
+
+
+@dataclass
+class Params:
+    """The four parameters the path reads (reference src/correctionMSA.cpp:31-32,43-45);
+    defaults = CONSENT-correct wrapper defaults (reference CONSENT-correct:42-50)."""
+    mer_size: int = 9
+    solid_thresh: int = 4
+    common_kmers: int = 8
+    min_anchors: int = 2
+
+    def c(self) -> cg_params:
+        return cg_params(self.mer_size, self.solid_thresh, self.common_kmers, self.min_anchors)
+
+
+class Batch:
+    """W windows of piles in the flat layout of cg_batch (host memory, numpy-owned)."""
+
+    def __init__(self, win_seq_begin: np.ndarray, seq_off: np.ndarray, bases: np.ndarray):
+        self.win_seq_begin = np.ascontiguousarray(win_seq_begin, dtype=np.uint32)
+        self.seq_off = np.ascontiguousarray(seq_off, dtype=np.uint64)
+        self.bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        assert self.win_seq_begin.ndim == 1 and len(self.win_seq_begin) >= 1
+        assert len(self.seq_off) == int(self.win_seq_begin[-1]) + 1
+        assert int(self.seq_off[-1]) <= len(self.bases)
+
+    @property
+    def n_windows(self) -> int:
+        return len(self.win_seq_begin) - 1
+
+    @property
+    def n_seqs(self) -> int:
+        return int(self.win_seq_begin[-1])
+
+    @property
+    def n_bases(self) -> int:
+        return int(self.seq_off[-1])
+
+    @classmethod
+    def from_piles(cls, piles) -> "Batch":
+        """piles: iterable of windows, each a list of str/bytes sequences (piles[w][0] = template)."""
+        wsb = [0]
+        off = [0]
+        chunks = []
+        for pile in piles:
+            for s in pile:
+                b = s.encode() if isinstance(s, str) else bytes(s)
+                chunks.append(b)
+                off.append(off[-1] + len(b))
+            wsb.append(wsb[-1] + len(pile))
+        bases = np.frombuffer(b"".join(chunks), dtype=np.uint8) if chunks else np.zeros(0, np.uint8)
+        if len(bases) == 0:
+            bases = np.zeros(1, np.uint8)
+        return cls(np.array(wsb, np.uint32), np.array(off, np.uint64), bases.copy())
+
+    def pile(self, w: int):
+        a, b = int(self.win_seq_begin[w]), int(self.win_seq_begin[w + 1])
+        raw = self.bases
+        return [raw[int(self.seq_off[s]):int(self.seq_off[s + 1])].tobytes().decode() for s in range(a, b)]
+
+    def slice(self, w0: int, w1: int) -> "Batch":
+        a, b = int(self.win_seq_begin[w0]), int(self.win_seq_begin[w1])
+        o0, o1 = int(self.seq_off[a]), int(self.seq_off[b])
+        return Batch(self.win_seq_begin[w0:w1 + 1] - np.uint32(a), self.seq_off[a:b + 1] - np.uint64(o0),
+                     self.bases[o0:max(o1, o0 + 1)].copy())
+
+    def c(self) -> cg_batch:
+        return cg_batch(self.n_windows,
+                        self.win_seq_begin.ctypes.data_as(C.POINTER(C.c_uint32)),
+                        self.seq_off.ctypes.data_as(C.POINTER(C.c_uint64)),
+                        C.cast(self.bases.ctypes.data, C.c_char_p))
+
+
+class Results:
+    """Host copy of cg_results (numpy-owned; the C buffers are freed on construction)."""
+
+    def __init__(self, r: cg_results):
+        W = int(r.n_windows)
+        self.n_windows = W
+        self.cons_off = np.ctypeslib.as_array(r.cons_off, shape=(W + 1,)).copy()
+        nb = int(self.cons_off[-1])
+        self.cons = (np.ctypeslib.as_array(C.cast(r.cons, C.POINTER(C.c_uint8)), shape=(max(nb, 1),))[:nb].copy()
+                     if nb else np.zeros(0, np.uint8))
+        self.status = np.ctypeslib.as_array(r.status, shape=(max(W, 1),))[:W].copy()
+        self.solid_off = np.ctypeslib.as_array(r.solid_off, shape=(W + 1,)).copy()
+        ns = int(self.solid_off[-1])
+        if ns:
+            self.solid_kmer = np.ctypeslib.as_array(r.solid_kmer, shape=(ns,)).copy()
+            self.solid_count = np.ctypeslib.as_array(r.solid_count, shape=(ns,)).copy()
+        else:
+            self.solid_kmer = np.zeros(0, np.uint32)
+            self.solid_count = np.zeros(0, np.uint32)
+
+    def consensus(self, w: int) -> str:
+        return self.cons[int(self.cons_off[w]):int(self.cons_off[w + 1])].tobytes().decode()
+
+    def solid(self, w: int):
+        a, b = int(self.solid_off[w]), int(self.solid_off[w + 1])
+        return list(zip(self.solid_kmer[a:b].tolist(), self.solid_count[a:b].tolist()))
+
+    def equals(self, other: "Results") -> bool:
+        return (self.n_windows == other.n_windows
+                and np.array_equal(self.cons_off, other.cons_off)
+                and np.array_equal(self.cons, other.cons)
+                and np.array_equal(self.status, other.status)
+                and np.array_equal(self.solid_off, other.solid_off)
+                and np.array_equal(self.solid_kmer, other.solid_kmer)
+                and np.array_equal(self.solid_count, other.solid_count))
+
+    def first_mismatch(self, other: "Results"):
+        """Index of the first window that differs (consensus, status or solid list), or None."""
+        for w in range(min(self.n_windows, other.n_windows)):
+            if (self.consensus(w) != other.consensus(w) or self.status[w] != other.status[w]
+                    or self.solid(w) != other.solid(w)):
+                return w
+        return None if self.n_windows == other.n_windows else min(self.n_windows, other.n_windows)
+
+    def digest(self) -> str:
+        """sha256 over every output byte in a canonical order ("checksum of checksums" for big runs)."""
+        import hashlib
+        h = hashlib.sha256()
+        for a in (self.cons_off, self.cons, self.status, self.solid_off, self.solid_kmer, self.solid_count):
+            h.update(np.ascontiguousarray(a).tobytes())
+        return h.hexdigest()
+
+
+def load_library(path: str) -> C.CDLL:
+    if not os.path.exists(path):
+        raise FileNotFoundError(
+            f"{path} is missing — build it with `python -c 'import __graft_entry__ as g; g.build()'`")
+    return C.CDLL(path, mode=C.RTLD_GLOBAL if False else C.RTLD_LOCAL)

@@ -1,0 +1,150 @@
+/*
+ * consent_b200.h — C ABI of the B200-native CONSENT per-window correction path.
+ *
+ * This is the drop-in boundary.  The reference has no FFI layer: its seam is the
+ * in-process C++ call
+ *
+ *   std::pair<std::string, robin_hood::unordered_map<kmer,unsigned>>
+ *   computeConsensusReadCorrection(readId, piles, pilesPos, minSupport, merSize,
+ *        commonKMers, minAnchors, solidThresh, windowSize, maxMSA, path)
+ *                                        (reference src/correctionMSA.h:8, body
+ *                                         src/correctionMSA.cpp:29-49)
+ *   computeConsensusAssemblyPolishing(id, ...same..., nbThreads)
+ *                                        (src/correctionMSA.h:10, body :51-70)
+ *
+ * called once per window from processRead (src/CONSENT-correction.cpp:34-44) and
+ * from the CTPL jobs of processContig (src/CONSENT-polishing.cpp:49,66).  One
+ * window per call cannot feed a GPU, so the replacement is the same function
+ * *batched over windows*: every entry point below takes W windows and returns,
+ * per window, exactly what the reference call returns for that window:
+ *
+ *   - the consensus string, mixed case (upper = solid k-mer support), byte for
+ *     byte what `.first` of the reference pair holds,
+ *   - the solid k-mers of the pile with their occurrence counts, i.e. every
+ *     (kmer, count) of `.second` with count >= solidThresh, sorted by k-mer
+ *     value (the reference map additionally holds zero-count keys inserted by
+ *     operator[] look-ups; its consumers only look keys up and absent == 0:
+ *     src/correctionAlignment.cpp:6-15,103-104),
+ *   - a status byte telling whether MSABMAAC produced a consensus or the raw
+ *     template was returned (src/correctionMSA.cpp:34-36).
+ *
+ * Unused reference arguments (readId, pilesPos, minSupport, windowSize, maxMSA,
+ * path, id, nbThreads — never read on this path, BMEAN/bmean.cpp:585-599,738)
+ * are not part of the ABI.
+ *
+ * Plain pointers and sizes only; no C++ or torch types cross this boundary.
+ * All functions return CG_OK (0) or a negative cg_status; no exceptions.
+ */
+#ifndef CONSENT_B200_H
+#define CONSENT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CG_ABI_VERSION 1
+
+typedef enum cg_status {
+    CG_OK                 =  0,
+    CG_ERR_INVALID_ARG    = -1,  /* null pointer, empty pile, k out of range ...     */
+    CG_ERR_NO_DEVICE      = -2,  /* no CUDA device / extension not usable            */
+    CG_ERR_CUDA           = -3,  /* a CUDA runtime call failed, see cg_last_error    */
+    CG_ERR_OUT_OF_MEMORY  = -4,
+    CG_ERR_BAD_BASE       = -5,  /* a base outside {A,C,G,T} (reads are 2-bit stored
+                                    upstream, src/utils.cpp:21-54,189, so the
+                                    reference never sees one)                       */
+    CG_ERR_CAPACITY       = -6,  /* a per-window limit of this build was exceeded    */
+    CG_ERR_STATE          = -7   /* call sequence error (run before upload ...)      */
+} cg_status;
+
+/* Parameters actually read by the path (src/correctionMSA.cpp:31-32,43-45).
+ * Defaults of the CONSENT-correct wrapper: k=9, solid=4, commonKMers=8,
+ * minAnchors=2 (reference CONSENT-correct:42-50). */
+typedef struct cg_params {
+    uint32_t mer_size;      /* -k  merSize      : k-mer length, 2..15 (reference: 1<<(2k) overflows at 16, bmean.cpp:46) */
+    uint32_t solid_thresh;  /* -f  solidThresh  : min occurrences for a solid k-mer     */
+    uint32_t common_kmers;  /* -c  commonKMers  : anchor support cap; S = min(c, N/2)   */
+    uint32_t min_anchors;   /* -A  minAnchors   : MSABMAAC bails out if regions < this  */
+} cg_params;
+
+/* W windows.  Window w owns sequences [win_seq_begin[w], win_seq_begin[w+1]);
+ * its first sequence is the template (piles[0]).  Sequence s owns bytes
+ * [seq_off[s], seq_off[s+1]) of `bases` (ASCII, upper-case ACGT, no terminator).
+ * Caller owns all input buffers. */
+typedef struct cg_batch {
+    uint32_t        n_windows;
+    const uint32_t* win_seq_begin;   /* [n_windows + 1] */
+    const uint64_t* seq_off;         /* [n_seqs + 1], n_seqs = win_seq_begin[n_windows] */
+    const char*     bases;
+} cg_batch;
+
+#define CG_WINDOW_CONSENSUS   0   /* MSABMAAC produced a consensus                      */
+#define CG_WINDOW_TEMPLATE    1   /* fell back to the raw template (correctionMSA.cpp:34-36) */
+
+/* Results for W windows, owned by the library until cg_free_results(). */
+typedef struct cg_results {
+    uint32_t  n_windows;
+    uint64_t* cons_off;      /* [n_windows + 1] byte offsets into cons                 */
+    char*     cons;          /* consensus strings, mixed case, concatenated            */
+    uint8_t*  status;        /* [n_windows] CG_WINDOW_*                                */
+    uint64_t* solid_off;     /* [n_windows + 1] offsets into solid_kmer/solid_count    */
+    uint32_t* solid_kmer;    /* 2-bit packed k-mers (A0 C1 G2 T3, first base most
+                                significant: BMEAN/utils.cpp:18-30), ascending         */
+    uint32_t* solid_count;   /* total occurrences in the pile (>= solid_thresh)        */
+    void*     owner_;        /* private                                                */
+} cg_results;
+
+typedef struct cg_handle cg_handle;
+
+/* Device / lifetime ------------------------------------------------------ */
+int         cg_abi_version(void);
+int         cg_device_count(void);
+/* Create a context bound to CUDA device `device` (own stream, own workspaces). */
+int         cg_create(int device, const cg_params* params, cg_handle** out);
+void        cg_destroy(cg_handle* h);
+const char* cg_last_error(const cg_handle* h);   /* h may be NULL: last create error */
+
+/* One-shot call: host buffers in, host buffers out (H2D, kernels, D2H inside).
+ * This is the batched equivalent of calling computeConsensusReadCorrection on
+ * every window of `in`.  Blocking; one call at a time per handle. */
+int  cg_correct_windows(cg_handle* h, const cg_batch* in, cg_results* out);
+void cg_free_results(cg_results* r);
+
+/* Staged calls (what cg_correct_windows does, split so a caller — and bench.py —
+ * can keep a batch resident in HBM and time the kernels alone). */
+int  cg_upload(cg_handle* h, const cg_batch* in);   /* H2D + 2-bit packing on device  */
+int  cg_run(cg_handle* h);                          /* every kernel of the path       */
+int  cg_download(cg_handle* h, cg_results* out);    /* D2H of the results of cg_run   */
+
+/* Instrumentation -------------------------------------------------------- */
+#define CG_STAGE_PACK     0   /* ASCII -> 2-bit                                         */
+#define CG_STAGE_INDEX    1   /* k-mer counts, solid list, template anchor table  (a3-a5) */
+#define CG_STAGE_CHAIN    2   /* pair scores + chain DP                           (a6-a7) */
+#define CG_STAGE_SPLIT    3   /* distance stats + segment split                   (a8-a9) */
+#define CG_STAGE_POA      4   /* segmented POA + column vote                     (a11-a14) */
+#define CG_STAGE_STITCH   5   /* concatenate region consensuses                     (a11) */
+#define CG_STAGE_POLISH   6   /* weight + DBG polish                             (a15-a19) */
+#define CG_N_STAGES       7
+/* CUDA-event time (ms) each stage spent on the handle's stream in the last cg_run,
+ * and the number of kernel launches it made. */
+int  cg_stage_ms(const cg_handle* h, float ms[CG_N_STAGES], uint32_t launches[CG_N_STAGES]);
+
+/* Work counters of the last cg_run, the inputs of the algorithmic-bytes model
+ * (SURVEY §8d): alignments, score-matrix cells sum (V+1)*L, predecessor-row cells
+ * sum E*L, POA graphs, anchors in chains, solid k-mers, packed input bytes,
+ * consensus bytes. */
+typedef struct cg_counters {
+    uint64_t windows, sequences, bases;
+    uint64_t anchors, regions, poa_graphs, alignments;
+    uint64_t dp_cells, dp_pred_cells;
+    uint64_t solid_kmers, consensus_bytes, fallback_windows;
+} cg_counters;
+int  cg_get_counters(const cg_handle* h, cg_counters* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CONSENT_B200_H */

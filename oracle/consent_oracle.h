@@ -1,0 +1,25 @@
+/* consent_oracle.h — TEST INFRASTRUCTURE (CPU oracle), see consent_oracle.c. */
+#ifndef CONSENT_ORACLE_H
+#define CONSENT_ORACLE_H
+#include "consent_b200.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Same contract as the reference harness (oracle/ref_harness.cpp: ref_correct_windows). */
+int   oracle_correct_windows(const cg_batch* in, const cg_params* p, int threads, int with_status,
+                             cg_results* out, double* seconds);
+void  oracle_free_results(cg_results* r);
+/* Per-stage text dump of window w, same format as ref_dump_window. malloc'ed. */
+char* oracle_dump_window(const cg_batch* in, uint32_t w, const cg_params* p);
+/* MSA rows (newline separated) of one POA run over seqs[0..n). malloc'ed. */
+char* oracle_spoa_msa(const char* const* seqs, uint32_t n);
+void  oracle_free_text(char* p);
+/* Work counters accumulated by oracle_correct_windows since the last reset. */
+void  oracle_reset_counters(void);
+void  oracle_get_counters(cg_counters* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

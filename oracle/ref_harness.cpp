@@ -1,0 +1,258 @@
+// ref_harness.cpp — TEST INFRASTRUCTURE, not product code.
+//
+// Thin C-ABI harness around the UNMODIFIED reference implementation of the hot
+// path.  It is compiled by oracle/Makefile together with the reference's own
+// source files, taken where they lie under /root/reference (nothing is copied
+// into this repository), into oracle/_ref/libconsent_ref_*.so.
+//
+// What it calls (reference file:line):
+//   computeConsensusReadCorrection            src/correctionMSA.cpp:29-49
+//   and, for the per-stage dump only, the stage functions of BMEAN/bmean.cpp
+//   (fill_index_kmers :43, filter_index_kmers :88, get_template :220,
+//    longest_ordered_chain :239, average_distance_next_anchor :331,
+//    split_reads :476, easy_consensus :603) and weightConsensus /
+//   polishCorrection (src/correctionMSA.cpp:6, src/correctionDBG.cpp:93).
+//
+// Used by: tests/ (to pin oracle/consent_oracle.c and to generate
+// tests/golden/*), bench.py's cpu_baseline / --impl reference legs.
+// Threading = std::thread workers pulling windows from an atomic counter, the
+// faithful equivalent of the reference's CTPL pool (src/CONSENT-correction.cpp:77).
+
+#include <atomic>
+#include <chrono>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <sstream>
+#include <string>
+#include <thread>
+#include <utility>
+#include <vector>
+#include <algorithm>
+
+#include "robin_hood.h"          // src/robin_hood.h (3.11.3) via -I, see Makefile
+#include "correctionMSA.h"       // src/correctionMSA.h
+#include "correctionDBG.h"       // src/correctionDBG.h
+#include "consent_b200.h"        // our ABI structs (cg_batch, cg_results, cg_params)
+
+// ---- prototypes of the reference's stage functions (external linkage in
+// ---- BMEAN/bmean.cpp; re-declared here, layout-identical structs) ----------
+struct localisation { uint32_t read_id; int32_t position; };
+typedef robin_hood::unordered_map<kmer, std::vector<localisation>> kmer2localisation;
+void fill_index_kmers(const std::vector<std::string>& Reads, kmer2localisation& kmer_index, uint32_t kmer_size,
+                      robin_hood::unordered_map<kmer, unsigned>& merCounts, unsigned solidThresh);
+robin_hood::unordered_map<kmer, uint32_t> filter_index_kmers(kmer2localisation& kmer_index, double amount);
+std::vector<kmer> get_template(kmer2localisation& kmer_index, const std::string& read, int kmer_size);
+std::vector<kmer> longest_ordered_chain(kmer2localisation& kmer_index, const std::vector<kmer>& template_read, double edge_solidity);
+std::vector<double> average_distance_next_anchor(kmer2localisation& kmer_index, std::vector<kmer>& anchors,
+                                                 robin_hood::unordered_map<kmer, uint32_t>& k_count, bool clean);
+std::vector<std::vector<std::string>> split_reads(const std::vector<kmer>& anchors, const std::vector<double>& relative_positions,
+                                                  const std::vector<std::string>& Reads, kmer2localisation& kmer_index, uint32_t kmer_size);
+std::vector<std::string> easy_consensus(std::vector<std::string> V, unsigned maxMSA, std::string path);
+std::vector<std::string> consensus_SPOA(std::vector<std::string>& W, unsigned maxMSA, std::string path);
+std::pair<std::vector<std::vector<std::string>>, robin_hood::unordered_map<kmer, unsigned>>
+MSABMAAC(const std::vector<std::string>& Reads, uint32_t k, double edge_solidity, unsigned solidThresh,
+         unsigned minAnchors, unsigned maxMSA, std::string path);                 // BMEAN/bmean.cpp:738
+std::string weightConsensus(std::string& consensus, std::vector<std::string>& pile,
+                            robin_hood::unordered_map<kmer, unsigned>& merCounts, unsigned merSize,
+                            unsigned windowSize, unsigned solidThresh);
+
+namespace {
+
+struct Owner {
+    std::vector<uint64_t> cons_off, solid_off;
+    std::string cons;
+    std::vector<uint8_t> status;
+    std::vector<uint32_t> solid_kmer, solid_count;
+};
+
+std::vector<std::string> window_pile(const cg_batch* in, uint32_t w) {
+    std::vector<std::string> pile;
+    for (uint32_t s = in->win_seq_begin[w]; s < in->win_seq_begin[w + 1]; ++s)
+        pile.emplace_back(in->bases + in->seq_off[s], in->bases + in->seq_off[s + 1]);
+    return pile;
+}
+
+struct WinOut {
+    std::string cons;
+    std::vector<std::pair<uint32_t, uint32_t>> solid;
+    uint8_t status;
+};
+
+void run_one(const cg_batch* in, uint32_t w, const cg_params* p, WinOut& o) {
+    std::vector<std::string> pile = window_pile(in, w);
+    std::string readId = "w";
+    std::pair<unsigned, unsigned> pos(0, 0);
+    unsigned minSupport = 3, merSize = p->mer_size, commonKMers = p->common_kmers,
+             minAnchors = p->min_anchors, solid = p->solid_thresh, windowSize = 500;
+    auto r = computeConsensusReadCorrection(readId, pile, pos, minSupport, merSize, commonKMers,
+                                            minAnchors, solid, windowSize, 150, std::string());
+    o.cons = r.first;
+    o.solid.clear();
+    for (auto& kv : r.second)
+        if (kv.second >= solid) o.solid.emplace_back(kv.first, kv.second);
+    std::sort(o.solid.begin(), o.solid.end());
+    // "fell back to template" is not observable from the return value alone when the
+    // consensus happens to equal the template; recompute it the way the reference
+    // decides it: MSABMAAC returned no consensus (src/correctionMSA.cpp:34).
+    int bmeanSup = std::min((int)commonKMers, (int)pile.size() / 2);
+    auto m = MSABMAAC(pile, merSize, bmeanSup, solid, minAnchors, 150, std::string());
+    o.status = m.first.size() == 0 ? CG_WINDOW_TEMPLATE : CG_WINDOW_CONSENSUS;
+}
+
+}  // namespace
+
+extern "C" {
+
+// Runs the reference on every window of `in` with `threads` workers.
+// *seconds receives the wall time of the compute loop only.
+// If with_status == 0 the (costly, second MSABMAAC call) status derivation is
+// skipped and status[] is all CG_WINDOW_CONSENSUS — used for timing runs.
+int ref_correct_windows(const cg_batch* in, const cg_params* p, int threads, int with_status,
+                        cg_results* out, double* seconds) {
+    if (!in || !p || !out) return CG_ERR_INVALID_ARG;
+    const uint32_t W = in->n_windows;
+    std::vector<WinOut> res(W);
+    std::atomic<uint32_t> next(0);
+    if (threads < 1) threads = 1;
+    auto t0 = std::chrono::steady_clock::now();
+    auto worker = [&]() {
+        for (;;) {
+            uint32_t w = next.fetch_add(1);
+            if (w >= W) break;
+            if (with_status) {
+                run_one(in, w, p, res[w]);
+            } else {
+                std::vector<std::string> pile = window_pile(in, w);
+                std::string readId = "w";
+                std::pair<unsigned, unsigned> pos(0, 0);
+                unsigned minSupport = 3, merSize = p->mer_size, commonKMers = p->common_kmers,
+                         minAnchors = p->min_anchors, solid = p->solid_thresh, windowSize = 500;
+                auto r = computeConsensusReadCorrection(readId, pile, pos, minSupport, merSize, commonKMers,
+                                                        minAnchors, solid, windowSize, 150, std::string());
+                res[w].cons = r.first;
+                for (auto& kv : r.second)
+                    if (kv.second >= solid) res[w].solid.emplace_back(kv.first, kv.second);
+                std::sort(res[w].solid.begin(), res[w].solid.end());
+                res[w].status = CG_WINDOW_CONSENSUS;
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; ++t) pool.emplace_back(worker);
+    worker();
+    for (auto& t : pool) t.join();
+    auto t1 = std::chrono::steady_clock::now();
+    if (seconds) *seconds = std::chrono::duration<double>(t1 - t0).count();
+
+    Owner* ow = new Owner();
+    ow->cons_off.resize(W + 1, 0);
+    ow->solid_off.resize(W + 1, 0);
+    ow->status.resize(W);
+    for (uint32_t w = 0; w < W; ++w) {
+        ow->cons += res[w].cons;
+        ow->cons_off[w + 1] = ow->cons.size();
+        for (auto& kv : res[w].solid) { ow->solid_kmer.push_back(kv.first); ow->solid_count.push_back(kv.second); }
+        ow->solid_off[w + 1] = ow->solid_kmer.size();
+        ow->status[w] = res[w].status;
+    }
+    out->n_windows = W;
+    out->cons_off = ow->cons_off.data();
+    out->cons = const_cast<char*>(ow->cons.data());
+    out->status = ow->status.data();
+    out->solid_off = ow->solid_off.data();
+    out->solid_kmer = ow->solid_kmer.data();
+    out->solid_count = ow->solid_count.data();
+    out->owner_ = ow;
+    return CG_OK;
+}
+
+void ref_free_results(cg_results* r) {
+    if (r && r->owner_) { delete static_cast<Owner*>(r->owner_); r->owner_ = nullptr; }
+}
+
+// Per-stage text dump of one window, produced by calling the reference's own
+// stage functions in the order MSABMAAC does (BMEAN/bmean.cpp:763-821).  The
+// oracle emits the same format (oracle_dump_window) so stages can be diffed.
+// Returned buffer is malloc'ed; free with ref_free_text.
+char* ref_dump_window(const cg_batch* in, uint32_t w, const cg_params* p) {
+    std::vector<std::string> Reads = window_pile(in, w);
+    std::ostringstream os;
+    unsigned k = p->mer_size, solid = p->solid_thresh;
+    int S = std::min((int)p->common_kmers, (int)Reads.size() / 2);
+    os << "S " << S << "\n";
+    kmer2localisation kmer_index;
+    robin_hood::unordered_map<kmer, unsigned> merCounts;
+    fill_index_kmers(Reads, kmer_index, k, merCounts, solid);
+    {
+        std::vector<std::pair<uint32_t, uint32_t>> v;
+        for (auto& kv : merCounts) if (kv.second >= solid) v.emplace_back(kv.first, kv.second);
+        std::sort(v.begin(), v.end());
+        os << "M " << v.size();
+        for (auto& kv : v) os << " " << kv.first << ":" << kv.second;
+        os << "\n";
+    }
+    auto kmer_count = filter_index_kmers(kmer_index, (double)S);
+    auto tpl = get_template(kmer_index, Reads[0], (int)k);
+    os << "T " << tpl.size();
+    for (auto x : tpl) os << " " << x;
+    os << "\n";
+    std::vector<kmer> anchors = longest_ordered_chain(kmer_index, tpl, (double)S);
+    os << "A " << anchors.size();
+    for (auto x : anchors) os << " " << x;
+    os << "\n";
+    std::vector<double> rel = average_distance_next_anchor(kmer_index, anchors, kmer_count, false);
+    os << "R " << rel.size();
+    for (auto x : rel) os << " " << (long long)x;
+    os << "\n";
+    auto regions = split_reads(anchors, rel, Reads, kmer_index, k);
+    os << "G " << regions.size() << "\n";
+    std::string stacked;
+    if (regions.size() >= p->min_anchors) {
+        for (size_t i = 0; i < regions.size(); ++i) {
+            os << "g " << i << " " << regions[i].size();
+            for (auto& s : regions[i]) os << " " << s;
+            os << "\n";
+            if (regions[i].empty()) continue;
+            auto c = easy_consensus(regions[i], 150, std::string());
+            os << "c " << i << " " << c[0] << "\n";
+            stacked += c[0];
+        }
+    }
+    os << "C " << stacked << "\n";
+    std::string cons;
+    if (stacked.empty()) {
+        cons = Reads[0];
+    } else {
+        cons = stacked;
+        if (cons.length() >= k) {
+            cons = weightConsensus(cons, Reads, merCounts, k, 500, solid);
+            os << "W " << cons << "\n";
+            cons = polishCorrection(cons, merCounts, k, solid);
+        }
+    }
+    os << "P " << cons << "\n";
+    std::string s = os.str();
+    char* buf = (char*)malloc(s.size() + 1);
+    memcpy(buf, s.c_str(), s.size() + 1);
+    return buf;
+}
+
+// MSA rows of one POA run over the given strings (consensus_SPOA, bmean.cpp:585-599),
+// newline separated.  For pinning the oracle's POA restatement in isolation.
+char* ref_spoa_msa(const char* const* seqs, uint32_t n) {
+    std::vector<std::string> W;
+    for (uint32_t i = 0; i < n; ++i) W.emplace_back(seqs[i]);
+    auto msa = consensus_SPOA(W, 150, std::string());
+    std::string s;
+    for (auto& r : msa) { s += r; s += '\n'; }
+    char* buf = (char*)malloc(s.size() + 1);
+    memcpy(buf, s.c_str(), s.size() + 1);
+    return buf;
+}
+
+void ref_free_text(char* p) { free(p); }
+
+int ref_hardware_threads(void) { return (int)std::thread::hardware_concurrency(); }
+
+}  // extern "C"

@@ -1,0 +1,110 @@
+"""Test-only access to the checkers: oracle/liboracle.so (our C restatement) and
+oracle/_ref/libconsent_ref_*.so (the unmodified reference).  Product code never imports this."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from consent_b200._ffi import (Batch, Params, REPO_DIR, Results, cg_batch, cg_counters, cg_params,
+                               cg_results)
+
+ORACLE_DIR = os.path.join(REPO_DIR, "oracle")
+
+
+def _cpu_has(flag: str) -> bool:
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    return flag in line.split()
+    except OSError:
+        pass
+    return False
+
+
+def ref_library_path() -> str | None:
+    for name, flag in (("avx2", "avx2"), ("sse41", "sse4_1")):
+        p = os.path.join(ORACLE_DIR, "_ref", f"libconsent_ref_{name}.so")
+        if os.path.exists(p) and _cpu_has(flag):
+            return p
+    return None
+
+
+class _Checker:
+    prefix = ""
+
+    def __init__(self, path: str):
+        self.path = path
+        self.lib = C.CDLL(path)
+        f = getattr(self.lib, self.prefix + "_correct_windows")
+        f.restype = C.c_int
+        f.argtypes = [C.POINTER(cg_batch), C.POINTER(cg_params), C.c_int, C.c_int,
+                      C.POINTER(cg_results), C.POINTER(C.c_double)]
+        self._run = f
+        self._free = getattr(self.lib, self.prefix + "_free_results")
+        self._free.argtypes = [C.POINTER(cg_results)]
+        self._dump = getattr(self.lib, self.prefix + "_dump_window")
+        self._dump.restype = C.c_void_p
+        self._dump.argtypes = [C.POINTER(cg_batch), C.c_uint32, C.POINTER(cg_params)]
+        self._msa = getattr(self.lib, self.prefix + "_spoa_msa")
+        self._msa.restype = C.c_void_p
+        self._msa.argtypes = [C.POINTER(C.c_char_p), C.c_uint32]
+        self._free_text = getattr(self.lib, self.prefix + "_free_text")
+        self._free_text.argtypes = [C.c_void_p]
+
+    def correct_windows(self, batch: Batch, params: Params = Params(), threads: int = 1,
+                        with_status: bool = True):
+        """-> (Results, seconds of the compute loop)"""
+        cb, cp, r, sec = batch.c(), params.c(), cg_results(), C.c_double(0)
+        rc = self._run(C.byref(cb), C.byref(cp), threads, int(with_status), C.byref(r), C.byref(sec))
+        if rc != 0:
+            raise RuntimeError(f"{self.prefix}_correct_windows -> {rc}")
+        out = Results(r)
+        self._free(C.byref(r))
+        return out, sec.value
+
+    def dump_window(self, batch: Batch, w: int, params: Params = Params()) -> str:
+        cb, cp = batch.c(), params.c()
+        p = self._dump(C.byref(cb), w, C.byref(cp))
+        s = C.string_at(p).decode()
+        self._free_text(p)
+        return s
+
+    def spoa_msa(self, seqs) -> list[str]:
+        arr = (C.c_char_p * len(seqs))(*[s.encode() for s in seqs])
+        p = self._msa(arr, len(seqs))
+        s = C.string_at(p).decode()
+        self._free_text(p)
+        return s.split("\n")[:-1] if s else []
+
+
+class Reference(_Checker):
+    """The unmodified reference (oracle/_ref)."""
+    prefix = "ref"
+
+    def __init__(self):
+        p = ref_library_path()
+        if p is None:
+            raise FileNotFoundError("oracle/_ref/libconsent_ref_*.so not built (make -C oracle ref)")
+        super().__init__(p)
+        self.lib.ref_hardware_threads.restype = C.c_int
+
+    def hardware_threads(self) -> int:
+        return int(self.lib.ref_hardware_threads())
+
+
+class Oracle(_Checker):
+    """Our plain-C restatement (oracle/consent_oracle.c)."""
+    prefix = "oracle"
+
+    def __init__(self):
+        p = os.path.join(ORACLE_DIR, "liboracle.so")
+        if not os.path.exists(p):
+            raise FileNotFoundError("oracle/liboracle.so not built (make -C oracle oracle)")
+        super().__init__(p)
+        self.lib.oracle_get_counters.argtypes = [C.POINTER(cg_counters)]
+
+    def counters(self) -> dict:
+        c = cg_counters()
+        self.lib.oracle_get_counters(C.byref(c))
+        return c.as_dict()
