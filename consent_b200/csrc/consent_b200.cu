@@ -1,0 +1,541 @@
+// consent_b200.cu — C ABI (include/consent_b200.h) of the B200-native CONSENT per-window correction path.
+//
+// Host side = the batched equivalent of the reference's per-window call
+//   computeConsensusReadCorrection / computeConsensusAssemblyPolishing   (src/correctionMSA.cpp:29-70)
+// as driven by processRead (src/CONSENT-correction.cpp:34-44): upload a batch of piles, run every stage as
+// CUDA kernels over chunks of windows, hand back consensus + solid k-mers + status per window.
+// There is no CPU implementation behind this ABI: without a CUDA device cg_create fails (CG_ERR_NO_DEVICE).
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "consent_b200.h"
+#include "cg_common.cuh"
+#include "k_prep.cuh"
+#include "k_index.cuh"
+#include "k_chain.cuh"
+#include "k_split.cuh"
+#include "k_poa.cuh"
+#include "k_polish.cuh"
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes, bool keep = false, cudaStream_t st = nullptr) {
+        if (bytes <= cap) return cudaSuccess;
+        size_t ncap = bytes + bytes / 4 + 256;
+        void* np = nullptr;
+        cudaError_t e = cudaMalloc(&np, ncap);
+        if (e != cudaSuccess) return e;
+        if (keep && p && cap) {
+            e = cudaMemcpyAsync(np, p, cap, cudaMemcpyDeviceToDevice, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) { cudaFree(np); return e; }
+        }
+        if (p) cudaFree(p);
+        p = np; cap = ncap;
+        return cudaSuccess;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return (T*)p; }
+};
+
+struct ChunkPlan {
+    u32 w0, nwin;
+    u64 pword_base, nwords;
+    u64 solid_tot, slot_tot, pos_tot, reg_tot, arena_tot;
+    u32 max_tk, max_n;
+};
+
+struct PoaTier {
+    u32 vcap, ecap, lcap;
+    u64 hcap;
+    u32 warps;
+    DevBuf mem, desc;
+    bool ready = false;
+};
+
+struct cg_handle {
+    int device = 0;
+    cg_params p{};
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int sms = 148;
+    int smem_optin = 0;
+    // options
+    size_t chunk_budget = (size_t)6 << 30;
+    u32 chunk_max_windows = 16384;
+    u32 poa_warps_per_sm[3] = {16, 1, 0};           // tier 2: fixed 8 warps
+    // batch (device) + host copies of the offsets for planning
+    u32 W = 0;
+    u64 n_seqs = 0, n_bases = 0;
+    DevBuf d_bases, d_seq_off, d_wsb;
+    std::vector<u32> h_wsb;
+    std::vector<u64> h_seq_off;
+    std::vector<ChunkPlan> chunks;
+    bool uploaded = false, ran = false;
+    // chunk workspaces
+    DevBuf pwords, ptags, win, offs, solid_k, solid_c, slot_tpos, slot_kmer, anchors, chain, rel, pos, regions, arena, fin, visited;
+    DevBuf jobs, jobs_next, ctl, off_fin, out_off;
+    PoaTier tier[3];
+    // batch outputs (device, dense)
+    DevBuf o_cons, o_sk, o_sc, o_status, o_len, o_nsol;
+    u64 o_cons_n = 0, o_solid_n = 0;
+    // instrumentation
+    float stage_ms[CG_N_STAGES]{};
+    u32 stage_launches[CG_N_STAGES]{};
+    cg_counters counters{};
+    u32* h_ctl = nullptr;        // pinned: flags + queue control + totals
+};
+
+namespace {
+
+std::string g_create_err;
+
+#define CK(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e__ = (call);                                                                    \
+        if (e__ != cudaSuccess) {                                                                    \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e__);                            \
+            return e__ == cudaErrorMemoryAllocation ? CG_ERR_OUT_OF_MEMORY : CG_ERR_CUDA;            \
+        }                                                                                            \
+    } while (0)
+
+inline u64 round_up(u64 v, u64 m) { return (v + m - 1) / m * m; }
+
+// ctl layout (u32 words, device): [0] flags, [4..7] tier-0 queue {njobs,next,overflow,_}, [8..11] tier 1, [12..15] tier 2
+enum { CTL_FLAGS = 0, CTL_Q0 = 4, CTL_Q1 = 8, CTL_Q2 = 12, CTL_WORDS = 16 };
+// offs layout (u64 arrays of nwin+1): solid, slot, pos, reg, arena
+// out_off layout: cons_off[nwin+1], solid_off[nwin+1]
+
+int plan_chunks(cg_handle* h) {
+    h->chunks.clear();
+    const u32 k = h->p.mer_size;
+    u32 w = 0;
+    while (w < h->W) {
+        ChunkPlan c{};
+        c.w0 = w;
+        c.pword_base = (h->h_seq_off[h->h_wsb[w]] >> 4) + h->h_wsb[w];
+        size_t bytes = 0;
+        while (w < h->W && c.nwin < h->chunk_max_windows) {
+            const u32 s0 = h->h_wsb[w], s1 = h->h_wsb[w + 1], N = s1 - s0;
+            u64 nocc = 0;
+            for (u32 s = s0; s < s1; ++s) {
+                const u64 len = h->h_seq_off[s + 1] - h->h_seq_off[s];
+                if (len >= k) nocc += len - k + 1;
+            }
+            const u64 tlen = h->h_seq_off[s0 + 1] - h->h_seq_off[s0];
+            const u64 tk = tlen >= k ? tlen - k + 1 : 0;
+            const u64 nb = h->h_seq_off[s1] - h->h_seq_off[s0];
+            const u64 a_solid = round_up(nocc / h->p.solid_thresh, 4), a_slot = round_up(tk, 8), a_pos = round_up(tk * N, 8),
+                      a_reg = tk + 2, a_arena = round_up(nb + N, 16);
+            const u64 words = ((h->h_seq_off[s1] >> 4) + s1) - ((h->h_seq_off[s0] >> 4) + s0);
+            const size_t wbytes = a_solid * 8 + a_solid / 8 + 8 + a_slot * 14 + a_pos * 2 + a_reg * (sizeof(CgRegion) + 8) + a_arena +
+                                  words * 8 + sizeof(CgWin) + 64 + 6 * tlen + 256;
+            if (c.nwin > 0 && bytes + wbytes > h->chunk_budget) break;
+            bytes += wbytes;
+            c.solid_tot += a_solid; c.slot_tot += a_slot; c.pos_tot += a_pos; c.reg_tot += a_reg; c.arena_tot += a_arena;
+            c.max_tk = std::max<u32>(c.max_tk, (u32)tk); c.max_n = std::max<u32>(c.max_n, N);
+            c.nwin++; ++w;
+        }
+        const u32 s1 = h->h_wsb[w];
+        c.nwords = ((h->h_seq_off[s1] >> 4) + s1) - c.pword_base;
+        h->chunks.push_back(c);
+    }
+    return CG_OK;
+}
+
+int ensure_tier(cg_handle* h, int t) {
+    PoaTier& T = h->tier[t];
+    if (T.ready) return CG_OK;
+    const u32 ncap = CG_N_MAX + 1;
+    const u32 scap = 2 * (T.ecap + 4 * T.vcap);
+    const u32 alncap = T.vcap + T.lcap + 2;
+    // per-warp layout (all sub-arrays 16-byte aligned)
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t at = o; o += round_up(bytes, 16); return at; };
+    const size_t o_letter = take(T.vcap), o_in0 = take(T.vcap), o_nal = take(T.vcap), o_leader = take(T.vcap), o_marks = take(T.vcap),
+                 o_check = take(T.vcap), o_nseq = take(2 * (size_t)T.vcap), o_aligned = take(6 * (size_t)T.vcap),
+                 o_rank = take(2 * (size_t)T.vcap), o_r2n = take(2 * (size_t)T.vcap), o_ih = take(4 * (size_t)T.vcap),
+                 o_it = take(4 * (size_t)T.vcap), o_ep = take(2 * (size_t)T.ecap), o_en = take(4 * (size_t)T.ecap),
+                 o_stack = take(2 * (size_t)scap), o_an = take(4 * (size_t)alncap), o_ap = take(4 * (size_t)alncap),
+                 o_sr = take(2 * (size_t)ncap), o_ss = take(2 * (size_t)ncap), o_sl = take(2 * (size_t)ncap), o_H = take(2 * T.hcap);
+    const size_t per_warp = round_up(o, 256);
+    CK(T.mem.ensure(per_warp * T.warps));
+    CK(T.desc.ensure(sizeof(CgPoaScratch) * T.warps));
+    std::vector<CgPoaScratch> d(T.warps);
+    for (u32 i = 0; i < T.warps; ++i) {
+        u8* b = T.mem.as<u8>() + per_warp * i;
+        CgPoaScratch& s = d[i];
+        s.vcap = T.vcap; s.ecap = T.ecap; s.scap = scap; s.alncap = alncap; s.ncap = ncap; s.hcap = T.hcap;
+        s.letter = b + o_letter; s.in0 = b + o_in0; s.nal = b + o_nal; s.leader = b + o_leader; s.marks = b + o_marks; s.check = b + o_check;
+        s.nseq = (u16*)(b + o_nseq); s.aligned = (u16*)(b + o_aligned); s.rank_of = (u16*)(b + o_rank); s.r2n = (u16*)(b + o_r2n);
+        s.in_head = (u32*)(b + o_ih); s.in_tail = (u32*)(b + o_it); s.e_pred = (u16*)(b + o_ep); s.e_next = (u32*)(b + o_en);
+        s.stack = (u16*)(b + o_stack); s.aln_node = (i32*)(b + o_an); s.aln_pos = (i32*)(b + o_ap);
+        s.seg_read = (u16*)(b + o_sr); s.seg_start = (u16*)(b + o_ss); s.seg_len = (u16*)(b + o_sl); s.H = (i16*)(b + o_H);
+    }
+    CK(cudaMemcpyAsync(T.desc.p, d.data(), sizeof(CgPoaScratch) * T.warps, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    T.ready = true;
+    return CG_OK;
+}
+
+// One timed stage = a pair of events on the stream; collected after the final sync of cg_run.
+struct StageSpan { int stage; cudaEvent_t a, b; };
+
+int run_chunk(cg_handle* h, const ChunkPlan& cp, std::vector<StageSpan>& spans, std::vector<cudaEvent_t>& pool, size_t& pool_at) {
+    cudaStream_t st = h->stream;
+    const u32 nwin = cp.nwin;
+    auto ev = [&]() -> cudaEvent_t {
+        if (pool_at == pool.size()) { cudaEvent_t e; cudaEventCreate(&e); pool.push_back(e); }
+        return pool[pool_at++];
+    };
+    auto span_begin = [&](int stage) { StageSpan s{stage, ev(), ev()}; cudaEventRecord(s.a, st); spans.push_back(s); };
+    auto span_end = [&]() { cudaEventRecord(spans.back().b, st); };
+
+    // ---- workspaces
+    CK(h->pwords.ensure((cp.nwords + 16) * 4)); CK(h->ptags.ensure((cp.nwords + 16) * 4));
+    CK(h->win.ensure(sizeof(CgWin) * nwin));
+    CK(h->offs.ensure(sizeof(u64) * 5 * (nwin + 1)));
+    CK(h->solid_k.ensure(cp.solid_tot * 4 + 16)); CK(h->solid_c.ensure(cp.solid_tot * 4 + 16));
+    CK(h->slot_tpos.ensure(cp.slot_tot * 2 + 16)); CK(h->slot_kmer.ensure(cp.slot_tot * 4 + 16));
+    CK(h->anchors.ensure(cp.slot_tot * 2 + 16)); CK(h->chain.ensure(cp.slot_tot * 2 + 16)); CK(h->rel.ensure(cp.slot_tot * 4 + 16));
+    CK(h->pos.ensure(cp.pos_tot * 2 + 16));
+    CK(h->regions.ensure(cp.reg_tot * sizeof(CgRegion) + 16));
+    CK(h->arena.ensure(cp.arena_tot + 16));
+    CK(h->visited.ensure((cp.solid_tot / 32 + nwin + 2) * 4));
+    CK(h->jobs.ensure(cp.reg_tot * sizeof(uint2) + 16)); CK(h->jobs_next.ensure(cp.reg_tot * sizeof(uint2) + 16));
+    CK(h->off_fin.ensure(sizeof(u64) * (nwin + 1)));
+    CK(h->out_off.ensure(sizeof(u64) * 2 * (nwin + 1)));
+
+    CgChunk c{};
+    c.bases = h->d_bases.as<char>(); c.seq_off = h->d_seq_off.as<u64>(); c.win_seq_begin = h->d_wsb.as<u32>();
+    c.w0 = cp.w0; c.nwin = nwin;
+    c.k = h->p.mer_size; c.solid = h->p.solid_thresh; c.common = h->p.common_kmers; c.min_anchors = h->p.min_anchors;
+    c.pwords = h->pwords.as<u32>(); c.ptags = h->ptags.as<u32>(); c.pword_base = cp.pword_base;
+    c.win = h->win.as<CgWin>();
+    u64* offs = h->offs.as<u64>();
+    c.off_solid = offs; c.off_slot = offs + (nwin + 1); c.off_pos = offs + 2 * (nwin + 1); c.off_reg = offs + 3 * (nwin + 1);
+    c.off_arena = offs + 4 * (nwin + 1);
+    c.solid_k = h->solid_k.as<u32>(); c.solid_c = h->solid_c.as<u32>();
+    c.slot_tpos = h->slot_tpos.as<u16>(); c.slot_kmer = h->slot_kmer.as<u32>(); c.anchors = h->anchors.as<u16>();
+    c.chain = h->chain.as<u16>(); c.rel = h->rel.as<u32>(); c.pos = h->pos.as<u16>();
+    c.regions = h->regions.as<CgRegion>(); c.arena = h->arena.as<u8>(); c.fin = nullptr; c.visited = h->visited.as<u32>();
+    u32* ctl = h->ctl.as<u32>();
+    c.job_count = ctl + CTL_Q0; c.jobs = h->jobs.as<uint2>(); c.jobs_next = h->jobs_next.as<uint2>();
+    c.flags = ctl + CTL_FLAGS;
+    c.counters = (CgCountersDev*)(ctl + CTL_WORDS);
+    u64* off_fin = h->off_fin.as<u64>();
+    u64* cons_off = h->out_off.as<u64>();
+    u64* solid_off = cons_off + (nwin + 1);
+
+    // ---- stage 0: plan, offsets, pack
+    span_begin(CG_STAGE_PACK);
+    CK(cudaMemsetAsync(ctl + CTL_Q0, 0, 12 * sizeof(u32), st));
+    CK(cudaMemsetAsync(h->pwords.as<u32>() + cp.nwords, 0, 16 * 4, st));
+    CK(cudaMemsetAsync(h->ptags.as<u32>() + cp.nwords, 0xff, 16 * 4, st));
+    CG_LAUNCH(k_plan, (nwin + 127) / 128, 128, 0, st, c);
+    CG_LAUNCH(k_scan, 5, 1024, 1024 * sizeof(u64), st, c.off_solid, c.off_slot, c.off_pos, c.off_reg, c.off_arena, nwin);
+    CG_LAUNCH(k_pack, nwin, 256, 0, st, c);
+    h->stage_launches[CG_STAGE_PACK] += 3;
+    span_end();
+
+    span_begin(CG_STAGE_INDEX);
+    CG_LAUNCH(k_index, nwin, CG_IDX_THREADS, CG_IDX_SMEM_BYTES, st, c);
+    h->stage_launches[CG_STAGE_INDEX] += 1;
+    span_end();
+
+    span_begin(CG_STAGE_CHAIN);
+    size_t chain_smem = cg_chain_smem(cp.max_tk, cp.max_n);
+    const size_t smem_cap = (size_t)h->smem_optin;
+    if (chain_smem > smem_cap) chain_smem = smem_cap;      // windows that really need more are flagged by the kernel
+    CG_LAUNCH(k_chain, nwin, CG_CHAIN_THREADS, chain_smem, st, c, (u32)chain_smem);
+    h->stage_launches[CG_STAGE_CHAIN] += 1;
+    span_end();
+
+    span_begin(CG_STAGE_SPLIT);
+    CG_LAUNCH(k_split, nwin, CG_SPLIT_THREADS, 0, st, c);
+    h->stage_launches[CG_STAGE_SPLIT] += 1;
+    span_end();
+
+    span_begin(CG_STAGE_POA);
+    { int rc = ensure_tier(h, 0); if (rc) return rc; }
+    CG_LAUNCH(k_poa, h->tier[0].warps / CG_POA_WARPS_PER_CTA, CG_POA_THREADS, 0, st, c, h->tier[0].desc.as<CgPoaScratch>(),
+              (const uint2*)c.jobs, ctl + CTL_Q0, c.jobs_next);
+    h->stage_launches[CG_STAGE_POA] += 1;
+    span_end();
+
+    // overflow tiers: need the count on the host
+    CK(cudaMemcpyAsync(h->h_ctl, ctl, CTL_WORDS * sizeof(u32), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    uint2* q_in = c.jobs_next; uint2* q_out = c.jobs;
+    for (int t = 1; t <= 2; ++t) {
+        const u32 over = h->h_ctl[CTL_Q0 + 4 * (t - 1) + 2];
+        if (!over) break;
+        if (h->tier[t].warps == 0) { h->err = "a POA job outgrew the largest enabled scratch tier"; return CG_ERR_CAPACITY; }
+        { int rc = ensure_tier(h, t); if (rc) return rc; }
+        u32 q[4] = {over, 0, 0, 0};
+        CK(cudaMemcpyAsync(ctl + CTL_Q0 + 4 * t, q, sizeof q, cudaMemcpyHostToDevice, st));
+        span_begin(CG_STAGE_POA);
+        CG_LAUNCH(k_poa, (h->tier[t].warps + CG_POA_WARPS_PER_CTA - 1) / CG_POA_WARPS_PER_CTA, CG_POA_THREADS, 0, st, c,
+                  h->tier[t].desc.as<CgPoaScratch>(), (const uint2*)q_in, ctl + CTL_Q0 + 4 * t, t < 2 ? q_out : (uint2*)nullptr);
+        h->stage_launches[CG_STAGE_POA] += 1;
+        span_end();
+        CK(cudaMemcpyAsync(h->h_ctl, ctl, CTL_WORDS * sizeof(u32), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        std::swap(q_in, q_out);
+    }
+
+    // ---- stitched lengths -> work slices
+    span_begin(CG_STAGE_STITCH);
+    CG_LAUNCH(k_stitch_len, (nwin + 127) / 128, 128, 0, st, c, off_fin);
+    CG_LAUNCH(k_scan, 1, 1024, 1024 * sizeof(u64), st, off_fin, (u64*)nullptr, (u64*)nullptr, (u64*)nullptr, (u64*)nullptr, nwin);
+    h->stage_launches[CG_STAGE_STITCH] += 2;
+    span_end();
+    u64 fin_total = 0;
+    CK(cudaMemcpyAsync(&fin_total, off_fin + nwin, sizeof(u64), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(h->fin.ensure(fin_total + 16));
+    c.fin = h->fin.as<u8>();
+
+    span_begin(CG_STAGE_POLISH);
+    CG_LAUNCH(k_polish, (nwin + CG_POLISH_WARPS_PER_CTA - 1) / CG_POLISH_WARPS_PER_CTA, CG_POLISH_THREADS, 0, st, c, (const u64*)off_fin);
+    h->stage_launches[CG_STAGE_POLISH] += 1;
+    span_end();
+
+    span_begin(CG_STAGE_STITCH);
+    CG_LAUNCH(k_out_sizes, (nwin + 127) / 128, 128, 0, st, c, cons_off, solid_off);
+    CG_LAUNCH(k_scan, 2, 1024, 1024 * sizeof(u64), st, cons_off, solid_off, (u64*)nullptr, (u64*)nullptr, (u64*)nullptr, nwin);
+    h->stage_launches[CG_STAGE_STITCH] += 2;
+    span_end();
+    u64 tot[2] = {0, 0};
+    CK(cudaMemcpyAsync(&tot[0], cons_off + nwin, sizeof(u64), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&tot[1], solid_off + nwin, sizeof(u64), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h->h_ctl, ctl, CTL_WORDS * sizeof(u32), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (h->h_ctl[CTL_FLAGS] & CG_FLAG_BAD_BASE) { h->err = "a base outside {A,C,G,T} in the batch"; return CG_ERR_BAD_BASE; }
+    if (h->h_ctl[CTL_FLAGS] & CG_FLAG_CAPACITY) { h->err = "a per-window capacity limit of this build was exceeded"; return CG_ERR_CAPACITY; }
+    if (h->h_ctl[CTL_FLAGS] & CG_FLAG_INTERNAL) { h->err = "internal invariant violated (anchor pair without common read)"; return CG_ERR_CUDA; }
+    CK(h->o_cons.ensure(h->o_cons_n + tot[0] + 16, true, st));
+    CK(h->o_sk.ensure((h->o_solid_n + tot[1]) * 4 + 16, true, st));
+    CK(h->o_sc.ensure((h->o_solid_n + tot[1]) * 4 + 16, true, st));
+
+    span_begin(CG_STAGE_STITCH);
+    CG_LAUNCH(k_gather, nwin, 256, 0, st, c, (const u64*)off_fin, (const u64*)cons_off, (const u64*)solid_off,
+              h->o_cons.as<u8>() + h->o_cons_n, h->o_sk.as<u32>() + h->o_solid_n, h->o_sc.as<u32>() + h->o_solid_n,
+              h->o_status.as<u8>() + cp.w0, h->o_cons_n, h->o_solid_n, h->o_len.as<u64>() + cp.w0, h->o_nsol.as<u64>() + cp.w0);
+    h->stage_launches[CG_STAGE_STITCH] += 1;
+    span_end();
+    h->o_cons_n += tot[0];
+    h->o_solid_n += tot[1];
+    return CG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cg_abi_version(void) { return CG_ABI_VERSION; }
+
+int cg_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+const char* cg_last_error(const cg_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+int cg_create(int device, const cg_params* params, cg_handle** out) {
+    if (!params || !out) { g_create_err = "null argument"; return CG_ERR_INVALID_ARG; }
+    *out = nullptr;
+    if (params->mer_size < 2 || params->mer_size > 15 || params->solid_thresh < 1) { g_create_err = "mer_size must be 2..15, solid_thresh >= 1"; return CG_ERR_INVALID_ARG; }
+    if (params->mer_size > CG_KMAX) { g_create_err = "mer_size > 9 is not supported by this build (direct-addressed k-mer table)"; return CG_ERR_CAPACITY; }
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) {
+        g_create_err = "no usable CUDA device (this library has no CPU path)";
+        return CG_ERR_NO_DEVICE;
+    }
+    cg_handle* h = new cg_handle();
+    h->device = device; h->p = *params;
+    if (cudaSetDevice(device) != cudaSuccess) { g_create_err = "cudaSetDevice failed"; delete h; return CG_ERR_NO_DEVICE; }
+    cudaDeviceGetAttribute(&h->sms, cudaDevAttrMultiProcessorCount, device);
+    cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    if ((size_t)h->smem_optin < CG_IDX_SMEM_BYTES) {
+        g_create_err = "device has too little shared memory per block for k_index (needs sm_100-class 227 KB)";
+        delete h; return CG_ERR_NO_DEVICE;
+    }
+    bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaMallocHost(&h->h_ctl, 64 * sizeof(u32)) == cudaSuccess;
+    ok = ok && h->ctl.ensure(CTL_WORDS * sizeof(u32) + sizeof(CgCountersDev)) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_index, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CG_IDX_SMEM_BYTES) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin) == cudaSuccess;
+    if (!ok) { g_create_err = std::string("CUDA initialisation failed: ") + cudaGetErrorString(cudaGetLastError()); cg_destroy(h); return CG_ERR_CUDA; }
+    // POA scratch tiers: {nodes, edges, max segment length, score-matrix cells, resident warps}
+    h->tier[0].vcap = 2048;  h->tier[0].ecap = 8192;   h->tier[0].lcap = CG_LEN_MAX; h->tier[0].hcap = 256u << 10;
+    h->tier[1].vcap = 16384; h->tier[1].ecap = 65536;  h->tier[1].lcap = CG_LEN_MAX; h->tier[1].hcap = 16u << 20;
+    h->tier[2].vcap = 65535; h->tier[2].ecap = 262144; h->tier[2].lcap = CG_LEN_MAX; h->tier[2].hcap = 256u << 20;
+    h->tier[0].warps = (u32)h->sms * h->poa_warps_per_sm[0];
+    h->tier[1].warps = (u32)h->sms * h->poa_warps_per_sm[1];
+    h->tier[2].warps = 8;
+    *out = h;
+    return CG_OK;
+}
+
+void cg_destroy(cg_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    DevBuf* bufs[] = {&h->d_bases, &h->d_seq_off, &h->d_wsb, &h->pwords, &h->ptags, &h->win, &h->offs, &h->solid_k, &h->solid_c, &h->slot_tpos,
+                      &h->slot_kmer, &h->anchors, &h->chain, &h->rel, &h->pos, &h->regions, &h->arena, &h->fin, &h->visited, &h->jobs,
+                      &h->jobs_next, &h->ctl, &h->off_fin, &h->out_off, &h->o_cons, &h->o_sk, &h->o_sc, &h->o_status, &h->o_len, &h->o_nsol};
+    for (DevBuf* b : bufs) b->release();
+    for (auto& t : h->tier) { t.mem.release(); t.desc.release(); }
+    if (h->h_ctl) cudaFreeHost(h->h_ctl);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int cg_set_option(cg_handle* h, const char* key, long long value) {
+    if (!h || !key) return CG_ERR_INVALID_ARG;
+    const std::string k(key);
+    if (k == "chunk_budget_bytes") h->chunk_budget = (size_t)value;
+    else if (k == "chunk_max_windows") h->chunk_max_windows = (u32)std::max<long long>(1, value);
+    else if (k == "poa_tier0_warps") { h->tier[0].warps = (u32)value / CG_POA_WARPS_PER_CTA * CG_POA_WARPS_PER_CTA; h->tier[0].ready = false; }
+    else if (k == "poa_tier1_warps") { h->tier[1].warps = (u32)value; h->tier[1].ready = false; }
+    else if (k == "poa_tier2_warps") { h->tier[2].warps = (u32)value; h->tier[2].ready = false; }
+    else if (k == "poa_tier0_nodes") { h->tier[0].vcap = (u32)value; h->tier[0].ecap = 4 * (u32)value; h->tier[0].ready = false; }
+    else if (k == "poa_tier0_cells") { h->tier[0].hcap = (u64)value; h->tier[0].ready = false; }
+    else if (k == "poa_tier1_nodes") { h->tier[1].vcap = (u32)value; h->tier[1].ecap = 4 * (u32)value; h->tier[1].ready = false; }
+    else if (k == "poa_tier1_cells") { h->tier[1].hcap = (u64)value; h->tier[1].ready = false; }
+    else if (k == "poa_tier2_nodes") { h->tier[2].vcap = (u32)std::min<long long>(value, 65535); h->tier[2].ecap = 4 * h->tier[2].vcap; h->tier[2].ready = false; }
+    else if (k == "poa_tier2_cells") { h->tier[2].hcap = (u64)value; h->tier[2].ready = false; }
+    else { h->err = "unknown option " + k; return CG_ERR_INVALID_ARG; }
+    if (h->uploaded) plan_chunks(h);
+    return CG_OK;
+}
+
+int cg_upload(cg_handle* h, const cg_batch* in) {
+    if (!h) return CG_ERR_INVALID_ARG;
+    if (!in || !in->win_seq_begin || !in->seq_off || (!in->bases && in->n_windows)) { h->err = "null batch pointer"; return CG_ERR_INVALID_ARG; }
+    cudaSetDevice(h->device);
+    h->uploaded = h->ran = false;
+    const u32 W = in->n_windows;
+    const u64 n_seqs = in->win_seq_begin[W];
+    if (in->win_seq_begin[0] != 0) { h->err = "win_seq_begin[0] must be 0"; return CG_ERR_INVALID_ARG; }
+    for (u32 w = 0; w < W; ++w) {
+        if (in->win_seq_begin[w + 1] <= in->win_seq_begin[w]) { h->err = "empty pile (window without a template)"; return CG_ERR_INVALID_ARG; }
+        if (in->win_seq_begin[w + 1] - in->win_seq_begin[w] > CG_N_MAX) { h->err = "more than 4095 sequences in one window"; return CG_ERR_CAPACITY; }
+    }
+    const u32 k = h->p.mer_size;
+    for (u64 s = 0; s < n_seqs; ++s) {
+        if (in->seq_off[s + 1] < in->seq_off[s]) { h->err = "seq_off must be non-decreasing"; return CG_ERR_INVALID_ARG; }
+        if (in->seq_off[s + 1] - in->seq_off[s] > CG_LEN_MAX) { h->err = "a sequence is longer than 6000 bases"; return CG_ERR_CAPACITY; }
+    }
+    for (u32 w = 0; w < W; ++w) {
+        const u32 s0 = in->win_seq_begin[w];
+        const u64 tlen = in->seq_off[s0 + 1] - in->seq_off[s0];
+        if (tlen >= k && tlen - k + 1 > CG_TK_MAX) { h->err = "template longer than 2047 k-mers"; return CG_ERR_CAPACITY; }
+    }
+    const u64 n_bases = n_seqs ? in->seq_off[n_seqs] : 0;
+    h->W = W; h->n_seqs = n_seqs; h->n_bases = n_bases;
+    h->h_wsb.assign(in->win_seq_begin, in->win_seq_begin + W + 1);
+    h->h_seq_off.assign(in->seq_off, in->seq_off + n_seqs + 1);
+    CK(h->d_bases.ensure(n_bases + 64));
+    CK(h->d_seq_off.ensure((n_seqs + 1) * sizeof(u64)));
+    CK(h->d_wsb.ensure((W + 1) * sizeof(u32)));
+    if (n_bases) CK(cudaMemcpyAsync(h->d_bases.p, in->bases, n_bases, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_seq_off.p, in->seq_off, (n_seqs + 1) * sizeof(u64), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_wsb.p, in->win_seq_begin, (W + 1) * sizeof(u32), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    plan_chunks(h);
+    h->uploaded = true;
+    return CG_OK;
+}
+
+int cg_run(cg_handle* h) {
+    if (!h) return CG_ERR_INVALID_ARG;
+    if (!h->uploaded) { h->err = "cg_run before cg_upload"; return CG_ERR_STATE; }
+    cudaSetDevice(h->device);
+    h->ran = false;
+    h->o_cons_n = h->o_solid_n = 0;
+    memset(h->stage_ms, 0, sizeof h->stage_ms);
+    memset(h->stage_launches, 0, sizeof h->stage_launches);
+    CK(h->o_status.ensure(h->W + 16)); CK(h->o_len.ensure((h->W + 1) * sizeof(u64))); CK(h->o_nsol.ensure((h->W + 1) * sizeof(u64)));
+    CK(cudaMemsetAsync(h->ctl.p, 0, CTL_WORDS * sizeof(u32) + sizeof(CgCountersDev), h->stream));
+    std::vector<StageSpan> spans;
+    static thread_local std::vector<cudaEvent_t> pool;
+    size_t pool_at = 0;
+    for (const ChunkPlan& cp : h->chunks) {
+        int rc = run_chunk(h, cp, spans, pool, pool_at);
+        if (rc != CG_OK) { cudaStreamSynchronize(h->stream); return rc; }
+    }
+    CgCountersDev cd{};
+    CK(cudaMemcpyAsync(&cd, h->ctl.as<u32>() + CTL_WORDS, sizeof cd, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (const StageSpan& s : spans) { float ms = 0; cudaEventElapsedTime(&ms, s.a, s.b); h->stage_ms[s.stage] += ms; }
+    cg_counters& o = h->counters;
+    o.windows = h->W; o.sequences = h->n_seqs; o.bases = h->n_bases;
+    o.anchors = cd.anchors; o.regions = cd.regions; o.poa_graphs = cd.poa_graphs; o.alignments = cd.alignments;
+    o.dp_cells = cd.dp_cells; o.dp_pred_cells = cd.dp_pred_cells; o.solid_kmers = cd.solid_kmers;
+    o.consensus_bytes = cd.consensus_bytes; o.fallback_windows = cd.fallback_windows;
+    h->ran = true;
+    return CG_OK;
+}
+
+namespace {
+struct ResultOwner { std::vector<u64> cons_off, solid_off; std::vector<char> cons; std::vector<u8> status; std::vector<u32> sk, sc; };
+}
+
+int cg_download(cg_handle* h, cg_results* out) {
+    if (!h || !out) return CG_ERR_INVALID_ARG;
+    if (!h->ran) { h->err = "cg_download before a successful cg_run"; return CG_ERR_STATE; }
+    cudaSetDevice(h->device);
+    ResultOwner* ow = new ResultOwner();
+    const u32 W = h->W;
+    ow->cons_off.resize(W + 1); ow->solid_off.resize(W + 1); ow->status.resize(W ? W : 1);
+    ow->cons.resize(h->o_cons_n ? h->o_cons_n : 1); ow->sk.resize(h->o_solid_n ? h->o_solid_n : 1); ow->sc.resize(h->o_solid_n ? h->o_solid_n : 1);
+    cudaError_t e = cudaSuccess;
+    if (W) {
+        e = cudaMemcpyAsync(ow->cons_off.data(), h->o_len.p, W * sizeof(u64), cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(ow->solid_off.data(), h->o_nsol.p, W * sizeof(u64), cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(ow->status.data(), h->o_status.p, W, cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess && h->o_cons_n) e = cudaMemcpyAsync(ow->cons.data(), h->o_cons.p, h->o_cons_n, cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess && h->o_solid_n) e = cudaMemcpyAsync(ow->sk.data(), h->o_sk.p, h->o_solid_n * 4, cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess && h->o_solid_n) e = cudaMemcpyAsync(ow->sc.data(), h->o_sc.p, h->o_solid_n * 4, cudaMemcpyDeviceToHost, h->stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) { h->err = std::string("download: ") + cudaGetErrorString(e); delete ow; return CG_ERR_CUDA; }
+    ow->cons_off[W] = h->o_cons_n; ow->solid_off[W] = h->o_solid_n;
+    out->n_windows = W; out->cons_off = ow->cons_off.data(); out->cons = ow->cons.data(); out->status = ow->status.data();
+    out->solid_off = ow->solid_off.data(); out->solid_kmer = ow->sk.data(); out->solid_count = ow->sc.data(); out->owner_ = ow;
+    return CG_OK;
+}
+
+void cg_free_results(cg_results* r) {
+    if (r && r->owner_) { delete static_cast<ResultOwner*>(r->owner_); r->owner_ = nullptr; }
+}
+
+int cg_correct_windows(cg_handle* h, const cg_batch* in, cg_results* out) {
+    int rc = cg_upload(h, in);
+    if (rc == CG_OK) rc = cg_run(h);
+    if (rc == CG_OK) rc = cg_download(h, out);
+    return rc;
+}
+
+int cg_stage_ms(const cg_handle* h, float ms[CG_N_STAGES], uint32_t launches[CG_N_STAGES]) {
+    if (!h) return CG_ERR_INVALID_ARG;
+    for (int i = 0; i < CG_N_STAGES; ++i) { if (ms) ms[i] = h->stage_ms[i]; if (launches) launches[i] = h->stage_launches[i]; }
+    return CG_OK;
+}
+
+int cg_get_counters(const cg_handle* h, cg_counters* out) {
+    if (!h || !out) return CG_ERR_INVALID_ARG;
+    *out = h->counters;
+    return CG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,246 @@
+// k_index.cuh — k-mer index of one pile: solid k-mer list, template anchor candidates, position table.
+//
+// Replaces fill_index_kmers (BMEAN/bmean.cpp:43-84), filter_index_kmers (:88-114), get_template (:220-234).
+//
+// The reference keeps a hash map kmer -> vector<(read,pos)> of all ~N*(L-k+1) occurrences.  Only two things
+// are ever read from it: (1) merCounts = total occurrences of k-mers seen >= solid times (:72-76) and
+// (2) the location lists of k-mers that occur in the template, are never repeated inside one read (:58-60,
+// 66-68, 78-82) and are present in >= S reads (:101).  So this kernel
+//   - counts all k-mers of the pile in a direct-addressed shared-memory table, 2^15 keys per pass
+//     (8 passes for k=9); after each pass the solid entries are compacted *in key order* (the sorted list
+//     the ABI returns) and the counts of the template's k-mers are picked up;
+//   - keeps template positions with S <= count <= N (necessary for "alive"), gives each a slot, and in one
+//     more sweep over the pile records pos[read][slot] = position + 1;
+//   - a slot is alive iff (#reads holding it) == count, i.e. no read holds it twice.
+//
+// One CTA (512 threads) per window.  The 2-bit pile (words + tags, <= 72 KB) is bulk-copied HBM -> shared
+// memory by the TMA engine (cp.async.bulk + mbarrier); bigger piles are read through L1/L2.
+#pragma once
+#include "cg_common.cuh"
+
+#define CG_IDX_THREADS 512u
+#define CG_IDX_SMEM_BYTES (131072u + 8u * CG_PW_CAP + 2u * 2048u * 4u + 64u * 4u + 16u)
+
+#ifndef CG_EMU
+__device__ __forceinline__ u32 cg_smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+#endif
+
+__global__ void __launch_bounds__(CG_IDX_THREADS, 1) k_index(CgChunk c) {
+    CG_DYN_SMEM(smem);
+    u32* tab = (u32*)smem;
+    u32* pile_s = tab + 32768;
+    u32* tags_s = pile_s + CG_PW_CAP;
+    u32* tkmer = tags_s + CG_PW_CAP;
+    u32* tcount = tkmer + 2048;
+    u32* misc = tcount + 2048;
+
+    const u32 w = blockIdx.x, tid = threadIdx.x, lane = cg_lane(), warp = cg_warp();
+    const u32 T = CG_IDX_THREADS, NWARPS = CG_IDX_THREADS / 32;
+    const CgWin W = c.win[w];
+    const u32 k = c.k, N = W.n_seqs, tk = W.tk, S = W.S;
+
+    const u64 g0 = cg_pword(c.seq_off, W.seq_begin) - c.pword_base;
+    const u32 nw = (u32)(cg_pword(c.seq_off, W.seq_begin + N) - c.pword_base - g0);
+
+    // ---- stage the 2-bit pile in shared memory (TMA bulk copy), if it fits
+    const u32* pw;
+    const u32* pt;
+    {
+        const u64 ga = g0 & ~3ull;                    // 16-byte aligned source
+        const u32 shift = (u32)(g0 - ga);
+        const u32 ncopy = (shift + nw + 1 + 3) & ~3u; // + the look-ahead word; multiple of 16 bytes
+        if (ncopy <= CG_PW_CAP) {
+#ifndef CG_EMU
+            u64* bar = (u64*)(misc + 64);
+            const u32 bar_a = cg_smem_addr(bar);
+            if (tid == 0) {
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            }
+            __syncthreads();
+            if (tid == 0) {
+                const u32 bytes = ncopy * 4u;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(2u * bytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(cg_smem_addr(pile_s)), "l"(c.pwords + ga), "r"(bytes), "r"(bar_a) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(cg_smem_addr(tags_s)), "l"(c.ptags + ga), "r"(bytes), "r"(bar_a) : "memory");
+            }
+            asm volatile(
+                "{\n"
+                ".reg .pred p;\n"
+                "CG_WAIT:\n"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+                "@p bra CG_DONE;\n"
+                "bra CG_WAIT;\n"
+                "CG_DONE:\n"
+                "}\n" ::"r"(bar_a) : "memory");
+#else
+            for (u32 i = tid; i < ncopy; i += T) { pile_s[i] = c.pwords[ga + i]; tags_s[i] = c.ptags[ga + i]; }
+            __syncthreads();
+#endif
+            pw = pile_s + shift;
+            pt = tags_s + shift;
+        } else {
+            pw = c.pwords + g0;
+            pt = c.ptags + g0;
+        }
+    }
+
+    // ---- template k-mers (read 0 starts at word 0 of the pile)
+    for (u32 p = tid; p < tk; p += T) {
+        tkmer[p] = cg_kmer_at(pw[p >> 4], pw[(p >> 4) + 1], p & 15u, k);
+        tcount[p] = 0;
+    }
+
+    // ---- counting passes
+    const u32 tab_bits = 2 * k < CG_TAB_BITS ? 2 * k : CG_TAB_BITS;
+    const u32 tab_n = 1u << tab_bits, tab_mask = tab_n - 1;
+    const u32 npass = 1u << (2 * k - tab_bits);
+    const u64 solid_base = c.off_solid[w];
+    u32 nsolid = 0;
+    u32 per_warp = ((tab_n + NWARPS - 1) / NWARPS + 31u) & ~31u;
+    const u32 wb = warp * per_warp < tab_n ? warp * per_warp : tab_n;
+    const u32 we = wb + per_warp < tab_n ? wb + per_warp : tab_n;
+
+    for (u32 pass = 0; pass < npass; ++pass) {
+        for (u32 i = tid; i < tab_n; i += T) tab[i] = 0;
+        __syncthreads();
+        for (u32 g = tid; g < nw; g += T) {
+            const u32 tag = pt[g];
+            if (tag == CG_NONE32) continue;
+            const u32 nv = (tag & 15u) + 1;
+            const u32 w0 = pw[g], w1 = pw[g + 1];
+#pragma unroll
+            for (u32 b = 0; b < 16; ++b) {
+                if (b < nv) {
+                    const u32 km = cg_kmer_at(w0, w1, b, k);
+                    if ((km >> tab_bits) == pass) atomicAdd(&tab[km & tab_mask], 1u);
+                }
+            }
+        }
+        __syncthreads();
+        for (u32 p = tid; p < tk; p += T) {
+            const u32 km = tkmer[p];
+            if ((km >> tab_bits) == pass) tcount[p] = tab[km & tab_mask];
+        }
+        // solid entries of this pass, in key order: count per warp range, scan, write
+        u32 wc = 0;
+        for (u32 b = wb; b < we; b += 32) {
+            const u32 i = b + lane;
+            const bool f = i < we && tab[i] >= c.solid;
+            wc += __popc(__ballot_sync(CG_FULL, f));
+        }
+        if (lane == 0) misc[warp] = wc;
+        __syncthreads();
+        u32 woff = 0, total = 0;
+        for (u32 i = 0; i < NWARPS; ++i) { const u32 v = misc[i]; if (i < warp) woff += v; total += v; }
+        u64 run = solid_base + nsolid + woff;
+        for (u32 b = wb; b < we; b += 32) {
+            const u32 i = b + lane;
+            const u32 cnt = i < we ? tab[i] : 0;
+            const bool f = i < we && cnt >= c.solid;
+            const u32 m = __ballot_sync(CG_FULL, f);
+            if (f) {
+                const u64 idx = run + __popc(m & ((1u << lane) - 1u));
+                c.solid_k[idx] = (pass << tab_bits) | i;
+                c.solid_c[idx] = cnt;
+            }
+            run += __popc(m);
+        }
+        nsolid += total;
+        __syncthreads();
+    }
+
+    // ---- candidate anchors: template positions with S <= count <= N, slots in template order
+    u32* bitmap = tab;                      // 4^k bits
+    u32* hkey = tab + 8192;                 // 4096 keys
+    u16* hval = (u16*)(tab + 12288);        // 4096 slots
+    u32* scnt = tab + 14336;                // count by slot
+    const u32 bm_words = (1u << (2 * k)) >= 32 ? (1u << (2 * k)) / 32 : 1;
+    for (u32 i = tid; i < bm_words; i += T) bitmap[i] = 0;
+    for (u32 i = tid; i < 4096; i += T) hkey[i] = CG_NONE32;
+    const u64 slot_base = c.off_slot[w];
+    u32 flags4 = 0, nloc = 0;
+#pragma unroll
+    for (u32 q = 0; q < 4; ++q) {
+        const u32 p = tid * 4 + q;
+        if (p < tk) {
+            const u32 cnt = tcount[p];
+            if (cnt >= S && cnt <= N) { flags4 |= 1u << q; ++nloc; }
+        }
+    }
+    u32 C = 0;
+    u32 slot = cg_block_scan(nloc, misc, &C);
+#pragma unroll
+    for (u32 q = 0; q < 4; ++q) {
+        if (flags4 & (1u << q)) {
+            const u32 p = tid * 4 + q, km = tkmer[p];
+            scnt[slot] = tcount[p];
+            c.slot_tpos[slot_base + slot] = (u16)p;
+            c.slot_kmer[slot_base + slot] = km;
+            atomicOr(&bitmap[km >> 5], 1u << (km & 31u));
+            u32 h = (km * 2654435761u) >> 20;
+            for (;;) {
+                const u32 old = atomicCAS(&hkey[h], CG_NONE32, km);
+                if (old == CG_NONE32 || old == km) { hval[h] = (u16)slot; break; }
+                h = (h + 1) & 4095u;
+            }
+            ++slot;
+        }
+    }
+    // zero the position table [N][C]
+    u16* pos = c.pos + c.off_pos[w];
+    {
+        u32* p32 = (u32*)pos;
+        const u32 n32 = (u32)(((u64)C * N + 1) / 2);
+        for (u32 i = tid; i < n32; i += T) p32[i] = 0;
+    }
+    __syncthreads();
+
+    // ---- positions of the candidate k-mers in every read
+    if (C) {
+        for (u32 g = tid; g < nw; g += T) {
+            const u32 tag = pt[g];
+            if (tag == CG_NONE32) continue;
+            const u32 nv = (tag & 15u) + 1, r = tag >> 16, wi = (tag >> 4) & 0xfffu;
+            const u32 w0 = pw[g], w1 = pw[g + 1];
+            for (u32 b = 0; b < nv; ++b) {
+                const u32 km = cg_kmer_at(w0, w1, b, k);
+                if (!((bitmap[km >> 5] >> (km & 31u)) & 1u)) continue;
+                u32 h = (km * 2654435761u) >> 20;
+                while (hkey[h] != km) h = (h + 1) & 4095u;
+                pos[(size_t)r * C + hval[h]] = (u16)(16 * wi + b + 1);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- alive <=> every occurrence is in a different read; anchors = alive slots in template order
+    u32* filled = tab + 16384;              // reads holding the slot
+    for (u32 i = tid; i < C; i += T) filled[i] = 0;
+    __syncthreads();
+    for (u32 r = warp; r < N; r += NWARPS) {
+        const u16* prow = pos + (size_t)r * C;
+        for (u32 sb = 0; sb < C; sb += 32) {
+            const u32 s = sb + lane;
+            if (s < C && prow[s] != 0) atomicAdd(&filled[s], 1u);
+        }
+    }
+    __syncthreads();
+    flags4 = 0; nloc = 0;
+#pragma unroll
+    for (u32 q = 0; q < 4; ++q) {
+        const u32 s = tid * 4 + q;
+        if (s < C && filled[s] == scnt[s]) { flags4 |= 1u << q; ++nloc; }
+    }
+    u32 A = 0;
+    u32 a = cg_block_scan(nloc, misc, &A);
+#pragma unroll
+    for (u32 q = 0; q < 4; ++q)
+        if (flags4 & (1u << q)) c.anchors[slot_base + a++] = (u16)(tid * 4 + q);
+    if (tid == 0) {
+        CgWin* Wg = &c.win[w];
+        Wg->n_solid = nsolid; Wg->n_cand = C; Wg->n_alive = A;
+    }
+}

@@ -1,0 +1,387 @@
+// k_poa.cuh — segmented partial-order alignment + column vote, one warp per region.
+//
+// Replaces consensus_SPOA (BMEAN/bmean.cpp:585-599), the vote of easy_consensus (:649-694) and the spoa 4.0.0
+// subset CONSENT uses: local (kSW) alignment with linear gaps m=5 n=-10 g=-4
+// (spoa/src/simd_alignment_engine_impl.hpp:712-1056 == sisd_alignment_engine.cpp:260-435), Graph::add_alignment
+// (graph.cpp:155-272), add_sequence (:274-292), add_edge (:100-116), topological_sort (:294-354) and
+// generate_multiple_sequence_alignment (:372-427).
+//
+// What is kept of spoa's graph — exactly what its results depend on:
+//   node  : letter, ordered in-edge list (predecessor order drives the traceback tie-breaks), aligned set
+//           (<= 3 others: a column holds at most one node per base), #sequences through it, "sequence 0 is here"
+//   order : rank <-> node from the explicit-stack DFS of topological_sort, reproduced step by step
+// Out-edges and per-edge sequence labels are not stored: edge existence is tested on the in-list, and the MSA
+// rows are never built — the vote only needs, per column, how many sequences pass through each of its nodes
+// (gaps = the rest) and row 0's letter.
+//
+// Parallelism: a persistent warp takes jobs (regions) from the chunk queue.  The score matrix is swept row by
+// row in rank order with the 32 lanes across query columns; the in-row gap dependency
+//   H[i][j] = max(v[j], H[i][j-1] - 4)        is the max-plus prefix scan   H[i][j] = max_{t<=j}(v[t] + 4t) - 4j,
+// done with 5 warp shuffles per 32 columns and a carry between chunks.  Rows are int16 in global memory
+// (coalesced 64-byte row segments; L1/L2 resident for the short segments of deep piles, HBM-streamed for the
+// long ones) because the traceback needs the whole matrix, as in the reference.  Traceback, graph update and
+// the DFS are sequential by nature (and a few percent of the cells): lane 0 runs them.
+//
+// Scratch sizes are per tier; a job that outgrows its tier is re-queued for the next one.
+#pragma once
+#include "cg_common.cuh"
+
+#define CG_POA_WARPS_PER_CTA 4u
+#define CG_POA_THREADS (CG_POA_WARPS_PER_CTA * 32u)
+#define CG_POA_NEG (-(1 << 28))
+
+struct CgPoaState {
+    u32 V, E, nseqs, nrank;
+    bool ovf;
+};
+
+__device__ __forceinline__ u32 cg_poa_add_node(const CgPoaScratch& s, CgPoaState& g, u8 letter) {
+    if (g.V >= s.vcap) { g.ovf = true; return 0; }
+    const u32 id = g.V++;
+    s.letter[id] = letter; s.in0[id] = 0; s.nal[id] = 0; s.nseq[id] = 0;
+    s.in_head[id] = CG_NONE32; s.in_tail[id] = CG_NONE32;
+    return id;
+}
+// graph.cpp:100-116 — an existing edge is reused (only its label list would grow; labels are not needed here)
+__device__ __forceinline__ void cg_poa_add_edge(const CgPoaScratch& s, CgPoaState& g, u32 b, u32 e) {
+    for (u32 ee = s.in_head[e]; ee != CG_NONE32; ee = s.e_next[ee])
+        if (s.e_pred[ee] == b) return;
+    if (g.E >= s.ecap) { g.ovf = true; return; }
+    const u32 id = g.E++;
+    s.e_pred[id] = (u16)b; s.e_next[id] = CG_NONE32;
+    if (s.in_tail[e] == CG_NONE32) s.in_head[e] = id; else s.e_next[s.in_tail[e]] = id;
+    s.in_tail[e] = id;
+}
+__device__ __forceinline__ void cg_poa_visit(const CgPoaScratch& s, const CgPoaState& g, u32 node) {
+    s.nseq[node] = (u16)(s.nseq[node] + 1);
+    if (g.nseqs == 0) s.in0[node] = 1;
+}
+// graph.cpp:274-292 — a chain of new nodes for seq[begin,end); -1 if empty
+__device__ __forceinline__ i32 cg_poa_add_sequence(const CgPoaScratch& s, CgPoaState& g, const u8* seq, u32 begin, u32 end) {
+    if (begin == end) return -1;
+    const u32 first = cg_poa_add_node(s, g, seq[begin]);
+    cg_poa_visit(s, g, first);
+    u32 prev = first;
+    for (u32 i = begin + 1; i < end && !g.ovf; ++i) {
+        const u32 id = cg_poa_add_node(s, g, seq[i]);
+        cg_poa_visit(s, g, id);
+        cg_poa_add_edge(s, g, prev, id);
+        prev = id;
+    }
+    return (i32)first;
+}
+
+// graph.cpp:155-272.  The alignment is stored in traceback order (last pair first): index n_aln-1 .. 0.
+__device__ CG_NOINLINE void cg_poa_add_alignment(const CgPoaScratch& s, CgPoaState& g, u32 n_aln, const u8* seq, u32 L) {
+    if (n_aln == 0) {
+        cg_poa_add_sequence(s, g, seq, 0, L);
+        g.nseqs++;
+        return;
+    }
+    i32 first_valid = -1, last_valid = -1;
+    for (i32 i = (i32)n_aln - 1; i >= 0; --i)
+        if (s.aln_pos[i] != -1) { if (first_valid == -1) first_valid = s.aln_pos[i]; last_valid = s.aln_pos[i]; }
+    const u32 tmp = g.V;
+    cg_poa_add_sequence(s, g, seq, 0, (u32)first_valid);
+    i32 head = tmp == g.V ? -1 : (i32)g.V - 1;
+    const i32 tail = cg_poa_add_sequence(s, g, seq, (u32)last_valid + 1, L);
+    for (i32 i = (i32)n_aln - 1; i >= 0 && !g.ovf; --i) {
+        const i32 qp = s.aln_pos[i];
+        if (qp == -1) continue;
+        const u8 letter = seq[qp];
+        const i32 an = s.aln_node[i];
+        u32 nn;
+        if (an == -1) {
+            nn = cg_poa_add_node(s, g, letter);
+        } else if (s.letter[an] == letter) {
+            nn = (u32)an;
+        } else {
+            i32 aligned_to = -1;
+            const u32 na = s.nal[an];
+            for (u32 a = 0; a < na; ++a) {
+                const u32 aid = s.aligned[3 * an + a];
+                if (s.letter[aid] == letter) { aligned_to = (i32)aid; break; }
+            }
+            if (aligned_to == -1) {
+                nn = cg_poa_add_node(s, g, letter);
+                if (g.ovf) break;
+                if (na >= 3) { g.ovf = true; break; }          // cannot happen with ACGT input
+                for (u32 a = 0; a < na; ++a) {
+                    const u32 aid = s.aligned[3 * an + a];
+                    s.aligned[3 * nn + s.nal[nn]] = (u16)aid; s.nal[nn]++;
+                    s.aligned[3 * aid + s.nal[aid]] = (u16)nn; s.nal[aid]++;
+                }
+                s.aligned[3 * nn + s.nal[nn]] = (u16)an; s.nal[nn]++;
+                s.aligned[3 * an + s.nal[an]] = (u16)nn; s.nal[an]++;
+            } else nn = (u32)aligned_to;
+        }
+        if (g.ovf) break;
+        cg_poa_visit(s, g, nn);
+        if (head != -1) cg_poa_add_edge(s, g, (u32)head, nn);
+        head = (i32)nn;
+    }
+    if (tail != -1 && !g.ovf) cg_poa_add_edge(s, g, (u32)head, (u32)tail);
+    g.nseqs++;
+}
+
+// graph.cpp:294-354 — explicit-stack DFS over node ids; marks/check are pre-initialised (0 / 1) by the warp.
+__device__ CG_NOINLINE void cg_poa_toposort(const CgPoaScratch& s, CgPoaState& g) {
+    u32 nrank = 0, sp = 0;
+    const u32 V = g.V;
+    for (u32 i = 0; i < V; ++i) {
+        if (s.marks[i] != 0) continue;
+        s.stack[sp++] = (u16)i;
+        while (sp != 0) {
+            const u32 id = s.stack[sp - 1];
+            bool valid = true;
+            if (s.marks[id] != 2) {
+                for (u32 ee = s.in_head[id]; ee != CG_NONE32; ee = s.e_next[ee]) {
+                    const u32 b = s.e_pred[ee];
+                    if (s.marks[b] != 2) {
+                        if (sp >= s.scap) { g.ovf = true; return; }
+                        s.stack[sp++] = (u16)b; valid = false;
+                    }
+                }
+                const u32 na = s.nal[id];
+                if (s.check[id]) {
+                    for (u32 a = 0; a < na; ++a) {
+                        const u32 aid = s.aligned[3 * id + a];
+                        if (s.marks[aid] != 2) {
+                            if (sp >= s.scap) { g.ovf = true; return; }
+                            s.stack[sp++] = (u16)aid; s.check[aid] = 0; valid = false;
+                        }
+                    }
+                }
+                if (valid) {
+                    s.marks[id] = 2;
+                    if (s.check[id]) {
+                        s.r2n[nrank] = (u16)id; s.leader[nrank] = 1; ++nrank;
+                        for (u32 a = 0; a < na; ++a) { s.r2n[nrank] = s.aligned[3 * id + a]; s.leader[nrank] = 0; ++nrank; }
+                    }
+                } else s.marks[id] = 1;
+            }
+            if (valid) --sp;
+        }
+    }
+    g.nrank = nrank;
+}
+
+// Traceback (simd_alignment_engine_impl.hpp:968-1004 == sisd_alignment_engine.cpp:392-431): diagonal over the
+// predecessors in in-edge order, then vertical over them, then horizontal.  Returns the number of pairs.
+__device__ CG_NOINLINE u32 cg_poa_traceback(const CgPoaScratch& s, CgPoaState& g, const u8* seq, u32 Wd, u32 bi, u32 bj) {
+    const i16* H = s.H;
+    u32 i = bi, j = bj, n = 0, pi_ = 0, pj_ = 0;
+    while (H[(size_t)i * Wd + j] != 0) {
+        const i32 Hij = H[(size_t)i * Wd + j];
+        const u32 node = s.r2n[i - 1];
+        const u32 eh = s.in_head[node];
+        bool found = false;
+        if (j != 0) {
+            const i32 sc = s.letter[node] == seq[j - 1] ? 5 : -10;
+            if (eh == CG_NONE32) {
+                if (Hij == H[j - 1] + sc) { pi_ = 0; pj_ = j - 1; found = true; }
+            } else {
+                for (u32 ee = eh; ee != CG_NONE32 && !found; ee = s.e_next[ee]) {
+                    const u32 pr = (u32)s.rank_of[s.e_pred[ee]] + 1;
+                    if (Hij == H[(size_t)pr * Wd + (j - 1)] + sc) { pi_ = pr; pj_ = j - 1; found = true; }
+                }
+            }
+        }
+        if (!found) {
+            if (eh == CG_NONE32) {
+                if (Hij == H[j] - 4) { pi_ = 0; pj_ = j; found = true; }
+            } else {
+                for (u32 ee = eh; ee != CG_NONE32 && !found; ee = s.e_next[ee]) {
+                    const u32 pr = (u32)s.rank_of[s.e_pred[ee]] + 1;
+                    if (Hij == H[(size_t)pr * Wd + j] - 4) { pi_ = pr; pj_ = j; found = true; }
+                }
+            }
+        }
+        if (!found && j != 0 && Hij == H[(size_t)i * Wd + j - 1] - 4) { pi_ = i; pj_ = j - 1; found = true; }
+        if (!found || n >= s.alncap) { g.ovf = true; return 0; }     // inconsistent matrix: cannot happen
+        s.aln_node[n] = i == pi_ ? -1 : (i32)node;
+        s.aln_pos[n] = j == pj_ ? -1 : (i32)(j - 1);
+        ++n;
+        i = pi_; j = pj_;
+    }
+    return n;
+}
+
+// One job.  Returns the consensus length, or CG_NONE32 if the tier's scratch was outgrown.
+__device__ u32 cg_poa_job(const CgChunk& c, const CgPoaScratch& s, u32 w, u32 rg, u64* cnt_aln, u64* cnt_cells, u64* cnt_pred) {
+    const u32 lane = cg_lane();
+    const CgWin W = c.win[w];
+    CgRegion* R = &c.regions[c.off_reg[w] + rg];
+    CgWinView v;
+    v.seq_off = c.seq_off + W.seq_begin; v.pos = c.pos + c.off_pos[w]; v.chain = c.chain + c.off_slot[w];
+    v.rel = c.rel + c.off_slot[w]; v.N = W.n_seqs; v.C = W.n_cand; v.nA = W.n_chain;
+    const u8* bases = (const u8*)c.bases;
+
+    // ---- the region's segments, in read order (split_reads)
+    u32 nseg = 0;
+    for (u32 rb = 0; rb < v.N; rb += 32) {
+        const u32 r = rb + lane;
+        u32 st = 0, ln = 0;
+        const bool keep = r < v.N && cg_eval_segment(v, rg, r, &st, &ln);
+        const u32 bal = __ballot_sync(CG_FULL, keep);
+        if (keep) {
+            const u32 idx = nseg + __popc(bal & ((1u << lane) - 1u));
+            if (idx < s.ncap) { s.seg_read[idx] = (u16)r; s.seg_start[idx] = (u16)st; s.seg_len[idx] = (u16)ln; }
+        }
+        nseg += __popc(bal);
+    }
+    if (nseg > s.ncap) return CG_NONE32;
+    __syncwarp();
+
+    CgPoaState g;
+    g.V = 0; g.E = 0; g.nseqs = 0; g.nrank = 0; g.ovf = false;
+    i16* H = s.H;
+
+    for (u32 si = 0; si < nseg; ++si) {
+        const u32 L = s.seg_len[si];
+        if (L == 0) continue;                                        // graph.cpp:160 — not a row of the MSA
+        const u8* seq = bases + v.seq_off[s.seg_read[si]] + s.seg_start[si];
+        const u32 Wd = L + 1;
+        u32 n_aln = 0;
+        if (g.V != 0) {
+            if ((u64)(g.V + 1) * Wd > s.hcap) return CG_NONE32;
+            // ---- score matrix, row by row in rank order
+            for (u32 j = lane; j < Wd; j += 32) H[j] = 0;
+            i32 bv = 0; u32 bi = 0, bj = 0;
+            u64 pred_rows = 0;
+            __syncwarp();
+            for (u32 r = 0; r < g.V; ++r) {
+                const u32 node = s.r2n[r];
+                const u8 ch = s.letter[node];
+                const u32 eh = s.in_head[node];
+                i16* row = H + (size_t)(r + 1) * Wd;
+                if (lane == 0) row[0] = 0;
+                i32 carry = 0;
+                for (u32 jb = 1; jb < Wd; jb += 32) {
+                    const u32 j = jb + lane;
+                    const bool act = j < Wd;
+                    i32 val = CG_POA_NEG;
+                    if (act) {
+                        const i32 sc = seq[j - 1] == ch ? 5 : -10;
+                        if (eh == CG_NONE32) {
+                            val = sc > -4 ? sc : -4;                  // virtual start row of zeros
+                        } else {
+                            for (u32 ee = eh; ee != CG_NONE32; ee = s.e_next[ee]) {
+                                const i16* prow = H + (size_t)((u32)s.rank_of[s.e_pred[ee]] + 1) * Wd;
+                                const i32 a = (i32)prow[j - 1] + sc, b = (i32)prow[j] - 4;
+                                const i32 m = a > b ? a : b;
+                                val = m > val ? m : val;
+                            }
+                        }
+                        val = val > 0 ? val : 0;
+                    }
+                    i32 u = act ? val + 4 * (i32)j : CG_POA_NEG;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const i32 o = __shfl_up_sync(CG_FULL, u, d);
+                        if (lane >= (u32)d) u = o > u ? o : u;
+                    }
+                    u = u > carry ? u : carry;
+                    carry = __shfl_sync(CG_FULL, u, 31);
+                    if (act) {
+                        const i32 h = u - 4 * (i32)j;
+                        row[j] = (i16)h;
+                        if (h > bv) { bv = h; bi = r + 1; bj = j; }
+                    }
+                }
+                if (lane == 0) {
+                    u32 deg = 0;
+                    for (u32 ee = eh; ee != CG_NONE32; ee = s.e_next[ee]) ++deg;
+                    pred_rows += deg ? deg : 1;
+                }
+                __syncwarp();
+            }
+            if (lane == 0) { *cnt_aln += 1; *cnt_cells += (u64)(g.V + 1) * L; *cnt_pred += pred_rows * L; }
+            // first cell in row-major order holding the maximum (simd...impl.hpp:828-833, 860-862)
+            const u64 key = ((u64)(u32)bv << 32) | ((u64)(0xffffu - bi) << 16) | (u64)(0xffffu - bj);
+            const u64 kb = cg_warp_max64(key);
+            bv = (i32)(kb >> 32); bi = 0xffffu - (u32)((kb >> 16) & 0xffffu); bj = 0xffffu - (u32)(kb & 0xffffu);
+            if (lane == 0 && bv > 0) n_aln = cg_poa_traceback(s, g, seq, Wd, bi, bj);
+        }
+        // ---- graph update + topological order (sequential)
+        if (lane == 0 && !g.ovf) cg_poa_add_alignment(s, g, n_aln, seq, L);
+        g.V = __shfl_sync(CG_FULL, g.V, 0); g.E = __shfl_sync(CG_FULL, g.E, 0);
+        g.nseqs = __shfl_sync(CG_FULL, g.nseqs, 0);
+        g.ovf = __shfl_sync(CG_FULL, (u32)g.ovf, 0) != 0;
+        if (g.ovf) return CG_NONE32;
+        for (u32 i = lane; i < g.V; i += 32) { s.marks[i] = 0; s.check[i] = 1; }
+        __syncwarp();
+        if (lane == 0) cg_poa_toposort(s, g);
+        g.ovf = __shfl_sync(CG_FULL, (u32)g.ovf, 0) != 0;
+        g.nrank = __shfl_sync(CG_FULL, g.nrank, 0);
+        if (g.ovf) return CG_NONE32;
+        __syncwarp();
+        for (u32 i = lane; i < g.V; i += 32) s.rank_of[s.r2n[i]] = (u16)i;
+        __syncwarp();
+    }
+
+    // ---- column vote (bmean.cpp:649-694) straight off the graph: a column = a leader and its aligned nodes
+    u8* out = c.arena + c.off_arena[w] + R->arena_off;
+    u32 outn = 0;
+    for (u32 ib = 0; ib < g.V; ib += 32) {
+        const u32 i = ib + lane;
+        u8 emit = 0;
+        if (i < g.V && s.leader[i]) {
+            u32 cnt[4] = {0, 0, 0, 0};
+            u8 row0 = 0;
+            const u32 node = s.r2n[i];
+            const u32 na = s.nal[node];
+            for (u32 a = 0; a <= na; ++a) {
+                const u32 x = a == 0 ? node : (u32)s.aligned[3 * node + a - 1];
+                const u8 ch = s.letter[x];
+                const u32 code = cg_base_code(ch) & 3u;
+                cnt[code] = s.nseq[x];
+                if (s.in0[x]) row0 = ch;
+            }
+            const u32 cA = cnt[0], cC = cnt[1], cG = cnt[2], cT = cnt[3];
+            const u32 cM = g.nseqs - (cA + cC + cG + cT);
+            if (cM > cA && cM > cC && cM > cT && cM > cG) emit = 0;
+            else if (cA > cC && cA > cG && cA > cT) emit = 'A';
+            else if (cC > cA && cC > cG && cC > cT) emit = 'C';
+            else if (cG > cA && cG > cC && cG > cT) emit = 'G';
+            else if (cT > cA && cT > cG && cT > cC) emit = 'T';
+            else emit = row0;                                        // row 0's letter, if it has one here
+        }
+        const u32 bal = __ballot_sync(CG_FULL, emit != 0);
+        if (emit) out[outn + __popc(bal & ((1u << lane) - 1u))] = emit;
+        outn += __popc(bal);
+    }
+    return outn;
+}
+
+// Persistent warps draining the job queue of one tier.
+// qctl[0] = number of jobs, qctl[1] = next job, qctl[2] = jobs re-queued for the next tier.
+__global__ void __launch_bounds__(CG_POA_THREADS) k_poa(CgChunk c, const CgPoaScratch* scratch, const uint2* jobs, u32* qctl, uint2* jobs_next) {
+    const u32 lane = cg_lane();
+    const u32 gw = blockIdx.x * CG_POA_WARPS_PER_CTA + cg_warp();
+    const CgPoaScratch s = scratch[gw];
+    const u32 njobs = qctl[0];
+    u64 cnt_aln = 0, cnt_cells = 0, cnt_pred = 0;
+    for (;;) {
+        u32 j = 0;
+        if (lane == 0) j = atomicAdd(&qctl[1], 1u);
+        j = __shfl_sync(CG_FULL, j, 0);
+        if (j >= njobs) break;
+        const uint2 job = jobs[j];
+        const u32 n = cg_poa_job(c, s, job.x, job.y, &cnt_aln, &cnt_cells, &cnt_pred);
+        if (lane == 0) {
+            if (n == CG_NONE32) {
+                if (jobs_next) jobs_next[atomicAdd(&qctl[2], 1u)] = job;
+                else { c.win[job.x].bad = 1; atomicOr(c.flags, (u32)CG_FLAG_CAPACITY); }
+            } else {
+                c.regions[c.off_reg[job.x] + job.y].cons_len = n;
+            }
+        }
+        __syncwarp();
+    }
+    if (lane == 0 && cnt_aln) {
+        atomicAdd((unsigned long long*)&c.counters->alignments, (unsigned long long)cnt_aln);
+        atomicAdd((unsigned long long*)&c.counters->dp_cells, (unsigned long long)cnt_cells);
+        atomicAdd((unsigned long long*)&c.counters->dp_pred_cells, (unsigned long long)cnt_pred);
+    }
+}

@@ -1,0 +1,94 @@
+// k_prep.cuh — per-chunk planning, offset scans and ASCII -> 2-bit packing.
+#pragma once
+#include "cg_common.cuh"
+
+__device__ __forceinline__ u64 cg_round_up(u64 v, u64 m) { return (v + m - 1) / m * m; }
+
+// One thread per window: sizes and arena capacities (written into the off_* arrays, scanned by k_scan).
+__global__ void k_plan(CgChunk c) {
+    u32 w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= c.nwin) return;
+    u32 gw = c.w0 + w;
+    u32 s0 = c.win_seq_begin[gw], s1 = c.win_seq_begin[gw + 1];
+    u32 N = s1 - s0, k = c.k;
+    u64 nocc = 0;
+    for (u32 s = s0; s < s1; ++s) {
+        u32 len = (u32)(c.seq_off[s + 1] - c.seq_off[s]);
+        if (len >= k) nocc += len - k + 1;
+    }
+    u32 tlen = (u32)(c.seq_off[s0 + 1] - c.seq_off[s0]);
+    u32 tk = tlen >= k ? tlen - k + 1 : 0;
+    u64 nb = c.seq_off[s1] - c.seq_off[s0];
+    CgWin W;
+    W.seq_begin = s0; W.n_seqs = N; W.tlen = tlen; W.tk = tk;
+    int S = (int)c.common < (int)N / 2 ? (int)c.common : (int)N / 2;     // src/correctionMSA.cpp:31
+    W.S = (u32)S;
+    W.n_cand = W.n_alive = W.n_chain = W.n_regions = W.n_solid = 0;
+    W.stitched_len = W.final_len = W.final_beg = 0; W.status = 0; W.bad = 0;
+    W.n_occ = (u32)nocc; W.n_bases = (u32)nb;
+    c.win[w] = W;
+    c.off_solid[w] = cg_round_up(nocc / c.solid, 4);
+    c.off_slot[w] = cg_round_up(tk, 8);
+    c.off_pos[w] = cg_round_up((u64)tk * N, 8);
+    c.off_reg[w] = (u64)tk + 2;
+    c.off_arena[w] = cg_round_up(nb + N, 16);
+}
+
+// Exclusive in-place scan of up to 5 arrays of n entries (+ total at [n]); block b handles array b.
+__global__ void k_scan(u64* a0, u64* a1, u64* a2, u64* a3, u64* a4, u32 n) {
+    CG_DYN_SMEM(smem);
+    u64* part = (u64*)smem;                       // blockDim.x entries
+    u64* a = blockIdx.x == 0 ? a0 : blockIdx.x == 1 ? a1 : blockIdx.x == 2 ? a2 : blockIdx.x == 3 ? a3 : a4;
+    u32 T = blockDim.x, t = threadIdx.x;
+    u32 per = (n + T - 1) / T;
+    u32 b = t * per, e = b + per < n ? b + per : n;
+    u64 s = 0;
+    if (a) for (u32 i = b; i < e; ++i) s += a[i];
+    part[t] = s;
+    __syncthreads();
+    if (t == 0) {
+        u64 run = 0;
+        for (u32 i = 0; i < T; ++i) { u64 v = part[i]; part[i] = run; run += v; }
+        if (a) a[n] = run;
+    }
+    __syncthreads();
+    if (a) {
+        u64 run = part[t];
+        for (u32 i = b; i < e; ++i) { u64 v = a[i]; a[i] = run; run += v; }
+    }
+}
+
+// One CTA per window, one warp per sequence, one lane per 16-base word.
+// word: base i of the word at bits [31-2i, 30-2i] (so a k-mer read off the word is BMEAN's code, utils.cpp:18-30)
+// tag : (read index in the window) << 16 | (word index in the read) << 4 | (k-mer starts in the word - 1); ~0 = none
+__global__ void __launch_bounds__(256) k_pack(CgChunk c) {
+    const CgWin W = c.win[blockIdx.x];
+    u32 lane = cg_lane(), nwarps = blockDim.x >> 5;
+    u32 bad = 0;
+    for (u32 r = cg_warp(); r < W.n_seqs; r += nwarps) {
+        u32 s = W.seq_begin + r;
+        u64 off = c.seq_off[s];
+        u32 len = (u32)(c.seq_off[s + 1] - off);
+        u64 g0 = cg_pword(c.seq_off, s) - c.pword_base;
+        u32 nw = (u32)(cg_pword(c.seq_off, s + 1) - c.pword_base - g0);
+        u32 nkm = len >= c.k ? len - c.k + 1 : 0;
+        const u8* src = (const u8*)c.bases + off;
+        for (u32 wi = lane; wi < nw; wi += 32) {
+            u32 word = 0;
+#pragma unroll
+            for (u32 b = 0; b < 16; ++b) {
+                u32 idx = 16 * wi + b;
+                if (idx < len) {
+                    u32 code = cg_base_code(src[idx]);
+                    bad |= code >> 2;
+                    word |= (code & 3u) << (30 - 2 * b);
+                }
+            }
+            u32 nv = nkm > 16 * wi ? (nkm - 16 * wi < 16 ? nkm - 16 * wi : 16) : 0;
+            u32 tag = nv ? ((r << 16) | (wi << 4) | (nv - 1)) : CG_NONE32;
+            c.pwords[g0 + wi] = word;
+            c.ptags[g0 + wi] = tag;
+        }
+    }
+    if (bad) atomicOr(c.flags, (u32)CG_FLAG_BAD_BASE);
+}

@@ -1,0 +1,165 @@
+// k_split.cuh — distance statistics between consecutive chain anchors, region classification, POA job list.
+//
+// Replaces deciles / comparable / average_distance_next_anchor (BMEAN/bmean.cpp:264-295, 324-418),
+// get_position + split_reads (:422-430, 476-554) and the trivial cases of easy_consensus (:603-641).
+//
+// The reference materialises every region as a vector of strings.  Here a region is never copied: a kept
+// segment is (read, start, len) recomputed from the position table by cg_eval_segment, so this kernel only
+// *classifies* regions (empty / one distinct string -> copy / needs POA), sizes their consensus slot and
+// appends POA jobs to the chunk-wide queue that k_poa's persistent warps drain.
+//
+// The two order statistics of the reference's sorted distance vector (V[floor((n-1)*0.2)], V[ceil((n-1)*0.8)])
+// are found by a warp radix select over the bits of the largest distance; nothing is sorted.
+#pragma once
+#include "cg_common.cuh"
+
+#define CG_SPLIT_THREADS 256u
+#define CG_SPLIT_WARPS (CG_SPLIT_THREADS / 32u)
+
+// idx-th smallest (0-based) distance of the pair (s1,s2) over reads holding both.
+__device__ __forceinline__ u32 cg_select_distance(const u16* pos, u32 C, u32 N, u32 s1, u32 s2, u32 nbits, u32 idx) {
+    const u32 lane = cg_lane();
+    u64 prefix = 0;
+    u32 rem = idx;
+    for (int b = (int)nbits - 1; b >= 0; --b) {
+        u32 cnt0 = 0;
+        for (u32 rb = 0; rb < N; rb += 32) {
+            const u32 r = rb + lane;
+            if (r < N) {
+                const u32 p1 = pos[(size_t)r * C + s1], p2 = pos[(size_t)r * C + s2];
+                if (p1 && p2) {
+                    const u64 d = (u32)(p2 - p1);
+                    if ((d >> (b + 1)) == (prefix >> (b + 1)) && !((d >> b) & 1ull)) ++cnt0;
+                }
+            }
+        }
+        cnt0 = cg_warp_sum(cnt0);
+        if (rem >= cnt0) { rem -= cnt0; prefix |= 1ull << b; }
+    }
+    return (u32)prefix;
+}
+
+__global__ void __launch_bounds__(CG_SPLIT_THREADS) k_split(CgChunk c) {
+    const u32 w = blockIdx.x, lane = cg_lane(), warp = cg_warp();
+    const CgWin W = c.win[w];
+    const u32 N = W.n_seqs, C = W.n_cand, nA = W.n_chain;
+    const u64 slot_base = c.off_slot[w];
+    const u16* chain = c.chain + slot_base;
+    const u16* pos = c.pos + c.off_pos[w];
+    u32* rel = c.rel + slot_base;
+    CgRegion* regs = c.regions + c.off_reg[w];
+    const u8* wbases = (const u8*)c.bases;
+
+    // ---- average_distance_next_anchor: one warp per consecutive anchor pair
+    for (u32 i = warp; i + 1 < nA; i += CG_SPLIT_WARPS) {
+        const u32 s1 = chain[i], s2 = chain[i + 1];
+        u32 n = 0, mx = 0;
+        for (u32 rb = 0; rb < N; rb += 32) {
+            const u32 r = rb + lane;
+            bool has = false;
+            if (r < N) {
+                const u32 p1 = pos[(size_t)r * C + s1], p2 = pos[(size_t)r * C + s2];
+                if (p1 && p2) { has = true; const u32 d = p2 - p1; mx = d > mx ? d : mx; }
+            }
+            n += __popc(__ballot_sync(CG_FULL, has));
+        }
+        mx = cg_warp_max(mx);
+        if (n == 0) {                                   // unreachable: chain edges share >= max(S,1) reads
+            if (lane == 0) { rel[i] = 0; atomicOr(c.flags, (u32)CG_FLAG_INTERNAL); }
+            continue;
+        }
+        const u32 nbits = 32u - (u32)__clz((int)mx);
+        const u32 ilo = (u32)floor((double)(n - 1) * 0.2);     // deciles, bmean.cpp:324-327
+        const u32 ihi = (u32)ceil((double)(n - 1) * 0.8);
+        const double lo = (double)cg_select_distance(pos, C, N, s1, s2, nbits, ilo);
+        const double hi = (double)cg_select_distance(pos, C, N, s1, s2, nbits, ihi);
+        u32 sum = 0, cnt = 0;
+        for (u32 rb = 0; rb < N; rb += 32) {
+            const u32 r = rb + lane;
+            if (r < N) {
+                const u32 p1 = pos[(size_t)r * C + s1], p2 = pos[(size_t)r * C + s2];
+                if (p1 && p2) {
+                    const u32 d = p2 - p1;
+                    if (cg_comparable_dec((double)d, lo, hi)) { sum += d; ++cnt; }
+                }
+            }
+        }
+        sum = cg_warp_sum(sum);
+        cnt = cg_warp_sum(cnt);
+        if (lane == 0) rel[i] = cnt ? sum / cnt : 0u;           // integer division, bmean.cpp:401
+    }
+    __syncthreads();
+
+    // ---- split_reads + trivial cases of easy_consensus: one warp per region
+    u32 nreg = nA ? nA + 1 : 2;
+    if (nreg < c.min_anchors) nreg = 0;                         // MSABMAAC bails out, bmean.cpp:796-805
+    CgWinView v;
+    v.seq_off = c.seq_off + W.seq_begin; v.pos = pos; v.chain = chain; v.rel = rel; v.N = N; v.C = C; v.nA = nA;
+    for (u32 g = warp; g < nreg; g += CG_SPLIT_WARPS) {
+        u32 n = 0, r0 = 0, st0 = 0, ln0 = 0, sum = 0;
+        bool same = true;
+        for (u32 rb = 0; rb < N; rb += 32) {
+            const u32 r = rb + lane;
+            u32 st = 0, ln = 0;
+            const bool keep = r < N && cg_eval_segment(v, g, r, &st, &ln);
+            const u32 bal = __ballot_sync(CG_FULL, keep);
+            if (bal && n == 0) {
+                const int src = __ffs((int)bal) - 1;
+                r0 = __shfl_sync(CG_FULL, r, src); st0 = __shfl_sync(CG_FULL, st, src); ln0 = __shfl_sync(CG_FULL, ln, src);
+            }
+            bool eq = true;
+            if (keep) {
+                sum += ln;
+                eq = ln == ln0;
+                if (eq) {
+                    const u8* a = wbases + v.seq_off[r] + st;
+                    const u8* b = wbases + v.seq_off[r0] + st0;
+                    for (u32 t = 0; t < ln; ++t) if (a[t] != b[t]) { eq = false; break; }
+                }
+            }
+            const bool alleq = __all_sync(CG_FULL, eq);
+            same = same && alleq;
+            n += __popc(bal);
+        }
+        sum = cg_warp_sum(sum);
+        if (lane == 0) {
+            CgRegion R;
+            R.kind = n == 0 ? CG_REG_EMPTY : (n == 1 || same) ? CG_REG_COPY : CG_REG_POA;
+            R.n = n; R.read = r0; R.start = st0; R.len = ln0; R.sum_len = sum; R.arena_off = 0; R.cons_len = 0;
+            regs[g] = R;
+        }
+    }
+    __syncthreads();
+
+    // ---- consensus slots and POA jobs (warp 0)
+    if (warp != 0) return;
+    u32 njobs = 0;
+    for (u32 gb = 0; gb < nreg; gb += 32) {
+        const u32 g = gb + lane;
+        njobs += (g < nreg && regs[g].kind == CG_REG_POA) ? 1u : 0u;
+    }
+    njobs = cg_warp_sum(njobs);
+    u32 jbase = 0;
+    if (lane == 0 && njobs) jbase = atomicAdd(&c.job_count[0], njobs);
+    jbase = __shfl_sync(CG_FULL, jbase, 0);
+    u32 run_off = 0, run_job = 0;
+    for (u32 gb = 0; gb < nreg; gb += 32) {
+        const u32 g = gb + lane;
+        const bool isp = g < nreg && regs[g].kind == CG_REG_POA;
+        const u32 sz = isp ? regs[g].sum_len : 0u;
+        const u32 inc = cg_warp_scan(sz);
+        const u32 bal = __ballot_sync(CG_FULL, isp);
+        if (isp) {
+            regs[g].arena_off = run_off + inc - sz;
+            c.jobs[jbase + run_job + __popc(bal & ((1u << lane) - 1u))] = make_uint2(w, g);
+        }
+        run_off += __shfl_sync(CG_FULL, inc, 31);
+        run_job += __popc(bal);
+    }
+    if (lane == 0) {
+        c.win[w].n_regions = nreg;
+        atomicAdd((unsigned long long*)&c.counters->anchors, (unsigned long long)nA);
+        atomicAdd((unsigned long long*)&c.counters->regions, (unsigned long long)(nA ? nA + 1 : 2));
+        atomicAdd((unsigned long long*)&c.counters->poa_graphs, (unsigned long long)njobs);
+    }
+}

@@ -1,0 +1,132 @@
+"""Host-side mirror of the reference's per-window operator, batched.
+
+`Corrector.correct_windows(batch)` is `computeConsensusReadCorrection` (reference
+src/correctionMSA.cpp:29-49; `computeConsensusAssemblyPolishing` :51-70 has the same body) applied to
+every window of `batch`, through the C ABI of include/consent_b200.h.  Same argument meaning as the
+reference (`Params` = merSize / solidThresh / commonKMers / minAnchors), same results: per window the
+mixed-case consensus, the solid k-mer counts (`merCounts` entries >= solidThresh) and whether the raw
+template was returned.  Errors are exceptions carrying the library's status code.
+
+There is no CPU path: the CUDA library must be built (`__graft_entry__.build()`) and a GPU present.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from ._ffi import (Batch, CG_N_STAGES, PKG_DIR, Params, Results, STAGE_NAMES, STATUS_NAMES, cg_batch,
+                   cg_counters, cg_params, cg_results, load_library)
+
+LIB_PATH = os.path.join(PKG_DIR, "libconsent_b200.so")
+
+EXPORTS = ("cg_abi_version", "cg_device_count", "cg_create", "cg_destroy", "cg_last_error", "cg_set_option",
+           "cg_correct_windows", "cg_free_results", "cg_upload", "cg_run", "cg_download", "cg_stage_ms",
+           "cg_get_counters")
+
+
+class ConsentError(RuntimeError):
+    def __init__(self, code: int, what: str):
+        super().__init__(f"{STATUS_NAMES.get(code, code)}: {what}")
+        self.code = code
+
+
+def bind(lib: C.CDLL) -> C.CDLL:
+    H = C.c_void_p
+    lib.cg_abi_version.restype = C.c_int
+    lib.cg_device_count.restype = C.c_int
+    lib.cg_create.restype = C.c_int
+    lib.cg_create.argtypes = [C.c_int, C.POINTER(cg_params), C.POINTER(H)]
+    lib.cg_destroy.argtypes = [H]
+    lib.cg_last_error.restype = C.c_char_p
+    lib.cg_last_error.argtypes = [H]
+    lib.cg_set_option.restype = C.c_int
+    lib.cg_set_option.argtypes = [H, C.c_char_p, C.c_longlong]
+    for name in ("cg_correct_windows",):
+        f = getattr(lib, name)
+        f.restype = C.c_int
+        f.argtypes = [H, C.POINTER(cg_batch), C.POINTER(cg_results)]
+    lib.cg_upload.restype = C.c_int
+    lib.cg_upload.argtypes = [H, C.POINTER(cg_batch)]
+    lib.cg_run.restype = C.c_int
+    lib.cg_run.argtypes = [H]
+    lib.cg_download.restype = C.c_int
+    lib.cg_download.argtypes = [H, C.POINTER(cg_results)]
+    lib.cg_free_results.argtypes = [C.POINTER(cg_results)]
+    lib.cg_stage_ms.restype = C.c_int
+    lib.cg_stage_ms.argtypes = [H, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]
+    lib.cg_get_counters.restype = C.c_int
+    lib.cg_get_counters.argtypes = [H, C.POINTER(cg_counters)]
+    return lib
+
+
+class Corrector:
+    """One context = one GPU, one stream, its own workspaces (cg_handle)."""
+
+    def __init__(self, params: Params = Params(), device: int = 0, lib_path: str | None = None):
+        self.lib = bind(load_library(lib_path or LIB_PATH))
+        self.params = params
+        self._h = C.c_void_p()
+        cp = params.c()
+        rc = self.lib.cg_create(device, C.byref(cp), C.byref(self._h))
+        if rc != 0:
+            raise ConsentError(rc, (self.lib.cg_last_error(None) or b"").decode())
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self.lib.cg_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise ConsentError(rc, (self.lib.cg_last_error(self._h) or b"").decode())
+
+    def set_option(self, key: str, value: int):
+        self._check(self.lib.cg_set_option(self._h, key.encode(), int(value)))
+
+    # -- the operator -------------------------------------------------------------------------
+    def correct_windows(self, batch: Batch) -> Results:
+        """Host buffers in, host buffers out (H2D, every kernel, D2H)."""
+        cb, r = batch.c(), cg_results()
+        self._check(self.lib.cg_correct_windows(self._h, C.byref(cb), C.byref(r)))
+        out = Results(r)
+        self.lib.cg_free_results(C.byref(r))
+        return out
+
+    # -- staged (bench: keep the batch resident in HBM, time the kernels alone) ---------------
+    def upload(self, batch: Batch):
+        cb = batch.c()
+        self._check(self.lib.cg_upload(self._h, C.byref(cb)))
+
+    def run(self):
+        self._check(self.lib.cg_run(self._h))
+
+    def download(self) -> Results:
+        r = cg_results()
+        self._check(self.lib.cg_download(self._h, C.byref(r)))
+        out = Results(r)
+        self.lib.cg_free_results(C.byref(r))
+        return out
+
+    # -- instrumentation ----------------------------------------------------------------------
+    def stage_ms(self) -> dict:
+        ms = (C.c_float * CG_N_STAGES)()
+        n = (C.c_uint32 * CG_N_STAGES)()
+        self._check(self.lib.cg_stage_ms(self._h, ms, n))
+        return {name: {"ms": float(ms[i]), "launches": int(n[i])} for i, name in enumerate(STAGE_NAMES)}
+
+    def counters(self) -> dict:
+        c = cg_counters()
+        self._check(self.lib.cg_get_counters(self._h, C.byref(c)))
+        return c.as_dict()

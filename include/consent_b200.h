@@ -107,6 +107,10 @@ int         cg_create(int device, const cg_params* params, cg_handle** out);
 void        cg_destroy(cg_handle* h);
 const char* cg_last_error(const cg_handle* h);   /* h may be NULL: last create error */
 
+/* Tuning knobs that never change results (workspace budget per chunk of windows, POA scratch
+ * tiers: "chunk_budget_bytes", "chunk_max_windows", "poa_tier{0,1,2}_{warps,nodes,cells}"). */
+int         cg_set_option(cg_handle* h, const char* key, long long value);
+
 /* One-shot call: host buffers in, host buffers out (H2D, kernels, D2H inside).
  * This is the batched equivalent of calling computeConsensusReadCorrection on
  * every window of `in`.  Blocking; one call at a time per handle. */
