@@ -264,8 +264,8 @@ int run_chunk(cg_handle* h, const ChunkPlan& cp, std::vector<StageSpan>& spans, 
 
     span_begin(CG_STAGE_POA);
     { int rc = ensure_tier(h, 0); if (rc) return rc; }
-    CG_LAUNCH(k_poa, h->tier[0].warps / CG_POA_WARPS_PER_CTA, CG_POA_THREADS, 0, st, c, h->tier[0].desc.as<CgPoaScratch>(),
-              (const uint2*)c.jobs, ctl + CTL_Q0, c.jobs_next);
+    CG_LAUNCH(k_poa, (h->tier[0].warps + CG_POA_WARPS_PER_CTA - 1) / CG_POA_WARPS_PER_CTA, CG_POA_THREADS, 0, st, c, h->tier[0].desc.as<CgPoaScratch>(),
+              h->tier[0].warps, (const uint2*)c.jobs, ctl + CTL_Q0, c.jobs_next);
     h->stage_launches[CG_STAGE_POA] += 1;
     span_end();
 
@@ -282,7 +282,7 @@ int run_chunk(cg_handle* h, const ChunkPlan& cp, std::vector<StageSpan>& spans, 
         CK(cudaMemcpyAsync(ctl + CTL_Q0 + 4 * t, q, sizeof q, cudaMemcpyHostToDevice, st));
         span_begin(CG_STAGE_POA);
         CG_LAUNCH(k_poa, (h->tier[t].warps + CG_POA_WARPS_PER_CTA - 1) / CG_POA_WARPS_PER_CTA, CG_POA_THREADS, 0, st, c,
-                  h->tier[t].desc.as<CgPoaScratch>(), (const uint2*)q_in, ctl + CTL_Q0 + 4 * t, t < 2 ? q_out : (uint2*)nullptr);
+                  h->tier[t].desc.as<CgPoaScratch>(), h->tier[t].warps, (const uint2*)q_in, ctl + CTL_Q0 + 4 * t, t < 2 ? q_out : (uint2*)nullptr);
         h->stage_launches[CG_STAGE_POA] += 1;
         span_end();
         CK(cudaMemcpyAsync(h->h_ctl, ctl, CTL_WORDS * sizeof(u32), cudaMemcpyDeviceToHost, st));
@@ -404,7 +404,7 @@ int cg_set_option(cg_handle* h, const char* key, long long value) {
     const std::string k(key);
     if (k == "chunk_budget_bytes") h->chunk_budget = (size_t)value;
     else if (k == "chunk_max_windows") h->chunk_max_windows = (u32)std::max<long long>(1, value);
-    else if (k == "poa_tier0_warps") { h->tier[0].warps = (u32)value / CG_POA_WARPS_PER_CTA * CG_POA_WARPS_PER_CTA; h->tier[0].ready = false; }
+    else if (k == "poa_tier0_warps") { h->tier[0].warps = (u32)std::max<long long>(1, value); h->tier[0].ready = false; }
     else if (k == "poa_tier1_warps") { h->tier[1].warps = (u32)value; h->tier[1].ready = false; }
     else if (k == "poa_tier2_warps") { h->tier[2].warps = (u32)value; h->tier[2].ready = false; }
     else if (k == "poa_tier0_nodes") { h->tier[0].vcap = (u32)value; h->tier[0].ecap = 4 * (u32)value; h->tier[0].ready = false; }

@@ -356,9 +356,10 @@ __device__ u32 cg_poa_job(const CgChunk& c, const CgPoaScratch& s, u32 w, u32 rg
 
 // Persistent warps draining the job queue of one tier.
 // qctl[0] = number of jobs, qctl[1] = next job, qctl[2] = jobs re-queued for the next tier.
-__global__ void __launch_bounds__(CG_POA_THREADS) k_poa(CgChunk c, const CgPoaScratch* scratch, const uint2* jobs, u32* qctl, uint2* jobs_next) {
+__global__ void __launch_bounds__(CG_POA_THREADS) k_poa(CgChunk c, const CgPoaScratch* scratch, u32 nwarps, const uint2* jobs, u32* qctl, uint2* jobs_next) {
     const u32 lane = cg_lane();
     const u32 gw = blockIdx.x * CG_POA_WARPS_PER_CTA + cg_warp();
+    if (gw >= nwarps) return;                       // warp-uniform; no block-wide barrier in this kernel
     const CgPoaScratch s = scratch[gw];
     const u32 njobs = qctl[0];
     u64 cnt_aln = 0, cnt_cells = 0, cnt_pred = 0;

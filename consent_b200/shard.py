@@ -1,0 +1,107 @@
+"""Multi-GPU sharding of the window stream (one process per GPU, torch.distributed).
+
+Windows (and the piles they come from) are independent: the reference parallelises them over a thread
+pool (src/CONSENT-correction.cpp:76-111, src/CONSENT-polishing.cpp:49-66) and never exchanges anything
+between jobs.  So the data path has no collective: rank r owns a contiguous block of windows in input
+order, runs the whole path on its own GPU, and the only exchange is the final ordered gather of the
+corrected windows to rank 0 — the reference's "print results in submission order"
+(src/CONSENT-correction.cpp:100-103) — over NCCL (NVLink 5 / NVSwitch) on GPUs, gloo in the CPU tests.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from ._ffi import Batch, Results, cg_results  # noqa: F401
+
+
+def shard_range(n_windows: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous block [w0, w1) of rank `rank`; block sizes differ by at most one."""
+    base, rem = divmod(n_windows, world)
+    w0 = rank * base + min(rank, rem)
+    return w0, w0 + base + (1 if rank < rem else 0)
+
+
+def shard_by_bases(batch: Batch, world: int) -> list[tuple[int, int]]:
+    """Contiguous blocks balanced by bases (piles of very different depth): greedy prefix split."""
+    per_win = np.array([int(batch.seq_off[int(batch.win_seq_begin[w + 1])]) - int(batch.seq_off[int(batch.win_seq_begin[w])])
+                        for w in range(batch.n_windows)], dtype=np.int64)
+    cum = np.concatenate([[0], np.cumsum(per_win)])
+    total = int(cum[-1])
+    cuts = [0]
+    for r in range(1, world):
+        cuts.append(int(np.searchsorted(cum, total * r / world, side="left")))
+    cuts.append(batch.n_windows)
+    cuts = [min(max(c, 0), batch.n_windows) for c in cuts]
+    for i in range(1, len(cuts)):
+        cuts[i] = max(cuts[i], cuts[i - 1])
+    return [(cuts[i], cuts[i + 1]) for i in range(world)]
+
+
+class _Flat:
+    """Results as flat numpy arrays (what travels in the gather)."""
+
+    def __init__(self, r: Results):
+        self.cons_len = np.diff(r.cons_off).astype(np.int64)
+        self.solid_len = np.diff(r.solid_off).astype(np.int64)
+        self.cons = r.cons
+        self.status = r.status
+        self.solid_kmer = r.solid_kmer
+        self.solid_count = r.solid_count
+
+
+def _from_parts(parts) -> Results:
+    out = Results.__new__(Results)
+    cons_len = np.concatenate([p.cons_len for p in parts]) if parts else np.zeros(0, np.int64)
+    solid_len = np.concatenate([p.solid_len for p in parts]) if parts else np.zeros(0, np.int64)
+    out.n_windows = int(len(cons_len))
+    out.cons_off = np.concatenate([[0], np.cumsum(cons_len)]).astype(np.uint64)
+    out.solid_off = np.concatenate([[0], np.cumsum(solid_len)]).astype(np.uint64)
+    out.cons = np.concatenate([p.cons for p in parts]).astype(np.uint8) if parts else np.zeros(0, np.uint8)
+    out.status = np.concatenate([p.status for p in parts]).astype(np.uint8) if parts else np.zeros(0, np.uint8)
+    out.solid_kmer = np.concatenate([p.solid_kmer for p in parts]).astype(np.uint32) if parts else np.zeros(0, np.uint32)
+    out.solid_count = np.concatenate([p.solid_count for p in parts]).astype(np.uint32) if parts else np.zeros(0, np.uint32)
+    return out
+
+
+def gather_results(local: Results, device=None, group=None):
+    """Ordered gather of every rank's results to rank 0 (variable length: sizes first, then padded payloads).
+
+    Returns the concatenated Results on rank 0, None elsewhere.  `device`: torch device of the payload tensors
+    ("cuda:N" under NCCL, "cpu" under gloo)."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    f = _Flat(local)
+    # one byte payload per rank: [cons_len i64][solid_len i64][status u8][cons u8][solid_kmer u32][solid_count u32]
+    chunks = [f.cons_len.view(np.uint8), f.solid_len.view(np.uint8), f.status.view(np.uint8), f.cons.view(np.uint8),
+              np.ascontiguousarray(f.solid_kmer).view(np.uint8), np.ascontiguousarray(f.solid_count).view(np.uint8)]
+    payload = np.concatenate([np.ascontiguousarray(c).reshape(-1) for c in chunks]) if local.n_windows else np.zeros(0, np.uint8)
+    meta = torch.tensor([local.n_windows, len(f.cons), len(f.solid_kmer), len(payload)], dtype=torch.int64, device=device)
+    metas = [torch.zeros_like(meta) for _ in range(world)]
+    dist.all_gather(metas, meta, group=group)
+    max_len = max(int(m[3]) for m in metas)
+    buf = torch.zeros(max(max_len, 1), dtype=torch.uint8, device=device)
+    if len(payload):
+        buf[:len(payload)] = torch.from_numpy(payload).to(device)
+    gathered = [torch.zeros_like(buf) for _ in range(world)] if rank == 0 else None
+    dist.gather(buf, gathered, dst=0, group=group)
+    if rank != 0:
+        return None
+    parts = []
+    for r in range(world):
+        nw, nc, ns, nbytes = (int(x) for x in metas[r])
+        raw = gathered[r][:nbytes].cpu().numpy()
+        p = _Flat.__new__(_Flat)
+        o = 0
+        p.cons_len = raw[o:o + 8 * nw].view(np.int64).copy(); o += 8 * nw
+        p.solid_len = raw[o:o + 8 * nw].view(np.int64).copy(); o += 8 * nw
+        p.status = raw[o:o + nw].copy(); o += nw
+        p.cons = raw[o:o + nc].copy(); o += nc
+        p.solid_kmer = raw[o:o + 4 * ns].view(np.uint32).copy(); o += 4 * ns
+        p.solid_count = raw[o:o + 4 * ns].view(np.uint32).copy(); o += 4 * ns
+        parts.append(p)
+    return _from_parts(parts)

@@ -98,6 +98,7 @@ struct Block {
     dim3 bidx, bdim, gdim;
     unsigned nthreads = 0;
     unsigned bar_arrived = 0, bar_gen = 0;
+    unsigned long long progress = 0;      // barrier completions (deadlock detection)
     std::vector<WarpState> warps;
     unsigned char* dyn_smem = nullptr;
     void* sched_sp = nullptr;
@@ -153,9 +154,9 @@ void run_block(Worker& w, Block& b) {
         f.sp = sp0;
     }
     unsigned alive = b.nthreads;
-    unsigned long long idle_rounds = 0;
     while (alive) {
         unsigned a = 0;
+        const unsigned long long before = b.progress;
         for (unsigned t = 0; t < b.nthreads; ++t) {
             Fiber& f = w.fibers[t];
             if (f.done) continue;
@@ -163,8 +164,8 @@ void run_block(Worker& w, Block& b) {
             cg_emu_switch(&b.sched_sp, f.sp);
             if (!f.done) ++a;
         }
-        if (a == alive && ++idle_rounds > 2000000ull) { fprintf(stderr, "simt_emu: deadlock (block %u)\n", b.bidx.x); abort(); }
-        if (a != alive) idle_rounds = 0;
+        // fibers only yield inside barrier waits: a round with no barrier completed and nobody done is a deadlock
+        if (a == alive && b.progress == before) { fprintf(stderr, "simt_emu: deadlock (block %u): a collective is not reached by all threads\n", b.bidx.x); abort(); }
         alive = a;
     }
     cur = nullptr;
@@ -207,7 +208,7 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
 inline void block_barrier() {
     Block* b = cur->blk;
     unsigned g = b->bar_gen;
-    if (++b->bar_arrived == b->nthreads) { b->bar_arrived = 0; b->bar_gen = g + 1; return; }
+    if (++b->bar_arrived == b->nthreads) { b->bar_arrived = 0; b->bar_gen = g + 1; b->progress++; return; }
     while (b->bar_gen == g) yield();
 }
 inline unsigned linear_tid() { Fiber* f = cur; return f->tidx.x + f->blk->bdim.x * (f->tidx.y + f->blk->bdim.y * f->tidx.z); }
@@ -220,7 +221,7 @@ inline void warp_barrier() {
     WarpState& w = my_warp();
     unsigned n = warp_size_here();
     unsigned g = w.gen;
-    if (++w.arrived == n) { w.arrived = 0; w.gen = g + 1; return; }
+    if (++w.arrived == n) { w.arrived = 0; w.gen = g + 1; cur->blk->progress++; return; }
     while (w.gen == g) yield();
 }
 inline void check_mask(unsigned mask) {

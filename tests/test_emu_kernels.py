@@ -1,0 +1,82 @@
+"""CPU suite, part 3: the product's CUDA kernel sources (consent_b200/csrc/*.cuh), compiled for the SIMT emulator of
+tests/emu, against the oracle and the golden vectors.  This is how the kernels are debugged on a box without a GPU;
+the `-m gpu` tests repeat the same checks through the real library on a B200."""
+import pytest
+
+from consent_b200._ffi import Batch, Params
+from consent_b200.engine import ConsentError
+from consent_b200.synth import synth_windows
+from tests.cases import concat, edge_piles
+from tests.helpers import assert_matches_golden, assert_same, golden_batch
+
+FAST_EDGES = {"single_sequence", "two_identical", "template_shorter_than_k", "all_shorter_than_k", "some_reads_shorter_than_k",
+              "unrelated_short_no_anchor", "homopolymer", "homopolymer_mixed", "ragged_lengths", "short_window_30",
+              "two_haplotypes", "weak_ends", "low_error_deep"}
+
+
+def test_emulated_kernels_match_golden(emu, golden):
+    cor = emu()
+    n = 0
+    for case in golden["cases"]:
+        name = case["name"]
+        if name.startswith("edge_") and name[5:] not in FAST_EDGES:
+            continue
+        if name.startswith("synth_") and any(t in name for t in ("_n20_", "_n60_")):
+            continue                                       # long POA rows: covered on the GPU
+        batch, params = golden_batch(case)
+        c = cor if params == Params() else emu(params)
+        assert_matches_golden(c.correct_windows(batch), case)
+        n += 1
+    assert n >= 20
+
+
+@pytest.mark.parametrize("n_seqs,n_win,seed", [(1, 8, 31), (2, 16, 32), (3, 16, 33), (8, 8, 34), (47, 3, 36), (150, 3, 37)])
+def test_emulated_kernels_match_oracle(emu, oracle, n_seqs, n_win, seed):
+    batch = synth_windows(n_win, n_seqs, seed=seed)
+    cor = emu()
+    got = cor.correct_windows(batch)
+    want, _ = oracle.correct_windows(batch, threads=4)
+    assert_same(got, want, f"emulated CUDA path vs oracle N={n_seqs}")
+    oracle.lib.oracle_reset_counters()
+    oracle.correct_windows(batch, threads=1)
+    oc, gc = oracle.counters(), cor.counters()
+    for key in ("windows", "sequences", "bases", "anchors", "regions", "poa_graphs", "alignments", "dp_cells", "dp_pred_cells",
+                "solid_kmers", "consensus_bytes", "fallback_windows"):
+        assert gc[key] == oc[key], key
+
+
+def test_emulated_chunking_and_staged_calls_do_not_change_results(emu, oracle):
+    batch = concat([synth_windows(5, 8, seed=41), synth_windows(4, 3, seed=42), synth_windows(2, 47, seed=43)])
+    want, _ = oracle.correct_windows(batch, threads=4)
+    one = emu()
+    assert_same(one.correct_windows(batch), want, "one chunk")
+    many = emu(chunk_max_windows=3)
+    many.upload(batch)
+    many.run()
+    assert_same(many.download(), want, "chunks of 3 windows, staged calls")
+    many.run()                                              # re-running a resident batch is idempotent
+    assert_same(many.download(), want, "second run")
+
+
+def test_emulated_poa_tier_overflow_requeues_jobs(emu, oracle):
+    batch = synth_windows(3, 8, seed=44)
+    want, _ = oracle.correct_windows(batch, threads=4)
+    tiny = emu(poa_tier0_nodes=64, poa_tier0_cells=4096, poa_tier1_nodes=512, poa_tier1_cells=1 << 18)
+    assert_same(tiny.correct_windows(batch), want, "jobs re-queued to the larger scratch tiers")
+    with pytest.raises(ConsentError) as e:
+        emu(poa_tier0_nodes=64, poa_tier0_cells=4096, poa_tier1_nodes=128, poa_tier1_cells=8192,
+            poa_tier2_nodes=256, poa_tier2_cells=16384).correct_windows(batch)
+    assert e.value.code == -6
+
+
+def test_emulated_errors(emu):
+    cor = emu()
+    with pytest.raises(ConsentError) as e:
+        cor.correct_windows(Batch.from_piles([["ACGTNACGTACGTAGCTAGCTAGCATCGATCGATCGA", "ACGTACGTACGTAGCTAGCTAGC"]]))
+    assert e.value.code == -5                               # CG_ERR_BAD_BASE
+    with pytest.raises(ConsentError) as e:
+        cor.run() if False else emu().run()
+    assert e.value.code == -7                               # CG_ERR_STATE: run before upload
+    with pytest.raises(ConsentError) as e:
+        cor.correct_windows(Batch.from_piles([["A" * 7000, "ACGT"]]))
+    assert e.value.code == -6                               # CG_ERR_CAPACITY: stated limit

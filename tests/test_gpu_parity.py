@@ -1,0 +1,140 @@
+"""GPU suite (-m gpu): the CUDA path, called through the C ABI (libconsent_b200.so), against the oracle on the same
+seeded inputs, against the committed golden vectors (reference outputs), and — at sizes the oracle cannot cover in
+seconds — through size-independent properties.  Bit-exact everywhere: the path is integer/byte work."""
+import numpy as np
+import pytest
+
+from consent_b200._ffi import Batch, Params
+from consent_b200.engine import ConsentError
+from consent_b200.synth import synth_windows
+from tests.cases import concat, edge_batch, edge_piles
+from tests.helpers import assert_matches_golden, assert_same, golden_batch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_gpu_matches_golden(gpu, golden):
+    cor = gpu()
+    for case in golden["cases"]:
+        batch, params = golden_batch(case)
+        c = cor if params == Params() else gpu(params)
+        assert_matches_golden(c.correct_windows(batch), case)
+
+
+@pytest.mark.parametrize("n_seqs,n_win,seed,profile", [
+    (1, 64, 51, "PB"), (2, 128, 52, "PB"), (3, 128, 53, "PB"), (5, 128, 54, "PB"), (8, 256, 55, "PB"),
+    (20, 400, 56, "PB"), (47, 96, 57, "PB"), (150, 64, 58, "PB"), (20, 128, 59, "ONT"), (60, 48, 60, "ONT")])
+def test_gpu_matches_oracle(gpu, oracle, n_seqs, n_win, seed, profile):
+    batch = synth_windows(n_win, n_seqs, seed=seed, profile=profile)
+    cor = gpu()
+    got = cor.correct_windows(batch)
+    want, _ = oracle.correct_windows(batch, threads=32)
+    assert_same(got, want, f"CUDA path vs oracle N={n_seqs} {profile}")
+    oracle.lib.oracle_reset_counters()
+    oracle.correct_windows(batch, threads=32)
+    oc, gc = oracle.counters(), cor.counters()
+    for key in oc:
+        assert gc[key] == oc[key], key                      # the inputs of the algorithmic-bytes model agree too
+
+
+def test_gpu_matches_oracle_on_edge_cases(gpu, oracle):
+    for seed in (1, 2, 3):
+        batch = edge_batch(seed)
+        want, _ = oracle.correct_windows(batch, threads=32)
+        assert_same(gpu().correct_windows(batch), want, f"edge cases seed {seed}")
+
+
+def test_gpu_parameter_variants(gpu, oracle):
+    batch = synth_windows(48, 12, seed=61)
+    for p in (Params(mer_size=7), Params(mer_size=5, solid_thresh=2), Params(mer_size=4), Params(solid_thresh=8),
+              Params(common_kmers=3), Params(min_anchors=50), Params(min_anchors=10), Params(mer_size=2, solid_thresh=1)):
+        want, _ = oracle.correct_windows(batch, p, threads=32)
+        assert_same(gpu(p).correct_windows(batch), want, str(p))
+
+
+def test_gpu_mixed_depth_batch_and_chunking(gpu, oracle):
+    batch = concat([synth_windows(40, 8, seed=62), synth_windows(30, 3, seed=63), synth_windows(6, 150, seed=64),
+                    synth_windows(20, 20, seed=65), edge_batch(4)])
+    want, _ = oracle.correct_windows(batch, threads=32)
+    assert_same(gpu().correct_windows(batch), want, "one chunk")
+    small = gpu(chunk_max_windows=7)
+    small.upload(batch)
+    small.run()
+    assert_same(small.download(), want, "chunks of 7 windows, staged calls")
+    small.run()
+    assert_same(small.download(), want, "re-run of a resident batch")
+
+
+def test_gpu_poa_tier_overflow(gpu, oracle):
+    batch = concat([synth_windows(16, 8, seed=66), Batch.from_piles([p for n, p in edge_piles(5) if "no_anchor" in n or "outlier" in n])])
+    want, _ = oracle.correct_windows(batch, threads=32)
+    tiny = gpu(poa_tier0_nodes=64, poa_tier0_cells=4096, poa_tier1_nodes=1024, poa_tier1_cells=1 << 20)
+    assert_same(tiny.correct_windows(batch), want, "jobs re-queued to larger scratch tiers")
+
+
+def test_gpu_errors(gpu):
+    cor = gpu()
+    with pytest.raises(ConsentError) as e:
+        cor.correct_windows(Batch.from_piles([["ACGTNACGTACGTAGCTAGCTAGCATCGATCGATCGA", "ACGTACGTACGTAGCTAGCTAGC"]]))
+    assert e.value.code == -5
+    with pytest.raises(ConsentError) as e:
+        gpu().run()
+    assert e.value.code == -7
+    with pytest.raises(ConsentError) as e:
+        cor.correct_windows(Batch.from_piles([["A" * 7000, "ACGT"]]))
+    assert e.value.code == -6
+    # the context stays usable after an error
+    b = synth_windows(4, 5, seed=67)
+    assert cor.correct_windows(b).n_windows == 4
+
+
+# ---- BASELINE-size shapes: properties that do not need the oracle on every window --------------------------------
+
+def test_gpu_config2_shape_properties(gpu, oracle):
+    """10k x 20 (config 2) is too slow for the oracle in a test; check 2 000 windows by properties + a 200-window
+    oracle sample + invariance of the digest under re-chunking and under a permutation of the windows."""
+    W = 2000
+    batch = synth_windows(W, 20, seed=42)
+    cor = gpu()
+    res = cor.correct_windows(batch)
+    assert res.n_windows == W
+    sample = batch.slice(900, 1100)
+    want, _ = oracle.correct_windows(sample, threads=32)
+    got = gpu().correct_windows(sample)
+    assert_same(got, want, "windows 900..1100 of the config-2 stream")
+    for w in range(0, 200, 17):
+        assert res.consensus(900 + w) == want.consensus(w)                     # a window's result does not depend on its batch
+        assert res.solid(900 + w) == want.solid(w)
+    assert gpu(chunk_max_windows=333).correct_windows(batch).digest() == res.digest()
+    # domain properties: solid lists sorted, counts >= solid; consensus alphabet; status; length near the truth (500)
+    for w in range(0, W, 97):
+        s = res.solid(w)
+        ks = [k for k, _ in s]
+        assert ks == sorted(ks) and len(set(ks)) == len(ks) and all(c >= 4 for _, c in s)
+        cons = res.consensus(w)
+        assert set(cons) <= set("ACGTacgt") and 400 < len(cons) < 650
+    assert int(res.status.sum()) == 0
+    # permutation: reversed window order -> reversed results
+    rev = Batch.from_piles([batch.pile(w) for w in range(W - 1, W - 201, -1)])
+    rres = gpu().correct_windows(rev)
+    for i in range(200):
+        assert rres.consensus(i) == res.consensus(W - 1 - i)
+
+
+def test_gpu_config3_shape_properties(gpu, oracle):
+    """100k x 150 (config 3): 1 000 windows here; 24 of them against the oracle."""
+    W = 1000
+    batch = synth_windows(W, 150, seed=42)
+    res = gpu().correct_windows(batch)
+    sample = batch.slice(500, 524)
+    want, _ = oracle.correct_windows(sample, threads=32)
+    for w in range(24):
+        assert res.consensus(500 + w) == want.consensus(w)
+        assert res.solid(500 + w) == want.solid(w)
+        assert res.status[500 + w] == want.status[w]
+    assert gpu(chunk_max_windows=128).correct_windows(batch).digest() == res.digest()
+    # self-consistency: correcting a pile whose reads are all the consensus returns the consensus, fully solid
+    cons = [res.consensus(w).upper() for w in range(0, 40)]
+    again = gpu().correct_windows(Batch.from_piles([[c] * 6 for c in cons]))
+    for i, c in enumerate(cons):
+        assert again.consensus(i) == c

@@ -1,0 +1,67 @@
+"""CPU suite, part 4: the multi-GPU host logic (window sharding + the final ordered gather), world_size 2 over gloo.
+Each rank computes its block with the oracle standing in for its GPU (this test checks the plumbing, not the kernels)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+from consent_b200.shard import shard_by_bases, shard_range
+from consent_b200.synth import synth_windows
+from tests.cases import concat
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import torch.distributed as dist
+from consent_b200.shard import gather_results, shard_range
+from consent_b200.synth import synth_windows
+from tests.refs import Oracle
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+rank = dist.get_rank()
+batch = synth_windows(11, 5, seed=71)
+w0, w1 = shard_range(batch.n_windows, rank, 2)
+orc = Oracle()
+local, _ = orc.correct_windows(batch.slice(w0, w1))
+full = gather_results(local)
+if rank == 0:
+    want, _ = orc.correct_windows(batch)
+    assert full.equals(want), "gathered results differ from the single-process run"
+    print("GATHER_OK", full.n_windows)
+else:
+    assert full is None
+dist.barrier()
+dist.destroy_process_group()
+"""
+
+
+def test_shard_ranges_cover_everything():
+    for n in (0, 1, 7, 100, 100001):
+        for world in (1, 2, 3, 8):
+            blocks = [shard_range(n, r, world) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in blocks]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_shard_by_bases_balances_mixed_depths():
+    batch = concat([synth_windows(20, 3, seed=1), synth_windows(4, 60, seed=2)])
+    blocks = shard_by_bases(batch, 4)
+    assert blocks[0][0] == 0 and blocks[-1][1] == batch.n_windows
+    assert all(blocks[i][1] == blocks[i + 1][0] for i in range(3))
+    loads = [int(batch.seq_off[int(batch.win_seq_begin[b])]) - int(batch.seq_off[int(batch.win_seq_begin[a])]) for a, b in blocks]
+    assert max(loads) <= 0.5 * sum(loads)
+
+
+def test_gather_world_size_2_gloo(entry, tmp_path):
+    port = 29500 + os.getpid() % 2000
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER.format(root=ROOT, port=port))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+             for r in range(2)]
+    outs = [p.communicate(timeout=300)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(outs)
+    assert "GATHER_OK 11" in outs[0]
