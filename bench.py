@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""bench.py — corrected windows/s of the CONSENT per-window hot path on B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--windows W] [--seqs N]
+
+A step = one pass of the hot path over one batch of synthetic windows (default: the configuration the metric is
+quoted on, BASELINE.json configs[2]: 500-base windows x 150 sequences, PacBio 15 % profile, seed 42; the batch is
+a slice of that 100k-window stream sized by --windows).  Prints ONE JSON line (rank 0).
+
+  value        windows/s with the batch resident in HBM (cg_run timed with CUDA events on the library's stream)
+  e2e          the same through the reference-facing call cg_correct_windows with HOST (pinned) buffers:
+               H2D of the piles, every kernel, D2H of consensus + solid k-mers inside the timed region
+  roofline     dominant kernel: algorithmic bytes per launch / its CUDA-event time, against MEASURED_PEAKS.json
+  cpu_baseline the reference's own CPU code (oracle/_ref) on this box's host cores, bounded sample of the same stream
+  --impl reference : times that CPU implementation as the arm itself.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOAD = "config3: synthetic 500 bp windows x 150 seqs/pile (maxMSA cap), PB 15% error, seed 42"
+METRIC = "corrected windows/sec"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_batch(n_windows: int, n_seqs: int, first_window: int, pinned: bool):
+    """Slice [first_window, first_window + n_windows) of the seed-42 PB stream; arrays in pinned host memory if asked."""
+    from consent_b200._ffi import Batch
+    from consent_b200.synth import synth_windows
+    b = synth_windows(n_windows, n_seqs, seed=42, profile="PB", first_window=first_window, threads=min(host_cores(), 64))
+    if pinned:
+        import torch
+        keep = []
+        arrs = []
+        for a in (b.win_seq_begin, b.seq_off, b.bases):
+            t = torch.from_numpy(a.view(np.uint8).reshape(-1).copy()).pin_memory()
+            keep.append(t)
+            arrs.append(t.numpy().view(a.dtype))
+        nb = Batch.__new__(Batch)
+        nb.win_seq_begin, nb.seq_off, nb.bases = arrs
+        nb._keep = keep
+        return nb
+    return b
+
+
+def cpu_reference(batch, threads: int):
+    """-> (checker, kind): oracle/_ref (the reference itself) when it loads on this host, else the oracle port."""
+    from tests.refs import Oracle, Reference, ref_library_path
+    import __graft_entry__ as g
+    g.build_oracle()
+    if ref_library_path() is not None:
+        return Reference(), "reference"
+    return Oracle(), "port"
+
+
+def time_cpu(checker, batch, threads: int, budget_s: float = 15.0):
+    """Bounded sample: grow the sample until one timed call takes >= budget/3, report windows/s of the last call."""
+    n = min(batch.n_windows, max(threads, 8))
+    best = None
+    while True:
+        sample = batch.slice(0, n)
+        _, sec = checker.correct_windows(sample, threads=threads, with_status=False)
+        best = (n, sec)
+        if sec >= budget_s / 3 or n >= batch.n_windows:
+            break
+        n = min(batch.n_windows, max(n * 2, int(n * (budget_s / 2) / max(sec, 1e-3))))
+    n, sec = best
+    return n / sec, n, sec
+
+
+def algorithmic_bytes(counters: dict, n_occ: int) -> dict:
+    """Per-stage algorithmic bytes of one pass."""
+    b_in = (counters["bases"] + 3) // 4 + 8 * counters["sequences"]
+    b_out = counters["consensus_bytes"] + 8 * counters["solid_kmers"]
+    b_dp = 2 * (counters["dp_cells"] + counters["dp_pred_cells"])
+    b_idx = 8 * n_occ
+    return {"in": b_in, "out": b_out, "poa": b_dp, "index": b_idx, "window_total": b_in + b_out + b_dp}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=("b200", "reference"))
+    ap.add_argument("--windows", type=int, default=int(os.environ.get("CG_BENCH_WINDOWS", "20000")), help="windows per step and per GPU")
+    ap.add_argument("--seqs", type=int, default=150)
+    ap.add_argument("--cpu-budget", type=float, default=15.0)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cores = host_cores()
+    config = {"workload": WORKLOAD, "windows_per_step_per_gpu": args.windows, "seqs_per_window": args.seqs, "window_len": 500,
+              "k": 9, "solid": 4, "commonKMers": 8, "minAnchors": 2,
+              "l2": "inputs larger than L2 (>= 1.5 GB of piles per step, 126 MB L2)", "parallelism": f"windows sharded x{world}"}
+
+    import __graft_entry__ as g
+    g.build_host()
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        batch = make_batch(min(args.windows, 4096), args.seqs, 0, pinned=False)
+        checker, kind = cpu_reference(batch, cores)
+        for _ in range(max(args.warmup, 1)):
+            checker.correct_windows(batch.slice(0, min(batch.n_windows, cores)), threads=cores, with_status=False)
+        per_step_budget = max(2.0, min(20.0, 90.0 / max(args.steps, 1)))
+        tot_w, tot_s, n = 0, 0.0, 0
+        for _ in range(args.steps):
+            wps, n, sec = time_cpu(checker, batch, cores, per_step_budget)
+            tot_w += n; tot_s += sec
+        value = tot_w / tot_s
+        out = {"impl": "reference", "metric": METRIC, "value": value, "unit": "windows/s", "n_gpus": args.gpus, "steps": args.steps,
+               "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / args.steps, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "int16/u8", "data": "synthetic", "config": config,
+               "cpu_baseline": {"value": value, "unit": "windows/s", "cores": cores, "kind": kind,
+                                "sample": f"{n} windows x {args.seqs} seqs per step (first windows of the same stream)"},
+               "e2e": {"value": value, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(out), flush=True)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — this path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    g.build_cuda()
+    from consent_b200.engine import Corrector
+    from consent_b200.shard import gather_results
+
+    t0 = time.time()
+    batch = make_batch(args.windows, args.seqs, rank * args.windows, pinned=True)       # weak scaling: every rank its own slice
+    n_occ = int(np.maximum(np.diff(batch.seq_off.astype(np.int64)) - 8, 0).sum())
+    log(f"[rank {rank}] generated {batch.n_windows} windows, {batch.n_bases / 1e9:.2f} GB of bases in {time.time() - t0:.1f}s")
+
+    cor = Corrector(device=local_rank)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- HBM-resident arm
+    cor.upload(batch)
+    for _ in range(args.warmup):
+        cor.run()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    dev_ms, stage_acc, launches = 0.0, {}, 0
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        cor.run()
+        dev_ms += cor.run_ms()
+        for k, v in cor.stage_ms().items():
+            stage_acc[k] = stage_acc.get(k, 0.0) + v["ms"]
+            launches += v["launches"]
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - wall0)
+    clocks = sampler.stop()
+    counters = cor.counters()
+    t = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, wall_ms = float(t[0]), float(t[1])
+    value = world * args.windows * args.steps / (dev_ms / 1e3)
+
+    # ---- end-to-end arm: host buffers in, host buffers out (+ the ordered gather to rank 0 when sharded)
+    res = None
+    for _ in range(max(1, args.warmup - 1)):
+        res = cor.correct_windows(batch)
+    barrier()
+    e0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = cor.correct_windows(batch)
+        if world > 1:
+            gather_results(res)
+    barrier()
+    e2e_s = time.perf_counter() - e0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t[0])
+    h2d = int(batch.n_bases + batch.seq_off.nbytes + batch.win_seq_begin.nbytes)
+    d2h = int(res.cons.nbytes + res.status.nbytes + res.cons_off.nbytes + res.solid_off.nbytes + res.solid_kmer.nbytes + res.solid_count.nbytes)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    ab = algorithmic_bytes(counters, n_occ)
+    stage_avg = {k: v / args.steps for k, v in stage_acc.items()}
+    kernel_stage = {"index": "k_index", "poa": "k_poa", "chain": "k_chain", "split": "k_split", "polish": "k_polish"}
+    dom = max(kernel_stage, key=lambda k: stage_avg.get(k, 0.0))
+    dom_bytes = {"index": ab["index"], "poa": ab["poa"], "chain": ab["index"], "split": ab["in"], "polish": ab["out"]}[dom]
+    n_launch = max(1, cor.stage_ms()[dom]["launches"])
+    achieved = dom_bytes / n_launch / (stage_avg[dom] / n_launch / 1e3) / 1e9 if stage_avg.get(dom) else 0.0
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(kernel_stage[dom])
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": kernel_stage[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": dom_bytes / n_launch, "launches_per_step": n_launch,
+                "whole_path_GBps": ab["window_total"] / (dev_ms / args.steps / 1e3) / 1e9,
+                "stage_ms_per_step": {k: round(v, 3) for k, v in stage_avg.items()}}
+
+    # ---- CPU baseline on this box's host cores (rank 0, N=1 only)
+    cpu = None
+    if world == 1:
+        try:
+            checker, kind = cpu_reference(batch, cores)
+            wps, n, sec = time_cpu(checker, batch, cores, args.cpu_budget)
+            cpu = {"value": wps, "unit": "windows/s", "cores": cores, "kind": kind,
+                   "sample": f"first {n} windows of the same batch, {sec:.1f} s, all host threads"}
+            # the sample doubles as a parity spot-check of this very run
+            want, _ = checker.correct_windows(batch.slice(0, min(n, 64)), threads=cores)
+            got = [res.consensus(w) for w in range(want.n_windows)]
+            cpu["parity_spot_check"] = all(got[w] == want.consensus(w) for w in range(want.n_windows))
+        except Exception as e:  # the checker is optional for the bench line
+            cpu = {"value": None, "unit": "windows/s", "cores": cores, "kind": "unavailable", "sample": repr(e)}
+
+    out = {"metric": METRIC, "value": value, "unit": "windows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "int16/u8", "data": "synthetic", "config": config, "clocks": clocks,
+           "e2e": {"value": world * args.windows * args.steps / e2e_s, "unit": "windows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+           "gpu_launches": launches, "wall_ms_per_step": wall_ms / args.steps,
+           "roofline": roofline, "cpu_baseline": cpu,
+           "counters_per_step": counters}
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -61,6 +61,7 @@ struct CgRegion {
     u32 n;            // sequences kept in the region
     u32 read, start, len;   // first kept segment (the consensus itself for CG_REG_COPY)
     u32 sum_len;      // total bases of the kept segments (bounds the POA graph and the consensus)
+    u32 max_len;      // longest kept segment (routes the job to a scratch tier)
     u32 arena_off;    // CG_REG_POA: offset of the region consensus inside the window's arena slice
     u32 cons_len;     // CG_REG_POA: length of the region consensus (written by k_poa)
 };
@@ -90,7 +91,7 @@ struct CgPoaScratch {     // one per resident POA warp (global memory, L1/L2 res
     u64 hcap;             // score-matrix cells
     u8* letter; u8* in0; u8* nal; u8* leader; u8* marks; u8* check;
     u16* nseq; u16* aligned; u16* rank_of; u16* r2n;
-    u32* in_head; u32* in_tail;
+    u32* in_head; u32* in_tail; u32* rdesc;
     u16* e_pred; u32* e_next;
     u16* stack;
     i32* aln_node; i32* aln_pos;
@@ -124,9 +125,10 @@ struct CgChunk {
     u8* arena;                    // region consensuses
     u8* fin;                      // per window: 3 slices of (2*n_bases+64) bytes: consensus, temp, path
     u32* visited;                 // per window ceil(solid_cap/32) words (bit per solid k-mer)
-    // POA job queue
-    u32* job_count;               // [0] jobs appended, [1] next job to take, [2..3] overflow list of the next tier
-    uint2* jobs; uint2* jobs_next;
+    // POA job queues, one per scratch tier: small (shared memory), medium (graph in shared memory), global.
+    // qctl[4*t + 0] = jobs in queue t, [4*t + 1] = next job to take.  A job that outgrows tier t is appended to t+1.
+    u32* qctl;
+    uint2* jobs_s; uint2* jobs_m; uint2* jobs_g;
     // status
     u32* flags;
     CgCountersDev* counters;

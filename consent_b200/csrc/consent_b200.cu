@@ -52,9 +52,9 @@ struct ChunkPlan {
 };
 
 struct PoaTier {
-    u32 vcap, ecap, lcap;
-    u64 hcap;
-    u32 warps;
+    u32 vcap = 0, ecap = 0, lcap = 0;   // graph arrays in global memory (0: the kernel keeps them in shared memory)
+    u64 hcap = 0;                       // score matrix + alignment in global memory (0: shared memory)
+    u32 warps = 0;
     DevBuf mem, desc;
     bool ready = false;
 };
@@ -69,7 +69,6 @@ struct cg_handle {
     // options
     size_t chunk_budget = (size_t)6 << 30;
     u32 chunk_max_windows = 16384;
-    u32 poa_warps_per_sm[3] = {16, 1, 0};           // tier 2: fixed 8 warps
     // batch (device) + host copies of the offsets for planning
     u32 W = 0;
     u64 n_seqs = 0, n_bases = 0;
@@ -80,13 +79,15 @@ struct cg_handle {
     bool uploaded = false, ran = false;
     // chunk workspaces
     DevBuf pwords, ptags, win, offs, solid_k, solid_c, slot_tpos, slot_kmer, anchors, chain, rel, pos, regions, arena, fin, visited;
-    DevBuf jobs, jobs_next, ctl, off_fin, out_off;
-    PoaTier tier[3];
+    DevBuf jobs_s, jobs_m, jobs_g, jobs_x, ctl, off_fin, out_off;
+    PoaTier tier_s, tier_m, tier[3];     // shared-memory small / medium tiers, then global tiers of growing size
     // batch outputs (device, dense)
     DevBuf o_cons, o_sk, o_sc, o_status, o_len, o_nsol;
     u64 o_cons_n = 0, o_solid_n = 0;
     // instrumentation
     float stage_ms[CG_N_STAGES]{};
+    float run_ms = 0;             // whole cg_run on the stream (CUDA events)
+    cudaEvent_t ev_run[2]{};
     u32 stage_launches[CG_N_STAGES]{};
     cg_counters counters{};
     u32* h_ctl = nullptr;        // pinned: flags + queue control + totals
@@ -107,8 +108,8 @@ std::string g_create_err;
 
 inline u64 round_up(u64 v, u64 m) { return (v + m - 1) / m * m; }
 
-// ctl layout (u32 words, device): [0] flags, [4..7] tier-0 queue {njobs,next,overflow,_}, [8..11] tier 1, [12..15] tier 2
-enum { CTL_FLAGS = 0, CTL_Q0 = 4, CTL_Q1 = 8, CTL_Q2 = 12, CTL_WORDS = 16 };
+// ctl layout (u32 words, device): [0] flags, [4 + 4t ..] queue t {jobs, next, -, -}: t = 0 small, 1 medium, 2..4 global tiers
+enum { CTL_FLAGS = 0, CTL_Q = 4, CTL_WORDS = 32 };
 // offs layout (u64 arrays of nwin+1): solid, slot, pos, reg, arena
 // out_off layout: cons_off[nwin+1], solid_off[nwin+1]
 
@@ -149,19 +150,18 @@ int plan_chunks(cg_handle* h) {
     return CG_OK;
 }
 
-int ensure_tier(cg_handle* h, int t) {
-    PoaTier& T = h->tier[t];
+int ensure_tier(cg_handle* h, PoaTier& T) {
     if (T.ready) return CG_OK;
     const u32 ncap = CG_N_MAX + 1;
-    const u32 scap = 2 * (T.ecap + 4 * T.vcap);
-    const u32 alncap = T.vcap + T.lcap + 2;
+    const u32 scap = T.vcap ? 2 * (T.ecap + 4 * T.vcap) : 0;
+    const u32 alncap = T.hcap ? (T.vcap ? T.vcap : CgPoaTierM::VCAP) + T.lcap + 2 : 0;
     // per-warp layout (all sub-arrays 16-byte aligned)
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t at = o; o += round_up(bytes, 16); return at; };
     const size_t o_letter = take(T.vcap), o_in0 = take(T.vcap), o_nal = take(T.vcap), o_leader = take(T.vcap), o_marks = take(T.vcap),
                  o_check = take(T.vcap), o_nseq = take(2 * (size_t)T.vcap), o_aligned = take(6 * (size_t)T.vcap),
                  o_rank = take(2 * (size_t)T.vcap), o_r2n = take(2 * (size_t)T.vcap), o_ih = take(4 * (size_t)T.vcap),
-                 o_it = take(4 * (size_t)T.vcap), o_ep = take(2 * (size_t)T.ecap), o_en = take(4 * (size_t)T.ecap),
+                 o_it = take(4 * (size_t)T.vcap), o_rd = take(4 * (size_t)T.vcap), o_ep = take(2 * (size_t)T.ecap), o_en = take(4 * (size_t)T.ecap),
                  o_stack = take(2 * (size_t)scap), o_an = take(4 * (size_t)alncap), o_ap = take(4 * (size_t)alncap),
                  o_sr = take(2 * (size_t)ncap), o_ss = take(2 * (size_t)ncap), o_sl = take(2 * (size_t)ncap), o_H = take(2 * T.hcap);
     const size_t per_warp = round_up(o, 256);
@@ -174,7 +174,8 @@ int ensure_tier(cg_handle* h, int t) {
         s.vcap = T.vcap; s.ecap = T.ecap; s.scap = scap; s.alncap = alncap; s.ncap = ncap; s.hcap = T.hcap;
         s.letter = b + o_letter; s.in0 = b + o_in0; s.nal = b + o_nal; s.leader = b + o_leader; s.marks = b + o_marks; s.check = b + o_check;
         s.nseq = (u16*)(b + o_nseq); s.aligned = (u16*)(b + o_aligned); s.rank_of = (u16*)(b + o_rank); s.r2n = (u16*)(b + o_r2n);
-        s.in_head = (u32*)(b + o_ih); s.in_tail = (u32*)(b + o_it); s.e_pred = (u16*)(b + o_ep); s.e_next = (u32*)(b + o_en);
+        s.in_head = (u32*)(b + o_ih); s.in_tail = (u32*)(b + o_it); s.rdesc = (u32*)(b + o_rd);
+        s.e_pred = (u16*)(b + o_ep); s.e_next = (u32*)(b + o_en);
         s.stack = (u16*)(b + o_stack); s.aln_node = (i32*)(b + o_an); s.aln_pos = (i32*)(b + o_ap);
         s.seg_read = (u16*)(b + o_sr); s.seg_start = (u16*)(b + o_ss); s.seg_len = (u16*)(b + o_sl); s.H = (i16*)(b + o_H);
     }
@@ -208,7 +209,8 @@ int run_chunk(cg_handle* h, const ChunkPlan& cp, std::vector<StageSpan>& spans, 
     CK(h->regions.ensure(cp.reg_tot * sizeof(CgRegion) + 16));
     CK(h->arena.ensure(cp.arena_tot + 16));
     CK(h->visited.ensure((cp.solid_tot / 32 + nwin + 2) * 4));
-    CK(h->jobs.ensure(cp.reg_tot * sizeof(uint2) + 16)); CK(h->jobs_next.ensure(cp.reg_tot * sizeof(uint2) + 16));
+    CK(h->jobs_s.ensure(cp.reg_tot * sizeof(uint2) + 16)); CK(h->jobs_m.ensure(cp.reg_tot * sizeof(uint2) + 16));
+    CK(h->jobs_g.ensure(cp.reg_tot * sizeof(uint2) + 16)); CK(h->jobs_x.ensure(cp.reg_tot * sizeof(uint2) + 16));
     CK(h->off_fin.ensure(sizeof(u64) * (nwin + 1)));
     CK(h->out_off.ensure(sizeof(u64) * 2 * (nwin + 1)));
 
@@ -226,7 +228,7 @@ int run_chunk(cg_handle* h, const ChunkPlan& cp, std::vector<StageSpan>& spans, 
     c.chain = h->chain.as<u16>(); c.rel = h->rel.as<u32>(); c.pos = h->pos.as<u16>();
     c.regions = h->regions.as<CgRegion>(); c.arena = h->arena.as<u8>(); c.fin = nullptr; c.visited = h->visited.as<u32>();
     u32* ctl = h->ctl.as<u32>();
-    c.job_count = ctl + CTL_Q0; c.jobs = h->jobs.as<uint2>(); c.jobs_next = h->jobs_next.as<uint2>();
+    c.qctl = ctl + CTL_Q; c.jobs_s = h->jobs_s.as<uint2>(); c.jobs_m = h->jobs_m.as<uint2>(); c.jobs_g = h->jobs_g.as<uint2>();
     c.flags = ctl + CTL_FLAGS;
     c.counters = (CgCountersDev*)(ctl + CTL_WORDS);
     u64* off_fin = h->off_fin.as<u64>();
@@ -235,7 +237,7 @@ int run_chunk(cg_handle* h, const ChunkPlan& cp, std::vector<StageSpan>& spans, 
 
     // ---- stage 0: plan, offsets, pack
     span_begin(CG_STAGE_PACK);
-    CK(cudaMemsetAsync(ctl + CTL_Q0, 0, 12 * sizeof(u32), st));
+    CK(cudaMemsetAsync(ctl + CTL_Q, 0, 20 * sizeof(u32), st));
     CK(cudaMemsetAsync(h->pwords.as<u32>() + cp.nwords, 0, 16 * 4, st));
     CK(cudaMemsetAsync(h->ptags.as<u32>() + cp.nwords, 0xff, 16 * 4, st));
     CG_LAUNCH(k_plan, (nwin + 127) / 128, 128, 0, st, c);
@@ -262,27 +264,39 @@ int run_chunk(cg_handle* h, const ChunkPlan& cp, std::vector<StageSpan>& spans, 
     h->stage_launches[CG_STAGE_SPLIT] += 1;
     span_end();
 
+    // ---- POA: small (shared memory) -> medium (graph in shared memory) -> global tier 0; each re-queues what it cannot hold
     span_begin(CG_STAGE_POA);
-    { int rc = ensure_tier(h, 0); if (rc) return rc; }
-    CG_LAUNCH(k_poa, (h->tier[0].warps + CG_POA_WARPS_PER_CTA - 1) / CG_POA_WARPS_PER_CTA, CG_POA_THREADS, 0, st, c, h->tier[0].desc.as<CgPoaScratch>(),
-              h->tier[0].warps, (const uint2*)c.jobs, ctl + CTL_Q0, c.jobs_next);
-    h->stage_launches[CG_STAGE_POA] += 1;
+    { int rc = ensure_tier(h, h->tier_s); if (rc) return rc; }
+    { int rc = ensure_tier(h, h->tier_m); if (rc) return rc; }
+    { int rc = ensure_tier(h, h->tier[0]); if (rc) return rc; }
+    u32* q = ctl + CTL_Q;
+    CG_LAUNCH(k_poa_smem<CgPoaTierS>, (h->tier_s.warps + CG_POA_WARPS_PER_CTA - 1) / CG_POA_WARPS_PER_CTA, CG_POA_THREADS,
+              CgPoaSmemLayout<CgPoaTierS>::cta_bytes, st, c, h->tier_s.desc.as<CgPoaScratch>(), h->tier_s.warps, (const uint2*)c.jobs_s, q + 0,
+              c.jobs_m, q + 4);
+    CG_LAUNCH(k_poa_smem<CgPoaTierM>, (h->tier_m.warps + CG_POA_WARPS_PER_CTA - 1) / CG_POA_WARPS_PER_CTA, CG_POA_THREADS,
+              CgPoaSmemLayout<CgPoaTierM>::cta_bytes, st, c, h->tier_m.desc.as<CgPoaScratch>(), h->tier_m.warps, (const uint2*)c.jobs_m, q + 4,
+              c.jobs_g, q + 8);
+    CG_LAUNCH(k_poa, (h->tier[0].warps + CG_POA_WARPS_PER_CTA - 1) / CG_POA_WARPS_PER_CTA, CG_POA_THREADS, 0, st, c,
+              h->tier[0].desc.as<CgPoaScratch>(), h->tier[0].warps, (const uint2*)c.jobs_g, q + 8, h->jobs_x.as<uint2>(), q + 12);
+    h->stage_launches[CG_STAGE_POA] += 3;
     span_end();
 
-    // overflow tiers: need the count on the host
+    // larger global tiers: only if something outgrew tier 0 (needs the count on the host)
     CK(cudaMemcpyAsync(h->h_ctl, ctl, CTL_WORDS * sizeof(u32), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    uint2* q_in = c.jobs_next; uint2* q_out = c.jobs;
+    if (getenv("CG_DEBUG"))
+        fprintf(stderr, "[consent_b200] chunk w0=%u nwin=%u POA jobs: small %u, medium %u (incl. re-queued), global0 %u, global1 %u\n", cp.w0, nwin,
+                h->h_ctl[CTL_Q + 0], h->h_ctl[CTL_Q + 4], h->h_ctl[CTL_Q + 8], h->h_ctl[CTL_Q + 12]);
+    uint2* q_in = h->jobs_x.as<uint2>(); uint2* q_out = c.jobs_g;
     for (int t = 1; t <= 2; ++t) {
-        const u32 over = h->h_ctl[CTL_Q0 + 4 * (t - 1) + 2];
+        const u32 over = h->h_ctl[CTL_Q + 4 * (t + 2)];
         if (!over) break;
         if (h->tier[t].warps == 0) { h->err = "a POA job outgrew the largest enabled scratch tier"; return CG_ERR_CAPACITY; }
-        { int rc = ensure_tier(h, t); if (rc) return rc; }
-        u32 q[4] = {over, 0, 0, 0};
-        CK(cudaMemcpyAsync(ctl + CTL_Q0 + 4 * t, q, sizeof q, cudaMemcpyHostToDevice, st));
+        { int rc = ensure_tier(h, h->tier[t]); if (rc) return rc; }
         span_begin(CG_STAGE_POA);
         CG_LAUNCH(k_poa, (h->tier[t].warps + CG_POA_WARPS_PER_CTA - 1) / CG_POA_WARPS_PER_CTA, CG_POA_THREADS, 0, st, c,
-                  h->tier[t].desc.as<CgPoaScratch>(), h->tier[t].warps, (const uint2*)q_in, ctl + CTL_Q0 + 4 * t, t < 2 ? q_out : (uint2*)nullptr);
+                  h->tier[t].desc.as<CgPoaScratch>(), h->tier[t].warps, (const uint2*)q_in, q + 4 * (t + 2), t < 2 ? q_out : (uint2*)nullptr,
+                  q + 4 * (t + 3));
         h->stage_launches[CG_STAGE_POA] += 1;
         span_end();
         CK(cudaMemcpyAsync(h->h_ctl, ctl, CTL_WORDS * sizeof(u32), cudaMemcpyDeviceToHost, st));
@@ -370,16 +384,23 @@ int cg_create(int device, const cg_params* params, cg_handle** out) {
     }
     bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaMallocHost(&h->h_ctl, 64 * sizeof(u32)) == cudaSuccess;
+    ok = ok && cudaEventCreate(&h->ev_run[0]) == cudaSuccess && cudaEventCreate(&h->ev_run[1]) == cudaSuccess;
     ok = ok && h->ctl.ensure(CTL_WORDS * sizeof(u32) + sizeof(CgCountersDev)) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_index, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CG_IDX_SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin) == cudaSuccess;
     if (!ok) { g_create_err = std::string("CUDA initialisation failed: ") + cudaGetErrorString(cudaGetLastError()); cg_destroy(h); return CG_ERR_CUDA; }
-    // POA scratch tiers: {nodes, edges, max segment length, score-matrix cells, resident warps}
-    h->tier[0].vcap = 2048;  h->tier[0].ecap = 8192;   h->tier[0].lcap = CG_LEN_MAX; h->tier[0].hcap = 256u << 10;
-    h->tier[1].vcap = 16384; h->tier[1].ecap = 65536;  h->tier[1].lcap = CG_LEN_MAX; h->tier[1].hcap = 16u << 20;
-    h->tier[2].vcap = 65535; h->tier[2].ecap = 262144; h->tier[2].lcap = CG_LEN_MAX; h->tier[2].hcap = 256u << 20;
-    h->tier[0].warps = (u32)h->sms * h->poa_warps_per_sm[0];
-    h->tier[1].warps = (u32)h->sms * h->poa_warps_per_sm[1];
+    ok = cudaFuncSetAttribute(k_poa_smem<CgPoaTierS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CgPoaSmemLayout<CgPoaTierS>::cta_bytes) == cudaSuccess &&
+         cudaFuncSetAttribute(k_poa_smem<CgPoaTierM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CgPoaSmemLayout<CgPoaTierM>::cta_bytes) == cudaSuccess;
+    if (!ok) { g_create_err = std::string("CUDA initialisation failed: ") + cudaGetErrorString(cudaGetLastError()); cg_destroy(h); return CG_ERR_CUDA; }
+    // POA scratch tiers.  Shared-memory tiers keep only the segment list (small) or segment list + matrix + alignment (medium)
+    // in global memory; the global tiers keep everything there: {nodes, edges, max segment length, matrix cells, resident warps}.
+    h->tier_s.lcap = CG_LEN_MAX; h->tier_s.warps = (u32)h->sms * 16;
+    h->tier_m.lcap = CG_LEN_MAX; h->tier_m.hcap = 512u << 10; h->tier_m.warps = (u32)h->sms * 8;
+    h->tier[0].vcap = 2048;  h->tier[0].ecap = 8192;   h->tier[0].lcap = CG_LEN_MAX; h->tier[0].hcap = 2u << 20;
+    h->tier[1].vcap = 16384; h->tier[1].ecap = 65536;  h->tier[1].lcap = CG_LEN_MAX; h->tier[1].hcap = 32u << 20;
+    h->tier[2].vcap = 65535; h->tier[2].ecap = 262144; h->tier[2].lcap = CG_LEN_MAX; h->tier[2].hcap = 400u << 20;
+    h->tier[0].warps = (u32)h->sms * 4;
+    h->tier[1].warps = (u32)h->sms;
     h->tier[2].warps = 8;
     *out = h;
     return CG_OK;
@@ -390,10 +411,12 @@ void cg_destroy(cg_handle* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     DevBuf* bufs[] = {&h->d_bases, &h->d_seq_off, &h->d_wsb, &h->pwords, &h->ptags, &h->win, &h->offs, &h->solid_k, &h->solid_c, &h->slot_tpos,
-                      &h->slot_kmer, &h->anchors, &h->chain, &h->rel, &h->pos, &h->regions, &h->arena, &h->fin, &h->visited, &h->jobs,
-                      &h->jobs_next, &h->ctl, &h->off_fin, &h->out_off, &h->o_cons, &h->o_sk, &h->o_sc, &h->o_status, &h->o_len, &h->o_nsol};
+                      &h->slot_kmer, &h->anchors, &h->chain, &h->rel, &h->pos, &h->regions, &h->arena, &h->fin, &h->visited, &h->jobs_s,
+                      &h->jobs_m, &h->jobs_g, &h->jobs_x, &h->ctl, &h->off_fin, &h->out_off, &h->o_cons, &h->o_sk, &h->o_sc, &h->o_status, &h->o_len, &h->o_nsol};
     for (DevBuf* b : bufs) b->release();
     for (auto& t : h->tier) { t.mem.release(); t.desc.release(); }
+    h->tier_s.mem.release(); h->tier_s.desc.release(); h->tier_m.mem.release(); h->tier_m.desc.release();
+    for (auto& e : h->ev_run) if (e) cudaEventDestroy(e);
     if (h->h_ctl) cudaFreeHost(h->h_ctl);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -404,6 +427,9 @@ int cg_set_option(cg_handle* h, const char* key, long long value) {
     const std::string k(key);
     if (k == "chunk_budget_bytes") h->chunk_budget = (size_t)value;
     else if (k == "chunk_max_windows") h->chunk_max_windows = (u32)std::max<long long>(1, value);
+    else if (k == "poa_small_warps") { h->tier_s.warps = (u32)std::max<long long>(1, value); h->tier_s.ready = false; }
+    else if (k == "poa_medium_warps") { h->tier_m.warps = (u32)std::max<long long>(1, value); h->tier_m.ready = false; }
+    else if (k == "poa_medium_cells") { h->tier_m.hcap = (u64)value; h->tier_m.ready = false; }
     else if (k == "poa_tier0_warps") { h->tier[0].warps = (u32)std::max<long long>(1, value); h->tier[0].ready = false; }
     else if (k == "poa_tier1_warps") { h->tier[1].warps = (u32)value; h->tier[1].ready = false; }
     else if (k == "poa_tier2_warps") { h->tier[2].warps = (u32)value; h->tier[2].ready = false; }
@@ -465,6 +491,7 @@ int cg_run(cg_handle* h) {
     memset(h->stage_ms, 0, sizeof h->stage_ms);
     memset(h->stage_launches, 0, sizeof h->stage_launches);
     CK(h->o_status.ensure(h->W + 16)); CK(h->o_len.ensure((h->W + 1) * sizeof(u64))); CK(h->o_nsol.ensure((h->W + 1) * sizeof(u64)));
+    CK(cudaEventRecord(h->ev_run[0], h->stream));
     CK(cudaMemsetAsync(h->ctl.p, 0, CTL_WORDS * sizeof(u32) + sizeof(CgCountersDev), h->stream));
     std::vector<StageSpan> spans;
     static thread_local std::vector<cudaEvent_t> pool;
@@ -475,7 +502,9 @@ int cg_run(cg_handle* h) {
     }
     CgCountersDev cd{};
     CK(cudaMemcpyAsync(&cd, h->ctl.as<u32>() + CTL_WORDS, sizeof cd, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaEventRecord(h->ev_run[1], h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    cudaEventElapsedTime(&h->run_ms, h->ev_run[0], h->ev_run[1]);
     for (const StageSpan& s : spans) { float ms = 0; cudaEventElapsedTime(&ms, s.a, s.b); h->stage_ms[s.stage] += ms; }
     cg_counters& o = h->counters;
     o.windows = h->W; o.sequences = h->n_seqs; o.bases = h->n_bases;
@@ -529,6 +558,12 @@ int cg_correct_windows(cg_handle* h, const cg_batch* in, cg_results* out) {
 int cg_stage_ms(const cg_handle* h, float ms[CG_N_STAGES], uint32_t launches[CG_N_STAGES]) {
     if (!h) return CG_ERR_INVALID_ARG;
     for (int i = 0; i < CG_N_STAGES; ++i) { if (ms) ms[i] = h->stage_ms[i]; if (launches) launches[i] = h->stage_launches[i]; }
+    return CG_OK;
+}
+
+int cg_run_ms(const cg_handle* h, float* ms) {
+    if (!h || !ms) return CG_ERR_INVALID_ARG;
+    *ms = h->run_ms;
     return CG_OK;
 }
 

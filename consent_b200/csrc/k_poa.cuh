@@ -207,7 +207,176 @@ __device__ CG_NOINLINE u32 cg_poa_traceback(const CgPoaScratch& s, CgPoaState& g
     return n;
 }
 
-// One job.  Returns the consensus length, or CG_NONE32 if the tier's scratch was outgrown.
+// Row descriptors: rank r -> letter | in-degree << 8 | (row index of the first predecessor) << 16  (0 = the virtual
+// start row).  Built by all lanes after every topological sort, so that the row loop of the score matrix has no
+// dependent pointer chasing: 32 descriptors are fetched at once and broadcast by shuffle.
+__device__ __forceinline__ void cg_poa_build_rdesc(const CgPoaScratch& s, u32 V) {
+    for (u32 r = cg_lane(); r < V; r += 32) {
+        const u32 node = s.r2n[r];
+        const u32 eh = s.in_head[node];
+        u32 deg = 0;
+        for (u32 ee = eh; ee != CG_NONE32; ee = s.e_next[ee]) ++deg;
+        const u32 p0 = eh == CG_NONE32 ? 0u : (u32)s.rank_of[s.e_pred[eh]] + 1u;
+        s.rdesc[r] = (u32)s.letter[node] | ((deg > 255u ? 255u : deg) << 8) | (p0 << 16);
+    }
+}
+
+// Score matrix of one alignment, rows in rank order, CH chunks of 32 query columns per row held in registers.
+// The common row (one predecessor = the row just computed) needs no loads at all: the left neighbour comes from
+// the adjacent lane.  Other rows read their predecessor rows back from the stored matrix.
+template <int CH>
+__device__ __forceinline__ void cg_poa_dp(const CgPoaScratch& s, u32 V, const u8* seq, u32 L, i32& bv, u32& bi, u32& bj, u64& pred_rows) {
+    const u32 lane = cg_lane(), Wd = L + 1;
+    i16* H = s.H;
+    u8 q[CH];
+    bool act[CH];
+    i32 prev[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+        const u32 j = 1 + 32 * c + lane;
+        act[c] = j < Wd;
+        q[c] = act[c] ? seq[j - 1] : (u8)0;
+        prev[c] = 0;
+    }
+    for (u32 j = lane; j < Wd; j += 32) H[j] = 0;
+    u32 desc_l = 0;
+    __syncwarp();
+    for (u32 r = 0; r < V; ++r) {
+        if ((r & 31u) == 0) desc_l = r + lane < V ? s.rdesc[r + lane] : 0u;
+        const u32 d = __shfl_sync(CG_FULL, desc_l, (int)(r & 31u));
+        const u8 ch = (u8)(d & 0xffu);
+        u32 deg = (d >> 8) & 0xffu;
+        const u32 p0 = d >> 16;
+        i16* row = H + (size_t)(r + 1) * Wd;
+        i32 val[CH];
+        if (deg <= 1 && p0 == r) {                       // predecessor = the row just computed (or the zero row for r = 0)
+#pragma unroll
+            for (int c = 0; c < CH; ++c) {
+                i32 left = __shfl_up_sync(CG_FULL, prev[c], 1);
+                const i32 l31 = c > 0 ? __shfl_sync(CG_FULL, prev[c > 0 ? c - 1 : 0], 31) : 0;
+                if (lane == 0) left = l31;
+                const i32 sc = q[c] == ch ? 5 : -10;
+                const i32 a = left + sc, b = prev[c] - 4;
+                val[c] = a > b ? a : b;
+            }
+        } else if (deg <= 1) {                           // one predecessor elsewhere, or none (virtual row 0)
+            const i16* prow = H + (size_t)p0 * Wd;
+#pragma unroll
+            for (int c = 0; c < CH; ++c) {
+                val[c] = CG_POA_NEG;
+                if (act[c]) {
+                    const u32 j = 1 + 32 * c + lane;
+                    const i32 sc = q[c] == ch ? 5 : -10;
+                    const i32 a = (i32)prow[j - 1] + sc, b = (i32)prow[j] - 4;
+                    val[c] = a > b ? a : b;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < CH; ++c) val[c] = CG_POA_NEG;
+            u32 n = 0;
+            for (u32 ee = s.in_head[s.r2n[r]]; ee != CG_NONE32; ee = s.e_next[ee]) {
+                const i16* prow = H + (size_t)((u32)s.rank_of[s.e_pred[ee]] + 1) * Wd;
+                ++n;
+#pragma unroll
+                for (int c = 0; c < CH; ++c) {
+                    if (act[c]) {
+                        const u32 j = 1 + 32 * c + lane;
+                        const i32 sc = q[c] == ch ? 5 : -10;
+                        const i32 a = (i32)prow[j - 1] + sc, b = (i32)prow[j] - 4;
+                        const i32 m = a > b ? a : b;
+                        val[c] = m > val[c] ? m : val[c];
+                    }
+                }
+            }
+            deg = n;
+        }
+        pred_rows += deg ? deg : 1;
+        // clamp, then the in-row gap term as a max-plus prefix scan over u = H + 4j
+        i32 u[CH];
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            const i32 v0 = val[c] > 0 ? val[c] : 0;
+            u[c] = act[c] ? v0 + 4 * (i32)(1 + 32 * c + lane) : CG_POA_NEG;
+        }
+#pragma unroll
+        for (int dd = 1; dd < 32; dd <<= 1) {
+#pragma unroll
+            for (int c = 0; c < CH; ++c) {
+                const i32 o = __shfl_up_sync(CG_FULL, u[c], dd);
+                if (lane >= (u32)dd) u[c] = o > u[c] ? o : u[c];
+            }
+        }
+        i32 carry = 0;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            u[c] = u[c] > carry ? u[c] : carry;
+            if (c + 1 < CH) carry = __shfl_sync(CG_FULL, u[c], 31);
+            const i32 h = u[c] - 4 * (i32)(1 + 32 * c + lane);
+            prev[c] = h;
+            if (act[c]) {
+                row[1 + 32 * c + lane] = (i16)h;
+                if (h > bv) { bv = h; bi = r + 1; bj = 1 + 32 * c + lane; }
+            }
+        }
+        if (lane == 0) row[0] = 0;
+        __syncwarp();
+    }
+}
+
+// Any length: chunks of 32 columns, every row read back from the stored matrix.
+__device__ CG_NOINLINE void cg_poa_dp_any(const CgPoaScratch& s, u32 V, const u8* seq, u32 L, i32& bv, u32& bi, u32& bj, u64& pred_rows) {
+    const u32 lane = cg_lane(), Wd = L + 1;
+    i16* H = s.H;
+    for (u32 j = lane; j < Wd; j += 32) H[j] = 0;
+    __syncwarp();
+    for (u32 r = 0; r < V; ++r) {
+        const u32 node = s.r2n[r];
+        const u8 ch = s.letter[node];
+        const u32 eh = s.in_head[node];
+        i16* row = H + (size_t)(r + 1) * Wd;
+        if (lane == 0) row[0] = 0;
+        i32 carry = 0;
+        for (u32 jb = 1; jb < Wd; jb += 32) {
+            const u32 j = jb + lane;
+            const bool act = j < Wd;
+            i32 val = CG_POA_NEG;
+            if (act) {
+                const i32 sc = seq[j - 1] == ch ? 5 : -10;
+                if (eh == CG_NONE32) {
+                    val = sc > -4 ? sc : -4;                  // virtual start row of zeros
+                } else {
+                    for (u32 ee = eh; ee != CG_NONE32; ee = s.e_next[ee]) {
+                        const i16* prow = H + (size_t)((u32)s.rank_of[s.e_pred[ee]] + 1) * Wd;
+                        const i32 a = (i32)prow[j - 1] + sc, b = (i32)prow[j] - 4;
+                        const i32 m = a > b ? a : b;
+                        val = m > val ? m : val;
+                    }
+                }
+                val = val > 0 ? val : 0;
+            }
+            i32 u = act ? val + 4 * (i32)j : CG_POA_NEG;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const i32 o = __shfl_up_sync(CG_FULL, u, d);
+                if (lane >= (u32)d) u = o > u ? o : u;
+            }
+            u = u > carry ? u : carry;
+            carry = __shfl_sync(CG_FULL, u, 31);
+            if (act) {
+                const i32 h = u - 4 * (i32)j;
+                row[j] = (i16)h;
+                if (h > bv) { bv = h; bi = r + 1; bj = j; }
+            }
+        }
+        u32 deg = 0;
+        for (u32 ee = eh; ee != CG_NONE32; ee = s.e_next[ee]) ++deg;
+        pred_rows += deg ? deg : 1;
+        __syncwarp();
+    }
+}
+
+// One job.  Returns the consensus length, or CG_NONE32 if the tier's scratch was outgrown (nothing is committed).
 __device__ u32 cg_poa_job(const CgChunk& c, const CgPoaScratch& s, u32 w, u32 rg, u64* cnt_aln, u64* cnt_cells, u64* cnt_pred) {
     const u32 lane = cg_lane();
     const CgWin W = c.win[w];
@@ -235,7 +404,7 @@ __device__ u32 cg_poa_job(const CgChunk& c, const CgPoaScratch& s, u32 w, u32 rg
 
     CgPoaState g;
     g.V = 0; g.E = 0; g.nseqs = 0; g.nrank = 0; g.ovf = false;
-    i16* H = s.H;
+    u64 j_aln = 0, j_cells = 0, j_pred = 0;
 
     for (u32 si = 0; si < nseg; ++si) {
         const u32 L = s.seg_len[si];
@@ -245,58 +414,14 @@ __device__ u32 cg_poa_job(const CgChunk& c, const CgPoaScratch& s, u32 w, u32 rg
         u32 n_aln = 0;
         if (g.V != 0) {
             if ((u64)(g.V + 1) * Wd > s.hcap) return CG_NONE32;
-            // ---- score matrix, row by row in rank order
-            for (u32 j = lane; j < Wd; j += 32) H[j] = 0;
             i32 bv = 0; u32 bi = 0, bj = 0;
             u64 pred_rows = 0;
-            __syncwarp();
-            for (u32 r = 0; r < g.V; ++r) {
-                const u32 node = s.r2n[r];
-                const u8 ch = s.letter[node];
-                const u32 eh = s.in_head[node];
-                i16* row = H + (size_t)(r + 1) * Wd;
-                if (lane == 0) row[0] = 0;
-                i32 carry = 0;
-                for (u32 jb = 1; jb < Wd; jb += 32) {
-                    const u32 j = jb + lane;
-                    const bool act = j < Wd;
-                    i32 val = CG_POA_NEG;
-                    if (act) {
-                        const i32 sc = seq[j - 1] == ch ? 5 : -10;
-                        if (eh == CG_NONE32) {
-                            val = sc > -4 ? sc : -4;                  // virtual start row of zeros
-                        } else {
-                            for (u32 ee = eh; ee != CG_NONE32; ee = s.e_next[ee]) {
-                                const i16* prow = H + (size_t)((u32)s.rank_of[s.e_pred[ee]] + 1) * Wd;
-                                const i32 a = (i32)prow[j - 1] + sc, b = (i32)prow[j] - 4;
-                                const i32 m = a > b ? a : b;
-                                val = m > val ? m : val;
-                            }
-                        }
-                        val = val > 0 ? val : 0;
-                    }
-                    i32 u = act ? val + 4 * (i32)j : CG_POA_NEG;
-#pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        const i32 o = __shfl_up_sync(CG_FULL, u, d);
-                        if (lane >= (u32)d) u = o > u ? o : u;
-                    }
-                    u = u > carry ? u : carry;
-                    carry = __shfl_sync(CG_FULL, u, 31);
-                    if (act) {
-                        const i32 h = u - 4 * (i32)j;
-                        row[j] = (i16)h;
-                        if (h > bv) { bv = h; bi = r + 1; bj = j; }
-                    }
-                }
-                if (lane == 0) {
-                    u32 deg = 0;
-                    for (u32 ee = eh; ee != CG_NONE32; ee = s.e_next[ee]) ++deg;
-                    pred_rows += deg ? deg : 1;
-                }
-                __syncwarp();
-            }
-            if (lane == 0) { *cnt_aln += 1; *cnt_cells += (u64)(g.V + 1) * L; *cnt_pred += pred_rows * L; }
+            if (L <= 32) cg_poa_dp<1>(s, g.V, seq, L, bv, bi, bj, pred_rows);
+            else if (L <= 64) cg_poa_dp<2>(s, g.V, seq, L, bv, bi, bj, pred_rows);
+            else if (L <= 128) cg_poa_dp<4>(s, g.V, seq, L, bv, bi, bj, pred_rows);
+            else if (L <= 256) cg_poa_dp<8>(s, g.V, seq, L, bv, bi, bj, pred_rows);
+            else cg_poa_dp_any(s, g.V, seq, L, bv, bi, bj, pred_rows);
+            j_aln += 1; j_cells += (u64)(g.V + 1) * L; j_pred += pred_rows * L;
             // first cell in row-major order holding the maximum (simd...impl.hpp:828-833, 860-862)
             const u64 key = ((u64)(u32)bv << 32) | ((u64)(0xffffu - bi) << 16) | (u64)(0xffffu - bj);
             const u64 kb = cg_warp_max64(key);
@@ -304,11 +429,13 @@ __device__ u32 cg_poa_job(const CgChunk& c, const CgPoaScratch& s, u32 w, u32 rg
             if (lane == 0 && bv > 0) n_aln = cg_poa_traceback(s, g, seq, Wd, bi, bj);
         }
         // ---- graph update + topological order (sequential)
+        const u32 V0 = g.V, E0 = g.E;
         if (lane == 0 && !g.ovf) cg_poa_add_alignment(s, g, n_aln, seq, L);
         g.V = __shfl_sync(CG_FULL, g.V, 0); g.E = __shfl_sync(CG_FULL, g.E, 0);
         g.nseqs = __shfl_sync(CG_FULL, g.nseqs, 0);
         g.ovf = __shfl_sync(CG_FULL, (u32)g.ovf, 0) != 0;
         if (g.ovf) return CG_NONE32;
+        if (g.V == V0 && g.E == E0) { __syncwarp(); continue; }      // same nodes, same edges, same aligned sets: same order
         for (u32 i = lane; i < g.V; i += 32) { s.marks[i] = 0; s.check[i] = 1; }
         __syncwarp();
         if (lane == 0) cg_poa_toposort(s, g);
@@ -317,6 +444,8 @@ __device__ u32 cg_poa_job(const CgChunk& c, const CgPoaScratch& s, u32 w, u32 rg
         if (g.ovf) return CG_NONE32;
         __syncwarp();
         for (u32 i = lane; i < g.V; i += 32) s.rank_of[s.r2n[i]] = (u16)i;
+        __syncwarp();
+        cg_poa_build_rdesc(s, g.V);
         __syncwarp();
     }
 
@@ -351,16 +480,14 @@ __device__ u32 cg_poa_job(const CgChunk& c, const CgPoaScratch& s, u32 w, u32 rg
         if (emit) out[outn + __popc(bal & ((1u << lane) - 1u))] = emit;
         outn += __popc(bal);
     }
+    *cnt_aln += j_aln; *cnt_cells += j_cells; *cnt_pred += j_pred;
     return outn;
 }
 
-// Persistent warps draining the job queue of one tier.
-// qctl[0] = number of jobs, qctl[1] = next job, qctl[2] = jobs re-queued for the next tier.
-__global__ void __launch_bounds__(CG_POA_THREADS) k_poa(CgChunk c, const CgPoaScratch* scratch, u32 nwarps, const uint2* jobs, u32* qctl, uint2* jobs_next) {
+// Persistent warps draining one job queue.  qctl[0] = number of jobs, qctl[1] = next job.  A job that outgrows the
+// scratch is appended to the next queue (qnext[0] = its count) or, for the last tier, flagged as over capacity.
+__device__ __forceinline__ void cg_poa_drain(const CgChunk& c, const CgPoaScratch& s, const uint2* jobs, u32* qctl, uint2* jobs_next, u32* qnext) {
     const u32 lane = cg_lane();
-    const u32 gw = blockIdx.x * CG_POA_WARPS_PER_CTA + cg_warp();
-    if (gw >= nwarps) return;                       // warp-uniform; no block-wide barrier in this kernel
-    const CgPoaScratch s = scratch[gw];
     const u32 njobs = qctl[0];
     u64 cnt_aln = 0, cnt_cells = 0, cnt_pred = 0;
     for (;;) {
@@ -372,7 +499,7 @@ __global__ void __launch_bounds__(CG_POA_THREADS) k_poa(CgChunk c, const CgPoaSc
         const u32 n = cg_poa_job(c, s, job.x, job.y, &cnt_aln, &cnt_cells, &cnt_pred);
         if (lane == 0) {
             if (n == CG_NONE32) {
-                if (jobs_next) jobs_next[atomicAdd(&qctl[2], 1u)] = job;
+                if (jobs_next) jobs_next[atomicAdd(&qnext[0], 1u)] = job;
                 else { c.win[job.x].bad = 1; atomicOr(c.flags, (u32)CG_FLAG_CAPACITY); }
             } else {
                 c.regions[c.off_reg[job.x] + job.y].cons_len = n;
@@ -385,4 +512,55 @@ __global__ void __launch_bounds__(CG_POA_THREADS) k_poa(CgChunk c, const CgPoaSc
         atomicAdd((unsigned long long*)&c.counters->dp_cells, (unsigned long long)cnt_cells);
         atomicAdd((unsigned long long*)&c.counters->dp_pred_cells, (unsigned long long)cnt_pred);
     }
+}
+
+// Everything in global memory (any graph size up to the tier's capacities).
+__global__ void __launch_bounds__(CG_POA_THREADS) k_poa(CgChunk c, const CgPoaScratch* scratch, u32 nwarps, const uint2* jobs, u32* qctl,
+                                                      uint2* jobs_next, u32* qnext) {
+    const u32 gw = blockIdx.x * CG_POA_WARPS_PER_CTA + cg_warp();
+    if (gw >= nwarps) return;                       // warp-uniform; no block-wide barrier in this kernel
+    const CgPoaScratch s = scratch[gw];
+    cg_poa_drain(c, s, jobs, qctl, jobs_next, qnext);
+}
+
+// Shared-memory tiers: the graph (and for the small tier the score matrix and the alignment) of each resident warp
+// lives in its own slice of shared memory — the sequential parts (traceback, graph update, DFS) then run at
+// shared-memory latency instead of L2 round trips.
+//   small : <= 160 nodes, <= 2304 matrix cells        16 warps per SM   (the inter-anchor segments of deep piles)
+//   medium: <= 624 nodes, matrix + alignment in HBM/L2  8 warps per SM   (window ends, shallow piles)
+struct CgPoaTierS { static constexpr u32 VCAP = 160, ECAP = 320, SCAP = 640, ALNCAP = 192, HCELLS = 2304; };
+struct CgPoaTierM { static constexpr u32 VCAP = 624, ECAP = 1248, SCAP = 1312, ALNCAP = 0, HCELLS = 0; };
+
+template <class T> struct CgPoaSmemLayout {
+    static constexpr size_t r16(size_t v) { return (v + 15) / 16 * 16; }
+    static constexpr size_t o_letter = 0, o_in0 = o_letter + r16(T::VCAP), o_nal = o_in0 + r16(T::VCAP), o_leader = o_nal + r16(T::VCAP),
+                            o_marks = o_leader + r16(T::VCAP), o_check = o_marks + r16(T::VCAP), o_nseq = o_check + r16(T::VCAP),
+                            o_aligned = o_nseq + r16(2 * T::VCAP), o_rank = o_aligned + r16(6 * T::VCAP), o_r2n = o_rank + r16(2 * T::VCAP),
+                            o_ih = o_r2n + r16(2 * T::VCAP), o_it = o_ih + r16(4 * T::VCAP), o_rdesc = o_it + r16(4 * T::VCAP),
+                            o_ep = o_rdesc + r16(4 * T::VCAP), o_en = o_ep + r16(2 * T::ECAP), o_stack = o_en + r16(4 * T::ECAP),
+                            o_an = o_stack + r16(2 * T::SCAP), o_ap = o_an + r16(4 * T::ALNCAP), o_H = o_ap + r16(4 * T::ALNCAP),
+                            per_warp = o_H + r16(2 * T::HCELLS);
+    static constexpr size_t cta_bytes = per_warp * CG_POA_WARPS_PER_CTA;
+};
+
+template <class T>
+__global__ void __launch_bounds__(CG_POA_THREADS) k_poa_smem(CgChunk c, const CgPoaScratch* scratch, u32 nwarps, const uint2* jobs, u32* qctl,
+                                                           uint2* jobs_next, u32* qnext) {
+    CG_DYN_SMEM(smem);
+    typedef CgPoaSmemLayout<T> Lay;
+    const u32 gw = blockIdx.x * CG_POA_WARPS_PER_CTA + cg_warp();
+    if (gw >= nwarps) return;
+    CgPoaScratch s = scratch[gw];                   // global part: segment list (+ matrix and alignment for the medium tier)
+    u8* b = smem + Lay::per_warp * cg_warp();
+    s.vcap = T::VCAP; s.ecap = T::ECAP; s.scap = T::SCAP;
+    s.letter = b + Lay::o_letter; s.in0 = b + Lay::o_in0; s.nal = b + Lay::o_nal; s.leader = b + Lay::o_leader;
+    s.marks = b + Lay::o_marks; s.check = b + Lay::o_check;
+    s.nseq = (u16*)(b + Lay::o_nseq); s.aligned = (u16*)(b + Lay::o_aligned); s.rank_of = (u16*)(b + Lay::o_rank); s.r2n = (u16*)(b + Lay::o_r2n);
+    s.in_head = (u32*)(b + Lay::o_ih); s.in_tail = (u32*)(b + Lay::o_it); s.rdesc = (u32*)(b + Lay::o_rdesc);
+    s.e_pred = (u16*)(b + Lay::o_ep); s.e_next = (u32*)(b + Lay::o_en); s.stack = (u16*)(b + Lay::o_stack);
+    if (T::HCELLS) {
+        s.alncap = T::ALNCAP; s.hcap = T::HCELLS;
+        s.aln_node = (i32*)(b + Lay::o_an); s.aln_pos = (i32*)(b + Lay::o_ap); s.H = (i16*)(b + Lay::o_H);
+    }
+    cg_poa_drain(c, s, jobs, qctl, jobs_next, qnext);
 }

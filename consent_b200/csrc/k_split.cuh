@@ -15,6 +15,7 @@
 
 #define CG_SPLIT_THREADS 256u
 #define CG_SPLIT_WARPS (CG_SPLIT_THREADS / 32u)
+#define CG_POA_SMALL_LEN 32u   // longest segment of a job that starts in the shared-memory (small) POA tier
 
 // idx-th smallest (0-based) distance of the pair (s1,s2) over reads holding both.
 __device__ __forceinline__ u32 cg_select_distance(const u16* pos, u32 C, u32 N, u32 s1, u32 s2, u32 nbits, u32 idx) {
@@ -96,7 +97,7 @@ __global__ void __launch_bounds__(CG_SPLIT_THREADS) k_split(CgChunk c) {
     CgWinView v;
     v.seq_off = c.seq_off + W.seq_begin; v.pos = pos; v.chain = chain; v.rel = rel; v.N = N; v.C = C; v.nA = nA;
     for (u32 g = warp; g < nreg; g += CG_SPLIT_WARPS) {
-        u32 n = 0, r0 = 0, st0 = 0, ln0 = 0, sum = 0;
+        u32 n = 0, r0 = 0, st0 = 0, ln0 = 0, sum = 0, mxl = 0;
         bool same = true;
         for (u32 rb = 0; rb < N; rb += 32) {
             const u32 r = rb + lane;
@@ -110,6 +111,7 @@ __global__ void __launch_bounds__(CG_SPLIT_THREADS) k_split(CgChunk c) {
             bool eq = true;
             if (keep) {
                 sum += ln;
+                mxl = ln > mxl ? ln : mxl;
                 eq = ln == ln0;
                 if (eq) {
                     const u8* a = wbases + v.seq_off[r] + st;
@@ -122,39 +124,51 @@ __global__ void __launch_bounds__(CG_SPLIT_THREADS) k_split(CgChunk c) {
             n += __popc(bal);
         }
         sum = cg_warp_sum(sum);
+        mxl = cg_warp_max(mxl);
         if (lane == 0) {
             CgRegion R;
             R.kind = n == 0 ? CG_REG_EMPTY : (n == 1 || same) ? CG_REG_COPY : CG_REG_POA;
-            R.n = n; R.read = r0; R.start = st0; R.len = ln0; R.sum_len = sum; R.arena_off = 0; R.cons_len = 0;
+            R.n = n; R.read = r0; R.start = st0; R.len = ln0; R.sum_len = sum; R.max_len = mxl; R.arena_off = 0; R.cons_len = 0;
             regs[g] = R;
         }
     }
     __syncthreads();
 
-    // ---- consensus slots and POA jobs (warp 0)
+    // ---- consensus slots and POA jobs (warp 0).  Jobs are routed by their longest segment: short ones to the
+    // shared-memory tier, the rest to the medium tier (either re-queues what it cannot hold).
     if (warp != 0) return;
-    u32 njobs = 0;
-    for (u32 gb = 0; gb < nreg; gb += 32) {
-        const u32 g = gb + lane;
-        njobs += (g < nreg && regs[g].kind == CG_REG_POA) ? 1u : 0u;
-    }
-    njobs = cg_warp_sum(njobs);
-    u32 jbase = 0;
-    if (lane == 0 && njobs) jbase = atomicAdd(&c.job_count[0], njobs);
-    jbase = __shfl_sync(CG_FULL, jbase, 0);
-    u32 run_off = 0, run_job = 0;
+    u32 njs = 0, njm = 0;
     for (u32 gb = 0; gb < nreg; gb += 32) {
         const u32 g = gb + lane;
         const bool isp = g < nreg && regs[g].kind == CG_REG_POA;
+        const bool small = isp && regs[g].max_len <= CG_POA_SMALL_LEN;
+        njs += small ? 1u : 0u;
+        njm += (isp && !small) ? 1u : 0u;
+    }
+    njs = cg_warp_sum(njs);
+    njm = cg_warp_sum(njm);
+    const u32 njobs = njs + njm;
+    u32 sbase = 0, mbase = 0;
+    if (lane == 0 && njs) sbase = atomicAdd(&c.qctl[0], njs);
+    if (lane == 0 && njm) mbase = atomicAdd(&c.qctl[4], njm);
+    sbase = __shfl_sync(CG_FULL, sbase, 0);
+    mbase = __shfl_sync(CG_FULL, mbase, 0);
+    u32 run_off = 0, run_s = 0, run_m = 0;
+    for (u32 gb = 0; gb < nreg; gb += 32) {
+        const u32 g = gb + lane;
+        const bool isp = g < nreg && regs[g].kind == CG_REG_POA;
+        const bool small = isp && regs[g].max_len <= CG_POA_SMALL_LEN;
         const u32 sz = isp ? regs[g].sum_len : 0u;
         const u32 inc = cg_warp_scan(sz);
-        const u32 bal = __ballot_sync(CG_FULL, isp);
+        const u32 bs = __ballot_sync(CG_FULL, small), bm = __ballot_sync(CG_FULL, isp && !small);
         if (isp) {
             regs[g].arena_off = run_off + inc - sz;
-            c.jobs[jbase + run_job + __popc(bal & ((1u << lane) - 1u))] = make_uint2(w, g);
+            if (small) c.jobs_s[sbase + run_s + __popc(bs & ((1u << lane) - 1u))] = make_uint2(w, g);
+            else c.jobs_m[mbase + run_m + __popc(bm & ((1u << lane) - 1u))] = make_uint2(w, g);
         }
         run_off += __shfl_sync(CG_FULL, inc, 31);
-        run_job += __popc(bal);
+        run_s += __popc(bs);
+        run_m += __popc(bm);
     }
     if (lane == 0) {
         c.win[w].n_regions = nreg;

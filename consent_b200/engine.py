@@ -21,7 +21,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libconsent_b200.so")
 
 EXPORTS = ("cg_abi_version", "cg_device_count", "cg_create", "cg_destroy", "cg_last_error", "cg_set_option",
            "cg_correct_windows", "cg_free_results", "cg_upload", "cg_run", "cg_download", "cg_stage_ms",
-           "cg_get_counters")
+           "cg_get_counters", "cg_run_ms")
 
 
 class ConsentError(RuntimeError):
@@ -54,6 +54,8 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.cg_free_results.argtypes = [C.POINTER(cg_results)]
     lib.cg_stage_ms.restype = C.c_int
     lib.cg_stage_ms.argtypes = [H, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]
+    lib.cg_run_ms.restype = C.c_int
+    lib.cg_run_ms.argtypes = [H, C.POINTER(C.c_float)]
     lib.cg_get_counters.restype = C.c_int
     lib.cg_get_counters.argtypes = [H, C.POINTER(cg_counters)]
     return lib
@@ -125,6 +127,12 @@ class Corrector:
         n = (C.c_uint32 * CG_N_STAGES)()
         self._check(self.lib.cg_stage_ms(self._h, ms, n))
         return {name: {"ms": float(ms[i]), "launches": int(n[i])} for i, name in enumerate(STAGE_NAMES)}
+
+    def run_ms(self) -> float:
+        """CUDA-event time of the whole last run() on the library's stream."""
+        ms = C.c_float(0)
+        self._check(self.lib.cg_run_ms(self._h, C.byref(ms)))
+        return float(ms.value)
 
     def counters(self) -> dict:
         c = cg_counters()

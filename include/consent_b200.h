@@ -135,6 +135,8 @@ int  cg_download(cg_handle* h, cg_results* out);    /* D2H of the results of cg_
 /* CUDA-event time (ms) each stage spent on the handle's stream in the last cg_run,
  * and the number of kernel launches it made. */
 int  cg_stage_ms(const cg_handle* h, float ms[CG_N_STAGES], uint32_t launches[CG_N_STAGES]);
+/* CUDA-event time (ms) of the whole last cg_run on the handle's stream, first launch to last result. */
+int  cg_run_ms(const cg_handle* h, float* ms);
 
 /* Work counters of the last cg_run, the inputs of the algorithmic-bytes model
  * (SURVEY §8d): alignments, score-matrix cells sum (V+1)*L, predecessor-row cells

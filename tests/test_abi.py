@@ -21,7 +21,7 @@ def header_functions():
 def test_header_declares_the_boundary():
     fns = header_functions()
     assert {"cg_create", "cg_destroy", "cg_correct_windows", "cg_upload", "cg_run", "cg_download", "cg_free_results",
-            "cg_last_error", "cg_stage_ms", "cg_get_counters", "cg_set_option", "cg_abi_version", "cg_device_count"} <= set(fns)
+            "cg_last_error", "cg_stage_ms", "cg_run_ms", "cg_get_counters", "cg_set_option", "cg_abi_version", "cg_device_count"} <= set(fns)
 
 
 def test_library_exports_every_declared_symbol(gpu_lib):

@@ -61,10 +61,10 @@ def test_emulated_chunking_and_staged_calls_do_not_change_results(emu, oracle):
 def test_emulated_poa_tier_overflow_requeues_jobs(emu, oracle):
     batch = synth_windows(3, 8, seed=44)
     want, _ = oracle.correct_windows(batch, threads=4)
-    tiny = emu(poa_tier0_nodes=64, poa_tier0_cells=4096, poa_tier1_nodes=512, poa_tier1_cells=1 << 18)
-    assert_same(tiny.correct_windows(batch), want, "jobs re-queued to the larger scratch tiers")
+    tiny = emu(poa_medium_cells=2048, poa_tier0_nodes=64, poa_tier0_cells=4096, poa_tier1_nodes=512, poa_tier1_cells=1 << 18)
+    assert_same(tiny.correct_windows(batch), want, "jobs re-queued small -> medium -> global tiers 0 -> 1")
     with pytest.raises(ConsentError) as e:
-        emu(poa_tier0_nodes=64, poa_tier0_cells=4096, poa_tier1_nodes=128, poa_tier1_cells=8192,
+        emu(poa_medium_cells=2048, poa_tier0_nodes=64, poa_tier0_cells=4096, poa_tier1_nodes=128, poa_tier1_cells=8192,
             poa_tier2_nodes=256, poa_tier2_cells=16384).correct_windows(batch)
     assert e.value.code == -6
 

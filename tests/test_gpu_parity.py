@@ -68,7 +68,7 @@ def test_gpu_mixed_depth_batch_and_chunking(gpu, oracle):
 def test_gpu_poa_tier_overflow(gpu, oracle):
     batch = concat([synth_windows(16, 8, seed=66), Batch.from_piles([p for n, p in edge_piles(5) if "no_anchor" in n or "outlier" in n])])
     want, _ = oracle.correct_windows(batch, threads=32)
-    tiny = gpu(poa_tier0_nodes=64, poa_tier0_cells=4096, poa_tier1_nodes=1024, poa_tier1_cells=1 << 20)
+    tiny = gpu(poa_medium_cells=2048, poa_tier0_nodes=64, poa_tier0_cells=4096, poa_tier1_nodes=1024, poa_tier1_cells=1 << 20)
     assert_same(tiny.correct_windows(batch), want, "jobs re-queued to larger scratch tiers")
 
 
