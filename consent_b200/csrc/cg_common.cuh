@@ -93,7 +93,7 @@ struct CgPoaScratch {     // one per resident POA warp (global memory, L1/L2 res
     u16* nseq; u16* aligned; u16* rank_of; u16* r2n;
     u32* in_head; u32* in_tail; u32* rdesc;
     u16* e_pred; u32* e_next;
-    u16* stack;
+    u32* stack;
     i32* aln_node; i32* aln_pos;
     u16* seg_read; u16* seg_start; u16* seg_len;
     i16* H;
@@ -126,7 +126,8 @@ struct CgChunk {
     u8* fin;                      // per window: 3 slices of (2*n_bases+64) bytes: consensus, temp, path
     u32* visited;                 // per window ceil(solid_cap/32) words (bit per solid k-mer)
     // POA job queues, one per scratch tier: small (shared memory), medium (graph in shared memory), global.
-    // qctl[4*t + 0] = jobs in queue t, [4*t + 1] = next job to take.  A job that outgrows tier t is appended to t+1.
+    // qctl[4*t + {0,1,2,3}] = jobs at the front of queue t, next job to take, jobs at the back, capacity of the array.
+    // A job that outgrows tier t is pushed to the front of queue t+1.
     u32* qctl;
     uint2* jobs_s; uint2* jobs_m; uint2* jobs_g;
     // status

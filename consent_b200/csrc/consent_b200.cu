@@ -162,7 +162,7 @@ int ensure_tier(cg_handle* h, PoaTier& T) {
                  o_check = take(T.vcap), o_nseq = take(2 * (size_t)T.vcap), o_aligned = take(6 * (size_t)T.vcap),
                  o_rank = take(2 * (size_t)T.vcap), o_r2n = take(2 * (size_t)T.vcap), o_ih = take(4 * (size_t)T.vcap),
                  o_it = take(4 * (size_t)T.vcap), o_rd = take(4 * (size_t)T.vcap), o_ep = take(2 * (size_t)T.ecap), o_en = take(4 * (size_t)T.ecap),
-                 o_stack = take(2 * (size_t)scap), o_an = take(4 * (size_t)alncap), o_ap = take(4 * (size_t)alncap),
+                 o_stack = take(4 * (size_t)scap), o_an = take(4 * (size_t)alncap), o_ap = take(4 * (size_t)alncap),
                  o_sr = take(2 * (size_t)ncap), o_ss = take(2 * (size_t)ncap), o_sl = take(2 * (size_t)ncap), o_H = take(2 * T.hcap);
     const size_t per_warp = round_up(o, 256);
     CK(T.mem.ensure(per_warp * T.warps));
@@ -176,7 +176,7 @@ int ensure_tier(cg_handle* h, PoaTier& T) {
         s.nseq = (u16*)(b + o_nseq); s.aligned = (u16*)(b + o_aligned); s.rank_of = (u16*)(b + o_rank); s.r2n = (u16*)(b + o_r2n);
         s.in_head = (u32*)(b + o_ih); s.in_tail = (u32*)(b + o_it); s.rdesc = (u32*)(b + o_rd);
         s.e_pred = (u16*)(b + o_ep); s.e_next = (u32*)(b + o_en);
-        s.stack = (u16*)(b + o_stack); s.aln_node = (i32*)(b + o_an); s.aln_pos = (i32*)(b + o_ap);
+        s.stack = (u32*)(b + o_stack); s.aln_node = (i32*)(b + o_an); s.aln_pos = (i32*)(b + o_ap);
         s.seg_read = (u16*)(b + o_sr); s.seg_start = (u16*)(b + o_ss); s.seg_len = (u16*)(b + o_sl); s.H = (i16*)(b + o_H);
     }
     CK(cudaMemcpyAsync(T.desc.p, d.data(), sizeof(CgPoaScratch) * T.warps, cudaMemcpyHostToDevice, h->stream));
@@ -237,7 +237,12 @@ int run_chunk(cg_handle* h, const ChunkPlan& cp, std::vector<StageSpan>& spans, 
 
     // ---- stage 0: plan, offsets, pack
     span_begin(CG_STAGE_PACK);
-    CK(cudaMemsetAsync(ctl + CTL_Q, 0, 20 * sizeof(u32), st));
+    {
+        u32 qinit[20] = {0};
+        for (int t = 0; t < 5; ++t) qinit[4 * t + 3] = (u32)cp.reg_tot;
+        memcpy(h->h_ctl + 32, qinit, sizeof qinit);                      // pinned staging, consumed before the next chunk's sync
+        CK(cudaMemcpyAsync(ctl + CTL_Q, h->h_ctl + 32, sizeof qinit, cudaMemcpyHostToDevice, st));
+    }
     CK(cudaMemsetAsync(h->pwords.as<u32>() + cp.nwords, 0, 16 * 4, st));
     CK(cudaMemsetAsync(h->ptags.as<u32>() + cp.nwords, 0xff, 16 * 4, st));
     CG_LAUNCH(k_plan, (nwin + 127) / 128, 128, 0, st, c);
@@ -285,8 +290,9 @@ int run_chunk(cg_handle* h, const ChunkPlan& cp, std::vector<StageSpan>& spans, 
     CK(cudaMemcpyAsync(h->h_ctl, ctl, CTL_WORDS * sizeof(u32), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (getenv("CG_DEBUG"))
-        fprintf(stderr, "[consent_b200] chunk w0=%u nwin=%u POA jobs: small %u, medium %u (incl. re-queued), global0 %u, global1 %u\n", cp.w0, nwin,
-                h->h_ctl[CTL_Q + 0], h->h_ctl[CTL_Q + 4], h->h_ctl[CTL_Q + 8], h->h_ctl[CTL_Q + 12]);
+        fprintf(stderr, "[consent_b200] chunk w0=%u nwin=%u POA jobs: small %u+%u, medium %u+%u (front incl. re-queued), global0 %u, global1 %u\n",
+                cp.w0, nwin, h->h_ctl[CTL_Q + 0], h->h_ctl[CTL_Q + 2], h->h_ctl[CTL_Q + 4], h->h_ctl[CTL_Q + 6], h->h_ctl[CTL_Q + 8],
+                h->h_ctl[CTL_Q + 12]);
     uint2* q_in = h->jobs_x.as<uint2>(); uint2* q_out = c.jobs_g;
     for (int t = 1; t <= 2; ++t) {
         const u32 over = h->h_ctl[CTL_Q + 4 * (t + 2)];
@@ -394,8 +400,8 @@ int cg_create(int device, const cg_params* params, cg_handle** out) {
     if (!ok) { g_create_err = std::string("CUDA initialisation failed: ") + cudaGetErrorString(cudaGetLastError()); cg_destroy(h); return CG_ERR_CUDA; }
     // POA scratch tiers.  Shared-memory tiers keep only the segment list (small) or segment list + matrix + alignment (medium)
     // in global memory; the global tiers keep everything there: {nodes, edges, max segment length, matrix cells, resident warps}.
-    h->tier_s.lcap = CG_LEN_MAX; h->tier_s.warps = (u32)h->sms * 16;
-    h->tier_m.lcap = CG_LEN_MAX; h->tier_m.hcap = 512u << 10; h->tier_m.warps = (u32)h->sms * 8;
+    h->tier_s.lcap = CG_LEN_MAX; h->tier_s.warps = (u32)h->sms * CgPoaTierS::CTAS_PER_SM * CG_POA_WARPS_PER_CTA;
+    h->tier_m.lcap = CG_LEN_MAX; h->tier_m.hcap = 512u << 10; h->tier_m.warps = (u32)h->sms * CgPoaTierM::CTAS_PER_SM * CG_POA_WARPS_PER_CTA;
     h->tier[0].vcap = 2048;  h->tier[0].ecap = 8192;   h->tier[0].lcap = CG_LEN_MAX; h->tier[0].hcap = 2u << 20;
     h->tier[1].vcap = 16384; h->tier[1].ecap = 65536;  h->tier[1].lcap = CG_LEN_MAX; h->tier[1].hcap = 32u << 20;
     h->tier[2].vcap = 65535; h->tier[2].ecap = 262144; h->tier[2].lcap = CG_LEN_MAX; h->tier[2].hcap = 400u << 20;

@@ -9,20 +9,23 @@
 // What is kept of spoa's graph — exactly what its results depend on:
 //   node  : letter, ordered in-edge list (predecessor order drives the traceback tie-breaks), aligned set
 //           (<= 3 others: a column holds at most one node per base), #sequences through it, "sequence 0 is here"
-//   order : rank <-> node from the explicit-stack DFS of topological_sort, reproduced step by step
+//   order : rank <-> node from the explicit-stack DFS of topological_sort
 // Out-edges and per-edge sequence labels are not stored: edge existence is tested on the in-list, and the MSA
 // rows are never built — the vote only needs, per column, how many sequences pass through each of its nodes
 // (gaps = the rest) and row 0's letter.
 //
-// Parallelism: a persistent warp takes jobs (regions) from the chunk queue.  The score matrix is swept row by
-// row in rank order with the 32 lanes across query columns; the in-row gap dependency
+// Parallelism: a persistent warp takes jobs (regions) from its tier's queue, heaviest first.  The score matrix is
+// swept row by row in rank order with the 32 lanes across query columns; the in-row gap dependency
 //   H[i][j] = max(v[j], H[i][j-1] - 4)        is the max-plus prefix scan   H[i][j] = max_{t<=j}(v[t] + 4t) - 4j,
-// done with 5 warp shuffles per 32 columns and a carry between chunks.  Rows are int16 in global memory
-// (coalesced 64-byte row segments; L1/L2 resident for the short segments of deep piles, HBM-streamed for the
-// long ones) because the traceback needs the whole matrix, as in the reference.  Traceback, graph update and
-// the DFS are sequential by nature (and a few percent of the cells): lane 0 runs them.
+// done with 5 warp shuffles per 32 columns and a carry between chunks; a row whose only predecessor is the row just
+// computed (the common case) is produced from registers, with no loads.  Rows are kept as int16 because the
+// traceback needs the whole matrix, as in the reference.  Traceback, graph update and the DFS are sequential by
+// nature: lane 0 runs them, at shared-memory latency in the two shared-memory tiers.
 //
-// Scratch sizes are per tier; a job that outgrows its tier is re-queued for the next one.
+// Storage tiers (a job that outgrows its tier is re-queued for the next one; nothing is committed before it ends):
+//   small  : graph, matrix, alignment in shared memory   (<= 160 nodes, <= 2048 cells)   20 warps / SM
+//   medium : graph in shared memory, matrix in HBM/L2    (<= 704 nodes)                   8 warps / SM
+//   global : everything in global memory, three sizes up to 65535 nodes
 #pragma once
 #include "cg_common.cuh"
 
@@ -30,34 +33,137 @@
 #define CG_POA_THREADS (CG_POA_WARPS_PER_CTA * 32u)
 #define CG_POA_NEG (-(1 << 28))
 
+// ------------------------------------------------------------------ storage policies
+#ifdef CG_EMU
+__device__ __forceinline__ u8* cg_smem_base() { return cg_emu::cur->blk->dyn_smem; }
+#else
+extern __shared__ __align__(128) unsigned char cg_dyn_smem_[];
+__device__ __forceinline__ u8* cg_smem_base() { return cg_dyn_smem_; }
+#endif
+
+struct CgPoaTierS { static constexpr u32 VCAP = 160, ECAP = 320, SCAP = 384, ALNCAP = 192, HCELLS = 2048, SEQCAP = 64, CTAS_PER_SM = 5; };
+struct CgPoaTierM { static constexpr u32 VCAP = 704, ECAP = 1408, SCAP = 1472, ALNCAP = 0, HCELLS = 0, SEQCAP = 256, CTAS_PER_SM = 2; };
+
+template <class T> struct CgPoaSmemLayout {
+    static constexpr u32 r16(u32 v) { return (v + 15u) / 16u * 16u; }
+    static constexpr u32 o_letter = 0, o_in0 = o_letter + r16(T::VCAP), o_nal = o_in0 + r16(T::VCAP), o_leader = o_nal + r16(T::VCAP),
+                         o_marks = o_leader + r16(T::VCAP), o_check = o_marks + r16(T::VCAP), o_nseq = o_check + r16(T::VCAP),
+                         o_aligned = o_nseq + r16(2 * T::VCAP), o_rank = o_aligned + r16(6 * T::VCAP), o_r2n = o_rank + r16(2 * T::VCAP),
+                         o_ih = o_r2n + r16(2 * T::VCAP), o_it = o_ih + r16(2 * T::VCAP), o_rdesc = o_it + r16(2 * T::VCAP),
+                         o_ep = o_rdesc + r16(4 * T::VCAP), o_en = o_ep + r16(2 * T::ECAP), o_stack = o_en + r16(2 * T::ECAP),
+                         o_an = o_stack + r16(2 * T::SCAP), o_ap = o_an + r16(2 * T::ALNCAP), o_seq = o_ap + r16(2 * T::ALNCAP),
+                         o_H = o_seq + r16(T::SEQCAP), per_warp = o_H + r16(2 * T::HCELLS);
+    static constexpr u32 cta_bytes = per_warp * CG_POA_WARPS_PER_CTA;
+};
+
+// Graph (and, for the small tier, matrix + alignment) at compile-time offsets of the warp's shared-memory slice:
+// every access below is an LDS/STS with an immediate offset.
+template <class T> struct CgPoaSmemG {
+    typedef CgPoaSmemLayout<T> Lay;
+    typedef u16 eidx;
+    typedef u16 stk_t;
+    static constexpr u32 ENONE = 0xffffu, STK_FLAG = 0x8000u;
+    static constexpr bool SMEM_MATRIX = T::HCELLS != 0;
+    u32 wo;                      // byte offset of this warp's slice
+    CgPoaScratch gs;             // global part: segment list (+ matrix and alignment for the medium tier)
+    __device__ __forceinline__ u8* b() const { return cg_smem_base() + wo; }
+    __device__ __forceinline__ u8& letter(u32 i) const { return b()[Lay::o_letter + i]; }
+    __device__ __forceinline__ u8& in0(u32 i) const { return b()[Lay::o_in0 + i]; }
+    __device__ __forceinline__ u8& nal(u32 i) const { return b()[Lay::o_nal + i]; }
+    __device__ __forceinline__ u8& leader(u32 i) const { return b()[Lay::o_leader + i]; }
+    __device__ __forceinline__ u8& marks(u32 i) const { return b()[Lay::o_marks + i]; }
+    __device__ __forceinline__ u8& check(u32 i) const { return b()[Lay::o_check + i]; }
+    __device__ __forceinline__ u16& nseq(u32 i) const { return ((u16*)(b() + Lay::o_nseq))[i]; }
+    __device__ __forceinline__ u16& aligned(u32 i) const { return ((u16*)(b() + Lay::o_aligned))[i]; }
+    __device__ __forceinline__ u16& rank_of(u32 i) const { return ((u16*)(b() + Lay::o_rank))[i]; }
+    __device__ __forceinline__ u16& r2n(u32 i) const { return ((u16*)(b() + Lay::o_r2n))[i]; }
+    __device__ __forceinline__ u16& in_head(u32 i) const { return ((u16*)(b() + Lay::o_ih))[i]; }
+    __device__ __forceinline__ u16& in_tail(u32 i) const { return ((u16*)(b() + Lay::o_it))[i]; }
+    __device__ __forceinline__ u32& rdesc(u32 i) const { return ((u32*)(b() + Lay::o_rdesc))[i]; }
+    __device__ __forceinline__ u16& e_pred(u32 i) const { return ((u16*)(b() + Lay::o_ep))[i]; }
+    __device__ __forceinline__ u16& e_next(u32 i) const { return ((u16*)(b() + Lay::o_en))[i]; }
+    __device__ __forceinline__ u16& stack(u32 i) const { return ((u16*)(b() + Lay::o_stack))[i]; }
+    __device__ __forceinline__ void aln_set(u32 i, i32 node, i32 pos) const {
+        if (SMEM_MATRIX) { ((i16*)(b() + Lay::o_an))[i] = (i16)node; ((i16*)(b() + Lay::o_ap))[i] = (i16)pos; }
+        else { gs.aln_node[i] = node; gs.aln_pos[i] = pos; }
+    }
+    __device__ __forceinline__ i32 aln_node(u32 i) const { return SMEM_MATRIX ? (i32)((i16*)(b() + Lay::o_an))[i] : gs.aln_node[i]; }
+    __device__ __forceinline__ i32 aln_pos(u32 i) const { return SMEM_MATRIX ? (i32)((i16*)(b() + Lay::o_ap))[i] : gs.aln_pos[i]; }
+    __device__ __forceinline__ i16* H() const { return SMEM_MATRIX ? (i16*)(b() + Lay::o_H) : gs.H; }
+    __device__ __forceinline__ u8* seqbuf() const { return b() + Lay::o_seq; }
+    __device__ __forceinline__ u32 seqcap() const { return T::SEQCAP; }
+    __device__ __forceinline__ u32 vcap() const { return T::VCAP; }
+    __device__ __forceinline__ u32 ecap() const { return T::ECAP; }
+    __device__ __forceinline__ u32 scap() const { return T::SCAP; }
+    __device__ __forceinline__ u32 alncap() const { return SMEM_MATRIX ? T::ALNCAP : gs.alncap; }
+    __device__ __forceinline__ u64 hcap() const { return SMEM_MATRIX ? (u64)T::HCELLS : gs.hcap; }
+};
+
+// Everything in global memory (per-warp scratch described by CgPoaScratch).
+struct CgPoaGlobG {
+    typedef u32 eidx;
+    typedef u32 stk_t;
+    static constexpr u32 ENONE = 0xffffffffu, STK_FLAG = 0x80000000u;
+    CgPoaScratch gs;
+    __device__ __forceinline__ u8& letter(u32 i) const { return gs.letter[i]; }
+    __device__ __forceinline__ u8& in0(u32 i) const { return gs.in0[i]; }
+    __device__ __forceinline__ u8& nal(u32 i) const { return gs.nal[i]; }
+    __device__ __forceinline__ u8& leader(u32 i) const { return gs.leader[i]; }
+    __device__ __forceinline__ u8& marks(u32 i) const { return gs.marks[i]; }
+    __device__ __forceinline__ u8& check(u32 i) const { return gs.check[i]; }
+    __device__ __forceinline__ u16& nseq(u32 i) const { return gs.nseq[i]; }
+    __device__ __forceinline__ u16& aligned(u32 i) const { return gs.aligned[i]; }
+    __device__ __forceinline__ u16& rank_of(u32 i) const { return gs.rank_of[i]; }
+    __device__ __forceinline__ u16& r2n(u32 i) const { return gs.r2n[i]; }
+    __device__ __forceinline__ u32& in_head(u32 i) const { return gs.in_head[i]; }
+    __device__ __forceinline__ u32& in_tail(u32 i) const { return gs.in_tail[i]; }
+    __device__ __forceinline__ u32& rdesc(u32 i) const { return gs.rdesc[i]; }
+    __device__ __forceinline__ u16& e_pred(u32 i) const { return gs.e_pred[i]; }
+    __device__ __forceinline__ u32& e_next(u32 i) const { return gs.e_next[i]; }
+    __device__ __forceinline__ u32& stack(u32 i) const { return gs.stack[i]; }
+    __device__ __forceinline__ void aln_set(u32 i, i32 node, i32 pos) const { gs.aln_node[i] = node; gs.aln_pos[i] = pos; }
+    __device__ __forceinline__ i32 aln_node(u32 i) const { return gs.aln_node[i]; }
+    __device__ __forceinline__ i32 aln_pos(u32 i) const { return gs.aln_pos[i]; }
+    __device__ __forceinline__ i16* H() const { return gs.H; }
+    __device__ __forceinline__ u8* seqbuf() const { return nullptr; }
+    __device__ __forceinline__ u32 seqcap() const { return 0; }
+    __device__ __forceinline__ u32 vcap() const { return gs.vcap; }
+    __device__ __forceinline__ u32 ecap() const { return gs.ecap; }
+    __device__ __forceinline__ u32 scap() const { return gs.scap; }
+    __device__ __forceinline__ u32 alncap() const { return gs.alncap; }
+    __device__ __forceinline__ u64 hcap() const { return gs.hcap; }
+};
+
 struct CgPoaState {
-    u32 V, E, nseqs, nrank;
+    u32 V, E, nseqs;
     bool ovf;
 };
 
-__device__ __forceinline__ u32 cg_poa_add_node(const CgPoaScratch& s, CgPoaState& g, u8 letter) {
-    if (g.V >= s.vcap) { g.ovf = true; return 0; }
+// ------------------------------------------------------------------ graph update (lane 0)
+template <class G> __device__ __forceinline__ u32 cg_poa_add_node(const G& s, CgPoaState& g, u8 letter) {
+    if (g.V >= s.vcap()) { g.ovf = true; return 0; }
     const u32 id = g.V++;
-    s.letter[id] = letter; s.in0[id] = 0; s.nal[id] = 0; s.nseq[id] = 0;
-    s.in_head[id] = CG_NONE32; s.in_tail[id] = CG_NONE32;
+    s.letter(id) = letter; s.in0(id) = 0; s.nal(id) = 0; s.nseq(id) = 0;
+    s.in_head(id) = (typename G::eidx)G::ENONE; s.in_tail(id) = (typename G::eidx)G::ENONE;
     return id;
 }
 // graph.cpp:100-116 — an existing edge is reused (only its label list would grow; labels are not needed here)
-__device__ __forceinline__ void cg_poa_add_edge(const CgPoaScratch& s, CgPoaState& g, u32 b, u32 e) {
-    for (u32 ee = s.in_head[e]; ee != CG_NONE32; ee = s.e_next[ee])
-        if (s.e_pred[ee] == b) return;
-    if (g.E >= s.ecap) { g.ovf = true; return; }
+template <class G> __device__ __forceinline__ void cg_poa_add_edge(const G& s, CgPoaState& g, u32 b, u32 e) {
+    for (u32 ee = s.in_head(e); ee != G::ENONE; ee = s.e_next(ee))
+        if (s.e_pred(ee) == b) return;
+    if (g.E >= s.ecap()) { g.ovf = true; return; }
     const u32 id = g.E++;
-    s.e_pred[id] = (u16)b; s.e_next[id] = CG_NONE32;
-    if (s.in_tail[e] == CG_NONE32) s.in_head[e] = id; else s.e_next[s.in_tail[e]] = id;
-    s.in_tail[e] = id;
+    s.e_pred(id) = (u16)b; s.e_next(id) = (typename G::eidx)G::ENONE;
+    const u32 tl = s.in_tail(e);
+    if (tl == G::ENONE) s.in_head(e) = (typename G::eidx)id; else s.e_next(tl) = (typename G::eidx)id;
+    s.in_tail(e) = (typename G::eidx)id;
 }
-__device__ __forceinline__ void cg_poa_visit(const CgPoaScratch& s, const CgPoaState& g, u32 node) {
-    s.nseq[node] = (u16)(s.nseq[node] + 1);
-    if (g.nseqs == 0) s.in0[node] = 1;
+template <class G> __device__ __forceinline__ void cg_poa_visit(const G& s, const CgPoaState& g, u32 node) {
+    s.nseq(node) = (u16)(s.nseq(node) + 1);
+    if (g.nseqs == 0) s.in0(node) = 1;
 }
 // graph.cpp:274-292 — a chain of new nodes for seq[begin,end); -1 if empty
-__device__ __forceinline__ i32 cg_poa_add_sequence(const CgPoaScratch& s, CgPoaState& g, const u8* seq, u32 begin, u32 end) {
+template <class G> __device__ __forceinline__ i32 cg_poa_add_sequence(const G& s, CgPoaState& g, const u8* seq, u32 begin, u32 end) {
     if (begin == end) return -1;
     const u32 first = cg_poa_add_node(s, g, seq[begin]);
     cg_poa_visit(s, g, first);
@@ -72,47 +178,49 @@ __device__ __forceinline__ i32 cg_poa_add_sequence(const CgPoaScratch& s, CgPoaS
 }
 
 // graph.cpp:155-272.  The alignment is stored in traceback order (last pair first): index n_aln-1 .. 0.
-__device__ CG_NOINLINE void cg_poa_add_alignment(const CgPoaScratch& s, CgPoaState& g, u32 n_aln, const u8* seq, u32 L) {
+template <class G> __device__ __forceinline__ void cg_poa_add_alignment(const G& s, CgPoaState& g, u32 n_aln, const u8* seq, u32 L) {
     if (n_aln == 0) {
         cg_poa_add_sequence(s, g, seq, 0, L);
         g.nseqs++;
         return;
     }
     i32 first_valid = -1, last_valid = -1;
-    for (i32 i = (i32)n_aln - 1; i >= 0; --i)
-        if (s.aln_pos[i] != -1) { if (first_valid == -1) first_valid = s.aln_pos[i]; last_valid = s.aln_pos[i]; }
+    for (i32 i = (i32)n_aln - 1; i >= 0; --i) {
+        const i32 qp = s.aln_pos((u32)i);
+        if (qp != -1) { if (first_valid == -1) first_valid = qp; last_valid = qp; }
+    }
     const u32 tmp = g.V;
     cg_poa_add_sequence(s, g, seq, 0, (u32)first_valid);
     i32 head = tmp == g.V ? -1 : (i32)g.V - 1;
     const i32 tail = cg_poa_add_sequence(s, g, seq, (u32)last_valid + 1, L);
     for (i32 i = (i32)n_aln - 1; i >= 0 && !g.ovf; --i) {
-        const i32 qp = s.aln_pos[i];
+        const i32 qp = s.aln_pos((u32)i);
         if (qp == -1) continue;
         const u8 letter = seq[qp];
-        const i32 an = s.aln_node[i];
+        const i32 an = s.aln_node((u32)i);
         u32 nn;
         if (an == -1) {
             nn = cg_poa_add_node(s, g, letter);
-        } else if (s.letter[an] == letter) {
+        } else if (s.letter((u32)an) == letter) {
             nn = (u32)an;
         } else {
             i32 aligned_to = -1;
-            const u32 na = s.nal[an];
+            const u32 na = s.nal((u32)an);
             for (u32 a = 0; a < na; ++a) {
-                const u32 aid = s.aligned[3 * an + a];
-                if (s.letter[aid] == letter) { aligned_to = (i32)aid; break; }
+                const u32 aid = s.aligned(3 * (u32)an + a);
+                if (s.letter(aid) == letter) { aligned_to = (i32)aid; break; }
             }
             if (aligned_to == -1) {
                 nn = cg_poa_add_node(s, g, letter);
                 if (g.ovf) break;
                 if (na >= 3) { g.ovf = true; break; }          // cannot happen with ACGT input
                 for (u32 a = 0; a < na; ++a) {
-                    const u32 aid = s.aligned[3 * an + a];
-                    s.aligned[3 * nn + s.nal[nn]] = (u16)aid; s.nal[nn]++;
-                    s.aligned[3 * aid + s.nal[aid]] = (u16)nn; s.nal[aid]++;
+                    const u32 aid = s.aligned(3 * (u32)an + a);
+                    s.aligned(3 * nn + s.nal(nn)) = (u16)aid; s.nal(nn)++;
+                    s.aligned(3 * aid + s.nal(aid)) = (u16)nn; s.nal(aid)++;
                 }
-                s.aligned[3 * nn + s.nal[nn]] = (u16)an; s.nal[nn]++;
-                s.aligned[3 * an + s.nal[an]] = (u16)nn; s.nal[an]++;
+                s.aligned(3 * nn + s.nal(nn)) = (u16)an; s.nal(nn)++;
+                s.aligned(3 * (u32)an + s.nal((u32)an)) = (u16)nn; s.nal((u32)an)++;
             } else nn = (u32)aligned_to;
         }
         if (g.ovf) break;
@@ -124,85 +232,103 @@ __device__ CG_NOINLINE void cg_poa_add_alignment(const CgPoaScratch& s, CgPoaSta
     g.nseqs++;
 }
 
-// graph.cpp:294-354 — explicit-stack DFS over node ids; marks/check are pre-initialised (0 / 1) by the warp.
-__device__ CG_NOINLINE void cg_poa_toposort(const CgPoaScratch& s, CgPoaState& g) {
+// graph.cpp:294-354 — the explicit-stack DFS over node ids, step for step, with one shortcut that cannot change
+// its output: when a node comes back to the top of the stack after everything it pushed has been popped, all of
+// its predecessors and aligned nodes are finished (each was pushed above it, or was finished already), so the
+// reference's second scan of its lists always succeeds; a flag on the stack entry replaces that scan.
+// marks/check are pre-initialised (0 / 1) by the warp.
+template <class G> __device__ __forceinline__ void cg_poa_toposort(const G& s, CgPoaState& g) {
     u32 nrank = 0, sp = 0;
-    const u32 V = g.V;
+    const u32 V = g.V, scap = s.scap();
     for (u32 i = 0; i < V; ++i) {
-        if (s.marks[i] != 0) continue;
-        s.stack[sp++] = (u16)i;
+        if (s.marks(i) != 0) continue;
+        s.stack(sp++) = (typename G::stk_t)i;
         while (sp != 0) {
-            const u32 id = s.stack[sp - 1];
-            bool valid = true;
-            if (s.marks[id] != 2) {
-                for (u32 ee = s.in_head[id]; ee != CG_NONE32; ee = s.e_next[ee]) {
-                    const u32 b = s.e_pred[ee];
-                    if (s.marks[b] != 2) {
-                        if (sp >= s.scap) { g.ovf = true; return; }
-                        s.stack[sp++] = (u16)b; valid = false;
+            const u32 top = s.stack(sp - 1);
+            const u32 id = top & ~G::STK_FLAG;
+            bool finish = (top & G::STK_FLAG) != 0;
+            if (!finish) {
+                if (s.marks(id) == 2) { --sp; continue; }
+                const u32 sp0 = sp;
+                for (u32 ee = s.in_head(id); ee != G::ENONE; ee = s.e_next(ee)) {
+                    const u32 b = s.e_pred(ee);
+                    if (s.marks(b) != 2) {
+                        if (sp >= scap) { g.ovf = true; return; }
+                        s.stack(sp++) = (typename G::stk_t)b;
                     }
                 }
-                const u32 na = s.nal[id];
-                if (s.check[id]) {
+                if (s.check(id)) {
+                    const u32 na = s.nal(id);
                     for (u32 a = 0; a < na; ++a) {
-                        const u32 aid = s.aligned[3 * id + a];
-                        if (s.marks[aid] != 2) {
-                            if (sp >= s.scap) { g.ovf = true; return; }
-                            s.stack[sp++] = (u16)aid; s.check[aid] = 0; valid = false;
+                        const u32 aid = s.aligned(3 * id + a);
+                        if (s.marks(aid) != 2) {
+                            if (sp >= scap) { g.ovf = true; return; }
+                            s.stack(sp++) = (typename G::stk_t)aid; s.check(aid) = 0;
                         }
                     }
                 }
-                if (valid) {
-                    s.marks[id] = 2;
-                    if (s.check[id]) {
-                        s.r2n[nrank] = (u16)id; s.leader[nrank] = 1; ++nrank;
-                        for (u32 a = 0; a < na; ++a) { s.r2n[nrank] = s.aligned[3 * id + a]; s.leader[nrank] = 0; ++nrank; }
-                    }
-                } else s.marks[id] = 1;
+                if (sp == sp0) finish = true;
+                else { s.marks(id) = 1; s.stack(sp0 - 1) = (typename G::stk_t)(id | G::STK_FLAG); }
             }
-            if (valid) --sp;
+            if (finish) {
+                s.marks(id) = 2;
+                if (s.check(id)) {
+                    const u32 na = s.nal(id);
+                    s.r2n(nrank) = (u16)id; s.leader(nrank) = 1; ++nrank;
+                    for (u32 a = 0; a < na; ++a) { s.r2n(nrank) = s.aligned(3 * id + a); s.leader(nrank) = 0; ++nrank; }
+                }
+                --sp;
+            }
         }
     }
-    g.nrank = nrank;
 }
 
 // Traceback (simd_alignment_engine_impl.hpp:968-1004 == sisd_alignment_engine.cpp:392-431): diagonal over the
 // predecessors in in-edge order, then vertical over them, then horizontal.  Returns the number of pairs.
-__device__ CG_NOINLINE u32 cg_poa_traceback(const CgPoaScratch& s, CgPoaState& g, const u8* seq, u32 Wd, u32 bi, u32 bj) {
-    const i16* H = s.H;
+template <class G> __device__ __forceinline__ u32 cg_poa_traceback(const G& s, CgPoaState& g, const u8* seq, u32 Wd, u32 bi, u32 bj) {
+    const i16* H = s.H();
+    const u32 alncap = s.alncap();
     u32 i = bi, j = bj, n = 0, pi_ = 0, pj_ = 0;
-    while (H[(size_t)i * Wd + j] != 0) {
-        const i32 Hij = H[(size_t)i * Wd + j];
-        const u32 node = s.r2n[i - 1];
-        const u32 eh = s.in_head[node];
+    i32 Hij = H[(size_t)i * Wd + j];
+    while (Hij != 0) {
+        const u32 node = s.r2n(i - 1);
+        const u32 eh = s.in_head(node);
         bool found = false;
+        i32 Hp = 0;
         if (j != 0) {
-            const i32 sc = s.letter[node] == seq[j - 1] ? 5 : -10;
-            if (eh == CG_NONE32) {
-                if (Hij == H[j - 1] + sc) { pi_ = 0; pj_ = j - 1; found = true; }
+            const i32 sc = s.letter(node) == seq[j - 1] ? 5 : -10;
+            if (eh == G::ENONE) {
+                Hp = H[j - 1];
+                if (Hij == Hp + sc) { pi_ = 0; pj_ = j - 1; found = true; }
             } else {
-                for (u32 ee = eh; ee != CG_NONE32 && !found; ee = s.e_next[ee]) {
-                    const u32 pr = (u32)s.rank_of[s.e_pred[ee]] + 1;
-                    if (Hij == H[(size_t)pr * Wd + (j - 1)] + sc) { pi_ = pr; pj_ = j - 1; found = true; }
+                for (u32 ee = eh; ee != G::ENONE && !found; ee = s.e_next(ee)) {
+                    const u32 pr = (u32)s.rank_of(s.e_pred(ee)) + 1;
+                    Hp = H[(size_t)pr * Wd + (j - 1)];
+                    if (Hij == Hp + sc) { pi_ = pr; pj_ = j - 1; found = true; }
                 }
             }
         }
         if (!found) {
-            if (eh == CG_NONE32) {
-                if (Hij == H[j] - 4) { pi_ = 0; pj_ = j; found = true; }
+            if (eh == G::ENONE) {
+                Hp = H[j];
+                if (Hij == Hp - 4) { pi_ = 0; pj_ = j; found = true; }
             } else {
-                for (u32 ee = eh; ee != CG_NONE32 && !found; ee = s.e_next[ee]) {
-                    const u32 pr = (u32)s.rank_of[s.e_pred[ee]] + 1;
-                    if (Hij == H[(size_t)pr * Wd + j] - 4) { pi_ = pr; pj_ = j; found = true; }
+                for (u32 ee = eh; ee != G::ENONE && !found; ee = s.e_next(ee)) {
+                    const u32 pr = (u32)s.rank_of(s.e_pred(ee)) + 1;
+                    Hp = H[(size_t)pr * Wd + j];
+                    if (Hij == Hp - 4) { pi_ = pr; pj_ = j; found = true; }
                 }
             }
         }
-        if (!found && j != 0 && Hij == H[(size_t)i * Wd + j - 1] - 4) { pi_ = i; pj_ = j - 1; found = true; }
-        if (!found || n >= s.alncap) { g.ovf = true; return 0; }     // inconsistent matrix: cannot happen
-        s.aln_node[n] = i == pi_ ? -1 : (i32)node;
-        s.aln_pos[n] = j == pj_ ? -1 : (i32)(j - 1);
+        if (!found && j != 0) {
+            Hp = H[(size_t)i * Wd + j - 1];
+            if (Hij == Hp - 4) { pi_ = i; pj_ = j - 1; found = true; }
+        }
+        if (!found || n >= alncap) { g.ovf = true; return 0; }       // inconsistent matrix: cannot happen
+        s.aln_set(n, i == pi_ ? -1 : (i32)node, j == pj_ ? -1 : (i32)(j - 1));
         ++n;
         i = pi_; j = pj_;
+        Hij = Hp;                                                    // the value just compared is the next cell
     }
     return n;
 }
@@ -210,24 +336,25 @@ __device__ CG_NOINLINE u32 cg_poa_traceback(const CgPoaScratch& s, CgPoaState& g
 // Row descriptors: rank r -> letter | in-degree << 8 | (row index of the first predecessor) << 16  (0 = the virtual
 // start row).  Built by all lanes after every topological sort, so that the row loop of the score matrix has no
 // dependent pointer chasing: 32 descriptors are fetched at once and broadcast by shuffle.
-__device__ __forceinline__ void cg_poa_build_rdesc(const CgPoaScratch& s, u32 V) {
+template <class G> __device__ __forceinline__ void cg_poa_build_rdesc(const G& s, u32 V) {
     for (u32 r = cg_lane(); r < V; r += 32) {
-        const u32 node = s.r2n[r];
-        const u32 eh = s.in_head[node];
+        const u32 node = s.r2n(r);
+        const u32 eh = s.in_head(node);
         u32 deg = 0;
-        for (u32 ee = eh; ee != CG_NONE32; ee = s.e_next[ee]) ++deg;
-        const u32 p0 = eh == CG_NONE32 ? 0u : (u32)s.rank_of[s.e_pred[eh]] + 1u;
-        s.rdesc[r] = (u32)s.letter[node] | ((deg > 255u ? 255u : deg) << 8) | (p0 << 16);
+        for (u32 ee = eh; ee != G::ENONE; ee = s.e_next(ee)) ++deg;
+        const u32 p0 = eh == G::ENONE ? 0u : (u32)s.rank_of(s.e_pred(eh)) + 1u;
+        s.rdesc(r) = (u32)s.letter(node) | ((deg > 255u ? 255u : deg) << 8) | (p0 << 16);
     }
 }
 
-// Score matrix of one alignment, rows in rank order, CH chunks of 32 query columns per row held in registers.
-// The common row (one predecessor = the row just computed) needs no loads at all: the left neighbour comes from
-// the adjacent lane.  Other rows read their predecessor rows back from the stored matrix.
-template <int CH>
-__device__ __forceinline__ void cg_poa_dp(const CgPoaScratch& s, u32 V, const u8* seq, u32 L, i32& bv, u32& bi, u32& bj, u64& pred_rows) {
+// ------------------------------------------------------------------ score matrix (all lanes)
+// CH chunks of 32 query columns per row held in registers.  The common row (one predecessor = the row just
+// computed) needs no loads at all: the left neighbour comes from the adjacent lane.  Other rows read their
+// predecessor rows back from the stored matrix.
+template <int CH, class G>
+__device__ __forceinline__ void cg_poa_dp(const G& s, u32 V, const u8* seq, u32 L, i32& bv, u32& bi, u32& bj, u64& pred_rows) {
     const u32 lane = cg_lane(), Wd = L + 1;
-    i16* H = s.H;
+    i16* H = s.H();
     u8 q[CH];
     bool act[CH];
     i32 prev[CH];
@@ -242,7 +369,7 @@ __device__ __forceinline__ void cg_poa_dp(const CgPoaScratch& s, u32 V, const u8
     u32 desc_l = 0;
     __syncwarp();
     for (u32 r = 0; r < V; ++r) {
-        if ((r & 31u) == 0) desc_l = r + lane < V ? s.rdesc[r + lane] : 0u;
+        if ((r & 31u) == 0) desc_l = r + lane < V ? s.rdesc(r + lane) : 0u;
         const u32 d = __shfl_sync(CG_FULL, desc_l, (int)(r & 31u));
         const u8 ch = (u8)(d & 0xffu);
         u32 deg = (d >> 8) & 0xffu;
@@ -275,8 +402,8 @@ __device__ __forceinline__ void cg_poa_dp(const CgPoaScratch& s, u32 V, const u8
 #pragma unroll
             for (int c = 0; c < CH; ++c) val[c] = CG_POA_NEG;
             u32 n = 0;
-            for (u32 ee = s.in_head[s.r2n[r]]; ee != CG_NONE32; ee = s.e_next[ee]) {
-                const i16* prow = H + (size_t)((u32)s.rank_of[s.e_pred[ee]] + 1) * Wd;
+            for (u32 ee = s.in_head(s.r2n(r)); ee != G::ENONE; ee = s.e_next(ee)) {
+                const i16* prow = H + (size_t)((u32)s.rank_of(s.e_pred(ee)) + 1) * Wd;
                 ++n;
 #pragma unroll
                 for (int c = 0; c < CH; ++c) {
@@ -325,15 +452,16 @@ __device__ __forceinline__ void cg_poa_dp(const CgPoaScratch& s, u32 V, const u8
 }
 
 // Any length: chunks of 32 columns, every row read back from the stored matrix.
-__device__ CG_NOINLINE void cg_poa_dp_any(const CgPoaScratch& s, u32 V, const u8* seq, u32 L, i32& bv, u32& bi, u32& bj, u64& pred_rows) {
+template <class G>
+__device__ __forceinline__ void cg_poa_dp_any(const G& s, u32 V, const u8* seq, u32 L, i32& bv, u32& bi, u32& bj, u64& pred_rows) {
     const u32 lane = cg_lane(), Wd = L + 1;
-    i16* H = s.H;
+    i16* H = s.H();
     for (u32 j = lane; j < Wd; j += 32) H[j] = 0;
     __syncwarp();
     for (u32 r = 0; r < V; ++r) {
-        const u32 node = s.r2n[r];
-        const u8 ch = s.letter[node];
-        const u32 eh = s.in_head[node];
+        const u32 node = s.r2n(r);
+        const u8 ch = s.letter(node);
+        const u32 eh = s.in_head(node);
         i16* row = H + (size_t)(r + 1) * Wd;
         if (lane == 0) row[0] = 0;
         i32 carry = 0;
@@ -343,11 +471,11 @@ __device__ CG_NOINLINE void cg_poa_dp_any(const CgPoaScratch& s, u32 V, const u8
             i32 val = CG_POA_NEG;
             if (act) {
                 const i32 sc = seq[j - 1] == ch ? 5 : -10;
-                if (eh == CG_NONE32) {
+                if (eh == G::ENONE) {
                     val = sc > -4 ? sc : -4;                  // virtual start row of zeros
                 } else {
-                    for (u32 ee = eh; ee != CG_NONE32; ee = s.e_next[ee]) {
-                        const i16* prow = H + (size_t)((u32)s.rank_of[s.e_pred[ee]] + 1) * Wd;
+                    for (u32 ee = eh; ee != G::ENONE; ee = s.e_next(ee)) {
+                        const i16* prow = H + (size_t)((u32)s.rank_of(s.e_pred(ee)) + 1) * Wd;
                         const i32 a = (i32)prow[j - 1] + sc, b = (i32)prow[j] - 4;
                         const i32 m = a > b ? a : b;
                         val = m > val ? m : val;
@@ -370,14 +498,16 @@ __device__ CG_NOINLINE void cg_poa_dp_any(const CgPoaScratch& s, u32 V, const u8
             }
         }
         u32 deg = 0;
-        for (u32 ee = eh; ee != CG_NONE32; ee = s.e_next[ee]) ++deg;
+        for (u32 ee = eh; ee != G::ENONE; ee = s.e_next(ee)) ++deg;
         pred_rows += deg ? deg : 1;
         __syncwarp();
     }
 }
 
-// One job.  Returns the consensus length, or CG_NONE32 if the tier's scratch was outgrown (nothing is committed).
-__device__ u32 cg_poa_job(const CgChunk& c, const CgPoaScratch& s, u32 w, u32 rg, u64* cnt_aln, u64* cnt_cells, u64* cnt_pred) {
+// ------------------------------------------------------------------ one job
+// Returns the consensus length, or CG_NONE32 if the tier's scratch was outgrown (nothing is committed).
+template <class G>
+__device__ __forceinline__ u32 cg_poa_job(const CgChunk& c, const G& s, u32 w, u32 rg, u64* cnt_aln, u64* cnt_cells, u64* cnt_pred) {
     const u32 lane = cg_lane();
     const CgWin W = c.win[w];
     CgRegion* R = &c.regions[c.off_reg[w] + rg];
@@ -385,6 +515,7 @@ __device__ u32 cg_poa_job(const CgChunk& c, const CgPoaScratch& s, u32 w, u32 rg
     v.seq_off = c.seq_off + W.seq_begin; v.pos = c.pos + c.off_pos[w]; v.chain = c.chain + c.off_slot[w];
     v.rel = c.rel + c.off_slot[w]; v.N = W.n_seqs; v.C = W.n_cand; v.nA = W.n_chain;
     const u8* bases = (const u8*)c.bases;
+    const CgPoaScratch& gs = s.gs;
 
     // ---- the region's segments, in read order (split_reads)
     u32 nseg = 0;
@@ -395,25 +526,32 @@ __device__ u32 cg_poa_job(const CgChunk& c, const CgPoaScratch& s, u32 w, u32 rg
         const u32 bal = __ballot_sync(CG_FULL, keep);
         if (keep) {
             const u32 idx = nseg + __popc(bal & ((1u << lane) - 1u));
-            if (idx < s.ncap) { s.seg_read[idx] = (u16)r; s.seg_start[idx] = (u16)st; s.seg_len[idx] = (u16)ln; }
+            if (idx < gs.ncap) { gs.seg_read[idx] = (u16)r; gs.seg_start[idx] = (u16)st; gs.seg_len[idx] = (u16)ln; }
         }
         nseg += __popc(bal);
     }
-    if (nseg > s.ncap) return CG_NONE32;
+    if (nseg > gs.ncap) return CG_NONE32;
     __syncwarp();
 
     CgPoaState g;
-    g.V = 0; g.E = 0; g.nseqs = 0; g.nrank = 0; g.ovf = false;
+    g.V = 0; g.E = 0; g.nseqs = 0; g.ovf = false;
     u64 j_aln = 0, j_cells = 0, j_pred = 0;
 
     for (u32 si = 0; si < nseg; ++si) {
-        const u32 L = s.seg_len[si];
+        const u32 L = gs.seg_len[si];
         if (L == 0) continue;                                        // graph.cpp:160 — not a row of the MSA
-        const u8* seq = bases + v.seq_off[s.seg_read[si]] + s.seg_start[si];
+        const u8* seq = bases + v.seq_off[gs.seg_read[si]] + gs.seg_start[si];
+        if (L <= s.seqcap()) {                                       // stage the segment next to the graph
+            u8* sb = s.seqbuf();
+            __syncwarp();
+            for (u32 i = lane; i < L; i += 32) sb[i] = seq[i];
+            __syncwarp();
+            seq = sb;
+        }
         const u32 Wd = L + 1;
         u32 n_aln = 0;
         if (g.V != 0) {
-            if ((u64)(g.V + 1) * Wd > s.hcap) return CG_NONE32;
+            if ((u64)(g.V + 1) * Wd > s.hcap()) return CG_NONE32;
             i32 bv = 0; u32 bi = 0, bj = 0;
             u64 pred_rows = 0;
             if (L <= 32) cg_poa_dp<1>(s, g.V, seq, L, bv, bi, bj, pred_rows);
@@ -436,14 +574,13 @@ __device__ u32 cg_poa_job(const CgChunk& c, const CgPoaScratch& s, u32 w, u32 rg
         g.ovf = __shfl_sync(CG_FULL, (u32)g.ovf, 0) != 0;
         if (g.ovf) return CG_NONE32;
         if (g.V == V0 && g.E == E0) { __syncwarp(); continue; }      // same nodes, same edges, same aligned sets: same order
-        for (u32 i = lane; i < g.V; i += 32) { s.marks[i] = 0; s.check[i] = 1; }
+        for (u32 i = lane; i < g.V; i += 32) { s.marks(i) = 0; s.check(i) = 1; }
         __syncwarp();
         if (lane == 0) cg_poa_toposort(s, g);
         g.ovf = __shfl_sync(CG_FULL, (u32)g.ovf, 0) != 0;
-        g.nrank = __shfl_sync(CG_FULL, g.nrank, 0);
         if (g.ovf) return CG_NONE32;
         __syncwarp();
-        for (u32 i = lane; i < g.V; i += 32) s.rank_of[s.r2n[i]] = (u16)i;
+        for (u32 i = lane; i < g.V; i += 32) s.rank_of(s.r2n(i)) = (u16)i;
         __syncwarp();
         cg_poa_build_rdesc(s, g.V);
         __syncwarp();
@@ -455,17 +592,17 @@ __device__ u32 cg_poa_job(const CgChunk& c, const CgPoaScratch& s, u32 w, u32 rg
     for (u32 ib = 0; ib < g.V; ib += 32) {
         const u32 i = ib + lane;
         u8 emit = 0;
-        if (i < g.V && s.leader[i]) {
+        if (i < g.V && s.leader(i)) {
             u32 cnt[4] = {0, 0, 0, 0};
             u8 row0 = 0;
-            const u32 node = s.r2n[i];
-            const u32 na = s.nal[node];
+            const u32 node = s.r2n(i);
+            const u32 na = s.nal(node);
             for (u32 a = 0; a <= na; ++a) {
-                const u32 x = a == 0 ? node : (u32)s.aligned[3 * node + a - 1];
-                const u8 ch = s.letter[x];
+                const u32 x = a == 0 ? node : (u32)s.aligned(3 * node + a - 1);
+                const u8 ch = s.letter(x);
                 const u32 code = cg_base_code(ch) & 3u;
-                cnt[code] = s.nseq[x];
-                if (s.in0[x]) row0 = ch;
+                cnt[code] = s.nseq(x);
+                if (s.in0(x)) row0 = ch;
             }
             const u32 cA = cnt[0], cC = cnt[1], cG = cnt[2], cT = cnt[3];
             const u32 cM = g.nseqs - (cA + cC + cG + cT);
@@ -484,22 +621,27 @@ __device__ u32 cg_poa_job(const CgChunk& c, const CgPoaScratch& s, u32 w, u32 rg
     return outn;
 }
 
-// Persistent warps draining one job queue.  qctl[0] = number of jobs, qctl[1] = next job.  A job that outgrows the
-// scratch is appended to the next queue (qnext[0] = its count) or, for the last tier, flagged as over capacity.
-__device__ __forceinline__ void cg_poa_drain(const CgChunk& c, const CgPoaScratch& s, const uint2* jobs, u32* qctl, uint2* jobs_next, u32* qnext) {
+// ------------------------------------------------------------------ queues
+// qctl[0] = jobs appended at the front (heavy, and jobs re-queued by the previous tier), qctl[1] = next job to take,
+// qctl[2] = jobs appended at the back (light), qctl[3] = capacity of the array.  Front jobs are taken first, so the
+// long jobs start early and the tail of the launch is made of short ones.
+__device__ __forceinline__ void cg_queue_push_front(uint2* jobs, u32* qctl, uint2 job) { jobs[atomicAdd(&qctl[0], 1u)] = job; }
+
+template <class G>
+__device__ __forceinline__ void cg_poa_drain(const CgChunk& c, const G& s, const uint2* jobs, u32* qctl, uint2* jobs_next, u32* qnext) {
     const u32 lane = cg_lane();
-    const u32 njobs = qctl[0];
+    const u32 nfront = qctl[0], nback = qctl[2], cap = qctl[3];
     u64 cnt_aln = 0, cnt_cells = 0, cnt_pred = 0;
     for (;;) {
         u32 j = 0;
         if (lane == 0) j = atomicAdd(&qctl[1], 1u);
         j = __shfl_sync(CG_FULL, j, 0);
-        if (j >= njobs) break;
-        const uint2 job = jobs[j];
+        if (j >= nfront + nback) break;
+        const uint2 job = j < nfront ? jobs[j] : jobs[cap - 1 - (j - nfront)];
         const u32 n = cg_poa_job(c, s, job.x, job.y, &cnt_aln, &cnt_cells, &cnt_pred);
         if (lane == 0) {
             if (n == CG_NONE32) {
-                if (jobs_next) jobs_next[atomicAdd(&qnext[0], 1u)] = job;
+                if (jobs_next) cg_queue_push_front(jobs_next, qnext, job);
                 else { c.win[job.x].bad = 1; atomicOr(c.flags, (u32)CG_FLAG_CAPACITY); }
             } else {
                 c.regions[c.off_reg[job.x] + job.y].cons_len = n;
@@ -519,48 +661,19 @@ __global__ void __launch_bounds__(CG_POA_THREADS) k_poa(CgChunk c, const CgPoaSc
                                                       uint2* jobs_next, u32* qnext) {
     const u32 gw = blockIdx.x * CG_POA_WARPS_PER_CTA + cg_warp();
     if (gw >= nwarps) return;                       // warp-uniform; no block-wide barrier in this kernel
-    const CgPoaScratch s = scratch[gw];
+    CgPoaGlobG s;
+    s.gs = scratch[gw];
     cg_poa_drain(c, s, jobs, qctl, jobs_next, qnext);
 }
 
-// Shared-memory tiers: the graph (and for the small tier the score matrix and the alignment) of each resident warp
-// lives in its own slice of shared memory — the sequential parts (traceback, graph update, DFS) then run at
-// shared-memory latency instead of L2 round trips.
-//   small : <= 160 nodes, <= 2304 matrix cells        16 warps per SM   (the inter-anchor segments of deep piles)
-//   medium: <= 624 nodes, matrix + alignment in HBM/L2  8 warps per SM   (window ends, shallow piles)
-struct CgPoaTierS { static constexpr u32 VCAP = 160, ECAP = 320, SCAP = 640, ALNCAP = 192, HCELLS = 2304; };
-struct CgPoaTierM { static constexpr u32 VCAP = 624, ECAP = 1248, SCAP = 1312, ALNCAP = 0, HCELLS = 0; };
-
-template <class T> struct CgPoaSmemLayout {
-    static constexpr size_t r16(size_t v) { return (v + 15) / 16 * 16; }
-    static constexpr size_t o_letter = 0, o_in0 = o_letter + r16(T::VCAP), o_nal = o_in0 + r16(T::VCAP), o_leader = o_nal + r16(T::VCAP),
-                            o_marks = o_leader + r16(T::VCAP), o_check = o_marks + r16(T::VCAP), o_nseq = o_check + r16(T::VCAP),
-                            o_aligned = o_nseq + r16(2 * T::VCAP), o_rank = o_aligned + r16(6 * T::VCAP), o_r2n = o_rank + r16(2 * T::VCAP),
-                            o_ih = o_r2n + r16(2 * T::VCAP), o_it = o_ih + r16(4 * T::VCAP), o_rdesc = o_it + r16(4 * T::VCAP),
-                            o_ep = o_rdesc + r16(4 * T::VCAP), o_en = o_ep + r16(2 * T::ECAP), o_stack = o_en + r16(4 * T::ECAP),
-                            o_an = o_stack + r16(2 * T::SCAP), o_ap = o_an + r16(4 * T::ALNCAP), o_H = o_ap + r16(4 * T::ALNCAP),
-                            per_warp = o_H + r16(2 * T::HCELLS);
-    static constexpr size_t cta_bytes = per_warp * CG_POA_WARPS_PER_CTA;
-};
-
+// Shared-memory tiers.
 template <class T>
-__global__ void __launch_bounds__(CG_POA_THREADS) k_poa_smem(CgChunk c, const CgPoaScratch* scratch, u32 nwarps, const uint2* jobs, u32* qctl,
-                                                           uint2* jobs_next, u32* qnext) {
-    CG_DYN_SMEM(smem);
-    typedef CgPoaSmemLayout<T> Lay;
+__global__ void __launch_bounds__(CG_POA_THREADS, T::CTAS_PER_SM) k_poa_smem(CgChunk c, const CgPoaScratch* scratch, u32 nwarps, const uint2* jobs,
+                                                                            u32* qctl, uint2* jobs_next, u32* qnext) {
     const u32 gw = blockIdx.x * CG_POA_WARPS_PER_CTA + cg_warp();
     if (gw >= nwarps) return;
-    CgPoaScratch s = scratch[gw];                   // global part: segment list (+ matrix and alignment for the medium tier)
-    u8* b = smem + Lay::per_warp * cg_warp();
-    s.vcap = T::VCAP; s.ecap = T::ECAP; s.scap = T::SCAP;
-    s.letter = b + Lay::o_letter; s.in0 = b + Lay::o_in0; s.nal = b + Lay::o_nal; s.leader = b + Lay::o_leader;
-    s.marks = b + Lay::o_marks; s.check = b + Lay::o_check;
-    s.nseq = (u16*)(b + Lay::o_nseq); s.aligned = (u16*)(b + Lay::o_aligned); s.rank_of = (u16*)(b + Lay::o_rank); s.r2n = (u16*)(b + Lay::o_r2n);
-    s.in_head = (u32*)(b + Lay::o_ih); s.in_tail = (u32*)(b + Lay::o_it); s.rdesc = (u32*)(b + Lay::o_rdesc);
-    s.e_pred = (u16*)(b + Lay::o_ep); s.e_next = (u32*)(b + Lay::o_en); s.stack = (u16*)(b + Lay::o_stack);
-    if (T::HCELLS) {
-        s.alncap = T::ALNCAP; s.hcap = T::HCELLS;
-        s.aln_node = (i32*)(b + Lay::o_an); s.aln_pos = (i32*)(b + Lay::o_ap); s.H = (i16*)(b + Lay::o_H);
-    }
+    CgPoaSmemG<T> s;
+    s.wo = CgPoaSmemLayout<T>::per_warp * cg_warp();
+    s.gs = scratch[gw];
     cg_poa_drain(c, s, jobs, qctl, jobs_next, qnext);
 }

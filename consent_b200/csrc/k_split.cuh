@@ -15,7 +15,9 @@
 
 #define CG_SPLIT_THREADS 256u
 #define CG_SPLIT_WARPS (CG_SPLIT_THREADS / 32u)
-#define CG_POA_SMALL_LEN 32u   // longest segment of a job that starts in the shared-memory (small) POA tier
+#define CG_POA_SMALL_LEN 32u       // longest segment of a job that starts in the shared-memory (small) POA tier
+#define CG_POA_SMALL_HEAVY 480u    // sequences x longest segment: front of the small queue
+#define CG_POA_MEDIUM_HEAVY 4000u  // front of the medium queue
 
 // idx-th smallest (0-based) distance of the pair (s1,s2) over reads holding both.
 __device__ __forceinline__ u32 cg_select_distance(const u16* pos, u32 C, u32 N, u32 s1, u32 s2, u32 nbits, u32 idx) {
@@ -135,40 +137,60 @@ __global__ void __launch_bounds__(CG_SPLIT_THREADS) k_split(CgChunk c) {
     __syncthreads();
 
     // ---- consensus slots and POA jobs (warp 0).  Jobs are routed by their longest segment: short ones to the
-    // shared-memory tier, the rest to the medium tier (either re-queues what it cannot hold).
+    // shared-memory tier, the rest to the medium tier (either re-queues what it cannot hold); inside a queue the
+    // heavy jobs (sequences x longest segment) go to the front, which is drained first.
     if (warp != 0) return;
-    u32 njs = 0, njm = 0;
+    u32 cnt4[4] = {0, 0, 0, 0};                       // small-heavy, small-light, medium-heavy, medium-light
     for (u32 gb = 0; gb < nreg; gb += 32) {
         const u32 g = gb + lane;
-        const bool isp = g < nreg && regs[g].kind == CG_REG_POA;
-        const bool small = isp && regs[g].max_len <= CG_POA_SMALL_LEN;
-        njs += small ? 1u : 0u;
-        njm += (isp && !small) ? 1u : 0u;
+        u32 cls = 4;
+        if (g < nreg && regs[g].kind == CG_REG_POA) {
+            const bool small = regs[g].max_len <= CG_POA_SMALL_LEN;
+            const u32 cost = regs[g].n * regs[g].max_len;
+            cls = small ? (cost >= CG_POA_SMALL_HEAVY ? 0u : 1u) : (cost >= CG_POA_MEDIUM_HEAVY ? 2u : 3u);
+        }
+#pragma unroll
+        for (u32 q = 0; q < 4; ++q) cnt4[q] += __popc(__ballot_sync(CG_FULL, cls == q));
     }
-    njs = cg_warp_sum(njs);
-    njm = cg_warp_sum(njm);
-    const u32 njobs = njs + njm;
-    u32 sbase = 0, mbase = 0;
-    if (lane == 0 && njs) sbase = atomicAdd(&c.qctl[0], njs);
-    if (lane == 0 && njm) mbase = atomicAdd(&c.qctl[4], njm);
-    sbase = __shfl_sync(CG_FULL, sbase, 0);
-    mbase = __shfl_sync(CG_FULL, mbase, 0);
-    u32 run_off = 0, run_s = 0, run_m = 0;
+    const u32 njobs = cnt4[0] + cnt4[1] + cnt4[2] + cnt4[3];
+    u32 base4[4] = {0, 0, 0, 0};
+    if (lane == 0) {
+        if (cnt4[0]) base4[0] = atomicAdd(&c.qctl[0], cnt4[0]);
+        if (cnt4[1]) base4[1] = atomicAdd(&c.qctl[2], cnt4[1]);
+        if (cnt4[2]) base4[2] = atomicAdd(&c.qctl[4], cnt4[2]);
+        if (cnt4[3]) base4[3] = atomicAdd(&c.qctl[6], cnt4[3]);
+    }
+#pragma unroll
+    for (u32 q = 0; q < 4; ++q) base4[q] = __shfl_sync(CG_FULL, base4[q], 0);
+    const u32 cap_s = c.qctl[3], cap_m = c.qctl[7];
+    u32 run_off = 0;
     for (u32 gb = 0; gb < nreg; gb += 32) {
         const u32 g = gb + lane;
         const bool isp = g < nreg && regs[g].kind == CG_REG_POA;
-        const bool small = isp && regs[g].max_len <= CG_POA_SMALL_LEN;
+        u32 cls = 4;
+        if (isp) {
+            const bool small = regs[g].max_len <= CG_POA_SMALL_LEN;
+            const u32 cost = regs[g].n * regs[g].max_len;
+            cls = small ? (cost >= CG_POA_SMALL_HEAVY ? 0u : 1u) : (cost >= CG_POA_MEDIUM_HEAVY ? 2u : 3u);
+        }
         const u32 sz = isp ? regs[g].sum_len : 0u;
         const u32 inc = cg_warp_scan(sz);
-        const u32 bs = __ballot_sync(CG_FULL, small), bm = __ballot_sync(CG_FULL, isp && !small);
+        u32 my = 0;
+#pragma unroll
+        for (u32 q = 0; q < 4; ++q) {
+            const u32 bal = __ballot_sync(CG_FULL, cls == q);
+            if (cls == q) my = base4[q] + __popc(bal & ((1u << lane) - 1u));
+            base4[q] += __popc(bal);
+        }
         if (isp) {
             regs[g].arena_off = run_off + inc - sz;
-            if (small) c.jobs_s[sbase + run_s + __popc(bs & ((1u << lane) - 1u))] = make_uint2(w, g);
-            else c.jobs_m[mbase + run_m + __popc(bm & ((1u << lane) - 1u))] = make_uint2(w, g);
+            const uint2 job = make_uint2(w, g);
+            if (cls == 0) c.jobs_s[my] = job;
+            else if (cls == 1) c.jobs_s[cap_s - 1 - my] = job;
+            else if (cls == 2) c.jobs_m[my] = job;
+            else c.jobs_m[cap_m - 1 - my] = job;
         }
         run_off += __shfl_sync(CG_FULL, inc, 31);
-        run_s += __popc(bs);
-        run_m += __popc(bm);
     }
     if (lane == 0) {
         c.win[w].n_regions = nreg;
