@@ -156,6 +156,7 @@ def main():
     ap.add_argument("--windows", type=int, default=int(os.environ.get("CG_BENCH_WINDOWS", "20000")), help="windows per step and per GPU")
     ap.add_argument("--seqs", type=int, default=150)
     ap.add_argument("--cpu-budget", type=float, default=15.0)
+    ap.add_argument("--chunk-windows", type=int, default=0, help="windows per chunk (0: library default); never changes results")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -208,6 +209,8 @@ def main():
     log(f"[rank {rank}] generated {batch.n_windows} windows, {batch.n_bases / 1e9:.2f} GB of bases in {time.time() - t0:.1f}s")
 
     cor = Corrector(device=local_rank)
+    if args.chunk_windows:
+        cor.set_option("chunk_max_windows", args.chunk_windows)
 
     def barrier():
         torch.cuda.synchronize()

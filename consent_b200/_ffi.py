@@ -134,24 +134,52 @@ class Batch:
 
 
 class Results:
-    """Host copy of cg_results (numpy-owned; the C buffers are freed on construction)."""
+    """Host view of cg_results.
 
-    def __init__(self, r: cg_results):
+    Results(r)            copies every array out of the C buffers (the caller frees them);
+    Results(r, free=f)    wraps the C buffers without copying and calls f(r) when this object dies —
+                          used by Corrector so that the (pinned, pooled) result buffers of the library
+                          are handed back by cg_free_results instead of being copied."""
+
+    def __init__(self, r: cg_results, free=None):
         W = int(r.n_windows)
         self.n_windows = W
-        self.cons_off = np.ctypeslib.as_array(r.cons_off, shape=(W + 1,)).copy()
+        self._r, self._free = (r, free) if free is not None else (None, None)
+        keep = (lambda a: a) if free is not None else (lambda a: a.copy())
+        self.cons_off = keep(np.ctypeslib.as_array(r.cons_off, shape=(W + 1,)))
         nb = int(self.cons_off[-1])
-        self.cons = (np.ctypeslib.as_array(C.cast(r.cons, C.POINTER(C.c_uint8)), shape=(max(nb, 1),))[:nb].copy()
+        self.cons = (keep(np.ctypeslib.as_array(C.cast(r.cons, C.POINTER(C.c_uint8)), shape=(max(nb, 1),))[:nb])
                      if nb else np.zeros(0, np.uint8))
-        self.status = np.ctypeslib.as_array(r.status, shape=(max(W, 1),))[:W].copy()
-        self.solid_off = np.ctypeslib.as_array(r.solid_off, shape=(W + 1,)).copy()
+        self.status = keep(np.ctypeslib.as_array(r.status, shape=(max(W, 1),))[:W])
+        self.solid_off = keep(np.ctypeslib.as_array(r.solid_off, shape=(W + 1,)))
         ns = int(self.solid_off[-1])
         if ns:
-            self.solid_kmer = np.ctypeslib.as_array(r.solid_kmer, shape=(ns,)).copy()
-            self.solid_count = np.ctypeslib.as_array(r.solid_count, shape=(ns,)).copy()
+            self.solid_kmer = keep(np.ctypeslib.as_array(r.solid_kmer, shape=(ns,)))
+            self.solid_count = keep(np.ctypeslib.as_array(r.solid_count, shape=(ns,)))
         else:
             self.solid_kmer = np.zeros(0, np.uint32)
             self.solid_count = np.zeros(0, np.uint32)
+
+    def __del__(self):
+        if getattr(self, "_free", None) is not None:
+            f, r = self._free, self._r
+            self._free = self._r = None
+            for n in ("cons_off", "cons", "status", "solid_off", "solid_kmer", "solid_count"):
+                setattr(self, n, None)
+            try:
+                f(r)
+            except Exception:
+                pass
+
+    def detach(self) -> "Results":
+        """Own copies of every array (the library buffers go back to its pool)."""
+        if self._free is not None:
+            for n in ("cons_off", "cons", "status", "solid_off", "solid_kmer", "solid_count"):
+                setattr(self, n, getattr(self, n).copy())
+            f, r = self._free, self._r
+            self._free = self._r = None
+            f(r)
+        return self
 
     def consensus(self, w: int) -> str:
         return self.cons[int(self.cons_off[w]):int(self.cons_off[w + 1])].tobytes().decode()

@@ -51,6 +51,7 @@ enum {
     CG_FLAG_BAD_BASE = 1u,
     CG_FLAG_CAPACITY = 2u,
     CG_FLAG_INTERNAL = 4u,
+    CG_FLAG_BAD_OFFSETS = 8u,
 };
 
 // ---- region kinds (easy_consensus cases, bmean.cpp:603-641)

@@ -10,6 +10,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -59,10 +60,28 @@ struct PoaTier {
     bool ready = false;
 };
 
+// Host copy of the results of one batch, in pinned memory (so the per-chunk D2H copies overlap the kernels of the
+// next chunk).  Pooled per handle: cg_free_results() hands the buffers back, the next call reuses them.
+struct HostResults {
+    u64* cons_off = nullptr; u64* solid_off = nullptr; u8* status = nullptr;
+    char* cons = nullptr; u32* sk = nullptr; u32* sc = nullptr;
+    size_t capW = 0, capC = 0, capS = 0;
+    struct cg_handle* owner = nullptr;
+    bool in_use = false, orphan = false;
+};
+
 struct cg_handle {
     int device = 0;
     cg_params p{};
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;      // kernels
+    cudaStream_t s_h2d = nullptr;       // batch upload, chunk by chunk
+    cudaStream_t s_d2h = nullptr;       // results download, chunk by chunk
+    std::vector<cudaEvent_t> ev_h2d;    // [chunk] bases of the chunk are resident
+    cudaEvent_t ev_gather = nullptr;
+    bool h2d_pending = false;           // cg_correct_windows: the kernels of chunk i wait for ev_h2d[i]
+    HostResults* stream_out = nullptr;  // cg_correct_windows: results are downloaded chunk by chunk into this
+    std::mutex pool_mu;
+    std::vector<HostResults*> pool;
     std::string err;
     int sms = 148;
     int smem_optin = 0;
@@ -73,8 +92,9 @@ struct cg_handle {
     u32 W = 0;
     u64 n_seqs = 0, n_bases = 0;
     DevBuf d_bases, d_seq_off, d_wsb;
-    std::vector<u32> h_wsb;
-    std::vector<u64> h_seq_off;
+    std::vector<u32> h_wsb;             // [W + 1]
+    std::vector<u64> h_wbase;           // [W + 1] seq_off[win_seq_begin[w]]
+    std::vector<u32> h_tlen;            // [W] template length
     std::vector<ChunkPlan> chunks;
     bool uploaded = false, ran = false;
     // chunk workspaces
@@ -109,10 +129,12 @@ std::string g_create_err;
 inline u64 round_up(u64 v, u64 m) { return (v + m - 1) / m * m; }
 
 // ctl layout (u32 words, device): [0] flags, [4 + 4t ..] queue t {jobs, next, -, -}: t = 0 small, 1 medium, 2..4 global tiers
-enum { CTL_FLAGS = 0, CTL_Q = 4, CTL_WORDS = 32 };
+enum { CTL_FLAGS = 0, CTL_VFLAGS = 1, CTL_Q = 4, CTL_WORDS = 32 };
 // offs layout (u64 arrays of nwin+1): solid, slot, pos, reg, arena
 // out_off layout: cons_off[nwin+1], solid_off[nwin+1]
 
+// Chunk plan from per-window summaries only (O(W) on the host): every capacity below is an upper bound of what
+// k_plan computes on the device from the exact per-sequence lengths (occurrences <= bases).
 int plan_chunks(cg_handle* h) {
     h->chunks.clear();
     const u32 k = h->p.mer_size;
@@ -120,21 +142,17 @@ int plan_chunks(cg_handle* h) {
     while (w < h->W) {
         ChunkPlan c{};
         c.w0 = w;
-        c.pword_base = (h->h_seq_off[h->h_wsb[w]] >> 4) + h->h_wsb[w];
+        c.pword_base = (h->h_wbase[w] >> 4) + h->h_wsb[w];
         size_t bytes = 0;
         while (w < h->W && c.nwin < h->chunk_max_windows) {
             const u32 s0 = h->h_wsb[w], s1 = h->h_wsb[w + 1], N = s1 - s0;
-            u64 nocc = 0;
-            for (u32 s = s0; s < s1; ++s) {
-                const u64 len = h->h_seq_off[s + 1] - h->h_seq_off[s];
-                if (len >= k) nocc += len - k + 1;
-            }
-            const u64 tlen = h->h_seq_off[s0 + 1] - h->h_seq_off[s0];
+            const u64 nb = h->h_wbase[w + 1] - h->h_wbase[w];
+            const u64 nocc = nb;
+            const u64 tlen = h->h_tlen[w];
             const u64 tk = tlen >= k ? tlen - k + 1 : 0;
-            const u64 nb = h->h_seq_off[s1] - h->h_seq_off[s0];
             const u64 a_solid = round_up(nocc / h->p.solid_thresh, 4), a_slot = round_up(tk, 8), a_pos = round_up(tk * N, 8),
                       a_reg = tk + 2, a_arena = round_up(nb + N, 16);
-            const u64 words = ((h->h_seq_off[s1] >> 4) + s1) - ((h->h_seq_off[s0] >> 4) + s0);
+            const u64 words = ((h->h_wbase[w + 1] >> 4) + s1) - ((h->h_wbase[w] >> 4) + s0);
             const size_t wbytes = a_solid * 8 + a_solid / 8 + 8 + a_slot * 14 + a_pos * 2 + a_reg * (sizeof(CgRegion) + 8) + a_arena +
                                   words * 8 + sizeof(CgWin) + 64 + 6 * tlen + 256;
             if (c.nwin > 0 && bytes + wbytes > h->chunk_budget) break;
@@ -143,8 +161,7 @@ int plan_chunks(cg_handle* h) {
             c.max_tk = std::max<u32>(c.max_tk, (u32)tk); c.max_n = std::max<u32>(c.max_n, N);
             c.nwin++; ++w;
         }
-        const u32 s1 = h->h_wsb[w];
-        c.nwords = ((h->h_seq_off[s1] >> 4) + s1) - c.pword_base;
+        c.nwords = ((h->h_wbase[w] >> 4) + h->h_wsb[w]) - c.pword_base;
         h->chunks.push_back(c);
     }
     return CG_OK;
@@ -188,7 +205,10 @@ int ensure_tier(cg_handle* h, PoaTier& T) {
 // One timed stage = a pair of events on the stream; collected after the final sync of cg_run.
 struct StageSpan { int stage; cudaEvent_t a, b; };
 
-int run_chunk(cg_handle* h, const ChunkPlan& cp, std::vector<StageSpan>& spans, std::vector<cudaEvent_t>& pool, size_t& pool_at) {
+int stream_out_chunk(cg_handle* h, const ChunkPlan& cp, u64 cons_n, u64 solid_n);
+
+int run_chunk(cg_handle* h, size_t ci, std::vector<StageSpan>& spans, std::vector<cudaEvent_t>& pool, size_t& pool_at) {
+    const ChunkPlan& cp = h->chunks[ci];
     cudaStream_t st = h->stream;
     const u32 nwin = cp.nwin;
     auto ev = [&]() -> cudaEvent_t {
@@ -234,6 +254,8 @@ int run_chunk(cg_handle* h, const ChunkPlan& cp, std::vector<StageSpan>& spans, 
     u64* off_fin = h->off_fin.as<u64>();
     u64* cons_off = h->out_off.as<u64>();
     u64* solid_off = cons_off + (nwin + 1);
+
+    if (h->h2d_pending) CK(cudaStreamWaitEvent(st, h->ev_h2d[ci], 0));
 
     // ---- stage 0: plan, offsets, pack
     span_begin(CG_STAGE_PACK);
@@ -340,9 +362,17 @@ int run_chunk(cg_handle* h, const ChunkPlan& cp, std::vector<StageSpan>& spans, 
     if (h->h_ctl[CTL_FLAGS] & CG_FLAG_BAD_BASE) { h->err = "a base outside {A,C,G,T} in the batch"; return CG_ERR_BAD_BASE; }
     if (h->h_ctl[CTL_FLAGS] & CG_FLAG_CAPACITY) { h->err = "a per-window capacity limit of this build was exceeded"; return CG_ERR_CAPACITY; }
     if (h->h_ctl[CTL_FLAGS] & CG_FLAG_INTERNAL) { h->err = "internal invariant violated (anchor pair without common read)"; return CG_ERR_CUDA; }
-    CK(h->o_cons.ensure(h->o_cons_n + tot[0] + 16, true, st));
-    CK(h->o_sk.ensure((h->o_solid_n + tot[1]) * 4 + 16, true, st));
-    CK(h->o_sc.ensure((h->o_solid_n + tot[1]) * 4 + 16, true, st));
+    {   // dense batch outputs: sized from the density of the chunks so far, so that they rarely move
+        const double frac = (double)(cp.w0 + nwin) / (double)h->W;
+        const u64 need_c = h->o_cons_n + tot[0] + 16, need_s = (h->o_solid_n + tot[1]) * 4 + 16;
+        if (need_c > h->o_cons.cap || need_s > h->o_sk.cap) {
+            if (h->stream_out) CK(cudaStreamSynchronize(h->s_d2h));        // a download may still read the old buffers
+            const u64 est_c = (u64)((double)need_c / frac * 1.05) + 4096, est_s = (u64)((double)need_s / frac * 1.05) + 4096;
+            CK(h->o_cons.ensure(std::max(need_c, est_c), true, st));
+            CK(h->o_sk.ensure(std::max(need_s, est_s), true, st));
+            CK(h->o_sc.ensure(std::max(need_s, est_s), true, st));
+        }
+    }
 
     span_begin(CG_STAGE_STITCH);
     CG_LAUNCH(k_gather, nwin, 256, 0, st, c, (const u64*)off_fin, (const u64*)cons_off, (const u64*)solid_off,
@@ -350,8 +380,90 @@ int run_chunk(cg_handle* h, const ChunkPlan& cp, std::vector<StageSpan>& spans, 
               h->o_status.as<u8>() + cp.w0, h->o_cons_n, h->o_solid_n, h->o_len.as<u64>() + cp.w0, h->o_nsol.as<u64>() + cp.w0);
     h->stage_launches[CG_STAGE_STITCH] += 1;
     span_end();
+    if (h->stream_out) { int rc = stream_out_chunk(h, cp, tot[0], tot[1]); if (rc) return rc; }
     h->o_cons_n += tot[0];
     h->o_solid_n += tot[1];
+    return CG_OK;
+}
+
+// ---- pinned result buffers
+template <class T> cudaError_t pinned_ensure(T*& p, size_t& cap, size_t need, size_t keep) {
+    if (need <= cap && p) return cudaSuccess;
+    const size_t ncap = need + need / 8 + 64;
+    T* np = nullptr;
+    cudaError_t e = cudaMallocHost((void**)&np, ncap * sizeof(T));
+    if (e != cudaSuccess) return e;
+    if (p && keep) memcpy(np, p, keep * sizeof(T));
+    if (p) cudaFreeHost(p);
+    p = np; cap = ncap;
+    return cudaSuccess;
+}
+
+void host_results_release(HostResults* r) {
+    if (r->cons_off) cudaFreeHost(r->cons_off);
+    if (r->solid_off) cudaFreeHost(r->solid_off);
+    if (r->status) cudaFreeHost(r->status);
+    if (r->cons) cudaFreeHost(r->cons);
+    if (r->sk) cudaFreeHost(r->sk);
+    if (r->sc) cudaFreeHost(r->sc);
+    delete r;
+}
+
+// A free HostResults of the handle's pool (or a new one) with room for W windows.
+int host_results_acquire(cg_handle* h, u32 W, HostResults** out) {
+    HostResults* r = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(h->pool_mu);
+        for (HostResults* c : h->pool) if (!c->in_use) { r = c; break; }
+        if (!r) { r = new HostResults(); r->owner = h; h->pool.push_back(r); }
+        r->in_use = true;
+    }
+    size_t capW2 = r->capW, capW3 = r->capW;
+    CK(pinned_ensure(r->cons_off, r->capW, (size_t)W + 1, 0));
+    CK(pinned_ensure(r->solid_off, capW2, (size_t)W + 1, 0));
+    CK(pinned_ensure(r->status, capW3, (size_t)W + 1, 0));
+    r->capW = std::min(r->capW, std::min(capW2, capW3));
+    *out = r;
+    return CG_OK;
+}
+
+// Make room for `need_c` consensus bytes and `need_s` solid k-mers, keeping what has already been downloaded.
+int host_results_reserve(cg_handle* h, HostResults* r, u64 need_c, u64 need_s, u64 keep_c, u64 keep_s) {
+    if (need_c > r->capC || !r->cons) {
+        CK(cudaStreamSynchronize(h->s_d2h));
+        CK(pinned_ensure(r->cons, r->capC, (size_t)need_c, (size_t)keep_c));
+    }
+    if (need_s > r->capS || !r->sk) {
+        CK(cudaStreamSynchronize(h->s_d2h));
+        size_t cap2 = r->capS;
+        CK(pinned_ensure(r->sk, r->capS, (size_t)need_s, (size_t)keep_s));
+        CK(pinned_ensure(r->sc, cap2, (size_t)need_s, (size_t)keep_s));
+        r->capS = std::min(r->capS, cap2);
+    }
+    return CG_OK;
+}
+
+// Download the dense results of one chunk on the D2H stream while the next chunk computes.
+int stream_out_chunk(cg_handle* h, const ChunkPlan& cp, u64 cons_n, u64 solid_n) {
+    HostResults* r = h->stream_out;
+    const double frac = (double)(cp.w0 + cp.nwin) / (double)h->W;
+    const u64 need_c = h->o_cons_n + cons_n + 1, need_s = h->o_solid_n + solid_n + 1;
+    if (need_c > r->capC || need_s > r->capS || !r->cons || !r->sk) {
+        const u64 est_c = (u64)((double)need_c / frac * 1.05) + 4096, est_s = (u64)((double)need_s / frac * 1.05) + 4096;
+        int rc = host_results_reserve(h, r, std::max(need_c, est_c), std::max(need_s, est_s), h->o_cons_n, h->o_solid_n);
+        if (rc) return rc;
+    }
+    CK(cudaEventRecord(h->ev_gather, h->stream));
+    CK(cudaStreamWaitEvent(h->s_d2h, h->ev_gather, 0));
+    cudaStream_t sd = h->s_d2h;
+    if (cons_n) CK(cudaMemcpyAsync(r->cons + h->o_cons_n, h->o_cons.as<u8>() + h->o_cons_n, cons_n, cudaMemcpyDeviceToHost, sd));
+    if (solid_n) {
+        CK(cudaMemcpyAsync(r->sk + h->o_solid_n, h->o_sk.as<u32>() + h->o_solid_n, solid_n * 4, cudaMemcpyDeviceToHost, sd));
+        CK(cudaMemcpyAsync(r->sc + h->o_solid_n, h->o_sc.as<u32>() + h->o_solid_n, solid_n * 4, cudaMemcpyDeviceToHost, sd));
+    }
+    CK(cudaMemcpyAsync(r->cons_off + cp.w0, h->o_len.as<u64>() + cp.w0, cp.nwin * sizeof(u64), cudaMemcpyDeviceToHost, sd));
+    CK(cudaMemcpyAsync(r->solid_off + cp.w0, h->o_nsol.as<u64>() + cp.w0, cp.nwin * sizeof(u64), cudaMemcpyDeviceToHost, sd));
+    CK(cudaMemcpyAsync(r->status + cp.w0, h->o_status.as<u8>() + cp.w0, cp.nwin, cudaMemcpyDeviceToHost, sd));
     return CG_OK;
 }
 
@@ -389,6 +501,9 @@ int cg_create(int device, const cg_params* params, cg_handle** out) {
         delete h; return CG_ERR_NO_DEVICE;
     }
     bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->ev_gather, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaMallocHost(&h->h_ctl, 64 * sizeof(u32)) == cudaSuccess;
     ok = ok && cudaEventCreate(&h->ev_run[0]) == cudaSuccess && cudaEventCreate(&h->ev_run[1]) == cudaSuccess;
     ok = ok && h->ctl.ensure(CTL_WORDS * sizeof(u32) + sizeof(CgCountersDev)) == cudaSuccess;
@@ -416,6 +531,17 @@ void cg_destroy(cg_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->s_h2d) cudaStreamSynchronize(h->s_h2d);
+    if (h->s_d2h) cudaStreamSynchronize(h->s_d2h);
+    {
+        std::lock_guard<std::mutex> lk(h->pool_mu);
+        for (HostResults* r : h->pool) { if (r->in_use) { r->orphan = true; r->owner = nullptr; } else host_results_release(r); }
+        h->pool.clear();
+    }
+    for (cudaEvent_t e : h->ev_h2d) cudaEventDestroy(e);
+    if (h->ev_gather) cudaEventDestroy(h->ev_gather);
+    if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
+    if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
     DevBuf* bufs[] = {&h->d_bases, &h->d_seq_off, &h->d_wsb, &h->pwords, &h->ptags, &h->win, &h->offs, &h->solid_k, &h->solid_c, &h->slot_tpos,
                       &h->slot_kmer, &h->anchors, &h->chain, &h->rel, &h->pos, &h->regions, &h->arena, &h->fin, &h->visited, &h->jobs_s,
                       &h->jobs_m, &h->jobs_g, &h->jobs_x, &h->ctl, &h->off_fin, &h->out_off, &h->o_cons, &h->o_sk, &h->o_sc, &h->o_status, &h->o_len, &h->o_nsol};
@@ -450,47 +576,75 @@ int cg_set_option(cg_handle* h, const char* key, long long value) {
     return CG_OK;
 }
 
-int cg_upload(cg_handle* h, const cg_batch* in) {
-    if (!h) return CG_ERR_INVALID_ARG;
+}  // extern "C"
+
+namespace {
+
+// Upload = offsets first (validated on the device), then the bases chunk by chunk on the H2D stream, one event per
+// chunk.  wait = true: return when everything is resident (cg_upload); false: the kernels of chunk i wait for
+// ev_h2d[i] (cg_correct_windows).
+int upload_impl(cg_handle* h, const cg_batch* in, bool wait) {
     if (!in || !in->win_seq_begin || !in->seq_off || (!in->bases && in->n_windows)) { h->err = "null batch pointer"; return CG_ERR_INVALID_ARG; }
     cudaSetDevice(h->device);
     h->uploaded = h->ran = false;
+    h->h2d_pending = false;
     const u32 W = in->n_windows;
     const u64 n_seqs = in->win_seq_begin[W];
-    if (in->win_seq_begin[0] != 0) { h->err = "win_seq_begin[0] must be 0"; return CG_ERR_INVALID_ARG; }
-    for (u32 w = 0; w < W; ++w) {
-        if (in->win_seq_begin[w + 1] <= in->win_seq_begin[w]) { h->err = "empty pile (window without a template)"; return CG_ERR_INVALID_ARG; }
-        if (in->win_seq_begin[w + 1] - in->win_seq_begin[w] > CG_N_MAX) { h->err = "more than 4095 sequences in one window"; return CG_ERR_CAPACITY; }
-    }
     const u32 k = h->p.mer_size;
-    for (u64 s = 0; s < n_seqs; ++s) {
-        if (in->seq_off[s + 1] < in->seq_off[s]) { h->err = "seq_off must be non-decreasing"; return CG_ERR_INVALID_ARG; }
-        if (in->seq_off[s + 1] - in->seq_off[s] > CG_LEN_MAX) { h->err = "a sequence is longer than 6000 bases"; return CG_ERR_CAPACITY; }
-    }
+    if (in->win_seq_begin[0] != 0) { h->err = "win_seq_begin[0] must be 0"; return CG_ERR_INVALID_ARG; }
+    h->h_wsb.assign(in->win_seq_begin, in->win_seq_begin + W + 1);
+    h->h_wbase.resize((size_t)W + 1);
+    h->h_tlen.resize(W);
     for (u32 w = 0; w < W; ++w) {
-        const u32 s0 = in->win_seq_begin[w];
-        const u64 tlen = in->seq_off[s0 + 1] - in->seq_off[s0];
+        const u32 s0 = in->win_seq_begin[w], s1 = in->win_seq_begin[w + 1];
+        if (s1 <= s0) { h->err = "empty pile (window without a template)"; return CG_ERR_INVALID_ARG; }
+        if (s1 - s0 > CG_N_MAX) { h->err = "more than 4095 sequences in one window"; return CG_ERR_CAPACITY; }
+        h->h_wbase[w] = in->seq_off[s0];
+        const u64 t1 = in->seq_off[s0 + 1];
+        if (t1 < h->h_wbase[w]) { h->err = "seq_off must be non-decreasing"; return CG_ERR_INVALID_ARG; }
+        const u64 tlen = t1 - h->h_wbase[w];
+        if (tlen > CG_LEN_MAX) { h->err = "a sequence is longer than 6000 bases"; return CG_ERR_CAPACITY; }
         if (tlen >= k && tlen - k + 1 > CG_TK_MAX) { h->err = "template longer than 2047 k-mers"; return CG_ERR_CAPACITY; }
+        h->h_tlen[w] = (u32)tlen;
     }
     const u64 n_bases = n_seqs ? in->seq_off[n_seqs] : 0;
+    h->h_wbase[W] = n_bases;
+    for (u32 w = 0; w < W; ++w)
+        if (h->h_wbase[w + 1] < h->h_wbase[w]) { h->err = "seq_off must be non-decreasing"; return CG_ERR_INVALID_ARG; }
     h->W = W; h->n_seqs = n_seqs; h->n_bases = n_bases;
-    h->h_wsb.assign(in->win_seq_begin, in->win_seq_begin + W + 1);
-    h->h_seq_off.assign(in->seq_off, in->seq_off + n_seqs + 1);
     CK(h->d_bases.ensure(n_bases + 64));
     CK(h->d_seq_off.ensure((n_seqs + 1) * sizeof(u64)));
     CK(h->d_wsb.ensure((W + 1) * sizeof(u32)));
-    if (n_bases) CK(cudaMemcpyAsync(h->d_bases.p, in->bases, n_bases, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->d_seq_off.p, in->seq_off, (n_seqs + 1) * sizeof(u64), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->d_wsb.p, in->win_seq_begin, (W + 1) * sizeof(u32), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    cudaStream_t sc = h->s_h2d;
+    CK(cudaMemcpyAsync(h->d_seq_off.p, in->seq_off, (n_seqs + 1) * sizeof(u64), cudaMemcpyHostToDevice, sc));
+    CK(cudaMemcpyAsync(h->d_wsb.p, in->win_seq_begin, (W + 1) * sizeof(u32), cudaMemcpyHostToDevice, sc));
+    // every sequence: offsets non-decreasing, length within the build's limit (checked on the device, one word back)
+    u32* vflags = h->ctl.as<u32>() + CTL_VFLAGS;
+    CK(cudaMemsetAsync(vflags, 0, sizeof(u32), sc));
+    if (n_seqs) CG_LAUNCH(k_validate, (u32)std::min<u64>((n_seqs + 255) / 256, 4096), 256, 0, sc, h->d_seq_off.as<u64>(), n_seqs, vflags);
+    CK(cudaMemcpyAsync(h->h_ctl + 60, vflags, sizeof(u32), cudaMemcpyDeviceToHost, sc));
     plan_chunks(h);
+    while (h->ev_h2d.size() < h->chunks.size()) {
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->ev_h2d.push_back(e);
+    }
+    CK(cudaStreamSynchronize(sc));
+    if (h->h_ctl[60] & CG_FLAG_BAD_OFFSETS) { h->err = "seq_off must be non-decreasing"; return CG_ERR_INVALID_ARG; }
+    if (h->h_ctl[60] & CG_FLAG_CAPACITY) { h->err = "a sequence is longer than 6000 bases"; return CG_ERR_CAPACITY; }
+    for (size_t ci = 0; ci < h->chunks.size(); ++ci) {
+        const ChunkPlan& cp = h->chunks[ci];
+        const u64 b0 = h->h_wbase[cp.w0], b1 = h->h_wbase[cp.w0 + cp.nwin];
+        if (b1 > b0) CK(cudaMemcpyAsync(h->d_bases.as<char>() + b0, in->bases + b0, b1 - b0, cudaMemcpyHostToDevice, sc));
+        CK(cudaEventRecord(h->ev_h2d[ci], sc));
+    }
+    if (wait) CK(cudaStreamSynchronize(sc));
+    else h->h2d_pending = true;
     h->uploaded = true;
     return CG_OK;
 }
 
-int cg_run(cg_handle* h) {
-    if (!h) return CG_ERR_INVALID_ARG;
-    if (!h->uploaded) { h->err = "cg_run before cg_upload"; return CG_ERR_STATE; }
+int run_impl(cg_handle* h) {
     cudaSetDevice(h->device);
     h->ran = false;
     h->o_cons_n = h->o_solid_n = 0;
@@ -502,9 +656,9 @@ int cg_run(cg_handle* h) {
     std::vector<StageSpan> spans;
     static thread_local std::vector<cudaEvent_t> pool;
     size_t pool_at = 0;
-    for (const ChunkPlan& cp : h->chunks) {
-        int rc = run_chunk(h, cp, spans, pool, pool_at);
-        if (rc != CG_OK) { cudaStreamSynchronize(h->stream); return rc; }
+    for (size_t ci = 0; ci < h->chunks.size(); ++ci) {
+        int rc = run_chunk(h, ci, spans, pool, pool_at);
+        if (rc != CG_OK) { cudaStreamSynchronize(h->stream); cudaStreamSynchronize(h->s_h2d); cudaStreamSynchronize(h->s_d2h); return rc; }
     }
     CgCountersDev cd{};
     CK(cudaMemcpyAsync(&cd, h->ctl.as<u32>() + CTL_WORDS, sizeof cd, cudaMemcpyDeviceToHost, h->stream));
@@ -521,44 +675,84 @@ int cg_run(cg_handle* h) {
     return CG_OK;
 }
 
-namespace {
-struct ResultOwner { std::vector<u64> cons_off, solid_off; std::vector<char> cons; std::vector<u8> status; std::vector<u32> sk, sc; };
+void fill_results(cg_handle* h, HostResults* r, cg_results* out) {
+    const u32 W = h->W;
+    r->cons_off[W] = h->o_cons_n; r->solid_off[W] = h->o_solid_n;
+    out->n_windows = W; out->cons_off = r->cons_off; out->cons = r->cons; out->status = r->status;
+    out->solid_off = r->solid_off; out->solid_kmer = r->sk; out->solid_count = r->sc; out->owner_ = r;
+}
+
+void give_back(cg_handle* h, HostResults* r) {
+    std::lock_guard<std::mutex> lk(h->pool_mu);
+    r->in_use = false;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cg_upload(cg_handle* h, const cg_batch* in) {
+    if (!h) return CG_ERR_INVALID_ARG;
+    return upload_impl(h, in, true);
+}
+
+int cg_run(cg_handle* h) {
+    if (!h) return CG_ERR_INVALID_ARG;
+    if (!h->uploaded) { h->err = "cg_run before cg_upload"; return CG_ERR_STATE; }
+    h->stream_out = nullptr;
+    return run_impl(h);
 }
 
 int cg_download(cg_handle* h, cg_results* out) {
     if (!h || !out) return CG_ERR_INVALID_ARG;
     if (!h->ran) { h->err = "cg_download before a successful cg_run"; return CG_ERR_STATE; }
     cudaSetDevice(h->device);
-    ResultOwner* ow = new ResultOwner();
     const u32 W = h->W;
-    ow->cons_off.resize(W + 1); ow->solid_off.resize(W + 1); ow->status.resize(W ? W : 1);
-    ow->cons.resize(h->o_cons_n ? h->o_cons_n : 1); ow->sk.resize(h->o_solid_n ? h->o_solid_n : 1); ow->sc.resize(h->o_solid_n ? h->o_solid_n : 1);
+    HostResults* r = nullptr;
+    { int rc = host_results_acquire(h, W, &r); if (rc) { if (r) give_back(h, r); return rc; } }
+    { int rc = host_results_reserve(h, r, h->o_cons_n + 1, h->o_solid_n + 1, 0, 0); if (rc) { give_back(h, r); return rc; } }
     cudaError_t e = cudaSuccess;
+    cudaStream_t sd = h->s_d2h;
     if (W) {
-        e = cudaMemcpyAsync(ow->cons_off.data(), h->o_len.p, W * sizeof(u64), cudaMemcpyDeviceToHost, h->stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(ow->solid_off.data(), h->o_nsol.p, W * sizeof(u64), cudaMemcpyDeviceToHost, h->stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(ow->status.data(), h->o_status.p, W, cudaMemcpyDeviceToHost, h->stream);
-        if (e == cudaSuccess && h->o_cons_n) e = cudaMemcpyAsync(ow->cons.data(), h->o_cons.p, h->o_cons_n, cudaMemcpyDeviceToHost, h->stream);
-        if (e == cudaSuccess && h->o_solid_n) e = cudaMemcpyAsync(ow->sk.data(), h->o_sk.p, h->o_solid_n * 4, cudaMemcpyDeviceToHost, h->stream);
-        if (e == cudaSuccess && h->o_solid_n) e = cudaMemcpyAsync(ow->sc.data(), h->o_sc.p, h->o_solid_n * 4, cudaMemcpyDeviceToHost, h->stream);
+        e = cudaMemcpyAsync(r->cons_off, h->o_len.p, W * sizeof(u64), cudaMemcpyDeviceToHost, sd);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(r->solid_off, h->o_nsol.p, W * sizeof(u64), cudaMemcpyDeviceToHost, sd);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(r->status, h->o_status.p, W, cudaMemcpyDeviceToHost, sd);
+        if (e == cudaSuccess && h->o_cons_n) e = cudaMemcpyAsync(r->cons, h->o_cons.p, h->o_cons_n, cudaMemcpyDeviceToHost, sd);
+        if (e == cudaSuccess && h->o_solid_n) e = cudaMemcpyAsync(r->sk, h->o_sk.p, h->o_solid_n * 4, cudaMemcpyDeviceToHost, sd);
+        if (e == cudaSuccess && h->o_solid_n) e = cudaMemcpyAsync(r->sc, h->o_sc.p, h->o_solid_n * 4, cudaMemcpyDeviceToHost, sd);
     }
-    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-    if (e != cudaSuccess) { h->err = std::string("download: ") + cudaGetErrorString(e); delete ow; return CG_ERR_CUDA; }
-    ow->cons_off[W] = h->o_cons_n; ow->solid_off[W] = h->o_solid_n;
-    out->n_windows = W; out->cons_off = ow->cons_off.data(); out->cons = ow->cons.data(); out->status = ow->status.data();
-    out->solid_off = ow->solid_off.data(); out->solid_kmer = ow->sk.data(); out->solid_count = ow->sc.data(); out->owner_ = ow;
+    if (e == cudaSuccess) e = cudaStreamSynchronize(sd);
+    if (e != cudaSuccess) { h->err = std::string("download: ") + cudaGetErrorString(e); give_back(h, r); return CG_ERR_CUDA; }
+    fill_results(h, r, out);
     return CG_OK;
 }
 
 void cg_free_results(cg_results* r) {
-    if (r && r->owner_) { delete static_cast<ResultOwner*>(r->owner_); r->owner_ = nullptr; }
+    if (!r || !r->owner_) return;
+    HostResults* hr = static_cast<HostResults*>(r->owner_);
+    r->owner_ = nullptr;
+    if (hr->orphan) host_results_release(hr);          // its handle is gone
+    else give_back(hr->owner, hr);
 }
 
+// H2D of chunk i+1, the kernels of chunk i and D2H of chunk i-1 overlap (three streams).
 int cg_correct_windows(cg_handle* h, const cg_batch* in, cg_results* out) {
-    int rc = cg_upload(h, in);
-    if (rc == CG_OK) rc = cg_run(h);
-    if (rc == CG_OK) rc = cg_download(h, out);
-    return rc;
+    if (!h || !out) return CG_ERR_INVALID_ARG;
+    int rc = upload_impl(h, in, false);
+    if (rc != CG_OK) return rc;
+    HostResults* r = nullptr;
+    rc = host_results_acquire(h, h->W, &r);
+    if (rc != CG_OK) { if (r) give_back(h, r); cudaStreamSynchronize(h->s_h2d); h->h2d_pending = false; return rc; }
+    h->stream_out = r;
+    rc = run_impl(h);
+    h->stream_out = nullptr;
+    h->h2d_pending = false;
+    cudaError_t e1 = cudaStreamSynchronize(h->s_h2d), e2 = cudaStreamSynchronize(h->s_d2h);
+    if (rc == CG_OK && (e1 != cudaSuccess || e2 != cudaSuccess)) { h->err = "transfer stream failed"; rc = CG_ERR_CUDA; }
+    if (rc == CG_OK && (!r->cons || !r->sk)) rc = host_results_reserve(h, r, 1, 1, 0, 0);      // zero windows
+    if (rc != CG_OK) { give_back(h, r); return rc; }
+    fill_results(h, r, out);
+    return CG_OK;
 }
 
 int cg_stage_ms(const cg_handle* h, float ms[CG_N_STAGES], uint32_t launches[CG_N_STAGES]) {

@@ -42,7 +42,7 @@ __device__ __forceinline__ u8* cg_smem_base() { return cg_dyn_smem_; }
 #endif
 
 struct CgPoaTierS { static constexpr u32 VCAP = 160, ECAP = 320, SCAP = 384, ALNCAP = 192, HCELLS = 2048, SEQCAP = 64, CTAS_PER_SM = 5; };
-struct CgPoaTierM { static constexpr u32 VCAP = 704, ECAP = 1408, SCAP = 1472, ALNCAP = 0, HCELLS = 0, SEQCAP = 256, CTAS_PER_SM = 2; };
+struct CgPoaTierM { static constexpr u32 VCAP = 320, ECAP = 640, SCAP = 704, ALNCAP = 0, HCELLS = 0, SEQCAP = 256, CTAS_PER_SM = 4; };
 
 template <class T> struct CgPoaSmemLayout {
     static constexpr u32 r16(u32 v) { return (v + 15u) / 16u * 16u; }

@@ -4,6 +4,17 @@
 
 __device__ __forceinline__ u64 cg_round_up(u64 v, u64 m) { return (v + m - 1) / m * m; }
 
+// Every sequence of the batch: offsets non-decreasing, length within CG_LEN_MAX (cg_upload reads the flags back).
+__global__ void k_validate(const u64* seq_off, u64 n_seqs, u32* flags) {
+    u32 f = 0;
+    for (u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x; s < n_seqs; s += (u64)gridDim.x * blockDim.x) {
+        const u64 a = seq_off[s], b = seq_off[s + 1];
+        if (b < a) f |= CG_FLAG_BAD_OFFSETS;
+        else if (b - a > CG_LEN_MAX) f |= CG_FLAG_CAPACITY;
+    }
+    if (f) atomicOr(flags, f);
+}
+
 // One thread per window: sizes and arena capacities (written into the off_* arrays, scanned by k_scan).
 __global__ void k_plan(CgChunk c) {
     u32 w = blockIdx.x * blockDim.x + threadIdx.x;

@@ -94,6 +94,9 @@ class Corrector:
         if rc != 0:
             raise ConsentError(rc, (self.lib.cg_last_error(self._h) or b"").decode())
 
+    def _free_results(self, r):
+        self.lib.cg_free_results(C.byref(r))
+
     def set_option(self, key: str, value: int):
         self._check(self.lib.cg_set_option(self._h, key.encode(), int(value)))
 
@@ -102,9 +105,7 @@ class Corrector:
         """Host buffers in, host buffers out (H2D, every kernel, D2H)."""
         cb, r = batch.c(), cg_results()
         self._check(self.lib.cg_correct_windows(self._h, C.byref(cb), C.byref(r)))
-        out = Results(r)
-        self.lib.cg_free_results(C.byref(r))
-        return out
+        return Results(r, free=self._free_results)
 
     # -- staged (bench: keep the batch resident in HBM, time the kernels alone) ---------------
     def upload(self, batch: Batch):
@@ -117,9 +118,7 @@ class Corrector:
     def download(self) -> Results:
         r = cg_results()
         self._check(self.lib.cg_download(self._h, C.byref(r)))
-        out = Results(r)
-        self.lib.cg_free_results(C.byref(r))
-        return out
+        return Results(r, free=self._free_results)
 
     # -- instrumentation ----------------------------------------------------------------------
     def stage_ms(self) -> dict:
