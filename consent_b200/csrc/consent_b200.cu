@@ -21,6 +21,7 @@
 #include "k_chain.cuh"
 #include "k_split.cuh"
 #include "k_poa.cuh"
+#include "k_poa2.cuh"
 #include "k_polish.cuh"
 
 struct DevBuf {
@@ -99,8 +100,11 @@ struct cg_handle {
     bool uploaded = false, ran = false;
     // chunk workspaces
     DevBuf pwords, ptags, win, offs, solid_k, solid_c, slot_tpos, slot_kmer, anchors, chain, rel, pos, regions, arena, fin, visited;
-    DevBuf jobs_s, jobs_m, jobs_g, jobs_x, ctl, off_fin, out_off;
-    PoaTier tier_s, tier_m, tier[3];     // shared-memory small / medium tiers, then global tiers of growing size
+    DevBuf jobs_s, jobs_m, jobs_o, jobs_g, jobs_x, ctl, off_fin, out_off;
+    PoaTier tier_m, tier[3];             // graph-in-shared-memory tier, then global tiers of growing size (the compact tiers need no scratch)
+    u32 c1_warps = 0, c2_warps = 0;      // resident warps of the two compact (all shared memory) POA tiers
+    cudaStream_t s_poa = nullptr;        // second compact tier runs beside the first
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // batch outputs (device, dense)
     DevBuf o_cons, o_sk, o_sc, o_status, o_len, o_nsol;
     u64 o_cons_n = 0, o_solid_n = 0;
@@ -128,8 +132,9 @@ std::string g_create_err;
 
 inline u64 round_up(u64 v, u64 m) { return (v + m - 1) / m * m; }
 
-// ctl layout (u32 words, device): [0] flags, [4 + 4t ..] queue t {jobs, next, -, -}: t = 0 small, 1 medium, 2..4 global tiers
-enum { CTL_FLAGS = 0, CTL_VFLAGS = 1, CTL_Q = 4, CTL_WORDS = 32 };
+// ctl layout (u32 words, device): [0] flags, [1] upload-validation flags, [4 + 4t ..] queue t {front jobs, next, back jobs, capacity}:
+// t = 0 compact tier 1, 1 compact tier 2, 2 compact tier 2 (what tier 1 re-queued), 3 graph-in-smem tier, 4..6 global tiers
+enum { CTL_FLAGS = 0, CTL_VFLAGS = 1, CTL_Q = 4, CTL_NQ = 8, CTL_WORDS = 40, HCTL_STAGE = 64, HCTL_VFLAGS = 120, HCTL_WORDS = 128 };
 // offs layout (u64 arrays of nwin+1): solid, slot, pos, reg, arena
 // out_off layout: cons_off[nwin+1], solid_off[nwin+1]
 
@@ -231,6 +236,7 @@ int run_chunk(cg_handle* h, size_t ci, std::vector<StageSpan>& spans, std::vecto
     CK(h->visited.ensure((cp.solid_tot / 32 + nwin + 2) * 4));
     CK(h->jobs_s.ensure(cp.reg_tot * sizeof(uint2) + 16)); CK(h->jobs_m.ensure(cp.reg_tot * sizeof(uint2) + 16));
     CK(h->jobs_g.ensure(cp.reg_tot * sizeof(uint2) + 16)); CK(h->jobs_x.ensure(cp.reg_tot * sizeof(uint2) + 16));
+    CK(h->jobs_o.ensure(cp.reg_tot * sizeof(uint2) + 16));
     CK(h->off_fin.ensure(sizeof(u64) * (nwin + 1)));
     CK(h->out_off.ensure(sizeof(u64) * 2 * (nwin + 1)));
 
@@ -260,10 +266,10 @@ int run_chunk(cg_handle* h, size_t ci, std::vector<StageSpan>& spans, std::vecto
     // ---- stage 0: plan, offsets, pack
     span_begin(CG_STAGE_PACK);
     {
-        u32 qinit[20] = {0};
-        for (int t = 0; t < 5; ++t) qinit[4 * t + 3] = (u32)cp.reg_tot;
-        memcpy(h->h_ctl + 32, qinit, sizeof qinit);                      // pinned staging, consumed before the next chunk's sync
-        CK(cudaMemcpyAsync(ctl + CTL_Q, h->h_ctl + 32, sizeof qinit, cudaMemcpyHostToDevice, st));
+        u32 qinit[4 * CTL_NQ] = {0};
+        for (int t = 0; t < CTL_NQ; ++t) qinit[4 * t + 3] = (u32)cp.reg_tot;
+        memcpy(h->h_ctl + HCTL_STAGE, qinit, sizeof qinit);              // pinned staging, consumed before the next chunk's sync
+        CK(cudaMemcpyAsync(ctl + CTL_Q, h->h_ctl + HCTL_STAGE, sizeof qinit, cudaMemcpyHostToDevice, st));
     }
     CK(cudaMemsetAsync(h->pwords.as<u32>() + cp.nwords, 0, 16 * 4, st));
     CK(cudaMemsetAsync(h->ptags.as<u32>() + cp.nwords, 0xff, 16 * 4, st));
@@ -291,40 +297,49 @@ int run_chunk(cg_handle* h, size_t ci, std::vector<StageSpan>& spans, std::vecto
     h->stage_launches[CG_STAGE_SPLIT] += 1;
     span_end();
 
-    // ---- POA: small (shared memory) -> medium (graph in shared memory) -> global tier 0; each re-queues what it cannot hold
+    // ---- POA.  Compact tiers (everything in shared memory): the second one (big regions, long jobs) starts first on
+    // its own stream so that its tail overlaps the bulk of the first; what the first re-queues goes through the
+    // second tier's kernel once more; then the graph-in-shared-memory tier and the global tiers take what is left.
     span_begin(CG_STAGE_POA);
-    { int rc = ensure_tier(h, h->tier_s); if (rc) return rc; }
     { int rc = ensure_tier(h, h->tier_m); if (rc) return rc; }
     { int rc = ensure_tier(h, h->tier[0]); if (rc) return rc; }
     u32* q = ctl + CTL_Q;
-    CG_LAUNCH(k_poa_smem<CgPoaTierS>, (h->tier_s.warps + CG_POA_WARPS_PER_CTA - 1) / CG_POA_WARPS_PER_CTA, CG_POA_THREADS,
-              CgPoaSmemLayout<CgPoaTierS>::cta_bytes, st, c, h->tier_s.desc.as<CgPoaScratch>(), h->tier_s.warps, (const uint2*)c.jobs_s, q + 0,
-              c.jobs_m, q + 4);
+    uint2* jobs_o = h->jobs_o.as<uint2>(); uint2* jobs_x = h->jobs_x.as<uint2>();
+    CK(cudaEventRecord(h->ev_fork, st));
+    CK(cudaStreamWaitEvent(h->s_poa, h->ev_fork, 0));
+    CG_LAUNCH(k_poa2<CgPoa2C2>, (h->c2_warps + CgPoa2C2::WARPS - 1) / CgPoa2C2::WARPS, CgPoa2C2::WARPS * 32, CgPoa2Lay<CgPoa2C2>::cta_bytes, h->s_poa,
+              c, h->c2_warps, (const uint2*)c.jobs_m, q + 4, c.jobs_g, q + 12);
+    CG_LAUNCH(k_poa2<CgPoa2C1>, (h->c1_warps + CgPoa2C1::WARPS - 1) / CgPoa2C1::WARPS, CgPoa2C1::WARPS * 32, CgPoa2Lay<CgPoa2C1>::cta_bytes, st,
+              c, h->c1_warps, (const uint2*)c.jobs_s, q + 0, jobs_o, q + 8);
+    CK(cudaEventRecord(h->ev_join, h->s_poa));
+    CK(cudaStreamWaitEvent(st, h->ev_join, 0));
+    CG_LAUNCH(k_poa2<CgPoa2C2>, (h->c2_warps + CgPoa2C2::WARPS - 1) / CgPoa2C2::WARPS, CgPoa2C2::WARPS * 32, CgPoa2Lay<CgPoa2C2>::cta_bytes, st,
+              c, h->c2_warps, (const uint2*)jobs_o, q + 8, c.jobs_g, q + 12);
     CG_LAUNCH(k_poa_smem<CgPoaTierM>, (h->tier_m.warps + CG_POA_WARPS_PER_CTA - 1) / CG_POA_WARPS_PER_CTA, CG_POA_THREADS,
-              CgPoaSmemLayout<CgPoaTierM>::cta_bytes, st, c, h->tier_m.desc.as<CgPoaScratch>(), h->tier_m.warps, (const uint2*)c.jobs_m, q + 4,
-              c.jobs_g, q + 8);
+              CgPoaSmemLayout<CgPoaTierM>::cta_bytes, st, c, h->tier_m.desc.as<CgPoaScratch>(), h->tier_m.warps, (const uint2*)c.jobs_g, q + 12,
+              jobs_x, q + 16);
     CG_LAUNCH(k_poa, (h->tier[0].warps + CG_POA_WARPS_PER_CTA - 1) / CG_POA_WARPS_PER_CTA, CG_POA_THREADS, 0, st, c,
-              h->tier[0].desc.as<CgPoaScratch>(), h->tier[0].warps, (const uint2*)c.jobs_g, q + 8, h->jobs_x.as<uint2>(), q + 12);
-    h->stage_launches[CG_STAGE_POA] += 3;
+              h->tier[0].desc.as<CgPoaScratch>(), h->tier[0].warps, (const uint2*)jobs_x, q + 16, c.jobs_g, q + 20);
+    h->stage_launches[CG_STAGE_POA] += 5;
     span_end();
 
     // larger global tiers: only if something outgrew tier 0 (needs the count on the host)
     CK(cudaMemcpyAsync(h->h_ctl, ctl, CTL_WORDS * sizeof(u32), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (getenv("CG_DEBUG"))
-        fprintf(stderr, "[consent_b200] chunk w0=%u nwin=%u POA jobs: small %u+%u, medium %u+%u (front incl. re-queued), global0 %u, global1 %u\n",
+        fprintf(stderr, "[consent_b200] chunk w0=%u nwin=%u POA jobs (front+back): compact1 %u+%u, compact2 %u+%u, compact2 again %u, smem-graph %u, global0 %u, global1 %u\n",
                 cp.w0, nwin, h->h_ctl[CTL_Q + 0], h->h_ctl[CTL_Q + 2], h->h_ctl[CTL_Q + 4], h->h_ctl[CTL_Q + 6], h->h_ctl[CTL_Q + 8],
-                h->h_ctl[CTL_Q + 12]);
-    uint2* q_in = h->jobs_x.as<uint2>(); uint2* q_out = c.jobs_g;
+                h->h_ctl[CTL_Q + 12], h->h_ctl[CTL_Q + 16], h->h_ctl[CTL_Q + 20]);
+    uint2* q_in = c.jobs_g; uint2* q_out = jobs_x;
     for (int t = 1; t <= 2; ++t) {
-        const u32 over = h->h_ctl[CTL_Q + 4 * (t + 2)];
+        const u32 over = h->h_ctl[CTL_Q + 4 * (t + 4)];
         if (!over) break;
         if (h->tier[t].warps == 0) { h->err = "a POA job outgrew the largest enabled scratch tier"; return CG_ERR_CAPACITY; }
         { int rc = ensure_tier(h, h->tier[t]); if (rc) return rc; }
         span_begin(CG_STAGE_POA);
         CG_LAUNCH(k_poa, (h->tier[t].warps + CG_POA_WARPS_PER_CTA - 1) / CG_POA_WARPS_PER_CTA, CG_POA_THREADS, 0, st, c,
-                  h->tier[t].desc.as<CgPoaScratch>(), h->tier[t].warps, (const uint2*)q_in, q + 4 * (t + 2), t < 2 ? q_out : (uint2*)nullptr,
-                  q + 4 * (t + 3));
+                  h->tier[t].desc.as<CgPoaScratch>(), h->tier[t].warps, (const uint2*)q_in, q + 4 * (t + 4), t < 2 ? q_out : (uint2*)nullptr,
+                  q + 4 * (t + 5));
         h->stage_launches[CG_STAGE_POA] += 1;
         span_end();
         CK(cudaMemcpyAsync(h->h_ctl, ctl, CTL_WORDS * sizeof(u32), cudaMemcpyDeviceToHost, st));
@@ -504,18 +519,22 @@ int cg_create(int device, const cg_params* params, cg_handle** out) {
     ok = ok && cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&h->ev_gather, cudaEventDisableTiming) == cudaSuccess;
-    ok = ok && cudaMallocHost(&h->h_ctl, 64 * sizeof(u32)) == cudaSuccess;
+    ok = ok && cudaMallocHost(&h->h_ctl, HCTL_WORDS * sizeof(u32)) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&h->s_poa, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreate(&h->ev_run[0]) == cudaSuccess && cudaEventCreate(&h->ev_run[1]) == cudaSuccess;
     ok = ok && h->ctl.ensure(CTL_WORDS * sizeof(u32) + sizeof(CgCountersDev)) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_index, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CG_IDX_SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin) == cudaSuccess;
     if (!ok) { g_create_err = std::string("CUDA initialisation failed: ") + cudaGetErrorString(cudaGetLastError()); cg_destroy(h); return CG_ERR_CUDA; }
-    ok = cudaFuncSetAttribute(k_poa_smem<CgPoaTierS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CgPoaSmemLayout<CgPoaTierS>::cta_bytes) == cudaSuccess &&
+    ok = cudaFuncSetAttribute(k_poa2<CgPoa2C1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CgPoa2Lay<CgPoa2C1>::cta_bytes) == cudaSuccess &&
+         cudaFuncSetAttribute(k_poa2<CgPoa2C2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CgPoa2Lay<CgPoa2C2>::cta_bytes) == cudaSuccess &&
          cudaFuncSetAttribute(k_poa_smem<CgPoaTierM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CgPoaSmemLayout<CgPoaTierM>::cta_bytes) == cudaSuccess;
     if (!ok) { g_create_err = std::string("CUDA initialisation failed: ") + cudaGetErrorString(cudaGetLastError()); cg_destroy(h); return CG_ERR_CUDA; }
     // POA scratch tiers.  Shared-memory tiers keep only the segment list (small) or segment list + matrix + alignment (medium)
     // in global memory; the global tiers keep everything there: {nodes, edges, max segment length, matrix cells, resident warps}.
-    h->tier_s.lcap = CG_LEN_MAX; h->tier_s.warps = (u32)h->sms * CgPoaTierS::CTAS_PER_SM * CG_POA_WARPS_PER_CTA;
+    h->c1_warps = (u32)h->sms * CgPoa2C1::CTAS_PER_SM * CgPoa2C1::WARPS;
+    h->c2_warps = (u32)h->sms * CgPoa2C2::CTAS_PER_SM * CgPoa2C2::WARPS;
     h->tier_m.lcap = CG_LEN_MAX; h->tier_m.hcap = 512u << 10; h->tier_m.warps = (u32)h->sms * CgPoaTierM::CTAS_PER_SM * CG_POA_WARPS_PER_CTA;
     h->tier[0].vcap = 2048;  h->tier[0].ecap = 8192;   h->tier[0].lcap = CG_LEN_MAX; h->tier[0].hcap = 2u << 20;
     h->tier[1].vcap = 16384; h->tier[1].ecap = 65536;  h->tier[1].lcap = CG_LEN_MAX; h->tier[1].hcap = 32u << 20;
@@ -544,10 +563,13 @@ void cg_destroy(cg_handle* h) {
     if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
     DevBuf* bufs[] = {&h->d_bases, &h->d_seq_off, &h->d_wsb, &h->pwords, &h->ptags, &h->win, &h->offs, &h->solid_k, &h->solid_c, &h->slot_tpos,
                       &h->slot_kmer, &h->anchors, &h->chain, &h->rel, &h->pos, &h->regions, &h->arena, &h->fin, &h->visited, &h->jobs_s,
-                      &h->jobs_m, &h->jobs_g, &h->jobs_x, &h->ctl, &h->off_fin, &h->out_off, &h->o_cons, &h->o_sk, &h->o_sc, &h->o_status, &h->o_len, &h->o_nsol};
+                      &h->jobs_m, &h->jobs_o, &h->jobs_g, &h->jobs_x, &h->ctl, &h->off_fin, &h->out_off, &h->o_cons, &h->o_sk, &h->o_sc, &h->o_status, &h->o_len, &h->o_nsol};
     for (DevBuf* b : bufs) b->release();
     for (auto& t : h->tier) { t.mem.release(); t.desc.release(); }
-    h->tier_s.mem.release(); h->tier_s.desc.release(); h->tier_m.mem.release(); h->tier_m.desc.release();
+    h->tier_m.mem.release(); h->tier_m.desc.release();
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->s_poa) { cudaStreamSynchronize(h->s_poa); cudaStreamDestroy(h->s_poa); }
     for (auto& e : h->ev_run) if (e) cudaEventDestroy(e);
     if (h->h_ctl) cudaFreeHost(h->h_ctl);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -559,7 +581,8 @@ int cg_set_option(cg_handle* h, const char* key, long long value) {
     const std::string k(key);
     if (k == "chunk_budget_bytes") h->chunk_budget = (size_t)value;
     else if (k == "chunk_max_windows") h->chunk_max_windows = (u32)std::max<long long>(1, value);
-    else if (k == "poa_small_warps") { h->tier_s.warps = (u32)std::max<long long>(1, value); h->tier_s.ready = false; }
+    else if (k == "poa_small_warps" || k == "poa_compact1_warps") h->c1_warps = (u32)std::max<long long>(1, value);
+    else if (k == "poa_compact2_warps") h->c2_warps = (u32)std::max<long long>(1, value);
     else if (k == "poa_medium_warps") { h->tier_m.warps = (u32)std::max<long long>(1, value); h->tier_m.ready = false; }
     else if (k == "poa_medium_cells") { h->tier_m.hcap = (u64)value; h->tier_m.ready = false; }
     else if (k == "poa_tier0_warps") { h->tier[0].warps = (u32)std::max<long long>(1, value); h->tier[0].ready = false; }
@@ -622,7 +645,7 @@ int upload_impl(cg_handle* h, const cg_batch* in, bool wait) {
     u32* vflags = h->ctl.as<u32>() + CTL_VFLAGS;
     CK(cudaMemsetAsync(vflags, 0, sizeof(u32), sc));
     if (n_seqs) CG_LAUNCH(k_validate, (u32)std::min<u64>((n_seqs + 255) / 256, 4096), 256, 0, sc, h->d_seq_off.as<u64>(), n_seqs, vflags);
-    CK(cudaMemcpyAsync(h->h_ctl + 60, vflags, sizeof(u32), cudaMemcpyDeviceToHost, sc));
+    CK(cudaMemcpyAsync(h->h_ctl + HCTL_VFLAGS, vflags, sizeof(u32), cudaMemcpyDeviceToHost, sc));
     plan_chunks(h);
     while (h->ev_h2d.size() < h->chunks.size()) {
         cudaEvent_t e;
@@ -630,8 +653,8 @@ int upload_impl(cg_handle* h, const cg_batch* in, bool wait) {
         h->ev_h2d.push_back(e);
     }
     CK(cudaStreamSynchronize(sc));
-    if (h->h_ctl[60] & CG_FLAG_BAD_OFFSETS) { h->err = "seq_off must be non-decreasing"; return CG_ERR_INVALID_ARG; }
-    if (h->h_ctl[60] & CG_FLAG_CAPACITY) { h->err = "a sequence is longer than 6000 bases"; return CG_ERR_CAPACITY; }
+    if (h->h_ctl[HCTL_VFLAGS] & CG_FLAG_BAD_OFFSETS) { h->err = "seq_off must be non-decreasing"; return CG_ERR_INVALID_ARG; }
+    if (h->h_ctl[HCTL_VFLAGS] & CG_FLAG_CAPACITY) { h->err = "a sequence is longer than 6000 bases"; return CG_ERR_CAPACITY; }
     for (size_t ci = 0; ci < h->chunks.size(); ++ci) {
         const ChunkPlan& cp = h->chunks[ci];
         const u64 b0 = h->h_wbase[cp.w0], b1 = h->h_wbase[cp.w0 + cp.nwin];

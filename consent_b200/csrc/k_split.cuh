@@ -15,9 +15,23 @@
 
 #define CG_SPLIT_THREADS 256u
 #define CG_SPLIT_WARPS (CG_SPLIT_THREADS / 32u)
-#define CG_POA_SMALL_LEN 32u       // longest segment of a job that starts in the shared-memory (small) POA tier
-#define CG_POA_SMALL_HEAVY 480u    // sequences x longest segment: front of the small queue
-#define CG_POA_MEDIUM_HEAVY 4000u  // front of the medium queue
+// POA job routing.  The final graph size of a region is predicted from its longest segment L and its depth n
+// (fit on PacBio-profile piles: V ~ 1.52 L + 0.022 L n - 7, +12 % margin); a wrong guess only costs a re-queue.
+// class 0/1: first compact tier (heavy / light), 2/3: second compact tier (heavy / light).
+#define CG_POA_C1_LCAP 64u
+#define CG_POA_C1_VCAP 128u
+#define CG_POA_C1_CELLS 2048u
+#define CG_POA_C1_HEAVY 24000u     // sequences x predicted cells: front of the queue (drained first)
+#define CG_POA_C2_HEAVY 200000u
+__device__ __forceinline__ u32 cg_poa_class(u32 n, u32 L) {
+    u32 vhat = (L * (1557u + 23u * n)) >> 10;
+    vhat = vhat > 8u ? vhat - 7u : 1u;
+    vhat += vhat >> 3;
+    const u32 cells = (vhat + 1u) * (L + 1u);
+    const u32 cost = n * cells;
+    const bool c1 = L <= CG_POA_C1_LCAP && vhat <= CG_POA_C1_VCAP && cells <= CG_POA_C1_CELLS;
+    return c1 ? (cost >= CG_POA_C1_HEAVY ? 0u : 1u) : (cost >= CG_POA_C2_HEAVY ? 2u : 3u);
+}
 
 // idx-th smallest (0-based) distance of the pair (s1,s2) over reads holding both.
 __device__ __forceinline__ u32 cg_select_distance(const u16* pos, u32 C, u32 N, u32 s1, u32 s2, u32 nbits, u32 idx) {
@@ -144,11 +158,7 @@ __global__ void __launch_bounds__(CG_SPLIT_THREADS) k_split(CgChunk c) {
     for (u32 gb = 0; gb < nreg; gb += 32) {
         const u32 g = gb + lane;
         u32 cls = 4;
-        if (g < nreg && regs[g].kind == CG_REG_POA) {
-            const bool small = regs[g].max_len <= CG_POA_SMALL_LEN;
-            const u32 cost = regs[g].n * regs[g].max_len;
-            cls = small ? (cost >= CG_POA_SMALL_HEAVY ? 0u : 1u) : (cost >= CG_POA_MEDIUM_HEAVY ? 2u : 3u);
-        }
+        if (g < nreg && regs[g].kind == CG_REG_POA) cls = cg_poa_class(regs[g].n, regs[g].max_len);
 #pragma unroll
         for (u32 q = 0; q < 4; ++q) cnt4[q] += __popc(__ballot_sync(CG_FULL, cls == q));
     }
@@ -168,11 +178,7 @@ __global__ void __launch_bounds__(CG_SPLIT_THREADS) k_split(CgChunk c) {
         const u32 g = gb + lane;
         const bool isp = g < nreg && regs[g].kind == CG_REG_POA;
         u32 cls = 4;
-        if (isp) {
-            const bool small = regs[g].max_len <= CG_POA_SMALL_LEN;
-            const u32 cost = regs[g].n * regs[g].max_len;
-            cls = small ? (cost >= CG_POA_SMALL_HEAVY ? 0u : 1u) : (cost >= CG_POA_MEDIUM_HEAVY ? 2u : 3u);
-        }
+        if (isp) cls = cg_poa_class(regs[g].n, regs[g].max_len);
         const u32 sz = isp ? regs[g].sum_len : 0u;
         const u32 inc = cg_warp_scan(sz);
         u32 my = 0;
