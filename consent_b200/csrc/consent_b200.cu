@@ -100,11 +100,12 @@ struct cg_handle {
     bool uploaded = false, ran = false;
     // chunk workspaces
     DevBuf pwords, ptags, win, offs, solid_k, solid_c, slot_tpos, slot_kmer, anchors, chain, rel, pos, regions, arena, fin, visited;
-    DevBuf jobs_s, jobs_m, jobs_o, jobs_g, jobs_x, ctl, off_fin, out_off;
-    PoaTier tier_m, tier[3];             // graph-in-shared-memory tier, then global tiers of growing size (the compact tiers need no scratch)
-    u32 c1_warps = 0, c2_warps = 0;      // resident warps of the two compact (all shared memory) POA tiers
-    cudaStream_t s_poa = nullptr;        // second compact tier runs beside the first
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    DevBuf jobs_s, jobs_m, jobs_3, jobs_w, jobs_r, jobs_x, ctl, off_fin, out_off;
+    PoaTier tier[3];                     // k_poa.cuh: global-memory tiers without an in-degree limit (the last resort); [0] unused
+    u32 c1_warps = 0, c2_warps = 0, c3_warps = 0, w1_warps = 0, w2_warps = 0;   // resident warps of the k_poa2.cuh tiers
+    DevBuf w2_mem;                       // per-warp scratch of the global-memory wide tier
+    cudaStream_t s_poa[3] = {nullptr, nullptr, nullptr};   // compact 2, compact 3 and wide 1 run beside compact 1
+    cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
     // batch outputs (device, dense)
     DevBuf o_cons, o_sk, o_sc, o_status, o_len, o_nsol;
     u64 o_cons_n = 0, o_solid_n = 0;
@@ -133,8 +134,9 @@ std::string g_create_err;
 inline u64 round_up(u64 v, u64 m) { return (v + m - 1) / m * m; }
 
 // ctl layout (u32 words, device): [0] flags, [1] upload-validation flags, [4 + 4t ..] queue t {front jobs, next, back jobs, capacity}:
-// t = 0 compact tier 1, 1 compact tier 2, 2 compact tier 2 (what tier 1 re-queued), 3 graph-in-smem tier, 4..6 global tiers
-enum { CTL_FLAGS = 0, CTL_VFLAGS = 1, CTL_Q = 4, CTL_NQ = 8, CTL_WORDS = 40, HCTL_STAGE = 64, HCTL_VFLAGS = 120, HCTL_WORDS = 128 };
+// t = 0 compact 1, 1 compact 2, 2 compact 3, 3 wide 1 (filled by k_split); 4 what the compact tiers re-queued (-> compact 3 again),
+// 5 -> wide 1 again, 6 -> wide 2, 7 -> k_poa tier 1, 8 -> k_poa tier 2
+enum { CTL_FLAGS = 0, CTL_VFLAGS = 1, CTL_Q = 4, CTL_NQ = 10, CTL_WORDS = 48, HCTL_STAGE = 64, HCTL_VFLAGS = 120, HCTL_WORDS = 128 };
 // offs layout (u64 arrays of nwin+1): solid, slot, pos, reg, arena
 // out_off layout: cons_off[nwin+1], solid_off[nwin+1]
 
@@ -234,9 +236,7 @@ int run_chunk(cg_handle* h, size_t ci, std::vector<StageSpan>& spans, std::vecto
     CK(h->regions.ensure(cp.reg_tot * sizeof(CgRegion) + 16));
     CK(h->arena.ensure(cp.arena_tot + 16));
     CK(h->visited.ensure((cp.solid_tot / 32 + nwin + 2) * 4));
-    CK(h->jobs_s.ensure(cp.reg_tot * sizeof(uint2) + 16)); CK(h->jobs_m.ensure(cp.reg_tot * sizeof(uint2) + 16));
-    CK(h->jobs_g.ensure(cp.reg_tot * sizeof(uint2) + 16)); CK(h->jobs_x.ensure(cp.reg_tot * sizeof(uint2) + 16));
-    CK(h->jobs_o.ensure(cp.reg_tot * sizeof(uint2) + 16));
+    for (DevBuf* jb : {&h->jobs_s, &h->jobs_m, &h->jobs_3, &h->jobs_w, &h->jobs_r, &h->jobs_x}) CK(jb->ensure(cp.reg_tot * sizeof(uint2) + 16));
     CK(h->off_fin.ensure(sizeof(u64) * (nwin + 1)));
     CK(h->out_off.ensure(sizeof(u64) * 2 * (nwin + 1)));
 
@@ -254,7 +254,8 @@ int run_chunk(cg_handle* h, size_t ci, std::vector<StageSpan>& spans, std::vecto
     c.chain = h->chain.as<u16>(); c.rel = h->rel.as<u32>(); c.pos = h->pos.as<u16>();
     c.regions = h->regions.as<CgRegion>(); c.arena = h->arena.as<u8>(); c.fin = nullptr; c.visited = h->visited.as<u32>();
     u32* ctl = h->ctl.as<u32>();
-    c.qctl = ctl + CTL_Q; c.jobs_s = h->jobs_s.as<uint2>(); c.jobs_m = h->jobs_m.as<uint2>(); c.jobs_g = h->jobs_g.as<uint2>();
+    c.qctl = ctl + CTL_Q; c.jobs_s = h->jobs_s.as<uint2>(); c.jobs_m = h->jobs_m.as<uint2>(); c.jobs_3 = h->jobs_3.as<uint2>();
+    c.jobs_w = h->jobs_w.as<uint2>();
     c.flags = ctl + CTL_FLAGS;
     c.counters = (CgCountersDev*)(ctl + CTL_WORDS);
     u64* off_fin = h->off_fin.as<u64>();
@@ -297,49 +298,49 @@ int run_chunk(cg_handle* h, size_t ci, std::vector<StageSpan>& spans, std::vecto
     h->stage_launches[CG_STAGE_SPLIT] += 1;
     span_end();
 
-    // ---- POA.  Compact tiers (everything in shared memory): the second one (big regions, long jobs) starts first on
-    // its own stream so that its tail overlaps the bulk of the first; what the first re-queues goes through the
-    // second tier's kernel once more; then the graph-in-shared-memory tier and the global tiers take what is left.
+    // ---- POA (k_poa2.cuh).  k_split routed every region to the tier its predicted size fits; the four tiers run side by
+    // side (the big, long-running jobs are launched first so that their tail overlaps the bulk of the small ones).  What a
+    // tier cannot hold after all is re-queued: compact -> compact 3 -> wide 1 -> wide 2 (global memory) -> k_poa.
     span_begin(CG_STAGE_POA);
-    { int rc = ensure_tier(h, h->tier_m); if (rc) return rc; }
-    { int rc = ensure_tier(h, h->tier[0]); if (rc) return rc; }
     u32* q = ctl + CTL_Q;
-    uint2* jobs_o = h->jobs_o.as<uint2>(); uint2* jobs_x = h->jobs_x.as<uint2>();
+    uint2* jobs_r = h->jobs_r.as<uint2>(); uint2* jobs_x = h->jobs_x.as<uint2>();
+    uint2* jobs_q5 = c.jobs_s; uint2* jobs_q7 = c.jobs_m; uint2* jobs_q8 = c.jobs_3;      // re-used once their first life is over
+    CK(h->w2_mem.ensure(CgPoa2Lay<CgPoa2W2>::per_warp * (size_t)h->w2_warps));
+#define CG_POA2_LAUNCH(TIER, warps, stream, jin, qin, jout, qout)                                                               \
+    CG_LAUNCH(k_poa2<TIER>, ((warps) + TIER::WARPS - 1) / TIER::WARPS, TIER::WARPS * 32, CgPoa2Lay<TIER>::cta_bytes, stream, c, \
+              TIER::SMEM ? (u8*)nullptr : h->w2_mem.as<u8>(), (warps), (const uint2*)(jin), q + 4 * (qin), (jout), q + 4 * (qout))
     CK(cudaEventRecord(h->ev_fork, st));
-    CK(cudaStreamWaitEvent(h->s_poa, h->ev_fork, 0));
-    CG_LAUNCH(k_poa2<CgPoa2C2>, (h->c2_warps + CgPoa2C2::WARPS - 1) / CgPoa2C2::WARPS, CgPoa2C2::WARPS * 32, CgPoa2Lay<CgPoa2C2>::cta_bytes, h->s_poa,
-              c, h->c2_warps, (const uint2*)c.jobs_m, q + 4, c.jobs_g, q + 12);
-    CG_LAUNCH(k_poa2<CgPoa2C1>, (h->c1_warps + CgPoa2C1::WARPS - 1) / CgPoa2C1::WARPS, CgPoa2C1::WARPS * 32, CgPoa2Lay<CgPoa2C1>::cta_bytes, st,
-              c, h->c1_warps, (const uint2*)c.jobs_s, q + 0, jobs_o, q + 8);
-    CK(cudaEventRecord(h->ev_join, h->s_poa));
-    CK(cudaStreamWaitEvent(st, h->ev_join, 0));
-    CG_LAUNCH(k_poa2<CgPoa2C2>, (h->c2_warps + CgPoa2C2::WARPS - 1) / CgPoa2C2::WARPS, CgPoa2C2::WARPS * 32, CgPoa2Lay<CgPoa2C2>::cta_bytes, st,
-              c, h->c2_warps, (const uint2*)jobs_o, q + 8, c.jobs_g, q + 12);
-    CG_LAUNCH(k_poa_smem<CgPoaTierM>, (h->tier_m.warps + CG_POA_WARPS_PER_CTA - 1) / CG_POA_WARPS_PER_CTA, CG_POA_THREADS,
-              CgPoaSmemLayout<CgPoaTierM>::cta_bytes, st, c, h->tier_m.desc.as<CgPoaScratch>(), h->tier_m.warps, (const uint2*)c.jobs_g, q + 12,
-              jobs_x, q + 16);
-    CG_LAUNCH(k_poa, (h->tier[0].warps + CG_POA_WARPS_PER_CTA - 1) / CG_POA_WARPS_PER_CTA, CG_POA_THREADS, 0, st, c,
-              h->tier[0].desc.as<CgPoaScratch>(), h->tier[0].warps, (const uint2*)jobs_x, q + 16, c.jobs_g, q + 20);
-    h->stage_launches[CG_STAGE_POA] += 5;
+    for (int i = 0; i < 3; ++i) CK(cudaStreamWaitEvent(h->s_poa[i], h->ev_fork, 0));
+    CG_POA2_LAUNCH(CgPoa2W1, h->w1_warps, h->s_poa[2], c.jobs_w, 3, jobs_x, 6);
+    CG_POA2_LAUNCH(CgPoa2C3, h->c3_warps, h->s_poa[1], c.jobs_3, 2, jobs_r, 4);
+    CG_POA2_LAUNCH(CgPoa2C2, h->c2_warps, h->s_poa[0], c.jobs_m, 1, jobs_r, 4);
+    CG_POA2_LAUNCH(CgPoa2C1, h->c1_warps, st, c.jobs_s, 0, jobs_r, 4);
+    for (int i = 0; i < 3; ++i) { CK(cudaEventRecord(h->ev_join[i], h->s_poa[i])); CK(cudaStreamWaitEvent(st, h->ev_join[i], 0)); }
+    CG_POA2_LAUNCH(CgPoa2C3, h->c3_warps, st, jobs_r, 4, jobs_q5, 5);
+    CG_POA2_LAUNCH(CgPoa2W1, h->w1_warps, st, jobs_q5, 5, jobs_x, 6);
+    CG_POA2_LAUNCH(CgPoa2W2, h->w2_warps, st, jobs_x, 6, jobs_q7, 7);
+#undef CG_POA2_LAUNCH
+    h->stage_launches[CG_STAGE_POA] += 7;
     span_end();
 
-    // larger global tiers: only if something outgrew tier 0 (needs the count on the host)
+    // the last resort (in-degree > 8, > 4096 nodes, > 2048-base segments): only if something got that far (count on the host)
     CK(cudaMemcpyAsync(h->h_ctl, ctl, CTL_WORDS * sizeof(u32), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (getenv("CG_DEBUG"))
-        fprintf(stderr, "[consent_b200] chunk w0=%u nwin=%u POA jobs (front+back): compact1 %u+%u, compact2 %u+%u, compact2 again %u, smem-graph %u, global0 %u, global1 %u\n",
+        fprintf(stderr, "[consent_b200] chunk w0=%u nwin=%u POA jobs: compact1 %u+%u, compact2 %u+%u, compact3 %u, wide1 %u | re-queued: compact %u, "
+                "->wide1 %u, ->wide2 %u, ->k_poa %u\n",
                 cp.w0, nwin, h->h_ctl[CTL_Q + 0], h->h_ctl[CTL_Q + 2], h->h_ctl[CTL_Q + 4], h->h_ctl[CTL_Q + 6], h->h_ctl[CTL_Q + 8],
-                h->h_ctl[CTL_Q + 12], h->h_ctl[CTL_Q + 16], h->h_ctl[CTL_Q + 20]);
-    uint2* q_in = c.jobs_g; uint2* q_out = jobs_x;
+                h->h_ctl[CTL_Q + 12], h->h_ctl[CTL_Q + 16], h->h_ctl[CTL_Q + 20], h->h_ctl[CTL_Q + 24], h->h_ctl[CTL_Q + 28]);
+    uint2* q_in = jobs_q7; uint2* q_out = jobs_q8;
     for (int t = 1; t <= 2; ++t) {
-        const u32 over = h->h_ctl[CTL_Q + 4 * (t + 4)];
+        const u32 over = h->h_ctl[CTL_Q + 4 * (t + 6)];
         if (!over) break;
         if (h->tier[t].warps == 0) { h->err = "a POA job outgrew the largest enabled scratch tier"; return CG_ERR_CAPACITY; }
         { int rc = ensure_tier(h, h->tier[t]); if (rc) return rc; }
         span_begin(CG_STAGE_POA);
         CG_LAUNCH(k_poa, (h->tier[t].warps + CG_POA_WARPS_PER_CTA - 1) / CG_POA_WARPS_PER_CTA, CG_POA_THREADS, 0, st, c,
-                  h->tier[t].desc.as<CgPoaScratch>(), h->tier[t].warps, (const uint2*)q_in, q + 4 * (t + 4), t < 2 ? q_out : (uint2*)nullptr,
-                  q + 4 * (t + 5));
+                  h->tier[t].desc.as<CgPoaScratch>(), h->tier[t].warps, (const uint2*)q_in, q + 4 * (t + 6), t < 2 ? q_out : (uint2*)nullptr,
+                  q + 4 * (t + 7));
         h->stage_launches[CG_STAGE_POA] += 1;
         span_end();
         CK(cudaMemcpyAsync(h->h_ctl, ctl, CTL_WORDS * sizeof(u32), cudaMemcpyDeviceToHost, st));
@@ -520,8 +521,9 @@ int cg_create(int device, const cg_params* params, cg_handle** out) {
     ok = ok && cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&h->ev_gather, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaMallocHost(&h->h_ctl, HCTL_WORDS * sizeof(u32)) == cudaSuccess;
-    ok = ok && cudaStreamCreateWithFlags(&h->s_poa, cudaStreamNonBlocking) == cudaSuccess;
-    ok = ok && cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < 3; ++i)
+        ok = ok && cudaStreamCreateWithFlags(&h->s_poa[i], cudaStreamNonBlocking) == cudaSuccess && cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreate(&h->ev_run[0]) == cudaSuccess && cudaEventCreate(&h->ev_run[1]) == cudaSuccess;
     ok = ok && h->ctl.ensure(CTL_WORDS * sizeof(u32) + sizeof(CgCountersDev)) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_index, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CG_IDX_SMEM_BYTES) == cudaSuccess;
@@ -529,17 +531,18 @@ int cg_create(int device, const cg_params* params, cg_handle** out) {
     if (!ok) { g_create_err = std::string("CUDA initialisation failed: ") + cudaGetErrorString(cudaGetLastError()); cg_destroy(h); return CG_ERR_CUDA; }
     ok = cudaFuncSetAttribute(k_poa2<CgPoa2C1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CgPoa2Lay<CgPoa2C1>::cta_bytes) == cudaSuccess &&
          cudaFuncSetAttribute(k_poa2<CgPoa2C2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CgPoa2Lay<CgPoa2C2>::cta_bytes) == cudaSuccess &&
-         cudaFuncSetAttribute(k_poa_smem<CgPoaTierM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CgPoaSmemLayout<CgPoaTierM>::cta_bytes) == cudaSuccess;
+         cudaFuncSetAttribute(k_poa2<CgPoa2C3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CgPoa2Lay<CgPoa2C3>::cta_bytes) == cudaSuccess &&
+         cudaFuncSetAttribute(k_poa2<CgPoa2W1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CgPoa2Lay<CgPoa2W1>::cta_bytes) == cudaSuccess;
     if (!ok) { g_create_err = std::string("CUDA initialisation failed: ") + cudaGetErrorString(cudaGetLastError()); cg_destroy(h); return CG_ERR_CUDA; }
-    // POA scratch tiers.  Shared-memory tiers keep only the segment list (small) or segment list + matrix + alignment (medium)
-    // in global memory; the global tiers keep everything there: {nodes, edges, max segment length, matrix cells, resident warps}.
+    // POA tiers: resident warps of the k_poa2.cuh tiers; k_poa.cuh's global-memory tiers {nodes, edges, max segment length,
+    // matrix cells, resident warps} are the last resort.
     h->c1_warps = (u32)h->sms * CgPoa2C1::CTAS_PER_SM * CgPoa2C1::WARPS;
     h->c2_warps = (u32)h->sms * CgPoa2C2::CTAS_PER_SM * CgPoa2C2::WARPS;
-    h->tier_m.lcap = CG_LEN_MAX; h->tier_m.hcap = 512u << 10; h->tier_m.warps = (u32)h->sms * CgPoaTierM::CTAS_PER_SM * CG_POA_WARPS_PER_CTA;
-    h->tier[0].vcap = 2048;  h->tier[0].ecap = 8192;   h->tier[0].lcap = CG_LEN_MAX; h->tier[0].hcap = 2u << 20;
+    h->c3_warps = (u32)h->sms * CgPoa2C3::CTAS_PER_SM * CgPoa2C3::WARPS;
+    h->w1_warps = (u32)h->sms * CgPoa2W1::CTAS_PER_SM * CgPoa2W1::WARPS;
+    h->w2_warps = (u32)h->sms * 2;
     h->tier[1].vcap = 16384; h->tier[1].ecap = 65536;  h->tier[1].lcap = CG_LEN_MAX; h->tier[1].hcap = 32u << 20;
     h->tier[2].vcap = 65535; h->tier[2].ecap = 262144; h->tier[2].lcap = CG_LEN_MAX; h->tier[2].hcap = 400u << 20;
-    h->tier[0].warps = (u32)h->sms * 4;
     h->tier[1].warps = (u32)h->sms;
     h->tier[2].warps = 8;
     *out = h;
@@ -563,13 +566,14 @@ void cg_destroy(cg_handle* h) {
     if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
     DevBuf* bufs[] = {&h->d_bases, &h->d_seq_off, &h->d_wsb, &h->pwords, &h->ptags, &h->win, &h->offs, &h->solid_k, &h->solid_c, &h->slot_tpos,
                       &h->slot_kmer, &h->anchors, &h->chain, &h->rel, &h->pos, &h->regions, &h->arena, &h->fin, &h->visited, &h->jobs_s,
-                      &h->jobs_m, &h->jobs_o, &h->jobs_g, &h->jobs_x, &h->ctl, &h->off_fin, &h->out_off, &h->o_cons, &h->o_sk, &h->o_sc, &h->o_status, &h->o_len, &h->o_nsol};
+                      &h->jobs_m, &h->jobs_3, &h->jobs_w, &h->jobs_r, &h->w2_mem, &h->jobs_x, &h->ctl, &h->off_fin, &h->out_off, &h->o_cons, &h->o_sk, &h->o_sc, &h->o_status, &h->o_len, &h->o_nsol};
     for (DevBuf* b : bufs) b->release();
     for (auto& t : h->tier) { t.mem.release(); t.desc.release(); }
-    h->tier_m.mem.release(); h->tier_m.desc.release();
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
-    if (h->ev_join) cudaEventDestroy(h->ev_join);
-    if (h->s_poa) { cudaStreamSynchronize(h->s_poa); cudaStreamDestroy(h->s_poa); }
+    for (int i = 0; i < 3; ++i) {
+        if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
+        if (h->s_poa[i]) { cudaStreamSynchronize(h->s_poa[i]); cudaStreamDestroy(h->s_poa[i]); }
+    }
     for (auto& e : h->ev_run) if (e) cudaEventDestroy(e);
     if (h->h_ctl) cudaFreeHost(h->h_ctl);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -581,15 +585,13 @@ int cg_set_option(cg_handle* h, const char* key, long long value) {
     const std::string k(key);
     if (k == "chunk_budget_bytes") h->chunk_budget = (size_t)value;
     else if (k == "chunk_max_windows") h->chunk_max_windows = (u32)std::max<long long>(1, value);
-    else if (k == "poa_small_warps" || k == "poa_compact1_warps") h->c1_warps = (u32)std::max<long long>(1, value);
+    else if (k == "poa_compact1_warps") h->c1_warps = (u32)std::max<long long>(1, value);
     else if (k == "poa_compact2_warps") h->c2_warps = (u32)std::max<long long>(1, value);
-    else if (k == "poa_medium_warps") { h->tier_m.warps = (u32)std::max<long long>(1, value); h->tier_m.ready = false; }
-    else if (k == "poa_medium_cells") { h->tier_m.hcap = (u64)value; h->tier_m.ready = false; }
-    else if (k == "poa_tier0_warps") { h->tier[0].warps = (u32)std::max<long long>(1, value); h->tier[0].ready = false; }
+    else if (k == "poa_compact3_warps") h->c3_warps = (u32)std::max<long long>(1, value);
+    else if (k == "poa_wide1_warps") h->w1_warps = (u32)std::max<long long>(1, value);
+    else if (k == "poa_wide2_warps") h->w2_warps = (u32)std::max<long long>(1, value);
     else if (k == "poa_tier1_warps") { h->tier[1].warps = (u32)value; h->tier[1].ready = false; }
     else if (k == "poa_tier2_warps") { h->tier[2].warps = (u32)value; h->tier[2].ready = false; }
-    else if (k == "poa_tier0_nodes") { h->tier[0].vcap = (u32)value; h->tier[0].ecap = 4 * (u32)value; h->tier[0].ready = false; }
-    else if (k == "poa_tier0_cells") { h->tier[0].hcap = (u64)value; h->tier[0].ready = false; }
     else if (k == "poa_tier1_nodes") { h->tier[1].vcap = (u32)value; h->tier[1].ecap = 4 * (u32)value; h->tier[1].ready = false; }
     else if (k == "poa_tier1_cells") { h->tier[1].hcap = (u64)value; h->tier[1].ready = false; }
     else if (k == "poa_tier2_nodes") { h->tier[2].vcap = (u32)std::min<long long>(value, 65535); h->tier[2].ecap = 4 * h->tier[2].vcap; h->tier[2].ready = false; }

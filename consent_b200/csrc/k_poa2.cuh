@@ -1,5 +1,4 @@
-// k_poa2.cuh — segmented partial-order alignment for small graphs (<= 254 nodes), one warp per region, everything in
-// shared memory, and almost nothing left on a single lane.
+// k_poa2.cuh — segmented partial-order alignment, one warp per region, with almost nothing left on a single lane.
 //
 // Same reference semantics as k_poa.cuh (consensus_SPOA BMEAN/bmean.cpp:585-599, vote :649-694, spoa 4.0.0 kSW linear
 // m=5 n=-10 g=-4: simd_alignment_engine_impl.hpp:712-1056, Graph::add_alignment graph.cpp:155-272, add_sequence
@@ -13,112 +12,181 @@
 //    So this kernel maintains *a* valid topological order incrementally, in parallel (new nodes of an alignment are
 //    spliced in front of the column of the next node they lead to; columns stay contiguous), and runs the reference's
 //    DFS only when two rows tie for the maximum (~8 % of the alignments) and once before the vote.
-//  * Packed node records: node ids are bytes; in-edges are 8 inline bytes per node (in-degree > 8 leaves the tier);
-//    the aligned set (<= 3 others, one node per base in a column) shares a word with the in-degree.  Per row of the
-//    matrix there is a descriptor (letter, in-degree, first predecessor row, node) and the 8 predecessor ROW indices,
-//    rebuilt by all lanes after each change, so neither the DP nor the traceback chase pointers.
+//  * Packed node records: in-edges are 8 inline ids per node (in-degree > 8 leaves these tiers); the aligned set
+//    (<= 3 others, one node per base in a column) shares a word with the in-degree.  Per row of the matrix there is
+//    a descriptor (letter, in-degree, first predecessor row, node) and the 8 predecessor ROW indices, rebuilt by all
+//    lanes after each change, so neither the DP nor the traceback chase pointers.
 //  * Data-parallel graph update: every query position q maps to exactly one node (prefix chain, aligned part, suffix
 //    chain — the id order of graph.cpp:195-201 comes from a warp scan), each node is touched once per alignment, and
 //    there is an edge node(q-1) -> node(q) for every q: lanes over q, no conflicts.
-//  * Traceback is the only per-alignment phase left on lane 0 (a dependent walk by nature), at two shared-memory
-//    round trips per step.
+//  * Traceback is the only per-alignment phase left on lane 0 (a dependent walk by nature), at two memory round
+//    trips per step.
 //
-// A job that outgrows the tier (nodes, cells, in-degree, segment length) is re-queued for the next tier before
-// anything is committed.
+// Tiers (one template, T = ids x storage x capacities):
+//   C1, C2, C3 : byte ids (<= 254 nodes), everything in shared memory, 2048 / 8192 / 24576 matrix cells
+//   W1         : 16-bit ids (<= 1024 nodes), shared memory, 49152 cells, one warp per SM
+//   W2, W3     : 16-bit ids, per-warp scratch in global memory (L2), up to 65534 nodes / 6000-base segments
+// A job that outgrows its tier (nodes, cells, in-degree, segment length) is re-queued for the next one before anything
+// is committed; in-degree > 8 ends in k_poa (k_poa.cuh), which has no such limit.
 #pragma once
 #include "cg_common.cuh"
 #include "k_poa.cuh"
 
-template <u32 VCAP_, u32 HCELLS_, u32 LCAP_, u32 WARPS_, u32 CTAS_> struct CgPoa2Tier {
-    static constexpr u32 VCAP = VCAP_, HCELLS = HCELLS_, LCAP = LCAP_, WARPS = WARPS_, CTAS_PER_SM = CTAS_;
-    static constexpr u32 SEGCAP = 192, SCAP = 3 * VCAP_, ALNCAP = VCAP_ + LCAP_;
-};
-typedef CgPoa2Tier<128, 2048, 64, 4, 5> CgPoa2C1;     // 86 % of the regions of a 150-deep pile
-typedef CgPoa2Tier<254, 8192, 120, 4, 2> CgPoa2C2;    // 99.4 %
+// ------------------------------------------------------------------ id packing
+struct __align__(16) CgVec16 { u64 lo, hi; };
 
-#define CG_P2_NONE 0xffu
+template <class IdT> struct CgIdPack;
+template <> struct CgIdPack<u8> {
+    typedef u64 Vec;        // 8 ids
+    typedef u32 Meta;       // flags | 3 aligned ids
+    typedef u32 Rdesc;      // letter | in-degree << 8 | first predecessor row << 16 | node << 24
+    typedef u16 Item;       // DFS stack entry (id | finish flag), alignment pair (node | qpos << 8), splice item (pos | node << 8)
+    typedef u32 Seg;        // read | start << 12 | len << 25
+    static constexpr u32 W = 8, NONE = 0xffu;
+    __device__ __forceinline__ static u32 get(Vec v, u32 e) { return (u32)(v >> (8u * e)) & 0xffu; }
+    __device__ __forceinline__ static Vec set(Vec v, u32 e, u32 x) { return (v & ~(0xffull << (8u * e))) | ((u64)x << (8u * e)); }
+    __device__ __forceinline__ static Vec none() { return ~0ull; }
+    __device__ __forceinline__ static Vec zero() { return 0ull; }
+    __device__ __forceinline__ static u32 first(Vec v) { return (u32)v & 0xffu; }
+    __device__ __forceinline__ static Seg seg_pack(u32 read, u32 start, u32 len) { return read | (start << 12) | (len << 25); }
+    __device__ __forceinline__ static u32 seg_read(Seg s) { return s & 0xfffu; }
+    __device__ __forceinline__ static u32 seg_start(Seg s) { return (s >> 12) & 0x1fffu; }
+    __device__ __forceinline__ static u32 seg_len(Seg s) { return s >> 25; }
+};
+template <> struct CgIdPack<u16> {
+    typedef CgVec16 Vec;
+    typedef u64 Meta;
+    typedef u64 Rdesc;      // letter | in-degree << 8 | first predecessor row << 16 | node << 32
+    typedef u32 Item;
+    typedef u64 Seg;        // read | start << 16 | len << 32
+    static constexpr u32 W = 16, NONE = 0xffffu;
+    __device__ __forceinline__ static u32 get(const Vec& v, u32 e) { return (u32)((e < 4 ? v.lo : v.hi) >> (16u * (e & 3u))) & 0xffffu; }
+    __device__ __forceinline__ static Vec set(Vec v, u32 e, u32 x) {
+        const u64 m = ~(0xffffull << (16u * (e & 3u))), b = (u64)x << (16u * (e & 3u));
+        if (e < 4) v.lo = (v.lo & m) | b; else v.hi = (v.hi & m) | b;
+        return v;
+    }
+    __device__ __forceinline__ static Vec none() { Vec v; v.lo = ~0ull; v.hi = ~0ull; return v; }
+    __device__ __forceinline__ static Vec zero() { Vec v; v.lo = 0; v.hi = 0; return v; }
+    __device__ __forceinline__ static u32 first(const Vec& v) { return (u32)v.lo & 0xffffu; }
+    __device__ __forceinline__ static Seg seg_pack(u32 read, u32 start, u32 len) { return (u64)read | ((u64)start << 16) | ((u64)len << 32); }
+    __device__ __forceinline__ static u32 seg_read(Seg s) { return (u32)s & 0xffffu; }
+    __device__ __forceinline__ static u32 seg_start(Seg s) { return (u32)(s >> 16) & 0xffffu; }
+    __device__ __forceinline__ static u32 seg_len(Seg s) { return (u32)(s >> 32); }
+};
+
+// ------------------------------------------------------------------ tiers
+template <class IdT_, bool SMEM_, u32 VCAP_, u32 HCELLS_, u32 LCAP_, u32 SEGCAP_, u32 WARPS_, u32 CTAS_> struct CgPoa2Tier {
+    typedef IdT_ IdT;
+    static constexpr bool SMEM = SMEM_;
+    static constexpr u32 VCAP = VCAP_, HCELLS = HCELLS_, LCAP = LCAP_, SEGCAP = SEGCAP_, WARPS = WARPS_, CTAS_PER_SM = CTAS_;
+    static constexpr u32 SCAP = 3 * VCAP_ + 8, ALNCAP = VCAP_ + LCAP_;
+    static constexpr u32 SEQCAP = LCAP_ < 512u ? LCAP_ : 512u;        // segments up to this long are staged next to the graph
+};
+typedef CgPoa2Tier<u8, true, 128, 2048, 64, 192, 4, 5> CgPoa2C1;          // 86 % of the regions of a 150-deep pile
+typedef CgPoa2Tier<u8, true, 254, 8192, 120, 192, 4, 2> CgPoa2C2;         // 99.2 %
+typedef CgPoa2Tier<u8, true, 254, 24576, 120, 192, 1, 3> CgPoa2C3;        // the rest of them, bar a handful
+typedef CgPoa2Tier<u16, true, 1024, 49152, 512, 512, 1, 1> CgPoa2W1;
+typedef CgPoa2Tier<u16, false, 4096, 4u << 20, 2048, 4096, 4, 2> CgPoa2W2;
+typedef CgPoa2Tier<u16, false, 65534, 400u << 20, 6000, 4096, 4, 1> CgPoa2W3;
 
 template <class T> struct CgPoa2Lay {
-    static constexpr u32 r8(u32 v) { return (v + 7u) / 8u * 8u; }
-    static constexpr u32 mx(u32 a, u32 b) { return a > b ? a : b; }
-    static constexpr u32 WORK = r8(2 * mx(T::SCAP, T::ALNCAP));          // DFS stack (u16) | alignment pairs (u16)
-    static constexpr u32 TMP = r8(mx(2 * T::VCAP, 4 * T::LCAP));         // DFS marks+check | update scratch (4 x LCAP)
-    static constexpr u32 o_pred = 0, o_prow = o_pred + 8 * T::VCAP, o_H = o_prow + 8 * T::VCAP, o_rdesc = o_H + r8(2 * T::HCELLS),
-                         o_meta = o_rdesc + 4 * T::VCAP, o_seg = o_meta + 4 * T::VCAP, o_nseq = o_seg + 4 * T::SEGCAP,
-                         o_work = o_nseq + r8(2 * T::VCAP), o_tmp = o_work + WORK, o_letter = o_tmp + TMP,
-                         o_r2n = o_letter + r8(T::VCAP), o_rank = o_r2n + 2 * r8(T::VCAP), o_xr2n = o_rank + r8(T::VCAP),
-                         o_xlead = o_xr2n + r8(T::VCAP), o_seq = o_xlead + r8(T::VCAP), per_warp = r8(o_seq + r8(T::LCAP) + 8),
-                         R2N_STRIDE = r8(T::VCAP);
-    static constexpr u32 cta_bytes = per_warp * T::WARPS;
+    typedef CgIdPack<typename T::IdT> Pk;
+    static constexpr size_t r16(size_t v) { return (v + 15u) / 16u * 16u; }
+    static constexpr size_t mx(size_t a, size_t b) { return a > b ? a : b; }
+    static constexpr size_t ID = sizeof(typename T::IdT);
+    static constexpr size_t WORK = r16(sizeof(typename Pk::Item) * mx(T::SCAP, T::ALNCAP));   // DFS stack | alignment pairs | splice items
+    static constexpr size_t TMP = r16(mx(2 * (size_t)T::VCAP, (3 * ID + 1) * T::LCAP));     // DFS marks+check | update scratch
+    static constexpr size_t o_pred = 0, o_prow = o_pred + sizeof(typename Pk::Vec) * T::VCAP, o_rdesc = o_prow + sizeof(typename Pk::Vec) * T::VCAP,
+                            o_meta = o_rdesc + r16(sizeof(typename Pk::Rdesc) * T::VCAP), o_seg = o_meta + r16(sizeof(typename Pk::Meta) * T::VCAP),
+                            o_nseq = o_seg + r16(sizeof(typename Pk::Seg) * T::SEGCAP), o_work = o_nseq + r16(2 * (size_t)T::VCAP),
+                            o_tmp = o_work + WORK, o_letter = o_tmp + TMP, o_r2n = o_letter + r16(T::VCAP),
+                            R2N_STRIDE = r16(ID * T::VCAP), o_rank = o_r2n + 2 * R2N_STRIDE, o_xr2n = o_rank + R2N_STRIDE,
+                            o_xlead = o_xr2n + R2N_STRIDE, o_seq = o_xlead + r16(T::VCAP), o_H = o_seq + r16((size_t)T::SEQCAP + 16),
+                            per_warp = r16(o_H + 2 * (size_t)T::HCELLS + 16);
+    static constexpr size_t cta_bytes = T::SMEM ? per_warp * T::WARPS : 0;
 };
 
-// meta word of a node: byte 0 = nal (bits 0-1) | "sequence 0 passes here" (bit 2) | in-degree (bits 4-7); bytes 1-3 = aligned ids
+// meta word of a node: low field = nal (bits 0-1) | "sequence 0 passes here" (bit 2) | in-degree (bits 4-7); then 3 aligned ids
 template <class T> struct CgPoa2G {
     typedef CgPoa2Lay<T> Lay;
-    u32 wo;
-    __device__ __forceinline__ u8* b() const { return cg_smem_base() + wo; }
-    __device__ __forceinline__ u64& pred(u32 i) const { return ((u64*)(b() + Lay::o_pred))[i]; }
-    __device__ __forceinline__ u64& prow(u32 i) const { return ((u64*)(b() + Lay::o_prow))[i]; }
+    typedef CgIdPack<typename T::IdT> Pk;
+    typedef typename T::IdT IdT;
+    u32 wo;                     // shared-memory tiers: byte offset of this warp's slice (every access an LDS/STS with an immediate offset)
+    u8* base;                   // global-memory tiers: this warp's scratch slice
+    __device__ __forceinline__ u8* b() const { return T::SMEM ? cg_smem_base() + wo : base; }
+    __device__ __forceinline__ typename Pk::Vec& pred(u32 i) const { return ((typename Pk::Vec*)(b() + Lay::o_pred))[i]; }
+    __device__ __forceinline__ typename Pk::Vec& prow(u32 i) const { return ((typename Pk::Vec*)(b() + Lay::o_prow))[i]; }
     __device__ __forceinline__ i16* H() const { return (i16*)(b() + Lay::o_H); }
-    __device__ __forceinline__ u32& rdesc(u32 i) const { return ((u32*)(b() + Lay::o_rdesc))[i]; }
-    __device__ __forceinline__ u32& meta(u32 i) const { return ((u32*)(b() + Lay::o_meta))[i]; }
-    __device__ __forceinline__ u32& seg(u32 i) const { return ((u32*)(b() + Lay::o_seg))[i]; }
+    __device__ __forceinline__ typename Pk::Rdesc& rdesc(u32 i) const { return ((typename Pk::Rdesc*)(b() + Lay::o_rdesc))[i]; }
+    __device__ __forceinline__ typename Pk::Meta& meta(u32 i) const { return ((typename Pk::Meta*)(b() + Lay::o_meta))[i]; }
+    __device__ __forceinline__ typename Pk::Seg& seg(u32 i) const { return ((typename Pk::Seg*)(b() + Lay::o_seg))[i]; }
     __device__ __forceinline__ u16& nseq(u32 i) const { return ((u16*)(b() + Lay::o_nseq))[i]; }
-    __device__ __forceinline__ u16& work(u32 i) const { return ((u16*)(b() + Lay::o_work))[i]; }
+    __device__ __forceinline__ typename Pk::Item& work(u32 i) const { return ((typename Pk::Item*)(b() + Lay::o_work))[i]; }
     __device__ __forceinline__ u8& marks(u32 i) const { return b()[Lay::o_tmp + i]; }
     __device__ __forceinline__ u8& check(u32 i) const { return b()[Lay::o_tmp + T::VCAP + i]; }
-    __device__ __forceinline__ u8& nodeq(u32 i) const { return b()[Lay::o_tmp + i]; }
-    __device__ __forceinline__ u8& kindq(u32 i) const { return b()[Lay::o_tmp + T::LCAP + i]; }
-    __device__ __forceinline__ u8& posq(u32 i) const { return b()[Lay::o_tmp + 2 * T::LCAP + i]; }
-    __device__ __forceinline__ u8& anchq(u32 i) const { return b()[Lay::o_tmp + 3 * T::LCAP + i]; }
+    __device__ __forceinline__ IdT& nodeq(u32 i) const { return ((IdT*)(b() + Lay::o_tmp))[i]; }
+    __device__ __forceinline__ IdT& posq(u32 i) const { return ((IdT*)(b() + Lay::o_tmp))[T::LCAP + i]; }
+    __device__ __forceinline__ IdT& anchq(u32 i) const { return ((IdT*)(b() + Lay::o_tmp))[2 * T::LCAP + i]; }
+    __device__ __forceinline__ u8& kindq(u32 i) const { return b()[Lay::o_tmp + 3 * Lay::ID * T::LCAP + i]; }
     __device__ __forceinline__ u8& letter(u32 i) const { return b()[Lay::o_letter + i]; }
-    __device__ __forceinline__ u8& r2n(u32 which, u32 i) const { return b()[Lay::o_r2n + which * Lay::R2N_STRIDE + i]; }
-    __device__ __forceinline__ u8& rank_of(u32 i) const { return b()[Lay::o_rank + i]; }
-    __device__ __forceinline__ u8& xr2n(u32 i) const { return b()[Lay::o_xr2n + i]; }
+    __device__ __forceinline__ IdT& r2n(u32 which, u32 i) const { return ((IdT*)(b() + Lay::o_r2n + which * Lay::R2N_STRIDE))[i]; }
+    __device__ __forceinline__ IdT& rank_of(u32 i) const { return ((IdT*)(b() + Lay::o_rank))[i]; }
+    __device__ __forceinline__ IdT& xr2n(u32 i) const { return ((IdT*)(b() + Lay::o_xr2n))[i]; }
     __device__ __forceinline__ u8& xlead(u32 i) const { return b()[Lay::o_xlead + i]; }
     __device__ __forceinline__ u8* seqbuf() const { return b() + Lay::o_seq; }
 };
 
-__device__ __forceinline__ u32 cg_byte64(u64 v, u32 i) { return (u32)(v >> (8u * i)) & 0xffu; }
 __device__ __forceinline__ u32 cg_lt_mask() { return (1u << cg_lane()) - 1u; }
+
+#define CG_P2_TYPES                                   \
+    typedef CgIdPack<typename T::IdT> Pk;             \
+    typedef typename T::IdT IdT;                      \
+    typedef typename Pk::Meta MetaT;                  \
+    typedef typename Pk::Vec VecT;                    \
+    typedef typename Pk::Item ItemT;                  \
+    constexpr u32 W = Pk::W, IDNONE = Pk::NONE;       \
+    constexpr MetaT IDMASK = (MetaT)Pk::NONE
 
 // ------------------------------------------------------------------ exact order: spoa's DFS (graph.cpp:294-354), lane 0
 // Same walk as cg_poa_toposort (k_poa.cuh) on the packed records.  marks/check are pre-initialised (0 / 1) by the warp.
 template <class T> __device__ __forceinline__ bool cg_poa2_dfs(const CgPoa2G<T>& s, u32 V) {
+    CG_P2_TYPES;
+    constexpr u32 FIN = 1u << W;
     u32 nrank = 0, sp = 0;
     for (u32 i = 0; i < V; ++i) {
         if (s.marks(i) != 0) continue;
-        s.work(sp++) = (u16)i;
+        s.work(sp++) = (ItemT)i;
         while (sp != 0) {
             const u32 top = s.work(sp - 1);
-            const u32 id = top & 0xffu;
-            bool finish = (top & 0x100u) != 0;
-            const u32 m = s.meta(id);
-            const u32 nal = m & 3u;
+            const u32 id = top & IDNONE;
+            bool finish = (top & FIN) != 0;
+            const MetaT m = s.meta(id);
+            const u32 nal = (u32)m & 3u;
             if (!finish) {
                 if (s.marks(id) == 2) { --sp; continue; }
                 const u32 sp0 = sp;
-                const u32 deg = (m >> 4) & 15u;
-                const u64 P = s.pred(id);
+                const u32 deg = ((u32)m >> 4) & 15u;
+                const VecT P = s.pred(id);
                 if (sp + deg + 3 > T::SCAP) return false;
                 for (u32 e = 0; e < deg; ++e) {
-                    const u32 b = cg_byte64(P, e);
-                    if (s.marks(b) != 2) s.work(sp++) = (u16)b;
+                    const u32 b = Pk::get(P, e);
+                    if (s.marks(b) != 2) s.work(sp++) = (ItemT)b;
                 }
                 if (s.check(id)) {
                     for (u32 a = 0; a < nal; ++a) {
-                        const u32 aid = (m >> (8u * (a + 1))) & 0xffu;
-                        if (s.marks(aid) != 2) { s.work(sp++) = (u16)aid; s.check(aid) = 0; }
+                        const u32 aid = (u32)((m >> (W * (a + 1))) & IDMASK);
+                        if (s.marks(aid) != 2) { s.work(sp++) = (ItemT)aid; s.check(aid) = 0; }
                     }
                 }
                 if (sp == sp0) finish = true;
-                else { s.marks(id) = 1; s.work(sp0 - 1) = (u16)(id | 0x100u); }
+                else { s.marks(id) = 1; s.work(sp0 - 1) = (ItemT)(id | FIN); }
             }
             if (finish) {
                 s.marks(id) = 2;
                 if (s.check(id)) {
-                    s.xr2n(nrank) = (u8)id; s.xlead(nrank) = 1; ++nrank;
-                    for (u32 a = 0; a < nal; ++a) { s.xr2n(nrank) = (u8)((m >> (8u * (a + 1))) & 0xffu); s.xlead(nrank) = 0; ++nrank; }
+                    s.xr2n(nrank) = (IdT)id; s.xlead(nrank) = 1; ++nrank;
+                    for (u32 a = 0; a < nal; ++a) { s.xr2n(nrank) = (IdT)((m >> (W * (a + 1))) & IDMASK); s.xlead(nrank) = 0; ++nrank; }
                 }
                 --sp;
             }
@@ -129,39 +197,41 @@ template <class T> __device__ __forceinline__ bool cg_poa2_dfs(const CgPoa2G<T>&
 
 // ------------------------------------------------------------------ traceback (lane 0)
 // simd_alignment_engine_impl.hpp:968-1004: diagonal over the predecessors in in-edge order, then vertical over them,
-// then horizontal.  Pairs are written in traceback order (last pair first) as node | qpos << 8 (0xff = none).
+// then horizontal.  Pairs are written in traceback order (last pair first) as node | qpos << W (all ones = none).
 template <class T> __device__ __forceinline__ u32 cg_poa2_traceback(const CgPoa2G<T>& s, const u8* seq, u32 Wd, u32 bi, u32 bj, bool* bad) {
+    CG_P2_TYPES;
     const i16* H = s.H();
     u32 i = bi, j = bj, n = 0;
-    i32 Hij = H[i * Wd + j];
+    i32 Hij = H[(size_t)i * Wd + j];
     while (Hij != 0) {
-        const u32 d = s.rdesc(i - 1);
-        const u64 pr = s.prow(i - 1);
-        const u32 deg = (d >> 8) & 0xffu, np = deg ? deg : 1u;
+        const typename Pk::Rdesc d = s.rdesc(i - 1);
+        const VecT pr = s.prow(i - 1);
+        const u32 deg = ((u32)d >> 8) & 0xffu, np = deg ? deg : 1u;
         u32 pi_ = 0, pj_ = 0;
         i32 Hp = 0;
         bool found = false;
         if (j != 0) {
-            const i32 sc = (d & 0xffu) == seq[j - 1] ? 5 : -10;
+            const i32 sc = ((u32)d & 0xffu) == seq[j - 1] ? 5 : -10;
             for (u32 e = 0; e < np && !found; ++e) {
-                const u32 p = deg ? cg_byte64(pr, e) : 0u;
-                Hp = H[p * Wd + (j - 1)];
+                const u32 p = deg ? Pk::get(pr, e) : 0u;
+                Hp = H[(size_t)p * Wd + (j - 1)];
                 if (Hij == Hp + sc) { pi_ = p; pj_ = j - 1; found = true; }
             }
         }
         if (!found) {
             for (u32 e = 0; e < np && !found; ++e) {
-                const u32 p = deg ? cg_byte64(pr, e) : 0u;
-                Hp = H[p * Wd + j];
+                const u32 p = deg ? Pk::get(pr, e) : 0u;
+                Hp = H[(size_t)p * Wd + j];
                 if (Hij == Hp - 4) { pi_ = p; pj_ = j; found = true; }
             }
         }
         if (!found && j != 0) {
-            Hp = H[i * Wd + j - 1];
+            Hp = H[(size_t)i * Wd + j - 1];
             if (Hij == Hp - 4) { pi_ = i; pj_ = j - 1; found = true; }
         }
         if (!found || n >= T::ALNCAP) { *bad = true; return 0; }      // inconsistent matrix: cannot happen
-        s.work(n) = (u16)((i == pi_ ? CG_P2_NONE : (d >> 24)) | ((j == pj_ ? CG_P2_NONE : (j - 1)) << 8));
+        const u32 node = (u32)(d >> (16 + W)) & IDNONE;
+        s.work(n) = (ItemT)((i == pi_ ? IDNONE : node) | ((j == pj_ ? IDNONE : (j - 1)) << W));
         ++n;
         i = pi_; j = pj_;
         Hij = Hp;
@@ -170,9 +240,12 @@ template <class T> __device__ __forceinline__ u32 cg_poa2_traceback(const CgPoa2
 }
 
 // ------------------------------------------------------------------ score matrix (all lanes), CH chunks of 32 columns
+// The common row (one predecessor = the row just computed) needs no loads: the left neighbour comes from the adjacent lane.
+// The in-row gap term H[i][j] = max(v[j], H[i][j-1] - 4) is the max-plus prefix scan H[i][j] = max_{t<=j}(v[t] + 4t) - 4j.
 // tie: some other row reached this lane's maximum again (the caller then needs the exact row order).
 template <int CH, class T>
 __device__ __forceinline__ void cg_poa2_dp(const CgPoa2G<T>& s, u32 V, const u8* seq, u32 L, i32& bv, u32& bi, u32& bj, bool& tie) {
+    CG_P2_TYPES;
     const u32 lane = cg_lane(), Wd = L + 1;
     i16* H = s.H();
     u8 q[CH];
@@ -189,12 +262,12 @@ __device__ __forceinline__ void cg_poa2_dp(const CgPoa2G<T>& s, u32 V, const u8*
     u32 desc_l = 0;
     __syncwarp();
     for (u32 r = 0; r < V; ++r) {
-        if ((r & 31u) == 0) desc_l = r + lane < V ? s.rdesc(r + lane) : 0u;
+        if ((r & 31u) == 0) desc_l = r + lane < V ? (u32)s.rdesc(r + lane) : 0u;
         const u32 d = __shfl_sync(CG_FULL, desc_l, (int)(r & 31u));
         const u8 ch = (u8)(d & 0xffu);
         const u32 deg = (d >> 8) & 0xffu;
-        const u32 p0 = (d >> 16) & 0xffu;
-        i16* row = H + (r + 1) * Wd;
+        const u32 p0 = (d >> 16) & IDNONE;
+        i16* row = H + (size_t)(r + 1) * Wd;
         i32 val[CH];
         if (deg <= 1 && p0 == r) {                       // predecessor = the row just computed (or the zero row for r = 0)
 #pragma unroll
@@ -207,7 +280,7 @@ __device__ __forceinline__ void cg_poa2_dp(const CgPoa2G<T>& s, u32 V, const u8*
                 val[c] = a > b ? a : b;
             }
         } else if (deg <= 1) {                           // one predecessor elsewhere, or none (virtual row 0)
-            const i16* prow = H + p0 * Wd;
+            const i16* prow = H + (size_t)p0 * Wd;
 #pragma unroll
             for (int c = 0; c < CH; ++c) {
                 val[c] = CG_POA_NEG;
@@ -221,9 +294,9 @@ __device__ __forceinline__ void cg_poa2_dp(const CgPoa2G<T>& s, u32 V, const u8*
         } else {
 #pragma unroll
             for (int c = 0; c < CH; ++c) val[c] = CG_POA_NEG;
-            const u64 pr = s.prow(r);
+            const VecT pr = s.prow(r);
             for (u32 e = 0; e < deg; ++e) {
-                const i16* prow = H + cg_byte64(pr, e) * Wd;
+                const i16* prow = H + (size_t)Pk::get(pr, e) * Wd;
 #pragma unroll
                 for (int c = 0; c < CH; ++c) {
                     if (act[c]) {
@@ -269,20 +342,70 @@ __device__ __forceinline__ void cg_poa2_dp(const CgPoa2G<T>& s, u32 V, const u8*
     }
 }
 
+// Any length: chunks of 32 columns, every row read back from the stored matrix.
+template <class T>
+__device__ __forceinline__ void cg_poa2_dp_any(const CgPoa2G<T>& s, u32 V, const u8* seq, u32 L, i32& bv, u32& bi, u32& bj, bool& tie) {
+    CG_P2_TYPES;
+    const u32 lane = cg_lane(), Wd = L + 1;
+    i16* H = s.H();
+    for (u32 j = lane; j < Wd; j += 32) H[j] = 0;
+    __syncwarp();
+    for (u32 r = 0; r < V; ++r) {
+        const u32 d = (u32)s.rdesc(r);
+        const u8 ch = (u8)(d & 0xffu);
+        const u32 deg = (d >> 8) & 0xffu, np = deg ? deg : 1u;
+        const VecT pr = s.prow(r);
+        i16* row = H + (size_t)(r + 1) * Wd;
+        if (lane == 0) row[0] = 0;
+        i32 carry = 0;
+        for (u32 jb = 1; jb < Wd; jb += 32) {
+            const u32 j = jb + lane;
+            const bool act = j < Wd;
+            i32 val = CG_POA_NEG;
+            if (act) {
+                const i32 sc = seq[j - 1] == ch ? 5 : -10;
+                for (u32 e = 0; e < np; ++e) {
+                    const i16* prow = H + (size_t)(deg ? Pk::get(pr, e) : 0u) * Wd;
+                    const i32 a = (i32)prow[j - 1] + sc, b = (i32)prow[j] - 4;
+                    const i32 m = a > b ? a : b;
+                    val = m > val ? m : val;
+                }
+                val = val > 0 ? val : 0;
+            }
+            i32 u = act ? val + 4 * (i32)j : CG_POA_NEG;
+#pragma unroll
+            for (int dd = 1; dd < 32; dd <<= 1) {
+                const i32 o = __shfl_up_sync(CG_FULL, u, dd);
+                if (lane >= (u32)dd) u = o > u ? o : u;
+            }
+            u = u > carry ? u : carry;
+            carry = __shfl_sync(CG_FULL, u, 31);
+            if (act) {
+                const i32 h = u - 4 * (i32)j;
+                row[j] = (i16)h;
+                if (h > bv) { bv = h; bi = r + 1; bj = j; tie = false; }
+                else if (h == bv && h > 0 && bi != r + 1) tie = true;
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // ------------------------------------------------------------------ one job
 // Returns the consensus length, or CG_NONE32 if the tier was outgrown (nothing is committed).
 template <class T>
 __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s, u32 w, u32 rg, u64* cnt_aln, u64* cnt_cells, u64* cnt_pred) {
+    CG_P2_TYPES;
     const u32 lane = cg_lane();
-    const CgWin W = c.win[w];
+    const CgWin W_ = c.win[w];
     CgRegion* R = &c.regions[c.off_reg[w] + rg];
     if (R->n > T::SEGCAP || R->max_len > T::LCAP) return CG_NONE32;
     CgWinView v;
-    v.seq_off = c.seq_off + W.seq_begin; v.pos = c.pos + c.off_pos[w]; v.chain = c.chain + c.off_slot[w];
-    v.rel = c.rel + c.off_slot[w]; v.N = W.n_seqs; v.C = W.n_cand; v.nA = W.n_chain;
+    v.seq_off = c.seq_off + W_.seq_begin; v.pos = c.pos + c.off_pos[w]; v.chain = c.chain + c.off_slot[w];
+    v.rel = c.rel + c.off_slot[w]; v.N = W_.n_seqs; v.C = W_.n_cand; v.nA = W_.n_chain;
     const u8* bases = (const u8*)c.bases;
 
-    // ---- the region's segments, in read order (split_reads): read | start << 12 | len << 25
+    // ---- the region's segments, in read order (split_reads)
     u32 nseg = 0;
     for (u32 rb = 0; rb < v.N; rb += 32) {
         const u32 r = rb + lane;
@@ -291,7 +414,7 @@ __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s
         const u32 bal = __ballot_sync(CG_FULL, keep);
         if (keep) {
             const u32 idx = nseg + __popc(bal & cg_lt_mask());
-            if (idx < T::SEGCAP) s.seg(idx) = r | (st << 12) | (ln << 25);
+            if (idx < T::SEGCAP) s.seg(idx) = Pk::seg_pack(r, st, ln);
         }
         nseg += __popc(bal);
     }
@@ -303,25 +426,28 @@ __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s
     u64 j_aln = 0, j_cells = 0, j_pred = 0;
 
     for (u32 si = 0; si < nseg; ++si) {
-        const u32 sg = s.seg(si);
-        const u32 L = sg >> 25;
+        const typename Pk::Seg sg = s.seg(si);
+        const u32 L = Pk::seg_len(sg);
         if (L == 0) continue;                                        // graph.cpp:160 — not a row of the MSA
-        u8* seq = s.seqbuf();
-        {
-            const u8* src = bases + v.seq_off[sg & 0xfffu] + ((sg >> 12) & 0x1fffu);
+        const u8* seq = bases + v.seq_off[Pk::seg_read(sg)] + Pk::seg_start(sg);
+        if (L <= T::SEQCAP) {                                        // stage the segment next to the graph
+            u8* sb = s.seqbuf();
             __syncwarp();
-            for (u32 i = lane; i < L; i += 32) seq[i] = src[i];
+            for (u32 i = lane; i < L; i += 32) sb[i] = seq[i];
             __syncwarp();
+            seq = sb;
         }
         const u32 Wd = L + 1;
         u32 n_aln = 0;
         if (V != 0) {
-            if ((V + 1) * Wd > T::HCELLS) return CG_NONE32;
+            if ((u64)(V + 1) * Wd > (u64)T::HCELLS) return CG_NONE32;
             i32 bv = 0; u32 bi = 0, bj = 0;
             bool tie = false;
             if (L <= 32) cg_poa2_dp<1>(s, V, seq, L, bv, bi, bj, tie);
             else if (L <= 64) cg_poa2_dp<2>(s, V, seq, L, bv, bi, bj, tie);
-            else cg_poa2_dp<4>(s, V, seq, L, bv, bi, bj, tie);
+            else if (L <= 128) cg_poa2_dp<4>(s, V, seq, L, bv, bi, bj, tie);
+            else if (T::LCAP > 128 && L <= 256) cg_poa2_dp<(T::LCAP > 128 ? 8 : 1)>(s, V, seq, L, bv, bi, bj, tie);
+            else if (T::LCAP > 256) cg_poa2_dp_any(s, V, seq, L, bv, bi, bj, tie);
             j_aln += 1; j_cells += (u64)(V + 1) * L; j_pred += (u64)sumdeg * L;
             const u64 key = ((u64)(u32)bv << 32) | ((u64)(0xffffu - bi) << 16) | (u64)(0xffffu - bj);
             const u64 kb = cg_warp_max64(key);
@@ -349,14 +475,14 @@ __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s
                     u32 myrow = 0;
                     if (i < V) {
                         myrow = (u32)s.rank_of(s.xr2n(i)) + 1;
-                        const i16* hr = H + myrow * Wd;
+                        const i16* hr = H + (size_t)myrow * Wd;
                         for (u32 j = 1; j < Wd; ++j) hit = hit || (i32)hr[j] == M;
                     }
                     const u32 bal = __ballot_sync(CG_FULL, hit);
                     if (bal) { row = __shfl_sync(CG_FULL, myrow, __ffs((int)bal) - 1); break; }
                 }
                 bi = row; bj = 0;
-                const i16* hr = H + row * Wd;
+                const i16* hr = H + (size_t)row * Wd;
                 for (u32 jb = 1; jb < Wd; jb += 32) {
                     const u32 j = jb + lane;
                     const u32 bal = __ballot_sync(CG_FULL, j < Wd && (i32)hr[j] == M);
@@ -373,17 +499,17 @@ __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s
         // ---- graph update, all lanes (graph.cpp:155-272).  Pair t in path order = work[n_aln - 1 - t].
         u32 first_valid = L, last_valid = 0;
         {
-            u32 mn = 0xffffu, mxq = 0;
+            u32 mn = 0xffffffffu, mxq = 0;
             for (u32 t = lane; t < n_aln; t += 32) {
-                const u32 qp = (u32)s.work(t) >> 8;
-                if (qp != CG_P2_NONE) { mn = qp < mn ? qp : mn; mxq = qp > mxq ? qp : mxq; }
+                const u32 qp = (u32)s.work(t) >> W;
+                if (qp != IDNONE) { mn = qp < mn ? qp : mn; mxq = qp > mxq ? qp : mxq; }
             }
 #pragma unroll
             for (int dlt = 16; dlt > 0; dlt >>= 1) {
                 const u32 o1 = __shfl_xor_sync(CG_FULL, mn, dlt), o2 = __shfl_xor_sync(CG_FULL, mxq, dlt);
                 mn = o1 < mn ? o1 : mn; mxq = o2 > mxq ? o2 : mxq;
             }
-            if (mn != 0xffffu) { first_valid = mn; last_valid = mxq; }
+            if (mn != 0xffffffffu) { first_valid = mn; last_valid = mxq; }
         }
         const bool has_aln = first_valid != L;
         const u32 V0 = V;
@@ -394,22 +520,22 @@ __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s
         // U1: the aligned part — which node does each consumed pair resolve to?
         for (u32 tb = 0; tb < n_aln; tb += 32) {
             const u32 t = tb + lane;
-            u32 kind = 3, nn = 0, an = CG_P2_NONE, qp = CG_P2_NONE;
+            u32 kind = 3, nn = 0, an = IDNONE, qp = IDNONE;
             u8 ch = 0;
-            u32 m_an = 0;
+            MetaT m_an = 0;
             if (t < n_aln) {
                 const u32 pr = s.work(n_aln - 1 - t);
-                an = pr & 0xffu; qp = pr >> 8;
-                if (qp != CG_P2_NONE) {
+                an = pr & IDNONE; qp = pr >> W;
+                if (qp != IDNONE) {
                     ch = seq[qp];
-                    if (an == CG_P2_NONE) kind = 1;                                   // new node, not aligned to anything
+                    if (an == IDNONE) kind = 1;                                       // new node, not aligned to anything
                     else if (s.letter(an) == ch) { kind = 0; nn = an; }
                     else {
                         m_an = s.meta(an);
                         kind = 2;                                                     // new node in an's column ...
-                        const u32 nal = m_an & 3u;
+                        const u32 nal = (u32)m_an & 3u;
                         for (u32 a = 0; a < nal; ++a) {
-                            const u32 aid = (m_an >> (8u * (a + 1))) & 0xffu;
+                            const u32 aid = (u32)((m_an >> (W * (a + 1))) & IDMASK);
                             if (s.letter(aid) == ch) { kind = 0; nn = aid; }          // ... unless the column already has the letter
                         }
                     }
@@ -421,22 +547,23 @@ __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s
             n_mid_new += __popc(bal);
             if (isnew && nn >= T::VCAP) ovf = true;
             else if (kind == 2) {
-                const u32 nal = m_an & 3u;
+                const u32 nal = (u32)m_an & 3u;
                 if (nal >= 3) ovf = true;                                             // cannot happen with ACGT input
                 else {
                     // aligned(nn) = aligned(an) + [an]; every member of the column appends nn (graph.cpp:232-243)
-                    s.letter(nn) = ch; s.nseq(nn) = 0; s.pred(nn) = ~0ull;
-                    s.meta(nn) = (nal + 1) | (m_an & 0xffffff00u & ~(0xffffffffu << (8u * (nal + 1)))) | (an << (8u * (nal + 1)));
+                    const u32 sh = W * (nal + 1);
+                    s.letter(nn) = ch; s.nseq(nn) = 0; s.pred(nn) = Pk::none();
+                    s.meta(nn) = (MetaT)(nal + 1) | (m_an & ~IDMASK & (((MetaT)1 << sh) - 1)) | ((MetaT)an << sh);
                     for (u32 a = 0; a < nal; ++a) {
-                        const u32 aid = (m_an >> (8u * (a + 1))) & 0xffu;
-                        const u32 ma = s.meta(aid);
-                        s.meta(aid) = (ma + 1) | (nn << (8u * ((ma & 3u) + 1)));
+                        const u32 aid = (u32)((m_an >> (W * (a + 1))) & IDMASK);
+                        const MetaT ma = s.meta(aid);
+                        s.meta(aid) = (ma + 1) | ((MetaT)nn << (W * (((u32)ma & 3u) + 1)));
                     }
-                    s.meta(an) = (m_an + 1) | (nn << (8u * (nal + 1)));
+                    s.meta(an) = (m_an + 1) | ((MetaT)nn << sh);
                 }
             }
-            if (qp != CG_P2_NONE && !(isnew && nn >= T::VCAP)) {
-                s.nodeq(qp) = (u8)nn; s.kindq(qp) = (u8)kind; s.anchq(qp) = (u8)(kind == 1 ? CG_P2_NONE : an);
+            if (qp != IDNONE && !(isnew && nn >= T::VCAP)) {
+                s.nodeq(qp) = (IdT)nn; s.kindq(qp) = (u8)kind; s.anchq(qp) = (IdT)(kind == 1 ? IDNONE : an);
             }
         }
         V = mid_base + n_mid_new;
@@ -451,8 +578,8 @@ __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s
                 if (q < first_valid) { node = V0 + q; kind = 1; }
                 else if (q > last_valid) { node = V0 + n_prefix + (q - last_valid - 1); kind = 1; }
                 else { node = s.nodeq(q); kind = s.kindq(q); }
-                if (q < first_valid || q > last_valid) { s.nodeq(q) = (u8)node; s.kindq(q) = 1; s.anchq(q) = CG_P2_NONE; }
-                if (kind == 1) { s.letter(node) = seq[q]; s.nseq(node) = 0; s.meta(node) = 0; s.pred(node) = ~0ull; }
+                if (q < first_valid || q > last_valid) { s.nodeq(q) = (IdT)node; s.kindq(q) = 1; s.anchq(q) = (IdT)IDNONE; }
+                if (kind == 1) { s.letter(node) = seq[q]; s.nseq(node) = 0; s.meta(node) = 0; s.pred(node) = Pk::none(); }
             }
         }
         __syncwarp();
@@ -463,19 +590,18 @@ __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s
             if (q < L) {
                 const u32 node = s.nodeq(q);
                 s.nseq(node) = (u16)(s.nseq(node) + 1);
-                u32 m = s.meta(node);
+                MetaT m = s.meta(node);
                 if (nseqs == 0) m |= 4u;
                 if (q > 0) {
                     const u32 src = s.nodeq(q - 1);
-                    const u32 deg = (m >> 4) & 15u;
-                    u64 P = s.pred(node);
+                    const u32 deg = ((u32)m >> 4) & 15u;
+                    const VecT P = s.pred(node);
                     bool have = false;
-                    for (u32 e = 0; e < deg; ++e) have = have || cg_byte64(P, e) == src;
+                    for (u32 e = 0; e < deg; ++e) have = have || Pk::get(P, e) == src;
                     if (!have) {
                         if (deg >= 8) ovf = true;
                         else {
-                            P = (P & ~(0xffull << (8u * deg))) | ((u64)src << (8u * deg));
-                            s.pred(node) = P;
+                            s.pred(node) = Pk::set(P, deg, src);
                             m += 16u;
                             changed = true;
                         }
@@ -492,26 +618,26 @@ __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s
 
         // ---- the incremental order: splice the new nodes into the old order (columns stay contiguous)
         // U3a: position (in the old order) in front of which each new node goes
-        u32 carry_min = CG_P2_NONE;                                   // smallest column start among the anchored positions behind
+        u32 carry_min = IDNONE;                                       // smallest column start among the anchored positions behind
         for (int qb = (int)((L - 1) & ~31u); qb >= 0; qb -= 32) {
             const u32 q = (u32)qb + lane;
-            u32 cs = CG_P2_NONE, ce = 0;
+            u32 cs = IDNONE, ce = 0;
             u32 kind = 3;
             if (q < L) {
                 kind = s.kindq(q);
                 const u32 an = s.anchq(q);
-                if (an != CG_P2_NONE) {                               // column of the anchor among the OLD nodes
-                    const u32 m = s.meta(an);
-                    const u32 nal = m & 3u;
+                if (an != IDNONE) {                                   // column of the anchor among the OLD nodes
+                    const MetaT m = s.meta(an);
+                    const u32 nal = (u32)m & 3u;
                     const u32 r0 = s.rank_of(an);
                     cs = r0; ce = r0 + 1;
                     for (u32 a = 0; a < nal; ++a) {
-                        const u32 aid = (m >> (8u * (a + 1))) & 0xffu;
+                        const u32 aid = (u32)((m >> (W * (a + 1))) & IDMASK);
                         if (aid < V0) { const u32 ra = s.rank_of(aid); cs = ra < cs ? ra : cs; ce = ra + 1 > ce ? ra + 1 : ce; }
                     }
                 }
             }
-            // exclusive suffix minimum of cs over q (positions never decrease along the path)
+            // suffix minimum of cs over q (positions never decrease along the path; unanchored positions hold "none")
             u32 sm = cs;
 #pragma unroll
             for (int dlt = 1; dlt < 32; dlt <<= 1) {
@@ -520,21 +646,21 @@ __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s
             }
             sm = sm < carry_min ? sm : carry_min;
             if (q < L) {
-                u32 pos = CG_P2_NONE;
+                u32 pos = IDNONE;
                 if (kind == 2) pos = ce;
-                else if (kind == 1) pos = sm == CG_P2_NONE ? V0 : sm;
-                s.posq(q) = (u8)pos;
+                else if (kind == 1) pos = sm == IDNONE ? V0 : sm;
+                s.posq(q) = (IdT)pos;
             }
             carry_min = __shfl_sync(CG_FULL, sm, 0);
         }
         __syncwarp();
-        // U3b: the new nodes in q order -> work[k] = pos | node << 8
+        // U3b: the new nodes in q order -> work[k] = pos | node << W
         u32 K = 0;
         for (u32 qb = 0; qb < L; qb += 32) {
             const u32 q = qb + lane;
             const bool isnew = q < L && s.kindq(q) != 0;
             const u32 bal = __ballot_sync(CG_FULL, isnew);
-            if (isnew) s.work(K + __popc(bal & cg_lt_mask())) = (u16)((u32)s.posq(q) | ((u32)s.nodeq(q) << 8));
+            if (isnew) s.work(K + __popc(bal & cg_lt_mask())) = (ItemT)((u32)s.posq(q) | ((u32)s.nodeq(q) << W));
             K += __popc(bal);
         }
         __syncwarp();
@@ -544,37 +670,37 @@ __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s
             const u32 p = pb + lane;
             if (p < V0) {
                 u32 lo = 0, hi = K;                                   // first k with pos_k > p
-                while (lo < hi) { const u32 mid = (lo + hi) >> 1; if (((u32)s.work(mid) & 0xffu) <= p) lo = mid + 1; else hi = mid; }
+                while (lo < hi) { const u32 mid = (lo + hi) >> 1; if (((u32)s.work(mid) & IDNONE) <= p) lo = mid + 1; else hi = mid; }
                 const u32 node = s.r2n(cur, p);
-                s.r2n(nxt, p + lo) = (u8)node;
-                s.rank_of(node) = (u8)(p + lo);
+                s.r2n(nxt, p + lo) = (IdT)node;
+                s.rank_of(node) = (IdT)(p + lo);
             }
         }
         for (u32 kb2 = 0; kb2 < K; kb2 += 32) {
             const u32 k = kb2 + lane;
             if (k < K) {
                 const u32 it = s.work(k);
-                const u32 node = it >> 8, at = (it & 0xffu) + k;
-                s.r2n(nxt, at) = (u8)node;
-                s.rank_of(node) = (u8)at;
+                const u32 node = it >> W, at = (it & IDNONE) + k;
+                s.r2n(nxt, at) = (IdT)node;
+                s.rank_of(node) = (IdT)at;
             }
         }
         cur = nxt;
         __syncwarp();
-        // U4: row descriptors: letter | in-degree << 8 | first predecessor row << 16 | node << 24, and the 8 predecessor rows
+        // U4: row descriptors and the predecessor rows
         u32 sd = 0;
         for (u32 rb = 0; rb < V; rb += 32) {
             const u32 r = rb + lane;
             if (r < V) {
                 const u32 node = s.r2n(cur, r);
-                const u32 deg = (s.meta(node) >> 4) & 15u;
-                const u64 P = s.pred(node);
-                u64 rows = 0;
+                const u32 deg = ((u32)s.meta(node) >> 4) & 15u;
+                const VecT P = s.pred(node);
+                VecT rows = Pk::zero();
 #pragma unroll
                 for (u32 e = 0; e < 8; ++e)
-                    if (e < deg) rows |= (u64)((u32)s.rank_of(cg_byte64(P, e)) + 1u) << (8u * e);
+                    if (e < deg) rows = Pk::set(rows, e, (u32)s.rank_of(Pk::get(P, e)) + 1u);
                 s.prow(r) = rows;
-                s.rdesc(r) = (u32)s.letter(node) | (deg << 8) | (((u32)rows & 0xffu) << 16) | (node << 24);
+                s.rdesc(r) = (typename Pk::Rdesc)((u32)s.letter(node) | (deg << 8) | (Pk::first(rows) << 16)) | ((typename Pk::Rdesc)node << (16 + W));
                 sd += deg ? deg : 1u;
             }
         }
@@ -603,14 +729,14 @@ __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s
             u32 cnt[4] = {0, 0, 0, 0};
             u8 row0 = 0;
             const u32 node = s.xr2n(i);
-            const u32 m = s.meta(node);
-            const u32 na = m & 3u;
+            const MetaT m = s.meta(node);
+            const u32 na = (u32)m & 3u;
             for (u32 a = 0; a <= na; ++a) {
-                const u32 x = a == 0 ? node : (m >> (8u * a)) & 0xffu;
+                const u32 x = a == 0 ? node : (u32)((m >> (W * a)) & IDMASK);
                 const u8 ch = s.letter(x);
                 const u32 code = cg_base_code(ch) & 3u;
                 cnt[code] = s.nseq(x);
-                if (s.meta(x) & 4u) row0 = ch;
+                if ((u32)s.meta(x) & 4u) row0 = ch;
             }
             const u32 cA = cnt[0], cC = cnt[1], cG = cnt[2], cT = cnt[3];
             const u32 cM = nseqs - (cA + cC + cG + cT);
@@ -629,14 +755,16 @@ __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s
     return outn;
 }
 
-// Persistent warps over the tier's queue (same protocol as cg_poa_drain).
+// Persistent warps over the tier's queue (same protocol as cg_poa_drain).  scratch: per-warp slices of
+// CgPoa2Lay<T>::per_warp bytes for the global-memory tiers, unused by the shared-memory tiers.
 template <class T>
-__global__ void __launch_bounds__(T::WARPS * 32, T::CTAS_PER_SM) k_poa2(CgChunk c, u32 nwarps, const uint2* jobs, u32* qctl, uint2* jobs_next,
-                                                                      u32* qnext) {
+__global__ void __launch_bounds__(T::WARPS * 32, T::CTAS_PER_SM) k_poa2(CgChunk c, u8* scratch, u32 nwarps, const uint2* jobs, u32* qctl,
+                                                                      uint2* jobs_next, u32* qnext) {
     const u32 gw = blockIdx.x * T::WARPS + cg_warp();
     if (gw >= nwarps) return;                       // warp-uniform; no block-wide barrier in this kernel
     CgPoa2G<T> s;
-    s.wo = CgPoa2Lay<T>::per_warp * cg_warp();
+    s.wo = (u32)CgPoa2Lay<T>::per_warp * cg_warp();
+    s.base = T::SMEM ? nullptr : scratch + CgPoa2Lay<T>::per_warp * (size_t)gw;
     const u32 lane = cg_lane();
     const u32 nfront = qctl[0], nback = qctl[2], cap = qctl[3];
     u64 cnt_aln = 0, cnt_cells = 0, cnt_pred = 0;

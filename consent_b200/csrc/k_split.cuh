@@ -17,20 +17,29 @@
 #define CG_SPLIT_WARPS (CG_SPLIT_THREADS / 32u)
 // POA job routing.  The final graph size of a region is predicted from its longest segment L and its depth n
 // (fit on PacBio-profile piles: V ~ 1.52 L + 0.022 L n - 7, +12 % margin); a wrong guess only costs a re-queue.
-// class 0/1: first compact tier (heavy / light), 2/3: second compact tier (heavy / light).
+// class 0/1: compact tier 1 (heavy / light), 2/3: compact tier 2 (heavy / light), 4: compact tier 3, 5: wide tiers.
+// The capacities mirror k_poa2.cuh's tiers.
 #define CG_POA_C1_LCAP 64u
 #define CG_POA_C1_VCAP 128u
 #define CG_POA_C1_CELLS 2048u
+#define CG_POA_C2_LCAP 120u
+#define CG_POA_C2_VCAP 254u
+#define CG_POA_C2_CELLS 8192u
+#define CG_POA_C3_CELLS 24576u
+#define CG_POA_C_SEGCAP 192u
 #define CG_POA_C1_HEAVY 24000u     // sequences x predicted cells: front of the queue (drained first)
 #define CG_POA_C2_HEAVY 200000u
+#define CG_POA_NCLASS 6u
 __device__ __forceinline__ u32 cg_poa_class(u32 n, u32 L) {
     u32 vhat = (L * (1557u + 23u * n)) >> 10;
     vhat = vhat > 8u ? vhat - 7u : 1u;
     vhat += vhat >> 3;
     const u32 cells = (vhat + 1u) * (L + 1u);
     const u32 cost = n * cells;
-    const bool c1 = L <= CG_POA_C1_LCAP && vhat <= CG_POA_C1_VCAP && cells <= CG_POA_C1_CELLS;
-    return c1 ? (cost >= CG_POA_C1_HEAVY ? 0u : 1u) : (cost >= CG_POA_C2_HEAVY ? 2u : 3u);
+    if (n > CG_POA_C_SEGCAP || L > CG_POA_C2_LCAP || vhat > CG_POA_C2_VCAP || cells > CG_POA_C3_CELLS) return 5u;
+    if (L <= CG_POA_C1_LCAP && vhat <= CG_POA_C1_VCAP && cells <= CG_POA_C1_CELLS) return cost >= CG_POA_C1_HEAVY ? 0u : 1u;
+    if (cells <= CG_POA_C2_CELLS) return cost >= CG_POA_C2_HEAVY ? 2u : 3u;
+    return 4u;
 }
 
 // idx-th smallest (0-based) distance of the pair (s1,s2) over reads holding both.
@@ -154,39 +163,43 @@ __global__ void __launch_bounds__(CG_SPLIT_THREADS) k_split(CgChunk c) {
     // shared-memory tier, the rest to the medium tier (either re-queues what it cannot hold); inside a queue the
     // heavy jobs (sequences x longest segment) go to the front, which is drained first.
     if (warp != 0) return;
-    u32 cnt4[4] = {0, 0, 0, 0};                       // small-heavy, small-light, medium-heavy, medium-light
+    u32 cnt[CG_POA_NCLASS];
+#pragma unroll
+    for (u32 q = 0; q < CG_POA_NCLASS; ++q) cnt[q] = 0;
     for (u32 gb = 0; gb < nreg; gb += 32) {
         const u32 g = gb + lane;
-        u32 cls = 4;
+        u32 cls = CG_POA_NCLASS;
         if (g < nreg && regs[g].kind == CG_REG_POA) cls = cg_poa_class(regs[g].n, regs[g].max_len);
 #pragma unroll
-        for (u32 q = 0; q < 4; ++q) cnt4[q] += __popc(__ballot_sync(CG_FULL, cls == q));
+        for (u32 q = 0; q < CG_POA_NCLASS; ++q) cnt[q] += __popc(__ballot_sync(CG_FULL, cls == q));
     }
-    const u32 njobs = cnt4[0] + cnt4[1] + cnt4[2] + cnt4[3];
-    u32 base4[4] = {0, 0, 0, 0};
-    if (lane == 0) {
-        if (cnt4[0]) base4[0] = atomicAdd(&c.qctl[0], cnt4[0]);
-        if (cnt4[1]) base4[1] = atomicAdd(&c.qctl[2], cnt4[1]);
-        if (cnt4[2]) base4[2] = atomicAdd(&c.qctl[4], cnt4[2]);
-        if (cnt4[3]) base4[3] = atomicAdd(&c.qctl[6], cnt4[3]);
-    }
+    u32 njobs = 0;
 #pragma unroll
-    for (u32 q = 0; q < 4; ++q) base4[q] = __shfl_sync(CG_FULL, base4[q], 0);
+    for (u32 q = 0; q < CG_POA_NCLASS; ++q) njobs += cnt[q];
+    // class -> (queue, end): 0 q0 front, 1 q0 back, 2 q1 front, 3 q1 back, 4 q2 front, 5 q3 front
+    u32 base[CG_POA_NCLASS];
+#pragma unroll
+    for (u32 q = 0; q < CG_POA_NCLASS; ++q) {
+        base[q] = 0;
+        const u32 ctl = q < 4 ? 4u * (q >> 1) + 2u * (q & 1u) : 4u * (q - 2u);
+        if (lane == 0 && cnt[q]) base[q] = atomicAdd(&c.qctl[ctl], cnt[q]);
+        base[q] = __shfl_sync(CG_FULL, base[q], 0);
+    }
     const u32 cap_s = c.qctl[3], cap_m = c.qctl[7];
     u32 run_off = 0;
     for (u32 gb = 0; gb < nreg; gb += 32) {
         const u32 g = gb + lane;
         const bool isp = g < nreg && regs[g].kind == CG_REG_POA;
-        u32 cls = 4;
+        u32 cls = CG_POA_NCLASS;
         if (isp) cls = cg_poa_class(regs[g].n, regs[g].max_len);
         const u32 sz = isp ? regs[g].sum_len : 0u;
         const u32 inc = cg_warp_scan(sz);
         u32 my = 0;
 #pragma unroll
-        for (u32 q = 0; q < 4; ++q) {
+        for (u32 q = 0; q < CG_POA_NCLASS; ++q) {
             const u32 bal = __ballot_sync(CG_FULL, cls == q);
-            if (cls == q) my = base4[q] + __popc(bal & ((1u << lane) - 1u));
-            base4[q] += __popc(bal);
+            if (cls == q) my = base[q] + __popc(bal & ((1u << lane) - 1u));
+            base[q] += __popc(bal);
         }
         if (isp) {
             regs[g].arena_off = run_off + inc - sz;
@@ -194,7 +207,9 @@ __global__ void __launch_bounds__(CG_SPLIT_THREADS) k_split(CgChunk c) {
             if (cls == 0) c.jobs_s[my] = job;
             else if (cls == 1) c.jobs_s[cap_s - 1 - my] = job;
             else if (cls == 2) c.jobs_m[my] = job;
-            else c.jobs_m[cap_m - 1 - my] = job;
+            else if (cls == 3) c.jobs_m[cap_m - 1 - my] = job;
+            else if (cls == 4) c.jobs_3[my] = job;
+            else c.jobs_w[my] = job;
         }
         run_off += __shfl_sync(CG_FULL, inc, 31);
     }

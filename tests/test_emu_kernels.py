@@ -59,13 +59,19 @@ def test_emulated_chunking_and_staged_calls_do_not_change_results(emu, oracle):
 
 
 def test_emulated_poa_tier_overflow_requeues_jobs(emu, oracle):
+    # N = 8 piles have few anchors: their regions run from a few bases to whole windows, so the jobs spread over the
+    # compact and the wide tiers (and some are re-queued from one to the next)
     batch = synth_windows(3, 8, seed=44)
     want, _ = oracle.correct_windows(batch, threads=4)
-    tiny = emu(poa_medium_cells=2048, poa_tier0_nodes=64, poa_tier0_cells=4096, poa_tier1_nodes=512, poa_tier1_cells=1 << 18)
-    assert_same(tiny.correct_windows(batch), want, "jobs re-queued small -> medium -> global tiers 0 -> 1")
+    assert_same(emu().correct_windows(batch), want, "jobs spread over / re-queued through the POA tiers")
+    # two unrelated sequences (1500 and 2100 bases): no anchors -> one whole-window region, too long for every k_poa2 tier -> k_poa
+    long_pile = Batch.from_piles([["".join("ACGT"[(i * 7 + i // 3) % 4] for i in range(1500)),
+                                   "".join("ACGT"[(i * 5 + i // 7 + 1) % 4] for i in range(2100))]])
+    want, _ = oracle.correct_windows(long_pile, threads=1)
+    assert_same(emu().correct_windows(long_pile), want, "last-resort tier 1")
+    assert_same(emu(poa_tier1_cells=1 << 20).correct_windows(long_pile), want, "last-resort tier 1 -> 2")
     with pytest.raises(ConsentError) as e:
-        emu(poa_medium_cells=2048, poa_tier0_nodes=64, poa_tier0_cells=4096, poa_tier1_nodes=128, poa_tier1_cells=8192,
-            poa_tier2_nodes=256, poa_tier2_cells=16384).correct_windows(batch)
+        emu(poa_tier1_cells=1 << 20, poa_tier2_cells=1 << 20).correct_windows(long_pile)
     assert e.value.code == -6
 
 

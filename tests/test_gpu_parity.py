@@ -68,8 +68,16 @@ def test_gpu_mixed_depth_batch_and_chunking(gpu, oracle):
 def test_gpu_poa_tier_overflow(gpu, oracle):
     batch = concat([synth_windows(16, 8, seed=66), Batch.from_piles([p for n, p in edge_piles(5) if "no_anchor" in n or "outlier" in n])])
     want, _ = oracle.correct_windows(batch, threads=32)
-    tiny = gpu(poa_medium_cells=2048, poa_tier0_nodes=64, poa_tier0_cells=4096, poa_tier1_nodes=1024, poa_tier1_cells=1 << 20)
-    assert_same(tiny.correct_windows(batch), want, "jobs re-queued to larger scratch tiers")
+    assert_same(gpu().correct_windows(batch), want, "jobs spread over / re-queued through the POA tiers")
+    # two unrelated sequences (1500 and 2100 bases): one whole-window region, too long for every k_poa2 tier -> k_poa (last resort)
+    long_pile = Batch.from_piles([["".join("ACGT"[(i * 7 + i // 3) % 4] for i in range(1500)),
+                                   "".join("ACGT"[(i * 5 + i // 7 + 1) % 4] for i in range(2100))]])
+    want, _ = oracle.correct_windows(long_pile, threads=1)
+    assert_same(gpu().correct_windows(long_pile), want, "last-resort tier 1")
+    assert_same(gpu(poa_tier1_cells=1 << 20).correct_windows(long_pile), want, "last-resort tier 1 -> 2")
+    with pytest.raises(ConsentError) as e:
+        gpu(poa_tier1_cells=1 << 20, poa_tier2_cells=1 << 20).correct_windows(long_pile)
+    assert e.value.code == -6
 
 
 def test_gpu_errors(gpu):
