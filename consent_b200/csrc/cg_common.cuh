@@ -126,11 +126,11 @@ struct CgChunk {
     u8* arena;                    // region consensuses
     u8* fin;                      // per window: 3 slices of (2*n_bases+64) bytes: consensus, temp, path
     u32* visited;                 // per window ceil(solid_cap/32) words (bit per solid k-mer)
-    // POA job queues (k_poa2.cuh tiers): 0 compact 1, 1 compact 2, 2 compact 3, 3 wide 1 (filled by k_split), then the
-    // re-queue chain (consent_b200.cu).  qctl[4*t + {0,1,2,3}] = jobs at the front of queue t, next job to take, jobs at
+    // POA job queues (k_poa2.cuh tiers): 0 tier C1, 1 tier G, 2 tier W1 (filled by k_split), then the re-queue chain
+    // (consent_b200.cu).  qctl[4*t + {0,1,2,3}] = jobs at the front of queue t, next job to take, jobs at
     // the back, capacity of the array.  A job that outgrows a tier is pushed to the front of that tier's overflow queue.
     u32* qctl;
-    uint2* jobs_s; uint2* jobs_m; uint2* jobs_3; uint2* jobs_w;
+    uint2* jobs_s; uint2* jobs_m; uint2* jobs_w;
     // status
     u32* flags;
     CgCountersDev* counters;

@@ -10,7 +10,9 @@
 #include <string.h>
 
 #include <algorithm>
+#include <condition_variable>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -71,14 +73,42 @@ struct HostResults {
     bool in_use = false, orphan = false;
 };
 
+// One timed stage = a pair of events on the lane's stream; collected after the final sync of cg_run.
+struct StageSpan { int stage; cudaEvent_t a, b; };
+
+// A lane = everything one chunk needs while it is in flight: its stream(s), workspaces and pinned control words.
+// Two lanes alternate over the chunks of a batch (chunk i on lane i % 2, each driven by its own host thread), so the
+// tail of one chunk's POA — a few long jobs on a few warps — runs under the next chunk's kernels.
+#ifndef CG_EMU
+#define CG_NLANES 2
+#else
+#define CG_NLANES 1          // the SIMT emulator runs launches synchronously on the calling thread
+#endif
+struct Lane {
+    cudaStream_t stream = nullptr;
+    cudaStream_t s_poa[3] = {nullptr, nullptr, nullptr};   // compact 2, compact 3 and wide 1 run beside compact 1
+    cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr}, ev_gather = nullptr, ev_end = nullptr;
+    DevBuf pwords, ptags, win, offs, solid_k, solid_c, slot_tpos, slot_kmer, anchors, chain, rel, pos, regions, arena, fin, visited;
+    DevBuf jobs_s, jobs_m, jobs_3, jobs_w, jobs_r, jobs_x, ctl, off_fin, out_off;
+    DevBuf g_mem, w1_mem, w2_mem; // per-warp global scratch of the POA tiers G (matrix only), W1 and W2
+    u32* h_ctl = nullptr;        // pinned: flags + queue control + totals
+    std::string err;
+    int rc = 0;
+    float stage_ms[CG_N_STAGES]{};
+    u32 stage_launches[CG_N_STAGES]{};
+    std::vector<StageSpan> spans;
+    std::vector<cudaEvent_t> evpool;
+    size_t pool_at = 0;
+};
+
 struct cg_handle {
     int device = 0;
     cg_params p{};
-    cudaStream_t stream = nullptr;      // kernels
+    Lane lane[CG_NLANES];
+    int n_lanes = CG_NLANES;
     cudaStream_t s_h2d = nullptr;       // batch upload, chunk by chunk
     cudaStream_t s_d2h = nullptr;       // results download, chunk by chunk
     std::vector<cudaEvent_t> ev_h2d;    // [chunk] bases of the chunk are resident
-    cudaEvent_t ev_gather = nullptr;
     bool h2d_pending = false;           // cg_correct_windows: the kernels of chunk i wait for ev_h2d[i]
     HostResults* stream_out = nullptr;  // cg_correct_windows: results are downloaded chunk by chunk into this
     std::mutex pool_mu;
@@ -98,44 +128,45 @@ struct cg_handle {
     std::vector<u32> h_tlen;            // [W] template length
     std::vector<ChunkPlan> chunks;
     bool uploaded = false, ran = false;
-    // chunk workspaces
-    DevBuf pwords, ptags, win, offs, solid_k, solid_c, slot_tpos, slot_kmer, anchors, chain, rel, pos, regions, arena, fin, visited;
-    DevBuf jobs_s, jobs_m, jobs_3, jobs_w, jobs_r, jobs_x, ctl, off_fin, out_off;
+    // POA tiers
+    std::mutex tier_mu;                  // the last-resort scratch is shared by the lanes
     PoaTier tier[3];                     // k_poa.cuh: global-memory tiers without an in-degree limit (the last resort); [0] unused
-    u32 c1_warps = 0, c2_warps = 0, c3_warps = 0, w1_warps = 0, w2_warps = 0;   // resident warps of the k_poa2.cuh tiers
-    DevBuf w2_mem;                       // per-warp scratch of the global-memory wide tier
-    cudaStream_t s_poa[3] = {nullptr, nullptr, nullptr};   // compact 2, compact 3 and wide 1 run beside compact 1
-    cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
-    // batch outputs (device, dense)
+    u32 c1_warps = 0, g_warps = 0, w1_warps = 0, w2_warps = 0;   // resident warps of the k_poa2.cuh tiers
+    // batch outputs (device, dense), appended chunk by chunk IN ORDER: commit_mu/commit_cv serialise the tail of run_chunk
     DevBuf o_cons, o_sk, o_sc, o_status, o_len, o_nsol;
     u64 o_cons_n = 0, o_solid_n = 0;
+    std::mutex commit_mu;
+    std::condition_variable commit_cv;
+    size_t next_commit = 0;
+    bool abort_run = false;
     // instrumentation
     float stage_ms[CG_N_STAGES]{};
-    float run_ms = 0;             // whole cg_run on the stream (CUDA events)
-    cudaEvent_t ev_run[2]{};
+    float run_ms = 0;             // whole cg_run (CUDA events: first launch of lane 0 to the last result of any lane)
+    cudaEvent_t ev_run0 = nullptr;
     u32 stage_launches[CG_N_STAGES]{};
     cg_counters counters{};
-    u32* h_ctl = nullptr;        // pinned: flags + queue control + totals
 };
 
 namespace {
 
 std::string g_create_err;
 
-#define CK(call)                                                                                     \
+#define CK_TO(errstr, call)                                                                          \
     do {                                                                                             \
         cudaError_t e__ = (call);                                                                    \
         if (e__ != cudaSuccess) {                                                                    \
-            h->err = std::string(#call) + ": " + cudaGetErrorString(e__);                            \
+            (errstr) = std::string(#call) + ": " + cudaGetErrorString(e__);                          \
             return e__ == cudaErrorMemoryAllocation ? CG_ERR_OUT_OF_MEMORY : CG_ERR_CUDA;            \
         }                                                                                            \
     } while (0)
+#define CK(call) CK_TO(h->err, call)      /* single-threaded parts */
+#define CKL(call) CK_TO(L.err, call)      /* inside a lane */
 
 inline u64 round_up(u64 v, u64 m) { return (v + m - 1) / m * m; }
 
 // ctl layout (u32 words, device): [0] flags, [1] upload-validation flags, [4 + 4t ..] queue t {front jobs, next, back jobs, capacity}:
-// t = 0 compact 1, 1 compact 2, 2 compact 3, 3 wide 1 (filled by k_split); 4 what the compact tiers re-queued (-> compact 3 again),
-// 5 -> wide 1 again, 6 -> wide 2, 7 -> k_poa tier 1, 8 -> k_poa tier 2
+// t = 0 tier C1, 1 tier G, 2 tier W1 (filled by k_split); re-queued: 3 -> G again, 4 -> W1 again, 5 -> W2, 6 -> k_poa tier 1,
+// 7 -> k_poa tier 2
 enum { CTL_FLAGS = 0, CTL_VFLAGS = 1, CTL_Q = 4, CTL_NQ = 10, CTL_WORDS = 48, HCTL_STAGE = 64, HCTL_VFLAGS = 120, HCTL_WORDS = 128 };
 // offs layout (u64 arrays of nwin+1): solid, slot, pos, reg, arena
 // out_off layout: cons_off[nwin+1], solid_off[nwin+1]
@@ -174,7 +205,7 @@ int plan_chunks(cg_handle* h) {
     return CG_OK;
 }
 
-int ensure_tier(cg_handle* h, PoaTier& T) {
+int ensure_tier(Lane& L, PoaTier& T) {
     if (T.ready) return CG_OK;
     const u32 ncap = CG_N_MAX + 1;
     const u32 scap = T.vcap ? 2 * (T.ecap + 4 * T.vcap) : 0;
@@ -189,8 +220,8 @@ int ensure_tier(cg_handle* h, PoaTier& T) {
                  o_stack = take(4 * (size_t)scap), o_an = take(4 * (size_t)alncap), o_ap = take(4 * (size_t)alncap),
                  o_sr = take(2 * (size_t)ncap), o_ss = take(2 * (size_t)ncap), o_sl = take(2 * (size_t)ncap), o_H = take(2 * T.hcap);
     const size_t per_warp = round_up(o, 256);
-    CK(T.mem.ensure(per_warp * T.warps));
-    CK(T.desc.ensure(sizeof(CgPoaScratch) * T.warps));
+    CKL(T.mem.ensure(per_warp * T.warps));
+    CKL(T.desc.ensure(sizeof(CgPoaScratch) * T.warps));
     std::vector<CgPoaScratch> d(T.warps);
     for (u32 i = 0; i < T.warps; ++i) {
         u8* b = T.mem.as<u8>() + per_warp * i;
@@ -203,86 +234,85 @@ int ensure_tier(cg_handle* h, PoaTier& T) {
         s.stack = (u32*)(b + o_stack); s.aln_node = (i32*)(b + o_an); s.aln_pos = (i32*)(b + o_ap);
         s.seg_read = (u16*)(b + o_sr); s.seg_start = (u16*)(b + o_ss); s.seg_len = (u16*)(b + o_sl); s.H = (i16*)(b + o_H);
     }
-    CK(cudaMemcpyAsync(T.desc.p, d.data(), sizeof(CgPoaScratch) * T.warps, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    CKL(cudaMemcpyAsync(T.desc.p, d.data(), sizeof(CgPoaScratch) * T.warps, cudaMemcpyHostToDevice, L.stream));
+    CKL(cudaStreamSynchronize(L.stream));
     T.ready = true;
     return CG_OK;
 }
 
-// One timed stage = a pair of events on the stream; collected after the final sync of cg_run.
-struct StageSpan { int stage; cudaEvent_t a, b; };
+int stream_out_chunk(cg_handle* h, Lane& L, const ChunkPlan& cp, u64 cons_n, u64 solid_n);
 
-int stream_out_chunk(cg_handle* h, const ChunkPlan& cp, u64 cons_n, u64 solid_n);
-
-int run_chunk(cg_handle* h, size_t ci, std::vector<StageSpan>& spans, std::vector<cudaEvent_t>& pool, size_t& pool_at) {
+// Every stage of the path for the windows of chunk ci, on lane L.  The ordered tail (dense outputs appended after those
+// of chunk ci - 1) waits for its turn.
+int run_chunk(cg_handle* h, Lane& L, size_t ci) {
     const ChunkPlan& cp = h->chunks[ci];
-    cudaStream_t st = h->stream;
+    cudaStream_t st = L.stream;
     const u32 nwin = cp.nwin;
     auto ev = [&]() -> cudaEvent_t {
-        if (pool_at == pool.size()) { cudaEvent_t e; cudaEventCreate(&e); pool.push_back(e); }
-        return pool[pool_at++];
+        if (L.pool_at == L.evpool.size()) { cudaEvent_t e; cudaEventCreate(&e); L.evpool.push_back(e); }
+        return L.evpool[L.pool_at++];
     };
-    auto span_begin = [&](int stage) { StageSpan s{stage, ev(), ev()}; cudaEventRecord(s.a, st); spans.push_back(s); };
-    auto span_end = [&]() { cudaEventRecord(spans.back().b, st); };
+    auto span_begin = [&](int stage) { StageSpan sp{stage, ev(), ev()}; cudaEventRecord(sp.a, st); L.spans.push_back(sp); };
+    auto span_end = [&]() { cudaEventRecord(L.spans.back().b, st); };
 
     // ---- workspaces
-    CK(h->pwords.ensure((cp.nwords + 16) * 4)); CK(h->ptags.ensure((cp.nwords + 16) * 4));
-    CK(h->win.ensure(sizeof(CgWin) * nwin));
-    CK(h->offs.ensure(sizeof(u64) * 5 * (nwin + 1)));
-    CK(h->solid_k.ensure(cp.solid_tot * 4 + 16)); CK(h->solid_c.ensure(cp.solid_tot * 4 + 16));
-    CK(h->slot_tpos.ensure(cp.slot_tot * 2 + 16)); CK(h->slot_kmer.ensure(cp.slot_tot * 4 + 16));
-    CK(h->anchors.ensure(cp.slot_tot * 2 + 16)); CK(h->chain.ensure(cp.slot_tot * 2 + 16)); CK(h->rel.ensure(cp.slot_tot * 4 + 16));
-    CK(h->pos.ensure(cp.pos_tot * 2 + 16));
-    CK(h->regions.ensure(cp.reg_tot * sizeof(CgRegion) + 16));
-    CK(h->arena.ensure(cp.arena_tot + 16));
-    CK(h->visited.ensure((cp.solid_tot / 32 + nwin + 2) * 4));
-    for (DevBuf* jb : {&h->jobs_s, &h->jobs_m, &h->jobs_3, &h->jobs_w, &h->jobs_r, &h->jobs_x}) CK(jb->ensure(cp.reg_tot * sizeof(uint2) + 16));
-    CK(h->off_fin.ensure(sizeof(u64) * (nwin + 1)));
-    CK(h->out_off.ensure(sizeof(u64) * 2 * (nwin + 1)));
+    CKL(L.pwords.ensure((cp.nwords + 16) * 4)); CKL(L.ptags.ensure((cp.nwords + 16) * 4));
+    CKL(L.win.ensure(sizeof(CgWin) * nwin));
+    CKL(L.offs.ensure(sizeof(u64) * 5 * (nwin + 1)));
+    CKL(L.solid_k.ensure(cp.solid_tot * 4 + 16)); CKL(L.solid_c.ensure(cp.solid_tot * 4 + 16));
+    CKL(L.slot_tpos.ensure(cp.slot_tot * 2 + 16)); CKL(L.slot_kmer.ensure(cp.slot_tot * 4 + 16));
+    CKL(L.anchors.ensure(cp.slot_tot * 2 + 16)); CKL(L.chain.ensure(cp.slot_tot * 2 + 16)); CKL(L.rel.ensure(cp.slot_tot * 4 + 16));
+    CKL(L.pos.ensure(cp.pos_tot * 2 + 16));
+    CKL(L.regions.ensure(cp.reg_tot * sizeof(CgRegion) + 16));
+    CKL(L.arena.ensure(cp.arena_tot + 16));
+    CKL(L.visited.ensure((cp.solid_tot / 32 + nwin + 2) * 4));
+    for (DevBuf* jb : {&L.jobs_s, &L.jobs_m, &L.jobs_3, &L.jobs_w, &L.jobs_r, &L.jobs_x}) CKL(jb->ensure(cp.reg_tot * sizeof(uint2) + 16));
+    CKL(L.off_fin.ensure(sizeof(u64) * (nwin + 1)));
+    CKL(L.out_off.ensure(sizeof(u64) * 2 * (nwin + 1)));
 
     CgChunk c{};
     c.bases = h->d_bases.as<char>(); c.seq_off = h->d_seq_off.as<u64>(); c.win_seq_begin = h->d_wsb.as<u32>();
     c.w0 = cp.w0; c.nwin = nwin;
     c.k = h->p.mer_size; c.solid = h->p.solid_thresh; c.common = h->p.common_kmers; c.min_anchors = h->p.min_anchors;
-    c.pwords = h->pwords.as<u32>(); c.ptags = h->ptags.as<u32>(); c.pword_base = cp.pword_base;
-    c.win = h->win.as<CgWin>();
-    u64* offs = h->offs.as<u64>();
+    c.pwords = L.pwords.as<u32>(); c.ptags = L.ptags.as<u32>(); c.pword_base = cp.pword_base;
+    c.win = L.win.as<CgWin>();
+    u64* offs = L.offs.as<u64>();
     c.off_solid = offs; c.off_slot = offs + (nwin + 1); c.off_pos = offs + 2 * (nwin + 1); c.off_reg = offs + 3 * (nwin + 1);
     c.off_arena = offs + 4 * (nwin + 1);
-    c.solid_k = h->solid_k.as<u32>(); c.solid_c = h->solid_c.as<u32>();
-    c.slot_tpos = h->slot_tpos.as<u16>(); c.slot_kmer = h->slot_kmer.as<u32>(); c.anchors = h->anchors.as<u16>();
-    c.chain = h->chain.as<u16>(); c.rel = h->rel.as<u32>(); c.pos = h->pos.as<u16>();
-    c.regions = h->regions.as<CgRegion>(); c.arena = h->arena.as<u8>(); c.fin = nullptr; c.visited = h->visited.as<u32>();
-    u32* ctl = h->ctl.as<u32>();
-    c.qctl = ctl + CTL_Q; c.jobs_s = h->jobs_s.as<uint2>(); c.jobs_m = h->jobs_m.as<uint2>(); c.jobs_3 = h->jobs_3.as<uint2>();
-    c.jobs_w = h->jobs_w.as<uint2>();
+    c.solid_k = L.solid_k.as<u32>(); c.solid_c = L.solid_c.as<u32>();
+    c.slot_tpos = L.slot_tpos.as<u16>(); c.slot_kmer = L.slot_kmer.as<u32>(); c.anchors = L.anchors.as<u16>();
+    c.chain = L.chain.as<u16>(); c.rel = L.rel.as<u32>(); c.pos = L.pos.as<u16>();
+    c.regions = L.regions.as<CgRegion>(); c.arena = L.arena.as<u8>(); c.fin = nullptr; c.visited = L.visited.as<u32>();
+    u32* ctl = L.ctl.as<u32>();
+    c.qctl = ctl + CTL_Q; c.jobs_s = L.jobs_s.as<uint2>(); c.jobs_m = L.jobs_m.as<uint2>(); c.jobs_w = L.jobs_w.as<uint2>();
     c.flags = ctl + CTL_FLAGS;
     c.counters = (CgCountersDev*)(ctl + CTL_WORDS);
-    u64* off_fin = h->off_fin.as<u64>();
-    u64* cons_off = h->out_off.as<u64>();
+    u64* off_fin = L.off_fin.as<u64>();
+    u64* cons_off = L.out_off.as<u64>();
     u64* solid_off = cons_off + (nwin + 1);
 
-    if (h->h2d_pending) CK(cudaStreamWaitEvent(st, h->ev_h2d[ci], 0));
+    if (h->h2d_pending) CKL(cudaStreamWaitEvent(st, h->ev_h2d[ci], 0));
 
     // ---- stage 0: plan, offsets, pack
     span_begin(CG_STAGE_PACK);
     {
         u32 qinit[4 * CTL_NQ] = {0};
         for (int t = 0; t < CTL_NQ; ++t) qinit[4 * t + 3] = (u32)cp.reg_tot;
-        memcpy(h->h_ctl + HCTL_STAGE, qinit, sizeof qinit);              // pinned staging, consumed before the next chunk's sync
-        CK(cudaMemcpyAsync(ctl + CTL_Q, h->h_ctl + HCTL_STAGE, sizeof qinit, cudaMemcpyHostToDevice, st));
+        memcpy(L.h_ctl + HCTL_STAGE, qinit, sizeof qinit);              // pinned staging, consumed before the lane's next sync
+        CKL(cudaMemcpyAsync(ctl + CTL_Q, L.h_ctl + HCTL_STAGE, sizeof qinit, cudaMemcpyHostToDevice, st));
+        CKL(cudaMemsetAsync(ctl + CTL_FLAGS, 0, sizeof(u32), st));
     }
-    CK(cudaMemsetAsync(h->pwords.as<u32>() + cp.nwords, 0, 16 * 4, st));
-    CK(cudaMemsetAsync(h->ptags.as<u32>() + cp.nwords, 0xff, 16 * 4, st));
+    CKL(cudaMemsetAsync(L.pwords.as<u32>() + cp.nwords, 0, 16 * 4, st));
+    CKL(cudaMemsetAsync(L.ptags.as<u32>() + cp.nwords, 0xff, 16 * 4, st));
     CG_LAUNCH(k_plan, (nwin + 127) / 128, 128, 0, st, c);
     CG_LAUNCH(k_scan, 5, 1024, 1024 * sizeof(u64), st, c.off_solid, c.off_slot, c.off_pos, c.off_reg, c.off_arena, nwin);
     CG_LAUNCH(k_pack, nwin, 256, 0, st, c);
-    h->stage_launches[CG_STAGE_PACK] += 3;
+    L.stage_launches[CG_STAGE_PACK] += 3;
     span_end();
 
     span_begin(CG_STAGE_INDEX);
     CG_LAUNCH(k_index, nwin, CG_IDX_THREADS, CG_IDX_SMEM_BYTES, st, c);
-    h->stage_launches[CG_STAGE_INDEX] += 1;
+    L.stage_launches[CG_STAGE_INDEX] += 1;
     span_end();
 
     span_begin(CG_STAGE_CHAIN);
@@ -290,115 +320,125 @@ int run_chunk(cg_handle* h, size_t ci, std::vector<StageSpan>& spans, std::vecto
     const size_t smem_cap = (size_t)h->smem_optin;
     if (chain_smem > smem_cap) chain_smem = smem_cap;      // windows that really need more are flagged by the kernel
     CG_LAUNCH(k_chain, nwin, CG_CHAIN_THREADS, chain_smem, st, c, (u32)chain_smem);
-    h->stage_launches[CG_STAGE_CHAIN] += 1;
+    L.stage_launches[CG_STAGE_CHAIN] += 1;
     span_end();
 
     span_begin(CG_STAGE_SPLIT);
     CG_LAUNCH(k_split, nwin, CG_SPLIT_THREADS, 0, st, c);
-    h->stage_launches[CG_STAGE_SPLIT] += 1;
+    L.stage_launches[CG_STAGE_SPLIT] += 1;
     span_end();
 
-    // ---- POA (k_poa2.cuh).  k_split routed every region to the tier its predicted size fits; the four tiers run side by
-    // side (the big, long-running jobs are launched first so that their tail overlaps the bulk of the small ones).  What a
-    // tier cannot hold after all is re-queued: compact -> compact 3 -> wide 1 -> wide 2 (global memory) -> k_poa.
+    // ---- POA (k_poa2.cuh).  k_split routed every region to the tier its predicted size fits; the three tiers run side by
+    // side (the wide, long-running jobs are launched first so that they overlap the bulk of the small ones).  What a tier
+    // cannot hold after all is re-queued: C1 -> G -> W1 -> W2 -> k_poa.
     span_begin(CG_STAGE_POA);
     u32* q = ctl + CTL_Q;
-    uint2* jobs_r = h->jobs_r.as<uint2>(); uint2* jobs_x = h->jobs_x.as<uint2>();
-    uint2* jobs_q5 = c.jobs_s; uint2* jobs_q7 = c.jobs_m; uint2* jobs_q8 = c.jobs_3;      // re-used once their first life is over
-    CK(h->w2_mem.ensure(CgPoa2Lay<CgPoa2W2>::per_warp * (size_t)h->w2_warps));
-#define CG_POA2_LAUNCH(TIER, warps, stream, jin, qin, jout, qout)                                                               \
+    uint2* jobs_q3 = L.jobs_r.as<uint2>(); uint2* jobs_q4 = L.jobs_x.as<uint2>(); uint2* jobs_q5 = L.jobs_3.as<uint2>();
+    uint2* jobs_q6 = c.jobs_s; uint2* jobs_q7 = c.jobs_m;                                    // re-used once their first life is over
+    CKL(L.g_mem.ensure(CgPoa2Lay<CgPoa2GT>::scratch_per_warp * (size_t)h->g_warps));
+    CKL(L.w1_mem.ensure(CgPoa2Lay<CgPoa2W1>::scratch_per_warp * (size_t)h->w1_warps));
+    CKL(L.w2_mem.ensure(CgPoa2Lay<CgPoa2W2>::scratch_per_warp * (size_t)h->w2_warps));
+#define CG_POA2_LAUNCH(TIER, mem, warps, stream, jin, qin, jout, qout)                                                          \
     CG_LAUNCH(k_poa2<TIER>, ((warps) + TIER::WARPS - 1) / TIER::WARPS, TIER::WARPS * 32, CgPoa2Lay<TIER>::cta_bytes, stream, c, \
-              TIER::SMEM ? (u8*)nullptr : h->w2_mem.as<u8>(), (warps), (const uint2*)(jin), q + 4 * (qin), (jout), q + 4 * (qout))
-    CK(cudaEventRecord(h->ev_fork, st));
-    for (int i = 0; i < 3; ++i) CK(cudaStreamWaitEvent(h->s_poa[i], h->ev_fork, 0));
-    CG_POA2_LAUNCH(CgPoa2W1, h->w1_warps, h->s_poa[2], c.jobs_w, 3, jobs_x, 6);
-    CG_POA2_LAUNCH(CgPoa2C3, h->c3_warps, h->s_poa[1], c.jobs_3, 2, jobs_r, 4);
-    CG_POA2_LAUNCH(CgPoa2C2, h->c2_warps, h->s_poa[0], c.jobs_m, 1, jobs_r, 4);
-    CG_POA2_LAUNCH(CgPoa2C1, h->c1_warps, st, c.jobs_s, 0, jobs_r, 4);
-    for (int i = 0; i < 3; ++i) { CK(cudaEventRecord(h->ev_join[i], h->s_poa[i])); CK(cudaStreamWaitEvent(st, h->ev_join[i], 0)); }
-    CG_POA2_LAUNCH(CgPoa2C3, h->c3_warps, st, jobs_r, 4, jobs_q5, 5);
-    CG_POA2_LAUNCH(CgPoa2W1, h->w1_warps, st, jobs_q5, 5, jobs_x, 6);
-    CG_POA2_LAUNCH(CgPoa2W2, h->w2_warps, st, jobs_x, 6, jobs_q7, 7);
+              (mem), (warps), (const uint2*)(jin), q + 4 * (qin), (jout), q + 4 * (qout))
+    CKL(cudaEventRecord(L.ev_fork, st));
+    for (int i = 0; i < 2; ++i) CKL(cudaStreamWaitEvent(L.s_poa[i], L.ev_fork, 0));
+    CG_POA2_LAUNCH(CgPoa2W1, L.w1_mem.as<u8>(), h->w1_warps, L.s_poa[1], c.jobs_w, 2, jobs_q5, 5);
+    CG_POA2_LAUNCH(CgPoa2GT, L.g_mem.as<u8>(), h->g_warps, L.s_poa[0], c.jobs_m, 1, jobs_q4, 4);
+    CG_POA2_LAUNCH(CgPoa2C1, (u8*)nullptr, h->c1_warps, st, c.jobs_s, 0, jobs_q3, 3);
+    for (int i = 0; i < 2; ++i) { CKL(cudaEventRecord(L.ev_join[i], L.s_poa[i])); CKL(cudaStreamWaitEvent(st, L.ev_join[i], 0)); }
+    CG_POA2_LAUNCH(CgPoa2GT, L.g_mem.as<u8>(), h->g_warps, st, jobs_q3, 3, jobs_q4, 4);
+    CG_POA2_LAUNCH(CgPoa2W1, L.w1_mem.as<u8>(), h->w1_warps, st, jobs_q4, 4, jobs_q5, 5);
+    CG_POA2_LAUNCH(CgPoa2W2, L.w2_mem.as<u8>(), h->w2_warps, st, jobs_q5, 5, jobs_q6, 6);
 #undef CG_POA2_LAUNCH
-    h->stage_launches[CG_STAGE_POA] += 7;
+    L.stage_launches[CG_STAGE_POA] += 6;
     span_end();
 
     // the last resort (in-degree > 8, > 4096 nodes, > 2048-base segments): only if something got that far (count on the host)
-    CK(cudaMemcpyAsync(h->h_ctl, ctl, CTL_WORDS * sizeof(u32), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    CKL(cudaMemcpyAsync(L.h_ctl, ctl, CTL_WORDS * sizeof(u32), cudaMemcpyDeviceToHost, st));
+    CKL(cudaStreamSynchronize(st));
     if (getenv("CG_DEBUG"))
-        fprintf(stderr, "[consent_b200] chunk w0=%u nwin=%u POA jobs: compact1 %u+%u, compact2 %u+%u, compact3 %u, wide1 %u | re-queued: compact %u, "
-                "->wide1 %u, ->wide2 %u, ->k_poa %u\n",
-                cp.w0, nwin, h->h_ctl[CTL_Q + 0], h->h_ctl[CTL_Q + 2], h->h_ctl[CTL_Q + 4], h->h_ctl[CTL_Q + 6], h->h_ctl[CTL_Q + 8],
-                h->h_ctl[CTL_Q + 12], h->h_ctl[CTL_Q + 16], h->h_ctl[CTL_Q + 20], h->h_ctl[CTL_Q + 24], h->h_ctl[CTL_Q + 28]);
-    uint2* q_in = jobs_q7; uint2* q_out = jobs_q8;
-    for (int t = 1; t <= 2; ++t) {
-        const u32 over = h->h_ctl[CTL_Q + 4 * (t + 6)];
-        if (!over) break;
-        if (h->tier[t].warps == 0) { h->err = "a POA job outgrew the largest enabled scratch tier"; return CG_ERR_CAPACITY; }
-        { int rc = ensure_tier(h, h->tier[t]); if (rc) return rc; }
-        span_begin(CG_STAGE_POA);
-        CG_LAUNCH(k_poa, (h->tier[t].warps + CG_POA_WARPS_PER_CTA - 1) / CG_POA_WARPS_PER_CTA, CG_POA_THREADS, 0, st, c,
-                  h->tier[t].desc.as<CgPoaScratch>(), h->tier[t].warps, (const uint2*)q_in, q + 4 * (t + 6), t < 2 ? q_out : (uint2*)nullptr,
-                  q + 4 * (t + 7));
-        h->stage_launches[CG_STAGE_POA] += 1;
-        span_end();
-        CK(cudaMemcpyAsync(h->h_ctl, ctl, CTL_WORDS * sizeof(u32), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        std::swap(q_in, q_out);
+        fprintf(stderr, "[consent_b200] chunk w0=%u nwin=%u POA jobs: C1 %u+%u, G %u+%u, W1 %u | re-queued: ->G %u, ->W1 %u, ->W2 %u, ->k_poa %u\n",
+                cp.w0, nwin, L.h_ctl[CTL_Q + 0], L.h_ctl[CTL_Q + 2], L.h_ctl[CTL_Q + 4], L.h_ctl[CTL_Q + 6], L.h_ctl[CTL_Q + 8],
+                L.h_ctl[CTL_Q + 12], L.h_ctl[CTL_Q + 16], L.h_ctl[CTL_Q + 20], L.h_ctl[CTL_Q + 24]);
+    if (L.h_ctl[CTL_Q + 24]) {
+        std::lock_guard<std::mutex> lk(h->tier_mu);         // one lane at a time on the shared last-resort scratch
+        uint2* q_in = jobs_q6; uint2* q_out = jobs_q7;
+        for (int t = 1; t <= 2; ++t) {
+            const u32 over = L.h_ctl[CTL_Q + 4 * (t + 5)];
+            if (!over) break;
+            if (h->tier[t].warps == 0) { L.err = "a POA job outgrew the largest enabled scratch tier"; return CG_ERR_CAPACITY; }
+            { int rc = ensure_tier(L, h->tier[t]); if (rc) return rc; }
+            span_begin(CG_STAGE_POA);
+            CG_LAUNCH(k_poa, (h->tier[t].warps + CG_POA_WARPS_PER_CTA - 1) / CG_POA_WARPS_PER_CTA, CG_POA_THREADS, 0, st, c,
+                      h->tier[t].desc.as<CgPoaScratch>(), h->tier[t].warps, (const uint2*)q_in, q + 4 * (t + 5), t < 2 ? q_out : (uint2*)nullptr,
+                      q + 4 * (t + 6));
+            L.stage_launches[CG_STAGE_POA] += 1;
+            span_end();
+            CKL(cudaMemcpyAsync(L.h_ctl, ctl, CTL_WORDS * sizeof(u32), cudaMemcpyDeviceToHost, st));
+            CKL(cudaStreamSynchronize(st));
+            std::swap(q_in, q_out);
+        }
     }
 
     // ---- stitched lengths -> work slices
     span_begin(CG_STAGE_STITCH);
     CG_LAUNCH(k_stitch_len, (nwin + 127) / 128, 128, 0, st, c, off_fin);
     CG_LAUNCH(k_scan, 1, 1024, 1024 * sizeof(u64), st, off_fin, (u64*)nullptr, (u64*)nullptr, (u64*)nullptr, (u64*)nullptr, nwin);
-    h->stage_launches[CG_STAGE_STITCH] += 2;
+    L.stage_launches[CG_STAGE_STITCH] += 2;
     span_end();
     u64 fin_total = 0;
-    CK(cudaMemcpyAsync(&fin_total, off_fin + nwin, sizeof(u64), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    CK(h->fin.ensure(fin_total + 16));
-    c.fin = h->fin.as<u8>();
+    CKL(cudaMemcpyAsync(&fin_total, off_fin + nwin, sizeof(u64), cudaMemcpyDeviceToHost, st));
+    CKL(cudaStreamSynchronize(st));
+    CKL(L.fin.ensure(fin_total + 16));
+    c.fin = L.fin.as<u8>();
 
     span_begin(CG_STAGE_POLISH);
     CG_LAUNCH(k_polish, (nwin + CG_POLISH_WARPS_PER_CTA - 1) / CG_POLISH_WARPS_PER_CTA, CG_POLISH_THREADS, 0, st, c, (const u64*)off_fin);
-    h->stage_launches[CG_STAGE_POLISH] += 1;
+    L.stage_launches[CG_STAGE_POLISH] += 1;
     span_end();
 
     span_begin(CG_STAGE_STITCH);
     CG_LAUNCH(k_out_sizes, (nwin + 127) / 128, 128, 0, st, c, cons_off, solid_off);
     CG_LAUNCH(k_scan, 2, 1024, 1024 * sizeof(u64), st, cons_off, solid_off, (u64*)nullptr, (u64*)nullptr, (u64*)nullptr, nwin);
-    h->stage_launches[CG_STAGE_STITCH] += 2;
+    L.stage_launches[CG_STAGE_STITCH] += 2;
     span_end();
     u64 tot[2] = {0, 0};
-    CK(cudaMemcpyAsync(&tot[0], cons_off + nwin, sizeof(u64), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(&tot[1], solid_off + nwin, sizeof(u64), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(h->h_ctl, ctl, CTL_WORDS * sizeof(u32), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    if (h->h_ctl[CTL_FLAGS] & CG_FLAG_BAD_BASE) { h->err = "a base outside {A,C,G,T} in the batch"; return CG_ERR_BAD_BASE; }
-    if (h->h_ctl[CTL_FLAGS] & CG_FLAG_CAPACITY) { h->err = "a per-window capacity limit of this build was exceeded"; return CG_ERR_CAPACITY; }
-    if (h->h_ctl[CTL_FLAGS] & CG_FLAG_INTERNAL) { h->err = "internal invariant violated (anchor pair without common read)"; return CG_ERR_CUDA; }
+    CKL(cudaMemcpyAsync(&tot[0], cons_off + nwin, sizeof(u64), cudaMemcpyDeviceToHost, st));
+    CKL(cudaMemcpyAsync(&tot[1], solid_off + nwin, sizeof(u64), cudaMemcpyDeviceToHost, st));
+    CKL(cudaMemcpyAsync(L.h_ctl, ctl, CTL_WORDS * sizeof(u32), cudaMemcpyDeviceToHost, st));
+    CKL(cudaStreamSynchronize(st));
+    if (L.h_ctl[CTL_FLAGS] & CG_FLAG_BAD_BASE) { L.err = "a base outside {A,C,G,T} in the batch"; return CG_ERR_BAD_BASE; }
+    if (L.h_ctl[CTL_FLAGS] & CG_FLAG_CAPACITY) { L.err = "a per-window capacity limit of this build was exceeded"; return CG_ERR_CAPACITY; }
+    if (L.h_ctl[CTL_FLAGS] & CG_FLAG_INTERNAL) { L.err = "internal invariant violated (anchor pair without common read)"; return CG_ERR_CUDA; }
+
+    // ---- ordered tail: append this chunk's dense outputs after those of chunk ci - 1
+    std::unique_lock<std::mutex> lk(h->commit_mu);
+    h->commit_cv.wait(lk, [&] { return h->next_commit == ci || h->abort_run; });
+    if (h->abort_run) return CG_ERR_STATE;                 // another lane failed; its error is the one reported
     {   // dense batch outputs: sized from the density of the chunks so far, so that they rarely move
         const double frac = (double)(cp.w0 + nwin) / (double)h->W;
         const u64 need_c = h->o_cons_n + tot[0] + 16, need_s = (h->o_solid_n + tot[1]) * 4 + 16;
         if (need_c > h->o_cons.cap || need_s > h->o_sk.cap) {
-            if (h->stream_out) CK(cudaStreamSynchronize(h->s_d2h));        // a download may still read the old buffers
+            CKL(cudaDeviceSynchronize());                   // gathers of earlier chunks and downloads may still use the old buffers
             const u64 est_c = (u64)((double)need_c / frac * 1.05) + 4096, est_s = (u64)((double)need_s / frac * 1.05) + 4096;
-            CK(h->o_cons.ensure(std::max(need_c, est_c), true, st));
-            CK(h->o_sk.ensure(std::max(need_s, est_s), true, st));
-            CK(h->o_sc.ensure(std::max(need_s, est_s), true, st));
+            CKL(h->o_cons.ensure(std::max(need_c, est_c), true, st));
+            CKL(h->o_sk.ensure(std::max(need_s, est_s), true, st));
+            CKL(h->o_sc.ensure(std::max(need_s, est_s), true, st));
         }
     }
-
     span_begin(CG_STAGE_STITCH);
     CG_LAUNCH(k_gather, nwin, 256, 0, st, c, (const u64*)off_fin, (const u64*)cons_off, (const u64*)solid_off,
               h->o_cons.as<u8>() + h->o_cons_n, h->o_sk.as<u32>() + h->o_solid_n, h->o_sc.as<u32>() + h->o_solid_n,
               h->o_status.as<u8>() + cp.w0, h->o_cons_n, h->o_solid_n, h->o_len.as<u64>() + cp.w0, h->o_nsol.as<u64>() + cp.w0);
-    h->stage_launches[CG_STAGE_STITCH] += 1;
+    L.stage_launches[CG_STAGE_STITCH] += 1;
     span_end();
-    if (h->stream_out) { int rc = stream_out_chunk(h, cp, tot[0], tot[1]); if (rc) return rc; }
+    if (h->stream_out) { int rc = stream_out_chunk(h, L, cp, tot[0], tot[1]); if (rc) return rc; }
     h->o_cons_n += tot[0];
     h->o_solid_n += tot[1];
+    h->next_commit = ci + 1;
+    lk.unlock();
+    h->commit_cv.notify_all();
     return CG_OK;
 }
 
@@ -460,7 +500,7 @@ int host_results_reserve(cg_handle* h, HostResults* r, u64 need_c, u64 need_s, u
 }
 
 // Download the dense results of one chunk on the D2H stream while the next chunk computes.
-int stream_out_chunk(cg_handle* h, const ChunkPlan& cp, u64 cons_n, u64 solid_n) {
+int stream_out_chunk(cg_handle* h, Lane& L, const ChunkPlan& cp, u64 cons_n, u64 solid_n) {
     HostResults* r = h->stream_out;
     const double frac = (double)(cp.w0 + cp.nwin) / (double)h->W;
     const u64 need_c = h->o_cons_n + cons_n + 1, need_s = h->o_solid_n + solid_n + 1;
@@ -469,8 +509,8 @@ int stream_out_chunk(cg_handle* h, const ChunkPlan& cp, u64 cons_n, u64 solid_n)
         int rc = host_results_reserve(h, r, std::max(need_c, est_c), std::max(need_s, est_s), h->o_cons_n, h->o_solid_n);
         if (rc) return rc;
     }
-    CK(cudaEventRecord(h->ev_gather, h->stream));
-    CK(cudaStreamWaitEvent(h->s_d2h, h->ev_gather, 0));
+    CK(cudaEventRecord(L.ev_gather, L.stream));
+    CK(cudaStreamWaitEvent(h->s_d2h, L.ev_gather, 0));
     cudaStream_t sd = h->s_d2h;
     if (cons_n) CK(cudaMemcpyAsync(r->cons + h->o_cons_n, h->o_cons.as<u8>() + h->o_cons_n, cons_n, cudaMemcpyDeviceToHost, sd));
     if (solid_n) {
@@ -516,29 +556,30 @@ int cg_create(int device, const cg_params* params, cg_handle** out) {
         g_create_err = "device has too little shared memory per block for k_index (needs sm_100-class 227 KB)";
         delete h; return CG_ERR_NO_DEVICE;
     }
-    bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
-    ok = ok && cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking) == cudaSuccess;
+    bool ok = cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking) == cudaSuccess;
-    ok = ok && cudaEventCreateWithFlags(&h->ev_gather, cudaEventDisableTiming) == cudaSuccess;
-    ok = ok && cudaMallocHost(&h->h_ctl, HCTL_WORDS * sizeof(u32)) == cudaSuccess;
-    for (int i = 0; i < 3; ++i)
-        ok = ok && cudaStreamCreateWithFlags(&h->s_poa[i], cudaStreamNonBlocking) == cudaSuccess && cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming) == cudaSuccess;
-    ok = ok && cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) == cudaSuccess;
-    ok = ok && cudaEventCreate(&h->ev_run[0]) == cudaSuccess && cudaEventCreate(&h->ev_run[1]) == cudaSuccess;
-    ok = ok && h->ctl.ensure(CTL_WORDS * sizeof(u32) + sizeof(CgCountersDev)) == cudaSuccess;
+    ok = ok && cudaEventCreate(&h->ev_run0) == cudaSuccess;
+    for (Lane& L : h->lane) {
+        ok = ok && cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking) == cudaSuccess;
+        for (int i = 0; i < 3; ++i)
+            ok = ok && cudaStreamCreateWithFlags(&L.s_poa[i], cudaStreamNonBlocking) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&L.ev_join[i], cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&L.ev_fork, cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&L.ev_gather, cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreate(&L.ev_end) == cudaSuccess;
+        ok = ok && cudaMallocHost(&L.h_ctl, HCTL_WORDS * sizeof(u32)) == cudaSuccess;
+        ok = ok && L.ctl.ensure(CTL_WORDS * sizeof(u32) + sizeof(CgCountersDev)) == cudaSuccess;
+    }
     ok = ok && cudaFuncSetAttribute(k_index, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CG_IDX_SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin) == cudaSuccess;
     if (!ok) { g_create_err = std::string("CUDA initialisation failed: ") + cudaGetErrorString(cudaGetLastError()); cg_destroy(h); return CG_ERR_CUDA; }
     ok = cudaFuncSetAttribute(k_poa2<CgPoa2C1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CgPoa2Lay<CgPoa2C1>::cta_bytes) == cudaSuccess &&
-         cudaFuncSetAttribute(k_poa2<CgPoa2C2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CgPoa2Lay<CgPoa2C2>::cta_bytes) == cudaSuccess &&
-         cudaFuncSetAttribute(k_poa2<CgPoa2C3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CgPoa2Lay<CgPoa2C3>::cta_bytes) == cudaSuccess &&
-         cudaFuncSetAttribute(k_poa2<CgPoa2W1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CgPoa2Lay<CgPoa2W1>::cta_bytes) == cudaSuccess;
+         cudaFuncSetAttribute(k_poa2<CgPoa2GT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CgPoa2Lay<CgPoa2GT>::cta_bytes) == cudaSuccess;
     if (!ok) { g_create_err = std::string("CUDA initialisation failed: ") + cudaGetErrorString(cudaGetLastError()); cg_destroy(h); return CG_ERR_CUDA; }
     // POA tiers: resident warps of the k_poa2.cuh tiers; k_poa.cuh's global-memory tiers {nodes, edges, max segment length,
     // matrix cells, resident warps} are the last resort.
     h->c1_warps = (u32)h->sms * CgPoa2C1::CTAS_PER_SM * CgPoa2C1::WARPS;
-    h->c2_warps = (u32)h->sms * CgPoa2C2::CTAS_PER_SM * CgPoa2C2::WARPS;
-    h->c3_warps = (u32)h->sms * CgPoa2C3::CTAS_PER_SM * CgPoa2C3::WARPS;
+    h->g_warps = (u32)h->sms * CgPoa2GT::CTAS_PER_SM * CgPoa2GT::WARPS;
     h->w1_warps = (u32)h->sms * CgPoa2W1::CTAS_PER_SM * CgPoa2W1::WARPS;
     h->w2_warps = (u32)h->sms * 2;
     h->tier[1].vcap = 16384; h->tier[1].ecap = 65536;  h->tier[1].lcap = CG_LEN_MAX; h->tier[1].hcap = 32u << 20;
@@ -552,31 +593,29 @@ int cg_create(int device, const cg_params* params, cg_handle** out) {
 void cg_destroy(cg_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
-    if (h->stream) cudaStreamSynchronize(h->stream);
-    if (h->s_h2d) cudaStreamSynchronize(h->s_h2d);
-    if (h->s_d2h) cudaStreamSynchronize(h->s_d2h);
+    cudaDeviceSynchronize();
     {
         std::lock_guard<std::mutex> lk(h->pool_mu);
         for (HostResults* r : h->pool) { if (r->in_use) { r->orphan = true; r->owner = nullptr; } else host_results_release(r); }
         h->pool.clear();
     }
     for (cudaEvent_t e : h->ev_h2d) cudaEventDestroy(e);
-    if (h->ev_gather) cudaEventDestroy(h->ev_gather);
     if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
     if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
-    DevBuf* bufs[] = {&h->d_bases, &h->d_seq_off, &h->d_wsb, &h->pwords, &h->ptags, &h->win, &h->offs, &h->solid_k, &h->solid_c, &h->slot_tpos,
-                      &h->slot_kmer, &h->anchors, &h->chain, &h->rel, &h->pos, &h->regions, &h->arena, &h->fin, &h->visited, &h->jobs_s,
-                      &h->jobs_m, &h->jobs_3, &h->jobs_w, &h->jobs_r, &h->w2_mem, &h->jobs_x, &h->ctl, &h->off_fin, &h->out_off, &h->o_cons, &h->o_sk, &h->o_sc, &h->o_status, &h->o_len, &h->o_nsol};
+    if (h->ev_run0) cudaEventDestroy(h->ev_run0);
+    for (Lane& L : h->lane) {
+        DevBuf* lb[] = {&L.pwords, &L.ptags, &L.win, &L.offs, &L.solid_k, &L.solid_c, &L.slot_tpos, &L.slot_kmer, &L.anchors, &L.chain, &L.rel,
+                        &L.pos, &L.regions, &L.arena, &L.fin, &L.visited, &L.jobs_s, &L.jobs_m, &L.jobs_3, &L.jobs_w, &L.jobs_r, &L.jobs_x,
+                        &L.ctl, &L.off_fin, &L.out_off, &L.g_mem, &L.w1_mem, &L.w2_mem};
+        for (DevBuf* b : lb) b->release();
+        for (cudaEvent_t e : L.evpool) cudaEventDestroy(e);
+        for (cudaEvent_t e : {L.ev_fork, L.ev_gather, L.ev_end, L.ev_join[0], L.ev_join[1], L.ev_join[2]}) if (e) cudaEventDestroy(e);
+        for (cudaStream_t st : {L.stream, L.s_poa[0], L.s_poa[1], L.s_poa[2]}) if (st) cudaStreamDestroy(st);
+        if (L.h_ctl) cudaFreeHost(L.h_ctl);
+    }
+    DevBuf* bufs[] = {&h->d_bases, &h->d_seq_off, &h->d_wsb, &h->o_cons, &h->o_sk, &h->o_sc, &h->o_status, &h->o_len, &h->o_nsol};
     for (DevBuf* b : bufs) b->release();
     for (auto& t : h->tier) { t.mem.release(); t.desc.release(); }
-    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
-    for (int i = 0; i < 3; ++i) {
-        if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
-        if (h->s_poa[i]) { cudaStreamSynchronize(h->s_poa[i]); cudaStreamDestroy(h->s_poa[i]); }
-    }
-    for (auto& e : h->ev_run) if (e) cudaEventDestroy(e);
-    if (h->h_ctl) cudaFreeHost(h->h_ctl);
-    if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
 
@@ -585,9 +624,9 @@ int cg_set_option(cg_handle* h, const char* key, long long value) {
     const std::string k(key);
     if (k == "chunk_budget_bytes") h->chunk_budget = (size_t)value;
     else if (k == "chunk_max_windows") h->chunk_max_windows = (u32)std::max<long long>(1, value);
-    else if (k == "poa_compact1_warps") h->c1_warps = (u32)std::max<long long>(1, value);
-    else if (k == "poa_compact2_warps") h->c2_warps = (u32)std::max<long long>(1, value);
-    else if (k == "poa_compact3_warps") h->c3_warps = (u32)std::max<long long>(1, value);
+    else if (k == "lanes") h->n_lanes = (int)std::max<long long>(1, std::min<long long>(value, CG_NLANES));
+    else if (k == "poa_c1_warps") h->c1_warps = (u32)std::max<long long>(1, value);
+    else if (k == "poa_g_warps") h->g_warps = (u32)std::max<long long>(1, value);
     else if (k == "poa_wide1_warps") h->w1_warps = (u32)std::max<long long>(1, value);
     else if (k == "poa_wide2_warps") h->w2_warps = (u32)std::max<long long>(1, value);
     else if (k == "poa_tier1_warps") { h->tier[1].warps = (u32)value; h->tier[1].ready = false; }
@@ -644,10 +683,10 @@ int upload_impl(cg_handle* h, const cg_batch* in, bool wait) {
     CK(cudaMemcpyAsync(h->d_seq_off.p, in->seq_off, (n_seqs + 1) * sizeof(u64), cudaMemcpyHostToDevice, sc));
     CK(cudaMemcpyAsync(h->d_wsb.p, in->win_seq_begin, (W + 1) * sizeof(u32), cudaMemcpyHostToDevice, sc));
     // every sequence: offsets non-decreasing, length within the build's limit (checked on the device, one word back)
-    u32* vflags = h->ctl.as<u32>() + CTL_VFLAGS;
+    u32* vflags = h->lane[0].ctl.as<u32>() + CTL_VFLAGS;
     CK(cudaMemsetAsync(vflags, 0, sizeof(u32), sc));
     if (n_seqs) CG_LAUNCH(k_validate, (u32)std::min<u64>((n_seqs + 255) / 256, 4096), 256, 0, sc, h->d_seq_off.as<u64>(), n_seqs, vflags);
-    CK(cudaMemcpyAsync(h->h_ctl + HCTL_VFLAGS, vflags, sizeof(u32), cudaMemcpyDeviceToHost, sc));
+    CK(cudaMemcpyAsync(h->lane[0].h_ctl + HCTL_VFLAGS, vflags, sizeof(u32), cudaMemcpyDeviceToHost, sc));
     plan_chunks(h);
     while (h->ev_h2d.size() < h->chunks.size()) {
         cudaEvent_t e;
@@ -655,8 +694,8 @@ int upload_impl(cg_handle* h, const cg_batch* in, bool wait) {
         h->ev_h2d.push_back(e);
     }
     CK(cudaStreamSynchronize(sc));
-    if (h->h_ctl[HCTL_VFLAGS] & CG_FLAG_BAD_OFFSETS) { h->err = "seq_off must be non-decreasing"; return CG_ERR_INVALID_ARG; }
-    if (h->h_ctl[HCTL_VFLAGS] & CG_FLAG_CAPACITY) { h->err = "a sequence is longer than 6000 bases"; return CG_ERR_CAPACITY; }
+    if (h->lane[0].h_ctl[HCTL_VFLAGS] & CG_FLAG_BAD_OFFSETS) { h->err = "seq_off must be non-decreasing"; return CG_ERR_INVALID_ARG; }
+    if (h->lane[0].h_ctl[HCTL_VFLAGS] & CG_FLAG_CAPACITY) { h->err = "a sequence is longer than 6000 bases"; return CG_ERR_CAPACITY; }
     for (size_t ci = 0; ci < h->chunks.size(); ++ci) {
         const ChunkPlan& cp = h->chunks[ci];
         const u64 b0 = h->h_wbase[cp.w0], b1 = h->h_wbase[cp.w0 + cp.nwin];
@@ -669,33 +708,81 @@ int upload_impl(cg_handle* h, const cg_batch* in, bool wait) {
     return CG_OK;
 }
 
+// Chunks ci = lane, lane + n_lanes, ... on lane `li` (its own host thread when there are two lanes).
+void lane_main(cg_handle* h, int li, int n_lanes) {
+    Lane& L = h->lane[li];
+    cudaSetDevice(h->device);
+    L.rc = CG_OK;
+    for (size_t ci = (size_t)li; ci < h->chunks.size(); ci += (size_t)n_lanes) {
+        {
+            std::lock_guard<std::mutex> lk(h->commit_mu);
+            if (h->abort_run) break;
+        }
+        const int rc = run_chunk(h, L, ci);
+        if (rc != CG_OK) {
+            std::lock_guard<std::mutex> lk(h->commit_mu);
+            if (!h->abort_run) L.rc = rc;                  // the first failure is the one reported
+            h->abort_run = true;
+            h->commit_cv.notify_all();
+            break;
+        }
+    }
+    cudaEventRecord(L.ev_end, L.stream);
+}
+
 int run_impl(cg_handle* h) {
     cudaSetDevice(h->device);
     h->ran = false;
     h->o_cons_n = h->o_solid_n = 0;
+    h->next_commit = 0;
+    h->abort_run = false;
     memset(h->stage_ms, 0, sizeof h->stage_ms);
     memset(h->stage_launches, 0, sizeof h->stage_launches);
     CK(h->o_status.ensure(h->W + 16)); CK(h->o_len.ensure((h->W + 1) * sizeof(u64))); CK(h->o_nsol.ensure((h->W + 1) * sizeof(u64)));
-    CK(cudaEventRecord(h->ev_run[0], h->stream));
-    CK(cudaMemsetAsync(h->ctl.p, 0, CTL_WORDS * sizeof(u32) + sizeof(CgCountersDev), h->stream));
-    std::vector<StageSpan> spans;
-    static thread_local std::vector<cudaEvent_t> pool;
-    size_t pool_at = 0;
-    for (size_t ci = 0; ci < h->chunks.size(); ++ci) {
-        int rc = run_chunk(h, ci, spans, pool, pool_at);
-        if (rc != CG_OK) { cudaStreamSynchronize(h->stream); cudaStreamSynchronize(h->s_h2d); cudaStreamSynchronize(h->s_d2h); return rc; }
+    const int n_lanes = std::max(1, std::min<int>(h->n_lanes, (int)std::min<size_t>(h->chunks.size(), CG_NLANES)));
+    CK(cudaEventRecord(h->ev_run0, h->lane[0].stream));
+    for (int li = 0; li < n_lanes; ++li) {
+        Lane& L = h->lane[li];
+        L.spans.clear(); L.pool_at = 0; L.err.clear(); L.rc = CG_OK;
+        memset(L.stage_ms, 0, sizeof L.stage_ms); memset(L.stage_launches, 0, sizeof L.stage_launches);
+        CK(cudaMemsetAsync(L.ctl.p, 0, CTL_WORDS * sizeof(u32) + sizeof(CgCountersDev), L.stream));
+        if (li) CK(cudaStreamWaitEvent(L.stream, h->ev_run0, 0));      // nothing of this run starts before its first event
     }
-    CgCountersDev cd{};
-    CK(cudaMemcpyAsync(&cd, h->ctl.as<u32>() + CTL_WORDS, sizeof cd, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaEventRecord(h->ev_run[1], h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    cudaEventElapsedTime(&h->run_ms, h->ev_run[0], h->ev_run[1]);
-    for (const StageSpan& s : spans) { float ms = 0; cudaEventElapsedTime(&ms, s.a, s.b); h->stage_ms[s.stage] += ms; }
+#ifndef CG_EMU
+    std::vector<std::thread> workers;
+    for (int li = 1; li < n_lanes; ++li) workers.emplace_back(lane_main, h, li, n_lanes);
+    lane_main(h, 0, n_lanes);
+    for (std::thread& t : workers) t.join();
+#else
+    lane_main(h, 0, 1);
+#endif
+    int rc = CG_OK;
+    for (int li = 0; li < n_lanes; ++li) {
+        cudaStreamSynchronize(h->lane[li].stream);
+        for (int i = 0; i < 3; ++i) cudaStreamSynchronize(h->lane[li].s_poa[i]);
+        if (rc == CG_OK && h->lane[li].rc != CG_OK) { rc = h->lane[li].rc; h->err = h->lane[li].err; }
+    }
+    if (rc != CG_OK) { cudaStreamSynchronize(h->s_h2d); cudaStreamSynchronize(h->s_d2h); return rc; }
+    h->run_ms = 0;
+    CgCountersDev sum{};
+    for (int li = 0; li < n_lanes; ++li) {
+        Lane& L = h->lane[li];
+        float ms = 0;
+        cudaEventElapsedTime(&ms, h->ev_run0, L.ev_end);
+        h->run_ms = std::max(h->run_ms, ms);
+        for (const StageSpan& sp : L.spans) { float m2 = 0; cudaEventElapsedTime(&m2, sp.a, sp.b); h->stage_ms[sp.stage] += m2; }
+        for (int i = 0; i < CG_N_STAGES; ++i) h->stage_launches[i] += L.stage_launches[i];
+        CgCountersDev cd{};
+        CK(cudaMemcpy(&cd, L.ctl.as<u32>() + CTL_WORDS, sizeof cd, cudaMemcpyDeviceToHost));
+        sum.anchors += cd.anchors; sum.regions += cd.regions; sum.poa_graphs += cd.poa_graphs; sum.alignments += cd.alignments;
+        sum.dp_cells += cd.dp_cells; sum.dp_pred_cells += cd.dp_pred_cells; sum.solid_kmers += cd.solid_kmers;
+        sum.consensus_bytes += cd.consensus_bytes; sum.fallback_windows += cd.fallback_windows;
+    }
     cg_counters& o = h->counters;
     o.windows = h->W; o.sequences = h->n_seqs; o.bases = h->n_bases;
-    o.anchors = cd.anchors; o.regions = cd.regions; o.poa_graphs = cd.poa_graphs; o.alignments = cd.alignments;
-    o.dp_cells = cd.dp_cells; o.dp_pred_cells = cd.dp_pred_cells; o.solid_kmers = cd.solid_kmers;
-    o.consensus_bytes = cd.consensus_bytes; o.fallback_windows = cd.fallback_windows;
+    o.anchors = sum.anchors; o.regions = sum.regions; o.poa_graphs = sum.poa_graphs; o.alignments = sum.alignments;
+    o.dp_cells = sum.dp_cells; o.dp_pred_cells = sum.dp_pred_cells; o.solid_kmers = sum.solid_kmers;
+    o.consensus_bytes = sum.consensus_bytes; o.fallback_windows = sum.fallback_windows;
     h->ran = true;
     return CG_OK;
 }

@@ -22,12 +22,14 @@
 //  * Traceback is the only per-alignment phase left on lane 0 (a dependent walk by nature), at two memory round
 //    trips per step.
 //
-// Tiers (one template, T = ids x storage x capacities):
-//   C1, C2, C3 : byte ids (<= 254 nodes), everything in shared memory, 2048 / 8192 / 24576 matrix cells
-//   W1         : 16-bit ids (<= 1024 nodes), shared memory, 49152 cells, one warp per SM
-//   W2, W3     : 16-bit ids, per-warp scratch in global memory (L2), up to 65534 nodes / 6000-base segments
+// Tiers (one template, T = ids x storage x capacities).  What decides a tier's speed is how many warps an SM holds
+// (every warp is a chain of dependent steps), i.e. shared memory per warp, so only small matrices live there:
+//   C1 : byte ids (<= 128 nodes), graph AND matrix (<= 2048 cells) in shared memory             20 warps / SM
+//   G  : byte ids (<= 254 nodes), graph in shared memory, matrix in global memory (L2)            20 warps / SM
+//   W1 : 16-bit ids (<= 1024 nodes, 1024-base segments), everything in global memory (L2)         8 warps / SM
+//   W2 : 16-bit ids (<= 4096 nodes, 2048-base segments, 4 M cells), global memory                 2 warps / SM
 // A job that outgrows its tier (nodes, cells, in-degree, segment length) is re-queued for the next one before anything
-// is committed; in-degree > 8 ends in k_poa (k_poa.cuh), which has no such limit.
+// is committed; in-degree > 8 and anything bigger end in k_poa (k_poa.cuh), which has no such limits.
 #pragma once
 #include "cg_common.cuh"
 #include "k_poa.cuh"
@@ -76,19 +78,20 @@ template <> struct CgIdPack<u16> {
 };
 
 // ------------------------------------------------------------------ tiers
-template <class IdT_, bool SMEM_, u32 VCAP_, u32 HCELLS_, u32 LCAP_, u32 SEGCAP_, u32 WARPS_, u32 CTAS_> struct CgPoa2Tier {
+enum { CG_P2_ALL_SMEM = 0, CG_P2_H_GLOBAL = 1, CG_P2_ALL_GLOBAL = 2 };
+template <class IdT_, int STORE_, u32 VCAP_, u32 HCELLS_, u32 LCAP_, u32 SEGCAP_, u32 WARPS_, u32 CTAS_> struct CgPoa2Tier {
     typedef IdT_ IdT;
-    static constexpr bool SMEM = SMEM_;
+    static constexpr int STORE = STORE_;
+    static constexpr bool SMEM = STORE_ != CG_P2_ALL_GLOBAL;            // the graph is in shared memory
+    static constexpr bool H_SMEM = STORE_ == CG_P2_ALL_SMEM;            // ... and so is the score matrix
     static constexpr u32 VCAP = VCAP_, HCELLS = HCELLS_, LCAP = LCAP_, SEGCAP = SEGCAP_, WARPS = WARPS_, CTAS_PER_SM = CTAS_;
     static constexpr u32 SCAP = 3 * VCAP_ + 8, ALNCAP = VCAP_ + LCAP_;
     static constexpr u32 SEQCAP = LCAP_ < 512u ? LCAP_ : 512u;        // segments up to this long are staged next to the graph
 };
-typedef CgPoa2Tier<u8, true, 128, 2048, 64, 192, 4, 5> CgPoa2C1;          // 86 % of the regions of a 150-deep pile
-typedef CgPoa2Tier<u8, true, 254, 8192, 120, 192, 4, 2> CgPoa2C2;         // 99.2 %
-typedef CgPoa2Tier<u8, true, 254, 24576, 120, 192, 1, 3> CgPoa2C3;        // the rest of them, bar a handful
-typedef CgPoa2Tier<u16, true, 1024, 49152, 512, 512, 1, 1> CgPoa2W1;
-typedef CgPoa2Tier<u16, false, 4096, 4u << 20, 2048, 4096, 4, 2> CgPoa2W2;
-typedef CgPoa2Tier<u16, false, 65534, 400u << 20, 6000, 4096, 4, 1> CgPoa2W3;
+typedef CgPoa2Tier<u8, CG_P2_ALL_SMEM, 128, 2048, 64, 192, 4, 5> CgPoa2C1;
+typedef CgPoa2Tier<u8, CG_P2_H_GLOBAL, 254, 30976, 120, 192, 4, 5> CgPoa2GT;
+typedef CgPoa2Tier<u16, CG_P2_ALL_GLOBAL, 1024, 512u << 10, 1024, 1024, 4, 2> CgPoa2W1;
+typedef CgPoa2Tier<u16, CG_P2_ALL_GLOBAL, 4096, 4u << 20, 2048, 4096, 4, 2> CgPoa2W2;
 
 template <class T> struct CgPoa2Lay {
     typedef CgIdPack<typename T::IdT> Pk;
@@ -103,7 +106,9 @@ template <class T> struct CgPoa2Lay {
                             o_tmp = o_work + WORK, o_letter = o_tmp + TMP, o_r2n = o_letter + r16(T::VCAP),
                             R2N_STRIDE = r16(ID * T::VCAP), o_rank = o_r2n + 2 * R2N_STRIDE, o_xr2n = o_rank + R2N_STRIDE,
                             o_xlead = o_xr2n + R2N_STRIDE, o_seq = o_xlead + r16(T::VCAP), o_H = o_seq + r16((size_t)T::SEQCAP + 16),
-                            per_warp = r16(o_H + 2 * (size_t)T::HCELLS + 16);
+                            h_bytes = r16(2 * (size_t)T::HCELLS + 16),
+                            per_warp = T::STORE == CG_P2_H_GLOBAL ? o_H : o_H + h_bytes,         // the graph slice (+ matrix unless it is apart)
+                            scratch_per_warp = T::STORE == CG_P2_ALL_SMEM ? 0 : T::STORE == CG_P2_H_GLOBAL ? h_bytes : per_warp;
     static constexpr size_t cta_bytes = T::SMEM ? per_warp * T::WARPS : 0;
 };
 
@@ -112,12 +117,12 @@ template <class T> struct CgPoa2G {
     typedef CgPoa2Lay<T> Lay;
     typedef CgIdPack<typename T::IdT> Pk;
     typedef typename T::IdT IdT;
-    u32 wo;                     // shared-memory tiers: byte offset of this warp's slice (every access an LDS/STS with an immediate offset)
-    u8* base;                   // global-memory tiers: this warp's scratch slice
+    u32 wo;                     // graph in shared memory: byte offset of this warp's slice (every access an LDS/STS with an immediate offset)
+    u8* base;                   // this warp's global scratch slice: everything (all-global tiers) or the matrix alone
     __device__ __forceinline__ u8* b() const { return T::SMEM ? cg_smem_base() + wo : base; }
     __device__ __forceinline__ typename Pk::Vec& pred(u32 i) const { return ((typename Pk::Vec*)(b() + Lay::o_pred))[i]; }
     __device__ __forceinline__ typename Pk::Vec& prow(u32 i) const { return ((typename Pk::Vec*)(b() + Lay::o_prow))[i]; }
-    __device__ __forceinline__ i16* H() const { return (i16*)(b() + Lay::o_H); }
+    __device__ __forceinline__ i16* H() const { return T::STORE == CG_P2_H_GLOBAL ? (i16*)base : (i16*)(b() + Lay::o_H); }
     __device__ __forceinline__ typename Pk::Rdesc& rdesc(u32 i) const { return ((typename Pk::Rdesc*)(b() + Lay::o_rdesc))[i]; }
     __device__ __forceinline__ typename Pk::Meta& meta(u32 i) const { return ((typename Pk::Meta*)(b() + Lay::o_meta))[i]; }
     __device__ __forceinline__ typename Pk::Seg& seg(u32 i) const { return ((typename Pk::Seg*)(b() + Lay::o_seg))[i]; }
@@ -756,7 +761,7 @@ __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s
 }
 
 // Persistent warps over the tier's queue (same protocol as cg_poa_drain).  scratch: per-warp slices of
-// CgPoa2Lay<T>::per_warp bytes for the global-memory tiers, unused by the shared-memory tiers.
+// CgPoa2Lay<T>::scratch_per_warp bytes (nothing for the all-shared-memory tier).
 template <class T>
 __global__ void __launch_bounds__(T::WARPS * 32, T::CTAS_PER_SM) k_poa2(CgChunk c, u8* scratch, u32 nwarps, const uint2* jobs, u32* qctl,
                                                                       uint2* jobs_next, u32* qnext) {
@@ -764,7 +769,7 @@ __global__ void __launch_bounds__(T::WARPS * 32, T::CTAS_PER_SM) k_poa2(CgChunk 
     if (gw >= nwarps) return;                       // warp-uniform; no block-wide barrier in this kernel
     CgPoa2G<T> s;
     s.wo = (u32)CgPoa2Lay<T>::per_warp * cg_warp();
-    s.base = T::SMEM ? nullptr : scratch + CgPoa2Lay<T>::per_warp * (size_t)gw;
+    s.base = T::STORE == CG_P2_ALL_SMEM ? nullptr : scratch + CgPoa2Lay<T>::scratch_per_warp * (size_t)gw;
     const u32 lane = cg_lane();
     const u32 nfront = qctl[0], nback = qctl[2], cap = qctl[3];
     u64 cnt_aln = 0, cnt_cells = 0, cnt_pred = 0;

@@ -17,29 +17,25 @@
 #define CG_SPLIT_WARPS (CG_SPLIT_THREADS / 32u)
 // POA job routing.  The final graph size of a region is predicted from its longest segment L and its depth n
 // (fit on PacBio-profile piles: V ~ 1.52 L + 0.022 L n - 7, +12 % margin); a wrong guess only costs a re-queue.
-// class 0/1: compact tier 1 (heavy / light), 2/3: compact tier 2 (heavy / light), 4: compact tier 3, 5: wide tiers.
-// The capacities mirror k_poa2.cuh's tiers.
+// class 0/1: tier C1 (heavy / light), 2/3: tier G (heavy / light), 4: wide tiers.  Capacities mirror k_poa2.cuh.
 #define CG_POA_C1_LCAP 64u
 #define CG_POA_C1_VCAP 128u
 #define CG_POA_C1_CELLS 2048u
-#define CG_POA_C2_LCAP 120u
-#define CG_POA_C2_VCAP 254u
-#define CG_POA_C2_CELLS 8192u
-#define CG_POA_C3_CELLS 24576u
+#define CG_POA_G_LCAP 120u
+#define CG_POA_G_VCAP 254u
 #define CG_POA_C_SEGCAP 192u
 #define CG_POA_C1_HEAVY 24000u     // sequences x predicted cells: front of the queue (drained first)
-#define CG_POA_C2_HEAVY 200000u
-#define CG_POA_NCLASS 6u
+#define CG_POA_G_HEAVY 400000u
+#define CG_POA_NCLASS 5u
 __device__ __forceinline__ u32 cg_poa_class(u32 n, u32 L) {
     u32 vhat = (L * (1557u + 23u * n)) >> 10;
     vhat = vhat > 8u ? vhat - 7u : 1u;
     vhat += vhat >> 3;
     const u32 cells = (vhat + 1u) * (L + 1u);
     const u32 cost = n * cells;
-    if (n > CG_POA_C_SEGCAP || L > CG_POA_C2_LCAP || vhat > CG_POA_C2_VCAP || cells > CG_POA_C3_CELLS) return 5u;
+    if (n > CG_POA_C_SEGCAP || L > CG_POA_G_LCAP || vhat > CG_POA_G_VCAP) return 4u;
     if (L <= CG_POA_C1_LCAP && vhat <= CG_POA_C1_VCAP && cells <= CG_POA_C1_CELLS) return cost >= CG_POA_C1_HEAVY ? 0u : 1u;
-    if (cells <= CG_POA_C2_CELLS) return cost >= CG_POA_C2_HEAVY ? 2u : 3u;
-    return 4u;
+    return cost >= CG_POA_G_HEAVY ? 2u : 3u;
 }
 
 // idx-th smallest (0-based) distance of the pair (s1,s2) over reads holding both.
@@ -176,7 +172,7 @@ __global__ void __launch_bounds__(CG_SPLIT_THREADS) k_split(CgChunk c) {
     u32 njobs = 0;
 #pragma unroll
     for (u32 q = 0; q < CG_POA_NCLASS; ++q) njobs += cnt[q];
-    // class -> (queue, end): 0 q0 front, 1 q0 back, 2 q1 front, 3 q1 back, 4 q2 front, 5 q3 front
+    // class -> (queue, end): 0 q0 front, 1 q0 back, 2 q1 front, 3 q1 back, 4 q2 front
     u32 base[CG_POA_NCLASS];
 #pragma unroll
     for (u32 q = 0; q < CG_POA_NCLASS; ++q) {
@@ -208,7 +204,6 @@ __global__ void __launch_bounds__(CG_SPLIT_THREADS) k_split(CgChunk c) {
             else if (cls == 1) c.jobs_s[cap_s - 1 - my] = job;
             else if (cls == 2) c.jobs_m[my] = job;
             else if (cls == 3) c.jobs_m[cap_m - 1 - my] = job;
-            else if (cls == 4) c.jobs_3[my] = job;
             else c.jobs_w[my] = job;
         }
         run_off += __shfl_sync(CG_FULL, inc, 31);

@@ -108,7 +108,7 @@ void        cg_destroy(cg_handle* h);
 const char* cg_last_error(const cg_handle* h);   /* h may be NULL: last create error */
 
 /* Tuning knobs that never change results: workspace budget per chunk of windows ("chunk_budget_bytes",
- * "chunk_max_windows"), resident warps of the POA tiers ("poa_compact{1,2,3}_warps", "poa_wide{1,2}_warps"),
+ * "chunk_max_windows", "lanes"), resident warps of the POA tiers ("poa_c1_warps", "poa_g_warps", "poa_wide{1,2}_warps"),
  * last-resort POA scratch ("poa_tier{1,2}_{warps,nodes,cells}"). */
 int         cg_set_option(cg_handle* h, const char* key, long long value);
 

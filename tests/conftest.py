@@ -50,7 +50,7 @@ def emu(entry):
     def make(params=None, **options):
         from consent_b200._ffi import Params
         c = Corrector(params or Params(), lib_path=path)
-        opts = {"poa_compact1_warps": 16, "poa_compact2_warps": 8, "poa_compact3_warps": 3, "poa_wide1_warps": 2, "poa_wide2_warps": 4,
+        opts = {"poa_c1_warps": 16, "poa_g_warps": 16, "poa_wide1_warps": 4, "poa_wide2_warps": 4,
                 "poa_tier1_warps": 2, "poa_tier2_warps": 2, "poa_tier1_cells": 8 << 20, "poa_tier2_cells": 16 << 20}
         opts.update(options)
         for k, v in opts.items():

@@ -7,7 +7,7 @@ from consent_b200.synth import synth_windows
 from tests.refs import Oracle
 o=Oracle()
 c=Corrector(Params(), lib_path="tests/emu/libconsent_emu.so")
-for k,v in {"poa_compact1_warps": 16, "poa_compact2_warps": 8, "poa_compact3_warps": 3, "poa_wide1_warps": 2, "poa_wide2_warps": 4, "poa_tier1_warps": 2, "poa_tier2_warps": 2, "poa_tier1_cells": 8 << 20, "poa_tier2_cells": 16 << 20}.items(): c.set_option(k,v)
+for k,v in {"poa_c1_warps": 16, "poa_g_warps": 16, "poa_wide1_warps": 4, "poa_wide2_warps": 4, "poa_tier1_warps": 2, "poa_tier2_warps": 2, "poa_tier1_cells": 8 << 20, "poa_tier2_cells": 16 << 20}.items(): c.set_option(k,v)
 for n,nw,seed in ((150,40,42),(20,30,7),(8,40,9),(47,20,11),(3,50,12),(150,30,77)):
     b=synth_windows(nw,n,seed=seed)
     t=time.time(); got=c.correct_windows(b); t1=time.time()-t
