@@ -85,9 +85,11 @@ struct StageSpan { int stage; cudaEvent_t a, b; };
 #define CG_NLANES 1          // the SIMT emulator runs launches synchronously on the calling thread
 #endif
 struct Lane {
-    cudaStream_t stream = nullptr;
-    cudaStream_t s_poa[3] = {nullptr, nullptr, nullptr};   // compact 2, compact 3 and wide 1 run beside compact 1
-    cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr}, ev_gather = nullptr, ev_end = nullptr;
+    cudaStream_t stream = nullptr;       // the bulk of a chunk: pack .. first pass of the POA tiers
+    cudaStream_t s_tail = nullptr;       // the rest of it (re-queued POA jobs, polish, gather), high priority: it is latency, not work
+    cudaStream_t s_poa[3] = {nullptr, nullptr, nullptr};   // tiers G and W1 run beside C1
+    cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr}, ev_gather = nullptr, ev_end = nullptr, ev_tail = nullptr;
+    bool tail_recorded = false;
     DevBuf pwords, ptags, win, offs, solid_k, solid_c, slot_tpos, slot_kmer, anchors, chain, rel, pos, regions, arena, fin, visited;
     DevBuf jobs_s, jobs_m, jobs_3, jobs_w, jobs_r, jobs_x, ctl, off_fin, out_off;
     DevBuf g_mem, w1_mem, w2_mem; // per-warp global scratch of the POA tiers G (matrix only), W1 and W2
@@ -109,6 +111,8 @@ struct cg_handle {
     cudaStream_t s_h2d = nullptr;       // batch upload, chunk by chunk
     cudaStream_t s_d2h = nullptr;       // results download, chunk by chunk
     std::vector<cudaEvent_t> ev_h2d;    // [chunk] bases of the chunk are resident
+    std::vector<cudaEvent_t> ev_bulk;   // [chunk] the bulk of the chunk's work (everything up to the POA tiers' first pass) is done
+    size_t bulk_enqueued = 0;           // chunks whose ev_bulk has been recorded (guarded by commit_mu)
     bool h2d_pending = false;           // cg_correct_windows: the kernels of chunk i wait for ev_h2d[i]
     HostResults* stream_out = nullptr;  // cg_correct_windows: results are downloaded chunk by chunk into this
     std::mutex pool_mu;
@@ -240,7 +244,7 @@ int ensure_tier(Lane& L, PoaTier& T) {
     return CG_OK;
 }
 
-int stream_out_chunk(cg_handle* h, Lane& L, const ChunkPlan& cp, u64 cons_n, u64 solid_n);
+int stream_out_chunk(cg_handle* h, Lane& L, cudaStream_t st, const ChunkPlan& cp, u64 cons_n, u64 solid_n);
 
 // Every stage of the path for the windows of chunk ci, on lane L.  The ordered tail (dense outputs appended after those
 // of chunk ci - 1) waits for its turn.
@@ -248,6 +252,7 @@ int run_chunk(cg_handle* h, Lane& L, size_t ci) {
     const ChunkPlan& cp = h->chunks[ci];
     cudaStream_t st = L.stream;
     const u32 nwin = cp.nwin;
+    if (L.tail_recorded) CKL(cudaStreamWaitEvent(st, L.ev_tail, 0));        // the lane's workspaces are free again
     auto ev = [&]() -> cudaEvent_t {
         if (L.pool_at == L.evpool.size()) { cudaEvent_t e; cudaEventCreate(&e); L.evpool.push_back(e); }
         return L.evpool[L.pool_at++];
@@ -292,6 +297,16 @@ int run_chunk(cg_handle* h, Lane& L, size_t ci) {
     u64* solid_off = cons_off + (nwin + 1);
 
     if (h->h2d_pending) CKL(cudaStreamWaitEvent(st, h->ev_h2d[ci], 0));
+    // Stagger the lanes: the bulk of chunk ci starts when the bulk of chunk ci - 1 is done, so that the latency-bound rest of
+    // a chunk (re-queued POA jobs, polish, the host round trips for sizes) always runs under the next chunk's bulk.
+    if (ci > 0) {
+        {
+            std::unique_lock<std::mutex> lk(h->commit_mu);
+            h->commit_cv.wait(lk, [&] { return h->bulk_enqueued >= ci || h->abort_run; });
+            if (h->abort_run) return CG_ERR_STATE;
+        }
+        CKL(cudaStreamWaitEvent(st, h->ev_bulk[ci - 1], 0));
+    }
 
     // ---- stage 0: plan, offsets, pack
     span_begin(CG_STAGE_PACK);
@@ -346,8 +361,18 @@ int run_chunk(cg_handle* h, Lane& L, size_t ci) {
     CG_POA2_LAUNCH(CgPoa2W1, L.w1_mem.as<u8>(), h->w1_warps, L.s_poa[1], c.jobs_w, 2, jobs_q5, 5);
     CG_POA2_LAUNCH(CgPoa2GT, L.g_mem.as<u8>(), h->g_warps, L.s_poa[0], c.jobs_m, 1, jobs_q4, 4);
     CG_POA2_LAUNCH(CgPoa2C1, (u8*)nullptr, h->c1_warps, st, c.jobs_s, 0, jobs_q3, 3);
-    for (int i = 0; i < 2; ++i) { CKL(cudaEventRecord(L.ev_join[i], L.s_poa[i])); CKL(cudaStreamWaitEvent(st, L.ev_join[i], 0)); }
+    for (int i = 0; i < 2; ++i) CKL(cudaEventRecord(L.ev_join[i], L.s_poa[i]));
+    CKL(cudaStreamWaitEvent(st, L.ev_join[0], 0));
+    CKL(cudaEventRecord(h->ev_bulk[ci], st));              // C1 and G are through: the next chunk's bulk may start (W1's few long jobs go on)
+    {
+        std::lock_guard<std::mutex> lk(h->commit_mu);
+        h->bulk_enqueued = ci + 1;
+    }
+    h->commit_cv.notify_all();
+    st = L.s_tail;                                          // from here on: the chunk's tail
+    CKL(cudaStreamWaitEvent(st, h->ev_bulk[ci], 0));
     CG_POA2_LAUNCH(CgPoa2GT, L.g_mem.as<u8>(), h->g_warps, st, jobs_q3, 3, jobs_q4, 4);
+    CKL(cudaStreamWaitEvent(st, L.ev_join[1], 0));
     CG_POA2_LAUNCH(CgPoa2W1, L.w1_mem.as<u8>(), h->w1_warps, st, jobs_q4, 4, jobs_q5, 5);
     CG_POA2_LAUNCH(CgPoa2W2, L.w2_mem.as<u8>(), h->w2_warps, st, jobs_q5, 5, jobs_q6, 6);
 #undef CG_POA2_LAUNCH
@@ -433,7 +458,9 @@ int run_chunk(cg_handle* h, Lane& L, size_t ci) {
               h->o_status.as<u8>() + cp.w0, h->o_cons_n, h->o_solid_n, h->o_len.as<u64>() + cp.w0, h->o_nsol.as<u64>() + cp.w0);
     L.stage_launches[CG_STAGE_STITCH] += 1;
     span_end();
-    if (h->stream_out) { int rc = stream_out_chunk(h, L, cp, tot[0], tot[1]); if (rc) return rc; }
+    if (h->stream_out) { int rc = stream_out_chunk(h, L, st, cp, tot[0], tot[1]); if (rc) return rc; }
+    CKL(cudaEventRecord(L.ev_tail, st));
+    L.tail_recorded = true;
     h->o_cons_n += tot[0];
     h->o_solid_n += tot[1];
     h->next_commit = ci + 1;
@@ -500,7 +527,7 @@ int host_results_reserve(cg_handle* h, HostResults* r, u64 need_c, u64 need_s, u
 }
 
 // Download the dense results of one chunk on the D2H stream while the next chunk computes.
-int stream_out_chunk(cg_handle* h, Lane& L, const ChunkPlan& cp, u64 cons_n, u64 solid_n) {
+int stream_out_chunk(cg_handle* h, Lane& L, cudaStream_t st, const ChunkPlan& cp, u64 cons_n, u64 solid_n) {
     HostResults* r = h->stream_out;
     const double frac = (double)(cp.w0 + cp.nwin) / (double)h->W;
     const u64 need_c = h->o_cons_n + cons_n + 1, need_s = h->o_solid_n + solid_n + 1;
@@ -509,7 +536,7 @@ int stream_out_chunk(cg_handle* h, Lane& L, const ChunkPlan& cp, u64 cons_n, u64
         int rc = host_results_reserve(h, r, std::max(need_c, est_c), std::max(need_s, est_s), h->o_cons_n, h->o_solid_n);
         if (rc) return rc;
     }
-    CK(cudaEventRecord(L.ev_gather, L.stream));
+    CK(cudaEventRecord(L.ev_gather, st));
     CK(cudaStreamWaitEvent(h->s_d2h, L.ev_gather, 0));
     cudaStream_t sd = h->s_d2h;
     if (cons_n) CK(cudaMemcpyAsync(r->cons + h->o_cons_n, h->o_cons.as<u8>() + h->o_cons_n, cons_n, cudaMemcpyDeviceToHost, sd));
@@ -559,8 +586,12 @@ int cg_create(int device, const cg_params* params, cg_handle** out) {
     bool ok = cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaEventCreate(&h->ev_run0) == cudaSuccess;
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     for (Lane& L : h->lane) {
-        ok = ok && cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking) == cudaSuccess;
+        ok = ok && cudaStreamCreateWithPriority(&L.stream, cudaStreamNonBlocking, prio_lo) == cudaSuccess;
+        ok = ok && cudaStreamCreateWithPriority(&L.s_tail, cudaStreamNonBlocking, prio_hi) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&L.ev_tail, cudaEventDisableTiming) == cudaSuccess;
         for (int i = 0; i < 3; ++i)
             ok = ok && cudaStreamCreateWithFlags(&L.s_poa[i], cudaStreamNonBlocking) == cudaSuccess &&
                  cudaEventCreateWithFlags(&L.ev_join[i], cudaEventDisableTiming) == cudaSuccess;
@@ -600,6 +631,7 @@ void cg_destroy(cg_handle* h) {
         h->pool.clear();
     }
     for (cudaEvent_t e : h->ev_h2d) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->ev_bulk) cudaEventDestroy(e);
     if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
     if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
     if (h->ev_run0) cudaEventDestroy(h->ev_run0);
@@ -609,8 +641,8 @@ void cg_destroy(cg_handle* h) {
                         &L.ctl, &L.off_fin, &L.out_off, &L.g_mem, &L.w1_mem, &L.w2_mem};
         for (DevBuf* b : lb) b->release();
         for (cudaEvent_t e : L.evpool) cudaEventDestroy(e);
-        for (cudaEvent_t e : {L.ev_fork, L.ev_gather, L.ev_end, L.ev_join[0], L.ev_join[1], L.ev_join[2]}) if (e) cudaEventDestroy(e);
-        for (cudaStream_t st : {L.stream, L.s_poa[0], L.s_poa[1], L.s_poa[2]}) if (st) cudaStreamDestroy(st);
+        for (cudaEvent_t e : {L.ev_fork, L.ev_gather, L.ev_end, L.ev_tail, L.ev_join[0], L.ev_join[1], L.ev_join[2]}) if (e) cudaEventDestroy(e);
+        for (cudaStream_t st : {L.stream, L.s_tail, L.s_poa[0], L.s_poa[1], L.s_poa[2]}) if (st) cudaStreamDestroy(st);
         if (L.h_ctl) cudaFreeHost(L.h_ctl);
     }
     DevBuf* bufs[] = {&h->d_bases, &h->d_seq_off, &h->d_wsb, &h->o_cons, &h->o_sk, &h->o_sc, &h->o_status, &h->o_len, &h->o_nsol};
@@ -727,7 +759,9 @@ void lane_main(cg_handle* h, int li, int n_lanes) {
             break;
         }
     }
-    cudaEventRecord(L.ev_end, L.stream);
+    cudaStreamWaitEvent(L.s_tail, h->ev_run0, 0);
+    if (L.tail_recorded) cudaStreamWaitEvent(L.s_tail, L.ev_tail, 0);
+    cudaEventRecord(L.ev_end, L.s_tail);
 }
 
 int run_impl(cg_handle* h) {
@@ -735,7 +769,13 @@ int run_impl(cg_handle* h) {
     h->ran = false;
     h->o_cons_n = h->o_solid_n = 0;
     h->next_commit = 0;
+    h->bulk_enqueued = 0;
     h->abort_run = false;
+    while (h->ev_bulk.size() < h->chunks.size()) {
+        cudaEvent_t e;
+        CK(cudaEventCreate(&e));
+        h->ev_bulk.push_back(e);
+    }
     memset(h->stage_ms, 0, sizeof h->stage_ms);
     memset(h->stage_launches, 0, sizeof h->stage_launches);
     CK(h->o_status.ensure(h->W + 16)); CK(h->o_len.ensure((h->W + 1) * sizeof(u64))); CK(h->o_nsol.ensure((h->W + 1) * sizeof(u64)));
@@ -743,7 +783,7 @@ int run_impl(cg_handle* h) {
     CK(cudaEventRecord(h->ev_run0, h->lane[0].stream));
     for (int li = 0; li < n_lanes; ++li) {
         Lane& L = h->lane[li];
-        L.spans.clear(); L.pool_at = 0; L.err.clear(); L.rc = CG_OK;
+        L.spans.clear(); L.pool_at = 0; L.err.clear(); L.rc = CG_OK; L.tail_recorded = false;
         memset(L.stage_ms, 0, sizeof L.stage_ms); memset(L.stage_launches, 0, sizeof L.stage_launches);
         CK(cudaMemsetAsync(L.ctl.p, 0, CTL_WORDS * sizeof(u32) + sizeof(CgCountersDev), L.stream));
         if (li) CK(cudaStreamWaitEvent(L.stream, h->ev_run0, 0));      // nothing of this run starts before its first event
@@ -759,10 +799,25 @@ int run_impl(cg_handle* h) {
     int rc = CG_OK;
     for (int li = 0; li < n_lanes; ++li) {
         cudaStreamSynchronize(h->lane[li].stream);
+        cudaStreamSynchronize(h->lane[li].s_tail);
         for (int i = 0; i < 3; ++i) cudaStreamSynchronize(h->lane[li].s_poa[i]);
         if (rc == CG_OK && h->lane[li].rc != CG_OK) { rc = h->lane[li].rc; h->err = h->lane[li].err; }
     }
     if (rc != CG_OK) { cudaStreamSynchronize(h->s_h2d); cudaStreamSynchronize(h->s_d2h); return rc; }
+    if (getenv("CG_TIMELINE")) {
+        static const char* names[CG_N_STAGES] = {"pack", "index", "chain", "split", "poa", "stitch", "polish"};
+        for (int li = 0; li < n_lanes; ++li)
+            for (const StageSpan& sp : h->lane[li].spans) {
+                float t0 = 0, t1 = 0;
+                cudaEventElapsedTime(&t0, h->ev_run0, sp.a); cudaEventElapsedTime(&t1, h->ev_run0, sp.b);
+                fprintf(stderr, "[timeline] lane %d %-6s %9.3f -> %9.3f  (%.3f ms)\n", li, names[sp.stage], t0, t1, t1 - t0);
+            }
+        for (size_t ci = 0; ci < h->chunks.size(); ++ci) {
+            float t = 0;
+            cudaEventElapsedTime(&t, h->ev_run0, h->ev_bulk[ci]);
+            fprintf(stderr, "[timeline] chunk %zu bulk done at %9.3f\n", ci, t);
+        }
+    }
     h->run_ms = 0;
     CgCountersDev sum{};
     for (int li = 0; li < n_lanes; ++li) {

@@ -12,7 +12,7 @@
 //    So this kernel maintains *a* valid topological order incrementally, in parallel (new nodes of an alignment are
 //    spliced in front of the column of the next node they lead to; columns stay contiguous), and runs the reference's
 //    DFS only when two rows tie for the maximum (~8 % of the alignments) and once before the vote.
-//  * Packed node records: in-edges are 8 inline ids per node (in-degree > 8 leaves these tiers); the aligned set
+//  * Packed node records: in-edges are 8 (byte ids) or 16 (16-bit ids) inline ids per node (more leaves these tiers); the aligned set
 //    (<= 3 others, one node per base in a column) shares a word with the in-degree.  Per row of the matrix there is
 //    a descriptor (letter, in-degree, first predecessor row, node) and the 8 predecessor ROW indices, rebuilt by all
 //    lanes after each change, so neither the DP nor the traceback chase pointers.
@@ -29,13 +29,13 @@
 //   W1 : 16-bit ids (<= 1024 nodes, 1024-base segments), everything in global memory (L2)         8 warps / SM
 //   W2 : 16-bit ids (<= 4096 nodes, 2048-base segments, 4 M cells), global memory                 2 warps / SM
 // A job that outgrows its tier (nodes, cells, in-degree, segment length) is re-queued for the next one before anything
-// is committed; in-degree > 8 and anything bigger end in k_poa (k_poa.cuh), which has no such limits.
+// is committed; in-degree > 16 and anything bigger end in k_poa (k_poa.cuh), which has no such limits.
 #pragma once
 #include "cg_common.cuh"
 #include "k_poa.cuh"
 
 // ------------------------------------------------------------------ id packing
-struct __align__(16) CgVec16 { u64 lo, hi; };
+struct __align__(16) CgVec16 { u64 w[4]; };             // 16 ids of 16 bits
 
 template <class IdT> struct CgIdPack;
 template <> struct CgIdPack<u8> {
@@ -44,7 +44,7 @@ template <> struct CgIdPack<u8> {
     typedef u32 Rdesc;      // letter | in-degree << 8 | first predecessor row << 16 | node << 24
     typedef u16 Item;       // DFS stack entry (id | finish flag), alignment pair (node | qpos << 8), splice item (pos | node << 8)
     typedef u32 Seg;        // read | start << 12 | len << 25
-    static constexpr u32 W = 8, NONE = 0xffu;
+    static constexpr u32 W = 8, NONE = 0xffu, PMAX = 8;      // PMAX: in-edges a node can hold in these tiers
     __device__ __forceinline__ static u32 get(Vec v, u32 e) { return (u32)(v >> (8u * e)) & 0xffu; }
     __device__ __forceinline__ static Vec set(Vec v, u32 e, u32 x) { return (v & ~(0xffull << (8u * e))) | ((u64)x << (8u * e)); }
     __device__ __forceinline__ static Vec none() { return ~0ull; }
@@ -61,16 +61,20 @@ template <> struct CgIdPack<u16> {
     typedef u64 Rdesc;      // letter | in-degree << 8 | first predecessor row << 16 | node << 32
     typedef u32 Item;
     typedef u64 Seg;        // read | start << 16 | len << 32
-    static constexpr u32 W = 16, NONE = 0xffffu;
-    __device__ __forceinline__ static u32 get(const Vec& v, u32 e) { return (u32)((e < 4 ? v.lo : v.hi) >> (16u * (e & 3u))) & 0xffffu; }
+    static constexpr u32 W = 16, NONE = 0xffffu, PMAX = 16;
+    __device__ __forceinline__ static u32 get(const Vec& v, u32 e) {
+        const u64 w = (e >> 2) == 0 ? v.w[0] : (e >> 2) == 1 ? v.w[1] : (e >> 2) == 2 ? v.w[2] : v.w[3];
+        return (u32)(w >> (16u * (e & 3u))) & 0xffffu;
+    }
     __device__ __forceinline__ static Vec set(Vec v, u32 e, u32 x) {
         const u64 m = ~(0xffffull << (16u * (e & 3u))), b = (u64)x << (16u * (e & 3u));
-        if (e < 4) v.lo = (v.lo & m) | b; else v.hi = (v.hi & m) | b;
+#pragma unroll
+        for (u32 i = 0; i < 4; ++i) if ((e >> 2) == i) v.w[i] = (v.w[i] & m) | b;
         return v;
     }
-    __device__ __forceinline__ static Vec none() { Vec v; v.lo = ~0ull; v.hi = ~0ull; return v; }
-    __device__ __forceinline__ static Vec zero() { Vec v; v.lo = 0; v.hi = 0; return v; }
-    __device__ __forceinline__ static u32 first(const Vec& v) { return (u32)v.lo & 0xffffu; }
+    __device__ __forceinline__ static Vec none() { Vec v; v.w[0] = v.w[1] = v.w[2] = v.w[3] = ~0ull; return v; }
+    __device__ __forceinline__ static Vec zero() { Vec v; v.w[0] = v.w[1] = v.w[2] = v.w[3] = 0; return v; }
+    __device__ __forceinline__ static u32 first(const Vec& v) { return (u32)v.w[0] & 0xffffu; }
     __device__ __forceinline__ static Seg seg_pack(u32 read, u32 start, u32 len) { return (u64)read | ((u64)start << 16) | ((u64)len << 32); }
     __device__ __forceinline__ static u32 seg_read(Seg s) { return (u32)s & 0xffffu; }
     __device__ __forceinline__ static u32 seg_start(Seg s) { return (u32)(s >> 16) & 0xffffu; }
@@ -112,7 +116,7 @@ template <class T> struct CgPoa2Lay {
     static constexpr size_t cta_bytes = T::SMEM ? per_warp * T::WARPS : 0;
 };
 
-// meta word of a node: low field = nal (bits 0-1) | "sequence 0 passes here" (bit 2) | in-degree (bits 4-7); then 3 aligned ids
+// meta word of a node: low field = nal (bits 0-1) | "sequence 0 passes here" (bit 2) | in-degree (bits 3-7); then 3 aligned ids
 template <class T> struct CgPoa2G {
     typedef CgPoa2Lay<T> Lay;
     typedef CgIdPack<typename T::IdT> Pk;
@@ -171,7 +175,7 @@ template <class T> __device__ __forceinline__ bool cg_poa2_dfs(const CgPoa2G<T>&
             if (!finish) {
                 if (s.marks(id) == 2) { --sp; continue; }
                 const u32 sp0 = sp;
-                const u32 deg = ((u32)m >> 4) & 15u;
+                const u32 deg = ((u32)m >> 3) & 31u;
                 const VecT P = s.pred(id);
                 if (sp + deg + 3 > T::SCAP) return false;
                 for (u32 e = 0; e < deg; ++e) {
@@ -208,33 +212,37 @@ template <class T> __device__ __forceinline__ u32 cg_poa2_traceback(const CgPoa2
     const i16* H = s.H();
     u32 i = bi, j = bj, n = 0;
     i32 Hij = H[(size_t)i * Wd + j];
-    while (Hij != 0) {
+    while (Hij != 0) {                                   // column 0 is all zeros, so j >= 1 in here
         const typename Pk::Rdesc d = s.rdesc(i - 1);
-        const VecT pr = s.prow(i - 1);
-        const u32 deg = ((u32)d >> 8) & 0xffu, np = deg ? deg : 1u;
-        u32 pi_ = 0, pj_ = 0;
-        i32 Hp = 0;
-        bool found = false;
-        if (j != 0) {
-            const i32 sc = ((u32)d & 0xffu) == seq[j - 1] ? 5 : -10;
-            for (u32 e = 0; e < np && !found; ++e) {
-                const u32 p = deg ? Pk::get(pr, e) : 0u;
-                Hp = H[(size_t)p * Wd + (j - 1)];
-                if (Hij == Hp + sc) { pi_ = p; pj_ = j - 1; found = true; }
+        const u32 deg = ((u32)d >> 8) & 0xffu;
+        const i32 sc = ((u32)d & 0xffu) == seq[j - 1] ? 5 : -10;
+        const i16* hl = H + (size_t)i * Wd + (j - 1);
+        u32 pi_ = i, pj_ = j - 1;
+        i32 Hp;
+        if (deg <= 1) {                                  // one predecessor row (row 0 if the node has no in-edge)
+            const u32 p = ((u32)d >> 16) & IDNONE;
+            const i16* hp = H + (size_t)p * Wd + (j - 1);
+            const i32 hd = hp[0], hv = hp[1], hh = hl[0];
+            if (Hij == hd + sc) { pi_ = p; Hp = hd; }
+            else if (Hij == hv - 4) { pi_ = p; pj_ = j; Hp = hv; }
+            else { Hp = hh; if (Hij != hh - 4) { *bad = true; return 0; } }
+        } else {
+            const VecT pr = s.prow(i - 1);
+            u32 pd = IDNONE, pv = IDNONE;
+            i32 hd_ = 0, hv_ = 0;
+#pragma unroll 1
+            for (u32 e = 0; e < deg && pd == IDNONE; ++e) {
+                const u32 p = Pk::get(pr, e);
+                const i16* hp = H + (size_t)p * Wd + (j - 1);
+                const i32 hd = hp[0], hv = hp[1];
+                if (Hij == hd + sc) { pd = p; hd_ = hd; }
+                if (pv == IDNONE && Hij == hv - 4) { pv = p; hv_ = hv; }
             }
+            if (pd != IDNONE) { pi_ = pd; Hp = hd_; }
+            else if (pv != IDNONE) { pi_ = pv; pj_ = j; Hp = hv_; }
+            else { Hp = hl[0]; if (Hij != Hp - 4) { *bad = true; return 0; } }
         }
-        if (!found) {
-            for (u32 e = 0; e < np && !found; ++e) {
-                const u32 p = deg ? Pk::get(pr, e) : 0u;
-                Hp = H[(size_t)p * Wd + j];
-                if (Hij == Hp - 4) { pi_ = p; pj_ = j; found = true; }
-            }
-        }
-        if (!found && j != 0) {
-            Hp = H[(size_t)i * Wd + j - 1];
-            if (Hij == Hp - 4) { pi_ = i; pj_ = j - 1; found = true; }
-        }
-        if (!found || n >= T::ALNCAP) { *bad = true; return 0; }      // inconsistent matrix: cannot happen
+        if (n >= T::ALNCAP) { *bad = true; return 0; }  // cannot happen: a path visits a cell once
         const u32 node = (u32)(d >> (16 + W)) & IDNONE;
         s.work(n) = (ItemT)((i == pi_ ? IDNONE : node) | ((j == pj_ ? IDNONE : (j - 1)) << W));
         ++n;
@@ -247,32 +255,39 @@ template <class T> __device__ __forceinline__ u32 cg_poa2_traceback(const CgPoa2
 // ------------------------------------------------------------------ score matrix (all lanes), CH chunks of 32 columns
 // The common row (one predecessor = the row just computed) needs no loads: the left neighbour comes from the adjacent lane.
 // The in-row gap term H[i][j] = max(v[j], H[i][j-1] - 4) is the max-plus prefix scan H[i][j] = max_{t<=j}(v[t] + 4t) - 4j.
-// tie: some other row reached this lane's maximum again (the caller then needs the exact row order).
+// Lanes past the end of the query compute harmless values (a scan only moves data towards higher lanes) and store nothing,
+// so the loop carries no activity masks; shfl_up hands a lane its own value back when the source is out of range, so the
+// scan needs no lane tests either.  The loop keeps one running maximum per lane; the winning cell is found afterwards
+// (cg_poa2_find_max), which costs cells/32 loads instead of a dozen instructions per row.
+// Column 0 of every row is zeroed beforehand.  Returns the lane's maximum over its columns.
 template <int CH, class T>
-__device__ __forceinline__ void cg_poa2_dp(const CgPoa2G<T>& s, u32 V, const u8* seq, u32 L, i32& bv, u32& bi, u32& bj, bool& tie) {
+__device__ __forceinline__ i32 cg_poa2_dp(const CgPoa2G<T>& s, u32 V, const u8* seq, u32 L) {
     CG_P2_TYPES;
     const u32 lane = cg_lane(), Wd = L + 1;
     i16* H = s.H();
     u8 q[CH];
+    i32 prev[CH], j4[CH];
     bool act[CH];
-    i32 prev[CH];
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
         const u32 j = 1 + 32 * c + lane;
         act[c] = j < Wd;
         q[c] = act[c] ? seq[j - 1] : (u8)0;
         prev[c] = 0;
+        j4[c] = 4 * (i32)j;
     }
     for (u32 j = lane; j < Wd; j += 32) H[j] = 0;
-    u32 desc_l = 0;
+    for (u32 r = lane; r < V; r += 32) H[(size_t)(r + 1) * Wd] = 0;
     __syncwarp();
+    i32 bv = 0;
+    u32 dnext = (u32)s.rdesc(0);
+    i16* row = H + Wd + 1 + lane;                        // cell (r + 1, 1 + lane)
     for (u32 r = 0; r < V; ++r) {
-        if ((r & 31u) == 0) desc_l = r + lane < V ? (u32)s.rdesc(r + lane) : 0u;
-        const u32 d = __shfl_sync(CG_FULL, desc_l, (int)(r & 31u));
+        const u32 d = dnext;
+        if (r + 1 < V) dnext = (u32)s.rdesc(r + 1);      // one row ahead: off the dependent chain
         const u8 ch = (u8)(d & 0xffu);
         const u32 deg = (d >> 8) & 0xffu;
         const u32 p0 = (d >> 16) & IDNONE;
-        i16* row = H + (size_t)(r + 1) * Wd;
         i32 val[CH];
         if (deg <= 1 && p0 == r) {                       // predecessor = the row just computed (or the zero row for r = 0)
 #pragma unroll
@@ -285,48 +300,44 @@ __device__ __forceinline__ void cg_poa2_dp(const CgPoa2G<T>& s, u32 V, const u8*
                 val[c] = a > b ? a : b;
             }
         } else if (deg <= 1) {                           // one predecessor elsewhere, or none (virtual row 0)
-            const i16* prow = H + (size_t)p0 * Wd;
+            const i16* prow = H + (size_t)p0 * Wd + lane;
 #pragma unroll
             for (int c = 0; c < CH; ++c) {
-                val[c] = CG_POA_NEG;
+                val[c] = 0;
                 if (act[c]) {
-                    const u32 j = 1 + 32 * c + lane;
                     const i32 sc = q[c] == ch ? 5 : -10;
-                    const i32 a = (i32)prow[j - 1] + sc, b = (i32)prow[j] - 4;
+                    const i32 a = (i32)prow[32 * c] + sc, b = (i32)prow[32 * c + 1] - 4;
                     val[c] = a > b ? a : b;
                 }
             }
         } else {
 #pragma unroll
-            for (int c = 0; c < CH; ++c) val[c] = CG_POA_NEG;
+            for (int c = 0; c < CH; ++c) val[c] = 0;
             const VecT pr = s.prow(r);
+#pragma unroll 1
             for (u32 e = 0; e < deg; ++e) {
-                const i16* prow = H + (size_t)Pk::get(pr, e) * Wd;
+                const i16* prow = H + (size_t)Pk::get(pr, e) * Wd + lane;
 #pragma unroll
                 for (int c = 0; c < CH; ++c) {
                     if (act[c]) {
-                        const u32 j = 1 + 32 * c + lane;
                         const i32 sc = q[c] == ch ? 5 : -10;
-                        const i32 a = (i32)prow[j - 1] + sc, b = (i32)prow[j] - 4;
+                        const i32 a = (i32)prow[32 * c] + sc, b = (i32)prow[32 * c + 1] - 4;
                         const i32 m = a > b ? a : b;
                         val[c] = m > val[c] ? m : val[c];
                     }
                 }
             }
         }
-        // clamp, then the in-row gap term as a max-plus prefix scan over u = H + 4j
+        // clamp at 0 (a zero start for val above is the same clamp), then the in-row gap term as a max-plus prefix scan
         i32 u[CH];
 #pragma unroll
-        for (int c = 0; c < CH; ++c) {
-            const i32 v0 = val[c] > 0 ? val[c] : 0;
-            u[c] = act[c] ? v0 + 4 * (i32)(1 + 32 * c + lane) : CG_POA_NEG;
-        }
+        for (int c = 0; c < CH; ++c) u[c] = (val[c] > 0 ? val[c] : 0) + j4[c];
 #pragma unroll
         for (int dd = 1; dd < 32; dd <<= 1) {
 #pragma unroll
             for (int c = 0; c < CH; ++c) {
-                const i32 o = __shfl_up_sync(CG_FULL, u[c], dd);
-                if (lane >= (u32)dd) u[c] = o > u[c] ? o : u[c];
+                const i32 o = __shfl_up_sync(CG_FULL, u[c], dd);       // lanes < dd get their own value back
+                u[c] = o > u[c] ? o : u[c];
             }
         }
         i32 carry = 0;
@@ -334,27 +345,28 @@ __device__ __forceinline__ void cg_poa2_dp(const CgPoa2G<T>& s, u32 V, const u8*
         for (int c = 0; c < CH; ++c) {
             u[c] = u[c] > carry ? u[c] : carry;
             if (c + 1 < CH) carry = __shfl_sync(CG_FULL, u[c], 31);
-            const i32 h = u[c] - 4 * (i32)(1 + 32 * c + lane);
+            const i32 h = u[c] - j4[c];
             prev[c] = h;
             if (act[c]) {
-                row[1 + 32 * c + lane] = (i16)h;
-                if (h > bv) { bv = h; bi = r + 1; bj = 1 + 32 * c + lane; tie = false; }
-                else if (h == bv && h > 0 && bi != r + 1) tie = true;
+                row[32 * c] = (i16)h;
+                bv = h > bv ? h : bv;
             }
         }
-        if (lane == 0) row[0] = 0;
+        row += Wd;
         __syncwarp();
     }
+    return bv;
 }
 
 // Any length: chunks of 32 columns, every row read back from the stored matrix.
 template <class T>
-__device__ __forceinline__ void cg_poa2_dp_any(const CgPoa2G<T>& s, u32 V, const u8* seq, u32 L, i32& bv, u32& bi, u32& bj, bool& tie) {
+__device__ __forceinline__ i32 cg_poa2_dp_any(const CgPoa2G<T>& s, u32 V, const u8* seq, u32 L) {
     CG_P2_TYPES;
     const u32 lane = cg_lane(), Wd = L + 1;
     i16* H = s.H();
     for (u32 j = lane; j < Wd; j += 32) H[j] = 0;
     __syncwarp();
+    i32 bv = 0;
     for (u32 r = 0; r < V; ++r) {
         const u32 d = (u32)s.rdesc(r);
         const u8 ch = (u8)(d & 0xffu);
@@ -366,7 +378,7 @@ __device__ __forceinline__ void cg_poa2_dp_any(const CgPoa2G<T>& s, u32 V, const
         for (u32 jb = 1; jb < Wd; jb += 32) {
             const u32 j = jb + lane;
             const bool act = j < Wd;
-            i32 val = CG_POA_NEG;
+            i32 val = 0;
             if (act) {
                 const i32 sc = seq[j - 1] == ch ? 5 : -10;
                 for (u32 e = 0; e < np; ++e) {
@@ -375,25 +387,51 @@ __device__ __forceinline__ void cg_poa2_dp_any(const CgPoa2G<T>& s, u32 V, const
                     const i32 m = a > b ? a : b;
                     val = m > val ? m : val;
                 }
-                val = val > 0 ? val : 0;
             }
-            i32 u = act ? val + 4 * (i32)j : CG_POA_NEG;
+            i32 u = val + 4 * (i32)j;
 #pragma unroll
             for (int dd = 1; dd < 32; dd <<= 1) {
                 const i32 o = __shfl_up_sync(CG_FULL, u, dd);
-                if (lane >= (u32)dd) u = o > u ? o : u;
+                u = o > u ? o : u;
             }
             u = u > carry ? u : carry;
             carry = __shfl_sync(CG_FULL, u, 31);
             if (act) {
                 const i32 h = u - 4 * (i32)j;
                 row[j] = (i16)h;
-                if (h > bv) { bv = h; bi = r + 1; bj = j; tie = false; }
-                else if (h == bv && h > 0 && bi != r + 1) tie = true;
+                bv = h > bv ? h : bv;
             }
         }
         __syncwarp();
     }
+    return bv;
+}
+
+// Where is the maximum M (> 0)?  Lanes over rows, each scanning its row.  Returns the number of rows that hold M; if it is
+// exactly one, (*bi, *bj) is the first cell of that row equal to M (simd_alignment_engine_impl.hpp:860-862).
+template <class T>
+__device__ __forceinline__ u32 cg_poa2_find_max(const CgPoa2G<T>& s, u32 V, u32 Wd, i32 M, u32* bi, u32* bj) {
+    const u32 lane = cg_lane();
+    const i16* H = s.H();
+    u32 nrows = 0, frow = 0, fcol = 0;
+    for (u32 rb = 0; rb < V; rb += 32) {
+        const u32 r = rb + lane;
+        u32 col = 0;
+        if (r < V) {
+            const i16* hr = H + (size_t)(r + 1) * Wd;
+#pragma unroll 4
+            for (u32 j = Wd - 1; j >= 1; --j) col = (i32)hr[j] == M ? j : col;
+        }
+        const u32 bal = __ballot_sync(CG_FULL, col != 0);
+        if (bal && nrows == 0) {
+            const int src = __ffs((int)bal) - 1;
+            frow = rb + (u32)src + 1;
+            fcol = __shfl_sync(CG_FULL, col, src);
+        }
+        nrows += __popc(bal);
+    }
+    *bi = frow; *bj = fcol;
+    return nrows;
 }
 
 // ------------------------------------------------------------------ one job
@@ -446,21 +484,17 @@ __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s
         u32 n_aln = 0;
         if (V != 0) {
             if ((u64)(V + 1) * Wd > (u64)T::HCELLS) return CG_NONE32;
-            i32 bv = 0; u32 bi = 0, bj = 0;
-            bool tie = false;
-            if (L <= 32) cg_poa2_dp<1>(s, V, seq, L, bv, bi, bj, tie);
-            else if (L <= 64) cg_poa2_dp<2>(s, V, seq, L, bv, bi, bj, tie);
-            else if (L <= 128) cg_poa2_dp<4>(s, V, seq, L, bv, bi, bj, tie);
-            else if (T::LCAP > 128 && L <= 256) cg_poa2_dp<(T::LCAP > 128 ? 8 : 1)>(s, V, seq, L, bv, bi, bj, tie);
-            else if (T::LCAP > 256) cg_poa2_dp_any(s, V, seq, L, bv, bi, bj, tie);
+            i32 bv;
+            if (L <= 32) bv = cg_poa2_dp<1>(s, V, seq, L);
+            else if (L <= 64) bv = cg_poa2_dp<2>(s, V, seq, L);
+            else if (T::LCAP > 64 && L <= 128) bv = cg_poa2_dp<(T::LCAP > 64 ? 4 : 1)>(s, V, seq, L);
+            else if (T::LCAP > 128 && L <= 256) bv = cg_poa2_dp<(T::LCAP > 128 ? 8 : 1)>(s, V, seq, L);
+            else if (T::LCAP > 256) bv = cg_poa2_dp_any(s, V, seq, L);
+            else bv = 0;
             j_aln += 1; j_cells += (u64)(V + 1) * L; j_pred += (u64)sumdeg * L;
-            const u64 key = ((u64)(u32)bv << 32) | ((u64)(0xffffu - bi) << 16) | (u64)(0xffffu - bj);
-            const u64 kb = cg_warp_max64(key);
-            const i32 M = (i32)(kb >> 32);
-            const u32 gbi = 0xffffu - (u32)((kb >> 16) & 0xffffu), gbj = 0xffffu - (u32)(kb & 0xffffu);
-            const bool mytie = M > 0 && bv == M && (tie || bi != gbi);
-            bi = gbi; bj = gbj;
-            if (__any_sync(CG_FULL, mytie)) {
+            const i32 M = (i32)cg_warp_max((u32)bv);
+            u32 bi = 0, bj = 0;
+            if (M > 0 && cg_poa2_find_max(s, V, Wd, M, &bi, &bj) > 1) {
                 // several rows reach the maximum: the winner is the first of them in spoa's own order (simd...impl.hpp:828-833)
                 if (!dfs_valid) {
                     for (u32 i = lane; i < V; i += 32) { s.marks(i) = 0; s.check(i) = 1; }
@@ -539,6 +573,7 @@ __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s
                         m_an = s.meta(an);
                         kind = 2;                                                     // new node in an's column ...
                         const u32 nal = (u32)m_an & 3u;
+#pragma unroll 1
                         for (u32 a = 0; a < nal; ++a) {
                             const u32 aid = (u32)((m_an >> (W * (a + 1))) & IDMASK);
                             if (s.letter(aid) == ch) { kind = 0; nn = aid; }          // ... unless the column already has the letter
@@ -559,6 +594,7 @@ __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s
                     const u32 sh = W * (nal + 1);
                     s.letter(nn) = ch; s.nseq(nn) = 0; s.pred(nn) = Pk::none();
                     s.meta(nn) = (MetaT)(nal + 1) | (m_an & ~IDMASK & (((MetaT)1 << sh) - 1)) | ((MetaT)an << sh);
+#pragma unroll 1
                     for (u32 a = 0; a < nal; ++a) {
                         const u32 aid = (u32)((m_an >> (W * (a + 1))) & IDMASK);
                         const MetaT ma = s.meta(aid);
@@ -599,15 +635,16 @@ __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s
                 if (nseqs == 0) m |= 4u;
                 if (q > 0) {
                     const u32 src = s.nodeq(q - 1);
-                    const u32 deg = ((u32)m >> 4) & 15u;
+                    const u32 deg = ((u32)m >> 3) & 31u;
                     const VecT P = s.pred(node);
                     bool have = false;
+#pragma unroll 1
                     for (u32 e = 0; e < deg; ++e) have = have || Pk::get(P, e) == src;
                     if (!have) {
-                        if (deg >= 8) ovf = true;
+                        if (deg >= Pk::PMAX) ovf = true;
                         else {
                             s.pred(node) = Pk::set(P, deg, src);
-                            m += 16u;
+                            m += 8u;
                             changed = true;
                         }
                     }
@@ -636,6 +673,7 @@ __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s
                     const u32 nal = (u32)m & 3u;
                     const u32 r0 = s.rank_of(an);
                     cs = r0; ce = r0 + 1;
+#pragma unroll 1
                     for (u32 a = 0; a < nal; ++a) {
                         const u32 aid = (u32)((m >> (W * (a + 1))) & IDMASK);
                         if (aid < V0) { const u32 ra = s.rank_of(aid); cs = ra < cs ? ra : cs; ce = ra + 1 > ce ? ra + 1 : ce; }
@@ -675,6 +713,7 @@ __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s
             const u32 p = pb + lane;
             if (p < V0) {
                 u32 lo = 0, hi = K;                                   // first k with pos_k > p
+#pragma unroll 1
                 while (lo < hi) { const u32 mid = (lo + hi) >> 1; if (((u32)s.work(mid) & IDNONE) <= p) lo = mid + 1; else hi = mid; }
                 const u32 node = s.r2n(cur, p);
                 s.r2n(nxt, p + lo) = (IdT)node;
@@ -698,12 +737,11 @@ __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s
             const u32 r = rb + lane;
             if (r < V) {
                 const u32 node = s.r2n(cur, r);
-                const u32 deg = ((u32)s.meta(node) >> 4) & 15u;
+                const u32 deg = ((u32)s.meta(node) >> 3) & 31u;
                 const VecT P = s.pred(node);
                 VecT rows = Pk::zero();
-#pragma unroll
-                for (u32 e = 0; e < 8; ++e)
-                    if (e < deg) rows = Pk::set(rows, e, (u32)s.rank_of(Pk::get(P, e)) + 1u);
+#pragma unroll 1
+                for (u32 e = 0; e < deg; ++e) rows = Pk::set(rows, e, (u32)s.rank_of(Pk::get(P, e)) + 1u);
                 s.prow(r) = rows;
                 s.rdesc(r) = (typename Pk::Rdesc)((u32)s.letter(node) | (deg << 8) | (Pk::first(rows) << 16)) | ((typename Pk::Rdesc)node << (16 + W));
                 sd += deg ? deg : 1u;
