@@ -121,7 +121,7 @@ struct cg_handle {
     int sms = 148;
     int smem_optin = 0;
     // options
-    size_t chunk_budget = (size_t)6 << 30;
+    size_t chunk_budget = (size_t)8 << 30;
     u32 chunk_max_windows = 16384;
     // batch (device) + host copies of the offsets for planning
     u32 W = 0;
@@ -213,7 +213,7 @@ int ensure_tier(Lane& L, PoaTier& T) {
     if (T.ready) return CG_OK;
     const u32 ncap = CG_N_MAX + 1;
     const u32 scap = T.vcap ? 2 * (T.ecap + 4 * T.vcap) : 0;
-    const u32 alncap = T.hcap ? (T.vcap ? T.vcap : CgPoaTierM::VCAP) + T.lcap + 2 : 0;
+    const u32 alncap = T.vcap + T.lcap + 2;
     // per-warp layout (all sub-arrays 16-byte aligned)
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t at = o; o += round_up(bytes, 16); return at; };

@@ -1,4 +1,7 @@
-// k_poa.cuh — segmented partial-order alignment + column vote, one warp per region.
+// k_poa.cuh — the last-resort POA tier: one warp per region, everything in global memory, no limit on in-degree,
+// graphs up to 65 535 nodes, segments up to 6000 bases.  Regions normally never get here: k_poa2.cuh's tiers take them
+// (and document the algorithm); a region lands here only when a node collects more than 16 in-edges or the graph
+// outgrows 4096 nodes / 2048-base segments / 4 M matrix cells.
 //
 // Replaces consensus_SPOA (BMEAN/bmean.cpp:585-599), the vote of easy_consensus (:649-694) and the spoa 4.0.0
 // subset CONSENT uses: local (kSW) alignment with linear gaps m=5 n=-10 g=-4
@@ -9,23 +12,11 @@
 // What is kept of spoa's graph — exactly what its results depend on:
 //   node  : letter, ordered in-edge list (predecessor order drives the traceback tie-breaks), aligned set
 //           (<= 3 others: a column holds at most one node per base), #sequences through it, "sequence 0 is here"
-//   order : rank <-> node from the explicit-stack DFS of topological_sort
+//   order : rank <-> node from the explicit-stack DFS of topological_sort, re-run after every sequence as spoa does
 // Out-edges and per-edge sequence labels are not stored: edge existence is tested on the in-list, and the MSA
 // rows are never built — the vote only needs, per column, how many sequences pass through each of its nodes
-// (gaps = the rest) and row 0's letter.
-//
-// Parallelism: a persistent warp takes jobs (regions) from its tier's queue, heaviest first.  The score matrix is
-// swept row by row in rank order with the 32 lanes across query columns; the in-row gap dependency
-//   H[i][j] = max(v[j], H[i][j-1] - 4)        is the max-plus prefix scan   H[i][j] = max_{t<=j}(v[t] + 4t) - 4j,
-// done with 5 warp shuffles per 32 columns and a carry between chunks; a row whose only predecessor is the row just
-// computed (the common case) is produced from registers, with no loads.  Rows are kept as int16 because the
-// traceback needs the whole matrix, as in the reference.  Traceback, graph update and the DFS are sequential by
-// nature: lane 0 runs them, at shared-memory latency in the two shared-memory tiers.
-//
-// Storage tiers (a job that outgrows its tier is re-queued for the next one; nothing is committed before it ends):
-//   small  : graph, matrix, alignment in shared memory   (<= 160 nodes, <= 2048 cells)   20 warps / SM
-//   medium : graph in shared memory, matrix in HBM/L2    (<= 704 nodes)                   8 warps / SM
-//   global : everything in global memory, three sizes up to 65535 nodes
+// (gaps = the rest) and row 0's letter.  The score matrix is swept row by row in rank order with the 32 lanes across
+// query columns (max-plus prefix scan for the in-row gap term); traceback, graph update and the DFS run on lane 0.
 #pragma once
 #include "cg_common.cuh"
 
@@ -40,64 +31,6 @@ __device__ __forceinline__ u8* cg_smem_base() { return cg_emu::cur->blk->dyn_sme
 extern __shared__ __align__(128) unsigned char cg_dyn_smem_[];
 __device__ __forceinline__ u8* cg_smem_base() { return cg_dyn_smem_; }
 #endif
-
-struct CgPoaTierS { static constexpr u32 VCAP = 160, ECAP = 320, SCAP = 384, ALNCAP = 192, HCELLS = 2048, SEQCAP = 64, CTAS_PER_SM = 5; };
-struct CgPoaTierM { static constexpr u32 VCAP = 320, ECAP = 640, SCAP = 704, ALNCAP = 0, HCELLS = 0, SEQCAP = 256, CTAS_PER_SM = 4; };
-
-template <class T> struct CgPoaSmemLayout {
-    static constexpr u32 r16(u32 v) { return (v + 15u) / 16u * 16u; }
-    static constexpr u32 o_letter = 0, o_in0 = o_letter + r16(T::VCAP), o_nal = o_in0 + r16(T::VCAP), o_leader = o_nal + r16(T::VCAP),
-                         o_marks = o_leader + r16(T::VCAP), o_check = o_marks + r16(T::VCAP), o_nseq = o_check + r16(T::VCAP),
-                         o_aligned = o_nseq + r16(2 * T::VCAP), o_rank = o_aligned + r16(6 * T::VCAP), o_r2n = o_rank + r16(2 * T::VCAP),
-                         o_ih = o_r2n + r16(2 * T::VCAP), o_it = o_ih + r16(2 * T::VCAP), o_rdesc = o_it + r16(2 * T::VCAP),
-                         o_ep = o_rdesc + r16(4 * T::VCAP), o_en = o_ep + r16(2 * T::ECAP), o_stack = o_en + r16(2 * T::ECAP),
-                         o_an = o_stack + r16(2 * T::SCAP), o_ap = o_an + r16(2 * T::ALNCAP), o_seq = o_ap + r16(2 * T::ALNCAP),
-                         o_H = o_seq + r16(T::SEQCAP), per_warp = o_H + r16(2 * T::HCELLS);
-    static constexpr u32 cta_bytes = per_warp * CG_POA_WARPS_PER_CTA;
-};
-
-// Graph (and, for the small tier, matrix + alignment) at compile-time offsets of the warp's shared-memory slice:
-// every access below is an LDS/STS with an immediate offset.
-template <class T> struct CgPoaSmemG {
-    typedef CgPoaSmemLayout<T> Lay;
-    typedef u16 eidx;
-    typedef u16 stk_t;
-    static constexpr u32 ENONE = 0xffffu, STK_FLAG = 0x8000u;
-    static constexpr bool SMEM_MATRIX = T::HCELLS != 0;
-    u32 wo;                      // byte offset of this warp's slice
-    CgPoaScratch gs;             // global part: segment list (+ matrix and alignment for the medium tier)
-    __device__ __forceinline__ u8* b() const { return cg_smem_base() + wo; }
-    __device__ __forceinline__ u8& letter(u32 i) const { return b()[Lay::o_letter + i]; }
-    __device__ __forceinline__ u8& in0(u32 i) const { return b()[Lay::o_in0 + i]; }
-    __device__ __forceinline__ u8& nal(u32 i) const { return b()[Lay::o_nal + i]; }
-    __device__ __forceinline__ u8& leader(u32 i) const { return b()[Lay::o_leader + i]; }
-    __device__ __forceinline__ u8& marks(u32 i) const { return b()[Lay::o_marks + i]; }
-    __device__ __forceinline__ u8& check(u32 i) const { return b()[Lay::o_check + i]; }
-    __device__ __forceinline__ u16& nseq(u32 i) const { return ((u16*)(b() + Lay::o_nseq))[i]; }
-    __device__ __forceinline__ u16& aligned(u32 i) const { return ((u16*)(b() + Lay::o_aligned))[i]; }
-    __device__ __forceinline__ u16& rank_of(u32 i) const { return ((u16*)(b() + Lay::o_rank))[i]; }
-    __device__ __forceinline__ u16& r2n(u32 i) const { return ((u16*)(b() + Lay::o_r2n))[i]; }
-    __device__ __forceinline__ u16& in_head(u32 i) const { return ((u16*)(b() + Lay::o_ih))[i]; }
-    __device__ __forceinline__ u16& in_tail(u32 i) const { return ((u16*)(b() + Lay::o_it))[i]; }
-    __device__ __forceinline__ u32& rdesc(u32 i) const { return ((u32*)(b() + Lay::o_rdesc))[i]; }
-    __device__ __forceinline__ u16& e_pred(u32 i) const { return ((u16*)(b() + Lay::o_ep))[i]; }
-    __device__ __forceinline__ u16& e_next(u32 i) const { return ((u16*)(b() + Lay::o_en))[i]; }
-    __device__ __forceinline__ u16& stack(u32 i) const { return ((u16*)(b() + Lay::o_stack))[i]; }
-    __device__ __forceinline__ void aln_set(u32 i, i32 node, i32 pos) const {
-        if (SMEM_MATRIX) { ((i16*)(b() + Lay::o_an))[i] = (i16)node; ((i16*)(b() + Lay::o_ap))[i] = (i16)pos; }
-        else { gs.aln_node[i] = node; gs.aln_pos[i] = pos; }
-    }
-    __device__ __forceinline__ i32 aln_node(u32 i) const { return SMEM_MATRIX ? (i32)((i16*)(b() + Lay::o_an))[i] : gs.aln_node[i]; }
-    __device__ __forceinline__ i32 aln_pos(u32 i) const { return SMEM_MATRIX ? (i32)((i16*)(b() + Lay::o_ap))[i] : gs.aln_pos[i]; }
-    __device__ __forceinline__ i16* H() const { return SMEM_MATRIX ? (i16*)(b() + Lay::o_H) : gs.H; }
-    __device__ __forceinline__ u8* seqbuf() const { return b() + Lay::o_seq; }
-    __device__ __forceinline__ u32 seqcap() const { return T::SEQCAP; }
-    __device__ __forceinline__ u32 vcap() const { return T::VCAP; }
-    __device__ __forceinline__ u32 ecap() const { return T::ECAP; }
-    __device__ __forceinline__ u32 scap() const { return T::SCAP; }
-    __device__ __forceinline__ u32 alncap() const { return SMEM_MATRIX ? T::ALNCAP : gs.alncap; }
-    __device__ __forceinline__ u64 hcap() const { return SMEM_MATRIX ? (u64)T::HCELLS : gs.hcap; }
-};
 
 // Everything in global memory (per-warp scratch described by CgPoaScratch).
 struct CgPoaGlobG {
@@ -662,18 +595,6 @@ __global__ void __launch_bounds__(CG_POA_THREADS) k_poa(CgChunk c, const CgPoaSc
     const u32 gw = blockIdx.x * CG_POA_WARPS_PER_CTA + cg_warp();
     if (gw >= nwarps) return;                       // warp-uniform; no block-wide barrier in this kernel
     CgPoaGlobG s;
-    s.gs = scratch[gw];
-    cg_poa_drain(c, s, jobs, qctl, jobs_next, qnext);
-}
-
-// Shared-memory tiers.
-template <class T>
-__global__ void __launch_bounds__(CG_POA_THREADS, T::CTAS_PER_SM) k_poa_smem(CgChunk c, const CgPoaScratch* scratch, u32 nwarps, const uint2* jobs,
-                                                                            u32* qctl, uint2* jobs_next, u32* qnext) {
-    const u32 gw = blockIdx.x * CG_POA_WARPS_PER_CTA + cg_warp();
-    if (gw >= nwarps) return;
-    CgPoaSmemG<T> s;
-    s.wo = CgPoaSmemLayout<T>::per_warp * cg_warp();
     s.gs = scratch[gw];
     cg_poa_drain(c, s, jobs, qctl, jobs_next, qnext);
 }
