@@ -63,11 +63,14 @@ def _from_parts(parts) -> Results:
     return out
 
 
-def gather_results(local: Results, device=None, group=None):
+def gather_results(local: Results, device=None, group=None, with_solid: bool = True):
     """Ordered gather of every rank's results to rank 0 (variable length: sizes first, then padded payloads).
 
     Returns the concatenated Results on rank 0, None elsewhere.  `device`: torch device of the payload tensors
-    ("cuda:N" under NCCL, "cpu" under gloo)."""
+    ("cuda:N" under NCCL, "cpu" under gloo).  with_solid=False gathers what the reference finally emits — the
+    corrected sequences and their status — and leaves the solid k-mer lists on the rank that computed them: their only
+    consumer is that rank's own re-anchoring of the window consensuses (src/correctionAlignment.cpp:6-15,103-104),
+    and at 150-deep piles they are 50x the bytes of the consensuses."""
     import torch
     import torch.distributed as dist
 
@@ -76,6 +79,10 @@ def gather_results(local: Results, device=None, group=None):
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
     f = _Flat(local)
+    if not with_solid:
+        f.solid_len = np.zeros_like(f.solid_len)
+        f.solid_kmer = np.zeros(0, np.uint32)
+        f.solid_count = np.zeros(0, np.uint32)
     # one byte payload per rank: [cons_len i64][solid_len i64][status u8][cons u8][solid_kmer u32][solid_count u32]
     chunks = [f.cons_len.view(np.uint8), f.solid_len.view(np.uint8), f.status.view(np.uint8), f.cons.view(np.uint8),
               np.ascontiguousarray(f.solid_kmer).view(np.uint8), np.ascontiguousarray(f.solid_count).view(np.uint8)]
