@@ -331,11 +331,12 @@ int run_chunk(cg_handle* h, Lane& L, size_t ci) {
     span_end();
 
     span_begin(CG_STAGE_CHAIN);
-    size_t chain_smem = cg_chain_smem(cp.max_tk, cp.max_n);
     const size_t smem_cap = (size_t)h->smem_optin;
-    if (chain_smem > smem_cap) chain_smem = smem_cap;      // windows that really need more are flagged by the kernel
-    CG_LAUNCH(k_chain, nwin, CG_CHAIN_THREADS, chain_smem, st, c, (u32)chain_smem);
-    L.stage_launches[CG_STAGE_CHAIN] += 1;
+    const size_t chain_full = std::min(cg_chain_smem(cp.max_tk, cp.max_n), smem_cap);     // windows that need more are flagged by the kernel
+    const size_t chain_small = std::min(cg_chain_smem(std::min<u32>(cp.max_tk, 192u), cp.max_n), chain_full);
+    CG_LAUNCH(k_chain, nwin, CG_CHAIN_THREADS, chain_small, st, c, (u32)chain_small, 0u);
+    if (chain_full > chain_small) CG_LAUNCH(k_chain, nwin, CG_CHAIN_THREADS, chain_full, st, c, (u32)chain_full, 1u);
+    L.stage_launches[CG_STAGE_CHAIN] += chain_full > chain_small ? 2 : 1;
     span_end();
 
     span_begin(CG_STAGE_SPLIT);

@@ -24,17 +24,24 @@ __host__ __device__ inline size_t cg_chain_smem(u32 A, u32 N) {
     return 4 * ((size_t)A * cg_chain_nwp(N) + (size_t)A * aw + (size_t)CG_CHAIN_WARPS * A + 2 * (size_t)A) + 64;
 }
 
-__global__ void __launch_bounds__(CG_CHAIN_THREADS) k_chain(CgChunk c, u32 smem_bytes) {
+// Two launches: pass 0 with a shared-memory size that fits ordinary windows (many CTAs per SM) defers the windows that
+// need more; pass 1, with the device's maximum, takes those (and flags what does not fit even then).
+#define CG_CHAIN_DEFERRED 0xffffffffu
+__global__ void __launch_bounds__(CG_CHAIN_THREADS) k_chain(CgChunk c, u32 smem_bytes, u32 pass) {
     CG_DYN_SMEM(smem);
     const u32 w = blockIdx.x, tid = threadIdx.x, lane = cg_lane(), warp = cg_warp();
     const CgWin W = c.win[w];
     const u32 A = W.n_alive, N = W.n_seqs, C = W.n_cand, S = W.S;
+    if (pass == 1 && W.n_chain != CG_CHAIN_DEFERRED) return;
     if (A == 0) {
         if (tid == 0) c.win[w].n_chain = 0;
         return;
     }
     if (cg_chain_smem(A, N) > smem_bytes) {
-        if (tid == 0) { c.win[w].n_chain = 0; c.win[w].bad = 1; atomicOr(c.flags, (u32)CG_FLAG_CAPACITY); }
+        if (tid == 0) {
+            if (pass == 0) c.win[w].n_chain = CG_CHAIN_DEFERRED;
+            else { c.win[w].n_chain = 0; c.win[w].bad = 1; atomicOr(c.flags, (u32)CG_FLAG_CAPACITY); }
+        }
         return;
     }
     const u32 NWp = cg_chain_nwp(N), AW = (A + 31u) / 32u;
@@ -55,24 +62,51 @@ __global__ void __launch_bounds__(CG_CHAIN_THREADS) k_chain(CgChunk c, u32 smem_
     for (u32 r = warp; r < N; r += CG_CHAIN_WARPS) {
         const u16* prow = pos + (size_t)r * C;
         u32 m = 0;
-        for (u32 ab = 0; ab < A; ab += 32) {
-            const u32 a = ab + lane;
-            const u32 p = a < A ? prow[anchors[a]] : 0u;
-            const u32 bal = __ballot_sync(CG_FULL, p != 0);
-            if (p) {
-                cl[m + __popc(bal & ((1u << lane) - 1u))] = (a << 16) | p;
-                atomicOr(&pres[a * NWp + (r >> 5)], 1u << (r & 31u));
+        for (u32 ab = 0; ab < A; ab += 128) {           // four independent loads in flight per lane
+            u32 pv[4];
+#pragma unroll
+            for (u32 t = 0; t < 4; ++t) {
+                const u32 a = ab + 32 * t + lane;
+                pv[t] = a < A ? prow[anchors[a]] : 0u;
             }
-            m += __popc(bal);
+#pragma unroll
+            for (u32 t = 0; t < 4; ++t) {
+                const u32 a = ab + 32 * t + lane;
+                const u32 p = pv[t];
+                const u32 bal = __ballot_sync(CG_FULL, p != 0);
+                if (p) {
+                    cl[m + __popc(bal & ((1u << lane) - 1u))] = (a << 16) | p;
+                    atomicOr(&pres[a * NWp + (r >> 5)], 1u << (r & 31u));
+                }
+                m += __popc(bal);
+            }
         }
         __syncwarp();
         if (r != 0) {                              // the template holds its anchors in order by construction
-            for (u32 j = lane; j < m; j += 32) {
-                const u32 ej = cl[j], pj = ej & 0xffffu, aj = ej >> 16;
-                for (u32 l = j + 1; l < m; ++l) {
-                    const u32 el = cl[l];
-                    if ((el & 0xffffu) < pj) atomicOr(&inv[aj * AW + ((el >> 16) >> 5)], 1u << ((el >> 16) & 31u));
+            // an anchor is the left end of an inversion iff a smaller position follows it: suffix minima, back to front
+            u32 carry = 0xffffu;
+            for (int jb = (int)((m ? m - 1 : 0) & ~31u); jb >= 0; jb -= 32) {
+                const u32 j = (u32)jb + lane;
+                const u32 ej = j < m ? cl[j] : 0xffffffffu;
+                const u32 pj = ej & 0xffffu;
+                u32 sm = pj;                          // inclusive suffix minimum inside the chunk
+#pragma unroll
+                for (int dlt = 1; dlt < 32; dlt <<= 1) {
+                    const u32 o = __shfl_down_sync(CG_FULL, sm, dlt);
+                    if (lane + (u32)dlt < 32u) sm = o < sm ? o : sm;
                 }
+                u32 after = __shfl_down_sync(CG_FULL, sm, 1);     // minimum over the lanes behind this one ...
+                if (lane == 31) after = 0xffffu;
+                after = after < carry ? after : carry;            // ... and over the chunks behind
+                if (j < m && after < pj) {
+                    const u32 aj = ej >> 16;
+                    for (u32 l = j + 1; l < m; ++l) {
+                        const u32 el = cl[l];
+                        if ((el & 0xffffu) < pj) atomicOr(&inv[aj * AW + ((el >> 16) >> 5)], 1u << ((el >> 16) & 31u));
+                    }
+                }
+                const u32 first = __shfl_sync(CG_FULL, sm, 0);
+                carry = first < carry ? first : carry;
             }
         }
         __syncwarp();

@@ -61,6 +61,21 @@ __device__ __forceinline__ u32 cg_select_distance(const u16* pos, u32 C, u32 N, 
     return (u32)prefix;
 }
 
+// The same over distances held in registers: lane l keeps reads l, l + 32, ... (0xffffffff = the read lacks an anchor).
+#define CG_SPLIT_REG_READS 8u       // piles of up to 256 sequences take this path
+__device__ __forceinline__ u32 cg_select_distance_reg(const u32 (&d)[CG_SPLIT_REG_READS], u32 nbits, u32 idx) {
+    u32 prefix = 0, rem = idx;
+    for (int b = (int)nbits - 1; b >= 0; --b) {
+        u32 cnt0 = 0;
+#pragma unroll
+        for (u32 t = 0; t < CG_SPLIT_REG_READS; ++t)
+            cnt0 += ((d[t] >> (b + 1)) == (prefix >> (b + 1)) && !((d[t] >> b) & 1u)) ? 1u : 0u;
+        cnt0 = cg_warp_sum(cnt0);
+        if (rem >= cnt0) { rem -= cnt0; prefix |= 1u << b; }
+    }
+    return prefix;
+}
+
 __global__ void __launch_bounds__(CG_SPLIT_THREADS) k_split(CgChunk c) {
     const u32 w = blockIdx.x, lane = cg_lane(), warp = cg_warp();
     const CgWin W = c.win[w];
@@ -75,6 +90,38 @@ __global__ void __launch_bounds__(CG_SPLIT_THREADS) k_split(CgChunk c) {
     // ---- average_distance_next_anchor: one warp per consecutive anchor pair
     for (u32 i = warp; i + 1 < nA; i += CG_SPLIT_WARPS) {
         const u32 s1 = chain[i], s2 = chain[i + 1];
+        if (N <= 32u * CG_SPLIT_REG_READS) {            // distances once into registers
+            u32 d[CG_SPLIT_REG_READS];
+            u32 n = 0, mx = 0;
+#pragma unroll
+            for (u32 t = 0; t < CG_SPLIT_REG_READS; ++t) {
+                const u32 r = 32 * t + lane;
+                d[t] = 0xffffffffu;
+                if (r < N) {
+                    const u32 p1 = pos[(size_t)r * C + s1], p2 = pos[(size_t)r * C + s2];
+                    if (p1 && p2) { d[t] = p2 - p1; ++n; mx = d[t] > mx ? d[t] : mx; }
+                }
+            }
+            n = cg_warp_sum(n);
+            mx = cg_warp_max(mx);
+            if (n == 0) {                                   // unreachable: chain edges share >= max(S,1) reads
+                if (lane == 0) { rel[i] = 0; atomicOr(c.flags, (u32)CG_FLAG_INTERNAL); }
+                continue;
+            }
+            const u32 nbits = 32u - (u32)__clz((int)mx);
+            const u32 ilo = (u32)floor((double)(n - 1) * 0.2);     // deciles, bmean.cpp:324-327
+            const u32 ihi = (u32)ceil((double)(n - 1) * 0.8);
+            const double lo = (double)cg_select_distance_reg(d, nbits, ilo);
+            const double hi = (double)cg_select_distance_reg(d, nbits, ihi);
+            u32 sum = 0, cnt = 0;
+#pragma unroll
+            for (u32 t = 0; t < CG_SPLIT_REG_READS; ++t)
+                if (d[t] != 0xffffffffu && cg_comparable_dec((double)d[t], lo, hi)) { sum += d[t]; ++cnt; }
+            sum = cg_warp_sum(sum);
+            cnt = cg_warp_sum(cnt);
+            if (lane == 0) rel[i] = cnt ? sum / cnt : 0u;           // integer division, bmean.cpp:401
+            continue;
+        }
         u32 n = 0, mx = 0;
         for (u32 rb = 0; rb < N; rb += 32) {
             const u32 r = rb + lane;
