@@ -20,6 +20,12 @@
 
 #define CG_IDX_THREADS 512u
 #define CG_IDX_SMEM_BYTES (131072u + 8u * CG_PW_CAP + 2u * 2048u * 4u + 64u * 4u + 16u)
+// Bucketed counting (piles of up to CG_IDX_BUCKET_CAP k-mer occurrences, 2k > 13): the k-mers are extracted ONCE and
+// scattered, as their low 13 bits, into 2^(2k-13) buckets by their high bits (two sweeps over the pile: histogram, then
+// scatter); each counting pass then only touches its own bucket.  The 8-pass direct count below re-extracts every k-mer
+// in every pass and stays for deeper piles.
+#define CG_IDX_BUCKET_CAP 81920u
+#define CG_IDX_BKT_BITS 13u
 
 #ifndef CG_EMU
 __device__ __forceinline__ u32 cg_smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
@@ -42,9 +48,112 @@ __global__ void __launch_bounds__(CG_IDX_THREADS, 1) k_index(CgChunk c) {
     const u64 g0 = cg_pword(c.seq_off, W.seq_begin) - c.pword_base;
     const u32 nw = (u32)(cg_pword(c.seq_off, W.seq_begin + N) - c.pword_base - g0);
 
-    // ---- stage the 2-bit pile in shared memory (TMA bulk copy), if it fits
+    const u32 solid_thr = c.solid;
+    const u64 solid_base = c.off_solid[w];
+    u32 nsolid = 0;
     const u32* pw;
     const u32* pt;
+    const bool bucketed = W.n_occ <= CG_IDX_BUCKET_CAP && 2 * k > CG_IDX_BKT_BITS;
+    if (bucketed) {
+        // shared memory: [table 8192 u32][histogram + cursors 2 x 512 u32][bucket store CAP u16][tkmer][tcount][misc]
+        u32* whist = tab + 8192;                  // [warp][bucket] counts, then the bucket bases at [512 ..]
+        u32* cursor = whist + 512;
+        u16* bstore = (u16*)(cursor + 512);
+        tkmer = (u32*)(bstore + CG_IDX_BUCKET_CAP);
+        tcount = tkmer + 2048;
+        misc = tcount + 2048;
+        pw = c.pwords + g0;
+        pt = c.ptags + g0;
+        const u32 nbkt = 1u << (2 * k - CG_IDX_BKT_BITS);      // <= 32
+        const u32 lowmask = (1u << CG_IDX_BKT_BITS) - 1u;
+        for (u32 p = tid; p < tk; p += T) {
+            tkmer[p] = cg_kmer_at(pw[p >> 4], pw[(p >> 4) + 1], p & 15u, k);
+            tcount[p] = 0;
+        }
+        for (u32 i = tid; i < 1024; i += T) whist[i] = 0;
+        __syncthreads();
+        // sweep 1: per-warp histogram of the buckets
+        for (u32 g = tid; g < nw; g += T) {
+            const u32 tag = pt[g];
+            if (tag == CG_NONE32) continue;
+            const u32 nv = (tag & 15u) + 1;
+            const u32 w0 = pw[g], w1 = pw[g + 1];
+#pragma unroll
+            for (u32 b = 0; b < 16; ++b)
+                if (b < nv) atomicAdd(&whist[warp * 32 + (cg_kmer_at(w0, w1, b, k) >> CG_IDX_BKT_BITS)], 1u);
+        }
+        __syncthreads();
+        // bucket bases (exclusive scan over buckets) and the per-warp cursors inside each bucket
+        if (tid < 32) {
+            u32 tot = 0;
+            if (tid < nbkt) for (u32 x = 0; x < NWARPS; ++x) tot += whist[x * 32 + tid];
+            const u32 inc = cg_warp_scan(tot);
+            misc[40 + tid] = inc - tot;               // base of bucket tid
+            if (tid == 31) misc[39] = inc;           // all occurrences
+        }
+        __syncthreads();
+        {
+            const u32 x = tid >> 5, b = tid & 31u;    // 16 warps x 32 buckets = 512 threads
+            u32 off = misc[40 + b];
+            for (u32 y = 0; y < x; ++y) off += whist[y * 32 + b];
+            cursor[x * 32 + b] = off;
+        }
+        __syncthreads();
+        // sweep 2: scatter the low bits into the buckets
+        for (u32 g = tid; g < nw; g += T) {
+            const u32 tag = pt[g];
+            if (tag == CG_NONE32) continue;
+            const u32 nv = (tag & 15u) + 1;
+            const u32 w0 = pw[g], w1 = pw[g + 1];
+#pragma unroll
+            for (u32 b = 0; b < 16; ++b) {
+                if (b < nv) {
+                    const u32 km = cg_kmer_at(w0, w1, b, k);
+                    bstore[atomicAdd(&cursor[warp * 32 + (km >> CG_IDX_BKT_BITS)], 1u)] = (u16)(km & lowmask);
+                }
+            }
+        }
+        __syncthreads();
+        // one counting pass per bucket: 8192 keys, only the bucket's own occurrences
+        const u32 tab_n = 1u << CG_IDX_BKT_BITS;
+        const u32 per_warp = tab_n / NWARPS;          // 512 keys per warp, in key order
+        const u32 wb = warp * per_warp;
+        for (u32 bkt = 0; bkt < nbkt; ++bkt) {
+            for (u32 i = tid; i < tab_n; i += T) tab[i] = 0;
+            __syncthreads();
+            const u32 b0 = misc[40 + bkt], b1 = bkt + 1 < 32 ? (bkt + 1 < nbkt ? misc[40 + bkt + 1] : misc[39]) : misc[39];
+            for (u32 i = b0 + tid; i < b1; i += T) atomicAdd(&tab[bstore[i]], 1u);
+            __syncthreads();
+            for (u32 p = tid; p < tk; p += T) {
+                const u32 km = tkmer[p];
+                if ((km >> CG_IDX_BKT_BITS) == bkt) tcount[p] = tab[km & lowmask];
+            }
+            // solid entries of this bucket, in key order: count per warp range, scan, write
+            u32 wc = 0;
+            for (u32 b = wb; b < wb + per_warp; b += 32) wc += __popc(__ballot_sync(CG_FULL, tab[b + lane] >= solid_thr));
+            if (lane == 0) misc[warp] = wc;
+            __syncthreads();
+            u32 woff = 0, total = 0;
+            for (u32 i = 0; i < NWARPS; ++i) { const u32 v = misc[i]; if (i < warp) woff += v; total += v; }
+            if (wc) {
+                u64 run = solid_base + nsolid + woff;
+                for (u32 b = wb; b < wb + per_warp; b += 32) {
+                    const u32 cnt = tab[b + lane];
+                    const bool f = cnt >= solid_thr;
+                    const u32 m = __ballot_sync(CG_FULL, f);
+                    if (f) {
+                        const u64 idx = run + __popc(m & ((1u << lane) - 1u));
+                        c.solid_k[idx] = (bkt << CG_IDX_BKT_BITS) | (b + lane);
+                        c.solid_c[idx] = cnt;
+                    }
+                    run += __popc(m);
+                }
+            }
+            nsolid += total;
+            __syncthreads();
+        }
+    } else {
+    // ---- stage the 2-bit pile in shared memory (TMA bulk copy), if it fits
     {
         const u64 ga = g0 & ~3ull;                    // 16-byte aligned source
         const u32 shift = (u32)(g0 - ga);
@@ -97,8 +206,6 @@ __global__ void __launch_bounds__(CG_IDX_THREADS, 1) k_index(CgChunk c) {
     const u32 tab_bits = 2 * k < CG_TAB_BITS ? 2 * k : CG_TAB_BITS;
     const u32 tab_n = 1u << tab_bits, tab_mask = tab_n - 1;
     const u32 npass = 1u << (2 * k - tab_bits);
-    const u64 solid_base = c.off_solid[w];
-    u32 nsolid = 0;
     u32 per_warp = ((tab_n + NWARPS - 1) / NWARPS + 31u) & ~31u;
     const u32 wb = warp * per_warp < tab_n ? warp * per_warp : tab_n;
     const u32 we = wb + per_warp < tab_n ? wb + per_warp : tab_n;
@@ -128,7 +235,7 @@ __global__ void __launch_bounds__(CG_IDX_THREADS, 1) k_index(CgChunk c) {
         u32 wc = 0;
         for (u32 b = wb; b < we; b += 32) {
             const u32 i = b + lane;
-            const bool f = i < we && tab[i] >= c.solid;
+            const bool f = i < we && tab[i] >= solid_thr;
             wc += __popc(__ballot_sync(CG_FULL, f));
         }
         if (lane == 0) misc[warp] = wc;
@@ -139,7 +246,7 @@ __global__ void __launch_bounds__(CG_IDX_THREADS, 1) k_index(CgChunk c) {
         for (u32 b = wb; b < we; b += 32) {
             const u32 i = b + lane;
             const u32 cnt = i < we ? tab[i] : 0;
-            const bool f = i < we && cnt >= c.solid;
+            const bool f = i < we && cnt >= solid_thr;
             const u32 m = __ballot_sync(CG_FULL, f);
             if (f) {
                 const u64 idx = run + __popc(m & ((1u << lane) - 1u));
@@ -150,6 +257,7 @@ __global__ void __launch_bounds__(CG_IDX_THREADS, 1) k_index(CgChunk c) {
         }
         nsolid += total;
         __syncthreads();
+    }
     }
 
     // ---- candidate anchors: template positions with S <= count <= N, slots in template order
