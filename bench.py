@@ -214,6 +214,8 @@ def main():
         cor.set_option("chunk_max_windows", args.chunk_windows)
     if args.lanes:
         cor.set_option("lanes", args.lanes)
+    if os.environ.get("CG_CHUNK_BUDGET_GB"):
+        cor.set_option("chunk_budget_bytes", int(float(os.environ["CG_CHUNK_BUDGET_GB"]) * (1 << 30)))
 
     def barrier():
         torch.cuda.synchronize()

@@ -207,21 +207,21 @@ template <class T> __device__ __forceinline__ bool cg_poa2_dfs(const CgPoa2G<T>&
 // ------------------------------------------------------------------ traceback (lane 0)
 // simd_alignment_engine_impl.hpp:968-1004: diagonal over the predecessors in in-edge order, then vertical over them,
 // then horizontal.  Pairs are written in traceback order (last pair first) as node | qpos << W (all ones = none).
-template <class T> __device__ __forceinline__ u32 cg_poa2_traceback(const CgPoa2G<T>& s, const u8* seq, u32 Wd, u32 bi, u32 bj, bool* bad) {
+template <class T> __device__ __forceinline__ u32 cg_poa2_traceback(const CgPoa2G<T>& s, const u8* seq, u32 Ws, u32 bi, u32 bj, bool* bad) {
     CG_P2_TYPES;
     const i16* H = s.H();
     u32 i = bi, j = bj, n = 0;
-    i32 Hij = H[(size_t)i * Wd + j];
+    i32 Hij = H[(size_t)i * Ws + j];
     while (Hij != 0) {                                   // column 0 is all zeros, so j >= 1 in here
         const typename Pk::Rdesc d = s.rdesc(i - 1);
         const u32 deg = ((u32)d >> 8) & 0xffu;
         const i32 sc = ((u32)d & 0xffu) == seq[j - 1] ? 5 : -10;
-        const i16* hl = H + (size_t)i * Wd + (j - 1);
+        const i16* hl = H + (size_t)i * Ws + (j - 1);
         u32 pi_ = i, pj_ = j - 1;
         i32 Hp;
         if (deg <= 1) {                                  // one predecessor row (row 0 if the node has no in-edge)
             const u32 p = ((u32)d >> 16) & IDNONE;
-            const i16* hp = H + (size_t)p * Wd + (j - 1);
+            const i16* hp = H + (size_t)p * Ws + (j - 1);
             const i32 hd = hp[0], hv = hp[1], hh = hl[0];
             if (Hij == hd + sc) { pi_ = p; Hp = hd; }
             else if (Hij == hv - 4) { pi_ = p; pj_ = j; Hp = hv; }
@@ -233,7 +233,7 @@ template <class T> __device__ __forceinline__ u32 cg_poa2_traceback(const CgPoa2
 #pragma unroll 1
             for (u32 e = 0; e < deg && pd == IDNONE; ++e) {
                 const u32 p = Pk::get(pr, e);
-                const i16* hp = H + (size_t)p * Wd + (j - 1);
+                const i16* hp = H + (size_t)p * Ws + (j - 1);
                 const i32 hd = hp[0], hv = hp[1];
                 if (Hij == hd + sc) { pd = p; hd_ = hd; }
                 if (pv == IDNONE && Hij == hv - 4) { pv = p; hv_ = hv; }
@@ -260,8 +260,18 @@ template <class T> __device__ __forceinline__ u32 cg_poa2_traceback(const CgPoa2
 // scan needs no lane tests either.  The loop keeps one running maximum per lane; the winning cell is found afterwards
 // (cg_poa2_find_max), which costs cells/32 loads instead of a dozen instructions per row.
 // Column 0 of every row is zeroed beforehand.  Returns the lane's maximum over its columns.
+// Where the matrix lives in global memory the post-pass over it is expensive, so those tiers find the maximum as they go:
+// one warp reduction per row (redux.sync) and warp-uniform bookkeeping: the maximum, the first row holding it (in this
+// kernel's row order) and how many rows hold it.
+struct CgPoa2Max { i32 M; u32 row, nrows; };
+__device__ __forceinline__ void cg_poa2_track(CgPoa2Max& t, i32 lane_max, u32 row) {
+    const i32 m = __reduce_max_sync(CG_FULL, lane_max);
+    if (m > t.M) { t.M = m; t.row = row; t.nrows = 1; }
+    else if (m == t.M) t.nrows++;
+}
+
 template <int CH, class T>
-__device__ __forceinline__ i32 cg_poa2_dp(const CgPoa2G<T>& s, u32 V, const u8* seq, u32 L) {
+__device__ __forceinline__ i32 cg_poa2_dp(const CgPoa2G<T>& s, u32 V, const u8* seq, u32 L, u32 Ws) {
     CG_P2_TYPES;
     const u32 lane = cg_lane(), Wd = L + 1;
     i16* H = s.H();
@@ -277,11 +287,11 @@ __device__ __forceinline__ i32 cg_poa2_dp(const CgPoa2G<T>& s, u32 V, const u8* 
         j4[c] = 4 * (i32)j;
     }
     for (u32 j = lane; j < Wd; j += 32) H[j] = 0;
-    for (u32 r = lane; r < V; r += 32) H[(size_t)(r + 1) * Wd] = 0;
+    for (u32 r = lane; r < V; r += 32) H[(size_t)(r + 1) * Ws] = 0;
     __syncwarp();
     i32 bv = 0;
     u32 dnext = (u32)s.rdesc(0);
-    i16* row = H + Wd + 1 + lane;                        // cell (r + 1, 1 + lane)
+    i16* row = H + Ws + 1 + lane;                        // cell (r + 1, 1 + lane)
     for (u32 r = 0; r < V; ++r) {
         const u32 d = dnext;
         if (r + 1 < V) dnext = (u32)s.rdesc(r + 1);      // one row ahead: off the dependent chain
@@ -300,7 +310,7 @@ __device__ __forceinline__ i32 cg_poa2_dp(const CgPoa2G<T>& s, u32 V, const u8* 
                 val[c] = a > b ? a : b;
             }
         } else if (deg <= 1) {                           // one predecessor elsewhere, or none (virtual row 0)
-            const i16* prow = H + (size_t)p0 * Wd + lane;
+            const i16* prow = H + (size_t)p0 * Ws + lane;
 #pragma unroll
             for (int c = 0; c < CH; ++c) {
                 val[c] = 0;
@@ -316,7 +326,7 @@ __device__ __forceinline__ i32 cg_poa2_dp(const CgPoa2G<T>& s, u32 V, const u8* 
             const VecT pr = s.prow(r);
 #pragma unroll 1
             for (u32 e = 0; e < deg; ++e) {
-                const i16* prow = H + (size_t)Pk::get(pr, e) * Wd + lane;
+                const i16* prow = H + (size_t)Pk::get(pr, e) * Ws + lane;
 #pragma unroll
                 for (int c = 0; c < CH; ++c) {
                     if (act[c]) {
@@ -352,15 +362,125 @@ __device__ __forceinline__ i32 cg_poa2_dp(const CgPoa2G<T>& s, u32 V, const u8* 
                 bv = h > bv ? h : bv;
             }
         }
-        row += Wd;
+        row += Ws;
         __syncwarp();
     }
     return bv;
 }
 
+// The same for longer segments with TWO columns per lane, as packed 16-bit halves of one register (VIADD.16x2 /
+// VIMNMX.S16x2 / VIADDMNMX.S16x2 are native on sm_100a): lane l of chunk c owns columns 64c + 2l (low half) and
+// 64c + 2l + 1 (high half), so a row of up to 64 columns costs one pass of the scan instead of two, and one 32-bit store.
+// Column 0 is lane 0's low half: it is forced to 0 in every row.  Rows have an even stride, so the pairs are aligned.
+__device__ __forceinline__ u32 cg_vadd2(u32 a, u32 b) { return __vadd2(a, b); }
+__device__ __forceinline__ u32 cg_vmax2(u32 a, u32 b) { return __vmaxs2(a, b); }
+#ifndef CG_EMU
+__device__ __forceinline__ u32 cg_viaddmax2_relu(u32 a, u32 b, u32 c) { return __viaddmax_s16x2_relu(a, b, c); }
+#else
+__device__ __forceinline__ u32 cg_viaddmax2_relu(u32 a, u32 b, u32 c) { return __vmaxs2(__vmaxs2(__vadd2(a, b), c), 0u); }
+#endif
+template <int CH, class T>
+__device__ __forceinline__ i32 cg_poa2_dp2(const CgPoa2G<T>& s, u32 V, const u8* seq, u32 L, u32 Ws, CgPoa2Max& trk) {
+    CG_P2_TYPES;
+    const u32 lane = cg_lane(), Wd = L + 1;
+    i16* H = s.H();
+    u32 q0[CH], q1[CH];                                  // query letters of the two columns (0 = none)
+    u32 prev[CH], j4[CH], nj4[CH], keep[CH], actm[CH];
+    bool act[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+        const u32 j0 = 64 * c + 2 * lane, j1 = j0 + 1;
+        act[c] = j0 < Wd;
+        q0[c] = (j0 >= 1 && j0 < Wd) ? seq[j0 - 1] : 0u;
+        q1[c] = j1 < Wd ? seq[j1 - 1] : 0u;
+        prev[c] = 0;
+        j4[c] = (4 * j0) | ((4 * j1) << 16);
+        nj4[c] = ((0u - 4 * j0) & 0xffffu) | ((0u - 4 * j1) << 16);
+        keep[c] = j0 == 0 ? 0xffff0000u : 0xffffffffu;   // column 0 stays 0
+        actm[c] = (j0 < Wd ? 0xffffu : 0u) | (j1 < Wd ? 0xffff0000u : 0u);
+    }
+    for (u32 j = lane; j < Ws; j += 32) H[j] = 0;
+    __syncwarp();
+    u32 bv2 = 0;
+    u32 dnext = (u32)s.rdesc(0);
+    u32* row = (u32*)(H + Ws) + lane;                    // cells (r + 1, 2 lane) and (r + 1, 2 lane + 1)
+    for (u32 r = 0; r < V; ++r) {
+        const u32 d = dnext;
+        if (r + 1 < V) dnext = (u32)s.rdesc(r + 1);
+        const u32 ch = d & 0xffu;
+        const u32 deg = (d >> 8) & 0xffu;
+        const u32 p0 = (d >> 16) & IDNONE;
+        u32 val[CH];
+        if (deg <= 1 && p0 == r) {                       // predecessor = the row just computed (or the zero row for r = 0)
+#pragma unroll
+            for (int c = 0; c < CH; ++c) {
+                u32 up = __shfl_up_sync(CG_FULL, prev[c], 1);
+                const u32 l31 = c > 0 ? __shfl_sync(CG_FULL, prev[c > 0 ? c - 1 : 0], 31) : 0u;
+                if (lane == 0) up = l31;
+                const u32 left = __funnelshift_l(up, prev[c], 16);            // (column 2l - 1, column 2l) of the row above
+                const u32 sc = (q0[c] == ch ? 5u : 0xfff6u) | (q1[c] == ch ? 0x00050000u : 0xfff60000u);
+                val[c] = cg_viaddmax2_relu(left, sc, cg_vadd2(prev[c], 0xfffcfffcu));
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < CH; ++c) val[c] = 0;
+            const VecT pr = s.prow(r);
+            const u32 np = deg ? deg : 1u;
+#pragma unroll 1
+            for (u32 e = 0; e < np; ++e) {
+                const i16* prow = H + (size_t)(deg ? Pk::get(pr, e) : 0u) * Ws + 2 * lane;
+#pragma unroll
+                for (int c = 0; c < CH; ++c) {
+                    if (act[c]) {
+                        const u32 sc = (q0[c] == ch ? 5u : 0xfff6u) | (q1[c] == ch ? 0x00050000u : 0xfff60000u);
+                        const u32 h01 = *(const u32*)(prow + 64 * c);                 // columns 2l, 2l + 1
+                        const u32 hm1 = (c == 0 && lane == 0) ? 0u : (u32)(u16)prow[64 * c - 1];
+                        const u32 diag = hm1 | (h01 << 16);                           // columns 2l - 1, 2l
+                        val[c] = cg_vmax2(val[c], cg_viaddmax2_relu(diag, sc, cg_vadd2(h01, 0xfffcfffcu)));
+                    }
+                }
+            }
+        }
+        // in-row gap term: max-plus prefix scan over u = H + 4j, first inside the lane, then across lanes
+        u32 u[CH], x[CH];
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            u[c] = cg_vadd2(val[c] & keep[c], j4[c]);
+            u[c] = cg_vmax2(u[c], u[c] << 16);                              // high column also sees the low one
+            x[c] = __byte_perm(u[c], 0, 0x3232);                            // the lane's maximum in both halves
+        }
+#pragma unroll
+        for (int dd = 1; dd < 32; dd <<= 1) {
+#pragma unroll
+            for (int c = 0; c < CH; ++c) x[c] = cg_vmax2(x[c], __shfl_up_sync(CG_FULL, x[c], dd));
+        }
+        u32 carry = 0, rowmax = 0;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            u32 e = __shfl_up_sync(CG_FULL, x[c], 1);                       // maximum over the lanes before this one
+            if (lane == 0) e = 0;
+            e = cg_vmax2(e, carry);
+            if (c + 1 < CH) carry = cg_vmax2(carry, __shfl_sync(CG_FULL, x[c], 31));
+            const u32 h = cg_vadd2(cg_vmax2(u[c], e), nj4[c]) & keep[c];
+            prev[c] = h;
+            if (act[c]) row[32 * c] = h;
+            if (T::H_SMEM) bv2 = cg_vmax2(bv2, h & actm[c]);
+            else rowmax = c == 0 ? (h & actm[c]) : cg_vmax2(rowmax, h & actm[c]);
+        }
+        if (!T::H_SMEM) {
+            const u32 lo = rowmax & 0xffffu, hi = rowmax >> 16;          // scores are never negative
+            cg_poa2_track(trk, (i32)(lo > hi ? lo : hi), r + 1);
+        }
+        row += Ws / 2;
+        __syncwarp();
+    }
+    const i32 lo = (i32)(i16)(bv2 & 0xffffu), hi = (i32)(i16)(bv2 >> 16);
+    return lo > hi ? lo : hi;
+}
+
 // Any length: chunks of 32 columns, every row read back from the stored matrix.
 template <class T>
-__device__ __forceinline__ i32 cg_poa2_dp_any(const CgPoa2G<T>& s, u32 V, const u8* seq, u32 L) {
+__device__ __forceinline__ i32 cg_poa2_dp_any(const CgPoa2G<T>& s, u32 V, const u8* seq, u32 L, u32 Ws, CgPoa2Max& trk) {
     CG_P2_TYPES;
     const u32 lane = cg_lane(), Wd = L + 1;
     i16* H = s.H();
@@ -372,9 +492,9 @@ __device__ __forceinline__ i32 cg_poa2_dp_any(const CgPoa2G<T>& s, u32 V, const 
         const u8 ch = (u8)(d & 0xffu);
         const u32 deg = (d >> 8) & 0xffu, np = deg ? deg : 1u;
         const VecT pr = s.prow(r);
-        i16* row = H + (size_t)(r + 1) * Wd;
+        i16* row = H + (size_t)(r + 1) * Ws;
         if (lane == 0) row[0] = 0;
-        i32 carry = 0;
+        i32 carry = 0, rowmax = 0;
         for (u32 jb = 1; jb < Wd; jb += 32) {
             const u32 j = jb + lane;
             const bool act = j < Wd;
@@ -382,7 +502,7 @@ __device__ __forceinline__ i32 cg_poa2_dp_any(const CgPoa2G<T>& s, u32 V, const 
             if (act) {
                 const i32 sc = seq[j - 1] == ch ? 5 : -10;
                 for (u32 e = 0; e < np; ++e) {
-                    const i16* prow = H + (size_t)(deg ? Pk::get(pr, e) : 0u) * Wd;
+                    const i16* prow = H + (size_t)(deg ? Pk::get(pr, e) : 0u) * Ws;
                     const i32 a = (i32)prow[j - 1] + sc, b = (i32)prow[j] - 4;
                     const i32 m = a > b ? a : b;
                     val = m > val ? m : val;
@@ -400,8 +520,10 @@ __device__ __forceinline__ i32 cg_poa2_dp_any(const CgPoa2G<T>& s, u32 V, const 
                 const i32 h = u - 4 * (i32)j;
                 row[j] = (i16)h;
                 bv = h > bv ? h : bv;
+                rowmax = h > rowmax ? h : rowmax;
             }
         }
+        if (!T::H_SMEM) cg_poa2_track(trk, rowmax, r + 1);
         __syncwarp();
     }
     return bv;
@@ -410,7 +532,7 @@ __device__ __forceinline__ i32 cg_poa2_dp_any(const CgPoa2G<T>& s, u32 V, const 
 // Where is the maximum M (> 0)?  Lanes over rows, each scanning its row.  Returns the number of rows that hold M; if it is
 // exactly one, (*bi, *bj) is the first cell of that row equal to M (simd_alignment_engine_impl.hpp:860-862).
 template <class T>
-__device__ __forceinline__ u32 cg_poa2_find_max(const CgPoa2G<T>& s, u32 V, u32 Wd, i32 M, u32* bi, u32* bj) {
+__device__ __forceinline__ u32 cg_poa2_find_max(const CgPoa2G<T>& s, u32 V, u32 Wd, u32 Ws, i32 M, u32* bi, u32* bj) {
     const u32 lane = cg_lane();
     const i16* H = s.H();
     u32 nrows = 0, frow = 0, fcol = 0;
@@ -418,7 +540,7 @@ __device__ __forceinline__ u32 cg_poa2_find_max(const CgPoa2G<T>& s, u32 V, u32 
         const u32 r = rb + lane;
         u32 col = 0;
         if (r < V) {
-            const i16* hr = H + (size_t)(r + 1) * Wd;
+            const i16* hr = H + (size_t)(r + 1) * Ws;
 #pragma unroll 4
             for (u32 j = Wd - 1; j >= 1; --j) col = (i32)hr[j] == M ? j : col;
         }
@@ -480,21 +602,37 @@ __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s
             __syncwarp();
             seq = sb;
         }
-        const u32 Wd = L + 1;
+        const u32 Wd = L + 1, Ws = (L + 2) & ~1u;              // columns 0..L; rows are stored with an even stride
         u32 n_aln = 0;
         if (V != 0) {
-            if ((u64)(V + 1) * Wd > (u64)T::HCELLS) return CG_NONE32;
+            if ((u64)(V + 1) * Ws > (u64)T::HCELLS) return CG_NONE32;
             i32 bv;
-            if (L <= 32) bv = cg_poa2_dp<1>(s, V, seq, L);
-            else if (L <= 64) bv = cg_poa2_dp<2>(s, V, seq, L);
-            else if (T::LCAP > 64 && L <= 128) bv = cg_poa2_dp<(T::LCAP > 64 ? 4 : 1)>(s, V, seq, L);
-            else if (T::LCAP > 128 && L <= 256) bv = cg_poa2_dp<(T::LCAP > 128 ? 8 : 1)>(s, V, seq, L);
-            else if (T::LCAP > 256) bv = cg_poa2_dp_any(s, V, seq, L);
+            CgPoa2Max trk;
+            trk.M = 0; trk.row = 0; trk.nrows = 0;
+            if (L <= 32 && T::H_SMEM) bv = cg_poa2_dp<1>(s, V, seq, L, Ws);
+            else if (L <= 63) bv = cg_poa2_dp2<1>(s, V, seq, L, Ws, trk);
+            else if (T::LCAP > 63 && L <= 127) bv = cg_poa2_dp2<(T::LCAP > 63 ? 2 : 1)>(s, V, seq, L, Ws, trk);
+            else if (T::LCAP > 127 && L <= 255) bv = cg_poa2_dp2<(T::LCAP > 127 ? 4 : 1)>(s, V, seq, L, Ws, trk);
+            else if (T::LCAP > 255) bv = cg_poa2_dp_any(s, V, seq, L, Ws, trk);
             else bv = 0;
             j_aln += 1; j_cells += (u64)(V + 1) * L; j_pred += (u64)sumdeg * L;
-            const i32 M = (i32)cg_warp_max((u32)bv);
-            u32 bi = 0, bj = 0;
-            if (M > 0 && cg_poa2_find_max(s, V, Wd, M, &bi, &bj) > 1) {
+            i32 M;
+            u32 bi = 0, bj = 0, nrows;
+            if (T::H_SMEM) {
+                M = (i32)cg_warp_max((u32)bv);
+                nrows = M > 0 ? cg_poa2_find_max(s, V, Wd, Ws, M, &bi, &bj) : 0u;
+            } else {
+                M = trk.M; nrows = trk.nrows; bi = trk.row;
+                if (M > 0 && nrows == 1) {                   // first cell of that row equal to M
+                    const i16* hr = s.H() + (size_t)bi * Ws;
+                    for (u32 jb = 1; jb < Wd; jb += 32) {
+                        const u32 j = jb + lane;
+                        const u32 bal = __ballot_sync(CG_FULL, j < Wd && (i32)hr[j] == M);
+                        if (bal) { bj = jb + (u32)__ffs((int)bal) - 1; break; }
+                    }
+                }
+            }
+            if (M > 0 && nrows > 1) {
                 // several rows reach the maximum: the winner is the first of them in spoa's own order (simd...impl.hpp:828-833)
                 if (!dfs_valid) {
                     for (u32 i = lane; i < V; i += 32) { s.marks(i) = 0; s.check(i) = 1; }
@@ -514,14 +652,14 @@ __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s
                     u32 myrow = 0;
                     if (i < V) {
                         myrow = (u32)s.rank_of(s.xr2n(i)) + 1;
-                        const i16* hr = H + (size_t)myrow * Wd;
+                        const i16* hr = H + (size_t)myrow * Ws;
                         for (u32 j = 1; j < Wd; ++j) hit = hit || (i32)hr[j] == M;
                     }
                     const u32 bal = __ballot_sync(CG_FULL, hit);
                     if (bal) { row = __shfl_sync(CG_FULL, myrow, __ffs((int)bal) - 1); break; }
                 }
                 bi = row; bj = 0;
-                const i16* hr = H + (size_t)row * Wd;
+                const i16* hr = H + (size_t)row * Ws;
                 for (u32 jb = 1; jb < Wd; jb += 32) {
                     const u32 j = jb + lane;
                     const u32 bal = __ballot_sync(CG_FULL, j < Wd && (i32)hr[j] == M);
@@ -529,7 +667,7 @@ __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s
                 }
             }
             bool bad = false;
-            if (lane == 0 && M > 0) n_aln = cg_poa2_traceback(s, seq, Wd, bi, bj, &bad);
+            if (lane == 0 && M > 0) n_aln = cg_poa2_traceback(s, seq, Ws, bi, bj, &bad);
             n_aln = __shfl_sync(CG_FULL, n_aln, 0);
             if (__shfl_sync(CG_FULL, (u32)bad, 0)) return CG_NONE32;
         }

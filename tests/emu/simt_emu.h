@@ -289,6 +289,10 @@ static inline unsigned __ballot_sync(unsigned mask, int pred) {
     return r;
 }
 static inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
+static inline int __reduce_max_sync(unsigned mask, int v) {
+    for (int d = 16; d > 0; d >>= 1) { const int o = __shfl_xor_sync(mask, v, d); v = o > v ? o : v; }
+    return v;
+}
 static inline int __all_sync(unsigned mask, int pred) {
     unsigned n = cg_emu::warp_size_here();
     unsigned full = n == 32 ? 0xffffffffu : ((1u << n) - 1);
@@ -301,6 +305,19 @@ static inline int __popcll(unsigned long long x) { return __builtin_popcountll(x
 static inline int __clz(int x) { return x == 0 ? 32 : __builtin_clz((unsigned)x); }
 static inline int __ffs(int x) { return __builtin_ffs(x); }
 static inline unsigned __brev(unsigned x) { unsigned r = 0; for (int i = 0; i < 32; ++i) if (x & (1u << i)) r |= 1u << (31 - i); return r; }
+static inline unsigned __vadd2(unsigned a, unsigned b) {          // per-halfword add, wrap-around
+    return (((a & 0xffffu) + (b & 0xffffu)) & 0xffffu) | ((((a >> 16) + (b >> 16)) & 0xffffu) << 16);
+}
+static inline unsigned __vmaxs2(unsigned a, unsigned b) {         // per-halfword signed maximum
+    const short al = (short)(a & 0xffffu), bl = (short)(b & 0xffffu), ah = (short)(a >> 16), bh = (short)(b >> 16);
+    return (unsigned)(unsigned short)(al > bl ? al : bl) | ((unsigned)(unsigned short)(ah > bh ? ah : bh) << 16);
+}
+static inline unsigned __byte_perm(unsigned x, unsigned y, unsigned sel) {
+    const unsigned long long v = ((unsigned long long)y << 32) | x;
+    unsigned r = 0;
+    for (int i = 0; i < 4; ++i) r |= (unsigned)((v >> (8 * ((sel >> (4 * i)) & 7u))) & 0xffu) << (8 * i);
+    return r;
+}
 static inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned shift) {
     unsigned long long v = ((unsigned long long)hi << 32) | lo;
     return (unsigned)((v << (shift & 31)) >> 32);
