@@ -287,16 +287,20 @@ def main():
     kernel_stage = {"index": "k_index", "poa": "k_poa2 (tiers C1+G+W)", "chain": "k_chain", "split": "k_split", "polish": "k_polish"}
     dom = max(kernel_stage, key=lambda k: stage_avg.get(k, 0.0))
     dom_bytes = {"index": ab["index"], "poa": ab["poa"], "chain": ab["index"], "split": ab["in"], "polish": ab["out"]}[dom]
-    n_launch = max(1, cor.stage_ms()[dom]["launches"])
-    achieved = dom_bytes / n_launch / (stage_avg[dom] / n_launch / 1e3) / 1e9 if stage_avg.get(dom) else 0.0
+    # one "launch" of the dominant kernel = its pass over one chunk of windows (the POA tiers of a chunk run side by side
+    # and count as one); its duration = the stage's CUDA-event time on the launching stream / chunks
+    n_launch = max(1, cor.chunk_count())
+    achieved = dom_bytes / (stage_avg[dom] / 1e3) / 1e9 if stage_avg.get(dom) else 0.0
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tr.get(dom, {}).get("dram_bytes_per_window") * args.windows / n_launch
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": kernel_stage[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": dom_bytes / n_launch, "launches_per_step": n_launch,
+                "ms_per_launch": stage_avg[dom] / n_launch,
                 "whole_path_GBps": ab["window_total"] / (dev_ms / args.steps / 1e3) / 1e9,
                 "stage_ms_per_step": {k: round(v, 3) for k, v in stage_avg.items()}}
 

@@ -935,6 +935,8 @@ int cg_run_ms(const cg_handle* h, float* ms) {
     return CG_OK;
 }
 
+int cg_chunk_count(const cg_handle* h) { return h && h->uploaded ? (int)h->chunks.size() : 0; }
+
 int cg_get_counters(const cg_handle* h, cg_counters* out) {
     if (!h || !out) return CG_ERR_INVALID_ARG;
     *out = h->counters;

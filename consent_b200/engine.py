@@ -21,7 +21,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libconsent_b200.so")
 
 EXPORTS = ("cg_abi_version", "cg_device_count", "cg_create", "cg_destroy", "cg_last_error", "cg_set_option",
            "cg_correct_windows", "cg_free_results", "cg_upload", "cg_run", "cg_download", "cg_stage_ms",
-           "cg_get_counters", "cg_run_ms")
+           "cg_get_counters", "cg_run_ms", "cg_chunk_count")
 
 
 class ConsentError(RuntimeError):
@@ -56,6 +56,8 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.cg_stage_ms.argtypes = [H, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]
     lib.cg_run_ms.restype = C.c_int
     lib.cg_run_ms.argtypes = [H, C.POINTER(C.c_float)]
+    lib.cg_chunk_count.restype = C.c_int
+    lib.cg_chunk_count.argtypes = [H]
     lib.cg_get_counters.restype = C.c_int
     lib.cg_get_counters.argtypes = [H, C.POINTER(cg_counters)]
     return lib
@@ -132,6 +134,10 @@ class Corrector:
         ms = C.c_float(0)
         self._check(self.lib.cg_run_ms(self._h, C.byref(ms)))
         return float(ms.value)
+
+    def chunk_count(self) -> int:
+        """Chunks the uploaded batch is processed in (one launch of every kernel per chunk)."""
+        return int(self.lib.cg_chunk_count(self._h))
 
     def counters(self) -> dict:
         c = cg_counters()

@@ -138,6 +138,8 @@ int  cg_download(cg_handle* h, cg_results* out);    /* D2H of the results of cg_
 int  cg_stage_ms(const cg_handle* h, float ms[CG_N_STAGES], uint32_t launches[CG_N_STAGES]);
 /* CUDA-event time (ms) of the whole last cg_run on the handle's stream, first launch to last result. */
 int  cg_run_ms(const cg_handle* h, float* ms);
+/* Number of chunks the uploaded batch is processed in (each chunk = one launch of every kernel of the path). */
+int  cg_chunk_count(const cg_handle* h);
 
 /* Work counters of the last cg_run, the inputs of the algorithmic-bytes model
  * (SURVEY §8d): alignments, score-matrix cells sum (V+1)*L, predecessor-row cells
