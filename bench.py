@@ -93,11 +93,12 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_batch(n_windows: int, n_seqs: int, first_window: int, pinned: bool):
+def make_batch(n_windows: int, n_seqs: int, first_window: int, pinned: bool, world: int = 1):
     """Slice [first_window, first_window + n_windows) of the seed-42 PB stream; arrays in pinned host memory if asked."""
     from consent_b200._ffi import Batch
     from consent_b200.synth import synth_windows
-    b = synth_windows(n_windows, n_seqs, seed=42, profile="PB", first_window=first_window, threads=min(host_cores(), 64))
+    b = synth_windows(n_windows, n_seqs, seed=42, profile="PB", first_window=first_window,
+                      threads=max(1, min(host_cores() // max(world, 1), 64)))
     if pinned:
         import torch
         keep = []
@@ -205,7 +206,7 @@ def main():
     from consent_b200.shard import gather_results
 
     t0 = time.time()
-    batch = make_batch(args.windows, args.seqs, rank * args.windows, pinned=True)       # weak scaling: every rank its own slice
+    batch = make_batch(args.windows, args.seqs, rank * args.windows, pinned=True, world=world)   # weak scaling: every rank its own slice
     n_occ = int(np.maximum(np.diff(batch.seq_off.astype(np.int64)) - 8, 0).sum())
     log(f"[rank {rank}] generated {batch.n_windows} windows, {batch.n_bases / 1e9:.2f} GB of bases in {time.time() - t0:.1f}s")
 

@@ -131,7 +131,7 @@ struct cg_handle {
     std::vector<u64> h_wbase;           // [W + 1] seq_off[win_seq_begin[w]]
     std::vector<u32> h_tlen;            // [W] template length
     std::vector<ChunkPlan> chunks;
-    bool uploaded = false, ran = false;
+    bool uploaded = false, ran = false, planned_ramp = false;
     // POA tiers
     std::mutex tier_mu;                  // the last-resort scratch is shared by the lanes
     PoaTier tier[3];                     // k_poa.cuh: global-memory tiers without an in-degree limit (the last resort); [0] unused
@@ -177,8 +177,11 @@ enum { CTL_FLAGS = 0, CTL_VFLAGS = 1, CTL_Q = 4, CTL_NQ = 10, CTL_WORDS = 48, HC
 
 // Chunk plan from per-window summaries only (O(W) on the host): every capacity below is an upper bound of what
 // k_plan computes on the device from the exact per-sequence lengths (occurrences <= bases).
-int plan_chunks(cg_handle* h) {
+// ramp: the first chunk is a quarter of the others, so that a pipelined call (cg_correct_windows) starts computing after a
+// quarter of the first upload.
+int plan_chunks(cg_handle* h, bool ramp = false) {
     h->chunks.clear();
+    h->planned_ramp = ramp;
     const u32 k = h->p.mer_size;
     u32 w = 0;
     while (w < h->W) {
@@ -186,7 +189,8 @@ int plan_chunks(cg_handle* h) {
         c.w0 = w;
         c.pword_base = (h->h_wbase[w] >> 4) + h->h_wsb[w];
         size_t bytes = 0;
-        while (w < h->W && c.nwin < h->chunk_max_windows) {
+        const u32 max_windows = (ramp && w == 0 && h->W > h->chunk_max_windows) ? std::max<u32>(1u, h->chunk_max_windows / 4) : h->chunk_max_windows;
+        while (w < h->W && c.nwin < max_windows) {
             const u32 s0 = h->h_wsb[w], s1 = h->h_wsb[w + 1], N = s1 - s0;
             const u64 nb = h->h_wbase[w + 1] - h->h_wbase[w];
             const u64 nocc = nb;
@@ -669,7 +673,7 @@ int cg_set_option(cg_handle* h, const char* key, long long value) {
     else if (k == "poa_tier2_nodes") { h->tier[2].vcap = (u32)std::min<long long>(value, 65535); h->tier[2].ecap = 4 * h->tier[2].vcap; h->tier[2].ready = false; }
     else if (k == "poa_tier2_cells") { h->tier[2].hcap = (u64)value; h->tier[2].ready = false; }
     else { h->err = "unknown option " + k; return CG_ERR_INVALID_ARG; }
-    if (h->uploaded) plan_chunks(h);
+    if (h->uploaded) plan_chunks(h, h->planned_ramp);
     return CG_OK;
 }
 
@@ -720,7 +724,7 @@ int upload_impl(cg_handle* h, const cg_batch* in, bool wait) {
     CK(cudaMemsetAsync(vflags, 0, sizeof(u32), sc));
     if (n_seqs) CG_LAUNCH(k_validate, (u32)std::min<u64>((n_seqs + 255) / 256, 4096), 256, 0, sc, h->d_seq_off.as<u64>(), n_seqs, vflags);
     CK(cudaMemcpyAsync(h->lane[0].h_ctl + HCTL_VFLAGS, vflags, sizeof(u32), cudaMemcpyDeviceToHost, sc));
-    plan_chunks(h);
+    plan_chunks(h, !wait);
     while (h->ev_h2d.size() < h->chunks.size()) {
         cudaEvent_t e;
         CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));

@@ -141,8 +141,42 @@ def test_gpu_config3_shape_properties(gpu, oracle):
         assert res.solid(500 + w) == want.solid(w)
         assert res.status[500 + w] == want.status[w]
     assert gpu(chunk_max_windows=128).correct_windows(batch).digest() == res.digest()
+    assert gpu(chunk_max_windows=100, lanes=1).correct_windows(batch).digest() == res.digest()     # one lane, many chunks
     # self-consistency: correcting a pile whose reads are all the consensus returns the consensus, fully solid
     cons = [res.consensus(w).upper() for w in range(0, 40)]
     again = gpu().correct_windows(Batch.from_piles([[c] * 6 for c in cons]))
     for i, c in enumerate(cons):
         assert again.consensus(i) == c
+
+
+def test_gpu_config3_stream_is_invariant_under_scheduling(gpu, oracle, reference):
+    """A longer slice of the config-3 stream (8 192 windows x 150): the result must not depend on how the batch is cut
+    into chunks, on the number of lanes in flight, or on staged vs pipelined calls; a 96-window sample is checked against
+    the unmodified reference itself."""
+    W = 8192
+    batch = synth_windows(W, 150, seed=42, first_window=50000)
+    a = gpu().correct_windows(batch)
+    assert a.n_windows == W and int(a.status.sum()) == 0
+    d = a.digest()
+    assert gpu(chunk_max_windows=1500).correct_windows(batch).digest() == d
+    assert gpu(lanes=1).correct_windows(batch).digest() == d
+    staged = gpu(chunk_max_windows=3000)
+    staged.upload(batch)
+    staged.run()
+    assert staged.download().digest() == d
+    staged.run()
+    assert staged.download().digest() == d                                  # idempotent on a resident batch
+    sample = batch.slice(4000, 4096)
+    want, _ = reference.correct_windows(sample, threads=32)
+    for w in range(96):
+        assert a.consensus(4000 + w) == want.consensus(w)
+        assert a.solid(4000 + w) == want.solid(w)
+    # work counters of the run equal the oracle's on the same windows (the inputs of the algorithmic-byte model)
+    oracle.lib.oracle_reset_counters()
+    oracle.correct_windows(sample, threads=1)
+    oc = oracle.counters()
+    c2 = gpu()
+    c2.correct_windows(sample)
+    gc = c2.counters()
+    for key in ("alignments", "dp_cells", "dp_pred_cells", "poa_graphs", "anchors", "solid_kmers", "consensus_bytes"):
+        assert gc[key] == oc[key], key
