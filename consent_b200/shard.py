@@ -51,16 +51,29 @@ class _Flat:
 
 def _from_parts(parts) -> Results:
     out = Results.__new__(Results)
+    out._r = out._free = None
     cons_len = np.concatenate([p.cons_len for p in parts]) if parts else np.zeros(0, np.int64)
     solid_len = np.concatenate([p.solid_len for p in parts]) if parts else np.zeros(0, np.int64)
     out.n_windows = int(len(cons_len))
     out.cons_off = np.concatenate([[0], np.cumsum(cons_len)]).astype(np.uint64)
     out.solid_off = np.concatenate([[0], np.cumsum(solid_len)]).astype(np.uint64)
-    out.cons = np.concatenate([p.cons for p in parts]).astype(np.uint8) if parts else np.zeros(0, np.uint8)
-    out.status = np.concatenate([p.status for p in parts]).astype(np.uint8) if parts else np.zeros(0, np.uint8)
-    out.solid_kmer = np.concatenate([p.solid_kmer for p in parts]).astype(np.uint32) if parts else np.zeros(0, np.uint32)
-    out.solid_count = np.concatenate([p.solid_count for p in parts]).astype(np.uint32) if parts else np.zeros(0, np.uint32)
+    out.cons = np.concatenate([p.cons for p in parts]) if parts else np.zeros(0, np.uint8)
+    out.status = np.concatenate([p.status for p in parts]) if parts else np.zeros(0, np.uint8)
+    out.solid_kmer = np.concatenate([p.solid_kmer for p in parts]) if parts else np.zeros(0, np.uint32)
+    out.solid_count = np.concatenate([p.solid_count for p in parts]) if parts else np.zeros(0, np.uint32)
     return out
+
+
+_PINNED = {}          # (tag, device index) -> pinned host staging tensor, grown on demand and reused across calls
+
+
+def _pinned(tag: str, nbytes: int):
+    import torch
+    t = _PINNED.get(tag)
+    if t is None or t.numel() < nbytes:
+        t = torch.empty(max(nbytes, 1) + max(nbytes, 1) // 4, dtype=torch.uint8, pin_memory=True)
+        _PINNED[tag] = t
+    return t
 
 
 def gather_results(local: Results, device=None, group=None, with_solid: bool = True):
@@ -78,37 +91,52 @@ def gather_results(local: Results, device=None, group=None, with_solid: bool = T
     rank = dist.get_rank(group)
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    on_gpu = torch.device(device).type == "cuda"
     f = _Flat(local)
     if not with_solid:
         f.solid_len = np.zeros_like(f.solid_len)
         f.solid_kmer = np.zeros(0, np.uint32)
         f.solid_count = np.zeros(0, np.uint32)
     # one byte payload per rank: [cons_len i64][solid_len i64][status u8][cons u8][solid_kmer u32][solid_count u32]
-    chunks = [f.cons_len.view(np.uint8), f.solid_len.view(np.uint8), f.status.view(np.uint8), f.cons.view(np.uint8),
-              np.ascontiguousarray(f.solid_kmer).view(np.uint8), np.ascontiguousarray(f.solid_count).view(np.uint8)]
-    payload = np.concatenate([np.ascontiguousarray(c).reshape(-1) for c in chunks]) if local.n_windows else np.zeros(0, np.uint8)
-    meta = torch.tensor([local.n_windows, len(f.cons), len(f.solid_kmer), len(payload)], dtype=torch.int64, device=device)
+    chunks = [np.ascontiguousarray(c).reshape(-1).view(np.uint8) for c in
+              (f.cons_len, f.solid_len, f.status, f.cons, f.solid_kmer, f.solid_count)] if local.n_windows else []
+    nbytes = int(sum(len(c) for c in chunks))
+    meta = torch.tensor([local.n_windows, len(f.cons), len(f.solid_kmer), nbytes], dtype=torch.int64, device=device)
     metas = [torch.zeros_like(meta) for _ in range(world)]
     dist.all_gather(metas, meta, group=group)
-    max_len = max(int(m[3]) for m in metas)
-    buf = torch.zeros(max(max_len, 1), dtype=torch.uint8, device=device)
-    if len(payload):
-        buf[:len(payload)] = torch.from_numpy(payload).to(device)
-    gathered = [torch.zeros_like(buf) for _ in range(world)] if rank == 0 else None
+    metas = [[int(x) for x in m.tolist()] for m in metas]
+    max_len = max(max(m[3] for m in metas), 1)
+    buf = torch.empty(max_len, dtype=torch.uint8, device=device)
+    o = 0
+    for c in chunks:                                    # straight from the (pinned) result buffers into the send buffer
+        if len(c):
+            buf[o:o + len(c)].copy_(torch.from_numpy(c), non_blocking=on_gpu)
+        o += len(c)
+    gathered = [torch.empty(max_len, dtype=torch.uint8, device=device) for _ in range(world)] if rank == 0 else None
     dist.gather(buf, gathered, dst=0, group=group)
     if rank != 0:
         return None
     parts = []
     for r in range(world):
-        nw, nc, ns, nbytes = (int(x) for x in metas[r])
-        raw = gathered[r][:nbytes].cpu().numpy()
+        nw, nc, ns, nb = metas[r]
+        if on_gpu:
+            host = _pinned(f"recv{r}", nb)[:nb]
+            host.copy_(gathered[r][:nb], non_blocking=True)
+        else:
+            host = gathered[r][:nb]
+        parts.append((nw, nc, ns, host))
+    if on_gpu:
+        torch.cuda.current_stream().synchronize()
+    flats = []
+    for nw, nc, ns, host in parts:
+        raw = host.numpy()
         p = _Flat.__new__(_Flat)
         o = 0
-        p.cons_len = raw[o:o + 8 * nw].view(np.int64).copy(); o += 8 * nw
-        p.solid_len = raw[o:o + 8 * nw].view(np.int64).copy(); o += 8 * nw
-        p.status = raw[o:o + nw].copy(); o += nw
-        p.cons = raw[o:o + nc].copy(); o += nc
-        p.solid_kmer = raw[o:o + 4 * ns].view(np.uint32).copy(); o += 4 * ns
-        p.solid_count = raw[o:o + 4 * ns].view(np.uint32).copy(); o += 4 * ns
-        parts.append(p)
-    return _from_parts(parts)
+        p.cons_len = raw[o:o + 8 * nw].view(np.int64); o += 8 * nw
+        p.solid_len = raw[o:o + 8 * nw].view(np.int64); o += 8 * nw
+        p.status = raw[o:o + nw]; o += nw
+        p.cons = raw[o:o + nc]; o += nc
+        p.solid_kmer = raw[o:o + 4 * ns].view(np.uint32); o += 4 * ns
+        p.solid_count = raw[o:o + 4 * ns].view(np.uint32); o += 4 * ns
+        flats.append(p)
+    return _from_parts(flats)
