@@ -254,13 +254,13 @@ def main():
     for _ in range(max(1, args.warmup - 1)):
         res = cor.correct_windows(batch)
         if world > 1:
-            gather_results(res, with_solid=False)
+            gather_results(res, with_solid=False, concat=False)
     barrier()
     e0 = time.perf_counter()
     for _ in range(args.steps):
         res = cor.correct_windows(batch)
         if world > 1:
-            gather_results(res, with_solid=False)        # the corrected windows, in input order, to rank 0 (NCCL)
+            gather_results(res, with_solid=False, concat=False)   # the corrected windows, in input order, to rank 0 (NCCL)
     barrier()
     e2e_s = time.perf_counter() - e0
     t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")

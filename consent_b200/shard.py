@@ -76,14 +76,37 @@ def _pinned(tag: str, nbytes: int):
     return t
 
 
-def gather_results(local: Results, device=None, group=None, with_solid: bool = True):
+class GatheredParts:
+    """What rank 0 holds after gather_results(..., concat=False): one part per rank, in input order, as views into the
+    receive buffers (nothing is concatenated; valid until the next gather).  Enough for the ordered writer:
+    `for w in range(g.n_windows): g.consensus(w)`."""
+
+    def __init__(self, flats):
+        self.parts = flats
+        self.first = np.concatenate([[0], np.cumsum([len(p.cons_len) for p in flats])]).astype(np.int64)
+        self.n_windows = int(self.first[-1])
+        self._offs = [np.concatenate([[0], np.cumsum(p.cons_len)]) for p in flats]
+
+    def consensus(self, w: int) -> str:
+        r = int(np.searchsorted(self.first, w, side="right")) - 1
+        i = w - int(self.first[r])
+        o = self._offs[r]
+        return self.parts[r].cons[int(o[i]):int(o[i + 1])].tobytes().decode()
+
+    def status(self, w: int) -> int:
+        r = int(np.searchsorted(self.first, w, side="right")) - 1
+        return int(self.parts[r].status[w - int(self.first[r])])
+
+
+def gather_results(local: Results, device=None, group=None, with_solid: bool = True, concat: bool = True):
     """Ordered gather of every rank's results to rank 0 (variable length: sizes first, then padded payloads).
 
     Returns the concatenated Results on rank 0, None elsewhere.  `device`: torch device of the payload tensors
     ("cuda:N" under NCCL, "cpu" under gloo).  with_solid=False gathers what the reference finally emits — the
     corrected sequences and their status — and leaves the solid k-mer lists on the rank that computed them: their only
     consumer is that rank's own re-anchoring of the window consensuses (src/correctionAlignment.cpp:6-15,103-104),
-    and at 150-deep piles they are 50x the bytes of the consensuses."""
+    and at 150-deep piles they are 50x the bytes of the consensuses.  concat=False returns GatheredParts (views, no
+    concatenation on rank 0)."""
     import torch
     import torch.distributed as dist
 
@@ -139,4 +162,4 @@ def gather_results(local: Results, device=None, group=None, with_solid: bool = T
         p.solid_kmer = raw[o:o + 4 * ns].view(np.uint32); o += 4 * ns
         p.solid_count = raw[o:o + 4 * ns].view(np.uint32); o += 4 * ns
         flats.append(p)
-    return _from_parts(flats)
+    return _from_parts(flats) if concat else GatheredParts(flats)

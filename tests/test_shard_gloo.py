@@ -32,6 +32,11 @@ if rank == 0:
     print("GATHER_OK", full.n_windows)
 else:
     assert full is None
+parts = gather_results(local, with_solid=False, concat=False)
+if rank == 0:
+    assert parts.n_windows == want.n_windows
+    assert all(parts.consensus(w) == want.consensus(w) and parts.status(w) == int(want.status[w]) for w in range(want.n_windows))
+    print("PARTS_OK")
 dist.barrier()
 dist.destroy_process_group()
 """
@@ -64,4 +69,4 @@ def test_gather_world_size_2_gloo(entry, tmp_path):
              for r in range(2)]
     outs = [p.communicate(timeout=300)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), "\n".join(outs)
-    assert "GATHER_OK 11" in outs[0]
+    assert "GATHER_OK 11" in outs[0] and "PARTS_OK" in outs[0]
