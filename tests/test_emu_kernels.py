@@ -75,6 +75,13 @@ def test_emulated_poa_tier_overflow_requeues_jobs(emu, oracle):
     assert e.value.code == -6
 
 
+def test_emulated_deep_piles(emu, oracle):
+    # > 256 sequences (k_split's general path) and > 81 920 k-mer occurrences (k_index's direct-count path)
+    batch = concat([synth_windows(1, 300, seed=81), synth_windows(1, 40, seed=82)])
+    want, _ = oracle.correct_windows(batch, threads=4)
+    assert_same(emu().correct_windows(batch), want, "300-deep pile")
+
+
 def test_emulated_errors(emu):
     cor = emu()
     with pytest.raises(ConsentError) as e:

@@ -180,3 +180,16 @@ def test_gpu_config3_stream_is_invariant_under_scheduling(gpu, oracle, reference
     gc = c2.counters()
     for key in ("alignments", "dp_cells", "dp_pred_cells", "poa_graphs", "anchors", "solid_kmers", "consensus_bytes"):
         assert gc[key] == oc[key], key
+
+
+def test_gpu_polishing_depth_piles(gpu, oracle):
+    """CONSENT-polish piles are far deeper than the corrector's 150 (maxSupport 20000, CONSENT-polish:42-43): more than
+    256 sequences (k_split's general path), more than 81 920 k-mer occurrences (k_index's direct-count path, pile too big
+    for shared memory), hundreds of segments per region (wide POA tiers)."""
+    batch = concat([synth_windows(3, 400, seed=91), synth_windows(2, 300, seed=92, profile="ONT"),
+                    Batch.from_piles([synth_windows(1, 150, seed=93).pile(0)[:1] + [s[:200] for s in synth_windows(8, 150, seed=94).pile(0)] * 6])])
+    want, _ = oracle.correct_windows(batch, threads=32)
+    assert_same(gpu().correct_windows(batch), want, "polishing-depth piles")
+    deep = synth_windows(1, 1200, seed=95)
+    want, _ = oracle.correct_windows(deep, threads=4)
+    assert_same(gpu().correct_windows(deep), want, "1200-deep pile")
