@@ -93,3 +93,20 @@ def test_emulated_errors(emu):
     with pytest.raises(ConsentError) as e:
         cor.correct_windows(Batch.from_piles([["A" * 7000, "ACGT"]]))
     assert e.value.code == -6                               # CG_ERR_CAPACITY: stated limit
+
+
+def test_emulated_lifetime_and_empty_batch(emu):
+    import numpy as np
+    cor = emu()
+    empty = Batch(np.zeros(1, np.uint32), np.zeros(1, np.uint64), np.zeros(1, np.uint8))
+    r = cor.correct_windows(empty)
+    assert r.n_windows == 0 and list(r.cons_off) == [0] and list(r.solid_off) == [0]
+    b = synth_windows(3, 5, seed=1)
+    r1 = cor.correct_windows(b)
+    r2 = cor.correct_windows(b)                      # two result sets alive at once (the pool grows), same content
+    assert r1.equals(r2)
+    text = r1.consensus(0)
+    cor.close()                                      # results outlive their corrector: freed when they die
+    assert r1.consensus(0) == text and r2.consensus(2) == r1.consensus(2)
+    own = r2.detach()
+    assert own.consensus(0) == text

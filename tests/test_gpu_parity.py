@@ -193,3 +193,24 @@ def test_gpu_polishing_depth_piles(gpu, oracle):
     deep = synth_windows(1, 1200, seed=95)
     want, _ = oracle.correct_windows(deep, threads=4)
     assert_same(gpu().correct_windows(deep), want, "1200-deep pile")
+
+
+def test_gpu_two_handles_in_two_threads(gpu, oracle):
+    """The ABI is re-entrant per handle (the reference call is made from --nproc threads, src/CONSENT-correction.cpp:76-111)."""
+    import threading
+    batches = [synth_windows(300, 20, seed=97), synth_windows(120, 150, seed=98)]
+    wants = [oracle.correct_windows(b, threads=16)[0] for b in batches]
+    got = [None, None]
+
+    def work(i):
+        cor = gpu(chunk_max_windows=64)
+        for _ in range(2):
+            got[i] = cor.correct_windows(batches[i]).detach()
+        cor.close()
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    for i in range(2):
+        assert_same(got[i], wants[i], f"handle {i} run beside another handle")
