@@ -88,6 +88,7 @@ template <class IdT_, int STORE_, u32 VCAP_, u32 HCELLS_, u32 LCAP_, u32 SEGCAP_
     static constexpr int STORE = STORE_;
     static constexpr bool SMEM = STORE_ != CG_P2_ALL_GLOBAL;            // the graph is in shared memory
     static constexpr bool H_SMEM = STORE_ == CG_P2_ALL_SMEM;            // ... and so is the score matrix
+    static constexpr bool POSTPASS_MAX = H_SMEM;                         // then the maximum cell is found after the DP, else row by row
     static constexpr u32 VCAP = VCAP_, HCELLS = HCELLS_, LCAP = LCAP_, SEGCAP = SEGCAP_, WARPS = WARPS_, CTAS_PER_SM = CTAS_;
     static constexpr u32 SCAP = 3 * VCAP_ + 8, ALNCAP = VCAP_ + LCAP_;
     static constexpr u32 SEQCAP = LCAP_ < 512u ? LCAP_ : 512u;        // segments up to this long are staged next to the graph
@@ -478,55 +479,64 @@ __device__ __forceinline__ i32 cg_poa2_dp2(const CgPoa2G<T>& s, u32 V, const u8*
     return lo > hi ? lo : hi;
 }
 
-// Any length: chunks of 32 columns, every row read back from the stored matrix.
+// Any length: packed chunks of 64 columns, every row read back from the stored matrix (the wide tiers' long segments).
 template <class T>
 __device__ __forceinline__ i32 cg_poa2_dp_any(const CgPoa2G<T>& s, u32 V, const u8* seq, u32 L, u32 Ws, CgPoa2Max& trk) {
     CG_P2_TYPES;
+    static_assert(9u * T::LCAP + 64u < 32767u, "packed 16-bit DP: score (<= 5 L) + 4 j must fit a signed halfword");
     const u32 lane = cg_lane(), Wd = L + 1;
     i16* H = s.H();
-    for (u32 j = lane; j < Wd; j += 32) H[j] = 0;
+    for (u32 j = lane; j < Ws; j += 32) H[j] = 0;
     __syncwarp();
-    i32 bv = 0;
+    u32 bv2 = 0;
     for (u32 r = 0; r < V; ++r) {
         const u32 d = (u32)s.rdesc(r);
-        const u8 ch = (u8)(d & 0xffu);
+        const u32 ch = d & 0xffu;
         const u32 deg = (d >> 8) & 0xffu, np = deg ? deg : 1u;
         const VecT pr = s.prow(r);
-        i16* row = H + (size_t)(r + 1) * Ws;
-        if (lane == 0) row[0] = 0;
-        i32 carry = 0, rowmax = 0;
-        for (u32 jb = 1; jb < Wd; jb += 32) {
-            const u32 j = jb + lane;
-            const bool act = j < Wd;
-            i32 val = 0;
+        u32* row = (u32*)(H + (size_t)(r + 1) * Ws);
+        u32 carry = 0, rowmax = 0;
+        for (u32 jb = 0; jb < Wd; jb += 64) {
+            const u32 j0 = jb + 2 * lane, j1 = j0 + 1;
+            const bool act = j0 < Wd;
+            u32 val = 0;
             if (act) {
-                const i32 sc = seq[j - 1] == ch ? 5 : -10;
+                const u32 q0 = j0 >= 1 ? seq[j0 - 1] : 0u, q1 = j1 < Wd ? seq[j1 - 1] : 0u;
+                const u32 sc = (q0 == ch ? 5u : 0xfff6u) | (q1 == ch ? 0x00050000u : 0xfff60000u);
+#pragma unroll 1
                 for (u32 e = 0; e < np; ++e) {
-                    const i16* prow = H + (size_t)(deg ? Pk::get(pr, e) : 0u) * Ws;
-                    const i32 a = (i32)prow[j - 1] + sc, b = (i32)prow[j] - 4;
-                    const i32 m = a > b ? a : b;
-                    val = m > val ? m : val;
+                    const i16* prow = H + (size_t)(deg ? Pk::get(pr, e) : 0u) * Ws + j0;
+                    const u32 h01 = *(const u32*)prow;
+                    const u32 hm1 = j0 == 0 ? 0u : (u32)(u16)prow[-1];
+                    val = cg_vmax2(val, cg_viaddmax2_relu(hm1 | (h01 << 16), sc, cg_vadd2(h01, 0xfffcfffcu)));
                 }
             }
-            i32 u = val + 4 * (i32)j;
+            const u32 keep = j0 == 0 ? 0xffff0000u : 0xffffffffu;
+            const u32 j4 = (4 * j0) | ((4 * j1) << 16), nj4 = ((0u - 4 * j0) & 0xffffu) | ((0u - 4 * j1) << 16);
+            u32 u = cg_vadd2(val & keep, j4);
+            u = cg_vmax2(u, u << 16);
+            u32 x = __byte_perm(u, 0, 0x3232);
 #pragma unroll
-            for (int dd = 1; dd < 32; dd <<= 1) {
-                const i32 o = __shfl_up_sync(CG_FULL, u, dd);
-                u = o > u ? o : u;
-            }
-            u = u > carry ? u : carry;
-            carry = __shfl_sync(CG_FULL, u, 31);
+            for (int dd = 1; dd < 32; dd <<= 1) x = cg_vmax2(x, __shfl_up_sync(CG_FULL, x, dd));
+            u32 e2 = __shfl_up_sync(CG_FULL, x, 1);
+            if (lane == 0) e2 = 0;
+            e2 = cg_vmax2(e2, carry);
+            carry = cg_vmax2(carry, __shfl_sync(CG_FULL, x, 31));
+            const u32 h = cg_vadd2(cg_vmax2(u, e2), nj4) & keep;
             if (act) {
-                const i32 h = u - 4 * (i32)j;
-                row[j] = (i16)h;
-                bv = h > bv ? h : bv;
-                rowmax = h > rowmax ? h : rowmax;
+                row[jb / 2 + lane] = h;
+                const u32 hm = h & ((j0 < Wd ? 0xffffu : 0u) | (j1 < Wd ? 0xffff0000u : 0u));
+                if (T::POSTPASS_MAX) bv2 = cg_vmax2(bv2, hm); else rowmax = cg_vmax2(rowmax, hm);
             }
         }
-        if (!T::H_SMEM) cg_poa2_track(trk, rowmax, r + 1);
+        if (!T::POSTPASS_MAX) {
+            const u32 lo = rowmax & 0xffffu, hi = rowmax >> 16;
+            cg_poa2_track(trk, (i32)(lo > hi ? lo : hi), r + 1);
+        }
         __syncwarp();
     }
-    return bv;
+    const i32 lo = (i32)(i16)(bv2 & 0xffffu), hi = (i32)(i16)(bv2 >> 16);
+    return lo > hi ? lo : hi;
 }
 
 // Where is the maximum M (> 0)?  Lanes over rows, each scanning its row.  Returns the number of rows that hold M; if it is
@@ -613,7 +623,8 @@ __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s
             else if (L <= 63) bv = cg_poa2_dp2<1>(s, V, seq, L, Ws, trk);
             else if (T::LCAP > 63 && L <= 127) bv = cg_poa2_dp2<(T::LCAP > 63 ? 2 : 1)>(s, V, seq, L, Ws, trk);
             else if (T::LCAP > 127 && L <= 255) bv = cg_poa2_dp2<(T::LCAP > 127 ? 4 : 1)>(s, V, seq, L, Ws, trk);
-            else if (T::LCAP > 255) bv = cg_poa2_dp_any(s, V, seq, L, Ws, trk);
+            else if (T::LCAP > 255 && L <= 511) bv = cg_poa2_dp2<(T::LCAP > 255 ? 8 : 1)>(s, V, seq, L, Ws, trk);
+            else if (T::LCAP > 511) bv = cg_poa2_dp_any(s, V, seq, L, Ws, trk);
             else bv = 0;
             j_aln += 1; j_cells += (u64)(V + 1) * L; j_pred += (u64)sumdeg * L;
             i32 M;
