@@ -36,6 +36,13 @@ def reference(entry):
 
 
 @pytest.fixture(scope="session")
+def example_golden():
+    """Reference outputs on 300 real-data windows of the shipped example (tests/golden/make_example_golden.py)."""
+    with open(os.path.join(ROOT, "tests", "golden", "example_golden.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="session")
 def golden():
     with open(os.path.join(ROOT, "tests", "golden", "golden.json")) as f:
         return json.load(f)

@@ -15,6 +15,29 @@ def solid_digest(res, w):
     return h.hexdigest()[:24]
 
 
+def example_piles():
+    """The 300 real-data piles of tests/golden/example_windows.txt.gz (pile[0] = template)."""
+    import gzip
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "example_windows.txt.gz")
+    piles, left = [], 0
+    with gzip.open(path, "rt") as f:
+        for line in f:
+            line = line.rstrip("\n")
+            if left == 0:
+                assert line.startswith("W "), line[:20]
+                left = int(line[2:])
+                piles.append([])
+            else:
+                piles[-1].append(line)
+                left -= 1
+    return piles
+
+
+def example_batch():
+    return Batch.from_piles(example_piles())
+
+
 def golden_batch(case):
     """(Batch, Params) of a golden case."""
     p = Params(**case["params"])

@@ -110,3 +110,11 @@ def test_emulated_lifetime_and_empty_batch(emu):
     assert r1.consensus(0) == text and r2.consensus(2) == r1.consensus(2)
     own = r2.detach()
     assert own.consensus(0) == text
+
+
+def test_emulated_kernels_on_real_piles(emu, example_golden):
+    from tests.helpers import assert_matches_golden, example_piles
+    piles = example_piles()[:60]
+    res = emu().correct_windows(Batch.from_piles(piles))
+    case = {k: (v[:60] if isinstance(v, list) else v) for k, v in example_golden.items()}
+    assert_matches_golden(res, case)

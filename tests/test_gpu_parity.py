@@ -214,3 +214,12 @@ def test_gpu_two_handles_in_two_threads(gpu, oracle):
         t.join()
     for i in range(2):
         assert_same(got[i], wants[i], f"handle {i} run beside another handle")
+
+
+def test_gpu_matches_reference_on_real_piles(gpu, example_golden):
+    """BASELINE config 1 shape: 300 windows of the shipped example/reads.fasta (piles cut by the reference's own
+    minimap2 + alignmentPiles/alignmentWindows code, outputs of the unmodified reference committed as a fixture)."""
+    from tests.helpers import assert_matches_golden, example_batch
+    batch = example_batch()
+    assert_matches_golden(gpu().correct_windows(batch), example_golden)
+    assert_matches_golden(gpu(chunk_max_windows=37, lanes=2).correct_windows(batch), example_golden)
