@@ -47,6 +47,31 @@ class cg_results(C.Structure):
                 ("owner_", C.c_void_p)]
 
 
+class cg_reads(C.Structure):
+    _fields_ = [("n_reads", C.c_uint32),
+                ("read_win_begin", C.POINTER(C.c_uint32)),
+                ("read_off", C.POINTER(C.c_uint64)),
+                ("read_bases", C.c_char_p),
+                ("win_pos", C.POINTER(C.c_uint32)),
+                ("window_size", C.c_uint32),
+                ("window_overlap", C.c_uint32)]
+
+
+class cg_corrected(C.Structure):
+    _fields_ = [("n_reads", C.c_uint32),
+                ("read_off", C.POINTER(C.c_uint64)),
+                ("bases", C.POINTER(C.c_char)),
+                ("owner_", C.c_void_p)]
+
+
+class cg_synth_read_spec(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("first_read", C.c_uint32), ("n_reads", C.c_uint32),
+                ("n_seqs", C.c_uint32), ("truth_len", C.c_uint32),
+                ("window_size", C.c_uint32), ("window_overlap", C.c_uint32),
+                ("thin_every", C.c_uint32), ("thin_seqs", C.c_uint32),
+                ("err", C.c_double), ("p_sub", C.c_double), ("p_ins", C.c_double)]
+
+
 class cg_counters(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "windows", "sequences", "bases", "anchors", "regions", "poa_graphs", "alignments",
@@ -131,6 +156,93 @@ class Batch:
                         self.win_seq_begin.ctypes.data_as(C.POINTER(C.c_uint32)),
                         self.seq_off.ctypes.data_as(C.POINTER(C.c_uint64)),
                         C.cast(self.bases.ctypes.data, C.c_char_p))
+
+
+class Reads:
+    """R reads and the windows cut from them, in the flat layout of cg_reads (host memory, numpy-owned).
+    Read r owns windows [read_win_begin[r], read_win_begin[r+1]) of the window batch it travels with."""
+
+    def __init__(self, read_win_begin, read_off, read_bases, win_pos, window_size: int = 500, window_overlap: int = 50):
+        self.read_win_begin = np.ascontiguousarray(read_win_begin, dtype=np.uint32)
+        self.read_off = np.ascontiguousarray(read_off, dtype=np.uint64)
+        self.read_bases = np.ascontiguousarray(read_bases, dtype=np.uint8)
+        self.win_pos = np.ascontiguousarray(win_pos, dtype=np.uint32)
+        if len(self.read_bases) == 0:
+            self.read_bases = np.zeros(1, np.uint8)
+        if len(self.win_pos) == 0:
+            self.win_pos = np.zeros(1, np.uint32)
+        self.window_size, self.window_overlap = int(window_size), int(window_overlap)
+        assert len(self.read_off) == len(self.read_win_begin)
+
+    @property
+    def n_reads(self) -> int:
+        return len(self.read_win_begin) - 1
+
+    @property
+    def n_windows(self) -> int:
+        return int(self.read_win_begin[-1])
+
+    @classmethod
+    def from_lists(cls, reads, windows_per_read, win_pos, window_size=500, window_overlap=50) -> "Reads":
+        rwb, off = [0], [0]
+        for s, n in zip(reads, windows_per_read):
+            rwb.append(rwb[-1] + n)
+            off.append(off[-1] + len(s))
+        raw = "".join(reads).encode()
+        return cls(np.array(rwb, np.uint32), np.array(off, np.uint64), np.frombuffer(raw, np.uint8).copy(),
+                   np.array(win_pos, np.uint32), window_size, window_overlap)
+
+    def read(self, r: int) -> str:
+        return self.read_bases[int(self.read_off[r]):int(self.read_off[r + 1])].tobytes().decode()
+
+    def c(self) -> cg_reads:
+        return cg_reads(self.n_reads, self.read_win_begin.ctypes.data_as(C.POINTER(C.c_uint32)),
+                        self.read_off.ctypes.data_as(C.POINTER(C.c_uint64)),
+                        C.cast(self.read_bases.ctypes.data, C.c_char_p),
+                        self.win_pos.ctypes.data_as(C.POINTER(C.c_uint32)),
+                        self.window_size, self.window_overlap)
+
+
+class Corrected:
+    """Host copy of cg_corrected: the re-anchored reads (upper case = replaced by a consensus)."""
+
+    def __init__(self, c: cg_corrected):
+        R = int(c.n_reads)
+        self.n_reads = R
+        self.read_off = np.ctypeslib.as_array(c.read_off, shape=(R + 1,)).copy()
+        nb = int(self.read_off[-1])
+        self.bases = (np.ctypeslib.as_array(C.cast(c.bases, C.POINTER(C.c_uint8)), shape=(nb,)).copy()
+                      if nb else np.zeros(0, np.uint8))
+
+    def read(self, r: int) -> str:
+        return self.bases[int(self.read_off[r]):int(self.read_off[r + 1])].tobytes().decode()
+
+    def equals(self, other: "Corrected") -> bool:
+        return (self.n_reads == other.n_reads and np.array_equal(self.read_off, other.read_off)
+                and np.array_equal(self.bases, other.bases))
+
+    def first_mismatch(self, other: "Corrected"):
+        for r in range(min(self.n_reads, other.n_reads)):
+            if self.read(r) != other.read(r):
+                return r
+        return None if self.n_reads == other.n_reads else min(self.n_reads, other.n_reads)
+
+    def digest(self) -> str:
+        import hashlib
+        h = hashlib.sha256()
+        h.update(np.ascontiguousarray(self.read_off).tobytes())
+        h.update(np.ascontiguousarray(self.bases).tobytes())
+        return h.hexdigest()
+
+
+def results_to_c(res: "Results") -> cg_results:
+    """A cg_results view of a (numpy-backed) Results, for calls that take results as input."""
+    def ptr(a, t):
+        a = a if len(a) else np.zeros(1, a.dtype)
+        return a.ctypes.data_as(C.POINTER(t))
+    return cg_results(res.n_windows, ptr(res.cons_off, C.c_uint64), C.cast(ptr(res.cons, C.c_uint8), C.POINTER(C.c_char)),
+                      ptr(res.status, C.c_uint8), ptr(res.solid_off, C.c_uint64), ptr(res.solid_kmer, C.c_uint32),
+                      ptr(res.solid_count, C.c_uint32), None)
 
 
 class Results:

@@ -25,6 +25,7 @@
 #include "k_poa.cuh"
 #include "k_poa2.cuh"
 #include "k_polish.cuh"
+#include "k_reanchor.cuh"
 
 struct DevBuf {
     void* p = nullptr;
@@ -71,6 +72,7 @@ struct HostResults {
     size_t capW = 0, capC = 0, capS = 0;
     struct cg_handle* owner = nullptr;
     bool in_use = false, orphan = false;
+    u64 gen = 0;            // cg_handle::run_gen when these results were produced (re-anchoring reuses the device copies)
 };
 
 // One timed stage = a pair of events on the lane's stream; collected after the final sync of cg_run.
@@ -149,7 +151,16 @@ struct cg_handle {
     cudaEvent_t ev_run0 = nullptr;
     u32 stage_launches[CG_N_STAGES]{};
     cg_counters counters{};
+    // re-anchoring (cg_reanchor_reads)
+    u64 run_gen = 0;              // bumped by every upload: results of an older batch are no longer resident
+    DevBuf ra_cons, ra_cons_off, ra_solid_off, ra_sk, ra_tpl, ra_tpl_off;           // copies, when the results are not resident
+    DevBuf ra_rwb, ra_roff, ra_rbases, ra_wpos, ra_order, ra_head_off, ra_head, ra_len, ra_out_off, ra_out, ra_scratch, ra_ctl;
+    float ra_ms = 0;
+    u64 ra_cells = 0;
 };
+
+// Host copy of the corrected reads (pinned).
+struct HostCorrected { u64* off = nullptr; char* bases = nullptr; };
 
 namespace {
 
@@ -650,7 +661,10 @@ void cg_destroy(cg_handle* h) {
         for (cudaStream_t st : {L.stream, L.s_tail, L.s_poa[0], L.s_poa[1], L.s_poa[2]}) if (st) cudaStreamDestroy(st);
         if (L.h_ctl) cudaFreeHost(L.h_ctl);
     }
-    DevBuf* bufs[] = {&h->d_bases, &h->d_seq_off, &h->d_wsb, &h->o_cons, &h->o_sk, &h->o_sc, &h->o_status, &h->o_len, &h->o_nsol};
+    DevBuf* bufs[] = {&h->d_bases, &h->d_seq_off, &h->d_wsb, &h->o_cons, &h->o_sk, &h->o_sc, &h->o_status, &h->o_len, &h->o_nsol,
+                      &h->ra_cons, &h->ra_cons_off, &h->ra_solid_off, &h->ra_sk, &h->ra_tpl, &h->ra_tpl_off, &h->ra_rwb, &h->ra_roff,
+                      &h->ra_rbases, &h->ra_wpos, &h->ra_order, &h->ra_head_off, &h->ra_head, &h->ra_len, &h->ra_out_off, &h->ra_out,
+                      &h->ra_scratch, &h->ra_ctl};
     for (DevBuf* b : bufs) b->release();
     for (auto& t : h->tier) { t.mem.release(); t.desc.release(); }
     delete h;
@@ -689,6 +703,7 @@ int upload_impl(cg_handle* h, const cg_batch* in, bool wait) {
     cudaSetDevice(h->device);
     h->uploaded = h->ran = false;
     h->h2d_pending = false;
+    h->run_gen++;
     const u32 W = in->n_windows;
     const u64 n_seqs = in->win_seq_begin[W];
     const u32 k = h->p.mer_size;
@@ -852,6 +867,7 @@ void fill_results(cg_handle* h, HostResults* r, cg_results* out) {
     r->cons_off[W] = h->o_cons_n; r->solid_off[W] = h->o_solid_n;
     out->n_windows = W; out->cons_off = r->cons_off; out->cons = r->cons; out->status = r->status;
     out->solid_off = r->solid_off; out->solid_kmer = r->sk; out->solid_count = r->sc; out->owner_ = r;
+    r->gen = h->run_gen;
 }
 
 void give_back(cg_handle* h, HostResults* r) {
@@ -924,6 +940,172 @@ int cg_correct_windows(cg_handle* h, const cg_batch* in, cg_results* out) {
     if (rc == CG_OK && (!r->cons || !r->sk)) rc = host_results_reserve(h, r, 1, 1, 0, 0);      // zero windows
     if (rc != CG_OK) { give_back(h, r); return rc; }
     fill_results(h, r, out);
+    return CG_OK;
+}
+
+// ---- consensus re-anchoring: alignConsensus for every read of the batch ------------------------------
+int cg_reanchor_reads(cg_handle* h, const cg_batch* windows, const cg_results* cons, const cg_reads* reads, cg_corrected* out) {
+    if (!h || !out) return CG_ERR_INVALID_ARG;
+    if (!windows || !cons || !reads || !reads->read_win_begin || !reads->read_off || !windows->win_seq_begin || !windows->seq_off) {
+        h->err = "null argument"; return CG_ERR_INVALID_ARG;
+    }
+    cudaSetDevice(h->device);
+    const u32 W = cons->n_windows, R = reads->n_reads;
+    if (windows->n_windows != W || reads->read_win_begin[0] != 0 || reads->read_win_begin[R] != W) {
+        h->err = "windows, results and reads do not describe the same windows"; return CG_ERR_INVALID_ARG;
+    }
+    if (W && (!cons->cons_off || !cons->solid_off || !reads->win_pos)) { h->err = "null argument"; return CG_ERR_INVALID_ARG; }
+    if (R && !reads->read_bases) { h->err = "null argument"; return CG_ERR_INVALID_ARG; }
+    const u32 k = h->p.mer_size;
+    // are these the results of the batch still resident on this handle?
+    bool resident = false;
+    if (cons->owner_ && h->ran && h->W == W) {
+        std::lock_guard<std::mutex> lk(h->pool_mu);
+        for (HostResults* c : h->pool)
+            if ((void*)c == cons->owner_ && c->gen == h->run_gen && c->cons_off == cons->cons_off) resident = true;
+    }
+    // sizes: longest query, per-read capacity of the corrected read
+    u32 maxL = 16;
+    std::vector<u64> head_off((size_t)R + 1, 0);
+    std::vector<u64> tpl_off;
+    u64 tpl_bytes = 0;
+    if (!resident) tpl_off.assign((size_t)W + 1, 0);
+    for (u32 r = 0; r < R; ++r) {
+        const u32 w0 = reads->read_win_begin[r], w1 = reads->read_win_begin[r + 1];
+        if (w1 < w0 || reads->read_off[r + 1] < reads->read_off[r]) { h->err = "read offsets must be non-decreasing"; return CG_ERR_INVALID_ARG; }
+        u64 sum = 0;
+        for (u32 w = w0; w < w1; ++w) {
+            u64 len = cons->cons_off[w + 1] - cons->cons_off[w];
+            if (len < k) {                                                     // the raw template stands in (correctionAlignment.cpp:72-74)
+                const u32 s0 = windows->win_seq_begin[w];
+                len = windows->seq_off[s0 + 1] - windows->seq_off[s0];
+                if (!resident) { tpl_off[w + 1] = len; tpl_bytes += len; }
+            }
+            if (len > (u64)CG_RA_QMAX) { h->err = "a consensus is longer than 8000 bases"; return CG_ERR_CAPACITY; }
+            maxL = std::max<u32>(maxL, (u32)len);
+            sum += len;
+        }
+        const u64 rawLen = reads->read_off[r + 1] - reads->read_off[r];
+        if (rawLen >= (1ull << 31)) { h->err = "a read is longer than 2^31 bases"; return CG_ERR_CAPACITY; }
+        head_off[r + 1] = head_off[r] + round_up(rawLen + 2 * sum + 64, 16);
+    }
+    const u32 rmax = std::max<u32>(maxL, reads->window_size + 2 * reads->window_overlap);
+    if (rmax > 48 * 1024) { h->err = "window_size + 2 * window_overlap too large for the shared-memory reference buffer"; return CG_ERR_CAPACITY; }
+    std::vector<u32> order(R);
+    for (u32 r = 0; r < R; ++r) order[r] = r;
+    std::stable_sort(order.begin(), order.end(), [&](u32 a, u32 b) {
+        return reads->read_win_begin[a + 1] - reads->read_win_begin[a] > reads->read_win_begin[b + 1] - reads->read_win_begin[b];
+    });
+    cudaStream_t st = h->lane[0].stream;
+    const u64 n_rbases = R ? reads->read_off[R] : 0;
+    // ---- uploads
+    CK(h->ra_rwb.ensure(((size_t)R + 1) * 4)); CK(h->ra_roff.ensure(((size_t)R + 1) * 8)); CK(h->ra_rbases.ensure(n_rbases + 16));
+    CK(h->ra_wpos.ensure(((size_t)W + 1) * 4)); CK(h->ra_order.ensure(((size_t)R + 1) * 4)); CK(h->ra_head_off.ensure(((size_t)R + 1) * 8));
+    CK(h->ra_head.ensure(head_off[R] + 64)); CK(h->ra_len.ensure(((size_t)R + 1) * 4)); CK(h->ra_out_off.ensure(((size_t)R + 1) * 8));
+    CK(h->ra_ctl.ensure(64));
+    CK(cudaMemcpyAsync(h->ra_rwb.p, reads->read_win_begin, ((size_t)R + 1) * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->ra_roff.p, reads->read_off, ((size_t)R + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (n_rbases) CK(cudaMemcpyAsync(h->ra_rbases.p, reads->read_bases, n_rbases, cudaMemcpyHostToDevice, st));
+    if (W) CK(cudaMemcpyAsync(h->ra_wpos.p, reads->win_pos, (size_t)W * 4, cudaMemcpyHostToDevice, st));
+    if (R) CK(cudaMemcpyAsync(h->ra_order.p, order.data(), (size_t)R * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->ra_head_off.p, head_off.data(), ((size_t)R + 1) * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(h->ra_ctl.p, 0, 64, st));
+    CgReanchorArgs A{};
+    std::vector<char> tpl;
+    if (resident) {
+        const u64 tot_c = h->o_cons_n, tot_s = h->o_solid_n;                 // o_len / o_nsol hold the W start offsets: close them
+        CK(cudaMemcpyAsync(h->o_len.as<u64>() + W, &tot_c, 8, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(h->o_nsol.as<u64>() + W, &tot_s, 8, cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));                                       // tot_c / tot_s live on this stack frame
+        A.cons = h->o_cons.as<char>(); A.cons_off = h->o_len.as<u64>(); A.solid_off = h->o_nsol.as<u64>(); A.solid_kmer = h->o_sk.as<u32>();
+        A.bases = h->d_bases.as<char>(); A.seq_off = h->d_seq_off.as<u64>(); A.win_seq_begin = h->d_wsb.as<u32>();
+    } else {
+        const u64 nc = cons->cons_off[W], ns = cons->solid_off[W];
+        for (u32 w = 0; w < W; ++w) tpl_off[w + 1] += tpl_off[w];
+        tpl.resize(tpl_bytes + 1);
+        for (u32 w = 0; w < W; ++w)
+            if (tpl_off[w + 1] > tpl_off[w])
+                memcpy(tpl.data() + tpl_off[w], windows->bases + windows->seq_off[windows->win_seq_begin[w]], tpl_off[w + 1] - tpl_off[w]);
+        CK(h->ra_cons.ensure(nc + 16)); CK(h->ra_cons_off.ensure(((size_t)W + 1) * 8)); CK(h->ra_solid_off.ensure(((size_t)W + 1) * 8));
+        CK(h->ra_sk.ensure(ns * 4 + 16)); CK(h->ra_tpl.ensure(tpl_bytes + 16)); CK(h->ra_tpl_off.ensure(((size_t)W + 1) * 8));
+        if (nc) CK(cudaMemcpyAsync(h->ra_cons.p, cons->cons, nc, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(h->ra_cons_off.p, cons->cons_off, ((size_t)W + 1) * 8, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(h->ra_solid_off.p, cons->solid_off, ((size_t)W + 1) * 8, cudaMemcpyHostToDevice, st));
+        if (ns) CK(cudaMemcpyAsync(h->ra_sk.p, cons->solid_kmer, ns * 4, cudaMemcpyHostToDevice, st));
+        if (tpl_bytes) CK(cudaMemcpyAsync(h->ra_tpl.p, tpl.data(), tpl_bytes, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(h->ra_tpl_off.p, tpl_off.data(), ((size_t)W + 1) * 8, cudaMemcpyHostToDevice, st));
+        A.cons = h->ra_cons.as<char>(); A.cons_off = h->ra_cons_off.as<u64>(); A.solid_off = h->ra_solid_off.as<u64>(); A.solid_kmer = h->ra_sk.as<u32>();
+        A.tpl = h->ra_tpl.as<char>(); A.tpl_off = h->ra_tpl_off.as<u64>();
+    }
+    // ---- scratch: resident warps, each with its buffers and a direction matrix for the banded sub-alignment
+    u32 ctas = std::min<u32>((R + CG_RA_WARPS - 1) / CG_RA_WARPS, (u32)h->sms * 4);
+    if (ctas == 0) ctas = 1;
+    u64 dir_cap = std::min<u64>((u64)maxL * maxL, 4ull << 20);
+    const u64 budget = 6ull << 30;
+    while ((cg_ra_fixed_bytes(maxL, rmax) + dir_cap) * ctas * CG_RA_WARPS > budget && ctas > (u32)h->sms) ctas = (ctas + 1) / 2;
+    const u64 stride = round_up(cg_ra_fixed_bytes(maxL, rmax) + dir_cap, 256);
+    CK(h->ra_scratch.ensure(stride * ctas * CG_RA_WARPS));
+    A.n_reads = R; A.order = h->ra_order.as<u32>(); A.read_win_begin = h->ra_rwb.as<u32>(); A.read_off = h->ra_roff.as<u64>();
+    A.read_bases = h->ra_rbases.as<char>(); A.win_pos = h->ra_wpos.as<u32>();
+    A.ws = reads->window_size; A.ov = reads->window_overlap; A.k = k;
+    A.head = h->ra_head.as<char>(); A.head_off = h->ra_head_off.as<u64>(); A.out_len = h->ra_len.as<u32>();
+    A.scratch = h->ra_scratch.as<u8>(); A.scratch_stride = stride; A.maxL = maxL; A.rmax = rmax; A.dir_cap = dir_cap;
+    A.ctl = h->ra_ctl.as<u32>();
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0, st));
+    if (R) CG_LAUNCH(k_reanchor, ctas, CG_RA_WARPS * 32, (size_t)CG_RA_WARPS * ((rmax + 15u) & ~15u), st, A);
+    CK(cudaEventRecord(e1, st));
+    CK(cudaGetLastError());
+    // ---- lengths -> dense offsets -> gather -> host
+    std::vector<u32> len((size_t)R + 1, 0);
+    u32 ctl[4] = {0, 0, 0, 0};
+    if (R) CK(cudaMemcpyAsync(len.data(), h->ra_len.p, (size_t)R * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ctl, h->ra_ctl.p, sizeof ctl, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaEventElapsedTime(&h->ra_ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    memcpy(&h->ra_cells, ctl + 2, 8);
+    if (ctl[1]) {
+        h->err = (ctl[1] & CG_RA_FLAG_CAPACITY) ? "re-anchoring: a window exceeds a capacity limit of this build (alignment region, consensus length or banded sub-alignment)"
+               : (ctl[1] & CG_RA_FLAG_TRACEBACK) ? "re-anchoring: the banded traceback left its matrix (undefined behaviour in the reference)"
+               : "re-anchoring: an alignment region is empty or nothing aligns (the reference does not survive this input either)";
+        return (ctl[1] & CG_RA_FLAG_CAPACITY) ? CG_ERR_CAPACITY : CG_ERR_INVALID_ARG;
+    }
+    HostCorrected* hc = new HostCorrected();
+    auto fail = [&](int rc) { if (hc->off) cudaFreeHost(hc->off); if (hc->bases) cudaFreeHost(hc->bases); delete hc; return rc; };
+    if (cudaMallocHost(&hc->off, ((size_t)R + 1) * 8) != cudaSuccess) { h->err = "out of pinned memory"; return fail(CG_ERR_OUT_OF_MEMORY); }
+    hc->off[0] = 0;
+    for (u32 r = 0; r < R; ++r) hc->off[r + 1] = hc->off[r] + len[r];
+    const u64 tot = hc->off[R];
+    if (cudaMallocHost(&hc->bases, tot + 1) != cudaSuccess) { h->err = "out of pinned memory"; return fail(CG_ERR_OUT_OF_MEMORY); }
+    cudaError_t e = h->ra_out.ensure(tot + 16);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h->ra_out_off.p, hc->off, ((size_t)R + 1) * 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && R && tot) {
+        CG_LAUNCH(k_reanchor_gather, std::min<u32>(R, (u32)h->sms * 8), 256, 0, st, (const char*)h->ra_head.as<char>(), (const u64*)h->ra_head_off.as<u64>(),
+                  (const u64*)h->ra_out_off.as<u64>(), h->ra_out.as<char>(), R);
+        e = cudaMemcpyAsync(hc->bases, h->ra_out.p, tot, cudaMemcpyDeviceToHost, st);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { h->err = std::string("re-anchoring download: ") + cudaGetErrorString(e); return fail(CG_ERR_CUDA); }
+    hc->bases[tot] = 0;
+    out->n_reads = R; out->read_off = hc->off; out->bases = hc->bases; out->owner_ = hc;
+    return CG_OK;
+}
+
+void cg_free_corrected(cg_corrected* c) {
+    if (!c || !c->owner_) return;
+    HostCorrected* hc = static_cast<HostCorrected*>(c->owner_);
+    c->owner_ = nullptr;
+    if (hc->off) cudaFreeHost(hc->off);
+    if (hc->bases) cudaFreeHost(hc->bases);
+    delete hc;
+}
+
+int cg_reanchor_stats(const cg_handle* h, float* kernel_ms, uint64_t* dp_cells) {
+    if (!h) return CG_ERR_INVALID_ARG;
+    if (kernel_ms) *kernel_ms = h->ra_ms;
+    if (dp_cells) *dp_cells = h->ra_cells;
     return CG_OK;
 }
 

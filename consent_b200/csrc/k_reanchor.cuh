@@ -1,0 +1,445 @@
+// k_reanchor.cuh — consensus re-anchoring on the device.
+//
+// Batched equivalent of alignConsensus (src/correctionAlignment.cpp:47-139): every window consensus of a read is
+// located on the progressively corrected read by a local alignment (StripedSmithWaterman::Aligner defaults, match 2 /
+// mismatch 2 / gap open 3 / gap extend 1: BMEAN/Complete-Striped-Smith-Waterman-Library/src/ssw_cpp.cpp:419-426,365-403,
+// ssw.c:788-850), overlaps with the previous window are arbitrated by solid k-mers (correctionAlignment.cpp:93-118)
+// and the aligned stretch of the read is replaced by the upper-cased consensus.
+//
+// Work layout: windows of one read depend on each other (each alignment sees the previous replacements), reads do
+// not -> ONE WARP PER READ, persistent warps pulling reads (longest first) from a counter.
+//
+// The local alignment itself (ssw.c's striped SSE2 kernels sw_sse2_byte/word :158-575) is re-cut for a warp: every
+// lane owns a block of up to CG_RA_RPL consecutive query rows whose H and E live in registers, reference columns
+// flow through the lanes as a skewed wavefront (lane l works on column t-l at step t) and the only communication is
+// one packed 32-bit shuffle per step carrying (H, F) of the block's last row and the column's base.  What the SSE2
+// kernels return besides the score is reproduced exactly: ref_end = first column whose maximum reaches the final
+// score, read_end = smallest query row holding it in that column (ssw.c:297-332), begin = the same scan over the
+// reversed query prefix and the reference prefix read backwards, first column reaching the score (ssw.c:836-850,318).
+// The CIGAR of the main alignment is never read by alignConsensus and is not computed; the one of the arbitration's
+// sub-alignment is needed only through its I/D totals (getIndels, correctionAlignment.cpp:28-45) and comes from a
+// faithful banded DP (banded_sw, ssw.c:577-758, band storage restated slot for slot because its edge handling is
+// observable) run by lane 0 — it touches a few thousand cells on ~10 % of the windows.
+#pragma once
+#include "cg_common.cuh"
+
+#define CG_RA_RPL 20u            // query rows per lane and band (640 rows per band)
+#define CG_RA_WARPS 4u           // warps per CTA
+#define CG_RA_QMAX 8000          // H must fit 14 bits of the wavefront message: 2 * rows <= 16383
+
+enum { CG_RA_FLAG_DEGENERATE = 16u, CG_RA_FLAG_CAPACITY = 32u, CG_RA_FLAG_TRACEBACK = 64u };
+
+struct CgReanchorArgs {
+    // per-window results of the correction path
+    const char* cons; const u64* cons_off; const u64* solid_off; const u32* solid_kmer;
+    // templates: the resident batch (bases / seq_off / win_seq_begin) or, when that is null, compact copies (tpl / tpl_off)
+    const char* bases; const u64* seq_off; const u32* win_seq_begin;
+    const char* tpl; const u64* tpl_off;
+    // reads
+    u32 n_reads; const u32* order; const u32* read_win_begin; const u64* read_off; const char* read_bases; const u32* win_pos;
+    u32 ws, ov, k;
+    // outputs: per read a private slice of `head` that ends up holding the corrected read
+    char* head; const u64* head_off; u32* out_len;
+    // per resident warp scratch
+    u8* scratch; u64 scratch_stride; u32 maxL, rmax; u64 dir_cap;
+    u32* ctl;                    // [0] next read, [1] flags, [2..3] DP cells (u64)
+};
+
+__host__ __device__ inline u64 cg_ra_align16(u64 v) { return (v + 15) & ~(u64)15; }
+__host__ __device__ inline u64 cg_ra_buf_bytes(u32 maxL) { return cg_ra_align16(2ull * maxL + 32); }
+__host__ __device__ inline u64 cg_ra_bnd_bytes(u32 rmax) { return cg_ra_align16(8ull * rmax + 16); }
+__host__ __device__ inline u64 cg_ra_line_bytes(u32 maxL) { return cg_ra_align16(4ull * (maxL + 8)); }
+__host__ __device__ inline u64 cg_ra_fixed_bytes(u32 maxL, u32 rmax) {
+    return 3 * cg_ra_buf_bytes(maxL) + cg_ra_bnd_bytes(rmax) + 3 * cg_ra_line_bytes(maxL);
+}
+
+// ssw_cpp.cpp:11-28 kBaseTranslation: A/a 0, C/c 1, G/g 2, T/t 3 (U/u 0), everything else 4
+__device__ __forceinline__ u32 cg_ra_code(char ch) {
+    const u32 c = (u32)(u8)ch | 0x20u;
+    return c == 'a' ? 0u : c == 'c' ? 1u : c == 'g' ? 2u : c == 't' ? 3u : c == 'u' ? 0u : 4u;
+}
+__device__ __forceinline__ char cg_ra_upper(char c) { return (c >= 'a' && c <= 'z') ? (char)(c - 32) : c; }
+__device__ __forceinline__ char cg_ra_lower(char c) { return (c >= 'A' && c <= 'Z') ? (char)(c + 32) : c; }
+
+__device__ __forceinline__ int cg_ra_wmax(int v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) { const int o = __shfl_xor_sync(CG_FULL, v, d); v = o > v ? o : v; }
+    return v;
+}
+__device__ __forceinline__ int cg_ra_wmin(int v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) { const int o = __shfl_xor_sync(CG_FULL, v, d); v = o < v ? o : v; }
+    return v;
+}
+__device__ __forceinline__ int cg_ra_wsum(int v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(CG_FULL, v, d);
+    return v;
+}
+
+struct CgRaEnd { int score, col, row; };
+
+// One scan of the local-alignment matrix by a warp.  Query row j = qsrc[qfirst + qstep * j], j in [0, nq); column c =
+// refc[rfirst + rstep * c] (codes in shared memory), c in [0, nr).  Returns the score, the first column whose maximum
+// reaches it and the smallest row holding it there.  bnd: 4 * rmax u16 of per-warp scratch (band boundaries when
+// nq > 32 * CG_RA_RPL).
+__device__ CG_NOINLINE CgRaEnd cg_ra_scan(const char* qsrc, int qfirst, int qstep, int nq, const u8* refc, int rfirst, int rstep,
+                                          int nr, u16* bnd, u32 rmax) {
+    const int lane = (int)(threadIdx.x & 31u);
+    int best = 0, bcol = 0x7fffffff, brow = 0x7fffffff;
+    const int band_rows = 32 * (int)CG_RA_RPL;
+    const int n_bands = (nq + band_rows - 1) / band_rows;
+    for (int b = 0; b < n_bands; ++b) {
+        const int row0 = b * band_rows;
+        const int rows = min(band_rows, nq - row0);
+        const int rpl = (rows + 31) / 32;                          // warp-uniform
+        const bool last_band = b + 1 == n_bands;
+        const u16* inH = bnd + (size_t)((b + 1) & 1) * 2 * rmax;   // written by band b - 1
+        const u16* inF = inH + rmax;
+        u16* outH = bnd + (size_t)(b & 1) * 2 * rmax;
+        u16* outF = outH + rmax;
+        int H[CG_RA_RPL], E[CG_RA_RPL];
+        u32 qc[CG_RA_RPL];
+        const int my0 = row0 + lane * rpl;
+#pragma unroll
+        for (int i = 0; i < (int)CG_RA_RPL; ++i) {
+            H[i] = 0; E[i] = 0;
+            u32 code = 7u;                                         // padding row: matches nothing
+            if (i < rpl && my0 + i < nq) {
+                code = cg_ra_code(qsrc[qfirst + qstep * (my0 + i)]);
+                if (code == 4u) code = 5u;                         // N never matches, not even N (ssw_cpp.cpp:47-55)
+            }
+            qc[i] = code;
+        }
+        int diag_in = 0;
+        u32 out_msg = 0;
+        const int n_steps = nr + 31;
+        for (int t = 0; t < n_steps; ++t) {
+            u32 in_msg = __shfl_up_sync(CG_FULL, out_msg, 1);
+            if (lane == 0) {
+                in_msg = 0;
+                if (t < nr) {
+                    in_msg = (u32)refc[rfirst + rstep * t];
+                    if (b > 0) in_msg |= ((u32)inH[t] << 18) | ((u32)inF[t] << 4);
+                }
+            }
+            const int c = t - lane;
+            if (c >= 0 && c < nr) {
+                const u32 rc = in_msg & 7u;
+                int f = (int)((in_msg >> 4) & 0x3fffu);
+                int d = diag_in;
+                diag_in = (int)(in_msg >> 18);
+                int colmax = 0, h = 0;
+#pragma unroll
+                for (int i = 0; i < (int)CG_RA_RPL; ++i) {
+                    if (i < rpl) {
+                        const int s = qc[i] == rc ? 2 : -2;
+                        h = max(max(d + s, E[i]), f);              // E, f >= 0: the floor at 0 is implied
+                        d = H[i]; H[i] = h;
+                        colmax = max(colmax, h);
+                        const int open = max(h - 3, 0);
+                        E[i] = max(E[i] - 1, open);
+                        f = max(f - 1, open);
+                    }
+                }
+                out_msg = ((u32)h << 18) | ((u32)f << 4) | rc;
+                if (!last_band && lane == 31) { outH[c] = (u16)h; outF[c] = (u16)f; }
+                if (colmax > best || (colmax == best && c < bcol && colmax > 0)) {
+                    int r = 0;
+#pragma unroll
+                    for (int i = (int)CG_RA_RPL - 1; i >= 0; --i)
+                        if (i < rpl && H[i] == colmax) r = i;
+                    best = colmax; bcol = c; brow = my0 + r;
+                }
+            }
+        }
+        __syncwarp();
+    }
+    CgRaEnd e;
+    e.score = cg_ra_wmax(best);
+    e.col = cg_ra_wmin(best == e.score ? bcol : 0x7fffffff);
+    e.row = cg_ra_wmin((best == e.score && bcol == e.col) ? brow : 0x7fffffff);
+    return e;
+}
+
+// merCounts[kmer] >= solidThresh on the window's sorted solid list
+__device__ __forceinline__ bool cg_ra_solid_has(const u32* keys, u32 n, u32 key) {
+    u32 lo = 0, hi = n;
+    while (lo < hi) { const u32 m = (lo + hi) >> 1; if (keys[m] < key) lo = m + 1; else hi = m; }
+    return lo < n && keys[lo] == key;
+}
+// nbSolidMers (correctionAlignment.cpp:6-15); str2num (BMEAN/utils.cpp:18-30): A0 C1 G2, anything else (lower case too) 3
+__device__ int cg_ra_nb_solid(const char* s, u32 n, const u32* keys, u32 nkeys, u32 k) {
+    const u32 lane = threadIdx.x & 31u;
+    int nb = 0;
+    for (u32 i = lane; i + k <= n; i += 32) {
+        u32 v = 0;
+        for (u32 t = 0; t < k; ++t) { const char c = s[i + t]; v = (v << 2) + (c == 'A' ? 0u : c == 'C' ? 1u : c == 'G' ? 2u : 3u); }
+        nb += cg_ra_solid_has(keys, nkeys, v) ? 1 : 0;
+    }
+    return cg_ra_wsum(nb);
+}
+__device__ int cg_ra_nb_upper(const char* s, u32 n) {                       // nbUpperCase, correctionAlignment.cpp:17-26
+    const u32 lane = threadIdx.x & 31u;
+    int nb = 0;
+    for (u32 i = lane; i < n; i += 32) nb += (s[i] >= 'A' && s[i] <= 'Z') ? 1 : 0;
+    return cg_ra_wsum(nb);
+}
+
+// banded_sw (ssw.c:577-758) by one lane: band DP with the band doubled until the best cell reaches `score`, traceback
+// from the last cell until read row 0; returns the numbers of I and D operations.  Storage follows the reference slot for
+// slot (slot(i, j) = j - max(0, i - w) + 1; slot 0 and the slot right of the row's last column are zeroed before every
+// row, ssw.c:624-627); the three direction codes of a cell are packed in one byte.
+__device__ __forceinline__ int cg_ra_slot(int w, int i, int j) { const int x = i - w; return j - (x > 0 ? x : 0) + 1; }
+__device__ CG_NOINLINE u32 cg_ra_banded(const u8* refc, const char* read, int refLen, int readLen, int score, int w, i32* h_prev,
+                                        i32* e_line, i32* h_cur, u8* dir, u64 dir_cap, int* n_ins, int* n_del) {
+    int best = 0, stride = 0;
+    for (;;) {
+        const int width = 2 * w + 3;
+        stride = min(2 * w + 1, refLen);
+        if ((u64)stride * (u64)readLen > dir_cap) return CG_RA_FLAG_CAPACITY;
+        for (int s = 1; s < width - 1 && s < refLen + 4; ++s) h_prev[s] = 0;
+        for (int i = 0; i < readLen; ++i) {
+            const int beg = max(i - w, 0), end = min(i + w, refLen - 1), edge = min(end + 1, width - 1);
+            int f = 0, last = 0;
+            h_prev[0] = 0; e_line[0] = 0; h_prev[edge] = 0; e_line[edge] = 0; h_cur[0] = 0;
+            u8* d = dir + (size_t)stride * (size_t)i;
+            u32 rcode = cg_ra_code(read[i]);
+            if (rcode == 4u) rcode = 5u;
+            for (int j = beg; j <= end; ++j) {
+                const int u = cg_ra_slot(w, i, j), up = cg_ra_slot(w, i - 1, j), left = cg_ra_slot(w, i, j - 1), dg = cg_ra_slot(w, i - 1, j - 1);
+                int a = i == 0 ? -3 : h_prev[up] - 3;
+                int b = i == 0 ? -1 : e_line[up] - 1;
+                const int e = a > b ? a : b;
+                const u32 de = a > b ? 3u : 2u;
+                e_line[u] = e;
+                a = h_cur[left] - 3;
+                b = f - 1;
+                f = a > b ? a : b;
+                const u32 df = a > b ? 5u : 4u;
+                const int e1 = max(e, 0), f1 = max(f, 0);
+                const int gap = max(e1, f1);
+                const int diag = h_prev[dg] + ((u32)refc[j] == rcode ? 2 : -2);
+                const int h = max(gap, diag);
+                h_cur[u] = h;
+                best = max(best, h);
+                const u32 dh = gap <= diag ? 1u : (e1 > f1 ? de : df);
+                d[j - beg] = (u8)((de & 1u) | ((df & 1u) << 1) | (dh << 2));
+                last = u;
+            }
+            for (int s = 1; s <= last; ++s) h_prev[s] = h_cur[s];
+        }
+        if (best >= score) break;
+        w *= 2;
+        if (w > 4 * (refLen + readLen) + 16) return CG_RA_FLAG_TRACEBACK;
+    }
+    int i = readLen - 1, j = refLen - 1, state = 2, ins = 0, del = 0;
+    while (i > 0) {
+        const int x = j - max(i - w, 0);
+        if (j < 0 || x < 0 || x >= stride) return CG_RA_FLAG_TRACEBACK;       // the reference reads outside its matrix here
+        const u32 cell = dir[(size_t)stride * (size_t)i + (size_t)x];
+        const u32 code = state == 0 ? 2u + (cell & 1u) : state == 1 ? 4u + ((cell >> 1) & 1u) : (cell >> 2);
+        if (code == 1u) { --i; --j; state = 2; }
+        else if (code == 2u) { --i; state = 0; ++ins; }
+        else if (code == 3u) { --i; state = 2; ++ins; }
+        else if (code == 4u) { --j; state = 1; ++del; }
+        else if (code == 5u) { --j; state = 2; ++del; }
+        else return CG_RA_FLAG_TRACEBACK;
+    }
+    *n_ins = ins; *n_del = del;
+    return 0;
+}
+
+// dst[0..n) <- src[0..n) inside one buffer (regions may overlap), by a warp
+__device__ void cg_ra_move(char* base, u32 dst, u32 src, u32 n) {
+    const u32 lane = threadIdx.x & 31u;
+    if (dst == src || n == 0) return;
+    if (dst < src) {
+        for (u32 o = 0; o < n; o += 32) {
+            const u32 i = o + lane;
+            char c = 0;
+            if (i < n) c = base[src + i];
+            __syncwarp();
+            if (i < n) base[dst + i] = c;
+            __syncwarp();
+        }
+    } else {
+        for (u32 done = 0; done < n; done += 32) {
+            const u32 chunk = min(32u, n - done);
+            const u32 o = n - done - chunk;
+            char c = 0;
+            if (lane < chunk) c = base[src + o + lane];
+            __syncwarp();
+            if (lane < chunk) base[dst + o + lane] = c;
+            __syncwarp();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(CG_RA_WARPS * 32) k_reanchor(CgReanchorArgs P) {
+    CG_DYN_SMEM(smem_raw);
+    const u32 lane = threadIdx.x & 31u, wip = threadIdx.x >> 5;
+    const u32 rpad = (P.rmax + 15u) & ~15u;
+    u8* refc = (u8*)smem_raw + (size_t)wip * rpad;
+    const u32 gw = blockIdx.x * CG_RA_WARPS + wip;
+    u8* sc = P.scratch + (size_t)gw * P.scratch_stride;
+    char* bufs[3];
+    bufs[0] = (char*)sc; bufs[1] = bufs[0] + cg_ra_buf_bytes(P.maxL); bufs[2] = bufs[1] + cg_ra_buf_bytes(P.maxL);
+    u16* bnd = (u16*)(bufs[2] + cg_ra_buf_bytes(P.maxL));
+    i32* line0 = (i32*)((u8*)bnd + cg_ra_bnd_bytes(P.rmax));
+    i32* line1 = (i32*)((u8*)line0 + cg_ra_line_bytes(P.maxL));
+    i32* line2 = (i32*)((u8*)line1 + cg_ra_line_bytes(P.maxL));
+    u8* dir = (u8*)line2 + cg_ra_line_bytes(P.maxL);
+    u64 cells = 0;
+    u32 flags = 0;
+
+    for (;;) {
+        u32 slot = 0;
+        if (lane == 0) slot = atomicAdd(&P.ctl[0], 1u);
+        slot = __shfl_sync(CG_FULL, slot, 0);
+        if (slot >= P.n_reads) break;
+        const u32 r = P.order[slot];
+        const u32 w0 = P.read_win_begin[r], w1 = P.read_win_begin[r + 1];
+        const char* raw = P.read_bases + P.read_off[r];
+        const u32 rawLen = (u32)(P.read_off[r + 1] - P.read_off[r]);
+        char* head = P.head + P.head_off[r];
+        if (w0 == w1) { if (lane == 0) P.out_len[r] = 0; continue; }          // CONSENT-correction.cpp:23-25
+        u32 hlen = 0, t0 = 0;                                                 // outSequence = head[0..hlen) + lower(raw[t0..))
+        int curPos = (int)P.win_pos[w0];                                      // startPos
+        u32 oldEnd = 0, old_n = 0, oldW = w0;
+        bool haveOld = false;
+        int ic = 0, io = 1, it = 2;
+        const char* oldp = bufs[io];
+
+        for (u32 w = w0; w < w1; ++w) {
+            const u64 c0 = P.cons_off[w], c1 = P.cons_off[w + 1];
+            const bool isCons = (c1 - c0) >= (u64)P.k;                        // :72
+            const char* src; u32 n;
+            if (isCons) { src = P.cons + c0; n = (u32)(c1 - c0); }
+            else if (P.win_seq_begin) { const u32 s0 = P.win_seq_begin[w]; src = P.bases + P.seq_off[s0]; n = (u32)(P.seq_off[s0 + 1] - P.seq_off[s0]); }
+            else { src = P.tpl + P.tpl_off[w]; n = (u32)(P.tpl_off[w + 1] - P.tpl_off[w]); }
+            const u32 outLen = hlen + (rawLen - t0);
+            int alPos = curPos - (int)P.ov; if (alPos < 0) alPos = 0;          // :80
+            int sizeAl = ((u64)alPos + P.ws + 2ull * P.ov >= (u64)outLen) ? (int)outLen - alPos : (int)(P.ws + 2 * P.ov);   // :81-85
+            if (sizeAl <= 0 || n == 0) { flags |= CG_RA_FLAG_DEGENERATE; break; }
+            if ((u32)sizeAl > P.rmax || n > P.maxL || n > CG_RA_QMAX) { flags |= CG_RA_FLAG_CAPACITY; break; }
+            char* cur = bufs[ic];
+            for (u32 i = lane; i < n; i += 32) cur[i] = src[i];
+            // the read up to the end of the alignment region becomes part of the head
+            {
+                const u32 upto = (u32)alPos + (u32)sizeAl;
+                if (upto > hlen) {
+                    const u32 m = upto - hlen;
+                    for (u32 i = lane; i < m; i += 32) head[hlen + i] = cg_ra_lower(raw[t0 + i]);
+                    hlen += m; t0 += m;
+                }
+            }
+            __syncwarp();
+            for (u32 i = lane; i < (u32)sizeAl; i += 32) refc[i] = (u8)cg_ra_code(head[alPos + i]);
+            __syncwarp();
+            const CgRaEnd fw = cg_ra_scan(cur, 0, 1, (int)n, refc, 0, 1, sizeAl, bnd, P.rmax);                          // :87
+            cells += (u64)n * (u64)sizeAl;
+            if (fw.score <= 0) { flags |= CG_RA_FLAG_DEGENERATE; break; }
+            const CgRaEnd bw = cg_ra_scan(cur, fw.row, -1, fw.row + 1, refc, fw.col, -1, fw.col + 1, bnd, P.rmax);
+            cells += (u64)(fw.row + 1) * (u64)(bw.col + 1);
+            const u32 beg = (u32)(fw.col - bw.col + alPos), end = (u32)(fw.col + alPos);                                  // :88-89
+            const char* curp = cur + (fw.row - bw.row);                                                                   // :90
+            u32 cn = (u32)(bw.row + 1);
+
+            if (w != w0 && oldEnd >= beg) {                                                                               // :93
+                const u32 overlap = oldEnd - beg + 1;
+                if (isCons && old_n >= overlap && cn >= overlap) {                                                        // :95
+                    const char* s1 = oldp + (old_n - overlap);
+                    const char* s2 = curp;
+                    bool differ = false;
+                    for (u32 o = 0; o < overlap; o += 32) {
+                        const u32 i = o + lane;
+                        const bool ne = i < overlap && cg_ra_upper(s1[i]) != cg_ra_upper(s2[i]);
+                        if (__ballot_sync(CG_FULL, ne)) { differ = true; break; }
+                    }
+                    if (differ) {
+                        int n1, n2;
+                        if (overlap >= P.k) {                                                                             // :99-101
+                            const u64 a0 = haveOld ? P.solid_off[oldW] : 0, a1 = haveOld ? P.solid_off[oldW + 1] : 0;
+                            n1 = cg_ra_nb_solid(s1, overlap, P.solid_kmer + a0, (u32)(a1 - a0), P.k);
+                            n2 = cg_ra_nb_solid(s2, overlap, P.solid_kmer + P.solid_off[w], (u32)(P.solid_off[w + 1] - P.solid_off[w]), P.k);
+                        } else { n1 = cg_ra_nb_upper(s1, overlap); n2 = cg_ra_nb_upper(s2, overlap); }                     // :103-104
+                        if (n1 > n2) {                                                                                    // :106-117
+                            __syncwarp();
+                            for (u32 i = lane; i < overlap; i += 32) refc[i] = (u8)cg_ra_code(s2[i]);
+                            __syncwarp();
+                            const CgRaEnd f2 = cg_ra_scan(s1, 0, 1, (int)overlap, refc, 0, 1, (int)overlap, bnd, P.rmax);
+                            cells += (u64)overlap * (u64)overlap;
+                            int ins = 0, del = 0;
+                            u32 bad = 0;
+                            if (f2.score > 0) {
+                                const CgRaEnd b2 = cg_ra_scan(s1, f2.row, -1, f2.row + 1, refc, f2.col, -1, f2.col + 1, bnd, P.rmax);
+                                cells += (u64)(f2.row + 1) * (u64)(b2.col + 1);
+                                const int rb = f2.col - b2.col, qb = f2.row - b2.row;
+                                const int refLen = b2.col + 1, readLen = b2.row + 1;
+                                if (lane == 0) {
+                                    const int bw0 = (refLen > readLen ? refLen - readLen : readLen - refLen) + 1;
+                                    bad = cg_ra_banded(refc + rb, s1 + qb, refLen, readLen, f2.score, bw0, line0, line1, line2, dir, P.dir_cap, &ins, &del);
+                                }
+                                bad = __shfl_sync(CG_FULL, bad, 0);
+                                ins = __shfl_sync(CG_FULL, ins, 0);
+                                del = __shfl_sync(CG_FULL, del, 0);
+                            }   // score 0: the reference's CIGAR is "1M" plus clips: no I, no D
+                            if (bad) { flags |= bad; break; }
+                            const u32 cut = overlap - (u32)ins + (u32)del;
+                            if (cut < cn) {
+                                char* tmp = bufs[it];
+                                for (u32 i = lane; i < overlap; i += 32) tmp[i] = s1[i];
+                                for (u32 i = lane; i < cn - cut; i += 32) tmp[overlap + i] = curp[cut + i];
+                                __syncwarp();
+                                cn = overlap + cn - cut;
+                                curp = tmp;
+                                const int x = ic; ic = it; it = x;
+                            } else cn = 0;
+                        }
+                    }
+                }
+            }
+
+            if (cn != 0) {                                                                                                // :121
+                if (isCons) {                                                                                             // :122-126
+                    const u32 oldLen = end - beg + 1;
+                    const u32 tail = hlen - (end + 1);
+                    __syncwarp();
+                    cg_ra_move(head, beg + cn, end + 1, tail);
+                    for (u32 i = lane; i < cn; i += 32) head[beg + i] = cg_ra_upper(curp[i]);
+                    hlen = hlen - oldLen + cn;
+                    __syncwarp();
+                }
+                if (w + 1 < w1) {                                                                                         // :127-132
+                    curPos = (int)((u32)curPos + P.win_pos[w + 1] - P.win_pos[w] - (end - beg + 1) + cn);
+                    oldp = curp; old_n = cn; oldW = w; haveOld = true;
+                    oldEnd = beg + cn - 1;
+                    const int x = io; io = ic; ic = x;            // the buffer holding cur now holds old
+                }
+            }
+        }
+        // the untouched rest of the read
+        {
+            const u32 m = rawLen - t0;
+            for (u32 i = lane; i < m; i += 32) head[hlen + i] = cg_ra_lower(raw[t0 + i]);
+            hlen += m;
+        }
+        if (lane == 0) P.out_len[r] = hlen;
+        __syncwarp();
+    }
+    if (lane == 0) {
+        if (flags) atomicOr(&P.ctl[1], flags);
+        atomicAdd((unsigned long long*)(P.ctl + 2), (unsigned long long)cells);
+    }
+}
+
+// corrected reads, dense: out[out_off[r] ..) <- head slice of read r
+__global__ void k_reanchor_gather(const char* head, const u64* head_off, const u64* out_off, char* out, u32 n_reads) {
+    for (u32 r = blockIdx.x; r < n_reads; r += gridDim.x) {
+        const char* s = head + head_off[r];
+        char* d = out + out_off[r];
+        const u64 n = out_off[r + 1] - out_off[r];
+        for (u64 i = threadIdx.x; i < n; i += blockDim.x) d[i] = s[i];
+    }
+}

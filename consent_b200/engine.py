@@ -14,14 +14,14 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-from ._ffi import (Batch, CG_N_STAGES, PKG_DIR, Params, Results, STAGE_NAMES, STATUS_NAMES, cg_batch,
-                   cg_counters, cg_params, cg_results, load_library)
+from ._ffi import (Batch, CG_N_STAGES, Corrected, PKG_DIR, Params, Reads, Results, STAGE_NAMES, STATUS_NAMES, cg_batch,
+                   cg_corrected, cg_counters, cg_params, cg_reads, cg_results, load_library, results_to_c)
 
 LIB_PATH = os.path.join(PKG_DIR, "libconsent_b200.so")
 
 EXPORTS = ("cg_abi_version", "cg_device_count", "cg_create", "cg_destroy", "cg_last_error", "cg_set_option",
            "cg_correct_windows", "cg_free_results", "cg_upload", "cg_run", "cg_download", "cg_stage_ms",
-           "cg_get_counters", "cg_run_ms", "cg_chunk_count")
+           "cg_get_counters", "cg_run_ms", "cg_chunk_count", "cg_reanchor_reads", "cg_free_corrected", "cg_reanchor_stats")
 
 
 class ConsentError(RuntimeError):
@@ -60,6 +60,11 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.cg_chunk_count.argtypes = [H]
     lib.cg_get_counters.restype = C.c_int
     lib.cg_get_counters.argtypes = [H, C.POINTER(cg_counters)]
+    lib.cg_reanchor_reads.restype = C.c_int
+    lib.cg_reanchor_reads.argtypes = [H, C.POINTER(cg_batch), C.POINTER(cg_results), C.POINTER(cg_reads), C.POINTER(cg_corrected)]
+    lib.cg_free_corrected.argtypes = [C.POINTER(cg_corrected)]
+    lib.cg_reanchor_stats.restype = C.c_int
+    lib.cg_reanchor_stats.argtypes = [H, C.POINTER(C.c_float), C.POINTER(C.c_uint64)]
     return lib
 
 
@@ -108,6 +113,25 @@ class Corrector:
         cb, r = batch.c(), cg_results()
         self._check(self.lib.cg_correct_windows(self._h, C.byref(cb), C.byref(r)))
         return Results(r, free=self._free_results)
+
+    # -- re-anchoring: alignConsensus (reference src/correctionAlignment.cpp:47-139) for every read --------------
+    def reanchor_reads(self, batch: Batch, results: Results, reads: Reads) -> Corrected:
+        """The window consensuses of every read aligned back onto it, overlaps arbitrated, aligned stretches
+        replaced by the upper-cased consensus: what `alignConsensus` returns per read (before the trim / drop
+        post-filters of processRead).  `results` = what correct_windows(batch) returned (when it is that very
+        object the device copies are reused), read r owns windows reads.read_win_begin[r] .. [r+1]."""
+        cb, rd, out = batch.c(), reads.c(), cg_corrected()
+        live = getattr(results, "_r", None)
+        cr = live if live is not None else results_to_c(results)
+        self._check(self.lib.cg_reanchor_reads(self._h, C.byref(cb), C.byref(cr), C.byref(rd), C.byref(out)))
+        got = Corrected(out)
+        self.lib.cg_free_corrected(C.byref(out))
+        return got
+
+    def reanchor_stats(self) -> dict:
+        ms, cells = C.c_float(0), C.c_uint64(0)
+        self._check(self.lib.cg_reanchor_stats(self._h, C.byref(ms), C.byref(cells)))
+        return {"kernel_ms": float(ms.value), "dp_cells": int(cells.value)}
 
     # -- staged (bench: keep the batch resident in HBM, time the kernels alone) ---------------
     def upload(self, batch: Batch):

@@ -5,6 +5,7 @@
 #include <vector>
 #include <cstring>
 #include <algorithm>
+#include <string>
 
 static uint32_t gen_window(const cg_synth_spec* s, uint32_t w, char* out, uint32_t* lens) {
     static const char B[4] = {'A', 'C', 'G', 'T'};
@@ -65,4 +66,75 @@ extern "C" uint64_t cg_synth_windows(const cg_synth_spec* s, uint32_t* win_seq_b
     win_seq_begin[W] = W * N;
     seq_off[(size_t)W * N] = off;
     return off;
+}
+
+// ---- reads with their windows (re-anchoring path) ----------------------------------------------
+namespace {
+const char kB[4] = {'A', 'C', 'G', 'T'};
+// truth[t0..t1] through the channel, appended to out; if map != nullptr also records the truth index
+// every emitted base belongs to.
+void channel(const cg_synth_read_spec* s, std::mt19937_64& rng, const std::vector<uint8_t>& truth,
+             uint32_t t0, uint32_t t1, std::string& out, std::vector<uint32_t>* map) {
+    for (uint32_t i = t0; i <= t1; ++i) {
+        double u = (double)(rng() >> 11) * (1.0 / 9007199254740992.0);
+        if (u >= s->err) {
+            out.push_back(kB[truth[i]]); if (map) map->push_back(i);
+        } else {
+            double v = u / s->err;
+            if (v < s->p_sub) {
+                out.push_back(kB[(truth[i] + 1 + (uint32_t)(rng() % 3)) & 3]); if (map) map->push_back(i);
+            } else if (v < s->p_sub + s->p_ins) {
+                out.push_back(kB[rng() & 3]); if (map) map->push_back(i);
+                out.push_back(kB[truth[i]]); if (map) map->push_back(i);
+            }
+        }
+    }
+}
+}  // namespace
+
+extern "C" void cg_synth_reads_bounds(const cg_synth_read_spec* s, uint64_t* max_windows, uint64_t* max_seqs,
+                                      uint64_t* max_bases, uint64_t* max_read_bases) {
+    uint64_t step = s->window_size > s->window_overlap ? s->window_size - s->window_overlap : 1;
+    uint64_t per_read = (2ULL * s->truth_len) / step + 2;
+    *max_windows = per_read * s->n_reads;
+    *max_seqs = *max_windows * s->n_seqs;
+    *max_bases = *max_seqs * (2ULL * s->window_size + 2);
+    *max_read_bases = 2ULL * s->truth_len * s->n_reads;
+}
+
+extern "C" uint64_t cg_synth_reads(const cg_synth_read_spec* s, uint32_t* win_seq_begin, uint64_t* seq_off, char* bases,
+                                   uint32_t* read_win_begin, uint64_t* read_off, char* read_bases, uint32_t* win_pos) {
+    uint64_t W = 0, S = 0, B = 0, RB = 0;
+    win_seq_begin[0] = 0; seq_off[0] = 0; read_win_begin[0] = 0; read_off[0] = 0;
+    const uint32_t ws = s->window_size, ov = s->window_overlap;
+    for (uint32_t r = 0; r < s->n_reads; ++r) {
+        std::mt19937_64 rng(s->seed * 7000003ULL + s->first_read + r);
+        std::vector<uint8_t> truth(s->truth_len);
+        for (auto& t : truth) t = (uint8_t)(rng() & 3);
+        std::string read; std::vector<uint32_t> map;
+        channel(s, rng, truth, 0, s->truth_len - 1, read, &map);
+        const uint32_t len = (uint32_t)read.size();
+        std::vector<uint32_t> starts;
+        if (len >= ws) {
+            for (uint32_t b = 0; b + ws <= len; b += ws - ov) starts.push_back(b);
+            if (len > ws) starts.push_back(len - ws);
+        }
+        for (size_t i = 0; i < starts.size(); ++i) {
+            uint32_t a = starts[i], b = a + ws - 1;
+            uint32_t n = (s->thin_every && (W % s->thin_every) == s->thin_every - 1) ? s->thin_seqs : s->n_seqs;
+            if (n < 1) n = 1;
+            memcpy(bases + B, read.data() + a, ws); B += ws; seq_off[++S] = B;
+            for (uint32_t q = 1; q < n; ++q) {
+                std::string o;
+                channel(s, rng, truth, map[a], map[b], o, nullptr);
+                memcpy(bases + B, o.data(), o.size()); B += o.size(); seq_off[++S] = B;
+            }
+            win_pos[W] = a;
+            win_seq_begin[++W] = (uint32_t)S;
+        }
+        memcpy(read_bases + RB, read.data(), len); RB += len;
+        read_off[r + 1] = RB;
+        read_win_begin[r + 1] = (uint32_t)W;
+    }
+    return W;
 }

@@ -40,6 +40,35 @@ uint64_t cg_synth_max_bases(const cg_synth_spec* s);
 uint64_t cg_synth_windows(const cg_synth_spec* s, uint32_t* win_seq_begin, uint64_t* seq_off,
                           char* bases, int threads);
 
+/* Synthetic reads with their windows, for the re-anchoring path.
+ *
+ * Read r of a run with seed s draws from std::mt19937_64(s * 7000003 + r):
+ *   truth[i] = rng() & 3, i in [0, truth_len); the read = truth through the error channel above,
+ *   remembering for every read base the truth index it was emitted at;
+ *   windows as getAlignmentWindowsPositions cuts them on a fully covered read
+ *   (src/alignmentWindows.cpp:27-85): starts 0, ws-ov, 2(ws-ov), ... while a full window fits,
+ *   then one last window [len-ws, len-1];
+ *   pile of window [a, b] = the read's own bases [a, b] (the template) followed by n_seqs-1 fresh
+ *   channel copies of truth[t(a) .. t(b)].  Every `thin_every`-th window (if non-zero) only gets
+ *   `thin_seqs` sequences (poorly covered windows, template fall-backs). */
+typedef struct cg_synth_read_spec {
+    uint64_t seed;
+    uint32_t first_read, n_reads;
+    uint32_t n_seqs;         /* sequences per window, template included */
+    uint32_t truth_len;      /* bases of truth per read                 */
+    uint32_t window_size, window_overlap;
+    uint32_t thin_every, thin_seqs;
+    double   err, p_sub, p_ins;
+} cg_synth_read_spec;
+
+/* Upper bounds for the buffers of one cg_synth_reads call. */
+void cg_synth_reads_bounds(const cg_synth_read_spec* s, uint64_t* max_windows, uint64_t* max_seqs,
+                           uint64_t* max_bases, uint64_t* max_read_bases);
+/* Fills the cg_batch arrays (win_seq_begin, seq_off, bases) and the cg_reads arrays (read_win_begin,
+ * read_off, read_bases, win_pos); returns the number of windows. */
+uint64_t cg_synth_reads(const cg_synth_read_spec* s, uint32_t* win_seq_begin, uint64_t* seq_off, char* bases,
+                        uint32_t* read_win_begin, uint64_t* read_off, char* read_bases, uint32_t* win_pos);
+
 #ifdef __cplusplus
 }
 #endif

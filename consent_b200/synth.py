@@ -7,7 +7,7 @@ import os
 
 import numpy as np
 
-from ._ffi import Batch, PKG_DIR, cg_synth_spec, load_library
+from ._ffi import Batch, PKG_DIR, Reads, cg_synth_read_spec, cg_synth_spec, load_library
 
 PROFILES = {
     # total error, share substitutions, share insertions (deletions = rest)
@@ -27,6 +27,12 @@ def _host():
         _lib.cg_synth_windows.restype = C.c_uint64
         _lib.cg_synth_windows.argtypes = [C.POINTER(cg_synth_spec), C.POINTER(C.c_uint32),
                                           C.POINTER(C.c_uint64), C.c_char_p, C.c_int]
+        _lib.cg_synth_reads_bounds.restype = None
+        _lib.cg_synth_reads_bounds.argtypes = [C.POINTER(cg_synth_read_spec)] + [C.POINTER(C.c_uint64)] * 4
+        _lib.cg_synth_reads.restype = C.c_uint64
+        _lib.cg_synth_reads.argtypes = [C.POINTER(cg_synth_read_spec), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64),
+                                        C.c_char_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.c_char_p,
+                                        C.POINTER(C.c_uint32)]
     return _lib
 
 
@@ -45,3 +51,32 @@ def synth_windows(n_windows: int, n_seqs: int, *, seed: int = 42, profile: str =
                              off.ctypes.data_as(C.POINTER(C.c_uint64)),
                              C.cast(bases.ctypes.data, C.c_char_p), threads)
     return Batch(wsb, off, bases[:max(int(n), 1)].copy())
+
+
+def synth_reads(n_reads: int, n_seqs: int, *, truth_len: int = 3000, seed: int = 42, profile: str = "PB",
+                window_size: int = 500, window_overlap: int = 50, first_read: int = 0,
+                thin_every: int = 0, thin_seqs: int = 1) -> tuple[Batch, Reads]:
+    """Seeded reads with the windows the reference would cut from them (consent_b200/host/synth.h):
+    -> (window batch, reads).  Input of the re-anchoring path."""
+    err, p_sub, p_ins = PROFILES[profile]
+    spec = cg_synth_read_spec(seed, first_read, n_reads, n_seqs, truth_len, window_size, window_overlap,
+                              thin_every, thin_seqs, err, p_sub, p_ins)
+    lib = _host()
+    mw, ms, mb, mr = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+    lib.cg_synth_reads_bounds(C.byref(spec), C.byref(mw), C.byref(ms), C.byref(mb), C.byref(mr))
+    wsb = np.zeros(mw.value + 1, np.uint32)
+    off = np.zeros(ms.value + 1, np.uint64)
+    bases = np.empty(max(mb.value, 1), np.uint8)
+    rwb = np.zeros(n_reads + 1, np.uint32)
+    roff = np.zeros(n_reads + 1, np.uint64)
+    rbases = np.empty(max(mr.value, 1), np.uint8)
+    wpos = np.zeros(mw.value + 1, np.uint32)
+    u32p, u64p = C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)
+    W = int(lib.cg_synth_reads(C.byref(spec), wsb.ctypes.data_as(u32p), off.ctypes.data_as(u64p),
+                               C.cast(bases.ctypes.data, C.c_char_p), rwb.ctypes.data_as(u32p),
+                               roff.ctypes.data_as(u64p), C.cast(rbases.ctypes.data, C.c_char_p),
+                               wpos.ctypes.data_as(u32p)))
+    S = int(wsb[W])
+    batch = Batch(wsb[:W + 1].copy(), off[:S + 1].copy(), bases[:max(int(off[S]), 1)].copy())
+    reads = Reads(rwb, roff, rbases[:max(int(roff[-1]), 1)].copy(), wpos[:W].copy(), window_size, window_overlap)
+    return batch, reads

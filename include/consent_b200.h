@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define CG_ABI_VERSION 1
+#define CG_ABI_VERSION 2
 
 typedef enum cg_status {
     CG_OK                 =  0,
@@ -123,6 +123,59 @@ void cg_free_results(cg_results* r);
 int  cg_upload(cg_handle* h, const cg_batch* in);   /* H2D + 2-bit packing on device  */
 int  cg_run(cg_handle* h);                          /* every kernel of the path       */
 int  cg_download(cg_handle* h, cg_results* out);    /* D2H of the results of cg_run   */
+
+/* Consensus re-anchoring ---------------------------------
+ * Batched equivalent of
+ *
+ *   std::string alignConsensus(rawRead, sequence, consensuses, merCounts, pilesPos,
+ *                              templates, startPos, windowSize, windowOverlap,
+ *                              solidThresh, merSize)      (src/correctionAlignment.h:7,
+ *                                                          body src/correctionAlignment.cpp:47-139)
+ *
+ * called once per read by processRead (src/CONSENT-correction.cpp:47) right after the
+ * per-window consensus calls.  Every window consensus is located on the (progressively
+ * corrected) read by a local alignment — StripedSmithWaterman::Aligner defaults: match 2,
+ * mismatch 2, gap open 3, gap extend 1, BMEAN/Complete-Striped-Smith-Waterman-Library/
+ * src/ssw_cpp.cpp:419-426, ssw.c:788-891 — overlaps with the previous window are
+ * arbitrated by solid k-mers (correctionAlignment.cpp:90-118) and the aligned stretch of
+ * the read is replaced by the upper-cased consensus.  Windows of one read are processed in
+ * order (each alignment sees the replacements of the previous ones); reads are independent.
+ *
+ * Inputs: the window batch (its first sequence per window = templates[i]), the results of
+ * cg_correct_windows on it (consensuses[i]; the solid k-mer lists stand for merCounts[i],
+ * whose consumers only test `count >= solidThresh`, correctionAlignment.cpp:6-15), and the
+ * reads below.  Read r owns windows [read_win_begin[r], read_win_begin[r+1]) of the batch in
+ * pile order; startPos = win_pos of its first window (CONSENT-correction.cpp:47).
+ * A read without windows yields an empty string (CONSENT-correction.cpp:23-25). */
+typedef struct cg_reads {
+    uint32_t        n_reads;
+    const uint32_t* read_win_begin;  /* [n_reads + 1], read_win_begin[n_reads] == n_windows          */
+    const uint64_t* read_off;        /* [n_reads + 1] byte offsets into read_bases                    */
+    const char*     read_bases;      /* the reads (`sequence`; any case, lower-cased internally :57)  */
+    const uint32_t* win_pos;         /* [n_windows] pilesPos[i].first                                 */
+    uint32_t        window_size;     /* -l windowSize    (CONSENT-correct default 500)                */
+    uint32_t        window_overlap;  /* -m windowOverlap (default 50)                                 */
+} cg_reads;
+
+/* Corrected reads, owned by the library until cg_free_corrected(): upper case = replaced by
+ * a consensus, lower case = untouched raw read (what alignConsensus returns, before the
+ * trimRead/dropRead post-filters of processRead). */
+typedef struct cg_corrected {
+    uint32_t  n_reads;
+    uint64_t* read_off;      /* [n_reads + 1] byte offsets into bases */
+    char*     bases;
+    void*     owner_;        /* private */
+} cg_corrected;
+
+/* Host buffers in, host buffers out (H2D, kernel, D2H inside).  `cons` may be the live result
+ * of cg_correct_windows on the same handle (it is only read).  Blocking; one call at a time
+ * per handle. */
+int  cg_reanchor_reads(cg_handle* h, const cg_batch* windows, const cg_results* cons,
+                       const cg_reads* reads, cg_corrected* out);
+void cg_free_corrected(cg_corrected* c);
+/* CUDA-event time (ms) of the kernel of the last cg_reanchor_reads and the DP cells
+ * (query x reference, forward + reverse passes of every alignment) it swept. */
+int  cg_reanchor_stats(const cg_handle* h, float* kernel_ms, uint64_t* dp_cells);
 
 /* Instrumentation -------------------------------------------------------- */
 #define CG_STAGE_PACK     0   /* ASCII -> 2-bit                                         */

@@ -19,6 +19,14 @@ void  oracle_free_text(char* p);
 void  oracle_reset_counters(void);
 void  oracle_get_counters(cg_counters* out);
 
+/* Re-anchoring oracle (oracle/reanchor_oracle.c): alignConsensus once per read; same contract as
+ * ref_reanchor_reads of the reference harness. */
+int   oracle_reanchor_reads(const cg_batch* win, const cg_results* cons, const cg_reads* reads, const cg_params* p,
+                            int threads, cg_corrected* out, double* seconds);
+void  oracle_free_corrected(cg_corrected* c);
+/* DP cells (forward + backward scans of every alignment) swept by the last oracle_reanchor_reads. */
+uint64_t oracle_reanchor_cells(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,6 +12,9 @@
 //    longest_ordered_chain :239, average_distance_next_anchor :331,
 //    split_reads :476, easy_consensus :603) and weightConsensus /
 //   polishCorrection (src/correctionMSA.cpp:6, src/correctionDBG.cpp:93).
+//   alignConsensus                            src/correctionAlignment.cpp:47-139
+//   (re-anchoring; pulls in the vendored SSW library,
+//    BMEAN/Complete-Striped-Smith-Waterman-Library/src/{ssw.c,ssw_cpp.cpp})
 //
 // Used by: tests/ (to pin oracle/consent_oracle.c and to generate
 // tests/golden/*), bench.py's cpu_baseline / --impl reference legs.
@@ -33,6 +36,7 @@
 #include "robin_hood.h"          // src/robin_hood.h (3.11.3) via -I, see Makefile
 #include "correctionMSA.h"       // src/correctionMSA.h
 #include "correctionDBG.h"       // src/correctionDBG.h
+#include "correctionAlignment.h" // src/correctionAlignment.h (alignConsensus)
 #include "consent_b200.h"        // our ABI structs (cg_batch, cg_results, cg_params)
 
 // ---- prototypes of the reference's stage functions (external linkage in
@@ -169,6 +173,66 @@ int ref_correct_windows(const cg_batch* in, const cg_params* p, int threads, int
 
 void ref_free_results(cg_results* r) {
     if (r && r->owner_) { delete static_cast<Owner*>(r->owner_); r->owner_ = nullptr; }
+}
+
+// ---- re-anchoring: the unmodified alignConsensus, once per read -------------------------
+// Arguments are rebuilt exactly as processRead hands them over (src/CONSENT-correction.cpp:
+// 27-47): consensuses[i] / merCounts[i] = what computeConsensusReadCorrection returned for
+// window i (merCounts restricted to its solid k-mers: the callee only tests
+// `merCounts[kmer] >= solidThresh`, correctionAlignment.cpp:6-15), templates[i] = pile[0],
+// pilesPos[i].first = win_pos[i] (.second is never read by alignConsensus), startPos =
+// pilesPos[0].first.
+struct CorrectedOwner { std::vector<uint64_t> off; std::string bases; };
+
+int ref_reanchor_reads(const cg_batch* win, const cg_results* cons, const cg_reads* reads,
+                       const cg_params* p, int threads, cg_corrected* out, double* seconds) {
+    if (!win || !cons || !reads || !p || !out) return CG_ERR_INVALID_ARG;
+    const uint32_t R = reads->n_reads;
+    std::vector<std::string> res(R);
+    std::atomic<uint32_t> next(0);
+    if (threads < 1) threads = 1;
+    auto t0 = std::chrono::steady_clock::now();
+    auto worker = [&]() {
+        for (;;) {
+            uint32_t r = next.fetch_add(1);
+            if (r >= R) break;
+            uint32_t w0 = reads->read_win_begin[r], w1 = reads->read_win_begin[r + 1];
+            if (w0 == w1) continue;                               // CONSENT-correction.cpp:23-25
+            std::vector<std::string> consensuses, templates;
+            std::vector<robin_hood::unordered_map<kmer, unsigned>> merCounts(w1 - w0);
+            std::vector<std::pair<unsigned, unsigned>> pilesPos;
+            for (uint32_t w = w0; w < w1; ++w) {
+                consensuses.emplace_back(cons->cons + cons->cons_off[w], cons->cons + cons->cons_off[w + 1]);
+                uint32_t s0 = win->win_seq_begin[w];
+                templates.emplace_back(win->bases + win->seq_off[s0], win->bases + win->seq_off[s0 + 1]);
+                for (uint64_t i = cons->solid_off[w]; i < cons->solid_off[w + 1]; ++i)
+                    merCounts[w - w0][cons->solid_kmer[i]] = cons->solid_count[i];
+                pilesPos.emplace_back(reads->win_pos[w], reads->win_pos[w] + reads->window_size - 1);
+            }
+            std::string seq(reads->read_bases + reads->read_off[r], reads->read_bases + reads->read_off[r + 1]);
+            res[r] = alignConsensus(std::string("r"), seq, consensuses, merCounts, pilesPos, templates,
+                                    (int)pilesPos[0].first, reads->window_size, reads->window_overlap,
+                                    p->solid_thresh, p->mer_size);
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; ++t) pool.emplace_back(worker);
+    worker();
+    for (auto& t : pool) t.join();
+    auto t1 = std::chrono::steady_clock::now();
+    if (seconds) *seconds = std::chrono::duration<double>(t1 - t0).count();
+    CorrectedOwner* ow = new CorrectedOwner();
+    ow->off.resize(R + 1, 0);
+    for (uint32_t r = 0; r < R; ++r) { ow->bases += res[r]; ow->off[r + 1] = ow->bases.size(); }
+    out->n_reads = R;
+    out->read_off = ow->off.data();
+    out->bases = const_cast<char*>(ow->bases.data());
+    out->owner_ = ow;
+    return CG_OK;
+}
+
+void ref_free_corrected(cg_corrected* c) {
+    if (c && c->owner_) { delete static_cast<CorrectedOwner*>(c->owner_); c->owner_ = nullptr; }
 }
 
 // Per-stage text dump of one window, produced by calling the reference's own

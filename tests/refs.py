@@ -5,8 +5,8 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-from consent_b200._ffi import (Batch, Params, REPO_DIR, Results, cg_batch, cg_counters, cg_params,
-                               cg_results)
+from consent_b200._ffi import (Batch, Corrected, Params, REPO_DIR, Reads, Results, cg_batch, cg_corrected,
+                               cg_counters, cg_params, cg_reads, cg_results, results_to_c)
 
 ORACLE_DIR = os.path.join(REPO_DIR, "oracle")
 
@@ -51,6 +51,22 @@ class _Checker:
         self._msa.argtypes = [C.POINTER(C.c_char_p), C.c_uint32]
         self._free_text = getattr(self.lib, self.prefix + "_free_text")
         self._free_text.argtypes = [C.c_void_p]
+
+    def reanchor_reads(self, batch: Batch, res: Results, reads: Reads, params: Params = Params(), threads: int = 1):
+        """alignConsensus for every read -> (Corrected, seconds of the compute loop)"""
+        f = getattr(self.lib, self.prefix + "_reanchor_reads")
+        f.restype = C.c_int
+        f.argtypes = [C.POINTER(cg_batch), C.POINTER(cg_results), C.POINTER(cg_reads), C.POINTER(cg_params), C.c_int,
+                      C.POINTER(cg_corrected), C.POINTER(C.c_double)]
+        free = getattr(self.lib, self.prefix + "_free_corrected")
+        free.argtypes = [C.POINTER(cg_corrected)]
+        cb, cr, rd, cp, out, sec = batch.c(), results_to_c(res), reads.c(), params.c(), cg_corrected(), C.c_double(0)
+        rc = f(C.byref(cb), C.byref(cr), C.byref(rd), C.byref(cp), threads, C.byref(out), C.byref(sec))
+        if rc != 0:
+            raise RuntimeError(f"{self.prefix}_reanchor_reads -> {rc}")
+        got = Corrected(out)
+        free(C.byref(out))
+        return got, sec.value
 
     def correct_windows(self, batch: Batch, params: Params = Params(), threads: int = 1,
                         with_status: bool = True):
