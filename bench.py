@@ -12,6 +12,9 @@ quoted on, BASELINE.json configs[2] = 100 000 windows of 500 bases x 150 sequenc
                H2D of the piles, every kernel, D2H of consensus + solid k-mers inside the timed region
   roofline     dominant kernel: algorithmic bytes per launch / its CUDA-event time, against MEASURED_PEAKS.json
   cpu_baseline the reference's own CPU code (oracle/_ref) on this box's host cores, bounded sample of the same stream
+  reanchor     (N=1) the next row of SURVEY §8f on its own bounded workload: alignConsensus for every read
+               (cg_reanchor_reads) — kernel windows/s and GCUPS from CUDA events, the two-stage call chain
+               cg_correct_windows -> cg_reanchor_reads with host buffers, and the reference's alignConsensus on the host cores
   --impl reference : times that CPU implementation as the arm itself.
 """
 from __future__ import annotations
@@ -148,6 +151,57 @@ def algorithmic_bytes(counters: dict, n_occ: int) -> dict:
     return {"in": b_in, "out": b_out, "poa": b_dp, "index": b_idx, "window_total": b_in + b_out + b_dp}
 
 
+def bench_reanchor(cor, n_reads: int, cores: int, steps: int) -> dict:
+    """Consensus re-anchoring on its own bounded workload: seeded 8 kb PB reads, 20 sequences per
+    window.  Kernel time from CUDA events (cg_reanchor_stats); the chain cg_correct_windows -> cg_reanchor_reads with
+    host buffers; the reference's own alignConsensus (oracle/_ref) on a sample of the same reads, all host threads."""
+    import torch
+    from consent_b200._ffi import Reads, Results
+    from consent_b200.synth import synth_reads
+    batch, reads = synth_reads(n_reads, 20, truth_len=8000, seed=42)
+    live = cor.correct_windows(batch)
+    cor.reanchor_reads(batch, live, reads)                                  # warm-up (allocations)
+    k_ms = []
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        live = None
+        live = cor.correct_windows(batch)
+        got = cor.reanchor_reads(batch, live, reads)
+        k_ms.append(cor.reanchor_stats()["kernel_ms"])
+    torch.cuda.synchronize()
+    chain_s = (time.perf_counter() - t0) / steps
+    st = cor.reanchor_stats()
+    kernel_ms = float(np.mean(k_ms))
+    out = {"workload": f"{n_reads} synthetic 8 kb PB reads (seed 42), {batch.n_windows} windows x 20 seqs, window 500 / overlap 50",
+           "windows": batch.n_windows, "reads": n_reads,
+           "kernel_ms": kernel_ms, "kernel_windows_per_s": batch.n_windows / (kernel_ms / 1e3),
+           "dp_cells": st["dp_cells"], "gcups": st["dp_cells"] / (kernel_ms / 1e3) / 1e9,
+           "chain_windows_per_s": batch.n_windows / chain_s,
+           "chain": "cg_correct_windows + cg_reanchor_reads, host buffers in / corrected reads out"}
+    try:
+        checker, kind = cpu_reference(batch, cores)
+        n = min(n_reads, max(64 * cores, 1024))
+        w1 = int(reads.read_win_begin[n])
+        sub_batch = batch.slice(0, w1)
+        sub_reads = Reads(reads.read_win_begin[:n + 1], reads.read_off[:n + 1], reads.read_bases[:int(reads.read_off[n])],
+                          reads.win_pos[:w1])
+        host = Results(live._r)
+        sub_res = Results.__new__(Results)
+        sub_res.n_windows = w1
+        sub_res._r = sub_res._free = None
+        c1, s1 = int(host.cons_off[w1]), int(host.solid_off[w1])
+        sub_res.cons_off, sub_res.cons, sub_res.status = host.cons_off[:w1 + 1], host.cons[:c1], host.status[:w1]
+        sub_res.solid_off, sub_res.solid_kmer, sub_res.solid_count = host.solid_off[:w1 + 1], host.solid_kmer[:s1], host.solid_count[:s1]
+        want, sec = checker.reanchor_reads(sub_batch, sub_res, sub_reads, threads=cores)
+        out["cpu_reference"] = {"value": w1 / sec, "unit": "windows/s", "cores": cores, "kind": kind,
+                                "sample": f"first {n} reads ({w1} windows), {sec:.2f} s, all host threads"}
+        out["parity_spot_check"] = all(got.read(r) == want.read(r) for r in range(n))
+    except Exception as e:
+        out["cpu_reference"] = {"value": None, "kind": "unavailable", "sample": repr(e)}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -159,6 +213,8 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--chunk-windows", type=int, default=0, help="windows per chunk (0: library default); never changes results")
     ap.add_argument("--lanes", type=int, default=0, help="chunks in flight (0: library default = 2); never changes results")
+    ap.add_argument("--reanchor-reads", type=int, default=int(os.environ.get("CG_BENCH_REANCHOR_READS", "2600")),
+                    help="reads of the re-anchoring measurement (0: skip it)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -320,13 +376,20 @@ def main():
         except Exception as e:  # the checker is optional for the bench line
             cpu = {"value": None, "unit": "windows/s", "cores": cores, "kind": "unavailable", "sample": repr(e)}
 
+    reanchor = None
+    if world == 1 and args.reanchor_reads > 0:
+        try:
+            reanchor = bench_reanchor(cor, args.reanchor_reads, cores, args.steps)
+        except Exception as e:
+            reanchor = {"error": repr(e)}
+
     out = {"metric": METRIC, "value": value, "unit": "windows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "int16/u8", "data": "synthetic", "config": config, "clocks": clocks,
            "e2e": {"value": world * args.windows * args.steps / e2e_s, "unit": "windows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
            "gpu_launches": launches, "wall_ms_per_step": wall_ms / args.steps,
            "roofline": roofline, "cpu_baseline": cpu,
-           "counters_per_step": counters}
+           "counters_per_step": counters, "reanchor": reanchor}
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()

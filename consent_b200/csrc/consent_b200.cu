@@ -1051,10 +1051,15 @@ int cg_reanchor_reads(cg_handle* h, const cg_batch* windows, const cg_results* c
     A.head = h->ra_head.as<char>(); A.head_off = h->ra_head_off.as<u64>(); A.out_len = h->ra_len.as<u32>();
     A.scratch = h->ra_scratch.as<u8>(); A.scratch_stride = stride; A.maxL = maxL; A.rmax = rmax; A.dir_cap = dir_cap;
     A.ctl = h->ra_ctl.as<u32>();
+    const size_t smem_ref = (size_t)CG_RA_WARPS * ((rmax + 15u) & ~15u);
+    size_t smem = smem_ref + (size_t)CG_RA_WARPS * 3 * cg_ra_line_bytes(maxL);
+    A.lines_in_smem = smem <= 72 * 1024 ? 1u : 0u;                           // 3 CTAs per SM keep their lines on chip
+    if (!A.lines_in_smem) smem = smem_ref;
+    CK(cudaFuncSetAttribute(k_reanchor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     CK(cudaEventRecord(e0, st));
-    if (R) CG_LAUNCH(k_reanchor, ctas, CG_RA_WARPS * 32, (size_t)CG_RA_WARPS * ((rmax + 15u) & ~15u), st, A);
+    if (R) CG_LAUNCH(k_reanchor, ctas, CG_RA_WARPS * 32, smem, st, A);
     CK(cudaEventRecord(e1, st));
     CK(cudaGetLastError());
     // ---- lengths -> dense offsets -> gather -> host

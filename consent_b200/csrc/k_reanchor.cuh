@@ -42,6 +42,7 @@ struct CgReanchorArgs {
     char* head; const u64* head_off; u32* out_len;
     // per resident warp scratch
     u8* scratch; u64 scratch_stride; u32 maxL, rmax; u64 dir_cap;
+    u32 lines_in_smem;           // the three rolling lines of the banded DP live in shared memory (else in the scratch)
     u32* ctl;                    // [0] next read, [1] flags, [2..3] DP cells (u64)
 };
 
@@ -79,13 +80,70 @@ __device__ __forceinline__ int cg_ra_wsum(int v) {
 
 struct CgRaEnd { int score, col, row; };
 
+// One band of a scan: query rows [row0, row0 + 32 * RPL) (rows >= nq are padding), every reference column.  RPL rows per
+// lane, all in registers.  The only loop-carried chain inside a lane is F: with hp = max(diag + s, E) and g = max(hp - 3, 0),
+//   F' = max(F - 1, max(H - 3, 0)) = max(F - 1, g)          (H = max(hp, F), and F - 3 < F - 1)
+// so a column costs RPL dependent VIADDMNMX and everything else (hp, g, H, E, the column maximum) is independent work.
+template <int RPL>
+__device__ __forceinline__ void cg_ra_band(const char* qsrc, int qfirst, int qstep, int nq, int row0, const u8* refc, int rfirst, int rstep,
+                                           int nr, const u32* in_msgs, u32* out_msgs, bool first_band, bool last_band,
+                                           int& best, int& bcol, int& brow) {
+    const int lane = (int)(threadIdx.x & 31u);
+    int H[RPL], E[RPL];
+    u32 qc[RPL];
+    const int my0 = row0 + lane * RPL;
+#pragma unroll
+    for (int i = 0; i < RPL; ++i) {
+        H[i] = 0; E[i] = 0;
+        u32 code = 7u;                                             // padding row: matches nothing
+        if (my0 + i < nq) {
+            code = cg_ra_code(qsrc[qfirst + qstep * (my0 + i)]);
+            if (code == 4u) code = 5u;                             // N never matches, not even N (ssw_cpp.cpp:47-55)
+        }
+        qc[i] = code;
+    }
+    int diag_in = 0;
+    u32 out_msg = 0;
+    const int n_steps = nr + 31;
+    for (int t = 0; t < n_steps; ++t) {
+        // lane 0 is fed from shared memory (every lane reads the same word: a broadcast), the others from their neighbour
+        const int tt = min(t, nr - 1);
+        const u32 feed = first_band ? (u32)refc[rfirst + rstep * tt] : in_msgs[tt];
+        const u32 up_msg = __shfl_up_sync(CG_FULL, out_msg, 1);
+        const u32 in_msg = lane == 0 ? feed : up_msg;
+        const int c = t - lane;
+        if (c >= 0 && c < nr) {
+            const u32 rc = in_msg & 7u;
+            int f = (int)((in_msg >> 4) & 0x3fffu);
+            int d = diag_in;
+            diag_in = (int)(in_msg >> 18);
+            int colkey = 0, h = 0;                                 // max over rows of (h << 5 | RPL - 1 - i): maximum and its first row
+#pragma unroll
+            for (int i = 0; i < RPL; ++i) {
+                const int hp = max(d + (qc[i] == rc ? 2 : -2), E[i]);      // E, f >= 0: the floor at 0 is implied
+                const int g = max(hp - 3, 0);
+                h = max(hp, f);
+                f = max(f - 1, g);
+                d = H[i]; H[i] = h;
+                colkey = max(colkey, h * 32 + (RPL - 1 - i));
+                E[i] = max(E[i] - 1, max(h - 3, 0));
+            }
+            out_msg = ((u32)h << 18) | ((u32)f << 4) | rc;
+            if (!last_band && lane == 31) out_msgs[c] = out_msg;
+            const int colmax = colkey >> 5;
+            if (colmax > best || (colmax == best && c < bcol && colmax > 0)) {
+                best = colmax; bcol = c; brow = my0 + (RPL - 1 - (colkey & 31));
+            }
+        }
+    }
+}
+
 // One scan of the local-alignment matrix by a warp.  Query row j = qsrc[qfirst + qstep * j], j in [0, nq); column c =
 // refc[rfirst + rstep * c] (codes in shared memory), c in [0, nr).  Returns the score, the first column whose maximum
-// reaches it and the smallest row holding it there.  bnd: 4 * rmax u16 of per-warp scratch (band boundaries when
-// nq > 32 * CG_RA_RPL).
+// reaches it and the smallest row holding it there.  bnd: 2 * rmax u32 of per-warp scratch (the wavefront messages of a
+// band's last row, read back by lane 0 of the next band, when nq > 32 * CG_RA_RPL).
 __device__ CG_NOINLINE CgRaEnd cg_ra_scan(const char* qsrc, int qfirst, int qstep, int nq, const u8* refc, int rfirst, int rstep,
-                                          int nr, u16* bnd, u32 rmax) {
-    const int lane = (int)(threadIdx.x & 31u);
+                                          int nr, u32* bnd, u32 rmax) {
     int best = 0, bcol = 0x7fffffff, brow = 0x7fffffff;
     const int band_rows = 32 * (int)CG_RA_RPL;
     const int n_bands = (nq + band_rows - 1) / band_rows;
@@ -94,65 +152,16 @@ __device__ CG_NOINLINE CgRaEnd cg_ra_scan(const char* qsrc, int qfirst, int qste
         const int rows = min(band_rows, nq - row0);
         const int rpl = (rows + 31) / 32;                          // warp-uniform
         const bool last_band = b + 1 == n_bands;
-        const u16* inH = bnd + (size_t)((b + 1) & 1) * 2 * rmax;   // written by band b - 1
-        const u16* inF = inH + rmax;
-        u16* outH = bnd + (size_t)(b & 1) * 2 * rmax;
-        u16* outF = outH + rmax;
-        int H[CG_RA_RPL], E[CG_RA_RPL];
-        u32 qc[CG_RA_RPL];
-        const int my0 = row0 + lane * rpl;
-#pragma unroll
-        for (int i = 0; i < (int)CG_RA_RPL; ++i) {
-            H[i] = 0; E[i] = 0;
-            u32 code = 7u;                                         // padding row: matches nothing
-            if (i < rpl && my0 + i < nq) {
-                code = cg_ra_code(qsrc[qfirst + qstep * (my0 + i)]);
-                if (code == 4u) code = 5u;                         // N never matches, not even N (ssw_cpp.cpp:47-55)
-            }
-            qc[i] = code;
-        }
-        int diag_in = 0;
-        u32 out_msg = 0;
-        const int n_steps = nr + 31;
-        for (int t = 0; t < n_steps; ++t) {
-            u32 in_msg = __shfl_up_sync(CG_FULL, out_msg, 1);
-            if (lane == 0) {
-                in_msg = 0;
-                if (t < nr) {
-                    in_msg = (u32)refc[rfirst + rstep * t];
-                    if (b > 0) in_msg |= ((u32)inH[t] << 18) | ((u32)inF[t] << 4);
-                }
-            }
-            const int c = t - lane;
-            if (c >= 0 && c < nr) {
-                const u32 rc = in_msg & 7u;
-                int f = (int)((in_msg >> 4) & 0x3fffu);
-                int d = diag_in;
-                diag_in = (int)(in_msg >> 18);
-                int colmax = 0, h = 0;
-#pragma unroll
-                for (int i = 0; i < (int)CG_RA_RPL; ++i) {
-                    if (i < rpl) {
-                        const int s = qc[i] == rc ? 2 : -2;
-                        h = max(max(d + s, E[i]), f);              // E, f >= 0: the floor at 0 is implied
-                        d = H[i]; H[i] = h;
-                        colmax = max(colmax, h);
-                        const int open = max(h - 3, 0);
-                        E[i] = max(E[i] - 1, open);
-                        f = max(f - 1, open);
-                    }
-                }
-                out_msg = ((u32)h << 18) | ((u32)f << 4) | rc;
-                if (!last_band && lane == 31) { outH[c] = (u16)h; outF[c] = (u16)f; }
-                if (colmax > best || (colmax == best && c < bcol && colmax > 0)) {
-                    int r = 0;
-#pragma unroll
-                    for (int i = (int)CG_RA_RPL - 1; i >= 0; --i)
-                        if (i < rpl && H[i] == colmax) r = i;
-                    best = colmax; bcol = c; brow = my0 + r;
-                }
-            }
-        }
+        const u32* in_msgs = bnd + (size_t)((b + 1) & 1) * rmax;    // written by band b - 1
+        u32* out_msgs = bnd + (size_t)(b & 1) * rmax;
+#define CG_RA_BAND(R) cg_ra_band<R>(qsrc, qfirst, qstep, nq, row0, refc, rfirst, rstep, nr, in_msgs, out_msgs, b == 0, last_band, best, bcol, brow)
+        if (rpl <= 4) CG_RA_BAND(4);
+        else if (rpl <= 8) CG_RA_BAND(8);
+        else if (rpl <= 12) CG_RA_BAND(12);
+        else if (rpl <= 16) CG_RA_BAND(16);
+        else if (rpl <= 18) CG_RA_BAND(18);
+        else CG_RA_BAND(20);
+#undef CG_RA_BAND
         __syncwarp();
     }
     CgRaEnd e;
@@ -206,22 +215,28 @@ __device__ CG_NOINLINE u32 cg_ra_banded(const u8* refc, const char* read, int re
             u8* d = dir + (size_t)stride * (size_t)i;
             u32 rcode = cg_ra_code(read[i]);
             if (rcode == 4u) rcode = 5u;
+            // slot(i, j - 1) = slot(i, j) - 1 and slot(i - 1, j - 1) = slot(i - 1, j) - 1: the left neighbour and the diagonal
+            // of a cell are what the previous cell wrote / read, so they travel in registers (h_left, h_diag)
+            int h_left = 0;                                              // h_cur[slot(i, beg - 1)] = h_cur[0]
+            int h_diag = h_prev[cg_ra_slot(w, i - 1, beg - 1)];
             for (int j = beg; j <= end; ++j) {
-                const int u = cg_ra_slot(w, i, j), up = cg_ra_slot(w, i - 1, j), left = cg_ra_slot(w, i, j - 1), dg = cg_ra_slot(w, i - 1, j - 1);
-                int a = i == 0 ? -3 : h_prev[up] - 3;
+                const int u = cg_ra_slot(w, i, j), up = cg_ra_slot(w, i - 1, j);
+                const int h_up = h_prev[up];
+                int a = i == 0 ? -3 : h_up - 3;
                 int b = i == 0 ? -1 : e_line[up] - 1;
                 const int e = a > b ? a : b;
                 const u32 de = a > b ? 3u : 2u;
                 e_line[u] = e;
-                a = h_cur[left] - 3;
+                a = h_left - 3;
                 b = f - 1;
                 f = a > b ? a : b;
                 const u32 df = a > b ? 5u : 4u;
                 const int e1 = max(e, 0), f1 = max(f, 0);
                 const int gap = max(e1, f1);
-                const int diag = h_prev[dg] + ((u32)refc[j] == rcode ? 2 : -2);
+                const int diag = h_diag + ((u32)refc[j] == rcode ? 2 : -2);
                 const int h = max(gap, diag);
                 h_cur[u] = h;
+                h_left = h; h_diag = h_up;
                 best = max(best, h);
                 const u32 dh = gap <= diag ? 1u : (e1 > f1 ? de : df);
                 d[j - beg] = (u8)((de & 1u) | ((df & 1u) << 1) | (dh << 2));
@@ -280,16 +295,17 @@ __global__ void __launch_bounds__(CG_RA_WARPS * 32) k_reanchor(CgReanchorArgs P)
     CG_DYN_SMEM(smem_raw);
     const u32 lane = threadIdx.x & 31u, wip = threadIdx.x >> 5;
     const u32 rpad = (P.rmax + 15u) & ~15u;
-    u8* refc = (u8*)smem_raw + (size_t)wip * rpad;
+    const size_t smem_per_warp = rpad + (P.lines_in_smem ? 3 * (size_t)cg_ra_line_bytes(P.maxL) : 0);
+    u8* refc = (u8*)smem_raw + (size_t)wip * smem_per_warp;
     const u32 gw = blockIdx.x * CG_RA_WARPS + wip;
     u8* sc = P.scratch + (size_t)gw * P.scratch_stride;
     char* bufs[3];
     bufs[0] = (char*)sc; bufs[1] = bufs[0] + cg_ra_buf_bytes(P.maxL); bufs[2] = bufs[1] + cg_ra_buf_bytes(P.maxL);
-    u16* bnd = (u16*)(bufs[2] + cg_ra_buf_bytes(P.maxL));
-    i32* line0 = (i32*)((u8*)bnd + cg_ra_bnd_bytes(P.rmax));
+    u32* bnd = (u32*)(bufs[2] + cg_ra_buf_bytes(P.maxL));
+    i32* line0 = P.lines_in_smem ? (i32*)(refc + rpad) : (i32*)((u8*)bnd + cg_ra_bnd_bytes(P.rmax));
     i32* line1 = (i32*)((u8*)line0 + cg_ra_line_bytes(P.maxL));
     i32* line2 = (i32*)((u8*)line1 + cg_ra_line_bytes(P.maxL));
-    u8* dir = (u8*)line2 + cg_ra_line_bytes(P.maxL);
+    u8* dir = (u8*)bnd + cg_ra_bnd_bytes(P.rmax) + 3 * cg_ra_line_bytes(P.maxL);
     u64 cells = 0;
     u32 flags = 0;
 
