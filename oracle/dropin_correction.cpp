@@ -1,0 +1,111 @@
+// dropin_correction.cpp — TEST INFRASTRUCTURE: the binding of INTEGRATION.md made real.
+//
+// The reference's CONSENT-correction binary with its per-window / per-read hot path replaced by two calls into
+// libconsent_b200.so.  Everything else is the reference's OWN, UNMODIFIED host code, compiled from /root/reference where
+// it lies (oracle/Makefile, target `dropin`): PAF pile reading (src/alignmentPiles.cpp), window positions and piles
+// (src/alignmentWindows.cpp), read index / trimRead / dropRead (src/utils.cpp), reverse complement.
+//
+// processRead (src/CONSENT-correction.cpp:19-60) is cut in two around the GPU, as INTEGRATION.md describes:
+//   phase A  per read: getSequencesMap, getAlignmentWindowsPositions, getAlignmentWindowsSequences  (:21-35)
+//            -> the flat cg_batch / cg_reads arrays instead of one computeConsensusReadCorrection call per window
+//   GPU      cg_correct_windows  (= every computeConsensusReadCorrection of the batch, :36)
+//            cg_reanchor_reads   (= every alignConsensus of the batch, :47)
+//   phase B  per read, in PAF order: trimRead / dropRead and the FASTA record (:50-59, :100-103)
+// Same command line as bin/CONSENT-correction (src/main.cpp:27-80).  tests/test_dropin_example.py runs it on a B200 and
+// compares its FASTA byte for byte with the one the unmodified reference binary printed for the same PAF.
+#include <getopt.h>
+#include <unistd.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <string>
+#include <vector>
+
+#include "alignmentPiles.h"      // reference src/
+#include "alignmentWindows.h"
+#include "utils.h"
+#include "consent_b200.h"        // our ABI
+
+static void die(const char* what, const char* why) { fprintf(stderr, "consent_correction_b200: %s: %s\n", what, why ? why : ""); exit(1); }
+
+int main(int argc, char** argv) {
+    std::string alignmentFile, readsFile;
+    unsigned minSupport = 3, maxSupport = 1000, windowSize = 500, merSize = 9, commonKMers = 8, minAnchors = 10,
+             solidThresh = 4, windowOverlap = 50;                                       // src/main.cpp:15-24
+    int opt, device = 0;
+    while ((opt = getopt(argc, argv, "a:A:d:k:s:S:M:l:f:e:p:c:m:j:w:r:R:n:i:g:")) != -1) {
+        switch (opt) {
+            case 'a': alignmentFile = optarg; break;
+            case 's': minSupport = atoi(optarg); break;
+            case 'S': maxSupport = atoi(optarg); break;
+            case 'l': windowSize = atoi(optarg); break;
+            case 'k': merSize = atoi(optarg); break;
+            case 'c': commonKMers = atoi(optarg); break;
+            case 'A': minAnchors = atoi(optarg); break;
+            case 'f': solidThresh = atoi(optarg); break;
+            case 'm': windowOverlap = atoi(optarg); break;
+            case 'r': readsFile = optarg; break;
+            case 'g': device = atoi(optarg); break;
+            default: break;                                                             // -j -M -p ...: no meaning here
+        }
+    }
+    if (alignmentFile.empty() || readsFile.empty()) die("usage", "-a alignments.paf -r reads.fasta [-s -S -l -k -c -A -f -m as bin/CONSENT-correction] [-g gpu]");
+
+    robin_hood::unordered_map<std::string, std::vector<bool>> readIndex;
+    indexReads(readIndex, readsFile);
+    std::ifstream alignments(alignmentFile);
+
+    // ---- phase A
+    std::vector<uint32_t> winSeqBegin(1, 0), readWinBegin(1, 0), winPos;
+    std::vector<uint64_t> seqOff(1, 0), readOff(1, 0);
+    std::string bases, readBases;
+    std::vector<std::string> readIds;
+    while (!alignments.eof()) {
+        std::vector<Overlap> al = getNextReadPile(alignments, maxSupport);
+        if (al.size() == 0) continue;
+        std::string readId = al.begin()->qName;
+        robin_hood::unordered_map<std::string, std::string> sequences = getSequencesMap(al, readIndex);
+        std::vector<std::pair<unsigned, unsigned>> pilesPos =
+            getAlignmentWindowsPositions(al.begin()->qLength, al, minSupport, maxSupport, windowSize, windowOverlap);
+        for (unsigned i = 0; i < pilesPos.size(); i++) {
+            std::vector<std::string> pile = getAlignmentWindowsSequences(al, minSupport, windowSize, windowOverlap, sequences,
+                                                                         pilesPos[i].first, pilesPos[i].second, merSize, maxSupport, commonKMers);
+            if (pile.empty()) die("empty pile", "the reference dereferences curPile[0] here (CONSENT-correction.cpp:36)");
+            for (const std::string& s : pile) { bases += s; seqOff.push_back(bases.size()); }
+            winSeqBegin.push_back((uint32_t)(seqOff.size() - 1));
+            winPos.push_back(pilesPos[i].first);
+        }
+        readIds.push_back(readId);
+        readBases += sequences[al[0].qName];
+        readOff.push_back(readBases.size());
+        readWinBegin.push_back((uint32_t)winPos.size());
+    }
+
+    // ---- GPU
+    cg_params prm = {merSize, solidThresh, commonKMers, minAnchors};
+    cg_handle* h = nullptr;
+    if (cg_create(device, &prm, &h) != CG_OK) die("cg_create", cg_last_error(nullptr));
+    if (bases.empty()) bases.push_back('A');
+    if (readBases.empty()) readBases.push_back('A');
+    if (winPos.empty()) winPos.push_back(0);
+    cg_batch in = {(uint32_t)(winSeqBegin.size() - 1), winSeqBegin.data(), seqOff.data(), bases.data()};
+    cg_results res;
+    if (cg_correct_windows(h, &in, &res) != CG_OK) die("cg_correct_windows", cg_last_error(h));
+    cg_reads rd = {(uint32_t)readIds.size(), readWinBegin.data(), readOff.data(), readBases.data(), winPos.data(), windowSize, windowOverlap};
+    cg_corrected cor;
+    if (cg_reanchor_reads(h, &in, &res, &rd, &cor) != CG_OK) die("cg_reanchor_reads", cg_last_error(h));
+
+    // ---- phase B (CONSENT-correction.cpp:50-59,100-103): doTrimRead is true without a proof file
+    for (size_t r = 0; r < readIds.size(); ++r) {
+        if (readWinBegin[r + 1] == readWinBegin[r]) continue;                           // :23-25: no window, nothing printed
+        std::string corrected(cor.bases + cor.read_off[r], cor.bases + cor.read_off[r + 1]);
+        corrected = trimRead(corrected, 1);
+        if (!dropRead(corrected) && corrected.length() != 0) std::cout << ">" << readIds[r] << std::endl << corrected << std::endl;
+    }
+    cg_free_corrected(&cor);
+    cg_free_results(&res);
+    cg_destroy(h);
+    return 0;
+}

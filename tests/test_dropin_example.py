@@ -1,0 +1,67 @@
+"""BASELINE config 1 shape, end to end: PAF piles of the shipped example -> corrected FASTA.
+
+oracle/_ref/consent_correction_b200 (oracle/dropin_correction.cpp) is the reference's own host code — PAF pile reading,
+window extraction, trimming, FASTA output, compiled unmodified from /root/reference — with the hot path replaced by the two
+calls INTEGRATION.md describes (cg_correct_windows, cg_reanchor_reads).  Its output must be byte-identical to what the
+unmodified reference binary printed for the same input (tests/golden/example_small_corrected.fasta.gz, written by
+tests/golden/make_example_small.py)."""
+import gzip
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+REFDIR = os.path.join(ROOT, "oracle", "_ref")
+FLAGS = ["-s", "3", "-S", "150", "-l", "500", "-k", "9", "-c", "8", "-A", "2", "-f", "4", "-m", "50", "-M", "150"]   # CONSENT-correct:42-50
+
+
+@pytest.fixture(scope="module")
+def small(tmp_path_factory):
+    d = tmp_path_factory.mktemp("example_small")
+    paf, fa = str(d / "small.paf"), str(d / "small.fasta")
+    open(paf, "wb").write(gzip.open(os.path.join(GOLD, "example_small.paf.gz")).read())
+    open(fa, "wb").write(gzip.open(os.path.join(GOLD, "example_small_reads.fasta.gz")).read())
+    want = gzip.open(os.path.join(GOLD, "example_small_corrected.fasta.gz")).read()
+    return d, paf, fa, want
+
+
+def _binary(name):
+    p = os.path.join(REFDIR, name)
+    if not os.path.exists(p):
+        pytest.skip(f"oracle/_ref/{name} not built (make -C oracle dropin needs /root/reference)")
+    return p
+
+
+def test_golden_fasta_is_what_the_unmodified_reference_prints(small):
+    """Pins the golden file against the reference binary itself (where it was built)."""
+    d, paf, fa, want = small
+    out = subprocess.run([_binary("consent_correction_ref"), "-a", paf, "-r", fa, "-j", "4", "-p", "/nonexistent"] + FLAGS,
+                         check=True, capture_output=True).stdout
+    assert out.count(b">") == 20
+    assert out == want
+
+
+def test_dropin_binary_on_emulated_kernels_prints_the_reference_fasta(small, entry):
+    """The reference's host code + this repo's kernel sources (SIMT emulator) = the reference's FASTA, byte for byte."""
+    d, paf, fa, want = small
+    exe = _binary("consent_correction_b200")
+    emu = entry.build_emu()
+    libdir = d / "emulib"
+    libdir.mkdir(exist_ok=True)
+    link = libdir / "libconsent_b200.so"
+    if not link.exists():
+        os.symlink(emu, link)
+    env = dict(os.environ, LD_LIBRARY_PATH=str(libdir))
+    out = subprocess.run([exe, "-a", paf, "-r", fa] + FLAGS, check=True, capture_output=True, env=env).stdout
+    assert out == want
+
+
+@pytest.mark.gpu
+def test_dropin_binary_on_the_gpu_prints_the_reference_fasta(small, gpu_lib):
+    """The same through libconsent_b200.so on a B200: bit-exact corrected FASTA for the real-data example."""
+    d, paf, fa, want = small
+    out = subprocess.run([_binary("consent_correction_b200"), "-a", paf, "-r", fa] + FLAGS, check=True, capture_output=True).stdout
+    assert out.count(b">") == 20
+    assert out == want
