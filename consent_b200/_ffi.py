@@ -64,6 +64,27 @@ class cg_corrected(C.Structure):
                 ("owner_", C.c_void_p)]
 
 
+class cg_overlap(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("t_read", "strand", "q_start", "q_end", "t_start", "t_end", "t_length")]
+
+
+class cg_piles(C.Structure):
+    _fields_ = [("n_store", C.c_uint32), ("store_off", C.POINTER(C.c_uint64)), ("store_bases", C.c_char_p),
+                ("n_piles", C.c_uint32), ("pile_read", C.POINTER(C.c_uint32)), ("pile_qlen", C.POINTER(C.c_uint32)),
+                ("pile_ov_begin", C.POINTER(C.c_uint32)), ("overlaps", C.POINTER(cg_overlap)),
+                ("min_support", C.c_uint32), ("window_size", C.c_uint32), ("window_overlap", C.c_uint32)]
+
+
+class cg_window_set(C.Structure):
+    _fields_ = [("batch", cg_batch), ("reads", cg_reads), ("win_end", C.POINTER(C.c_uint32)), ("owner_", C.c_void_p)]
+
+
+class cg_synth_pile_spec(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("genome_len", C.c_uint32), ("n_reads", C.c_uint32), ("read_len", C.c_uint32),
+                ("n_piles", C.c_uint32), ("max_support", C.c_uint32), ("min_overlap", C.c_uint32),
+                ("err", C.c_double), ("p_sub", C.c_double), ("p_ins", C.c_double)]
+
+
 class cg_synth_read_spec(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("first_read", C.c_uint32), ("n_reads", C.c_uint32),
                 ("n_seqs", C.c_uint32), ("truth_len", C.c_uint32),
@@ -201,6 +222,61 @@ class Reads:
                         C.cast(self.read_bases.ctypes.data, C.c_char_p),
                         self.win_pos.ctypes.data_as(C.POINTER(C.c_uint32)),
                         self.window_size, self.window_overlap)
+
+
+class Piles:
+    """Read store + read piles in the flat layout of cg_piles (host memory, numpy-owned).  overlaps: (n, 7) uint32 rows
+    (t_read, strand, q_start, q_end, t_start, t_end, t_length), ends inclusive as src/Overlap.h keeps them."""
+
+    def __init__(self, store_off, store_bases, pile_read, pile_qlen, pile_ov_begin, overlaps,
+                 min_support: int = 3, window_size: int = 500, window_overlap: int = 50):
+        self.store_off = np.ascontiguousarray(store_off, dtype=np.uint64)
+        self.store_bases = np.ascontiguousarray(store_bases, dtype=np.uint8)
+        self.pile_read = np.ascontiguousarray(pile_read, dtype=np.uint32)
+        self.pile_qlen = np.ascontiguousarray(pile_qlen, dtype=np.uint32)
+        self.pile_ov_begin = np.ascontiguousarray(pile_ov_begin, dtype=np.uint32)
+        self.overlaps = np.ascontiguousarray(overlaps, dtype=np.uint32).reshape(-1, 7)
+        for n in ("store_bases", "pile_read", "pile_qlen"):
+            if len(getattr(self, n)) == 0:
+                setattr(self, n, np.zeros(1, getattr(self, n).dtype))
+        if len(self.overlaps) == 0:
+            self.overlaps = np.zeros((1, 7), np.uint32)
+        self.min_support, self.window_size, self.window_overlap = int(min_support), int(window_size), int(window_overlap)
+
+    @property
+    def n_piles(self) -> int:
+        return len(self.pile_ov_begin) - 1
+
+    @property
+    def n_store(self) -> int:
+        return len(self.store_off) - 1
+
+    def c(self) -> cg_piles:
+        u32, u64 = C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)
+        return cg_piles(self.n_store, self.store_off.ctypes.data_as(u64), C.cast(self.store_bases.ctypes.data, C.c_char_p),
+                        self.n_piles, self.pile_read.ctypes.data_as(u32), self.pile_qlen.ctypes.data_as(u32),
+                        self.pile_ov_begin.ctypes.data_as(u32), C.cast(self.overlaps.ctypes.data, C.POINTER(cg_overlap)),
+                        self.min_support, self.window_size, self.window_overlap)
+
+
+def window_set_to_py(ws: cg_window_set, with_bases: bool = True):
+    """Copies a cg_window_set out: -> (Batch, Reads, win_end)."""
+    W, R = int(ws.batch.n_windows), int(ws.reads.n_reads)
+    wsb = np.ctypeslib.as_array(ws.batch.win_seq_begin, shape=(W + 1,)).copy()
+    S = int(wsb[W])
+    soff = np.ctypeslib.as_array(ws.batch.seq_off, shape=(S + 1,)).copy()
+    nb = int(soff[S])
+    if with_bases and nb:
+        bases = np.frombuffer(C.string_at(ws.batch.bases, nb), np.uint8).copy()
+    else:
+        bases = np.zeros(max(nb, 1), np.uint8)
+    rwb = np.ctypeslib.as_array(ws.reads.read_win_begin, shape=(R + 1,)).copy()
+    roff = np.ctypeslib.as_array(ws.reads.read_off, shape=(R + 1,)).copy()
+    nr = int(roff[R])
+    rbases = np.frombuffer(C.string_at(ws.reads.read_bases, nr), np.uint8).copy() if nr else np.zeros(1, np.uint8)
+    wpos = np.ctypeslib.as_array(ws.reads.win_pos, shape=(max(W, 1),))[:W].copy()
+    wend = np.ctypeslib.as_array(ws.win_end, shape=(max(W, 1),))[:W].copy()
+    return (Batch(wsb, soff, bases), Reads(rwb, roff, rbases, wpos, int(ws.reads.window_size), int(ws.reads.window_overlap)), wend)
 
 
 class Corrected:

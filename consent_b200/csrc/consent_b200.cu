@@ -26,6 +26,7 @@
 #include "k_poa2.cuh"
 #include "k_polish.cuh"
 #include "k_reanchor.cuh"
+#include "k_extract.cuh"
 
 struct DevBuf {
     void* p = nullptr;
@@ -157,6 +158,22 @@ struct cg_handle {
     DevBuf ra_rwb, ra_roff, ra_rbases, ra_wpos, ra_order, ra_head_off, ra_head, ra_len, ra_out_off, ra_out, ra_scratch, ra_ctl;
     float ra_ms = 0;
     u64 ra_cells = 0;
+    // window extraction (cg_upload_piles): device arrays + what cg_download_windows hands back
+    DevBuf ex_store, ex_store_off, ex_pile_read, ex_pile_qlen, ex_pile_ovb, ex_ov, ex_cov, ex_cov_off, ex_cap_off, ex_cap_beg, ex_cap_end,
+           ex_nwin, ex_win_pile, ex_win_beg, ex_win_end, ex_slot_base, ex_slot_len, ex_slot_src, ex_slot_loc, ex_win_nseq, ex_win_nbytes,
+           ex_win_base, ex_flags;
+    bool ex_valid = false;              // the resident batch was produced by cg_upload_piles
+    std::vector<u32> ex_rwb, ex_wpos, ex_wend, ex_pile_read_h;
+    std::vector<u64> ex_store_off_h;
+    u32 ex_ws = 0, ex_ovl = 0;
+    float ex_ms = 0;
+    u64 ex_bytes = 0;
+};
+
+struct HostWindowSet {
+    std::vector<u32> wsb, rwb, wpos, wend;
+    std::vector<u64> soff, roff;
+    std::vector<char> bases, rbases;
 };
 
 // Host copy of the corrected reads (pinned).
@@ -664,7 +681,10 @@ void cg_destroy(cg_handle* h) {
     DevBuf* bufs[] = {&h->d_bases, &h->d_seq_off, &h->d_wsb, &h->o_cons, &h->o_sk, &h->o_sc, &h->o_status, &h->o_len, &h->o_nsol,
                       &h->ra_cons, &h->ra_cons_off, &h->ra_solid_off, &h->ra_sk, &h->ra_tpl, &h->ra_tpl_off, &h->ra_rwb, &h->ra_roff,
                       &h->ra_rbases, &h->ra_wpos, &h->ra_order, &h->ra_head_off, &h->ra_head, &h->ra_len, &h->ra_out_off, &h->ra_out,
-                      &h->ra_scratch, &h->ra_ctl};
+                      &h->ra_scratch, &h->ra_ctl, &h->ex_store, &h->ex_store_off, &h->ex_pile_read, &h->ex_pile_qlen, &h->ex_pile_ovb, &h->ex_ov,
+                      &h->ex_cov, &h->ex_cov_off, &h->ex_cap_off, &h->ex_cap_beg, &h->ex_cap_end, &h->ex_nwin, &h->ex_win_pile, &h->ex_win_beg,
+                      &h->ex_win_end, &h->ex_slot_base, &h->ex_slot_len, &h->ex_slot_src, &h->ex_slot_loc, &h->ex_win_nseq, &h->ex_win_nbytes,
+                      &h->ex_win_base, &h->ex_flags};
     for (DevBuf* b : bufs) b->release();
     for (auto& t : h->tier) { t.mem.release(); t.desc.release(); }
     delete h;
@@ -703,6 +723,7 @@ int upload_impl(cg_handle* h, const cg_batch* in, bool wait) {
     cudaSetDevice(h->device);
     h->uploaded = h->ran = false;
     h->h2d_pending = false;
+    h->ex_valid = false;
     h->run_gen++;
     const u32 W = in->n_windows;
     const u64 n_seqs = in->win_seq_begin[W];
@@ -1111,6 +1132,209 @@ int cg_reanchor_stats(const cg_handle* h, float* kernel_ms, uint64_t* dp_cells) 
     if (!h) return CG_ERR_INVALID_ARG;
     if (kernel_ms) *kernel_ms = h->ra_ms;
     if (dp_cells) *dp_cells = h->ra_cells;
+    return CG_OK;
+}
+
+// ---- window extraction: phase A of processRead on the device, into the resident batch ----------------------
+int cg_upload_piles(cg_handle* h, const cg_piles* P) {
+    if (!h) return CG_ERR_INVALID_ARG;
+    if (!P || !P->store_off || !P->pile_ov_begin || (P->n_piles && (!P->pile_read || !P->pile_qlen)) || (P->n_store && !P->store_bases)) {
+        h->err = "null argument"; return CG_ERR_INVALID_ARG;
+    }
+    if (P->window_size == 0 || P->window_overlap >= P->window_size) { h->err = "window_overlap must be smaller than window_size"; return CG_ERR_INVALID_ARG; }
+    if (P->window_size > CG_LEN_MAX) { h->err = "window_size above 6000"; return CG_ERR_CAPACITY; }
+    cudaSetDevice(h->device);
+    h->uploaded = h->ran = false; h->h2d_pending = false; h->ex_valid = false;
+    h->run_gen++;
+    const u32 NP = P->n_piles, NS = P->n_store;
+    const u64 n_store_bases = P->store_off[NS];
+    const u64 n_ov = P->pile_ov_begin[NP];
+    if (n_ov && !P->overlaps) { h->err = "null argument"; return CG_ERR_INVALID_ARG; }
+    // per pile: coverage scratch and an upper bound of its windows (a window every ws - ovl bases, plus the last one)
+    std::vector<u64> cov_off((size_t)NP + 1, 0), cap_off((size_t)NP + 1, 0);
+    const u32 step = P->window_size - P->window_overlap;
+    for (u32 p = 0; p < NP; ++p) {
+        if (P->pile_read[p] >= NS) { h->err = "pile_read out of range"; return CG_ERR_INVALID_ARG; }
+        if (P->pile_ov_begin[p + 1] < P->pile_ov_begin[p]) { h->err = "pile_ov_begin must be non-decreasing"; return CG_ERR_INVALID_ARG; }
+        if (P->pile_ov_begin[p + 1] - P->pile_ov_begin[p] + 1 > CG_N_MAX) { h->err = "more than 4094 overlaps in one pile"; return CG_ERR_CAPACITY; }
+        cov_off[p + 1] = cov_off[p] + round_up((u64)P->pile_qlen[p] + 2, 4);
+        cap_off[p + 1] = cap_off[p] + (u64)P->pile_qlen[p] / step + 2;
+    }
+    cudaStream_t st = h->lane[0].stream;
+    CK(h->ex_store.ensure(n_store_bases + 16)); CK(h->ex_store_off.ensure(((size_t)NS + 1) * 8));
+    CK(h->ex_pile_read.ensure(((size_t)NP + 1) * 4)); CK(h->ex_pile_qlen.ensure(((size_t)NP + 1) * 4)); CK(h->ex_pile_ovb.ensure(((size_t)NP + 1) * 4));
+    CK(h->ex_ov.ensure((n_ov + 1) * sizeof(CgOverlapDev)));
+    CK(h->ex_cov.ensure((cov_off[NP] + 4) * 4)); CK(h->ex_cov_off.ensure(((size_t)NP + 1) * 8)); CK(h->ex_cap_off.ensure(((size_t)NP + 1) * 8));
+    CK(h->ex_cap_beg.ensure((cap_off[NP] + 1) * 4)); CK(h->ex_cap_end.ensure((cap_off[NP] + 1) * 4)); CK(h->ex_nwin.ensure(((size_t)NP + 1) * 4));
+    CK(h->ex_flags.ensure(16));
+    if (n_store_bases) CK(cudaMemcpyAsync(h->ex_store.p, P->store_bases, n_store_bases, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->ex_store_off.p, P->store_off, ((size_t)NS + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (NP) {
+        CK(cudaMemcpyAsync(h->ex_pile_read.p, P->pile_read, (size_t)NP * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(h->ex_pile_qlen.p, P->pile_qlen, (size_t)NP * 4, cudaMemcpyHostToDevice, st));
+    }
+    CK(cudaMemcpyAsync(h->ex_pile_ovb.p, P->pile_ov_begin, ((size_t)NP + 1) * 4, cudaMemcpyHostToDevice, st));
+    if (n_ov) CK(cudaMemcpyAsync(h->ex_ov.p, P->overlaps, n_ov * sizeof(CgOverlapDev), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->ex_cov_off.p, cov_off.data(), ((size_t)NP + 1) * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->ex_cap_off.p, cap_off.data(), ((size_t)NP + 1) * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(h->ex_flags.p, 0, 16, st));
+    CgExtractArgs A{};
+    A.store_off = h->ex_store_off.as<u64>(); A.store = h->ex_store.as<char>(); A.n_store = NS;
+    A.n_piles = NP; A.pile_read = h->ex_pile_read.as<u32>(); A.pile_qlen = h->ex_pile_qlen.as<u32>(); A.pile_ov_begin = h->ex_pile_ovb.as<u32>();
+    A.ov = h->ex_ov.as<CgOverlapDev>();
+    A.min_support = P->min_support; A.ws = P->window_size; A.ovl = P->window_overlap; A.k = h->p.mer_size;
+    A.cov = h->ex_cov.as<u32>(); A.cov_off = h->ex_cov_off.as<u64>(); A.win_cap_off = h->ex_cap_off.as<u64>();
+    A.cap_beg = h->ex_cap_beg.as<u32>(); A.cap_end = h->ex_cap_end.as<u32>(); A.n_win = h->ex_nwin.as<u32>();
+    A.flags = h->ex_flags.as<u32>();
+    cudaEvent_t e0, e1, e2, e3;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreate(&e2)); CK(cudaEventCreate(&e3));
+    CK(cudaEventRecord(e0, st));
+    if (n_store_bases) CG_LAUNCH(k_ex_normalise, (u32)std::min<u64>((n_store_bases + 255) / 256, (u64)h->sms * 16), 256, 0, st, h->ex_store.as<char>(), n_store_bases);
+    if (NP) CG_LAUNCH(k_ex_positions, (NP + 3) / 4, 128, 0, st, A);
+    CK(cudaEventRecord(e1, st));
+    // ---- window counts -> dense windows (host prefix; a few bytes per window)
+    std::vector<u32> nwin((size_t)NP + 1, 0), cap_beg(cap_off[NP] + 1), cap_end(cap_off[NP] + 1);
+    u32 flags = 0;
+    if (NP) CK(cudaMemcpyAsync(nwin.data(), h->ex_nwin.p, (size_t)NP * 4, cudaMemcpyDeviceToHost, st));
+    if (cap_off[NP]) {
+        CK(cudaMemcpyAsync(cap_beg.data(), h->ex_cap_beg.p, cap_off[NP] * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(cap_end.data(), h->ex_cap_end.p, cap_off[NP] * 4, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaMemcpyAsync(&flags, h->ex_flags.p, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    auto flag_error = [&](u32 f) {
+        if (f & CG_EX_FLAG_CAPACITY) { h->err = "window extraction: a capacity limit of this build was exceeded (sequence over 6000 bases)"; return (int)CG_ERR_CAPACITY; }
+        h->err = (f & CG_EX_FLAG_EMPTY_PILE) ? "window extraction: a window lies beyond its stored read (the reference dereferences an empty pile here)"
+               : (f & CG_EX_FLAG_SUBSTR) ? "window extraction: an overlap points outside its target read (std::out_of_range in the reference)"
+               : "window extraction: an overlap ends beyond qLength, names a read outside the store, or qLength is 0";
+        return (int)CG_ERR_INVALID_ARG;
+    };
+    if (flags) return flag_error(flags);
+    h->ex_rwb.assign((size_t)NP + 1, 0);
+    u64 Wtot = 0;
+    for (u32 p = 0; p < NP; ++p) { Wtot += nwin[p]; h->ex_rwb[p + 1] = (u32)Wtot; }
+    if (Wtot >= (1ull << 31)) { h->err = "too many windows"; return CG_ERR_CAPACITY; }
+    const u32 W = (u32)Wtot;
+    h->ex_wpos.resize(W); h->ex_wend.resize(W);
+    std::vector<u32> win_pile(W);
+    std::vector<u64> slot_base((size_t)W + 1, 0);
+    for (u32 p = 0, w = 0; p < NP; ++p)
+        for (u32 i = 0; i < nwin[p]; ++i, ++w) {
+            h->ex_wpos[w] = cap_beg[cap_off[p] + i]; h->ex_wend[w] = cap_end[cap_off[p] + i]; win_pile[w] = p;
+            slot_base[w + 1] = slot_base[w] + (P->pile_ov_begin[p + 1] - P->pile_ov_begin[p]) + 1;
+        }
+    const u64 S = slot_base[W];
+    CK(h->ex_win_pile.ensure(((size_t)W + 1) * 4)); CK(h->ex_win_beg.ensure(((size_t)W + 1) * 4)); CK(h->ex_win_end.ensure(((size_t)W + 1) * 4));
+    CK(h->ex_slot_base.ensure(((size_t)W + 1) * 8)); CK(h->ex_slot_len.ensure((S + 1) * 4)); CK(h->ex_slot_src.ensure((S + 1) * 8));
+    CK(h->ex_slot_loc.ensure((S + 1) * 4)); CK(h->ex_win_nseq.ensure(((size_t)W + 1) * 4)); CK(h->ex_win_nbytes.ensure(((size_t)W + 1) * 4));
+    CK(h->ex_win_base.ensure(((size_t)W + 1) * 8));
+    if (W) {
+        CK(cudaMemcpyAsync(h->ex_win_pile.p, win_pile.data(), (size_t)W * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(h->ex_win_beg.p, h->ex_wpos.data(), (size_t)W * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(h->ex_win_end.p, h->ex_wend.data(), (size_t)W * 4, cudaMemcpyHostToDevice, st));
+    }
+    CK(cudaMemcpyAsync(h->ex_slot_base.p, slot_base.data(), ((size_t)W + 1) * 8, cudaMemcpyHostToDevice, st));
+    A.n_windows = W; A.win_pile = h->ex_win_pile.as<u32>(); A.win_beg = h->ex_win_beg.as<u32>(); A.win_end = h->ex_win_end.as<u32>();
+    A.slot_base = h->ex_slot_base.as<u64>(); A.slot_len = h->ex_slot_len.as<u32>(); A.slot_src = h->ex_slot_src.as<u64>();
+    A.slot_loc = h->ex_slot_loc.as<u32>(); A.win_nseq = h->ex_win_nseq.as<u32>(); A.win_nbytes = h->ex_win_nbytes.as<u32>();
+    CK(cudaEventRecord(e2, st));
+    if (W) CG_LAUNCH(k_ex_sizes, (W + 3) / 4, 128, 0, st, A);
+    // ---- per-window totals -> win_seq_begin / window base offsets (host prefix: the planner needs them on the host anyway)
+    std::vector<u32> nseq((size_t)W + 1, 0), nbytes((size_t)W + 1, 0);
+    if (W) {
+        CK(cudaMemcpyAsync(nseq.data(), h->ex_win_nseq.p, (size_t)W * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(nbytes.data(), h->ex_win_nbytes.p, (size_t)W * 4, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaMemcpyAsync(&flags, h->ex_flags.p, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (flags) return flag_error(flags);
+    h->h_wsb.assign((size_t)W + 1, 0); h->h_wbase.assign((size_t)W + 1, 0); h->h_tlen.assign(W, 0);
+    const u32 k = h->p.mer_size;
+    for (u32 w = 0; w < W; ++w) {
+        const u64 ns = (u64)h->h_wsb[w] + nseq[w];
+        if (ns >= (1ull << 32)) { h->err = "too many sequences"; return CG_ERR_CAPACITY; }
+        h->h_wsb[w + 1] = (u32)ns;
+        h->h_wbase[w + 1] = h->h_wbase[w] + nbytes[w];
+        h->h_tlen[w] = h->ex_wend[w] - h->ex_wpos[w] + 1;
+        if (h->h_tlen[w] >= k && h->h_tlen[w] - k + 1 > CG_TK_MAX) { h->err = "template longer than 2047 k-mers"; return CG_ERR_CAPACITY; }
+    }
+    const u64 n_seqs = h->h_wsb[W], n_bases = h->h_wbase[W];
+    h->W = W; h->n_seqs = n_seqs; h->n_bases = n_bases;
+    CK(h->d_bases.ensure(n_bases + 64)); CK(h->d_seq_off.ensure((n_seqs + 1) * sizeof(u64))); CK(h->d_wsb.ensure(((size_t)W + 1) * sizeof(u32)));
+    CK(cudaMemcpyAsync(h->d_wsb.p, h->h_wsb.data(), ((size_t)W + 1) * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->ex_win_base.p, h->h_wbase.data(), ((size_t)W + 1) * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->d_seq_off.as<u64>() + n_seqs, &h->h_wbase[W], 8, cudaMemcpyHostToDevice, st));
+    A.win_seq_begin = h->d_wsb.as<u32>(); A.win_base = h->ex_win_base.as<u64>(); A.seq_off = h->d_seq_off.as<u64>(); A.bases = h->d_bases.as<char>();
+    if (W) CG_LAUNCH(k_ex_copy, std::min<u32>(W, (u32)h->sms * 16), 256, 0, st, A);
+    CK(cudaEventRecord(e3, st));
+    CK(cudaGetLastError());
+    plan_chunks(h, false);
+    while (h->ev_h2d.size() < h->chunks.size()) {
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->ev_h2d.push_back(e);
+    }
+    CK(cudaStreamSynchronize(st));
+    float m1 = 0, m2 = 0;
+    CK(cudaEventElapsedTime(&m1, e0, e1)); CK(cudaEventElapsedTime(&m2, e2, e3));
+    for (cudaEvent_t e : {e0, e1, e2, e3}) cudaEventDestroy(e);
+    h->ex_ms = m1 + m2; h->ex_bytes = n_bases;
+    h->ex_pile_read_h.assign(P->pile_read, P->pile_read + NP);
+    h->ex_store_off_h.assign(P->store_off, P->store_off + NS + 1);
+    h->ex_ws = P->window_size; h->ex_ovl = P->window_overlap;
+    h->ex_valid = true;
+    h->uploaded = true;
+    return CG_OK;
+}
+
+int cg_download_windows(cg_handle* h, int with_bases, cg_window_set* out) {
+    if (!h || !out) return CG_ERR_INVALID_ARG;
+    if (!h->uploaded || !h->ex_valid) { h->err = "cg_download_windows needs a batch produced by cg_upload_piles"; return CG_ERR_STATE; }
+    cudaSetDevice(h->device);
+    cudaStream_t st = h->lane[0].stream;
+    HostWindowSet* ws = new HostWindowSet();
+    const u32 W = h->W, NP = (u32)h->ex_pile_read_h.size();
+    ws->wsb = h->h_wsb; ws->rwb = h->ex_rwb; ws->wpos = h->ex_wpos; ws->wend = h->ex_wend;
+    if (ws->wpos.empty()) { ws->wpos.push_back(0); ws->wend.push_back(0); }
+    ws->soff.resize(h->n_seqs + 1);
+    cudaError_t e = cudaMemcpyAsync(ws->soff.data(), h->d_seq_off.p, (h->n_seqs + 1) * 8, cudaMemcpyDeviceToHost, st);
+    if (with_bases) {
+        ws->bases.resize(h->n_bases + 1);
+        if (e == cudaSuccess && h->n_bases) e = cudaMemcpyAsync(ws->bases.data(), h->d_bases.p, h->n_bases, cudaMemcpyDeviceToHost, st);
+    }
+    // the reads of the piles, as stored (normalised) on the device
+    std::vector<char> store(h->ex_store_off_h.back() + 1);
+    if (e == cudaSuccess && h->ex_store_off_h.back()) e = cudaMemcpyAsync(store.data(), h->ex_store.p, h->ex_store_off_h.back(), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { delete ws; h->err = std::string("cg_download_windows: ") + cudaGetErrorString(e); return CG_ERR_CUDA; }
+    ws->roff.assign((size_t)NP + 1, 0);
+    for (u32 p = 0; p < NP; ++p) {
+        const u32 r = h->ex_pile_read_h[p];
+        ws->roff[p + 1] = ws->roff[p] + (h->ex_store_off_h[r + 1] - h->ex_store_off_h[r]);
+    }
+    ws->rbases.resize(ws->roff[NP] + 1);
+    for (u32 p = 0; p < NP; ++p) {
+        const u32 r = h->ex_pile_read_h[p];
+        memcpy(ws->rbases.data() + ws->roff[p], store.data() + h->ex_store_off_h[r], h->ex_store_off_h[r + 1] - h->ex_store_off_h[r]);
+    }
+    out->batch.n_windows = W; out->batch.win_seq_begin = ws->wsb.data(); out->batch.seq_off = ws->soff.data();
+    out->batch.bases = with_bases ? ws->bases.data() : nullptr;
+    out->reads.n_reads = NP; out->reads.read_win_begin = ws->rwb.data(); out->reads.read_off = ws->roff.data();
+    out->reads.read_bases = ws->rbases.data(); out->reads.win_pos = ws->wpos.data();
+    out->reads.window_size = h->ex_ws; out->reads.window_overlap = h->ex_ovl;
+    out->win_end = ws->wend.data();
+    out->owner_ = ws;
+    return CG_OK;
+}
+
+void cg_free_window_set(cg_window_set* s) {
+    if (s && s->owner_) { delete static_cast<HostWindowSet*>(s->owner_); s->owner_ = nullptr; }
+}
+
+int cg_extract_stats(const cg_handle* h, float* kernel_ms, uint64_t* pile_bytes) {
+    if (!h) return CG_ERR_INVALID_ARG;
+    if (kernel_ms) *kernel_ms = h->ex_ms;
+    if (pile_bytes) *pile_bytes = h->ex_bytes;
     return CG_OK;
 }
 

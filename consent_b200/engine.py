@@ -14,14 +14,16 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-from ._ffi import (Batch, CG_N_STAGES, Corrected, PKG_DIR, Params, Reads, Results, STAGE_NAMES, STATUS_NAMES, cg_batch,
-                   cg_corrected, cg_counters, cg_params, cg_reads, cg_results, load_library, results_to_c)
+from ._ffi import (Batch, CG_N_STAGES, Corrected, PKG_DIR, Params, Piles, Reads, Results, STAGE_NAMES, STATUS_NAMES, cg_batch,
+                   cg_corrected, cg_counters, cg_params, cg_piles, cg_reads, cg_results, cg_window_set, load_library,
+                   results_to_c, window_set_to_py)
 
 LIB_PATH = os.path.join(PKG_DIR, "libconsent_b200.so")
 
 EXPORTS = ("cg_abi_version", "cg_device_count", "cg_create", "cg_destroy", "cg_last_error", "cg_set_option",
            "cg_correct_windows", "cg_free_results", "cg_upload", "cg_run", "cg_download", "cg_stage_ms",
-           "cg_get_counters", "cg_run_ms", "cg_chunk_count", "cg_reanchor_reads", "cg_free_corrected", "cg_reanchor_stats")
+           "cg_get_counters", "cg_run_ms", "cg_chunk_count", "cg_reanchor_reads", "cg_free_corrected", "cg_reanchor_stats",
+           "cg_upload_piles", "cg_download_windows", "cg_free_window_set", "cg_extract_stats")
 
 
 class ConsentError(RuntimeError):
@@ -65,6 +67,13 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.cg_free_corrected.argtypes = [C.POINTER(cg_corrected)]
     lib.cg_reanchor_stats.restype = C.c_int
     lib.cg_reanchor_stats.argtypes = [H, C.POINTER(C.c_float), C.POINTER(C.c_uint64)]
+    lib.cg_upload_piles.restype = C.c_int
+    lib.cg_upload_piles.argtypes = [H, C.POINTER(cg_piles)]
+    lib.cg_download_windows.restype = C.c_int
+    lib.cg_download_windows.argtypes = [H, C.c_int, C.POINTER(cg_window_set)]
+    lib.cg_free_window_set.argtypes = [C.POINTER(cg_window_set)]
+    lib.cg_extract_stats.restype = C.c_int
+    lib.cg_extract_stats.argtypes = [H, C.POINTER(C.c_float), C.POINTER(C.c_uint64)]
     return lib
 
 
@@ -132,6 +141,27 @@ class Corrector:
         ms, cells = C.c_float(0), C.c_uint64(0)
         self._check(self.lib.cg_reanchor_stats(self._h, C.byref(ms), C.byref(cells)))
         return {"kernel_ms": float(ms.value), "dp_cells": int(cells.value)}
+
+    # -- window extraction: phase A of processRead (reference src/alignmentWindows.cpp:27-149) on the device ----------
+    def upload_piles(self, piles: Piles):
+        """Read store + read piles (overlaps per query read) in, the window batch cut on the device and left resident:
+        run() / download() follow as after upload()."""
+        cp = piles.c()
+        self._check(self.lib.cg_upload_piles(self._h, C.byref(cp)))
+
+    def download_windows(self, with_bases: bool = True):
+        """The windows cg_upload_piles extracted -> (Batch, Reads, win_end): the piles, and per pile its read, its windows
+        and their positions (pilesPos)."""
+        ws = cg_window_set()
+        self._check(self.lib.cg_download_windows(self._h, int(with_bases), C.byref(ws)))
+        out = window_set_to_py(ws, with_bases)
+        self.lib.cg_free_window_set(C.byref(ws))
+        return out
+
+    def extract_stats(self) -> dict:
+        ms, nb = C.c_float(0), C.c_uint64(0)
+        self._check(self.lib.cg_extract_stats(self._h, C.byref(ms), C.byref(nb)))
+        return {"kernel_ms": float(ms.value), "pile_bytes": int(nb.value)}
 
     # -- staged (bench: keep the batch resident in HBM, time the kernels alone) ---------------
     def upload(self, batch: Batch):

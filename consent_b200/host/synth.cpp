@@ -138,3 +138,95 @@ extern "C" uint64_t cg_synth_reads(const cg_synth_read_spec* s, uint32_t* win_se
     }
     return W;
 }
+
+// ---- read piles over a random genome (window-extraction path) ------------------------------------------------------
+namespace {
+struct PileSet {
+    std::vector<uint64_t> store_off;
+    std::string store;
+    std::vector<uint32_t> pile_read, pile_qlen, pile_ov_begin, ov7;
+};
+}  // namespace
+
+extern "C" void* cg_synth_piles_build(const cg_synth_pile_spec* s, uint64_t* store_bases, uint64_t* n_overlaps) {
+    PileSet* ps = new PileSet();
+    std::mt19937_64 rng(s->seed * 9000011ULL);
+    std::vector<uint8_t> genome(s->genome_len);
+    for (auto& g : genome) g = (uint8_t)(rng() & 3);
+    const uint32_t R = s->n_reads, L = s->read_len;
+    std::vector<uint32_t> start(R), strand(R);
+    std::vector<std::vector<uint32_t>> gpos(R);               // genome position of every read base
+    ps->store_off.push_back(0);
+    cg_synth_read_spec ch{};
+    ch.err = s->err; ch.p_sub = s->p_sub; ch.p_ins = s->p_ins;
+    for (uint32_t r = 0; r < R; ++r) {
+        start[r] = (uint32_t)(rng() % (s->genome_len - L + 1));
+        strand[r] = (uint32_t)(rng() & 1);
+        std::vector<uint8_t> seg(L);
+        for (uint32_t i = 0; i < L; ++i) seg[i] = strand[r] ? (uint8_t)(3 - genome[start[r] + L - 1 - i]) : genome[start[r] + i];
+        std::string read; std::vector<uint32_t> map;
+        channel(&ch, rng, seg, 0, L - 1, read, &map);
+        gpos[r].resize(map.size());
+        for (size_t i = 0; i < map.size(); ++i) gpos[r][i] = strand[r] ? start[r] + L - 1 - map[i] : start[r] + map[i];
+        ps->store += read;
+        ps->store_off.push_back(ps->store.size());
+    }
+    // read positions whose genome coordinate lies in [g0, g1]: a contiguous range because gpos is monotone
+    auto range = [&](uint32_t r, uint32_t g0, uint32_t g1, uint32_t& a, uint32_t& b) {
+        const std::vector<uint32_t>& gp = gpos[r];
+        if (!strand[r]) {
+            a = (uint32_t)(std::lower_bound(gp.begin(), gp.end(), g0) - gp.begin());
+            b = (uint32_t)(std::upper_bound(gp.begin(), gp.end(), g1) - gp.begin());
+        } else {                                               // descending
+            a = (uint32_t)(std::lower_bound(gp.begin(), gp.end(), g1, [](uint32_t x, uint32_t v) { return x > v; }) - gp.begin());
+            b = (uint32_t)(std::upper_bound(gp.begin(), gp.end(), g0, [](uint32_t v, uint32_t x) { return v > x; }) - gp.begin());
+        }
+        return b > a;                                          // [a, b)
+    };
+    std::vector<uint32_t> by_start(R);
+    for (uint32_t r = 0; r < R; ++r) by_start[r] = r;
+    std::sort(by_start.begin(), by_start.end(), [&](uint32_t x, uint32_t y) { return start[x] < start[y] || (start[x] == start[y] && x < y); });
+    ps->pile_ov_begin.push_back(0);
+    const uint32_t P = std::min(s->n_piles, R);
+    for (uint32_t q = 0; q < P; ++q) {
+        struct Cand { uint32_t len, t, g0, g1; };
+        std::vector<Cand> cand;
+        const uint32_t q0 = start[q], q1 = start[q] + L - 1;
+        auto lo = std::lower_bound(by_start.begin(), by_start.end(), q0 > L ? q0 - L : 0u, [&](uint32_t r, uint32_t v) { return start[r] < v; });
+        for (auto it = lo; it != by_start.end() && start[*it] <= q1; ++it) {
+            const uint32_t t = *it;
+            if (t == q) continue;
+            const uint32_t g0 = std::max(q0, start[t]), g1 = std::min(q1, start[t] + L - 1);
+            if (g1 < g0 || g1 - g0 + 1 < s->min_overlap) continue;
+            cand.push_back({g1 - g0 + 1, t, g0, g1});
+        }
+        std::sort(cand.begin(), cand.end(), [](const Cand& a, const Cand& b) { return a.len > b.len || (a.len == b.len && a.t < b.t); });
+        if (cand.size() > s->max_support) cand.resize(s->max_support);
+        for (const Cand& c : cand) {
+            uint32_t qa, qb, ta, tb;
+            if (!range(q, c.g0, c.g1, qa, qb) || !range(c.t, c.g0, c.g1, ta, tb)) continue;
+            const uint32_t rec[7] = {c.t, strand[q] ^ strand[c.t], qa, qb - 1, ta, tb - 1, (uint32_t)gpos[c.t].size()};
+            ps->ov7.insert(ps->ov7.end(), rec, rec + 7);
+        }
+        ps->pile_read.push_back(q);
+        ps->pile_qlen.push_back((uint32_t)gpos[q].size());
+        ps->pile_ov_begin.push_back((uint32_t)(ps->ov7.size() / 7));
+    }
+    *store_bases = ps->store.size();
+    *n_overlaps = ps->ov7.size() / 7;
+    return ps;
+}
+
+extern "C" void cg_synth_piles_fetch(void* handle, uint64_t* store_off, char* store, uint32_t* pile_read, uint32_t* pile_qlen,
+                                     uint32_t* pile_ov_begin, uint32_t* overlaps7) {
+    PileSet* ps = static_cast<PileSet*>(handle);
+    memcpy(store_off, ps->store_off.data(), ps->store_off.size() * 8);
+    memcpy(store, ps->store.data(), ps->store.size());
+    if (!ps->pile_read.empty()) {
+        memcpy(pile_read, ps->pile_read.data(), ps->pile_read.size() * 4);
+        memcpy(pile_qlen, ps->pile_qlen.data(), ps->pile_qlen.size() * 4);
+    }
+    memcpy(pile_ov_begin, ps->pile_ov_begin.data(), ps->pile_ov_begin.size() * 4);
+    if (!ps->ov7.empty()) memcpy(overlaps7, ps->ov7.data(), ps->ov7.size() * 4);
+    delete ps;
+}

@@ -69,6 +69,23 @@ void cg_synth_reads_bounds(const cg_synth_read_spec* s, uint64_t* max_windows, u
 uint64_t cg_synth_reads(const cg_synth_read_spec* s, uint32_t* win_seq_begin, uint64_t* seq_off, char* bases,
                         uint32_t* read_win_begin, uint64_t* read_off, char* read_bases, uint32_t* win_pos);
 
+/* Synthetic read piles over a random genome, for the window-extraction path (BASELINE config 4 shape
+ * without the overlapper): genome[i] = rng() & 3 from std::mt19937_64(seed * 9000011); read r = `read_len` genome bases
+ * from a uniform start, on a random strand, through the error channel; the overlaps of a pile are derived from the true
+ * genome coordinates (what minimap2 would report up to its end-point jitter), sorted by overlap length (descending, ties by
+ * read index) and cut at max_support, as getNextReadPile leaves them (src/alignmentPiles.cpp:22-58).
+ * Piles are built for reads [0, n_piles). */
+typedef struct cg_synth_pile_spec {
+    uint64_t seed;
+    uint32_t genome_len, n_reads, read_len, n_piles, max_support, min_overlap;
+    double   err, p_sub, p_ins;
+} cg_synth_pile_spec;
+/* Sizes for the caller's buffers: total store bases and total overlaps (exact). Returns an opaque handle. */
+void* cg_synth_piles_build(const cg_synth_pile_spec* s, uint64_t* store_bases, uint64_t* n_overlaps);
+/* Copies the built set out (overlaps as 7 uint32 per record in cg_overlap order) and frees the handle. */
+void  cg_synth_piles_fetch(void* handle, uint64_t* store_off, char* store, uint32_t* pile_read, uint32_t* pile_qlen,
+                           uint32_t* pile_ov_begin, uint32_t* overlaps7);
+
 #ifdef __cplusplus
 }
 #endif

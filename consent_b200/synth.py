@@ -7,7 +7,7 @@ import os
 
 import numpy as np
 
-from ._ffi import Batch, PKG_DIR, Reads, cg_synth_read_spec, cg_synth_spec, load_library
+from ._ffi import Batch, PKG_DIR, Piles, Reads, cg_synth_pile_spec, cg_synth_read_spec, cg_synth_spec, load_library
 
 PROFILES = {
     # total error, share substitutions, share insertions (deletions = rest)
@@ -33,6 +33,10 @@ def _host():
         _lib.cg_synth_reads.argtypes = [C.POINTER(cg_synth_read_spec), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64),
                                         C.c_char_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.c_char_p,
                                         C.POINTER(C.c_uint32)]
+        _lib.cg_synth_piles_build.restype = C.c_void_p
+        _lib.cg_synth_piles_build.argtypes = [C.POINTER(cg_synth_pile_spec), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        _lib.cg_synth_piles_fetch.restype = None
+        _lib.cg_synth_piles_fetch.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_char_p] + [C.POINTER(C.c_uint32)] * 4
     return _lib
 
 
@@ -80,3 +84,26 @@ def synth_reads(n_reads: int, n_seqs: int, *, truth_len: int = 3000, seed: int =
     batch = Batch(wsb[:W + 1].copy(), off[:S + 1].copy(), bases[:max(int(off[S]), 1)].copy())
     reads = Reads(rwb, roff, rbases[:max(int(roff[-1]), 1)].copy(), wpos[:W].copy(), window_size, window_overlap)
     return batch, reads
+
+
+def synth_piles(n_reads: int, *, genome_len: int = 200_000, read_len: int = 4000, n_piles: int | None = None, seed: int = 42,
+                profile: str = "PB", max_support: int = 150, min_overlap: int = 500, min_support: int = 3,
+                window_size: int = 500, window_overlap: int = 50) -> Piles:
+    """Seeded reads over a random genome with their true overlaps as read piles (consent_b200/host/synth.h): the input of
+    the window-extraction path.  Coverage = n_reads * read_len / genome_len."""
+    err, p_sub, p_ins = PROFILES[profile]
+    n_piles = n_reads if n_piles is None else n_piles
+    spec = cg_synth_pile_spec(seed, genome_len, n_reads, read_len, n_piles, max_support, min_overlap, err, p_sub, p_ins)
+    lib = _host()
+    nb, no = C.c_uint64(), C.c_uint64()
+    h = lib.cg_synth_piles_build(C.byref(spec), C.byref(nb), C.byref(no))
+    store_off = np.zeros(n_reads + 1, np.uint64)
+    store = np.empty(max(nb.value, 1), np.uint8)
+    P = min(n_piles, n_reads)
+    pile_read, pile_qlen = np.zeros(max(P, 1), np.uint32), np.zeros(max(P, 1), np.uint32)
+    pile_ov_begin = np.zeros(P + 1, np.uint32)
+    ov = np.zeros((max(no.value, 1), 7), np.uint32)
+    u32, u64 = C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)
+    lib.cg_synth_piles_fetch(h, store_off.ctypes.data_as(u64), C.cast(store.ctypes.data, C.c_char_p), pile_read.ctypes.data_as(u32),
+                             pile_qlen.ctypes.data_as(u32), pile_ov_begin.ctypes.data_as(u32), ov.ctypes.data_as(u32))
+    return Piles(store_off, store, pile_read[:P], pile_qlen[:P], pile_ov_begin, ov[:no.value], min_support, window_size, window_overlap)

@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define CG_ABI_VERSION 2
+#define CG_ABI_VERSION 3
 
 typedef enum cg_status {
     CG_OK                 =  0,
@@ -176,6 +176,59 @@ void cg_free_corrected(cg_corrected* c);
 /* CUDA-event time (ms) of the kernel of the last cg_reanchor_reads and the DP cells
  * (query x reference, forward + reverse passes of every alignment) it swept. */
 int  cg_reanchor_stats(const cg_handle* h, float* kernel_ms, uint64_t* dp_cells);
+
+/* Window extraction ----------------------------------------
+ * Phase A of processRead (src/CONSENT-correction.cpp:21-35) on the device: for every read pile, the window positions
+ *
+ *   getAlignmentWindowsPositions(tplLen, alignments, minSupport, maxSupport, windowSize, windowOverlap)
+ *                                                        (src/alignmentWindows.cpp:27-85, getCoverages :5-25)
+ * and for every window its pile
+ *
+ *   getAlignmentWindowsSequences(alignments, ..., sequences, qBeg, end, merSize, ...)   (src/alignmentWindows.cpp:87-149)
+ *
+ * cut (and reverse-complemented, src/reverseComplement.cpp:6-24) from a read store that is shipped once, instead of
+ * W x N strings assembled on the host and uploaded.  The host keeps what is serial and tiny: PAF parsing, grouping by
+ * query and the top-maxSupport selection (src/alignmentPiles.cpp:22-58) — a pile's overlaps are given in the order
+ * getNextReadPile leaves them.  The result is the resident window batch: cg_run / cg_download follow as after cg_upload,
+ * cg_download_windows returns the extracted piles and the cg_reads view cg_reanchor_reads needs. */
+typedef struct cg_overlap {          /* one PAF record as src/Overlap.h:26-60 holds it */
+    uint32_t t_read;                 /* tName: index of the target read in the store                  */
+    uint32_t strand;                 /* 0 '+', 1 '-'                                                  */
+    uint32_t q_start, q_end;         /* qStart, qEnd = PAF end - 1 (inclusive, Overlap.h:37)          */
+    uint32_t t_start, t_end;         /* tStart, tEnd = PAF end - 1 (inclusive, Overlap.h:48)          */
+    uint32_t t_length;               /* tLength (PAF column 7)                                        */
+} cg_overlap;
+
+typedef struct cg_piles {
+    uint32_t          n_store;       /* reads in the store                                            */
+    const uint64_t*   store_off;     /* [n_store + 1] byte offsets into store_bases                   */
+    const char*       store_bases;   /* ASCII; stored as the reference stores reads: upper-cased, anything
+                                        but A, C, G becomes T (src/utils.cpp:21-32,189)              */
+    uint32_t          n_piles;
+    const uint32_t*   pile_read;     /* [n_piles] the query read (qName) of pile p                    */
+    const uint32_t*   pile_qlen;     /* [n_piles] qLength (PAF column 2)                              */
+    const uint32_t*   pile_ov_begin; /* [n_piles + 1] overlaps of pile p = [pile_ov_begin[p], [p+1])  */
+    const cg_overlap* overlaps;
+    uint32_t          min_support;   /* -s */
+    uint32_t          window_size;   /* -l */
+    uint32_t          window_overlap;/* -m */
+} cg_piles;
+
+/* The extracted windows on the host, owned by the library until cg_free_window_set(). */
+typedef struct cg_window_set {
+    cg_batch  batch;                 /* the piles (bases == NULL if they were not asked for)          */
+    cg_reads  reads;                 /* pile p = read p: its windows, pilesPos[i].first, its sequence */
+    uint32_t* win_end;               /* [n_windows] pilesPos[i].second                                */
+    void*     owner_;
+} cg_window_set;
+
+/* Extracts every window of every pile into the handle's resident batch (what cg_upload would have received from a host
+ * running phase A).  Blocking.  Piles without a window yield reads without windows. */
+int  cg_upload_piles(cg_handle* h, const cg_piles* piles);
+int  cg_download_windows(cg_handle* h, int with_bases, cg_window_set* out);
+void cg_free_window_set(cg_window_set* s);
+/* CUDA-event time (ms) of the extraction kernels of the last cg_upload_piles and the pile bytes they wrote. */
+int  cg_extract_stats(const cg_handle* h, float* kernel_ms, uint64_t* pile_bytes);
 
 /* Instrumentation -------------------------------------------------------- */
 #define CG_STAGE_PACK     0   /* ASCII -> 2-bit                                         */

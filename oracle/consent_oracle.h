@@ -27,6 +27,10 @@ void  oracle_free_corrected(cg_corrected* c);
 /* DP cells (forward + backward scans of every alignment) swept by the last oracle_reanchor_reads. */
 uint64_t oracle_reanchor_cells(void);
 
+/* Window-extraction oracle (oracle/extract_oracle.c): phase A of processRead; same contract as ref_extract_windows. */
+int   oracle_extract_windows(const cg_piles* p, unsigned merSize, cg_window_set* out);
+void  oracle_free_window_set(cg_window_set* s);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,6 +11,8 @@
 //   GPU      cg_correct_windows  (= every computeConsensusReadCorrection of the batch, :36)
 //            cg_reanchor_reads   (= every alignConsensus of the batch, :47)
 //   phase B  per read, in PAF order: trimRead / dropRead and the FASTA record (:50-59, :100-103)
+// With -x phase A's window cutting moves to the device as well (cg_upload_piles): the host only reads the PAF
+// piles (getNextReadPile: parsing, sort, top-maxSupport) and ships the read store once.
 // Same command line as bin/CONSENT-correction (src/main.cpp:27-80).  tests/test_dropin_example.py runs it on a B200 and
 // compares its FASTA byte for byte with the one the unmodified reference binary printed for the same PAF.
 #include <getopt.h>
@@ -35,7 +37,8 @@ int main(int argc, char** argv) {
     unsigned minSupport = 3, maxSupport = 1000, windowSize = 500, merSize = 9, commonKMers = 8, minAnchors = 10,
              solidThresh = 4, windowOverlap = 50;                                       // src/main.cpp:15-24
     int opt, device = 0;
-    while ((opt = getopt(argc, argv, "a:A:d:k:s:S:M:l:f:e:p:c:m:j:w:r:R:n:i:g:")) != -1) {
+    bool deviceExtraction = false;
+    while ((opt = getopt(argc, argv, "a:A:d:k:s:S:M:l:f:e:p:c:m:j:w:r:R:n:i:g:x")) != -1) {
         switch (opt) {
             case 'a': alignmentFile = optarg; break;
             case 's': minSupport = atoi(optarg); break;
@@ -48,6 +51,7 @@ int main(int argc, char** argv) {
             case 'm': windowOverlap = atoi(optarg); break;
             case 'r': readsFile = optarg; break;
             case 'g': device = atoi(optarg); break;
+            case 'x': deviceExtraction = true; break;
             default: break;                                                             // -j -M -p ...: no meaning here
         }
     }
@@ -56,6 +60,58 @@ int main(int argc, char** argv) {
     robin_hood::unordered_map<std::string, std::vector<bool>> readIndex;
     indexReads(readIndex, readsFile);
     std::ifstream alignments(alignmentFile);
+
+    cg_params prm = {merSize, solidThresh, commonKMers, minAnchors};
+    cg_handle* h = nullptr;
+    if (cg_create(device, &prm, &h) != CG_OK) die("cg_create", cg_last_error(nullptr));
+
+    if (deviceExtraction) {
+        // ---- phase A on the device: the store = every indexed read, decoded as getSequencesMap decodes them
+        robin_hood::unordered_map<std::string, uint32_t> id;
+        std::vector<uint64_t> storeOff(1, 0);
+        std::string store;
+        auto readId = [&](const std::string& name) {
+            auto it = id.find(name);
+            if (it != id.end()) return it->second;
+            uint32_t r = (uint32_t)id.size();
+            id[name] = r;
+            store += fullnum2str(readIndex[name]);
+            storeOff.push_back(store.size());
+            return r;
+        };
+        std::vector<uint32_t> pileRead, pileQlen, pileOvBegin(1, 0);
+        std::vector<cg_overlap> ovs;
+        std::vector<std::string> names;
+        while (!alignments.eof()) {
+            std::vector<Overlap> al = getNextReadPile(alignments, maxSupport);
+            if (al.size() == 0) continue;
+            names.push_back(al.begin()->qName);
+            pileRead.push_back(readId(al.begin()->qName));
+            pileQlen.push_back(al.begin()->qLength);
+            for (const Overlap& a : al) {
+                cg_overlap o = {readId(a.tName), a.strand ? 1u : 0u, a.qStart, a.qEnd, a.tStart, a.tEnd, a.tLength};
+                ovs.push_back(o);
+            }
+            pileOvBegin.push_back((uint32_t)ovs.size());
+        }
+        if (store.empty()) store.push_back('A');
+        cg_piles piles = {(uint32_t)id.size(), storeOff.data(), store.data(), (uint32_t)names.size(), pileRead.data(), pileQlen.data(),
+                          pileOvBegin.data(), ovs.data(), minSupport, windowSize, windowOverlap};
+        cg_results res; cg_window_set ws; cg_corrected cor;
+        if (cg_upload_piles(h, &piles) != CG_OK) die("cg_upload_piles", cg_last_error(h));
+        if (cg_run(h) != CG_OK) die("cg_run", cg_last_error(h));
+        if (cg_download(h, &res) != CG_OK) die("cg_download", cg_last_error(h));
+        if (cg_download_windows(h, 0, &ws) != CG_OK) die("cg_download_windows", cg_last_error(h));
+        if (cg_reanchor_reads(h, &ws.batch, &res, &ws.reads, &cor) != CG_OK) die("cg_reanchor_reads", cg_last_error(h));
+        for (size_t r = 0; r < names.size(); ++r) {
+            if (ws.reads.read_win_begin[r + 1] == ws.reads.read_win_begin[r]) continue;
+            std::string corrected(cor.bases + cor.read_off[r], cor.bases + cor.read_off[r + 1]);
+            corrected = trimRead(corrected, 1);
+            if (!dropRead(corrected) && corrected.length() != 0) std::cout << ">" << names[r] << std::endl << corrected << std::endl;
+        }
+        cg_free_corrected(&cor); cg_free_window_set(&ws); cg_free_results(&res); cg_destroy(h);
+        return 0;
+    }
 
     // ---- phase A
     std::vector<uint32_t> winSeqBegin(1, 0), readWinBegin(1, 0), winPos;
@@ -84,9 +140,6 @@ int main(int argc, char** argv) {
     }
 
     // ---- GPU
-    cg_params prm = {merSize, solidThresh, commonKMers, minAnchors};
-    cg_handle* h = nullptr;
-    if (cg_create(device, &prm, &h) != CG_OK) die("cg_create", cg_last_error(nullptr));
     if (bases.empty()) bases.push_back('A');
     if (readBases.empty()) readBases.push_back('A');
     if (winPos.empty()) winPos.push_back(0);

@@ -15,6 +15,8 @@
 //   alignConsensus                            src/correctionAlignment.cpp:47-139
 //   (re-anchoring; pulls in the vendored SSW library,
 //    BMEAN/Complete-Striped-Smith-Waterman-Library/src/{ssw.c,ssw_cpp.cpp})
+//   getAlignmentWindowsPositions / getAlignmentWindowsSequences   src/alignmentWindows.cpp:27-149
+//   (window extraction)
 //
 // Used by: tests/ (to pin oracle/consent_oracle.c and to generate
 // tests/golden/*), bench.py's cpu_baseline / --impl reference legs.
@@ -37,6 +39,7 @@
 #include "correctionMSA.h"       // src/correctionMSA.h
 #include "correctionDBG.h"       // src/correctionDBG.h
 #include "correctionAlignment.h" // src/correctionAlignment.h (alignConsensus)
+#include "alignmentWindows.h"    // src/alignmentWindows.h (window positions / piles; pulls in Overlap.h)
 #include "consent_b200.h"        // our ABI structs (cg_batch, cg_results, cg_params)
 
 // ---- prototypes of the reference's stage functions (external linkage in
@@ -233,6 +236,65 @@ int ref_reanchor_reads(const cg_batch* win, const cg_results* cons, const cg_rea
 
 void ref_free_corrected(cg_corrected* c) {
     if (c && c->owner_) { delete static_cast<CorrectedOwner*>(c->owner_); c->owner_ = nullptr; }
+}
+
+// ---- window extraction: the reference's own phase A of processRead (src/CONSENT-correction.cpp:21-35) --------------------
+// Overlaps are rebuilt field by field (src/Overlap.h:8-20), reads are named by their store index, `sequences` holds the reads
+// a pile mentions exactly as getSequencesMap would have decoded them from the 2-bit index (src/alignmentPiles.cpp:5-20).
+struct WindowSetOwner {
+    std::vector<uint32_t> wsb, rwb, wpos, wend;
+    std::vector<uint64_t> soff, roff;
+    std::string bases, rbases;
+};
+
+int ref_extract_windows(const cg_piles* p, unsigned merSize, cg_window_set* out) {
+    if (!p || !out) return CG_ERR_INVALID_ARG;
+    WindowSetOwner* ow = new WindowSetOwner();
+    ow->wsb.push_back(0); ow->rwb.push_back(0); ow->soff.push_back(0); ow->roff.push_back(0);
+    auto store = [&](uint32_t r) { return std::string(p->store_bases + p->store_off[r], p->store_bases + p->store_off[r + 1]); };
+    for (uint32_t pi = 0; pi < p->n_piles; ++pi) {
+        std::vector<Overlap> al;
+        robin_hood::unordered_map<std::string, std::string> sequences;
+        const std::string qName = "r" + std::to_string(p->pile_read[pi]);
+        sequences[qName] = store(p->pile_read[pi]);
+        for (uint32_t o = p->pile_ov_begin[pi]; o < p->pile_ov_begin[pi + 1]; ++o) {
+            const cg_overlap& c = p->overlaps[o];
+            Overlap a;
+            a.qName = qName; a.qLength = p->pile_qlen[pi]; a.qStart = c.q_start; a.qEnd = c.q_end; a.strand = c.strand != 0;
+            a.tName = "r" + std::to_string(c.t_read); a.tLength = c.t_length; a.tStart = c.t_start; a.tEnd = c.t_end;
+            a.resMatches = 0; a.alBlockLen = 0; a.mapQual = 0;
+            if (sequences[a.tName] == "") sequences[a.tName] = store(c.t_read);
+            al.push_back(a);
+        }
+        if (!al.empty()) {
+            std::vector<std::pair<unsigned, unsigned>> pilesPos =
+                getAlignmentWindowsPositions(al.begin()->qLength, al, p->min_support, 0, p->window_size, (int)p->window_overlap);
+            for (auto& pp : pilesPos) {
+                std::vector<std::string> pile = getAlignmentWindowsSequences(al, p->min_support, p->window_size, p->window_overlap, sequences,
+                                                                             pp.first, pp.second, merSize, 0, 0);
+                if (pile.empty()) { delete ow; return CG_ERR_INVALID_ARG; }      // the reference dereferences curPile[0] (CONSENT-correction.cpp:36)
+                for (auto& s : pile) { ow->bases += s; ow->soff.push_back(ow->bases.size()); }
+                ow->wsb.push_back((uint32_t)(ow->soff.size() - 1));
+                ow->wpos.push_back(pp.first); ow->wend.push_back(pp.second);
+            }
+        }
+        ow->rbases += sequences[qName];
+        ow->roff.push_back(ow->rbases.size());
+        ow->rwb.push_back((uint32_t)ow->wpos.size());
+    }
+    if (ow->wpos.empty()) { ow->wpos.push_back(0); ow->wend.push_back(0); }
+    out->batch.n_windows = (uint32_t)(ow->wsb.size() - 1);
+    out->batch.win_seq_begin = ow->wsb.data(); out->batch.seq_off = ow->soff.data(); out->batch.bases = ow->bases.data();
+    out->reads.n_reads = p->n_piles; out->reads.read_win_begin = ow->rwb.data(); out->reads.read_off = ow->roff.data();
+    out->reads.read_bases = ow->rbases.data(); out->reads.win_pos = ow->wpos.data();
+    out->reads.window_size = p->window_size; out->reads.window_overlap = p->window_overlap;
+    out->win_end = ow->wend.data();
+    out->owner_ = ow;
+    return CG_OK;
+}
+
+void ref_free_window_set(cg_window_set* s) {
+    if (s && s->owner_) { delete static_cast<WindowSetOwner*>(s->owner_); s->owner_ = nullptr; }
 }
 
 // Per-stage text dump of one window, produced by calling the reference's own

@@ -5,8 +5,9 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-from consent_b200._ffi import (Batch, Corrected, Params, REPO_DIR, Reads, Results, cg_batch, cg_corrected,
-                               cg_counters, cg_params, cg_reads, cg_results, results_to_c)
+from consent_b200._ffi import (Batch, Corrected, Params, Piles, REPO_DIR, Reads, Results, cg_batch, cg_corrected,
+                               cg_counters, cg_params, cg_piles, cg_reads, cg_results, cg_window_set, results_to_c,
+                               window_set_to_py)
 
 ORACLE_DIR = os.path.join(REPO_DIR, "oracle")
 
@@ -51,6 +52,21 @@ class _Checker:
         self._msa.argtypes = [C.POINTER(C.c_char_p), C.c_uint32]
         self._free_text = getattr(self.lib, self.prefix + "_free_text")
         self._free_text.argtypes = [C.c_void_p]
+
+    def extract_windows(self, piles: Piles, mer_size: int = 9):
+        """Phase A of processRead: window positions + piles of every read pile -> (Batch, Reads, win_end)"""
+        f = getattr(self.lib, self.prefix + "_extract_windows")
+        f.restype = C.c_int
+        f.argtypes = [C.POINTER(cg_piles), C.c_uint, C.POINTER(cg_window_set)]
+        free = getattr(self.lib, self.prefix + "_free_window_set")
+        free.argtypes = [C.POINTER(cg_window_set)]
+        cp, ws = piles.c(), cg_window_set()
+        rc = f(C.byref(cp), mer_size, C.byref(ws))
+        if rc != 0:
+            raise RuntimeError(f"{self.prefix}_extract_windows -> {rc}")
+        out = window_set_to_py(ws)
+        free(C.byref(ws))
+        return out
 
     def reanchor_reads(self, batch: Batch, res: Results, reads: Reads, params: Params = Params(), threads: int = 1):
         """alignConsensus for every read -> (Corrected, seconds of the compute loop)"""

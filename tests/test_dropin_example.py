@@ -58,6 +58,28 @@ def test_dropin_binary_on_emulated_kernels_prints_the_reference_fasta(small, ent
     assert out == want
 
 
+def test_dropin_binary_with_device_side_extraction_on_emulated_kernels(small, entry):
+    """-x: the window cutting of phase A runs on the device too (cg_upload_piles); still the reference's FASTA."""
+    d, paf, fa, want = small
+    exe = _binary("consent_correction_b200")
+    emu = entry.build_emu()
+    libdir = d / "emulib"
+    libdir.mkdir(exist_ok=True)
+    link = libdir / "libconsent_b200.so"
+    if not link.exists():
+        os.symlink(emu, link)
+    env = dict(os.environ, LD_LIBRARY_PATH=str(libdir))
+    out = subprocess.run([exe, "-x", "-a", paf, "-r", fa] + FLAGS, check=True, capture_output=True, env=env).stdout
+    assert out == want
+
+
+@pytest.mark.gpu
+def test_dropin_binary_with_device_side_extraction_on_the_gpu(small, gpu_lib):
+    d, paf, fa, want = small
+    out = subprocess.run([_binary("consent_correction_b200"), "-x", "-a", paf, "-r", fa] + FLAGS, check=True, capture_output=True).stdout
+    assert out == want
+
+
 @pytest.mark.gpu
 def test_dropin_binary_on_the_gpu_prints_the_reference_fasta(small, gpu_lib):
     """The same through libconsent_b200.so on a B200: bit-exact corrected FASTA for the real-data example."""
