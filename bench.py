@@ -15,6 +15,9 @@ quoted on, BASELINE.json configs[2] = 100 000 windows of 500 bases x 150 sequenc
   reanchor     (N=1) the next row of SURVEY §8f on its own bounded workload: alignConsensus for every read
                (cg_reanchor_reads) — kernel windows/s and GCUPS from CUDA events, the two-stage call chain
                cg_correct_windows -> cg_reanchor_reads with host buffers, and the reference's alignConsensus on the host cores
+  extract      (N=1) SURVEY §8f rank 2 on its own bounded workload: windows cut on the device from a read store + overlap
+               tuples (cg_upload_piles); the copy kernel against the HBM roofline, and the whole chain overlap tuples ->
+               corrected reads (extraction, window path, re-anchoring) with only the read store and the tuples uploaded
   --impl reference : times that CPU implementation as the arm itself.
 """
 from __future__ import annotations
@@ -202,6 +205,63 @@ def bench_reanchor(cor, n_reads: int, cores: int, steps: int) -> dict:
     return out
 
 
+def bench_extract(cor, n_reads: int, cores: int, steps: int, hbm_peak: float) -> dict:
+    """Window extraction on the device at the config-3 depth: seeded 8 kb PB reads over a random genome
+    at 150x, piles capped at 150 overlaps.  k_ex_copy reads and writes one byte per pile base: a plain HBM roofline row.
+    chain = cg_upload_piles -> cg_run -> cg_download -> cg_download_windows -> cg_reanchor_reads, i.e. overlap tuples and the
+    read store in host memory to corrected reads in host memory."""
+    import torch
+    from consent_b200.synth import synth_piles
+    read_len = 8000
+    piles = synth_piles(n_reads, genome_len=int(n_reads * read_len / 150), read_len=read_len, seed=42, max_support=150)
+    cor.upload_piles(piles)                                   # warm-up (allocations)
+    k_ms, c_ms = [], []
+    for _ in range(max(steps, 1)):
+        cor.upload_piles(piles)
+        st = cor.extract_stats()
+        k_ms.append(st["kernel_ms"]); c_ms.append(st["copy_ms"])
+    batch, reads, _ = cor.download_windows(with_bases=False)
+    W = batch.n_windows
+    copy_ms, kernel_ms = float(np.mean(c_ms)), float(np.mean(k_ms))
+    achieved = 2 * st["pile_bytes"] / (copy_ms / 1e3) / 1e9
+    out = {"workload": f"{n_reads} synthetic 8 kb PB reads at 150x (seed 42), {len(piles.overlaps)} overlap tuples -> {W} windows, "
+                       f"{batch.n_seqs / max(W, 1):.0f} seqs/window",
+           "windows": W, "pile_bytes": st["pile_bytes"], "kernel_ms": kernel_ms,
+           "kernel_windows_per_s": W / (kernel_ms / 1e3),
+           "roofline": {"bound": "hbm", "kernel": "k_ex_copy", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": achieved / hbm_peak, "algorithmic_bytes_per_launch": 2 * st["pile_bytes"], "ms_per_launch": copy_ms}}
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(max(steps, 1)):
+        cor.upload_piles(piles)
+        cor.run()
+        res = cor.download()
+        b, rd, _ = cor.download_windows(with_bases=False)
+        got = cor.reanchor_reads(b, res, rd)
+        res = None
+    torch.cuda.synchronize()
+    chain_s = (time.perf_counter() - t0) / max(steps, 1)
+    out["chain_windows_per_s"] = W / chain_s
+    out["chain"] = "cg_upload_piles + cg_run + cg_download + cg_download_windows + cg_reanchor_reads: overlap tuples + read store in, corrected reads out"
+    out["chain_h2d_bytes"] = int(piles.store_bases.nbytes + piles.overlaps.nbytes + piles.store_off.nbytes)
+    try:
+        checker, kind = cpu_reference(None, cores)
+        n = min(piles.n_piles, 64)
+        from consent_b200._ffi import Piles
+        sub = Piles(piles.store_off, piles.store_bases, piles.pile_read[:n], piles.pile_qlen[:n], piles.pile_ov_begin[:n + 1],
+                    piles.overlaps[:int(piles.pile_ov_begin[n])], piles.min_support, piles.window_size, piles.window_overlap)
+        t0 = time.perf_counter()
+        wb, wr, _ = checker.extract_windows(sub)
+        sec = time.perf_counter() - t0
+        out["cpu_reference"] = {"value": wb.n_windows / sec, "unit": "windows/s", "cores": 1, "kind": kind,
+                                "sample": f"first {n} piles ({wb.n_windows} windows), {sec:.2f} s, one thread (the harness is serial)"}
+        w1 = wb.n_windows
+        out["parity_spot_check"] = bool(np.array_equal(wb.seq_off, b.seq_off[:len(wb.seq_off)]) and np.array_equal(wr.win_pos, rd.win_pos[:w1]))
+    except Exception as e:
+        out["cpu_reference"] = {"value": None, "kind": "unavailable", "sample": repr(e)}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -213,6 +273,8 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--chunk-windows", type=int, default=0, help="windows per chunk (0: library default); never changes results")
     ap.add_argument("--lanes", type=int, default=0, help="chunks in flight (0: library default = 2); never changes results")
+    ap.add_argument("--extract-reads", type=int, default=int(os.environ.get("CG_BENCH_EXTRACT_READS", "2100")),
+                    help="reads of the window-extraction measurement (0: skip it)")
     ap.add_argument("--reanchor-reads", type=int, default=int(os.environ.get("CG_BENCH_REANCHOR_READS", "2600")),
                     help="reads of the re-anchoring measurement (0: skip it)")
     args = ap.parse_args()
@@ -383,13 +445,20 @@ def main():
         except Exception as e:
             reanchor = {"error": repr(e)}
 
+    extract = None
+    if world == 1 and args.extract_reads > 0:
+        try:
+            extract = bench_extract(cor, args.extract_reads, cores, args.steps, peak)
+        except Exception as e:
+            extract = {"error": repr(e)}
+
     out = {"metric": METRIC, "value": value, "unit": "windows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "int16/u8", "data": "synthetic", "config": config, "clocks": clocks,
            "e2e": {"value": world * args.windows * args.steps / e2e_s, "unit": "windows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
            "gpu_launches": launches, "wall_ms_per_step": wall_ms / args.steps,
            "roofline": roofline, "cpu_baseline": cpu,
-           "counters_per_step": counters, "reanchor": reanchor}
+           "counters_per_step": counters, "reanchor": reanchor, "extract": extract}
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -166,7 +166,7 @@ struct cg_handle {
     std::vector<u32> ex_rwb, ex_wpos, ex_wend, ex_pile_read_h;
     std::vector<u64> ex_store_off_h;
     u32 ex_ws = 0, ex_ovl = 0;
-    float ex_ms = 0;
+    float ex_ms = 0, ex_copy_ms = 0;
     u64 ex_bytes = 0;
 };
 
@@ -1186,8 +1186,8 @@ int cg_upload_piles(cg_handle* h, const cg_piles* P) {
     A.cov = h->ex_cov.as<u32>(); A.cov_off = h->ex_cov_off.as<u64>(); A.win_cap_off = h->ex_cap_off.as<u64>();
     A.cap_beg = h->ex_cap_beg.as<u32>(); A.cap_end = h->ex_cap_end.as<u32>(); A.n_win = h->ex_nwin.as<u32>();
     A.flags = h->ex_flags.as<u32>();
-    cudaEvent_t e0, e1, e2, e3;
-    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreate(&e2)); CK(cudaEventCreate(&e3));
+    cudaEvent_t e0, e1, e2, e2b, e2c, e3;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreate(&e2)); CK(cudaEventCreate(&e2b)); CK(cudaEventCreate(&e2c)); CK(cudaEventCreate(&e3));
     CK(cudaEventRecord(e0, st));
     if (n_store_bases) CG_LAUNCH(k_ex_normalise, (u32)std::min<u64>((n_store_bases + 255) / 256, (u64)h->sms * 16), 256, 0, st, h->ex_store.as<char>(), n_store_bases);
     if (NP) CG_LAUNCH(k_ex_positions, (NP + 3) / 4, 128, 0, st, A);
@@ -1239,6 +1239,7 @@ int cg_upload_piles(cg_handle* h, const cg_piles* P) {
     A.slot_loc = h->ex_slot_loc.as<u32>(); A.win_nseq = h->ex_win_nseq.as<u32>(); A.win_nbytes = h->ex_win_nbytes.as<u32>();
     CK(cudaEventRecord(e2, st));
     if (W) CG_LAUNCH(k_ex_sizes, (W + 3) / 4, 128, 0, st, A);
+    CK(cudaEventRecord(e2b, st));
     // ---- per-window totals -> win_seq_begin / window base offsets (host prefix: the planner needs them on the host anyway)
     std::vector<u32> nseq((size_t)W + 1, 0), nbytes((size_t)W + 1, 0);
     if (W) {
@@ -1265,6 +1266,7 @@ int cg_upload_piles(cg_handle* h, const cg_piles* P) {
     CK(cudaMemcpyAsync(h->ex_win_base.p, h->h_wbase.data(), ((size_t)W + 1) * 8, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->d_seq_off.as<u64>() + n_seqs, &h->h_wbase[W], 8, cudaMemcpyHostToDevice, st));
     A.win_seq_begin = h->d_wsb.as<u32>(); A.win_base = h->ex_win_base.as<u64>(); A.seq_off = h->d_seq_off.as<u64>(); A.bases = h->d_bases.as<char>();
+    CK(cudaEventRecord(e2c, st));
     if (W) CG_LAUNCH(k_ex_copy, std::min<u32>(W, (u32)h->sms * 16), 256, 0, st, A);
     CK(cudaEventRecord(e3, st));
     CK(cudaGetLastError());
@@ -1275,10 +1277,10 @@ int cg_upload_piles(cg_handle* h, const cg_piles* P) {
         h->ev_h2d.push_back(e);
     }
     CK(cudaStreamSynchronize(st));
-    float m1 = 0, m2 = 0;
-    CK(cudaEventElapsedTime(&m1, e0, e1)); CK(cudaEventElapsedTime(&m2, e2, e3));
-    for (cudaEvent_t e : {e0, e1, e2, e3}) cudaEventDestroy(e);
-    h->ex_ms = m1 + m2; h->ex_bytes = n_bases;
+    float m1 = 0, m2 = 0, m3 = 0;
+    CK(cudaEventElapsedTime(&m1, e0, e1)); CK(cudaEventElapsedTime(&m2, e2, e2b)); CK(cudaEventElapsedTime(&m3, e2c, e3));
+    for (cudaEvent_t e : {e0, e1, e2, e2b, e2c, e3}) cudaEventDestroy(e);
+    h->ex_ms = m1 + m2 + m3; h->ex_copy_ms = m3; h->ex_bytes = n_bases;
     h->ex_pile_read_h.assign(P->pile_read, P->pile_read + NP);
     h->ex_store_off_h.assign(P->store_off, P->store_off + NS + 1);
     h->ex_ws = P->window_size; h->ex_ovl = P->window_overlap;
@@ -1331,9 +1333,10 @@ void cg_free_window_set(cg_window_set* s) {
     if (s && s->owner_) { delete static_cast<HostWindowSet*>(s->owner_); s->owner_ = nullptr; }
 }
 
-int cg_extract_stats(const cg_handle* h, float* kernel_ms, uint64_t* pile_bytes) {
+int cg_extract_stats(const cg_handle* h, float* kernel_ms, float* copy_ms, uint64_t* pile_bytes) {
     if (!h) return CG_ERR_INVALID_ARG;
     if (kernel_ms) *kernel_ms = h->ex_ms;
+    if (copy_ms) *copy_ms = h->ex_copy_ms;
     if (pile_bytes) *pile_bytes = h->ex_bytes;
     return CG_OK;
 }

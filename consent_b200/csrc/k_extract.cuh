@@ -193,6 +193,44 @@ __global__ void k_ex_sizes(CgExtractArgs A) {
 __device__ __forceinline__ char cg_ex_comp(char c) {            // reverseComplement.cpp:34-43 (the store only holds A, C, G, T)
     return c == 'A' ? 'T' : c == 'T' ? 'A' : c == 'C' ? 'G' : c == 'G' ? 'C' : (char)0;
 }
+// four bases at once: A (0x41) <-> T (0x54) is x ^ 0x15, C (0x43) <-> G (0x47) is x ^ 0x04; bit 1 tells the pairs apart
+__device__ __forceinline__ u32 cg_ex_comp4(u32 x) { return x ^ 0x15151515u ^ (((x >> 1) & 0x01010101u) * 0x11u); }
+// the 4 bytes at byte address `a` of a buffer of aligned 32-bit words (little endian): two aligned loads + a funnel shift
+__device__ __forceinline__ u32 cg_ex_load4(const char* base, u64 a) {
+    const u32* w = (const u32*)(base + (a & ~(u64)3));
+    const u32 sh = (u32)(a & 3) * 8;
+    const u32 lo = w[0];
+    return sh ? __funnelshift_r(lo, w[1], sh) : lo;
+}
+
+// One piece by one warp: dst[0..len) <- store[src..] (forward) or the complement of store[src], store[src-1], ... (reverse).
+// Head bytes up to the first 16-byte boundary of dst and the tail go byte by byte; the body moves 16 bytes per lane and step
+// (one 128-bit store, aligned 32-bit loads re-aligned by funnel shifts), 512 bytes per warp and step.
+__device__ __forceinline__ void cg_ex_copy_piece(char* dst, const char* store, u64 src, bool reverse, u32 len, u32 lane) {
+    const u32 head = min(len, (u32)((16 - ((u64)dst & 15)) & 15));
+    const u32 body = (len - head) & ~15u;
+    if (!reverse) {
+        if (lane < head) dst[lane] = store[src + lane];
+        for (u32 o = head + lane * 16; o < head + body; o += 512) {
+            uint4 v;
+            v.x = cg_ex_load4(store, src + o); v.y = cg_ex_load4(store, src + o + 4);
+            v.z = cg_ex_load4(store, src + o + 8); v.w = cg_ex_load4(store, src + o + 12);
+            *(uint4*)(dst + o) = v;
+        }
+        for (u32 o = head + body + lane; o < len; o += 32) dst[o] = store[src + o];
+    } else {
+        if (lane < head) dst[lane] = cg_ex_comp(store[src - lane]);
+        for (u32 o = head + lane * 16; o < head + body; o += 512) {
+            uint4 v;                                            // output bytes o .. o+3 = complement of store[src-o], store[src-o-1], ...
+            v.x = cg_ex_comp4(__byte_perm(cg_ex_load4(store, src - o - 3), 0, 0x0123));
+            v.y = cg_ex_comp4(__byte_perm(cg_ex_load4(store, src - o - 7), 0, 0x0123));
+            v.z = cg_ex_comp4(__byte_perm(cg_ex_load4(store, src - o - 11), 0, 0x0123));
+            v.w = cg_ex_comp4(__byte_perm(cg_ex_load4(store, src - o - 15), 0, 0x0123));
+            *(uint4*)(dst + o) = v;
+        }
+        for (u32 o = head + body + lane; o < len; o += 32) dst[o] = cg_ex_comp(store[src - o]);
+    }
+}
 
 // One CTA per window: every kept piece copied from the store into the window's slice of the batch, seq_off filled.
 __global__ void __launch_bounds__(256) k_ex_copy(CgExtractArgs A) {
@@ -214,19 +252,12 @@ __global__ void __launch_bounds__(256) k_ex_copy(CgExtractArgs A) {
                 rank += __popc(m);
             }
         }
-        // pieces: one warp per piece, 32 consecutive bases per step (coalesced on both sides)
+        // pieces: one warp per piece
         for (u32 s = warp; s < nslot; s += nwarps) {
             const u32 len = A.slot_len[sb + s];
             if (!len) continue;
             const u64 src = A.slot_src[sb + s];
-            char* dst = A.bases + wbase + A.slot_loc[sb + s];
-            if (src >> 63) {
-                const char* from = A.store + (src & ~(1ull << 63));
-                for (u32 i = lane; i < len; i += 32) dst[i] = cg_ex_comp(*(from - i));
-            } else {
-                const char* from = A.store + src;
-                for (u32 i = lane; i < len; i += 32) dst[i] = from[i];
-            }
+            cg_ex_copy_piece(A.bases + wbase + A.slot_loc[sb + s], A.store, src & ~(1ull << 63), (src >> 63) != 0, len, lane);
         }
     }
 }

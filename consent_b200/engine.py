@@ -73,7 +73,7 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.cg_download_windows.argtypes = [H, C.c_int, C.POINTER(cg_window_set)]
     lib.cg_free_window_set.argtypes = [C.POINTER(cg_window_set)]
     lib.cg_extract_stats.restype = C.c_int
-    lib.cg_extract_stats.argtypes = [H, C.POINTER(C.c_float), C.POINTER(C.c_uint64)]
+    lib.cg_extract_stats.argtypes = [H, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_uint64)]
     return lib
 
 
@@ -159,9 +159,9 @@ class Corrector:
         return out
 
     def extract_stats(self) -> dict:
-        ms, nb = C.c_float(0), C.c_uint64(0)
-        self._check(self.lib.cg_extract_stats(self._h, C.byref(ms), C.byref(nb)))
-        return {"kernel_ms": float(ms.value), "pile_bytes": int(nb.value)}
+        ms, cms, nb = C.c_float(0), C.c_float(0), C.c_uint64(0)
+        self._check(self.lib.cg_extract_stats(self._h, C.byref(ms), C.byref(cms), C.byref(nb)))
+        return {"kernel_ms": float(ms.value), "copy_ms": float(cms.value), "pile_bytes": int(nb.value)}
 
     # -- staged (bench: keep the batch resident in HBM, time the kernels alone) ---------------
     def upload(self, batch: Batch):

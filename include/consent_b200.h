@@ -227,8 +227,9 @@ typedef struct cg_window_set {
 int  cg_upload_piles(cg_handle* h, const cg_piles* piles);
 int  cg_download_windows(cg_handle* h, int with_bases, cg_window_set* out);
 void cg_free_window_set(cg_window_set* s);
-/* CUDA-event time (ms) of the extraction kernels of the last cg_upload_piles and the pile bytes they wrote. */
-int  cg_extract_stats(const cg_handle* h, float* kernel_ms, uint64_t* pile_bytes);
+/* CUDA-event time (ms) of the extraction kernels of the last cg_upload_piles (host round trips for the window counts
+ * excluded), of the copy kernel alone (k_ex_copy: reads and writes one byte per pile base), and the pile bytes written. */
+int  cg_extract_stats(const cg_handle* h, float* kernel_ms, float* copy_ms, uint64_t* pile_bytes);
 
 /* Instrumentation -------------------------------------------------------- */
 #define CG_STAGE_PACK     0   /* ASCII -> 2-bit                                         */

@@ -22,7 +22,7 @@ for i in range(3):
     dt = time.time() - t
     st = cor.extract_stats()
     W = cor.chunk_count()
-    print(json.dumps({"step": "upload_piles", "wall_s": dt, **st, "GBps_written": st["pile_bytes"] / st["kernel_ms"] / 1e6}), flush=True)
+    print(json.dumps({"step": "upload_piles", "wall_s": dt, **st, "copy_GBps_rw": 2 * st["pile_bytes"] / max(st["copy_ms"], 1e-6) / 1e6}), flush=True)
 t = time.time(); cor.run(); t_run = time.time() - t
 res = cor.download()
 batch, reads, _ = cor.download_windows(with_bases=False)
