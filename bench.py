@@ -15,6 +15,9 @@ quoted on, BASELINE.json configs[2] = 100 000 windows of 500 bases x 150 sequenc
   reanchor     (N=1) the next row of SURVEY §8f on its own bounded workload: alignConsensus for every read
                (cg_reanchor_reads) — kernel windows/s and GCUPS from CUDA events, the two-stage call chain
                cg_correct_windows -> cg_reanchor_reads with host buffers, and the reference's alignConsensus on the host cores
+  ingest       (N=1) SURVEY §8f rank 3-4 on their own bounded workload: PAF text parsed, grouped, sorted and cut on the device
+               (k_paf_parse against the HBM roofline), next to the reference's getNextReadPile on one host thread; chain = PAF
+               text + read store in, trimmed / filtered FASTA sequence lines out
   extract      (N=1) SURVEY §8f rank 2 on its own bounded workload: windows cut on the device from a read store + overlap
                tuples (cg_upload_piles); the copy kernel against the HBM roofline, and the whole chain overlap tuples ->
                corrected reads (extraction, window path, re-anchoring) with only the read store and the tuples uploaded
@@ -262,6 +265,71 @@ def bench_extract(cor, n_reads: int, cores: int, steps: int, hbm_peak: float) ->
     return out
 
 
+def bench_ingest(cor, n_reads: int, cores: int, steps: int, hbm_peak: float) -> dict:
+    """PAF ingest on the device and the post-filters (rank 4): the PAF text of seeded 8 kb PB reads at 150x
+    (every true overlap, resMatches with ties) -> piles cut to 150 overlaps.  k_paf_parse reads every byte of the text once and
+    writes one 40-byte record per line: an HBM roofline row.  chain = cg_ingest_paf -> cg_upload_piles -> cg_run -> cg_download ->
+    cg_download_windows -> cg_finish_reads, i.e. PAF text + read store in host memory to FASTA sequence lines in host memory."""
+    import torch
+    from consent_b200.synth import synth_paf, synth_piles
+    read_len = 8000
+    piles = synth_piles(n_reads, genome_len=int(n_reads * read_len / 150), read_len=read_len, seed=42, max_support=4000)
+    text, names = synth_paf(piles, seed=42, tie_range=60)
+    ps = cor.ingest_paf(text, names, 150)                      # warm-up (allocations)
+    k_ms, p_ms = [], []
+    for _ in range(max(steps, 1)):
+        ps = cor.ingest_paf(text, names, 150)
+        st = cor.ingest_stats()
+        k_ms.append(st["kernel_ms"]); p_ms.append(st["parse_ms"])
+    kernel_ms, parse_ms = float(np.mean(k_ms)), float(np.mean(p_ms))
+    alg = len(text) + 40 * ps.n_lines + 8 * ps.n_lines
+    achieved = alg / (parse_ms / 1e3) / 1e9
+    out = {"workload": f"PAF text of {n_reads} synthetic 8 kb PB reads at 150x (seed 42): {len(text)} bytes, {ps.n_lines} lines -> "
+                       f"{ps.n_piles} piles, {len(ps.overlaps)} overlaps kept (maxSupport 150)",
+           "paf_bytes": len(text), "lines": ps.n_lines, "kernel_ms": kernel_ms, "kernel_lines_per_s": ps.n_lines / (kernel_ms / 1e3),
+           "kernel_GBps_text": len(text) / (kernel_ms / 1e3) / 1e9,
+           "roofline": {"bound": "hbm", "kernel": "k_paf_parse", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                        "algorithmic_bytes_per_launch": alg, "ms_per_launch": parse_ms,
+                        "model": "text bytes + 8 B newline position read + 40 B record written per line"}}
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(max(steps, 1)):
+        ps = cor.ingest_paf(text, names, 150)
+    torch.cuda.synchronize()
+    out["e2e_lines_per_s"] = ps.n_lines / ((time.perf_counter() - t0) / max(steps, 1))
+    t0 = time.perf_counter()
+    for _ in range(max(steps, 1)):
+        ps = cor.ingest_paf(text, names, 150)
+        cor.upload_piles(ps.piles(piles.store_off, piles.store_bases))
+        cor.run()
+        res = cor.download()
+        b, rd, _ = cor.download_windows(with_bases=False)
+        got = cor.finish_reads(b, res, rd, 1)
+        res = None
+    torch.cuda.synchronize()
+    chain_s = (time.perf_counter() - t0) / max(steps, 1)
+    out["chain_windows_per_s"] = b.n_windows / chain_s
+    out["chain"] = ("cg_ingest_paf + cg_upload_piles + cg_run + cg_download + cg_download_windows + cg_finish_reads: "
+                    "PAF text + read store in, trimmed / filtered FASTA sequence lines out")
+    out["chain_h2d_bytes"] = int(len(text) + piles.store_bases.nbytes + piles.store_off.nbytes + ps.overlaps.nbytes)
+    out["finish_kernel_ms"] = cor.finish_stats()["kernel_ms"]
+    out["fasta_records"] = int((got.read_off[1:] != got.read_off[:-1]).sum())
+    try:
+        checker, kind = cpu_reference(None, cores)
+        cut = text[:text.index(b"\n", min(len(text) - 1, 8 << 20)) + 1]             # a bounded sample: the first ~8 MB of lines
+        t0 = time.perf_counter()
+        want = checker.ingest_paf(cut, names, 150)
+        sec = time.perf_counter() - t0
+        out["cpu_reference"] = {"value": want.n_lines / sec, "unit": "lines/s", "cores": 1, "kind": kind,
+                                "sample": f"first {len(cut)} bytes ({want.n_lines} lines), {sec:.2f} s, one thread (getNextReadPile runs on the "
+                                          "reference's main thread, src/CONSENT-correction.cpp:87,107)"}
+        n = max(want.n_piles - 1, 0)                                                 # the sample's last pile may be cut short
+        out["parity_spot_check"] = bool(np.array_equal(want.overlaps[:int(want.pile_ov_begin[n])], ps.overlaps[:int(want.pile_ov_begin[n])]))
+    except Exception as e:
+        out["cpu_reference"] = {"value": None, "kind": "unavailable", "sample": repr(e)}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -273,6 +341,8 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--chunk-windows", type=int, default=0, help="windows per chunk (0: library default); never changes results")
     ap.add_argument("--lanes", type=int, default=0, help="chunks in flight (0: library default = 2); never changes results")
+    ap.add_argument("--ingest-reads", type=int, default=int(os.environ.get("CG_BENCH_INGEST_READS", "1000")),
+                    help="reads of the PAF-ingest / post-filter measurement (0: skip it)")
     ap.add_argument("--extract-reads", type=int, default=int(os.environ.get("CG_BENCH_EXTRACT_READS", "2100")),
                     help="reads of the window-extraction measurement (0: skip it)")
     ap.add_argument("--reanchor-reads", type=int, default=int(os.environ.get("CG_BENCH_REANCHOR_READS", "2600")),
@@ -452,13 +522,20 @@ def main():
         except Exception as e:
             extract = {"error": repr(e)}
 
+    ingest = None
+    if world == 1 and args.ingest_reads > 0:
+        try:
+            ingest = bench_ingest(cor, args.ingest_reads, cores, args.steps, peak)
+        except Exception as e:
+            ingest = {"error": repr(e)}
+
     out = {"metric": METRIC, "value": value, "unit": "windows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "int16/u8", "data": "synthetic", "config": config, "clocks": clocks,
            "e2e": {"value": world * args.windows * args.steps / e2e_s, "unit": "windows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
            "gpu_launches": launches, "wall_ms_per_step": wall_ms / args.steps,
            "roofline": roofline, "cpu_baseline": cpu,
-           "counters_per_step": counters, "reanchor": reanchor, "extract": extract}
+           "counters_per_step": counters, "reanchor": reanchor, "extract": extract, "ingest": ingest}
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -79,6 +79,16 @@ class cg_window_set(C.Structure):
     _fields_ = [("batch", cg_batch), ("reads", cg_reads), ("win_end", C.POINTER(C.c_uint32)), ("owner_", C.c_void_p)]
 
 
+class cg_read_names(C.Structure):
+    _fields_ = [("n_reads", C.c_uint32), ("name_off", C.POINTER(C.c_uint64)), ("names", C.c_char_p)]
+
+
+class cg_pile_set(C.Structure):
+    _fields_ = [("n_piles", C.c_uint32), ("pile_read", C.POINTER(C.c_uint32)), ("pile_qlen", C.POINTER(C.c_uint32)),
+                ("pile_ov_begin", C.POINTER(C.c_uint32)), ("overlaps", C.POINTER(cg_overlap)),
+                ("res_matches", C.POINTER(C.c_uint32)), ("n_lines", C.c_uint64), ("owner_", C.c_void_p)]
+
+
 class cg_synth_pile_spec(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("genome_len", C.c_uint32), ("n_reads", C.c_uint32), ("read_len", C.c_uint32),
                 ("n_piles", C.c_uint32), ("max_support", C.c_uint32), ("min_overlap", C.c_uint32),
@@ -257,6 +267,59 @@ class Piles:
                         self.n_piles, self.pile_read.ctypes.data_as(u32), self.pile_qlen.ctypes.data_as(u32),
                         self.pile_ov_begin.ctypes.data_as(u32), C.cast(self.overlaps.ctypes.data, C.POINTER(cg_overlap)),
                         self.min_support, self.window_size, self.window_overlap)
+
+
+class ReadNames:
+    """The read names of the store, index = store index (cg_read_names): FASTA headers up to the first blank."""
+
+    def __init__(self, names):
+        enc = [n.encode() if isinstance(n, str) else bytes(n) for n in names]
+        self.name_off = np.zeros(len(enc) + 1, np.uint64)
+        if enc:
+            self.name_off[1:] = np.cumsum([len(e) for e in enc])
+        self.names = np.frombuffer(b"".join(enc) or b"\0", np.uint8).copy()
+
+    @property
+    def n_reads(self) -> int:
+        return len(self.name_off) - 1
+
+    def c(self) -> cg_read_names:
+        return cg_read_names(self.n_reads, self.name_off.ctypes.data_as(C.POINTER(C.c_uint64)), C.cast(self.names.ctypes.data, C.c_char_p))
+
+
+class PileSet:
+    """Host copy of cg_pile_set: the piles getNextReadPile would return for a PAF text, one after the other."""
+
+    def __init__(self, c: cg_pile_set):
+        P = int(c.n_piles)
+        self.n_lines = int(c.n_lines)
+        self.pile_ov_begin = np.ctypeslib.as_array(c.pile_ov_begin, shape=(P + 1,)).copy()
+        n = int(self.pile_ov_begin[P])
+        self.pile_read = np.ctypeslib.as_array(c.pile_read, shape=(max(P, 1),))[:P].copy()
+        self.pile_qlen = np.ctypeslib.as_array(c.pile_qlen, shape=(max(P, 1),))[:P].copy()
+        self.overlaps = (np.ctypeslib.as_array(C.cast(c.overlaps, C.POINTER(C.c_uint32)), shape=(max(n, 1), 7))[:n].copy())
+        self.res_matches = np.ctypeslib.as_array(c.res_matches, shape=(max(n, 1),))[:n].copy()
+
+    @property
+    def n_piles(self) -> int:
+        return len(self.pile_ov_begin) - 1
+
+    def equals(self, o: "PileSet") -> bool:
+        return all(np.array_equal(getattr(self, n), getattr(o, n))
+                   for n in ("pile_ov_begin", "pile_read", "pile_qlen", "overlaps", "res_matches")) and self.n_lines == o.n_lines
+
+    def first_mismatch(self, o: "PileSet") -> str:
+        for n in ("pile_ov_begin", "pile_read", "pile_qlen", "res_matches", "overlaps"):
+            x, y = getattr(self, n), getattr(o, n)
+            if x.shape != y.shape:
+                return f"{n}: shapes {x.shape} / {y.shape}"
+            if not np.array_equal(x, y):
+                return f"{n}: first difference at {int(np.argmax((x != y).reshape(len(x), -1).any(axis=1)))}"
+        return "" if self.n_lines == o.n_lines else f"n_lines {self.n_lines} / {o.n_lines}"
+
+    def piles(self, store_off, store_bases, **kw) -> "Piles":
+        """These piles over a read store, as cg_upload_piles takes them."""
+        return Piles(store_off, store_bases, self.pile_read, self.pile_qlen, self.pile_ov_begin, self.overlaps, **kw)
 
 
 def window_set_to_py(ws: cg_window_set, with_bases: bool = True):

@@ -27,6 +27,7 @@
 #include "k_polish.cuh"
 #include "k_reanchor.cuh"
 #include "k_extract.cuh"
+#include "k_ingest.cuh"
 
 struct DevBuf {
     void* p = nullptr;
@@ -168,6 +169,11 @@ struct cg_handle {
     u32 ex_ws = 0, ex_ovl = 0;
     float ex_ms = 0, ex_copy_ms = 0;
     u64 ex_bytes = 0;
+    // PAF ingest (cg_ingest_paf) and post-filters (cg_finish_reads)
+    DevBuf in_text, in_tile, in_nl, in_names, in_name_off, in_slots, in_rec, in_head, in_pfirst, in_plast, in_keep, in_scratch,
+           in_pread, in_pqlen, in_ov, in_res, in_ctl, ra_skip;
+    float in_ms = 0, in_parse_ms = 0, fin_ms = 0;
+    u64 in_bytes = 0;
 };
 
 struct HostWindowSet {
@@ -684,7 +690,9 @@ void cg_destroy(cg_handle* h) {
                       &h->ra_scratch, &h->ra_ctl, &h->ex_store, &h->ex_store_off, &h->ex_pile_read, &h->ex_pile_qlen, &h->ex_pile_ovb, &h->ex_ov,
                       &h->ex_cov, &h->ex_cov_off, &h->ex_cap_off, &h->ex_cap_beg, &h->ex_cap_end, &h->ex_nwin, &h->ex_win_pile, &h->ex_win_beg,
                       &h->ex_win_end, &h->ex_slot_base, &h->ex_slot_len, &h->ex_slot_src, &h->ex_slot_loc, &h->ex_win_nseq, &h->ex_win_nbytes,
-                      &h->ex_win_base, &h->ex_flags};
+                      &h->ex_win_base, &h->ex_flags, &h->in_text, &h->in_tile, &h->in_nl, &h->in_names, &h->in_name_off, &h->in_slots, &h->in_rec,
+                      &h->in_head, &h->in_pfirst, &h->in_plast, &h->in_keep, &h->in_scratch, &h->in_pread, &h->in_pqlen, &h->in_ov, &h->in_res,
+                      &h->in_ctl, &h->ra_skip};
     for (DevBuf* b : bufs) b->release();
     for (auto& t : h->tier) { t.mem.release(); t.desc.release(); }
     delete h;
@@ -965,7 +973,7 @@ int cg_correct_windows(cg_handle* h, const cg_batch* in, cg_results* out) {
 }
 
 // ---- consensus re-anchoring: alignConsensus for every read of the batch ------------------------------
-int cg_reanchor_reads(cg_handle* h, const cg_batch* windows, const cg_results* cons, const cg_reads* reads, cg_corrected* out) {
+static int reanchor_impl(cg_handle* h, const cg_batch* windows, const cg_results* cons, const cg_reads* reads, u32 trim_mer, cg_corrected* out) {
     if (!h || !out) return CG_ERR_INVALID_ARG;
     if (!windows || !cons || !reads || !reads->read_win_begin || !reads->read_off || !windows->win_seq_begin || !windows->seq_off) {
         h->err = "null argument"; return CG_ERR_INVALID_ARG;
@@ -1083,6 +1091,20 @@ int cg_reanchor_reads(cg_handle* h, const cg_batch* windows, const cg_results* c
     if (R) CG_LAUNCH(k_reanchor, ctas, CG_RA_WARPS * 32, smem, st, A);
     CK(cudaEventRecord(e1, st));
     CK(cudaGetLastError());
+    // ---- post-filters in place: trimRead + dropRead rewrite the lengths and give the first kept base
+    h->fin_ms = 0;
+    if (trim_mer) {
+        cudaEvent_t f0, f1;
+        CK(h->ra_skip.ensure(((size_t)R + 1) * 4));
+        CK(cudaEventCreate(&f0)); CK(cudaEventCreate(&f1));
+        CK(cudaEventRecord(f0, st));
+        if (R) CG_LAUNCH(k_finish_reads, std::min<u32>(R, (u32)h->sms * 8), 256, 128, st, (const char*)h->ra_head.as<char>(), (const u64*)h->ra_head_off.as<u64>(),
+                         h->ra_len.as<u32>(), h->ra_skip.as<u32>(), R, trim_mer);
+        CK(cudaEventRecord(f1, st));
+        CK(cudaEventSynchronize(f1));
+        CK(cudaEventElapsedTime(&h->fin_ms, f0, f1));
+        cudaEventDestroy(f0); cudaEventDestroy(f1);
+    }
     // ---- lengths -> dense offsets -> gather -> host
     std::vector<u32> len((size_t)R + 1, 0);
     u32 ctl[4] = {0, 0, 0, 0};
@@ -1109,13 +1131,28 @@ int cg_reanchor_reads(cg_handle* h, const cg_batch* windows, const cg_results* c
     if (e == cudaSuccess) e = cudaMemcpyAsync(h->ra_out_off.p, hc->off, ((size_t)R + 1) * 8, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess && R && tot) {
         CG_LAUNCH(k_reanchor_gather, std::min<u32>(R, (u32)h->sms * 8), 256, 0, st, (const char*)h->ra_head.as<char>(), (const u64*)h->ra_head_off.as<u64>(),
-                  (const u64*)h->ra_out_off.as<u64>(), h->ra_out.as<char>(), R);
+                  (const u32*)(trim_mer ? h->ra_skip.as<u32>() : nullptr), (const u64*)h->ra_out_off.as<u64>(), h->ra_out.as<char>(), R);
         e = cudaMemcpyAsync(hc->bases, h->ra_out.p, tot, cudaMemcpyDeviceToHost, st);
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) { h->err = std::string("re-anchoring download: ") + cudaGetErrorString(e); return fail(CG_ERR_CUDA); }
     hc->bases[tot] = 0;
     out->n_reads = R; out->read_off = hc->off; out->bases = hc->bases; out->owner_ = hc;
+    return CG_OK;
+}
+
+int cg_reanchor_reads(cg_handle* h, const cg_batch* windows, const cg_results* cons, const cg_reads* reads, cg_corrected* out) {
+    return reanchor_impl(h, windows, cons, reads, 0u, out);
+}
+
+// ---- post-filters: alignConsensus + trimRead + dropRead = the sequence line of every FASTA record --------
+int cg_finish_reads(cg_handle* h, const cg_batch* windows, const cg_results* cons, const cg_reads* reads, uint32_t trim_mer, cg_corrected* out) {
+    return reanchor_impl(h, windows, cons, reads, trim_mer, out);
+}
+
+int cg_finish_stats(const cg_handle* h, float* kernel_ms) {
+    if (!h) return CG_ERR_INVALID_ARG;
+    if (kernel_ms) *kernel_ms = h->fin_ms;
     return CG_OK;
 }
 
@@ -1132,6 +1169,146 @@ int cg_reanchor_stats(const cg_handle* h, float* kernel_ms, uint64_t* dp_cells) 
     if (!h) return CG_ERR_INVALID_ARG;
     if (kernel_ms) *kernel_ms = h->ra_ms;
     if (dp_cells) *dp_cells = h->ra_cells;
+    return CG_OK;
+}
+
+// ---- PAF ingest: every getNextReadPile of a PAF text on the device ------------------------------------------
+struct HostPileSet { std::vector<u32> pile_read, pile_qlen, ovb, res; std::vector<cg_overlap> ov; };
+
+int cg_ingest_paf(cg_handle* h, const char* paf, uint64_t nbytes, const cg_read_names* names, uint32_t max_support, cg_pile_set* out) {
+    if (!h || !out) return CG_ERR_INVALID_ARG;
+    if (!names || !names->name_off || (nbytes && !paf) || (names->n_reads && !names->names)) { h->err = "null argument"; return CG_ERR_INVALID_ARG; }
+    if (max_support == 0) { h->err = "max_support must be at least 1"; return CG_ERR_INVALID_ARG; }
+    if (nbytes && paf[nbytes - 1] != '\n') {
+        h->err = "the PAF text must end with a newline (getNextReadPile never returns on a last line without one, src/alignmentPiles.cpp:29-35)";
+        return CG_ERR_INVALID_ARG;
+    }
+    cudaSetDevice(h->device);
+    cudaStream_t st = h->lane[0].stream;
+    const u32 NN = names->n_reads;
+    const u64 name_bytes = names->name_off[NN];
+    const u32 n_tiles = (u32)((nbytes + CG_IN_TILE - 1) / CG_IN_TILE);
+    if ((nbytes + CG_IN_TILE - 1) / CG_IN_TILE >= (1ull << 31)) { h->err = "PAF text too large for one call"; return CG_ERR_CAPACITY; }
+    u32 slots = 64;
+    while (slots < 2 * NN + 2) slots <<= 1;
+    CK(h->in_text.ensure((size_t)n_tiles * CG_IN_TILE + 16)); CK(h->in_tile.ensure(((size_t)n_tiles + 1) * 8));
+    CK(h->in_names.ensure(name_bytes + 16)); CK(h->in_name_off.ensure(((size_t)NN + 1) * 8)); CK(h->in_slots.ensure((size_t)slots * 4));
+    CK(h->in_ctl.ensure(64));
+    if (nbytes) {
+        CK(cudaMemcpyAsync(h->in_text.p, paf, nbytes, cudaMemcpyHostToDevice, st));
+        CK(cudaMemsetAsync(h->in_text.as<char>() + nbytes, 0, (size_t)n_tiles * CG_IN_TILE - nbytes, st));
+    }
+    if (name_bytes) CK(cudaMemcpyAsync(h->in_names.p, names->names, name_bytes, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->in_name_off.p, names->name_off, ((size_t)NN + 1) * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(h->in_slots.p, 0, (size_t)slots * 4, st));
+    CK(cudaMemsetAsync(h->in_ctl.p, 0, 64, st));
+    CgIngestArgs A{};
+    A.text = h->in_text.as<char>(); A.nbytes = nbytes; A.tile_cnt = h->in_tile.as<u64>(); A.n_tiles = n_tiles;
+    A.names = h->in_names.as<char>(); A.name_off = h->in_name_off.as<u64>(); A.n_names = NN; A.slots = h->in_slots.as<u32>(); A.slot_mask = slots - 1;
+    A.max_support = max_support; A.ctl = h->in_ctl.as<u32>();
+    cudaEvent_t ev[8];
+    for (cudaEvent_t& e : ev) CK(cudaEventCreate(&e));
+    auto done = [&](int rc) { for (cudaEvent_t e : ev) cudaEventDestroy(e); return rc; };
+    auto scan = [&](u64* a, u32 n) { CG_LAUNCH(k_scan, 1, 1024, 1024 * sizeof(u64), st, a, (u64*)nullptr, (u64*)nullptr, (u64*)nullptr, (u64*)nullptr, n); };
+    // ---- lines
+    CK(cudaEventRecord(ev[0], st));
+    if (NN) CG_LAUNCH(k_names_build, (NN + 255) / 256, 256, 0, st, A);
+    if (n_tiles) CG_LAUNCH(k_paf_count, n_tiles, 256, 256, st, A);
+    scan(A.tile_cnt, n_tiles);
+    CK(cudaEventRecord(ev[1], st));
+    u64 n_lines = 0;
+    CK(cudaMemcpyAsync(&n_lines, A.tile_cnt + n_tiles, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (n_lines >= (1ull << 31)) { h->err = "more than 2^31 PAF lines in one call"; return done(CG_ERR_CAPACITY); }
+    CK(h->in_nl.ensure((n_lines + 1) * 8)); CK(h->in_rec.ensure((n_lines + 1) * sizeof(CgPafRec))); CK(h->in_head.ensure((n_lines + 2) * 8));
+    CK(h->in_scratch.ensure((n_lines + 1) * 8));
+    A.nl_pos = h->in_nl.as<u64>(); A.n_lines = n_lines; A.rec = h->in_rec.as<CgPafRec>(); A.head = h->in_head.as<u64>(); A.sort_scratch = h->in_scratch.as<u64>();
+    // ---- records, pile boundaries
+    CK(cudaEventRecord(ev[2], st));
+    if (n_tiles) CG_LAUNCH(k_paf_lines, n_tiles, 256, 256, st, A);
+    CK(cudaEventRecord(ev[3], st));
+    if (n_lines) CG_LAUNCH(k_paf_parse, (u32)((n_lines + 7) / 8), 256, 0, st, A);
+    CK(cudaEventRecord(ev[4], st));
+    if (n_lines) CG_LAUNCH(k_paf_heads, (u32)((n_lines + 255) / 256), 256, 0, st, A);
+    scan(A.head, (u32)n_lines);
+    u64 n_piles64 = 0;
+    u32 ctl[2] = {0, 0};
+    CK(cudaMemcpyAsync(&n_piles64, A.head + n_lines, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ctl, A.ctl, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(ev[5], st));
+    CK(cudaStreamSynchronize(st));
+    if (ctl[0]) {
+        h->err = (ctl[0] & CG_IN_FLAG_COLUMNS) ? "PAF ingest: a line has fewer than 12 columns"
+               : (ctl[0] & CG_IN_FLAG_NUMBER) ? "PAF ingest: a numeric column is not a non-negative int (stoi throws in the reference)"
+               : "PAF ingest: a read name is not in the name table (the reference then works on an empty read)";
+        return done(CG_ERR_INVALID_ARG);
+    }
+    const u32 NP = (u32)n_piles64;
+    CK(h->in_pfirst.ensure(((size_t)NP + 1) * 4)); CK(h->in_plast.ensure(((size_t)NP + 1) * 4)); CK(h->in_keep.ensure(((size_t)NP + 2) * 8));
+    CK(h->in_pread.ensure(((size_t)NP + 1) * 4)); CK(h->in_pqlen.ensure(((size_t)NP + 1) * 4));
+    A.n_piles = NP; A.pile_first = h->in_pfirst.as<u32>(); A.pile_last = h->in_plast.as<u32>(); A.keep = h->in_keep.as<u64>();
+    A.pile_read = h->in_pread.as<u32>(); A.pile_qlen = h->in_pqlen.as<u32>();
+    CK(cudaEventRecord(ev[6], st));
+    if (n_lines) CG_LAUNCH(k_paf_piles, (u32)((n_lines + 255) / 256), 256, 0, st, A);
+    if (NP) CG_LAUNCH(k_paf_sizes, (NP + 255) / 256, 256, 0, st, A);
+    scan(A.keep, NP);
+    u64 n_keep = 0;
+    CK(cudaMemcpyAsync(&n_keep, A.keep + NP, 8, cudaMemcpyDeviceToHost, st));
+    u32 ctl3[3] = {0, 0, 0};
+    CK(cudaMemcpyAsync(ctl3, A.ctl, 12, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    ctl[1] = ctl3[1];
+    if (n_keep >= (1ull << 32)) { h->err = "too many overlaps"; return done(CG_ERR_CAPACITY); }
+    CK(h->in_ov.ensure((n_keep + 1) * sizeof(CgOverlapDev))); CK(h->in_res.ensure((n_keep + 1) * 4));
+    A.ov = h->in_ov.as<CgOverlapDev>(); A.res = h->in_res.as<u32>();
+    // ---- sort + cut: keys in shared memory when the longest pile fits (16 warps per SM up to 1 700 lines)
+    const u32 longest = ctl[1];
+    size_t smem = (size_t)longest * 8;
+    const size_t smem_max = h->smem_optin > 0 ? (size_t)h->smem_optin : 48 * 1024;
+    if (smem > smem_max) smem = smem_max;
+    if (smem < 1024) smem = 1024;
+    A.smem_cap = (u32)(smem / 8);
+    CK(cudaFuncSetAttribute(k_paf_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
+    if (NP) CG_LAUNCH(k_paf_select, std::min<u32>(NP, (u32)h->sms * 32), 32, smem, st, A);
+    CK(cudaEventRecord(ev[7], st));
+    CK(cudaGetLastError());
+    // ---- host copy
+    HostPileSet* ps = new HostPileSet();
+    ps->pile_read.resize((size_t)NP + 1); ps->pile_qlen.resize((size_t)NP + 1); ps->ovb.resize((size_t)NP + 1);
+    ps->res.resize(n_keep + 1); ps->ov.resize(n_keep + 1);
+    std::vector<u64> ovb64((size_t)NP + 1, 0);
+    cudaError_t e = cudaSuccess;
+    if (NP) {
+        e = cudaMemcpyAsync(ps->pile_read.data(), A.pile_read, (size_t)NP * 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(ps->pile_qlen.data(), A.pile_qlen, (size_t)NP * 4, cudaMemcpyDeviceToHost, st);
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ovb64.data(), A.keep, ((size_t)NP + 1) * 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && n_keep) e = cudaMemcpyAsync(ps->ov.data(), A.ov, n_keep * sizeof(cg_overlap), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && n_keep) e = cudaMemcpyAsync(ps->res.data(), A.res, n_keep * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { delete ps; h->err = std::string("PAF ingest: ") + cudaGetErrorString(e); return done(CG_ERR_CUDA); }
+    for (u32 p = 0; p <= NP; ++p) ps->ovb[p] = (u32)ovb64[p];
+    float m[4] = {0, 0, 0, 0}, mp = 0;
+    cudaEventElapsedTime(&m[0], ev[0], ev[1]); cudaEventElapsedTime(&m[1], ev[2], ev[5]); cudaEventElapsedTime(&m[2], ev[6], ev[7]);
+    cudaEventElapsedTime(&mp, ev[3], ev[4]);
+    h->in_ms = m[0] + m[1] + m[2]; h->in_parse_ms = mp; h->in_bytes = nbytes;
+    out->n_piles = NP; out->pile_read = ps->pile_read.data(); out->pile_qlen = ps->pile_qlen.data(); out->pile_ov_begin = ps->ovb.data();
+    out->overlaps = ps->ov.data(); out->res_matches = ps->res.data(); out->owner_ = ps;
+    out->n_lines = ctl3[2];
+    return done(CG_OK);
+}
+
+void cg_free_pile_set(cg_pile_set* s) {
+    if (!s || !s->owner_) return;
+    delete static_cast<HostPileSet*>(s->owner_);
+    s->owner_ = nullptr;
+}
+
+int cg_ingest_stats(const cg_handle* h, float* kernel_ms, float* parse_ms, uint64_t* paf_bytes) {
+    if (!h) return CG_ERR_INVALID_ARG;
+    if (kernel_ms) *kernel_ms = h->in_ms;
+    if (parse_ms) *parse_ms = h->in_parse_ms;
+    if (paf_bytes) *paf_bytes = h->in_bytes;
     return CG_OK;
 }
 

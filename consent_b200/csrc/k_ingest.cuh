@@ -1,0 +1,298 @@
+// k_ingest.cuh — PAF ingest on the device.
+//
+// Every getNextReadPile (src/alignmentPiles.cpp:22-58) of one PAF text at once:
+//   k_paf_count / k_paf_lines   where the lines are (newline positions; 16 bytes per thread, the text is read twice)
+//   k_names_build               read names -> store index: open-addressing table keyed by a 64-bit FNV-1a hash, verified by
+//                               byte compare; a name listed twice resolves to its last entry (`index[header] =`, src/utils.cpp:186)
+//   k_paf_parse                 Overlap(line) (src/Overlap.h:26-60): one warp per line, tabs found by ballot, one lane per column
+//   k_paf_heads / k_paf_piles   consecutive lines with the same qName form a pile; an empty line ends one (:29-37)
+//   k_paf_select                std::sort(rbegin, rend) by resMatches + the cut to maxSupport (:39-42).  std::sort is not stable and
+//                               the reference is a libstdc++ program: the order of overlaps with equal resMatches — hence which of
+//                               them survive the cut and in which order they enter a window's pile — is whatever that library's
+//                               introsort leaves.  Lane 0 of the pile's warp replays that algorithm move for move on the pile's keys
+//                               in shared memory (bits/stl_algo.h: __introsort_loop, threshold 16, depth limit 2·floor(log2 n),
+//                               __move_median_to_first, __unguarded_partition, heapsort via __partial_sort, __final_insertion_sort);
+//                               the other lanes load the keys and write the kept overlaps out.
+// Everything here is byte / integer work bound by HBM bandwidth (the text) or by latency (the per-pile replay).
+#pragma once
+#include "cg_common.cuh"
+#include "k_extract.cuh"      // CgOverlapDev
+
+enum { CG_IN_FLAG_COLUMNS = 1u, CG_IN_FLAG_NUMBER = 2u, CG_IN_FLAG_NAME = 4u };
+#define CG_IN_TILE 4096u      // bytes of text per CTA of k_paf_count / k_paf_lines: 256 threads x 16 bytes
+
+struct CgPafRec { u32 q, qlen, res; CgOverlapDev o; };            // 10 x u32; q == CG_NONE32: an empty line
+
+struct CgIngestArgs {
+    const char* text; u64 nbytes;                                   // padded with zeros to a multiple of CG_IN_TILE
+    u64* tile_cnt; u32 n_tiles;                                     // newlines per tile -> exclusive scan
+    u64* nl_pos; u64 n_lines;                                       // position of the i-th newline
+    const char* names; const u64* name_off; u32 n_names; u32* slots; u32 slot_mask;
+    CgPafRec* rec;                                                  // [n_lines]
+    u64* head;                                                      // [n_lines + 1] first line of a pile -> exclusive scan = pile index
+    u32 n_piles; u32* pile_first; u32* pile_last;
+    u64* keep;                                                      // [n_piles + 1] overlaps kept -> exclusive scan = pile_ov_begin
+    u32 max_support;
+    u64* sort_scratch; u32 smem_cap;                                // piles over smem_cap lines sort in sort_scratch[first ..]
+    u32* pile_read; u32* pile_qlen; CgOverlapDev* ov; u32* res;
+    u32* ctl;                                                       // [0] flags, [1] longest pile, [2] non-empty lines
+};
+
+// 0x80 in every byte of w that equals '\n' (exact: no borrow between bytes)
+__device__ __forceinline__ u32 cg_in_nl_mask(u32 w) {
+    const u32 x = w ^ 0x0a0a0a0au;
+    return ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x | 0x7f7f7f7fu);
+}
+
+__global__ void __launch_bounds__(256) k_paf_count(CgIngestArgs A) {
+    CG_DYN_SMEM(smem);
+    u32* scratch = (u32*)smem;
+    const u64 at = (u64)blockIdx.x * CG_IN_TILE + (u64)threadIdx.x * 16u;
+    const uint4 v = *(const uint4*)(A.text + at);
+    const u32 n = (u32)(__popc(cg_in_nl_mask(v.x)) + __popc(cg_in_nl_mask(v.y)) + __popc(cg_in_nl_mask(v.z)) + __popc(cg_in_nl_mask(v.w)));
+    u32 total;
+    cg_block_scan(n, scratch, &total);
+    if (threadIdx.x == 0) A.tile_cnt[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(256) k_paf_lines(CgIngestArgs A) {
+    CG_DYN_SMEM(smem);
+    u32* scratch = (u32*)smem;
+    const u64 at = (u64)blockIdx.x * CG_IN_TILE + (u64)threadIdx.x * 16u;
+    const uint4 v = *(const uint4*)(A.text + at);
+    const u32 m[4] = {cg_in_nl_mask(v.x), cg_in_nl_mask(v.y), cg_in_nl_mask(v.z), cg_in_nl_mask(v.w)};
+    const u32 n = (u32)(__popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]));
+    u32 total;
+    u64 rank = A.tile_cnt[blockIdx.x] + cg_block_scan(n, scratch, &total);
+#pragma unroll
+    for (u32 j = 0; j < 4; ++j) {
+        u32 x = m[j];
+        while (x) {
+            const u32 bit = (u32)__ffs((int)x) - 1u;                 // bit 7 of byte b -> 8b + 7 (little endian: byte b at address +b)
+            A.nl_pos[rank++] = at + 4u * j + (bit >> 3);
+            x &= x - 1u;
+        }
+    }
+}
+
+__device__ __forceinline__ u64 cg_in_hash(const char* s, u32 n) {
+    u64 h = 1469598103934665603ull;
+    for (u32 i = 0; i < n; ++i) { h ^= (u8)s[i]; h *= 1099511628211ull; }
+    return h;
+}
+__device__ __forceinline__ bool cg_in_same(const char* a, const char* b, u32 n) {
+    for (u32 i = 0; i < n; ++i) if (a[i] != b[i]) return false;
+    return true;
+}
+
+// slots[] = store index + 1 (0 = free).  Two entries with the same name share a slot, which keeps the larger index.
+__global__ void k_names_build(CgIngestArgs A) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.n_names) return;
+    const char* s = A.names + A.name_off[i];
+    const u32 n = (u32)(A.name_off[i + 1] - A.name_off[i]);
+    u32 slot = (u32)cg_in_hash(s, n) & A.slot_mask;
+    for (;;) {
+        const u32 old = atomicCAS(&A.slots[slot], 0u, i + 1u);
+        if (old == 0u) return;
+        const u32 j = old - 1u;
+        if ((u32)(A.name_off[j + 1] - A.name_off[j]) == n && cg_in_same(A.names + A.name_off[j], s, n)) { atomicMax(&A.slots[slot], i + 1u); return; }
+        slot = (slot + 1u) & A.slot_mask;
+    }
+}
+
+__device__ __forceinline__ u32 cg_in_lookup(const CgIngestArgs& A, const char* s, u32 n) {
+    u32 slot = (u32)cg_in_hash(s, n) & A.slot_mask;
+    for (;;) {
+        const u32 v = A.slots[slot];
+        if (v == 0u) return CG_NONE32;
+        const u32 j = v - 1u;
+        if ((u32)(A.name_off[j + 1] - A.name_off[j]) == n && cg_in_same(A.names + A.name_off[j], s, n)) return j;
+        slot = (slot + 1u) & A.slot_mask;
+    }
+}
+
+// One warp per line.  Columns (src/Overlap.h:30-58): 0 qName, 1 qLength, 2 qStart, 3 qEnd (+1), 4 strand, 5 tName, 6 tLength,
+// 7 tStart, 8 tEnd (+1), 9 resMatches, 10 alBlockLen, 11 mapQual; anything after the 12th column is ignored.  Numbers are what
+// stoi() takes from a PAF: digits first, whatever follows them ignored, at most INT_MAX.
+__global__ void __launch_bounds__(256) k_paf_parse(CgIngestArgs A) {
+    const u32 lane = threadIdx.x & 31u;
+    const u64 i = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= A.n_lines) return;
+    const u64 b = i ? A.nl_pos[i - 1] + 1u : 0u, e = A.nl_pos[i];
+    u32* out = (u32*)(A.rec + i);
+    if (e == b) { if (lane == 0) out[0] = CG_NONE32; return; }
+    u64 st = b, en = e;                                            // lane f: column f = [st, en)
+    u32 ntabs = 0;
+    for (u64 base = b; base < e && ntabs < 12u; base += 32u) {
+        const u64 p = base + lane;
+        u32 m = __ballot_sync(CG_FULL, p < e && A.text[p] == '\t');
+        while (m && ntabs < 12u) {
+            const u64 pos = base + ((u32)__ffs((int)m) - 1u);
+            if (lane == ntabs) en = pos;
+            if (lane == ntabs + 1u) st = pos + 1u;
+            ++ntabs;
+            m &= m - 1u;
+        }
+    }
+    if (ntabs < 11u) { if (lane == 0) { atomicOr(A.ctl, (u32)CG_IN_FLAG_COLUMNS); out[0] = CG_NONE32; } return; }
+    const char* s = A.text + st;
+    const u32 n = (u32)(en - st);
+    u32 v = 0, bad = 0;
+    if (lane == 0 || lane == 5) {
+        v = cg_in_lookup(A, s, n);
+        if (v == CG_NONE32) bad = CG_IN_FLAG_NAME;
+    } else if (lane == 4) {
+        v = (n == 1u && s[0] == '+') ? 0u : 1u;
+    } else if (lane < 12u) {
+        if (n == 0u || s[0] < '0' || s[0] > '9') bad = CG_IN_FLAG_NUMBER;
+        u64 x = 0;
+        for (u32 j = 0; j < n && s[j] >= '0' && s[j] <= '9'; ++j) { x = x * 10u + (u64)(s[j] - '0'); if (x > 0x7fffffffull) { bad = CG_IN_FLAG_NUMBER; break; } }
+        v = (u32)x;
+        if (lane == 3 || lane == 8) v -= 1u;                       // "Has to be -1" (Overlap.h:37,48); 0 wraps like the reference's unsigned
+    }
+    // CgPafRec slots: q, qlen, res, t_read, strand, q_start, q_end, t_start, t_end, t_length
+    const u32 slot = lane == 0 ? 0u : lane == 1 ? 1u : lane == 9 ? 2u : lane == 5 ? 3u : lane == 4 ? 4u : lane == 2 ? 5u : lane == 3 ? 6u
+                   : lane == 7 ? 7u : lane == 8 ? 8u : lane == 6 ? 9u : CG_NONE32;
+    const u32 anybad = __ballot_sync(CG_FULL, bad != 0u);
+    if (anybad) {
+        if (bad) atomicOr(A.ctl, bad);
+        if (lane == 0) out[0] = CG_NONE32;
+        return;
+    }
+    if (slot != CG_NONE32) out[slot] = v;
+}
+
+__global__ void k_paf_heads(CgIngestArgs A) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.n_lines) return;
+    const u32 q = A.rec[i].q;
+    u32 hd = 0;
+    if (q != CG_NONE32) { hd = 1; if (i) { const u32 pq = A.rec[i - 1].q; if (pq == q) hd = 0; } }
+    A.head[i] = hd;
+}
+
+// after the scan of head[]: first / last line of every pile
+__global__ void k_paf_piles(CgIngestArgs A) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.n_lines) return;
+    if (A.rec[i].q == CG_NONE32) return;
+    const bool is_head = A.head[i + 1] != A.head[i];
+    const u32 pid = (u32)(is_head ? A.head[i] : A.head[i] - 1u);
+    if (is_head) A.pile_first[pid] = (u32)i;
+    const bool is_last = i + 1 == A.n_lines || A.rec[i + 1].q == CG_NONE32 || A.head[i + 2] != A.head[i + 1];
+    if (is_last) A.pile_last[pid] = (u32)i;
+}
+
+__global__ void k_paf_sizes(CgIngestArgs A) {
+    const u32 p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= A.n_piles) return;
+    const u32 n = A.pile_last[p] - A.pile_first[p] + 1u;
+    A.keep[p] = n < A.max_support ? n : A.max_support;
+    atomicMax(A.ctl + 1, n);
+    atomicAdd(A.ctl + 2, n);                                        // non-empty lines
+}
+
+// ---- libstdc++'s std::sort on a[0..n), elements = key << 32 | payload, compared by key only --------------------------------
+#define CG_IN_LT(x, y) ((u32)((x) >> 32) < (u32)((y) >> 32))
+template <class P> __device__ __forceinline__ void cg_in_swap(P a, u32 i, u32 j) { const u64 t = a[i]; a[i] = a[j]; a[j] = t; }
+
+template <class P> __device__ void cg_in_adjust_heap(P a, u32 first, i32 hole, i32 len, u64 value) {
+    const i32 top = hole;
+    i32 child = hole;
+    while (child < (len - 1) / 2) {
+        child = 2 * (child + 1);
+        if (CG_IN_LT(a[first + child], a[first + child - 1])) child--;
+        a[first + hole] = a[first + child];
+        hole = child;
+    }
+    if ((len & 1) == 0 && child == (len - 2) / 2) {
+        child = 2 * (child + 1);
+        a[first + hole] = a[first + child - 1];
+        hole = child - 1;
+    }
+    i32 parent = (hole - 1) / 2;                                   // __push_heap
+    while (hole > top && CG_IN_LT(a[first + parent], value)) { a[first + hole] = a[first + parent]; hole = parent; parent = (hole - 1) / 2; }
+    a[first + hole] = value;
+}
+template <class P> __device__ void cg_in_heap_sort(P a, u32 first, i32 len) {
+    if (len >= 2) {
+        i32 parent = (len - 2) / 2;
+        for (;;) { const u64 v = a[first + parent]; cg_in_adjust_heap(a, first, parent, len, v); if (parent == 0) break; parent--; }
+    }
+    while (len > 1) { --len; const u64 v = a[first + len]; a[first + len] = a[first]; cg_in_adjust_heap(a, first, 0, len, v); }
+}
+template <class P> __device__ __forceinline__ void cg_in_linear_insert(P a, u32 last) {
+    const u64 v = a[last];
+    u32 next = last - 1u;
+    while (CG_IN_LT(v, a[next])) { a[last] = a[next]; last = next; --next; }
+    a[last] = v;
+}
+template <class P> __device__ void cg_in_insertion_sort(P a, u32 first, u32 last) {
+    if (first == last) return;
+    for (u32 i = first + 1u; i != last; ++i) {
+        if (CG_IN_LT(a[i], a[first])) { const u64 v = a[i]; for (u32 j = i; j > first; --j) a[j] = a[j - 1u]; a[first] = v; }
+        else cg_in_linear_insert(a, i);
+    }
+}
+template <class P> __device__ void cg_in_std_sort(P a, u32 n) {
+    if (n == 0u) return;
+    u32 sf[68], sl[68]; i32 sd[68];                                // the recursion of __introsort_loop: right part first
+    i32 sp = 0;
+    sf[0] = 0; sl[0] = n; sd[0] = 2 * (31 - __clz((int)n));
+    ++sp;
+    while (sp > 0) {
+        --sp;
+        u32 first = sf[sp], last = sl[sp];
+        i32 depth = sd[sp];
+        while (last - first > 16u) {
+            if (depth == 0) { cg_in_heap_sort(a, first, (i32)(last - first)); break; }
+            --depth;
+            const u32 mid = first + (last - first) / 2u, x = first + 1u, c = last - 1u;
+            if (CG_IN_LT(a[x], a[mid])) {                          // __move_median_to_first(first, first + 1, mid, last - 1)
+                if (CG_IN_LT(a[mid], a[c])) cg_in_swap(a, first, mid); else if (CG_IN_LT(a[x], a[c])) cg_in_swap(a, first, c); else cg_in_swap(a, first, x);
+            } else if (CG_IN_LT(a[x], a[c])) cg_in_swap(a, first, x);
+            else if (CG_IN_LT(a[mid], a[c])) cg_in_swap(a, first, c);
+            else cg_in_swap(a, first, mid);
+            u32 lo = first + 1u, hi = last;                         // __unguarded_partition(first + 1, last, first)
+            const u64 pivot = a[first];
+            for (;;) {
+                while (CG_IN_LT(a[lo], pivot)) ++lo;
+                --hi;
+                while (CG_IN_LT(pivot, a[hi])) --hi;
+                if (!(lo < hi)) break;
+                cg_in_swap(a, lo, hi);
+                ++lo;
+            }
+            sf[sp] = first; sl[sp] = lo; sd[sp] = depth; ++sp;      // the caller continues with [first, cut) ...
+            first = lo;                                             // ... after the call on [cut, last)
+        }
+    }
+    if (n > 16u) {
+        cg_in_insertion_sort(a, 0u, 16u);
+        for (u32 i = 16u; i != n; ++i) cg_in_linear_insert(a, i);
+    } else cg_in_insertion_sort(a, 0u, n);
+}
+
+// One warp (= one CTA) per pile.
+__global__ void __launch_bounds__(32) k_paf_select(CgIngestArgs A) {
+    CG_DYN_SMEM(smem);
+    const u32 lane = threadIdx.x;
+    for (u32 p = blockIdx.x; p < A.n_piles; p += gridDim.x) {
+        const u32 first = A.pile_first[p], n = A.pile_last[p] - first + 1u;
+        u64* a = n <= A.smem_cap ? (u64*)smem : A.sort_scratch + first;
+        for (u32 j = lane; j < n; j += 32u) a[j] = ((u64)A.rec[first + (n - 1u - j)].res << 32) | (n - 1u - j);   // the reversed range
+        __syncwarp();
+        if (lane == 0) cg_in_std_sort(a, n);
+        __syncwarp();
+        const u64 o0 = A.keep[p];
+        const u32 keep = (u32)(A.keep[p + 1] - o0);
+        for (u32 j = lane; j < keep; j += 32u) {
+            const CgPafRec r = A.rec[first + (u32)a[n - 1u - j]];
+            A.ov[o0 + j] = r.o;
+            A.res[o0 + j] = r.res;
+            if (j == 0) { A.pile_read[p] = r.q; A.pile_qlen[p] = r.qlen; }      // alignments.begin()
+        }
+        __syncwarp();
+    }
+}

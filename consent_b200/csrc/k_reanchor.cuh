@@ -450,10 +450,64 @@ __global__ void __launch_bounds__(CG_RA_WARPS * 32) k_reanchor(CgReanchorArgs P)
     }
 }
 
-// corrected reads, dense: out[out_off[r] ..) <- head slice of read r
-__global__ void k_reanchor_gather(const char* head, const u64* head_off, const u64* out_off, char* out, u32 n_reads) {
+// Post-filters: the tail of processRead (src/CONSENT-correction.cpp:49-59) on the re-anchored read in place.
+//   trimRead(read, m)  src/utils.cpp:96-128   beg = start of the first run of m upper-case bases, end = last base of the last such
+//                                             run; "" unless end > beg
+//   dropRead(read)     src/utils.cpp:60-73    (float) upper-case bases / length < 0.1
+// One CTA per read: len[r] becomes the length of the FASTA sequence line (0 = no record), skip[r] its first base.
+// A read without any such run yields "" (the reference's descending `unsigned i >= 0` loop leaves the string there).
+__global__ void __launch_bounds__(256) k_finish_reads(const char* head, const u64* head_off, u32* len, u32* skip, u32 n_reads, u32 m) {
+    CG_DYN_SMEM(smem);
+    u32* red = (u32*)smem;                                         // [0..8) minima, [8..16) maxima, [16..24) counts, [24..27) results
+    const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     for (u32 r = blockIdx.x; r < n_reads; r += gridDim.x) {
         const char* s = head + head_off[r];
+        const u32 n = len[r];
+        u32 lo = CG_NONE32, hi = 0;                                 // hi = last base of a run + 1 (0: none)
+        for (u32 i = threadIdx.x; i + m <= n; i += blockDim.x) {
+            bool run = true;
+            for (u32 j = 0; j < m; ++j) { const char c = s[i + j]; run = run && c >= 'A' && c <= 'Z'; }
+            if (run) { lo = lo < i ? lo : i; hi = i + m; }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const u32 a = __shfl_xor_sync(CG_FULL, lo, d), b = __shfl_xor_sync(CG_FULL, hi, d);
+            lo = a < lo ? a : lo; hi = b > hi ? b : hi;
+        }
+        if (lane == 0) { red[warp] = lo; red[8 + warp] = hi; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            u32 a = CG_NONE32, b = 0;
+            for (u32 w = 0; w < nw; ++w) { a = red[w] < a ? red[w] : a; b = red[8 + w] > b ? red[8 + w] : b; }
+            red[24] = a; red[25] = b;
+        }
+        __syncthreads();
+        const u32 beg = red[24], endp1 = red[25];
+        u32 cnt = 0;
+        if (beg != CG_NONE32)
+            for (u32 i = beg + threadIdx.x; i < endp1; i += blockDim.x) { const char c = s[i]; cnt += (c >= 'A' && c <= 'Z') ? 1u : 0u; }
+        cnt = cg_warp_sum(cnt);
+        if (lane == 0) red[16 + warp] = cnt;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            u32 out_len = 0, out_skip = 0;
+            if (beg != CG_NONE32 && endp1 - 1u > beg) {            // end > beg (utils.cpp:123)
+                u32 c = 0;
+                for (u32 w = 0; w < nw; ++w) c += red[16 + w];
+                const u32 L = endp1 - beg;
+                const float frac = (float)(int)c / (float)(size_t)L;
+                if (!((double)frac < 0.1)) { out_len = L; out_skip = beg; }
+            }
+            len[r] = out_len; skip[r] = out_skip;
+        }
+        __syncthreads();
+    }
+}
+
+// corrected reads, dense: out[out_off[r] ..) <- head slice of read r (from base skip[r] on when the post-filters ran)
+__global__ void k_reanchor_gather(const char* head, const u64* head_off, const u32* skip, const u64* out_off, char* out, u32 n_reads) {
+    for (u32 r = blockIdx.x; r < n_reads; r += gridDim.x) {
+        const char* s = head + head_off[r] + (skip ? skip[r] : 0u);
         char* d = out + out_off[r];
         const u64 n = out_off[r + 1] - out_off[r];
         for (u64 i = threadIdx.x; i < n; i += blockDim.x) d[i] = s[i];

@@ -14,16 +14,17 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-from ._ffi import (Batch, CG_N_STAGES, Corrected, PKG_DIR, Params, Piles, Reads, Results, STAGE_NAMES, STATUS_NAMES, cg_batch,
-                   cg_corrected, cg_counters, cg_params, cg_piles, cg_reads, cg_results, cg_window_set, load_library,
-                   results_to_c, window_set_to_py)
+from ._ffi import (Batch, CG_N_STAGES, Corrected, PKG_DIR, Params, Piles, PileSet, ReadNames, Reads, Results, STAGE_NAMES,
+                   STATUS_NAMES, cg_batch, cg_corrected, cg_counters, cg_params, cg_pile_set, cg_piles, cg_read_names, cg_reads,
+                   cg_results, cg_window_set, load_library, results_to_c, window_set_to_py)
 
 LIB_PATH = os.path.join(PKG_DIR, "libconsent_b200.so")
 
 EXPORTS = ("cg_abi_version", "cg_device_count", "cg_create", "cg_destroy", "cg_last_error", "cg_set_option",
            "cg_correct_windows", "cg_free_results", "cg_upload", "cg_run", "cg_download", "cg_stage_ms",
            "cg_get_counters", "cg_run_ms", "cg_chunk_count", "cg_reanchor_reads", "cg_free_corrected", "cg_reanchor_stats",
-           "cg_upload_piles", "cg_download_windows", "cg_free_window_set", "cg_extract_stats")
+           "cg_upload_piles", "cg_download_windows", "cg_free_window_set", "cg_extract_stats",
+           "cg_ingest_paf", "cg_free_pile_set", "cg_ingest_stats", "cg_finish_reads", "cg_finish_stats")
 
 
 class ConsentError(RuntimeError):
@@ -74,6 +75,15 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.cg_free_window_set.argtypes = [C.POINTER(cg_window_set)]
     lib.cg_extract_stats.restype = C.c_int
     lib.cg_extract_stats.argtypes = [H, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_uint64)]
+    lib.cg_ingest_paf.restype = C.c_int
+    lib.cg_ingest_paf.argtypes = [H, C.c_char_p, C.c_uint64, C.POINTER(cg_read_names), C.c_uint32, C.POINTER(cg_pile_set)]
+    lib.cg_free_pile_set.argtypes = [C.POINTER(cg_pile_set)]
+    lib.cg_ingest_stats.restype = C.c_int
+    lib.cg_ingest_stats.argtypes = [H, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_uint64)]
+    lib.cg_finish_stats.restype = C.c_int
+    lib.cg_finish_stats.argtypes = [H, C.POINTER(C.c_float)]
+    lib.cg_finish_reads.restype = C.c_int
+    lib.cg_finish_reads.argtypes = [H, C.POINTER(cg_batch), C.POINTER(cg_results), C.POINTER(cg_reads), C.c_uint32, C.POINTER(cg_corrected)]
     return lib
 
 
@@ -136,6 +146,38 @@ class Corrector:
         got = Corrected(out)
         self.lib.cg_free_corrected(C.byref(out))
         return got
+
+    def finish_reads(self, batch: Batch, results: Results, reads: Reads, trim_mer: int = 1) -> Corrected:
+        """reanchor_reads followed on the device by the tail of processRead (reference src/CONSENT-correction.cpp:49-59):
+        trimRead(read, trim_mer) and dropRead — the sequence line of every FASTA record (empty = no record).  trim_mer = 0
+        is the proof-file mode (no trimming, nothing dropped)."""
+        cb, rd, out = batch.c(), reads.c(), cg_corrected()
+        live = getattr(results, "_r", None)
+        cr = live if live is not None else results_to_c(results)
+        self._check(self.lib.cg_finish_reads(self._h, C.byref(cb), C.byref(cr), C.byref(rd), int(trim_mer), C.byref(out)))
+        got = Corrected(out)
+        self.lib.cg_free_corrected(C.byref(out))
+        return got
+
+    def finish_stats(self) -> dict:
+        ms = C.c_float(0)
+        self._check(self.lib.cg_finish_stats(self._h, C.byref(ms)))
+        return {"kernel_ms": float(ms.value)}
+
+    # -- PAF ingest: every getNextReadPile (reference src/alignmentPiles.cpp:22-58) of a PAF text on the device -------------
+    def ingest_paf(self, text: bytes, names: ReadNames, max_support: int = 150) -> PileSet:
+        """PAF text in, read piles out: lines parsed (src/Overlap.h:26-60), consecutive lines of one query grouped, every pile
+        ordered as std::sort(rbegin, rend) by resMatches leaves it and cut to max_support."""
+        cn, out = names.c(), cg_pile_set()
+        self._check(self.lib.cg_ingest_paf(self._h, text, len(text), C.byref(cn), int(max_support), C.byref(out)))
+        got = PileSet(out)
+        self.lib.cg_free_pile_set(C.byref(out))
+        return got
+
+    def ingest_stats(self) -> dict:
+        ms, pms, nb = C.c_float(0), C.c_float(0), C.c_uint64(0)
+        self._check(self.lib.cg_ingest_stats(self._h, C.byref(ms), C.byref(pms), C.byref(nb)))
+        return {"kernel_ms": float(ms.value), "parse_ms": float(pms.value), "paf_bytes": int(nb.value)}
 
     def reanchor_stats(self) -> dict:
         ms, cells = C.c_float(0), C.c_uint64(0)

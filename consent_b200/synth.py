@@ -107,3 +107,31 @@ def synth_piles(n_reads: int, *, genome_len: int = 200_000, read_len: int = 4000
     lib.cg_synth_piles_fetch(h, store_off.ctypes.data_as(u64), C.cast(store.ctypes.data, C.c_char_p), pile_read.ctypes.data_as(u32),
                              pile_qlen.ctypes.data_as(u32), pile_ov_begin.ctypes.data_as(u32), ov.ctypes.data_as(u32))
     return Piles(store_off, store, pile_read[:P], pile_qlen[:P], pile_ov_begin, ov[:no.value], min_support, window_size, window_overlap)
+
+
+def synth_paf(piles: Piles, *, seed: int = 1, tie_range: int = 40, blank_every: int = 0, extra_columns: bool = True):
+    """A PAF text (bytes) + the read names for `piles` (a pile's overlaps in their given order): what minimap2 would have
+    written for these overlaps.  resMatches (column 10) is drawn from `tie_range` values per pile so that the cut to maxSupport
+    has ties to break; blank_every > 0 inserts an empty line before every blank_every-th pile (a pile separator for
+    getNextReadPile, reference src/alignmentPiles.cpp:29-37).  -> (text, ReadNames)"""
+    from ._ffi import ReadNames
+    rng = np.random.default_rng(seed)
+    names = [f"read_{i}/{(i * 7919) % 1000}" for i in range(piles.n_store)]
+    out = []
+    ovb = piles.pile_ov_begin
+    for p in range(piles.n_piles):
+        a, b = int(ovb[p]), int(ovb[p + 1])
+        if blank_every and p and p % blank_every == 0:
+            out.append("")
+        q, qlen = names[int(piles.pile_read[p])], int(piles.pile_qlen[p])
+        base = int(rng.integers(100, 3000))
+        res = base + rng.integers(0, max(tie_range, 1), size=b - a)
+        for i in range(a, b):
+            t, st, qs, qe, ts, te, tl = (int(x) for x in piles.overlaps[i])
+            r = int(res[i - a])
+            line = f"{q}\t{qlen}\t{qs}\t{qe + 1}\t{'-' if st else '+'}\t{names[t]}\t{tl}\t{ts}\t{te + 1}\t{r}\t{r + 57}\t255"
+            if extra_columns and (i & 1):
+                line += "\ttp:A:S\tcm:i:73\ts1:i:512\tdv:f:0.1201"
+            out.append(line)
+    text = ("\n".join(out) + "\n").encode() if out else b""
+    return text, ReadNames(names)

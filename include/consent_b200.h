@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define CG_ABI_VERSION 3
+#define CG_ABI_VERSION 4
 
 typedef enum cg_status {
     CG_OK                 =  0,
@@ -230,6 +230,65 @@ void cg_free_window_set(cg_window_set* s);
 /* CUDA-event time (ms) of the extraction kernels of the last cg_upload_piles (host round trips for the window counts
  * excluded), of the copy kernel alone (k_ex_copy: reads and writes one byte per pile base), and the pile bytes written. */
 int  cg_extract_stats(const cg_handle* h, float* kernel_ms, float* copy_ms, uint64_t* pile_bytes);
+
+/* PAF ingest --------------------------------------------------
+ * The serial front of runCorrection (src/CONSENT-correction.cpp:87,107) on the device: every
+ *
+ *   std::vector<Overlap> getNextReadPile(std::ifstream& f, unsigned maxSupport)   (src/alignmentPiles.cpp:22-58)
+ *
+ * of one PAF text at once — Overlap(line) (src/Overlap.h:26-60: 12 tab-separated columns, qEnd / tEnd = column - 1,
+ * strand = column 5 != "+"), grouping of consecutive lines with the same qName into a pile (an empty line also ends a
+ * pile, :29-37), `std::sort(rbegin, rend)` by resMatches (column 10, Overlap.h:90-96) and the cut to maxSupport (:39-42).
+ * std::sort is not stable: the order of overlaps with equal resMatches is the one libstdc++'s introsort (median-of-3
+ * quicksort above 16 elements, heapsort below depth 2·log2 n, final insertion sort; bits/stl_algo.h) leaves on the
+ * reversed range, and the kernel replays exactly that sequence of comparisons and moves per pile — which overlaps survive
+ * the cut, and in which order they enter a window's pile, decides bytes downstream.
+ * Read names (PAF columns 1 and 6) become store indices through `names` (the FASTA headers up to the first blank, as
+ * indexReads keeps them: src/utils.cpp:163-190; a name listed twice resolves to its last entry, like `index[header] =`).
+ * A line with fewer than 12 columns, a numeric column stoi() would not take as a non-negative int, or a name that is
+ * not in the table is an error (the reference throws or reads an empty sequence there). */
+typedef struct cg_read_names {
+    uint32_t        n_reads;
+    const uint64_t* name_off;        /* [n_reads + 1] byte offsets into names                          */
+    const char*     names;           /* concatenated, no terminators                                   */
+} cg_read_names;
+
+/* Piles as cg_piles takes them (pile_* / overlaps fields), owned by the library until cg_free_pile_set(). */
+typedef struct cg_pile_set {
+    uint32_t    n_piles;
+    uint32_t*   pile_read;           /* [n_piles] qName of the pile                                    */
+    uint32_t*   pile_qlen;           /* [n_piles] alignments.begin()->qLength (after the sort)         */
+    uint32_t*   pile_ov_begin;       /* [n_piles + 1]                                                  */
+    cg_overlap* overlaps;            /* in the order getNextReadPile returns them                      */
+    uint32_t*   res_matches;         /* [pile_ov_begin[n_piles]] column 10 of every kept overlap       */
+    uint64_t    n_lines;             /* non-empty PAF lines parsed                                     */
+    void*       owner_;
+} cg_pile_set;
+
+/* Host text in, host piles out (H2D, kernels, D2H inside).  Blocking; one call at a time per handle. */
+int  cg_ingest_paf(cg_handle* h, const char* paf, uint64_t paf_bytes, const cg_read_names* names,
+                   uint32_t max_support, cg_pile_set* out);
+void cg_free_pile_set(cg_pile_set* s);
+/* CUDA-event time (ms) of all kernels of the last cg_ingest_paf, of the line parser alone (k_paf_parse: reads every
+ * byte of the text once), and the bytes of text. */
+int  cg_ingest_stats(const cg_handle* h, float* kernel_ms, float* parse_ms, uint64_t* paf_bytes);
+
+/* Post-filters -------------------------------------------------
+ * cg_reanchor_reads followed, still on the device, by the tail of processRead (src/CONSENT-correction.cpp:49-59):
+ *
+ *   correctedRead = trimRead(correctedRead, 1);          (src/utils.cpp:96-128: cut to the first / last run of
+ *                                                          `trim_mer` upper-case bases; "" unless end > beg)
+ *   if (dropRead(correctedRead)) correctedRead = "";     (src/utils.cpp:71-73: fewer than 10 % upper-case bases,
+ *                                                          (float) n / length < 0.1)
+ *
+ * so that `out` holds exactly the sequence line of every FASTA record runCorrection prints (:100-103; an empty string =
+ * no record).  trim_mer = 0 skips both filters (the proof-file mode, doTrimRead = false, :76-79) and equals
+ * cg_reanchor_reads.  A read without any upper-case base makes trimRead index before its string (unsigned i >= 0,
+ * utils.cpp:111-120); it yields "" here. */
+int  cg_finish_reads(cg_handle* h, const cg_batch* windows, const cg_results* cons, const cg_reads* reads,
+                     uint32_t trim_mer, cg_corrected* out);
+/* CUDA-event time (ms) of the post-filter kernel of the last cg_finish_reads. */
+int  cg_finish_stats(const cg_handle* h, float* kernel_ms);
 
 /* Instrumentation -------------------------------------------------------- */
 #define CG_STAGE_PACK     0   /* ASCII -> 2-bit                                         */

@@ -31,6 +31,14 @@ uint64_t oracle_reanchor_cells(void);
 int   oracle_extract_windows(const cg_piles* p, unsigned merSize, cg_window_set* out);
 void  oracle_free_window_set(cg_window_set* s);
 
+/* PAF-ingest and post-filter oracle (oracle/ingest_oracle.c); same contracts as ref_ingest_paf / ref_sort_desc /
+ * ref_finish_reads of the reference harness. */
+int   oracle_ingest_paf(const char* paf, uint64_t nbytes, const cg_read_names* names, uint32_t max_support, cg_pile_set* out);
+void  oracle_free_pile_set(cg_pile_set* s);
+void  oracle_sort_desc(const uint32_t* keys, uint32_t n, uint32_t* order);
+int   oracle_finish_reads(const cg_corrected* in, uint32_t trim_mer, cg_corrected* out);
+void  oracle_free_finished(cg_corrected* c);
+
 #ifdef __cplusplus
 }
 #endif

@@ -17,6 +17,9 @@
 //    BMEAN/Complete-Striped-Smith-Waterman-Library/src/{ssw.c,ssw_cpp.cpp})
 //   getAlignmentWindowsPositions / getAlignmentWindowsSequences   src/alignmentWindows.cpp:27-149
 //   (window extraction)
+//   getNextReadPile                           src/alignmentPiles.cpp:22-58 (PAF ingest; with
+//   Overlap(line) and operator<, src/Overlap.h:26-96)
+//   trimRead / dropRead                       src/utils.cpp:71-73,96-128 (post-filters)
 //
 // Used by: tests/ (to pin oracle/consent_oracle.c and to generate
 // tests/golden/*), bench.py's cpu_baseline / --impl reference legs.
@@ -40,6 +43,9 @@
 #include "correctionDBG.h"       // src/correctionDBG.h
 #include "correctionAlignment.h" // src/correctionAlignment.h (alignConsensus)
 #include "alignmentWindows.h"    // src/alignmentWindows.h (window positions / piles; pulls in Overlap.h)
+#include "alignmentPiles.h"      // src/alignmentPiles.h (getNextReadPile)
+#include <fstream>
+#include <unistd.h>
 #include "consent_b200.h"        // our ABI structs (cg_batch, cg_results, cg_params)
 
 // ---- prototypes of the reference's stage functions (external linkage in
@@ -295,6 +301,92 @@ int ref_extract_windows(const cg_piles* p, unsigned merSize, cg_window_set* out)
 
 void ref_free_window_set(cg_window_set* s) {
     if (s && s->owner_) { delete static_cast<WindowSetOwner*>(s->owner_); s->owner_ = nullptr; }
+}
+
+// ---- PAF ingest: the reference's own getNextReadPile over the text, driven like runCorrection drives it --------------------
+// (src/CONSENT-correction.cpp:87-90,107-110: empty piles are skipped while the stream is not at its end).  The text goes through
+// a temporary file because getNextReadPile takes a std::ifstream and seeks in it.  Names become store indices the way
+// indexReads fills its map (`index[header] = ...`: the last entry of a name wins, src/utils.cpp:186).
+struct PileSetOwner { std::vector<uint32_t> pile_read, pile_qlen, ovb, res; std::vector<cg_overlap> ov; };
+
+int ref_ingest_paf(const char* paf, uint64_t nbytes, const cg_read_names* names, uint32_t max_support, cg_pile_set* out) {
+    if (!out || !names || (nbytes && !paf) || max_support == 0) return CG_ERR_INVALID_ARG;
+    if (nbytes && paf[nbytes - 1] != '\n') return CG_ERR_INVALID_ARG;             // getNextReadPile never returns on such a text
+    robin_hood::unordered_map<std::string, uint32_t> id;
+    for (uint32_t i = 0; i < names->n_reads; ++i) id[std::string(names->names + names->name_off[i], names->names + names->name_off[i + 1])] = i;
+    char path[] = "/tmp/consent_ref_paf_XXXXXX";
+    int fd = mkstemp(path);
+    if (fd < 0) return CG_ERR_INVALID_ARG;
+    for (uint64_t w = 0; w < nbytes;) { ssize_t k = write(fd, paf + w, nbytes - w); if (k <= 0) { close(fd); unlink(path); return CG_ERR_INVALID_ARG; } w += (uint64_t)k; }
+    close(fd);
+    PileSetOwner* ow = new PileSetOwner();
+    ow->ovb.push_back(0);
+    uint64_t lines = 0;
+    for (uint64_t i = 0; i + 1 <= nbytes; ++i) if (paf[i] == '\n' && i > 0 && paf[i - 1] != '\n') ++lines;
+    int rc = CG_OK;
+    try {
+        std::ifstream f(path);
+        while (!f.eof()) {
+            std::vector<Overlap> al = getNextReadPile(f, max_support);
+            if (al.size() == 0) continue;
+            auto q = id.find(al.begin()->qName);
+            if (q == id.end()) { rc = CG_ERR_INVALID_ARG; break; }
+            ow->pile_read.push_back(q->second);
+            ow->pile_qlen.push_back(al.begin()->qLength);
+            for (const Overlap& a : al) {
+                auto t = id.find(a.tName);
+                if (t == id.end()) { rc = CG_ERR_INVALID_ARG; break; }
+                cg_overlap o = {t->second, a.strand ? 1u : 0u, a.qStart, a.qEnd, a.tStart, a.tEnd, a.tLength};
+                ow->ov.push_back(o);
+                ow->res.push_back(a.resMatches);
+            }
+            ow->ovb.push_back((uint32_t)ow->ov.size());
+        }
+    } catch (...) { rc = CG_ERR_INVALID_ARG; }                                       // stoi on a malformed column
+    unlink(path);
+    if (rc != CG_OK) { delete ow; return rc; }
+    if (ow->pile_read.empty()) { ow->pile_read.push_back(0); ow->pile_qlen.push_back(0); }
+    if (ow->ov.empty()) { ow->ov.push_back(cg_overlap{}); ow->res.push_back(0); }
+    out->n_piles = (uint32_t)(ow->ovb.size() - 1);
+    out->pile_read = ow->pile_read.data(); out->pile_qlen = ow->pile_qlen.data(); out->pile_ov_begin = ow->ovb.data();
+    out->overlaps = ow->ov.data(); out->res_matches = ow->res.data(); out->n_lines = lines; out->owner_ = ow;
+    return CG_OK;
+}
+
+void ref_free_pile_set(cg_pile_set* s) {
+    if (s && s->owner_) { delete static_cast<PileSetOwner*>(s->owner_); s->owner_ = nullptr; }
+}
+
+// std::sort(v.rbegin(), v.rend()) on Overlap records, exactly the call of getNextReadPile (src/alignmentPiles.cpp:40,51):
+// order[i] = index of the record that ends up at position i.
+void ref_sort_desc(const uint32_t* keys, uint32_t n, uint32_t* order) {
+    std::vector<Overlap> v(n);
+    for (uint32_t i = 0; i < n; ++i) { v[i].resMatches = keys[i]; v[i].alBlockLen = i; }
+    std::sort(v.rbegin(), v.rend());
+    for (uint32_t i = 0; i < n; ++i) order[i] = v[i].alBlockLen;
+}
+
+// ---- post-filters: the tail of processRead (src/CONSENT-correction.cpp:49-59) on the strings alignConsensus returned ----------
+int ref_finish_reads(const cg_corrected* in, uint32_t trim_mer, cg_corrected* out) {
+    if (!in || !out) return CG_ERR_INVALID_ARG;
+    CorrectedOwner* ow = new CorrectedOwner();
+    ow->off.resize((size_t)in->n_reads + 1, 0);
+    for (uint32_t r = 0; r < in->n_reads; ++r) {
+        std::string s(in->bases + in->read_off[r], in->bases + in->read_off[r + 1]);
+        if (trim_mer && !s.empty()) {
+            unsigned run = 0, best = 0;
+            for (char c : s) { run = isUpperCase(c) ? run + 1 : 0; best = std::max(best, run); }
+            if (best < trim_mer) s.clear();                                          // trimRead would index s[-1] (utils.cpp:111-120)
+            else {
+                s = trimRead(s, trim_mer);
+                if (dropRead(s)) s.clear();
+            }
+        }
+        ow->bases += s;
+        ow->off[r + 1] = ow->bases.size();
+    }
+    out->n_reads = in->n_reads; out->read_off = ow->off.data(); out->bases = const_cast<char*>(ow->bases.data()); out->owner_ = ow;
+    return CG_OK;
 }
 
 // Per-stage text dump of one window, produced by calling the reference's own

@@ -5,9 +5,11 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-from consent_b200._ffi import (Batch, Corrected, Params, Piles, REPO_DIR, Reads, Results, cg_batch, cg_corrected,
-                               cg_counters, cg_params, cg_piles, cg_reads, cg_results, cg_window_set, results_to_c,
-                               window_set_to_py)
+import numpy as np
+
+from consent_b200._ffi import (Batch, Corrected, Params, Piles, PileSet, REPO_DIR, ReadNames, Reads, Results, cg_batch,
+                               cg_corrected, cg_counters, cg_params, cg_pile_set, cg_piles, cg_read_names, cg_reads, cg_results,
+                               cg_window_set, results_to_c, window_set_to_py)
 
 ORACLE_DIR = os.path.join(REPO_DIR, "oracle")
 
@@ -67,6 +69,50 @@ class _Checker:
         out = window_set_to_py(ws)
         free(C.byref(ws))
         return out
+
+    def ingest_paf(self, text: bytes, names: ReadNames, max_support: int = 150) -> PileSet:
+        """Every getNextReadPile of a PAF text -> PileSet"""
+        f = getattr(self.lib, self.prefix + "_ingest_paf")
+        f.restype = C.c_int
+        f.argtypes = [C.c_char_p, C.c_uint64, C.POINTER(cg_read_names), C.c_uint32, C.POINTER(cg_pile_set)]
+        free = getattr(self.lib, self.prefix + "_free_pile_set")
+        free.argtypes = [C.POINTER(cg_pile_set)]
+        cn, out = names.c(), cg_pile_set()
+        rc = f(text, len(text), C.byref(cn), int(max_support), C.byref(out))
+        if rc != 0:
+            raise RuntimeError(f"{self.prefix}_ingest_paf -> {rc}")
+        got = PileSet(out)
+        free(C.byref(out))
+        return got
+
+    def sort_desc(self, keys) -> np.ndarray:
+        """std::sort(rbegin, rend) on records compared by `keys` -> the resulting order (indices)"""
+        f = getattr(self.lib, self.prefix + "_sort_desc")
+        f.restype = None
+        f.argtypes = [C.POINTER(C.c_uint32), C.c_uint32, C.POINTER(C.c_uint32)]
+        k = np.ascontiguousarray(keys, np.uint32)
+        o = np.zeros(max(len(k), 1), np.uint32)
+        f(k.ctypes.data_as(C.POINTER(C.c_uint32)) if len(k) else o.ctypes.data_as(C.POINTER(C.c_uint32)), len(k),
+          o.ctypes.data_as(C.POINTER(C.c_uint32)))
+        return o[:len(k)]
+
+    def finish_reads(self, cor: Corrected, trim_mer: int = 1) -> Corrected:
+        """trimRead + dropRead on the strings alignConsensus returned"""
+        f = getattr(self.lib, self.prefix + "_finish_reads")
+        f.restype = C.c_int
+        f.argtypes = [C.POINTER(cg_corrected), C.c_uint32, C.POINTER(cg_corrected)]
+        free = getattr(self.lib, "ref_free_corrected" if self.prefix == "ref" else "oracle_free_finished")
+        free.argtypes = [C.POINTER(cg_corrected)]
+        off = np.ascontiguousarray(cor.read_off, np.uint64)
+        b = cor.bases if len(cor.bases) else np.zeros(1, np.uint8)
+        cin = cg_corrected(cor.n_reads, off.ctypes.data_as(C.POINTER(C.c_uint64)), C.cast(b.ctypes.data, C.POINTER(C.c_char)), None)
+        out = cg_corrected()
+        rc = f(C.byref(cin), int(trim_mer), C.byref(out))
+        if rc != 0:
+            raise RuntimeError(f"{self.prefix}_finish_reads -> {rc}")
+        got = Corrected(out)
+        free(C.byref(out))
+        return got
 
     def reanchor_reads(self, batch: Batch, res: Results, reads: Reads, params: Params = Params(), threads: int = 1):
         """alignConsensus for every read -> (Corrected, seconds of the compute loop)"""
