@@ -13,6 +13,9 @@
 //   phase B  per read, in PAF order: trimRead / dropRead and the FASTA record (:50-59, :100-103)
 // With -x phase A's window cutting moves to the device as well (cg_upload_piles): the host only reads the PAF
 // piles (getNextReadPile: parsing, sort, top-maxSupport) and ships the read store once.
+// With -X nothing of processRead / getNextReadPile is left on the host: the PAF text goes to the device as it is
+// (cg_ingest_paf: parsing, grouping, std::sort + top-maxSupport), and trimRead / dropRead run behind the re-anchoring
+// (cg_finish_reads); the host reads two files and prints FASTA records.
 // Same command line as bin/CONSENT-correction (src/main.cpp:27-80).  tests/test_dropin_example.py runs it on a B200 and
 // compares its FASTA byte for byte with the one the unmodified reference binary printed for the same PAF.
 #include <getopt.h>
@@ -22,6 +25,7 @@
 #include <cstdlib>
 #include <fstream>
 #include <iostream>
+#include <iterator>
 #include <string>
 #include <vector>
 
@@ -37,8 +41,8 @@ int main(int argc, char** argv) {
     unsigned minSupport = 3, maxSupport = 1000, windowSize = 500, merSize = 9, commonKMers = 8, minAnchors = 10,
              solidThresh = 4, windowOverlap = 50;                                       // src/main.cpp:15-24
     int opt, device = 0;
-    bool deviceExtraction = false;
-    while ((opt = getopt(argc, argv, "a:A:d:k:s:S:M:l:f:e:p:c:m:j:w:r:R:n:i:g:x")) != -1) {
+    bool deviceExtraction = false, deviceIngest = false;
+    while ((opt = getopt(argc, argv, "a:A:d:k:s:S:M:l:f:e:p:c:m:j:w:r:R:n:i:g:xX")) != -1) {
         switch (opt) {
             case 'a': alignmentFile = optarg; break;
             case 's': minSupport = atoi(optarg); break;
@@ -52,6 +56,7 @@ int main(int argc, char** argv) {
             case 'r': readsFile = optarg; break;
             case 'g': device = atoi(optarg); break;
             case 'x': deviceExtraction = true; break;
+            case 'X': deviceIngest = true; break;
             default: break;                                                             // -j -M -p ...: no meaning here
         }
     }
@@ -64,6 +69,39 @@ int main(int argc, char** argv) {
     cg_params prm = {merSize, solidThresh, commonKMers, minAnchors};
     cg_handle* h = nullptr;
     if (cg_create(device, &prm, &h) != CG_OK) die("cg_create", cg_last_error(nullptr));
+
+    if (deviceIngest) {
+        // ---- everything between the two input files and the FASTA records on the device
+        std::vector<std::string> names;
+        std::vector<uint64_t> nameOff(1, 0), storeOff(1, 0);
+        std::string nameBytes, store;
+        for (auto& kv : readIndex) {                                                   // any order: indices are internal
+            names.push_back(kv.first);
+            nameBytes += kv.first; nameOff.push_back(nameBytes.size());
+            store += fullnum2str(kv.second); storeOff.push_back(store.size());
+        }
+        std::string text((std::istreambuf_iterator<char>(alignments)), std::istreambuf_iterator<char>());
+        if (nameBytes.empty()) nameBytes.push_back('x');
+        if (store.empty()) store.push_back('A');
+        cg_read_names rn = {(uint32_t)names.size(), nameOff.data(), nameBytes.data()};
+        cg_pile_set ps; cg_results res; cg_window_set ws; cg_corrected cor;
+        if (cg_ingest_paf(h, text.data(), text.size(), &rn, maxSupport, &ps) != CG_OK) die("cg_ingest_paf", cg_last_error(h));
+        cg_piles piles = {(uint32_t)names.size(), storeOff.data(), store.data(), ps.n_piles, ps.pile_read, ps.pile_qlen, ps.pile_ov_begin, ps.overlaps,
+                          minSupport, windowSize, windowOverlap};
+        if (cg_upload_piles(h, &piles) != CG_OK) die("cg_upload_piles", cg_last_error(h));
+        if (cg_run(h) != CG_OK) die("cg_run", cg_last_error(h));
+        if (cg_download(h, &res) != CG_OK) die("cg_download", cg_last_error(h));
+        if (cg_download_windows(h, 0, &ws) != CG_OK) die("cg_download_windows", cg_last_error(h));
+        if (cg_finish_reads(h, &ws.batch, &res, &ws.reads, 1, &cor) != CG_OK) die("cg_finish_reads", cg_last_error(h));
+        for (uint32_t p = 0; p < ps.n_piles; ++p)
+            if (cor.read_off[p + 1] != cor.read_off[p]) {
+                std::cout << ">" << names[ps.pile_read[p]] << std::endl;
+                std::cout.write(cor.bases + cor.read_off[p], (std::streamsize)(cor.read_off[p + 1] - cor.read_off[p]));
+                std::cout << std::endl;
+            }
+        cg_free_corrected(&cor); cg_free_window_set(&ws); cg_free_results(&res); cg_free_pile_set(&ps); cg_destroy(h);
+        return 0;
+    }
 
     if (deviceExtraction) {
         // ---- phase A on the device: the store = every indexed read, decoded as getSequencesMap decodes them

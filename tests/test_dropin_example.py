@@ -73,6 +73,29 @@ def test_dropin_binary_with_device_side_extraction_on_emulated_kernels(small, en
     assert out == want
 
 
+def test_dropin_binary_with_device_side_ingest_and_post_filters_on_emulated_kernels(small, entry):
+    """-X: PAF parsing / sorting / top-maxSupport (cg_ingest_paf) and trimRead / dropRead (cg_finish_reads) run on the device as
+    well — the host reads two files and prints records; still the reference's FASTA."""
+    d, paf, fa, want = small
+    exe = _binary("consent_correction_b200")
+    emu = entry.build_emu()
+    libdir = d / "emulib"
+    libdir.mkdir(exist_ok=True)
+    link = libdir / "libconsent_b200.so"
+    if not link.exists():
+        os.symlink(emu, link)
+    env = dict(os.environ, LD_LIBRARY_PATH=str(libdir))
+    out = subprocess.run([exe, "-X", "-a", paf, "-r", fa] + FLAGS, check=True, capture_output=True, env=env).stdout
+    assert out == want
+
+
+@pytest.mark.gpu
+def test_dropin_binary_with_device_side_ingest_and_post_filters_on_the_gpu(small, gpu_lib):
+    d, paf, fa, want = small
+    out = subprocess.run([_binary("consent_correction_b200"), "-X", "-a", paf, "-r", fa] + FLAGS, check=True, capture_output=True).stdout
+    assert out == want
+
+
 @pytest.mark.gpu
 def test_dropin_binary_with_device_side_extraction_on_the_gpu(small, gpu_lib):
     d, paf, fa, want = small
