@@ -1227,7 +1227,7 @@ int cg_ingest_paf(cg_handle* h, const char* paf, uint64_t nbytes, const cg_read_
     CK(cudaEventRecord(ev[2], st));
     if (n_tiles) CG_LAUNCH(k_paf_lines, n_tiles, 256, 256, st, A);
     CK(cudaEventRecord(ev[3], st));
-    if (n_lines) CG_LAUNCH(k_paf_parse, (u32)((n_lines + 7) / 8), 256, 0, st, A);
+    if (n_lines) CG_LAUNCH(k_paf_parse, (u32)((n_lines + 7) / 8), 256, 8 * 12 * sizeof(u32), st, A);
     CK(cudaEventRecord(ev[4], st));
     if (n_lines) CG_LAUNCH(k_paf_heads, (u32)((n_lines + 255) / 256), 256, 0, st, A);
     scan(A.head, (u32)n_lines);

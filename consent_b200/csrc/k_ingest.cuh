@@ -2,7 +2,7 @@
 //
 // Every getNextReadPile (src/alignmentPiles.cpp:22-58) of one PAF text at once:
 //   k_paf_count / k_paf_lines   where the lines are (newline positions; 16 bytes per thread, the text is read twice)
-//   k_names_build               read names -> store index: open-addressing table keyed by a 64-bit FNV-1a hash, verified by
+//   k_names_build               read names -> store index: open-addressing table keyed by a 32-bit FNV-1a hash, verified by
 //                               byte compare; a name listed twice resolves to its last entry (`index[header] =`, src/utils.cpp:186)
 //   k_paf_parse                 Overlap(line) (src/Overlap.h:26-60): one warp per line, tabs found by ballot, one lane per column
 //   k_paf_heads / k_paf_piles   consecutive lines with the same qName form a pile; an empty line ends one (:29-37)
@@ -75,9 +75,10 @@ __global__ void __launch_bounds__(256) k_paf_lines(CgIngestArgs A) {
     }
 }
 
-__device__ __forceinline__ u64 cg_in_hash(const char* s, u32 n) {
-    u64 h = 1469598103934665603ull;
-    for (u32 i = 0; i < n; ++i) { h ^= (u8)s[i]; h *= 1099511628211ull; }
+__device__ __forceinline__ u32 cg_in_hash(const char* s, u32 n) {   // FNV-1a, 32 bits: one multiply per byte
+    u32 h = 2166136261u;
+    for (u32 i = 0; i < n; ++i) { h ^= (u8)s[i]; h *= 16777619u; }
+    h ^= h >> 15;
     return h;
 }
 __device__ __forceinline__ bool cg_in_same(const char* a, const char* b, u32 n) {
@@ -91,7 +92,7 @@ __global__ void k_names_build(CgIngestArgs A) {
     if (i >= A.n_names) return;
     const char* s = A.names + A.name_off[i];
     const u32 n = (u32)(A.name_off[i + 1] - A.name_off[i]);
-    u32 slot = (u32)cg_in_hash(s, n) & A.slot_mask;
+    u32 slot = cg_in_hash(s, n) & A.slot_mask;
     for (;;) {
         const u32 old = atomicCAS(&A.slots[slot], 0u, i + 1u);
         if (old == 0u) return;
@@ -102,7 +103,7 @@ __global__ void k_names_build(CgIngestArgs A) {
 }
 
 __device__ __forceinline__ u32 cg_in_lookup(const CgIngestArgs& A, const char* s, u32 n) {
-    u32 slot = (u32)cg_in_hash(s, n) & A.slot_mask;
+    u32 slot = cg_in_hash(s, n) & A.slot_mask;
     for (;;) {
         const u32 v = A.slots[slot];
         if (v == 0u) return CG_NONE32;
@@ -122,19 +123,23 @@ __global__ void __launch_bounds__(256) k_paf_parse(CgIngestArgs A) {
     const u64 b = i ? A.nl_pos[i - 1] + 1u : 0u, e = A.nl_pos[i];
     u32* out = (u32*)(A.rec + i);
     if (e == b) { if (lane == 0) out[0] = CG_NONE32; return; }
-    u64 st = b, en = e;                                            // lane f: column f = [st, en)
+    // the first 12 tabs: every lane holding one knows its rank (ballot + popc) and posts its position for the two columns it bounds
+    CG_DYN_SMEM(smem);
+    u32* tab = (u32*)smem + (threadIdx.x >> 5) * 12u;
     u32 ntabs = 0;
     for (u64 base = b; base < e && ntabs < 12u; base += 32u) {
         const u64 p = base + lane;
-        u32 m = __ballot_sync(CG_FULL, p < e && A.text[p] == '\t');
-        while (m && ntabs < 12u) {
-            const u64 pos = base + ((u32)__ffs((int)m) - 1u);
-            if (lane == ntabs) en = pos;
-            if (lane == ntabs + 1u) st = pos + 1u;
-            ++ntabs;
-            m &= m - 1u;
-        }
+        const bool is_tab = p < e && A.text[p] == '\t';
+        const u32 m = __ballot_sync(CG_FULL, is_tab);
+        const u32 t = ntabs + (u32)__popc(m & ((1u << lane) - 1u));
+        if (is_tab && t < 12u) tab[t] = (u32)(p - b);
+        ntabs += (u32)__popc(m);
     }
+    __syncwarp();
+    if (ntabs > 12u) ntabs = 12u;
+    u64 st = b, en = e;                                            // lane f: column f = [st, en)
+    if (lane >= 1u && lane <= ntabs) st = b + tab[lane - 1u] + 1u;
+    if (lane < ntabs) en = b + tab[lane];
     if (ntabs < 11u) { if (lane == 0) { atomicOr(A.ctl, (u32)CG_IN_FLAG_COLUMNS); out[0] = CG_NONE32; } return; }
     const char* s = A.text + st;
     const u32 n = (u32)(en - st);
