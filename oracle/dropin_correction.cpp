@@ -16,7 +16,9 @@
 // With -X nothing of processRead / getNextReadPile is left on the host: the PAF text goes to the device as it is
 // (cg_ingest_paf: parsing, grouping, std::sort + top-maxSupport), and trimRead / dropRead run behind the re-anchoring
 // (cg_finish_reads); the host reads two files and prints FASTA records.
-// Same command line as bin/CONSENT-correction (src/main.cpp:27-80).  tests/test_dropin_example.py runs it on a B200 and
+// Same command line as bin/CONSENT-correction and bin/CONSENT-polishing (src/main.cpp:27-80; the two reference binaries differ in
+// that processContig runs its windows on the CTPL pool and never trims, src/CONSENT-polishing.cpp:19-111): with -R (contigs in -r,
+// reads in -R, as CONSENT-polish:197 calls it) this binary is the polisher.  tests/test_dropin_example.py runs it on a B200 and
 // compares its FASTA byte for byte with the one the unmodified reference binary printed for the same PAF.
 #include <getopt.h>
 #include <unistd.h>
@@ -37,7 +39,7 @@
 static void die(const char* what, const char* why) { fprintf(stderr, "consent_correction_b200: %s: %s\n", what, why ? why : ""); exit(1); }
 
 int main(int argc, char** argv) {
-    std::string alignmentFile, readsFile;
+    std::string alignmentFile, readsFile, proofFile;
     unsigned minSupport = 3, maxSupport = 1000, windowSize = 500, merSize = 9, commonKMers = 8, minAnchors = 10,
              solidThresh = 4, windowOverlap = 50;                                       // src/main.cpp:15-24
     int opt, device = 0;
@@ -54,6 +56,7 @@ int main(int argc, char** argv) {
             case 'f': solidThresh = atoi(optarg); break;
             case 'm': windowOverlap = atoi(optarg); break;
             case 'r': readsFile = optarg; break;
+            case 'R': proofFile = optarg; break;
             case 'g': device = atoi(optarg); break;
             case 'x': deviceExtraction = true; break;
             case 'X': deviceIngest = true; break;
@@ -64,6 +67,10 @@ int main(int argc, char** argv) {
 
     robin_hood::unordered_map<std::string, std::vector<bool>> readIndex;
     indexReads(readIndex, readsFile);
+    // -R: the second read set of bin/CONSENT-polishing (contigs in -r, reads in -R; src/CONSENT-polishing.cpp:113-117, where
+    // doTrimRead is false :19) and of bin/CONSENT-correction's proof mode (src/CONSENT-correction.cpp:76-79): no trim, no drop
+    bool doTrimRead = true;
+    if (!proofFile.empty()) { indexReads(readIndex, proofFile); doTrimRead = false; }
     std::ifstream alignments(alignmentFile);
 
     cg_params prm = {merSize, solidThresh, commonKMers, minAnchors};
@@ -92,7 +99,7 @@ int main(int argc, char** argv) {
         if (cg_run(h) != CG_OK) die("cg_run", cg_last_error(h));
         if (cg_download(h, &res) != CG_OK) die("cg_download", cg_last_error(h));
         if (cg_download_windows(h, 0, &ws) != CG_OK) die("cg_download_windows", cg_last_error(h));
-        if (cg_finish_reads(h, &ws.batch, &res, &ws.reads, 1, &cor) != CG_OK) die("cg_finish_reads", cg_last_error(h));
+        if (cg_finish_reads(h, &ws.batch, &res, &ws.reads, doTrimRead ? 1 : 0, &cor) != CG_OK) die("cg_finish_reads", cg_last_error(h));
         for (uint32_t p = 0; p < ps.n_piles; ++p)
             if (cor.read_off[p + 1] != cor.read_off[p]) {
                 std::cout << ">" << names[ps.pile_read[p]] << std::endl;
@@ -144,8 +151,8 @@ int main(int argc, char** argv) {
         for (size_t r = 0; r < names.size(); ++r) {
             if (ws.reads.read_win_begin[r + 1] == ws.reads.read_win_begin[r]) continue;
             std::string corrected(cor.bases + cor.read_off[r], cor.bases + cor.read_off[r + 1]);
-            corrected = trimRead(corrected, 1);
-            if (!dropRead(corrected) && corrected.length() != 0) std::cout << ">" << names[r] << std::endl << corrected << std::endl;
+            if (doTrimRead) { corrected = trimRead(corrected, 1); if (dropRead(corrected)) corrected.clear(); }
+            if (corrected.length() != 0) std::cout << ">" << names[r] << std::endl << corrected << std::endl;
         }
         cg_free_corrected(&cor); cg_free_window_set(&ws); cg_free_results(&res); cg_destroy(h);
         return 0;
@@ -192,8 +199,8 @@ int main(int argc, char** argv) {
     for (size_t r = 0; r < readIds.size(); ++r) {
         if (readWinBegin[r + 1] == readWinBegin[r]) continue;                           // :23-25: no window, nothing printed
         std::string corrected(cor.bases + cor.read_off[r], cor.bases + cor.read_off[r + 1]);
-        corrected = trimRead(corrected, 1);
-        if (!dropRead(corrected) && corrected.length() != 0) std::cout << ">" << readIds[r] << std::endl << corrected << std::endl;
+        if (doTrimRead) { corrected = trimRead(corrected, 1); if (dropRead(corrected)) corrected.clear(); }
+        if (corrected.length() != 0) std::cout << ">" << readIds[r] << std::endl << corrected << std::endl;
     }
     cg_free_corrected(&cor);
     cg_free_results(&res);

@@ -110,3 +110,49 @@ def test_dropin_binary_on_the_gpu_prints_the_reference_fasta(small, gpu_lib):
     out = subprocess.run([_binary("consent_correction_b200"), "-a", paf, "-r", fa] + FLAGS, check=True, capture_output=True).stdout
     assert out.count(b">") == 20
     assert out == want
+
+
+# ---------------------------------------------------------------------------------------------------- CONSENT-polish (config 5 shape)
+# bin/CONSENT-polishing = the same path with contigs as queries, windows on a thread pool and no trimming
+# (src/CONSENT-polishing.cpp:19-111).  Fixture: tests/golden/make_polish_small.py (synthetic contigs + 30x ONT reads, golden =
+# what the unmodified reference polisher prints).  The drop-in binary is the polisher when given -R.
+@pytest.fixture(scope="module")
+def polish(tmp_path_factory):
+    d = tmp_path_factory.mktemp("polish_small")
+    files = {}
+    for name in ("polish_small.paf", "polish_small_contigs.fasta", "polish_small_reads.fasta"):
+        files[name] = str(d / name)
+        open(files[name], "wb").write(gzip.open(os.path.join(GOLD, name + ".gz")).read())
+    want = gzip.open(os.path.join(GOLD, "polish_small_polished.fasta.gz")).read()
+    args = ["-a", files["polish_small.paf"], "-r", files["polish_small_contigs.fasta"], "-R", files["polish_small_reads.fasta"]]
+    return d, args, want
+
+
+def test_polish_golden_is_what_the_unmodified_reference_polisher_prints(polish):
+    d, args, want = polish
+    out = subprocess.run([_binary("consent_polishing_ref")] + args + ["-j", "4", "-p", "/nonexistent"] + FLAGS, check=True, capture_output=True).stdout
+    assert out.count(b">") == 4
+    assert out == want
+
+
+@pytest.mark.parametrize("mode", [[], ["-x"], ["-X"]])
+def test_dropin_binary_polishes_like_the_reference_on_emulated_kernels(polish, entry, mode):
+    d, args, want = polish
+    exe = _binary("consent_correction_b200")
+    emu = entry.build_emu()
+    libdir = d / "emulib"
+    libdir.mkdir(exist_ok=True)
+    link = libdir / "libconsent_b200.so"
+    if not link.exists():
+        os.symlink(emu, link)
+    env = dict(os.environ, LD_LIBRARY_PATH=str(libdir))
+    out = subprocess.run([exe] + mode + args + FLAGS, check=True, capture_output=True, env=env).stdout
+    assert out == want
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [[], ["-X"]])
+def test_dropin_binary_polishes_like_the_reference_on_the_gpu(polish, gpu_lib, mode):
+    d, args, want = polish
+    out = subprocess.run([_binary("consent_correction_b200")] + mode + args + FLAGS, check=True, capture_output=True).stdout
+    assert out == want
