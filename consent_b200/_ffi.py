@@ -317,9 +317,12 @@ class PileSet:
                 return f"{n}: first difference at {int(np.argmax((x != y).reshape(len(x), -1).any(axis=1)))}"
         return "" if self.n_lines == o.n_lines else f"n_lines {self.n_lines} / {o.n_lines}"
 
-    def piles(self, store_off, store_bases, **kw) -> "Piles":
-        """These piles over a read store, as cg_upload_piles takes them."""
-        return Piles(store_off, store_bases, self.pile_read, self.pile_qlen, self.pile_ov_begin, self.overlaps, **kw)
+    def piles(self, store_off, store_bases, p0: int = 0, p1: int | None = None, **kw) -> "Piles":
+        """Piles [p0, p1) over a read store, as cg_upload_piles takes them."""
+        p1 = self.n_piles if p1 is None else p1
+        a, b = int(self.pile_ov_begin[p0]), int(self.pile_ov_begin[p1])
+        return Piles(store_off, store_bases, self.pile_read[p0:p1], self.pile_qlen[p0:p1],
+                     self.pile_ov_begin[p0:p1 + 1] - self.pile_ov_begin[p0], self.overlaps[a:b], **kw)
 
 
 def window_set_to_py(ws: cg_window_set, with_bases: bool = True):

@@ -11,7 +11,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from ._ffi import Batch, Results, cg_results  # noqa: F401
+from ._ffi import Batch, Corrected, Results, cg_results  # noqa: F401
 
 
 def shard_range(n_windows: int, rank: int, world: int) -> tuple[int, int]:
@@ -163,3 +163,63 @@ def gather_results(local: Results, device=None, group=None, with_solid: bool = T
         p.solid_count = raw[o:o + 4 * ns].view(np.uint32); o += 4 * ns
         flats.append(p)
     return _from_parts(flats) if concat else GatheredParts(flats)
+
+
+# ---- the whole pipeline (BASELINE config 4): read piles sharded over the GPUs, corrected reads gathered in PAF order ---------
+def shard_piles(pile_qlen, pile_ov_begin, world: int) -> list[tuple[int, int]]:
+    """Contiguous blocks of piles in PAF order, one per rank, balanced by the bases their windows will hold:
+    a pile of n overlaps over a read of L bases cuts about L / step windows of about n * coverage fraction sequences, so the
+    weight of pile p is qlen[p] * (n_overlaps[p] + 1).  Greedy prefix split, like shard_by_bases."""
+    qlen = np.asarray(pile_qlen, dtype=np.int64)
+    n_ov = np.diff(np.asarray(pile_ov_begin, dtype=np.int64))
+    P = len(qlen)
+    cum = np.concatenate([[0], np.cumsum(qlen * (n_ov + 1))])
+    total = int(cum[-1])
+    cuts = [0] + [int(np.searchsorted(cum, total * r / world, side="left")) for r in range(1, world)] + [P]
+    cuts = [min(max(c, 0), P) for c in cuts]
+    for i in range(1, len(cuts)):
+        cuts[i] = max(cuts[i], cuts[i - 1])
+    return [(cuts[i], cuts[i + 1]) for i in range(world)]
+
+
+def gather_corrected(local: Corrected, device=None, group=None):
+    """Ordered gather of every rank's corrected reads (cg_reanchor_reads / cg_finish_reads output) to rank 0: the one
+    collective of the pipeline — rank 0 writes the FASTA in PAF order (src/CONSENT-correction.cpp:100-103).  Returns the
+    concatenated Corrected on rank 0, None elsewhere."""
+    import torch
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    on_gpu = torch.device(device).type == "cuda"
+    lens = np.diff(local.read_off).astype(np.int64)
+    chunks = [lens.view(np.uint8), np.ascontiguousarray(local.bases).view(np.uint8)]
+    nbytes = int(sum(len(c) for c in chunks))
+    meta = torch.tensor([local.n_reads, len(local.bases), nbytes], dtype=torch.int64, device=device)
+    metas = [torch.zeros_like(meta) for _ in range(world)]
+    dist.all_gather(metas, meta, group=group)
+    metas = [[int(x) for x in m.tolist()] for m in metas]
+    max_len = max(max(m[2] for m in metas), 1)
+    buf = torch.empty(max_len, dtype=torch.uint8, device=device)
+    o = 0
+    for c in chunks:
+        if len(c):
+            buf[o:o + len(c)].copy_(torch.from_numpy(c), non_blocking=on_gpu)
+        o += len(c)
+    gathered = [torch.empty(max_len, dtype=torch.uint8, device=device) for _ in range(world)] if rank == 0 else None
+    dist.gather(buf, gathered, dst=0, group=group)
+    if rank != 0:
+        return None
+    all_lens, all_bases = [], []
+    for r in range(world):
+        nr, nb, tot = metas[r]
+        raw = gathered[r][:tot].cpu().numpy()
+        all_lens.append(raw[:8 * nr].view(np.int64))
+        all_bases.append(raw[8 * nr:8 * nr + nb])
+    out = Corrected.__new__(Corrected)
+    lens = np.concatenate(all_lens) if all_lens else np.zeros(0, np.int64)
+    out.n_reads = int(len(lens))
+    out.read_off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    out.bases = np.concatenate(all_bases) if all_bases else np.zeros(0, np.uint8)
+    return out

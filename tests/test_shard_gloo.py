@@ -70,3 +70,51 @@ def test_gather_world_size_2_gloo(entry, tmp_path):
     outs = [p.communicate(timeout=300)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), "\n".join(outs)
     assert "GATHER_OK 11" in outs[0] and "PARTS_OK" in outs[0]
+
+
+PIPE_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np
+import torch.distributed as dist
+from consent_b200.shard import gather_corrected, shard_piles
+from consent_b200.synth import synth_paf, synth_piles
+from tests.refs import Oracle
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+rank = dist.get_rank()
+orc = Oracle()
+p = synth_piles(n_reads=16, genome_len=6000, read_len=1800, seed=9, max_support=4000)
+text, names = synth_paf(p, seed=3, tie_range=2)
+ps = orc.ingest_paf(text, names, 8)                       # every rank parses the (small) PAF, then owns a block of piles
+
+def run(p0, p1):
+    b, rd, _ = orc.extract_windows(ps.piles(p.store_off, p.store_bases, p0, p1))
+    res, _ = orc.correct_windows(b, threads=4)
+    return orc.finish_reads(orc.reanchor_reads(b, res, rd, threads=2)[0], 1)
+
+blocks = shard_piles(ps.pile_qlen, ps.pile_ov_begin, 2)
+local = run(*blocks[rank])
+full = gather_corrected(local)
+if rank == 0:
+    want = run(0, ps.n_piles)
+    assert blocks[0][1] > 0 and blocks[1][1] == ps.n_piles and blocks[0][1] == blocks[1][0]
+    assert full.equals(want), "gathered corrected reads differ from the single-process run"
+    print("PIPELINE_OK", full.n_reads, int((np.diff(full.read_off) > 0).sum()))
+else:
+    assert full is None
+dist.barrier()
+dist.destroy_process_group()
+"""
+
+
+def test_pipeline_sharded_by_piles_world_size_2_gloo(entry, tmp_path):
+    """BASELINE config 4 shape, small: PAF -> piles sharded over two ranks -> windows -> consensuses -> re-anchored, trimmed reads,
+    gathered to rank 0 in PAF order = the single-process result (oracle standing in for the GPUs)."""
+    port = 31500 + os.getpid() % 2000
+    script = tmp_path / "pipe_worker.py"
+    script.write_text(PIPE_WORKER.format(root=ROOT, port=port))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+             for r in range(2)]
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(outs)
+    assert "PIPELINE_OK 16" in outs[0]
