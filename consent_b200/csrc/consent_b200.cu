@@ -171,7 +171,7 @@ struct cg_handle {
     u64 ex_bytes = 0;
     // PAF ingest (cg_ingest_paf) and post-filters (cg_finish_reads)
     DevBuf in_text, in_tile, in_nl, in_names, in_name_off, in_slots, in_rec, in_head, in_pfirst, in_plast, in_keep, in_scratch,
-           in_pread, in_pqlen, in_ov, in_res, in_ctl, ra_skip;
+           in_pread, in_pqlen, in_ov, in_res, in_ctl, in_htile, ra_skip;
     float in_ms = 0, in_parse_ms = 0, fin_ms = 0;
     u64 in_bytes = 0;
 };
@@ -692,7 +692,7 @@ void cg_destroy(cg_handle* h) {
                       &h->ex_win_end, &h->ex_slot_base, &h->ex_slot_len, &h->ex_slot_src, &h->ex_slot_loc, &h->ex_win_nseq, &h->ex_win_nbytes,
                       &h->ex_win_base, &h->ex_flags, &h->in_text, &h->in_tile, &h->in_nl, &h->in_names, &h->in_name_off, &h->in_slots, &h->in_rec,
                       &h->in_head, &h->in_pfirst, &h->in_plast, &h->in_keep, &h->in_scratch, &h->in_pread, &h->in_pqlen, &h->in_ov, &h->in_res,
-                      &h->in_ctl, &h->ra_skip};
+                      &h->in_ctl, &h->in_htile, &h->ra_skip};
     for (DevBuf* b : bufs) b->release();
     for (auto& t : h->tier) { t.mem.release(); t.desc.release(); }
     delete h;
@@ -1220,20 +1220,21 @@ int cg_ingest_paf(cg_handle* h, const char* paf, uint64_t nbytes, const cg_read_
     CK(cudaMemcpyAsync(&n_lines, A.tile_cnt + n_tiles, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (n_lines >= (1ull << 31)) { h->err = "more than 2^31 PAF lines in one call"; return done(CG_ERR_CAPACITY); }
-    CK(h->in_nl.ensure((n_lines + 1) * 8)); CK(h->in_rec.ensure((n_lines + 1) * sizeof(CgPafRec))); CK(h->in_head.ensure((n_lines + 2) * 8));
+    CK(h->in_nl.ensure((n_lines + 1) * 8)); CK(h->in_rec.ensure((n_lines + 1) * sizeof(CgPafRec))); CK(h->in_head.ensure((n_lines + 2) * 4)); CK(h->in_htile.ensure((n_lines / 256 + 3) * 8));
     CK(h->in_scratch.ensure((n_lines + 1) * 8));
-    A.nl_pos = h->in_nl.as<u64>(); A.n_lines = n_lines; A.rec = h->in_rec.as<CgPafRec>(); A.head = h->in_head.as<u64>(); A.sort_scratch = h->in_scratch.as<u64>();
+    A.nl_pos = h->in_nl.as<u64>(); A.n_lines = n_lines; A.rec = h->in_rec.as<CgPafRec>(); A.head = h->in_head.as<u32>(); A.head_tile = h->in_htile.as<u64>(); A.sort_scratch = h->in_scratch.as<u64>();
     // ---- records, pile boundaries
     CK(cudaEventRecord(ev[2], st));
     if (n_tiles) CG_LAUNCH(k_paf_lines, n_tiles, 256, 256, st, A);
     CK(cudaEventRecord(ev[3], st));
     if (n_lines) CG_LAUNCH(k_paf_parse, (u32)((n_lines + 7) / 8), 256, 8 * 12 * sizeof(u32), st, A);
     CK(cudaEventRecord(ev[4], st));
-    if (n_lines) CG_LAUNCH(k_paf_heads, (u32)((n_lines + 255) / 256), 256, 0, st, A);
-    scan(A.head, (u32)n_lines);
+    const u32 n_hblocks = (u32)((n_lines + 255) / 256);
+    if (n_lines) CG_LAUNCH(k_paf_heads, n_hblocks, 256, 256, st, A);
+    scan(A.head_tile, n_hblocks);
     u64 n_piles64 = 0;
     u32 ctl[2] = {0, 0};
-    CK(cudaMemcpyAsync(&n_piles64, A.head + n_lines, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&n_piles64, A.head_tile + n_hblocks, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(ctl, A.ctl, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(ev[5], st));
     CK(cudaStreamSynchronize(st));

@@ -2,9 +2,10 @@
 //
 // Every getNextReadPile (src/alignmentPiles.cpp:22-58) of one PAF text at once:
 //   k_paf_count / k_paf_lines   where the lines are (newline positions; 16 bytes per thread, the text is read twice)
-//   k_names_build               read names -> store index: open-addressing table keyed by a 32-bit FNV-1a hash, verified by
+//   k_names_build               read names -> store index: open-addressing table keyed by a position-weighted byte sum (a warp builds it 32 bytes per step), verified by
 //                               byte compare; a name listed twice resolves to its last entry (`index[header] =`, src/utils.cpp:186)
-//   k_paf_parse                 Overlap(line) (src/Overlap.h:26-60): one warp per line, tabs found by ballot, one lane per column
+//   k_paf_parse                 Overlap(line) (src/Overlap.h:26-60): one warp per line: tabs ranked by ballot + popcount, the two names hashed /
+//                               looked up / compared by the whole warp, one lane per remaining column
 //   k_paf_heads / k_paf_piles   consecutive lines with the same qName form a pile; an empty line ends one (:29-37)
 //   k_paf_select                std::sort(rbegin, rend) by resMatches + the cut to maxSupport (:39-42).  std::sort is not stable and
 //                               the reference is a libstdc++ program: the order of overlaps with equal resMatches — hence which of
@@ -29,7 +30,8 @@ struct CgIngestArgs {
     u64* nl_pos; u64 n_lines;                                       // position of the i-th newline
     const char* names; const u64* name_off; u32 n_names; u32* slots; u32 slot_mask;
     CgPafRec* rec;                                                  // [n_lines]
-    u64* head;                                                      // [n_lines + 1] first line of a pile -> exclusive scan = pile index
+    u32* head;                                                      // [n_lines] (heads before the line inside its 256-line block) << 1 | line is the first of a pile
+    u64* head_tile;                                                 // [n_lines / 256 + 1] heads per block -> exclusive scan
     u32 n_piles; u32* pile_first; u32* pile_last;
     u64* keep;                                                      // [n_piles + 1] overlaps kept -> exclusive scan = pile_ov_begin
     u32 max_support;
@@ -75,11 +77,26 @@ __global__ void __launch_bounds__(256) k_paf_lines(CgIngestArgs A) {
     }
 }
 
-__device__ __forceinline__ u32 cg_in_hash(const char* s, u32 n) {   // FNV-1a, 32 bits: one multiply per byte
-    u32 h = 2166136261u;
-    for (u32 i = 0; i < n; ++i) { h ^= (u8)s[i]; h *= 16777619u; }
-    h ^= h >> 15;
+// Name hash: a position-weighted byte sum with a final mix — a sum, so that a warp can build it 32 bytes per step
+// (cg_in_hash_warp) and one thread byte by byte (cg_in_hash, table build) with the same result.
+__device__ __forceinline__ u32 cg_in_weight(u32 i) { return (i * 0x9E3779B1u + 0x85EBCA6Bu) | 1u; }
+__device__ __forceinline__ u32 cg_in_mix(u32 h, u32 n) {
+    h += n * 0x27D4EB2Fu;
+    h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
     return h;
+}
+__device__ __forceinline__ u32 cg_in_hash(const char* s, u32 n) {
+    u32 h = 0;
+    for (u32 i = 0; i < n; ++i) h += ((u32)(u8)s[i] + 1u) * cg_in_weight(i);
+    return cg_in_mix(h, n);
+}
+__device__ __forceinline__ u32 cg_in_hash_warp(const char* s, u32 n, u32 lane) {
+    u32 h = 0;
+    for (u32 base = 0; base < n; base += 32u) {
+        const u32 i = base + lane;
+        if (i < n) h += ((u32)(u8)s[i] + 1u) * cg_in_weight(i);
+    }
+    return cg_in_mix(cg_warp_sum(h), n);
 }
 __device__ __forceinline__ bool cg_in_same(const char* a, const char* b, u32 n) {
     for (u32 i = 0; i < n; ++i) if (a[i] != b[i]) return false;
@@ -102,13 +119,23 @@ __global__ void k_names_build(CgIngestArgs A) {
     }
 }
 
-__device__ __forceinline__ u32 cg_in_lookup(const CgIngestArgs& A, const char* s, u32 n) {
-    u32 slot = cg_in_hash(s, n) & A.slot_mask;
+// The whole warp looks one name up: hash and byte compare 32 bytes per step, the probe sequence is uniform.
+__device__ __forceinline__ u32 cg_in_lookup_warp(const CgIngestArgs& A, const char* s, u32 n, u32 lane) {
+    u32 slot = cg_in_hash_warp(s, n, lane) & A.slot_mask;
     for (;;) {
         const u32 v = A.slots[slot];
         if (v == 0u) return CG_NONE32;
         const u32 j = v - 1u;
-        if ((u32)(A.name_off[j + 1] - A.name_off[j]) == n && cg_in_same(A.names + A.name_off[j], s, n)) return j;
+        const u64 o = A.name_off[j];
+        if ((u32)(A.name_off[j + 1] - o) == n) {
+            const char* c = A.names + o;
+            u32 diff = 0;
+            for (u32 base = 0; base < n && !diff; base += 32u) {
+                const u32 i = base + lane;
+                diff = __ballot_sync(CG_FULL, i < n && c[i] != s[i]);
+            }
+            if (!diff) return j;
+        }
         slot = (slot + 1u) & A.slot_mask;
     }
 }
@@ -120,40 +147,51 @@ __global__ void __launch_bounds__(256) k_paf_parse(CgIngestArgs A) {
     const u32 lane = threadIdx.x & 31u;
     const u64 i = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (i >= A.n_lines) return;
-    const u64 b = i ? A.nl_pos[i - 1] + 1u : 0u, e = A.nl_pos[i];
+    const u64 b = i ? A.nl_pos[i - 1] + 1u : 0u;
+    const u32 len = (u32)(A.nl_pos[i] - b);
+    const char* line = A.text + b;
     u32* out = (u32*)(A.rec + i);
-    if (e == b) { if (lane == 0) out[0] = CG_NONE32; return; }
+    if (len == 0u) { if (lane == 0) out[0] = CG_NONE32; return; }
     // the first 12 tabs: every lane holding one knows its rank (ballot + popc) and posts its position for the two columns it bounds
     CG_DYN_SMEM(smem);
     u32* tab = (u32*)smem + (threadIdx.x >> 5) * 12u;
     u32 ntabs = 0;
-    for (u64 base = b; base < e && ntabs < 12u; base += 32u) {
-        const u64 p = base + lane;
-        const bool is_tab = p < e && A.text[p] == '\t';
+    for (u32 base = 0; base < len && ntabs < 12u; base += 32u) {
+        const u32 p = base + lane;
+        const bool is_tab = p < len && line[p] == '\t';
         const u32 m = __ballot_sync(CG_FULL, is_tab);
         const u32 t = ntabs + (u32)__popc(m & ((1u << lane) - 1u));
-        if (is_tab && t < 12u) tab[t] = (u32)(p - b);
+        if (is_tab && t < 12u) tab[t] = p;
         ntabs += (u32)__popc(m);
     }
     __syncwarp();
     if (ntabs > 12u) ntabs = 12u;
-    u64 st = b, en = e;                                            // lane f: column f = [st, en)
-    if (lane >= 1u && lane <= ntabs) st = b + tab[lane - 1u] + 1u;
-    if (lane < ntabs) en = b + tab[lane];
     if (ntabs < 11u) { if (lane == 0) { atomicOr(A.ctl, (u32)CG_IN_FLAG_COLUMNS); out[0] = CG_NONE32; } return; }
-    const char* s = A.text + st;
-    const u32 n = (u32)(en - st);
+    // the two names, by the whole warp
+    const u32 t4 = tab[4] + 1u;
+    const u32 qid = cg_in_lookup_warp(A, line, tab[0], lane);
+    const u32 tid = cg_in_lookup_warp(A, line + t4, tab[5] - t4, lane);
+    // the other columns: lane f owns column f = [st, en)
+    u32 st = 0, en = len;
+    if (lane >= 1u && lane <= ntabs) st = tab[lane - 1u] + 1u;
+    if (lane < ntabs) en = tab[lane];
+    const char* s = line + st;
+    const u32 n = en - st;
     u32 v = 0, bad = 0;
     if (lane == 0 || lane == 5) {
-        v = cg_in_lookup(A, s, n);
+        v = lane == 0 ? qid : tid;
         if (v == CG_NONE32) bad = CG_IN_FLAG_NAME;
     } else if (lane == 4) {
         v = (n == 1u && s[0] == '+') ? 0u : 1u;
     } else if (lane < 12u) {
-        if (n == 0u || s[0] < '0' || s[0] > '9') bad = CG_IN_FLAG_NUMBER;
-        u64 x = 0;
-        for (u32 j = 0; j < n && s[j] >= '0' && s[j] <= '9'; ++j) { x = x * 10u + (u64)(s[j] - '0'); if (x > 0x7fffffffull) { bad = CG_IN_FLAG_NUMBER; break; } }
-        v = (u32)x;
+        u32 nd = 0;
+        for (; nd < n && nd < 11u && s[nd] >= '0' && s[nd] <= '9'; ++nd) v = v * 10u + (u32)(s[nd] - '0');
+        if (nd == 0u || nd > 10u) bad = CG_IN_FLAG_NUMBER;
+        else if (nd == 10u) {                                       // may exceed INT_MAX (or 32 bits): decide in 64
+            u64 x = 0;
+            for (u32 j = 0; j < 10u; ++j) x = x * 10u + (u64)(s[j] - '0');
+            if (x > 0x7fffffffull) bad = CG_IN_FLAG_NUMBER;
+        }
         if (lane == 3 || lane == 8) v -= 1u;                       // "Has to be -1" (Overlap.h:37,48); 0 wraps like the reference's unsigned
     }
     // CgPafRec slots: q, qlen, res, t_read, strand, q_start, q_end, t_start, t_end, t_length
@@ -168,24 +206,33 @@ __global__ void __launch_bounds__(256) k_paf_parse(CgIngestArgs A) {
     if (slot != CG_NONE32) out[slot] = v;
 }
 
-__global__ void k_paf_heads(CgIngestArgs A) {
-    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= A.n_lines) return;
-    const u32 q = A.rec[i].q;
+// Pile index of a line = heads before it: a block scan here, one small scan over the block totals, summed up by the readers.
+__global__ void __launch_bounds__(256) k_paf_heads(CgIngestArgs A) {
+    CG_DYN_SMEM(smem);
+    u32* scratch = (u32*)smem;
+    const u64 i = (u64)blockIdx.x * 256u + threadIdx.x;
     u32 hd = 0;
-    if (q != CG_NONE32) { hd = 1; if (i) { const u32 pq = A.rec[i - 1].q; if (pq == q) hd = 0; } }
-    A.head[i] = hd;
+    if (i < A.n_lines) {
+        const u32 q = A.rec[i].q;
+        if (q != CG_NONE32) { hd = 1; if (i) { const u32 pq = A.rec[i - 1].q; if (pq == q) hd = 0; } }
+    }
+    u32 total;
+    const u32 before = cg_block_scan(hd, scratch, &total);
+    if (i < A.n_lines) A.head[i] = (before << 1) | hd;
+    if (threadIdx.x == 0) A.head_tile[blockIdx.x] = total;
 }
 
-// after the scan of head[]: first / last line of every pile
+// after the scan of head_tile[]: first / last line of every pile
 __global__ void k_paf_piles(CgIngestArgs A) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= A.n_lines) return;
     if (A.rec[i].q == CG_NONE32) return;
-    const bool is_head = A.head[i + 1] != A.head[i];
-    const u32 pid = (u32)(is_head ? A.head[i] : A.head[i] - 1u);
+    const u32 h = A.head[i];
+    const bool is_head = (h & 1u) != 0u;
+    const u32 before = (u32)A.head_tile[i >> 8] + (h >> 1);
+    const u32 pid = is_head ? before : before - 1u;
     if (is_head) A.pile_first[pid] = (u32)i;
-    const bool is_last = i + 1 == A.n_lines || A.rec[i + 1].q == CG_NONE32 || A.head[i + 2] != A.head[i + 1];
+    const bool is_last = i + 1 == A.n_lines || A.rec[i + 1].q == CG_NONE32 || (A.head[i + 1] & 1u) != 0u;
     if (is_last) A.pile_last[pid] = (u32)i;
 }
 
