@@ -1209,10 +1209,10 @@ int cg_ingest_paf(cg_handle* h, const char* paf, uint64_t nbytes, const cg_read_
     cudaEvent_t ev[8];
     for (cudaEvent_t& e : ev) CK(cudaEventCreate(&e));
     auto done = [&](int rc) { for (cudaEvent_t e : ev) cudaEventDestroy(e); return rc; };
-    auto scan = [&](u64* a, u32 n) { CG_LAUNCH(k_scan, 1, 1024, 1024 * sizeof(u64), st, a, (u64*)nullptr, (u64*)nullptr, (u64*)nullptr, (u64*)nullptr, n); };
+    auto scan = [&](u64* a, u32 n) { CG_LAUNCH(k_in_scan, 1, 1024, 40 * sizeof(u64), st, a, n); };
     // ---- lines
     CK(cudaEventRecord(ev[0], st));
-    if (NN) CG_LAUNCH(k_names_build, (NN + 255) / 256, 256, 0, st, A);
+    if (NN) CG_LAUNCH(k_names_build, (NN + 63) / 64, 64, 0, st, A);
     if (n_tiles) CG_LAUNCH(k_paf_count, n_tiles, 256, 256, st, A);
     scan(A.tile_cnt, n_tiles);
     CK(cudaEventRecord(ev[1], st));

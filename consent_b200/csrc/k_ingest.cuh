@@ -103,6 +103,35 @@ __device__ __forceinline__ bool cg_in_same(const char* a, const char* b, u32 n) 
     return true;
 }
 
+// Exclusive in-place scan of n u64 entries (+ total at [n]) by one CTA of 1024 threads: contiguous chunk per thread, block scan
+// of the chunk sums by warp shuffles.  For the few-thousand-entry arrays of this file (tiles, 256-line blocks, piles).
+__global__ void __launch_bounds__(1024) k_in_scan(u64* a, u32 n) {
+    CG_DYN_SMEM(smem);
+    u64* part = (u64*)smem;                                         // 33 entries
+    const u32 t = threadIdx.x, lane = t & 31u, warp = t >> 5;
+    const u32 per = (n + 1023u) / 1024u;
+    const u32 b = t * per < n ? t * per : n, e = b + per < n ? b + per : n;
+    u64 s = 0;
+    for (u32 i = b; i < e; ++i) s += a[i];
+    u64 inc = s;
+#pragma unroll
+    for (u32 d = 1; d < 32; d <<= 1) { const u64 o = __shfl_up_sync(CG_FULL, inc, d); if (lane >= d) inc += o; }
+    if (lane == 31) part[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        const u64 x = part[lane];
+        u64 xi = x;
+#pragma unroll
+        for (u32 d = 1; d < 32; d <<= 1) { const u64 o = __shfl_up_sync(CG_FULL, xi, d); if (lane >= d) xi += o; }
+        part[lane] = xi - x;
+        if (lane == 31) part[32] = xi;
+    }
+    __syncthreads();
+    u64 run = part[warp] + inc - s;
+    for (u32 i = b; i < e; ++i) { const u64 v = a[i]; a[i] = run; run += v; }
+    if (t == 0) a[n] = part[32];
+}
+
 // slots[] = store index + 1 (0 = free).  Two entries with the same name share a slot, which keeps the larger index.
 __global__ void k_names_build(CgIngestArgs A) {
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -195,8 +224,9 @@ __global__ void __launch_bounds__(256) k_paf_parse(CgIngestArgs A) {
         if (lane == 3 || lane == 8) v -= 1u;                       // "Has to be -1" (Overlap.h:37,48); 0 wraps like the reference's unsigned
     }
     // CgPafRec slots: q, qlen, res, t_read, strand, q_start, q_end, t_start, t_end, t_length
-    const u32 slot = lane == 0 ? 0u : lane == 1 ? 1u : lane == 9 ? 2u : lane == 5 ? 3u : lane == 4 ? 4u : lane == 2 ? 5u : lane == 3 ? 6u
-                   : lane == 7 ? 7u : lane == 8 ? 8u : lane == 6 ? 9u : CG_NONE32;
+    // (one nibble per lane: 0 1 5 6 4 3 9 7 8 2, then none)
+    const u32 nib = lane < 16u ? (u32)(0xFFFFFF2879346510ull >> (4u * lane)) & 15u : 15u;
+    const u32 slot = nib == 15u ? CG_NONE32 : nib;
     const u32 anybad = __ballot_sync(CG_FULL, bad != 0u);
     if (anybad) {
         if (bad) atomicOr(A.ctl, bad);
