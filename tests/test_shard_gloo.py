@@ -118,3 +118,46 @@ def test_pipeline_sharded_by_piles_world_size_2_gloo(entry, tmp_path):
     outs = [p.communicate(timeout=600)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), "\n".join(outs)
     assert "PIPELINE_OK 16" in outs[0]
+
+
+POLISH_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np
+import torch.distributed as dist
+from consent_b200.shard import gather_results, shard_by_bases
+from consent_b200.synth import synth_paf, synth_piles
+from tests.refs import Oracle
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+rank = dist.get_rank()
+orc = Oracle()
+p = synth_piles(n_reads=40, genome_len=6000, read_len=3000, n_piles=2, seed=19, profile="ONT", max_support=4000)   # 2 "contigs"
+text, names = synth_paf(p, seed=4, tie_range=3)
+ps = orc.ingest_paf(text, names, 30)
+batch, reads, _ = orc.extract_windows(ps.piles(p.store_off, p.store_bases))          # every rank cuts all windows (cheap) ...
+w0, w1 = shard_by_bases(batch, 2)[rank]                                             # ... and corrects its block of them
+local, _ = orc.correct_windows(batch.slice(w0, w1), threads=4)
+full = gather_results(local)                                                         # consensuses + solid k-mers to rank 0
+if rank == 0:
+    want_res, _ = orc.correct_windows(batch, threads=4)
+    assert full.equals(want_res)
+    got = orc.finish_reads(orc.reanchor_reads(batch, full, reads, threads=2)[0], 0)  # polishing never trims
+    want = orc.finish_reads(orc.reanchor_reads(batch, want_res, reads, threads=2)[0], 0)
+    assert got.equals(want) and 0 < w1 < batch.n_windows
+    print("POLISH_OK", batch.n_windows, got.n_reads)
+dist.barrier()
+dist.destroy_process_group()
+"""
+
+
+def test_polishing_sharded_by_windows_world_size_2_gloo(entry, tmp_path):
+    """BASELINE config 5 shape, small: a contig's windows are split over the ranks (one contig can dominate), the
+    window results are gathered and rank 0 re-anchors them on the contigs."""
+    port = 33500 + os.getpid() % 2000
+    script = tmp_path / "polish_worker.py"
+    script.write_text(POLISH_WORKER.format(root=ROOT, port=port))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+             for r in range(2)]
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(outs)
+    assert "POLISH_OK" in outs[0]
