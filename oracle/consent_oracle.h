@@ -14,6 +14,9 @@ void  oracle_free_results(cg_results* r);
 char* oracle_dump_window(const cg_batch* in, uint32_t w, const cg_params* p);
 /* MSA rows (newline separated) of one POA run over seqs[0..n). malloc'ed. */
 char* oracle_spoa_msa(const char* const* seqs, uint32_t n);
+/* Heaviest-bundle consensus of one POA run with scores m / x / gap — only to replay spoa's own known-answer tests
+ * (BMEAN/spoa/test/spoa_test.cpp) against the on-path DP / traceback / graph code. malloc'ed. */
+char* oracle_spoa_consensus(const char* const* seqs, uint32_t n, int m, int x, int gap);
 void  oracle_free_text(char* p);
 /* Work counters accumulated by oracle_correct_windows since the last reset. */
 void  oracle_reset_counters(void);

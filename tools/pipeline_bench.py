@@ -34,15 +34,28 @@ text, names = synth_paf(p, seed=42, tie_range=60)
 cor = Corrector(device=local)
 
 
+phase = {}
+
+
 def step():
+    t = [time.perf_counter()]
     ps = cor.ingest_paf(text, names, 150)                          # every rank parses the text (1 ms per 26 MB), then owns a block
     p0, p1 = shard_piles(ps.pile_qlen, ps.pile_ov_begin, world)[rank]
+    t.append(time.perf_counter())
     cor.upload_piles(ps.piles(p.store_off, p.store_bases, p0, p1))
+    t.append(time.perf_counter())
     cor.run()
+    t.append(time.perf_counter())
     res = cor.download()
+    t.append(time.perf_counter())
     batch, reads, _ = cor.download_windows(with_bases=False)
+    t.append(time.perf_counter())
     got = cor.finish_reads(batch, res, reads, 1)
+    t.append(time.perf_counter())
     full = gather_corrected(got) if world > 1 else got
+    t.append(time.perf_counter())
+    for k, name in enumerate(("ingest", "upload_piles", "run", "download", "download_windows", "finish_reads", "gather")):
+        phase[name] = round(t[k + 1] - t[k], 4)
     return batch.n_windows, p1 - p0, full
 
 
@@ -71,6 +84,6 @@ if rank == 0:
                       "n_gpus": world, "reads": n_reads, "coverage": cov, "paf_bytes": len(text), "windows": Wt,
                       "windows_per_rank": [int(v[1]) for v in allv], "s_per_step": sec, "reads_per_s": n_reads / sec, "windows_per_s": Wt / sec,
                       "fasta_records": int((np.diff(full.read_off) > 0).sum()), "corrected_bases": int(full.read_off[-1]),
-                      "digest": hashlib.sha256(np.ascontiguousarray(full.bases).tobytes()).hexdigest()[:16], "scaling": "strong"}), flush=True)
+                      "digest": hashlib.sha256(np.ascontiguousarray(full.bases).tobytes()).hexdigest()[:16], "scaling": "strong", "phase_s_rank0_last_step": phase, "run_ms_device": cor.run_ms()}), flush=True)
 if world > 1:
     dist.destroy_process_group()
