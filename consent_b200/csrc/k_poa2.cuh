@@ -95,7 +95,7 @@ template <class IdT_, int STORE_, u32 VCAP_, u32 HCELLS_, u32 LCAP_, u32 SEGCAP_
 };
 typedef CgPoa2Tier<u8, CG_P2_ALL_SMEM, 128, 2048, 64, 192, 4, 5> CgPoa2C1;
 typedef CgPoa2Tier<u8, CG_P2_H_GLOBAL, 254, 30976, 120, 192, 4, 5> CgPoa2GT;
-typedef CgPoa2Tier<u16, CG_P2_ALL_GLOBAL, 1024, 512u << 10, 1024, 1024, 4, 2> CgPoa2W1;
+typedef CgPoa2Tier<u16, CG_P2_ALL_GLOBAL, 1024, 512u << 10, 1024, 1024, 4, 4> CgPoa2W1;    // 16 warps per SM: +36 % at N = 20, +21 % at N = 40 over 8 (tools/poa_tier_sweep.py)
 typedef CgPoa2Tier<u16, CG_P2_ALL_GLOBAL, 4096, 4u << 20, 2048, 4096, 4, 2> CgPoa2W2;
 
 template <class T> struct CgPoa2Lay {
@@ -624,6 +624,7 @@ __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s
             else if (T::LCAP > 63 && L <= 127) bv = cg_poa2_dp2<(T::LCAP > 63 ? 2 : 1)>(s, V, seq, L, Ws, trk);
             else if (T::LCAP > 127 && L <= 255) bv = cg_poa2_dp2<(T::LCAP > 127 ? 4 : 1)>(s, V, seq, L, Ws, trk);
             else if (T::LCAP > 255 && L <= 511) bv = cg_poa2_dp2<(T::LCAP > 255 ? 8 : 1)>(s, V, seq, L, Ws, trk);
+            else if (T::LCAP > 511 && L <= 575) bv = cg_poa2_dp2<(T::LCAP > 511 ? 9 : 1)>(s, V, seq, L, Ws, trk);    // a 500-base PB window: 522 +- 8
             else if (T::LCAP > 511) bv = cg_poa2_dp_any(s, V, seq, L, Ws, trk);
             else bv = 0;
             j_aln += 1; j_cells += (u64)(V + 1) * L; j_pred += (u64)sumdeg * L;
