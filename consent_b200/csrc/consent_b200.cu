@@ -183,7 +183,33 @@ struct HostWindowSet {
 };
 
 // Host copy of the corrected reads (pinned).
-struct HostCorrected { u64* off = nullptr; char* bases = nullptr; };
+struct HostCorrected { u64* off = nullptr; char* bases = nullptr; size_t off_cap = 0, bases_cap = 0; };
+// One pair of pinned buffers is kept across calls (cudaMallocHost / cudaFreeHost of tens of MB per call cost 5-10 ms and spike).
+static std::mutex g_hc_mu;
+static HostCorrected* g_hc_spare = nullptr;
+static HostCorrected* hc_acquire() {
+    std::lock_guard<std::mutex> lk(g_hc_mu);
+    HostCorrected* hc = g_hc_spare ? g_hc_spare : new HostCorrected();
+    g_hc_spare = nullptr;
+    return hc;
+}
+static void hc_destroy(HostCorrected* hc) { if (hc->off) cudaFreeHost(hc->off); if (hc->bases) cudaFreeHost(hc->bases); delete hc; }
+static void hc_release(HostCorrected* hc) {
+    {
+        std::lock_guard<std::mutex> lk(g_hc_mu);
+        if (!g_hc_spare) { g_hc_spare = hc; return; }
+    }
+    hc_destroy(hc);
+}
+template <class T> static bool hc_ensure(T*& p, size_t& cap, size_t bytes) {
+    if (bytes <= cap) return true;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    const size_t want = bytes + bytes / 4 + 256;
+    if (cudaMallocHost(&p, want) != cudaSuccess) { p = nullptr; return false; }
+    cap = want;
+    return true;
+}
 
 namespace {
 
@@ -1120,13 +1146,13 @@ static int reanchor_impl(cg_handle* h, const cg_batch* windows, const cg_results
                : "re-anchoring: an alignment region is empty or nothing aligns (the reference does not survive this input either)";
         return (ctl[1] & CG_RA_FLAG_CAPACITY) ? CG_ERR_CAPACITY : CG_ERR_INVALID_ARG;
     }
-    HostCorrected* hc = new HostCorrected();
-    auto fail = [&](int rc) { if (hc->off) cudaFreeHost(hc->off); if (hc->bases) cudaFreeHost(hc->bases); delete hc; return rc; };
-    if (cudaMallocHost(&hc->off, ((size_t)R + 1) * 8) != cudaSuccess) { h->err = "out of pinned memory"; return fail(CG_ERR_OUT_OF_MEMORY); }
+    HostCorrected* hc = hc_acquire();
+    auto fail = [&](int rc) { hc_destroy(hc); return rc; };
+    if (!hc_ensure(hc->off, hc->off_cap, ((size_t)R + 1) * 8)) { h->err = "out of pinned memory"; return fail(CG_ERR_OUT_OF_MEMORY); }
     hc->off[0] = 0;
     for (u32 r = 0; r < R; ++r) hc->off[r + 1] = hc->off[r] + len[r];
     const u64 tot = hc->off[R];
-    if (cudaMallocHost(&hc->bases, tot + 1) != cudaSuccess) { h->err = "out of pinned memory"; return fail(CG_ERR_OUT_OF_MEMORY); }
+    if (!hc_ensure(hc->bases, hc->bases_cap, tot + 1)) { h->err = "out of pinned memory"; return fail(CG_ERR_OUT_OF_MEMORY); }
     cudaError_t e = h->ra_out.ensure(tot + 16);
     if (e == cudaSuccess) e = cudaMemcpyAsync(h->ra_out_off.p, hc->off, ((size_t)R + 1) * 8, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess && R && tot) {
@@ -1160,9 +1186,7 @@ void cg_free_corrected(cg_corrected* c) {
     if (!c || !c->owner_) return;
     HostCorrected* hc = static_cast<HostCorrected*>(c->owner_);
     c->owner_ = nullptr;
-    if (hc->off) cudaFreeHost(hc->off);
-    if (hc->bases) cudaFreeHost(hc->bases);
-    delete hc;
+    hc_release(hc);
 }
 
 int cg_reanchor_stats(const cg_handle* h, float* kernel_ms, uint64_t* dp_cells) {

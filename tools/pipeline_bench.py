@@ -84,6 +84,6 @@ if rank == 0:
                       "n_gpus": world, "reads": n_reads, "coverage": cov, "paf_bytes": len(text), "windows": Wt,
                       "windows_per_rank": [int(v[1]) for v in allv], "s_per_step": sec, "reads_per_s": n_reads / sec, "windows_per_s": Wt / sec,
                       "fasta_records": int((np.diff(full.read_off) > 0).sum()), "corrected_bases": int(full.read_off[-1]),
-                      "digest": hashlib.sha256(np.ascontiguousarray(full.bases).tobytes()).hexdigest()[:16], "scaling": "strong", "phase_s_rank0_last_step": phase, "run_ms_device": cor.run_ms()}), flush=True)
+                      "digest": hashlib.sha256(np.ascontiguousarray(full.bases).tobytes()).hexdigest()[:16], "scaling": "strong", "phase_s_rank0_last_step": phase, "run_ms_device": cor.run_ms(), "reanchor": cor.reanchor_stats(), "finish": cor.finish_stats()}), flush=True)
 if world > 1:
     dist.destroy_process_group()
