@@ -104,7 +104,8 @@ template <class T> struct CgPoa2Lay {
     static constexpr size_t mx(size_t a, size_t b) { return a > b ? a : b; }
     static constexpr size_t ID = sizeof(typename T::IdT);
     static constexpr size_t WORK = r16(sizeof(typename Pk::Item) * mx(T::SCAP, T::ALNCAP));   // DFS stack | alignment pairs | splice items
-    static constexpr size_t TMP = r16(mx(2 * (size_t)T::VCAP, (3 * ID + 1) * T::LCAP));     // DFS marks+check | update scratch
+    static constexpr size_t TMP0 = r16(mx(2 * (size_t)T::VCAP, (3 * ID + 1) * T::LCAP));    // DFS marks+check | update scratch
+    static constexpr size_t TMP = TMP0 + (T::STORE == CG_P2_ALL_GLOBAL ? r16(2 * ((size_t)T::VCAP + 1)) : 0);   // + the maximum of every matrix row (all-global tiers)
     static constexpr size_t o_pred = 0, o_prow = o_pred + sizeof(typename Pk::Vec) * T::VCAP, o_rdesc = o_prow + sizeof(typename Pk::Vec) * T::VCAP,
                             o_meta = o_rdesc + r16(sizeof(typename Pk::Rdesc) * T::VCAP), o_seg = o_meta + r16(sizeof(typename Pk::Meta) * T::VCAP),
                             o_nseq = o_seg + r16(sizeof(typename Pk::Seg) * T::SEGCAP), o_work = o_nseq + r16(2 * (size_t)T::VCAP),
@@ -139,6 +140,7 @@ template <class T> struct CgPoa2G {
     __device__ __forceinline__ IdT& posq(u32 i) const { return ((IdT*)(b() + Lay::o_tmp))[T::LCAP + i]; }
     __device__ __forceinline__ IdT& anchq(u32 i) const { return ((IdT*)(b() + Lay::o_tmp))[2 * T::LCAP + i]; }
     __device__ __forceinline__ u8& kindq(u32 i) const { return b()[Lay::o_tmp + 3 * Lay::ID * T::LCAP + i]; }
+    __device__ __forceinline__ i16& rowmax(u32 i) const { return ((i16*)(b() + Lay::o_tmp + Lay::TMP0))[i]; }   // all-global tiers only
     __device__ __forceinline__ u8& letter(u32 i) const { return b()[Lay::o_letter + i]; }
     __device__ __forceinline__ IdT& r2n(u32 which, u32 i) const { return ((IdT*)(b() + Lay::o_r2n + which * Lay::R2N_STRIDE))[i]; }
     __device__ __forceinline__ IdT& rank_of(u32 i) const { return ((IdT*)(b() + Lay::o_rank))[i]; }
@@ -265,11 +267,21 @@ template <class T> __device__ __forceinline__ u32 cg_poa2_traceback(const CgPoa2
 // one warp reduction per row (redux.sync) and warp-uniform bookkeeping: the maximum, the first row holding it (in this
 // kernel's row order) and how many rows hold it.
 struct CgPoa2Max { i32 M; u32 row, nrows; };
-__device__ __forceinline__ void cg_poa2_track(CgPoa2Max& t, i32 lane_max, u32 row) {
+__device__ __forceinline__ i32 cg_poa2_track(CgPoa2Max& t, i32 lane_max, u32 row) {
     const i32 m = __reduce_max_sync(CG_FULL, lane_max);
     if (m > t.M) { t.M = m; t.row = row; t.nrows = 1; }
     else if (m == t.M) t.nrows++;
+    return m;
 }
+// The wide tiers keep every row's maximum: when several rows tie for the matrix maximum, the first of them in spoa's order is
+// found from this array instead of scanning the rows of a matrix that lives in HBM.
+#define CG_P2_KEEP_ROWMAX(T, s, m, row) do { if (T::STORE == CG_P2_ALL_GLOBAL && cg_lane() == 0) (s).rowmax(row) = (i16)(m); } while (0)
+// Next row's predecessor vector into L1 while this row is computed (no registers held).
+#if !defined(CG_EMU)
+#define CG_P2_PREFETCH(p) asm volatile("prefetch.global.L1 [%0];" ::"l"(p))
+#else
+#define CG_P2_PREFETCH(p) ((void)(p))
+#endif
 
 template <int CH, class T>
 __device__ __forceinline__ i32 cg_poa2_dp(const CgPoa2G<T>& s, u32 V, const u8* seq, u32 L, u32 Ws) {
@@ -407,7 +419,7 @@ __device__ __forceinline__ i32 cg_poa2_dp2(const CgPoa2G<T>& s, u32 V, const u8*
     u32* row = (u32*)(H + Ws) + lane;                    // cells (r + 1, 2 lane) and (r + 1, 2 lane + 1)
     for (u32 r = 0; r < V; ++r) {
         const u32 d = dnext;
-        if (r + 1 < V) dnext = (u32)s.rdesc(r + 1);
+        if (r + 1 < V) { dnext = (u32)s.rdesc(r + 1); if (!T::SMEM) CG_P2_PREFETCH(&s.prow(r + 1)); }
         const u32 ch = d & 0xffu;
         const u32 deg = (d >> 8) & 0xffu;
         const u32 p0 = (d >> 16) & IDNONE;
@@ -470,7 +482,8 @@ __device__ __forceinline__ i32 cg_poa2_dp2(const CgPoa2G<T>& s, u32 V, const u8*
         }
         if (!T::H_SMEM) {
             const u32 lo = rowmax & 0xffffu, hi = rowmax >> 16;          // scores are never negative
-            cg_poa2_track(trk, (i32)(lo > hi ? lo : hi), r + 1);
+            const i32 m = cg_poa2_track(trk, (i32)(lo > hi ? lo : hi), r + 1);
+            CG_P2_KEEP_ROWMAX(T, s, m, r + 1);
         }
         row += Ws / 2;
         __syncwarp();
@@ -531,7 +544,8 @@ __device__ __forceinline__ i32 cg_poa2_dp_any(const CgPoa2G<T>& s, u32 V, const 
         }
         if (!T::POSTPASS_MAX) {
             const u32 lo = rowmax & 0xffffu, hi = rowmax >> 16;
-            cg_poa2_track(trk, (i32)(lo > hi ? lo : hi), r + 1);
+            const i32 m = cg_poa2_track(trk, (i32)(lo > hi ? lo : hi), r + 1);
+            CG_P2_KEEP_ROWMAX(T, s, m, r + 1);
         }
         __syncwarp();
     }
@@ -664,8 +678,11 @@ __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s
                     u32 myrow = 0;
                     if (i < V) {
                         myrow = (u32)s.rank_of(s.xr2n(i)) + 1;
-                        const i16* hr = H + (size_t)myrow * Ws;
-                        for (u32 j = 1; j < Wd; ++j) hit = hit || (i32)hr[j] == M;
+                        if (T::STORE == CG_P2_ALL_GLOBAL) hit = (i32)s.rowmax(myrow) == M;
+                        else {
+                            const i16* hr = H + (size_t)myrow * Ws;
+                            for (u32 j = 1; j < Wd; ++j) hit = hit || (i32)hr[j] == M;
+                        }
                     }
                     const u32 bal = __ballot_sync(CG_FULL, hit);
                     if (bal) { row = __shfl_sync(CG_FULL, myrow, __ffs((int)bal) - 1); break; }
