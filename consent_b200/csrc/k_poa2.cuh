@@ -207,6 +207,14 @@ template <class T> __device__ __forceinline__ bool cg_poa2_dfs(const CgPoa2G<T>&
     return true;
 }
 
+// A line into L1 ahead of its use (no registers held): the next row's predecessor vector during the DP.  (Prefetching the matrix
+// rows a traceback is about to reach — four rows, ~7 steps ahead — measured no gain on the wide tiers and was dropped.)
+#if !defined(CG_EMU)
+#define CG_P2_PREFETCH(p) asm volatile("prefetch.global.L1 [%0];" ::"l"(p))
+#else
+#define CG_P2_PREFETCH(p) ((void)(p))
+#endif
+
 // ------------------------------------------------------------------ traceback (lane 0)
 // simd_alignment_engine_impl.hpp:968-1004: diagonal over the predecessors in in-edge order, then vertical over them,
 // then horizontal.  Pairs are written in traceback order (last pair first) as node | qpos << W (all ones = none).
@@ -276,12 +284,7 @@ __device__ __forceinline__ i32 cg_poa2_track(CgPoa2Max& t, i32 lane_max, u32 row
 // The wide tiers keep every row's maximum: when several rows tie for the matrix maximum, the first of them in spoa's order is
 // found from this array instead of scanning the rows of a matrix that lives in HBM.
 #define CG_P2_KEEP_ROWMAX(T, s, m, row) do { if (T::STORE == CG_P2_ALL_GLOBAL && cg_lane() == 0) (s).rowmax(row) = (i16)(m); } while (0)
-// Next row's predecessor vector into L1 while this row is computed (no registers held).
-#if !defined(CG_EMU)
-#define CG_P2_PREFETCH(p) asm volatile("prefetch.global.L1 [%0];" ::"l"(p))
-#else
-#define CG_P2_PREFETCH(p) ((void)(p))
-#endif
+
 
 template <int CH, class T>
 __device__ __forceinline__ i32 cg_poa2_dp(const CgPoa2G<T>& s, u32 V, const u8* seq, u32 L, u32 Ws) {
