@@ -208,7 +208,8 @@ template <class T> __device__ __forceinline__ bool cg_poa2_dfs(const CgPoa2G<T>&
 }
 
 // A line into L1 ahead of its use (no registers held): the next row's predecessor vector during the DP.  (Prefetching the matrix
-// rows a traceback is about to reach — four rows, ~7 steps ahead — measured no gain on the wide tiers and was dropped.)
+// rows a traceback is about to reach — four rows ~7 steps ahead, or one row 8 steps ahead along the first-predecessor chain —
+// measured no gain on the wide tiers and was dropped.)
 #if !defined(CG_EMU)
 #define CG_P2_PREFETCH(p) asm volatile("prefetch.global.L1 [%0];" ::"l"(p))
 #else
