@@ -1230,9 +1230,13 @@ int cg_ingest_paf(cg_handle* h, const char* paf, uint64_t nbytes, const cg_read_
     A.text = h->in_text.as<char>(); A.nbytes = nbytes; A.tile_cnt = h->in_tile.as<u64>(); A.n_tiles = n_tiles;
     A.names = h->in_names.as<char>(); A.name_off = h->in_name_off.as<u64>(); A.n_names = NN; A.slots = h->in_slots.as<u32>(); A.slot_mask = slots - 1;
     A.max_support = max_support; A.ctl = h->in_ctl.as<u32>();
-    cudaEvent_t ev[8];
-    for (cudaEvent_t& e : ev) CK(cudaEventCreate(&e));
-    auto done = [&](int rc) { for (cudaEvent_t e : ev) cudaEventDestroy(e); return rc; };
+    struct Events {                                                 // destroyed on every return path, CK's included
+        cudaEvent_t e[8] = {};
+        ~Events() { for (cudaEvent_t x : e) if (x) cudaEventDestroy(x); }
+    } evs;
+    cudaEvent_t* ev = evs.e;
+    for (int i = 0; i < 8; ++i) CK(cudaEventCreate(&ev[i]));
+    auto done = [&](int rc) { return rc; };
     auto scan = [&](u64* a, u32 n) { CG_LAUNCH(k_in_scan, 1, 1024, 40 * sizeof(u64), st, a, n); };
     // ---- lines
     CK(cudaEventRecord(ev[0], st));
