@@ -2,8 +2,9 @@
 //
 // Every getNextReadPile (src/alignmentPiles.cpp:22-58) of one PAF text at once:
 //   k_paf_count / k_paf_lines   where the lines are (newline positions; 16 bytes per thread, the text is read twice)
-//   k_names_build               read names -> store index: open-addressing table keyed by a position-weighted byte sum (a warp builds it 32 bytes per step), verified by
-//                               byte compare; a name listed twice resolves to its last entry (`index[header] =`, src/utils.cpp:186)
+//   k_names_build               read names -> store index: open-addressing table keyed by a position-weighted byte sum (a sum, so that
+//                               the parser's warp can build it 32 bytes per step), verified by byte compare; a name listed twice
+//                               resolves to its last entry (`index[header] =`, src/utils.cpp:186)
 //   k_paf_parse                 Overlap(line) (src/Overlap.h:26-60): one warp per line: tabs ranked by ballot + popcount, the two names hashed /
 //                               looked up / compared by the whole warp, one lane per remaining column
 //   k_paf_heads / k_paf_piles   consecutive lines with the same qName form a pile; an empty line ends one (:29-37)
@@ -14,7 +15,9 @@
 //                               in shared memory (bits/stl_algo.h: __introsort_loop, threshold 16, depth limit 2·floor(log2 n),
 //                               __move_median_to_first, __unguarded_partition, heapsort via __partial_sort, __final_insertion_sort);
 //                               the other lanes load the keys and write the kept overlaps out.
-// Everything here is byte / integer work bound by HBM bandwidth (the text) or by latency (the per-pile replay).
+//   k_in_scan                   the small exclusive scans in between (tiles, 256-line blocks, piles)
+// Byte / integer work: the line kernels run at 2 TB/s, the parser is bound by instruction issue (645 warp instructions per line), the
+// per-pile replay by the latency of one lane (profiles/r01_ingest_summary.md).
 #pragma once
 #include "cg_common.cuh"
 #include "k_extract.cuh"      // CgOverlapDev
