@@ -999,9 +999,12 @@ int cg_correct_windows(cg_handle* h, const cg_batch* in, cg_results* out) {
 }
 
 // ---- consensus re-anchoring: alignConsensus for every read of the batch ------------------------------
-static int reanchor_impl(cg_handle* h, const cg_batch* windows, const cg_results* cons, const cg_reads* reads, u32 trim_mer, cg_corrected* out) {
+// on_device: cg_finish_resident — the results, the templates and the reads are taken where cg_upload_piles / cg_run left them in HBM
+// (template lengths from the host copy h_tlen, the reads gathered from the device store); windows->seq_off / reads->read_bases unused.
+static int reanchor_impl(cg_handle* h, const cg_batch* windows, const cg_results* cons, const cg_reads* reads, u32 trim_mer, cg_corrected* out,
+                         bool on_device = false) {
     if (!h || !out) return CG_ERR_INVALID_ARG;
-    if (!windows || !cons || !reads || !reads->read_win_begin || !reads->read_off || !windows->win_seq_begin || !windows->seq_off) {
+    if (!windows || !cons || !reads || !reads->read_win_begin || !reads->read_off || !windows->win_seq_begin || (!on_device && !windows->seq_off)) {
         h->err = "null argument"; return CG_ERR_INVALID_ARG;
     }
     cudaSetDevice(h->device);
@@ -1010,11 +1013,11 @@ static int reanchor_impl(cg_handle* h, const cg_batch* windows, const cg_results
         h->err = "windows, results and reads do not describe the same windows"; return CG_ERR_INVALID_ARG;
     }
     if (W && (!cons->cons_off || !cons->solid_off || !reads->win_pos)) { h->err = "null argument"; return CG_ERR_INVALID_ARG; }
-    if (R && !reads->read_bases) { h->err = "null argument"; return CG_ERR_INVALID_ARG; }
+    if (R && !reads->read_bases && !on_device) { h->err = "null argument"; return CG_ERR_INVALID_ARG; }
     const u32 k = h->p.mer_size;
     // are these the results of the batch still resident on this handle?
-    bool resident = false;
-    if (cons->owner_ && h->ran && h->W == W) {
+    bool resident = on_device;
+    if (!on_device && cons->owner_ && h->ran && h->W == W) {
         std::lock_guard<std::mutex> lk(h->pool_mu);
         for (HostResults* c : h->pool)
             if ((void*)c == cons->owner_ && c->gen == h->run_gen && c->cons_off == cons->cons_off) resident = true;
@@ -1033,7 +1036,7 @@ static int reanchor_impl(cg_handle* h, const cg_batch* windows, const cg_results
             u64 len = cons->cons_off[w + 1] - cons->cons_off[w];
             if (len < k) {                                                     // the raw template stands in (correctionAlignment.cpp:72-74)
                 const u32 s0 = windows->win_seq_begin[w];
-                len = windows->seq_off[s0 + 1] - windows->seq_off[s0];
+                len = on_device ? (u64)h->h_tlen[w] : windows->seq_off[s0 + 1] - windows->seq_off[s0];
                 if (!resident) { tpl_off[w + 1] = len; tpl_bytes += len; }
             }
             if (len > (u64)CG_RA_QMAX) { h->err = "a consensus is longer than 8000 bases"; return CG_ERR_CAPACITY; }
@@ -1060,7 +1063,10 @@ static int reanchor_impl(cg_handle* h, const cg_batch* windows, const cg_results
     CK(h->ra_ctl.ensure(64));
     CK(cudaMemcpyAsync(h->ra_rwb.p, reads->read_win_begin, ((size_t)R + 1) * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->ra_roff.p, reads->read_off, ((size_t)R + 1) * 8, cudaMemcpyHostToDevice, st));
-    if (n_rbases) CK(cudaMemcpyAsync(h->ra_rbases.p, reads->read_bases, n_rbases, cudaMemcpyHostToDevice, st));
+    if (n_rbases && !on_device) CK(cudaMemcpyAsync(h->ra_rbases.p, reads->read_bases, n_rbases, cudaMemcpyHostToDevice, st));
+    if (n_rbases && on_device)                                     // read r = store[pile_read[r]], already normalised by cg_upload_piles
+        CG_LAUNCH(k_reanchor_reads_from_store, std::min<u32>(R, (u32)h->sms * 8), 256, 0, st, (const char*)h->ex_store.as<char>(),
+                  (const u64*)h->ex_store_off.as<u64>(), (const u32*)h->ex_pile_read.as<u32>(), (const u64*)h->ra_roff.as<u64>(), h->ra_rbases.as<char>(), R);
     if (W) CK(cudaMemcpyAsync(h->ra_wpos.p, reads->win_pos, (size_t)W * 4, cudaMemcpyHostToDevice, st));
     if (R) CK(cudaMemcpyAsync(h->ra_order.p, order.data(), (size_t)R * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->ra_head_off.p, head_off.data(), ((size_t)R + 1) * 8, cudaMemcpyHostToDevice, st));
@@ -1174,6 +1180,29 @@ int cg_reanchor_reads(cg_handle* h, const cg_batch* windows, const cg_results* c
 // ---- post-filters: alignConsensus + trimRead + dropRead = the sequence line of every FASTA record --------
 int cg_finish_reads(cg_handle* h, const cg_batch* windows, const cg_results* cons, const cg_reads* reads, uint32_t trim_mer, cg_corrected* out) {
     return reanchor_impl(h, windows, cons, reads, trim_mer, out);
+}
+
+// The tail of the chain cg_upload_piles -> cg_run on one handle without taking the windows, the results or the reads through the host.
+int cg_finish_resident(cg_handle* h, uint32_t trim_mer, cg_corrected* out) {
+    if (!h || !out) return CG_ERR_INVALID_ARG;
+    if (!h->uploaded || !h->ran || !h->ex_valid) { h->err = "cg_finish_resident needs cg_upload_piles and cg_run on this handle"; return CG_ERR_STATE; }
+    cudaSetDevice(h->device);
+    cudaStream_t st = h->lane[0].stream;
+    const u32 W = h->W, R = (u32)h->ex_pile_read_h.size();
+    std::vector<u64> cons_off((size_t)W + 1, 0), roff((size_t)R + 1, 0);
+    if (W) CK(cudaMemcpyAsync(cons_off.data(), h->o_len.p, (size_t)W * 8, cudaMemcpyDeviceToHost, st));   // start offsets of the consensuses
+    CK(cudaStreamSynchronize(st));
+    cons_off[W] = h->o_cons_n;
+    for (u32 r = 0; r < R; ++r) {
+        const u32 q = h->ex_pile_read_h[r];
+        roff[r + 1] = roff[r] + (h->ex_store_off_h[q + 1] - h->ex_store_off_h[q]);
+    }
+    u32 zero = 0;
+    cg_batch wb = {W, h->h_wsb.data(), nullptr, nullptr};
+    cg_results cr{};
+    cr.n_windows = W; cr.cons_off = cons_off.data(); cr.solid_off = cons_off.data();   // solid_off: only read when the results are not resident
+    cg_reads rd = {R, h->ex_rwb.data(), roff.data(), nullptr, W ? h->ex_wpos.data() : &zero, h->ex_ws, h->ex_ovl};
+    return reanchor_impl(h, &wb, &cr, &rd, trim_mer, out, true);
 }
 
 int cg_finish_stats(const cg_handle* h, float* kernel_ms) {

@@ -504,6 +504,16 @@ __global__ void __launch_bounds__(256) k_finish_reads(const char* head, const u6
     }
 }
 
+// cg_finish_resident: the reads of the piles, dense, from the device store (read r = store[pile_read[r]])
+__global__ void k_reanchor_reads_from_store(const char* store, const u64* store_off, const u32* pile_read, const u64* read_off, char* out, u32 n_reads) {
+    for (u32 r = blockIdx.x; r < n_reads; r += gridDim.x) {
+        const char* s = store + store_off[pile_read[r]];
+        char* d = out + read_off[r];
+        const u64 n = read_off[r + 1] - read_off[r];
+        for (u64 i = threadIdx.x; i < n; i += blockDim.x) d[i] = s[i];
+    }
+}
+
 // corrected reads, dense: out[out_off[r] ..) <- head slice of read r (from base skip[r] on when the post-filters ran)
 __global__ void k_reanchor_gather(const char* head, const u64* head_off, const u32* skip, const u64* out_off, char* out, u32 n_reads) {
     for (u32 r = blockIdx.x; r < n_reads; r += gridDim.x) {

@@ -24,7 +24,7 @@ EXPORTS = ("cg_abi_version", "cg_device_count", "cg_create", "cg_destroy", "cg_l
            "cg_correct_windows", "cg_free_results", "cg_upload", "cg_run", "cg_download", "cg_stage_ms",
            "cg_get_counters", "cg_run_ms", "cg_chunk_count", "cg_reanchor_reads", "cg_free_corrected", "cg_reanchor_stats",
            "cg_upload_piles", "cg_download_windows", "cg_free_window_set", "cg_extract_stats",
-           "cg_ingest_paf", "cg_free_pile_set", "cg_ingest_stats", "cg_finish_reads", "cg_finish_stats")
+           "cg_ingest_paf", "cg_free_pile_set", "cg_ingest_stats", "cg_finish_reads", "cg_finish_stats", "cg_finish_resident")
 
 
 class ConsentError(RuntimeError):
@@ -80,6 +80,8 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.cg_free_pile_set.argtypes = [C.POINTER(cg_pile_set)]
     lib.cg_ingest_stats.restype = C.c_int
     lib.cg_ingest_stats.argtypes = [H, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_uint64)]
+    lib.cg_finish_resident.restype = C.c_int
+    lib.cg_finish_resident.argtypes = [H, C.c_uint32, C.POINTER(cg_corrected)]
     lib.cg_finish_stats.restype = C.c_int
     lib.cg_finish_stats.argtypes = [H, C.POINTER(C.c_float)]
     lib.cg_finish_reads.restype = C.c_int
@@ -155,6 +157,15 @@ class Corrector:
         live = getattr(results, "_r", None)
         cr = live if live is not None else results_to_c(results)
         self._check(self.lib.cg_finish_reads(self._h, C.byref(cb), C.byref(cr), C.byref(rd), int(trim_mer), C.byref(out)))
+        got = Corrected(out)
+        self.lib.cg_free_corrected(C.byref(out))
+        return got
+
+    def finish_resident(self, trim_mer: int = 1) -> Corrected:
+        """finish_reads for the batch upload_piles() + run() left on the device, with nothing but the corrected reads crossing to the
+        host (no download(), no download_windows())."""
+        out = cg_corrected()
+        self._check(self.lib.cg_finish_resident(self._h, int(trim_mer), C.byref(out)))
         got = Corrected(out)
         self.lib.cg_free_corrected(C.byref(out))
         return got

@@ -287,6 +287,10 @@ int  cg_ingest_stats(const cg_handle* h, float* kernel_ms, float* parse_ms, uint
  * utils.cpp:111-120); it yields "" here. */
 int  cg_finish_reads(cg_handle* h, const cg_batch* windows, const cg_results* cons, const cg_reads* reads,
                      uint32_t trim_mer, cg_corrected* out);
+/* The same for the batch cg_upload_piles + cg_run left resident on this handle, without taking anything through the host on the way:
+ * window consensuses, solid k-mer lists, templates and the reads (pile p = read p of the store) are read where they lie in HBM.
+ * Equals cg_download + cg_download_windows + cg_finish_reads(..., trim_mer, out); only the corrected reads come back. */
+int  cg_finish_resident(cg_handle* h, uint32_t trim_mer, cg_corrected* out);
 /* CUDA-event time (ms) of the post-filter kernel of the last cg_finish_reads. */
 int  cg_finish_stats(const cg_handle* h, float* kernel_ms);
 

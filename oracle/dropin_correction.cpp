@@ -14,8 +14,8 @@
 // With -x phase A's window cutting moves to the device as well (cg_upload_piles): the host only reads the PAF
 // piles (getNextReadPile: parsing, sort, top-maxSupport) and ships the read store once.
 // With -X nothing of processRead / getNextReadPile is left on the host: the PAF text goes to the device as it is
-// (cg_ingest_paf: parsing, grouping, std::sort + top-maxSupport), and trimRead / dropRead run behind the re-anchoring
-// (cg_finish_reads); the host reads two files and prints FASTA records.
+// (cg_ingest_paf: parsing, grouping, std::sort + top-maxSupport), and re-anchoring + trimRead / dropRead run on what cg_run left
+// in HBM (cg_finish_resident); the host reads two files and prints FASTA records.
 // Same command line as bin/CONSENT-correction and bin/CONSENT-polishing (src/main.cpp:27-80; the two reference binaries differ in
 // that processContig runs its windows on the CTPL pool and never trims, src/CONSENT-polishing.cpp:19-111): with -R (contigs in -r,
 // reads in -R, as CONSENT-polish:197 calls it) this binary is the polisher.  tests/test_dropin_example.py runs it on a B200 and
@@ -91,22 +91,20 @@ int main(int argc, char** argv) {
         if (nameBytes.empty()) nameBytes.push_back('x');
         if (store.empty()) store.push_back('A');
         cg_read_names rn = {(uint32_t)names.size(), nameOff.data(), nameBytes.data()};
-        cg_pile_set ps; cg_results res; cg_window_set ws; cg_corrected cor;
+        cg_pile_set ps; cg_corrected cor;
         if (cg_ingest_paf(h, text.data(), text.size(), &rn, maxSupport, &ps) != CG_OK) die("cg_ingest_paf", cg_last_error(h));
         cg_piles piles = {(uint32_t)names.size(), storeOff.data(), store.data(), ps.n_piles, ps.pile_read, ps.pile_qlen, ps.pile_ov_begin, ps.overlaps,
                           minSupport, windowSize, windowOverlap};
         if (cg_upload_piles(h, &piles) != CG_OK) die("cg_upload_piles", cg_last_error(h));
         if (cg_run(h) != CG_OK) die("cg_run", cg_last_error(h));
-        if (cg_download(h, &res) != CG_OK) die("cg_download", cg_last_error(h));
-        if (cg_download_windows(h, 0, &ws) != CG_OK) die("cg_download_windows", cg_last_error(h));
-        if (cg_finish_reads(h, &ws.batch, &res, &ws.reads, doTrimRead ? 1 : 0, &cor) != CG_OK) die("cg_finish_reads", cg_last_error(h));
+        if (cg_finish_resident(h, doTrimRead ? 1 : 0, &cor) != CG_OK) die("cg_finish_resident", cg_last_error(h));
         for (uint32_t p = 0; p < ps.n_piles; ++p)
             if (cor.read_off[p + 1] != cor.read_off[p]) {
                 std::cout << ">" << names[ps.pile_read[p]] << std::endl;
                 std::cout.write(cor.bases + cor.read_off[p], (std::streamsize)(cor.read_off[p + 1] - cor.read_off[p]));
                 std::cout << std::endl;
             }
-        cg_free_corrected(&cor); cg_free_window_set(&ws); cg_free_results(&res); cg_free_pile_set(&ps); cg_destroy(h);
+        cg_free_corrected(&cor); cg_free_pile_set(&ps); cg_destroy(h);
         return 0;
     }
 

@@ -244,6 +244,14 @@ def test_emulated_chain_paf_to_fasta_lines(emu, oracle):
     assert ps.equals(ops) and res.equals(ores)
     assert got.equals(want)
     assert batch.n_windows >= 20
+    # the same tail without the host round trips: nothing but the corrected reads leaves the device
+    for m in (1, 0, 3):
+        assert cor.finish_resident(m).equals(cor.finish_reads(batch, res, reads, m)), m
+    cor.upload_piles(ps.piles(p.store_off, p.store_bases))
+    with pytest.raises(ConsentError):
+        cor.finish_resident(1)                                                       # run() has not been called on the new batch
+    cor.run()
+    assert cor.finish_resident(1).equals(want)                                       # ... and without download() at all
 
 
 # ------------------------------------------------------------------------------------------------ GPU
@@ -299,4 +307,8 @@ def test_gpu_chain_paf_to_fasta_lines(gpu, oracle):
     assert ps.equals(ops) and res.equals(ores) and plain.equals(oplain)
     for m in (1, 4, 0):
         assert cor.finish_reads(batch, res, reads, m).equals(oracle.finish_reads(oplain, m)), m
+        assert cor.finish_resident(m).equals(oracle.finish_reads(oplain, m)), m
     assert batch.n_windows > 4000
+    cor.upload_piles(ps.piles(p.store_off, p.store_bases))
+    cor.run()
+    assert cor.finish_resident(1).equals(oracle.finish_reads(oplain, 1))             # no download() / download_windows() in between

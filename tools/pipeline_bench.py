@@ -22,6 +22,7 @@ from consent_b200.synth import synth_paf, synth_piles  # noqa: E402
 n_reads = int(sys.argv[1]) if len(sys.argv) > 1 else 4000
 cov = float(sys.argv[2]) if len(sys.argv) > 2 else 30.0
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+HOST_TAIL = len(sys.argv) > 4 and sys.argv[4] == "host-tail"
 read_len = 8000
 world = int(os.environ.get("WORLD_SIZE", "1"))
 rank = int(os.environ.get("RANK", "0"))
@@ -46,17 +47,18 @@ def step():
     t.append(time.perf_counter())
     cor.run()
     t.append(time.perf_counter())
-    res = cor.download()
-    t.append(time.perf_counter())
-    batch, reads, _ = cor.download_windows(with_bases=False)
-    t.append(time.perf_counter())
-    got = cor.finish_reads(batch, res, reads, 1)
+    if HOST_TAIL:                                                  # the tail through the host: results, windows and reads come down first
+        res = cor.download()
+        batch, reads, _ = cor.download_windows(with_bases=False)
+        got = cor.finish_reads(batch, res, reads, 1)
+    else:                                                          # cg_finish_resident: only the corrected reads leave the device
+        got = cor.finish_resident(1)
     t.append(time.perf_counter())
     full = gather_corrected(got) if world > 1 else got
     t.append(time.perf_counter())
-    for k, name in enumerate(("ingest", "upload_piles", "run", "download", "download_windows", "finish_reads", "gather")):
+    for k, name in enumerate(("ingest", "upload_piles", "run", "finish", "gather")):
         phase[name] = round(t[k + 1] - t[k], 4)
-    return batch.n_windows, p1 - p0, full
+    return int(cor.counters()["windows"]), p1 - p0, full
 
 
 for _ in range(2):
@@ -80,7 +82,8 @@ if rank == 0:
     sec = max(float(v[0]) for v in allv)
     Wt = int(sum(float(v[1]) for v in allv))
     import hashlib
-    print(json.dumps({"pipeline": "cg_ingest_paf -> cg_upload_piles -> cg_run -> cg_download -> cg_download_windows -> cg_finish_reads -> gather",
+    print(json.dumps({"pipeline": ("cg_ingest_paf -> cg_upload_piles -> cg_run -> cg_download -> cg_download_windows -> cg_finish_reads -> gather" if HOST_TAIL
+                                   else "cg_ingest_paf -> cg_upload_piles -> cg_run -> cg_finish_resident -> gather"),
                       "n_gpus": world, "reads": n_reads, "coverage": cov, "paf_bytes": len(text), "windows": Wt,
                       "windows_per_rank": [int(v[1]) for v in allv], "s_per_step": sec, "reads_per_s": n_reads / sec, "windows_per_s": Wt / sec,
                       "fasta_records": int((np.diff(full.read_off) > 0).sum()), "corrected_bases": int(full.read_off[-1]),
