@@ -33,6 +33,8 @@ if world > 1:
 p = synth_piles(n_reads, genome_len=int(n_reads * read_len / cov), read_len=read_len, seed=42, max_support=4000)
 text, names = synth_paf(p, seed=42, tie_range=60)
 cor = Corrector(device=local)
+if os.environ.get("CG_CHUNK_WINDOWS"):
+    cor.set_option("chunk_max_windows", int(os.environ["CG_CHUNK_WINDOWS"]))
 
 
 phase = {}
