@@ -33,6 +33,18 @@ import sys
 import threading
 import time
 
+# stdout carries exactly one JSON line.  Libraries print there too (NCCL's "NCCL version ..." banner is a bare printf at
+# NCCL_DEBUG=VERSION), so file descriptor 1 is pointed at stderr for the whole run and the line is written to the saved descriptor.
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+sys.stdout.flush()
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: str) -> None:
+    os.write(_REAL_STDOUT, (line + "\n").encode())
+
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -377,7 +389,7 @@ def main():
                "cpu_baseline": {"value": value, "unit": "windows/s", "cores": cores, "kind": kind,
                                 "sample": f"{n} windows x {args.seqs} seqs per step (first windows of the same stream)"},
                "e2e": {"value": value, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(out), flush=True)
+        emit(json.dumps(out))
         return
 
     import torch
@@ -534,7 +546,7 @@ def main():
            "gpu_launches": launches, "wall_ms_per_step": wall_ms / args.steps,
            "roofline": roofline, "cpu_baseline": cpu,
            "counters_per_step": counters, "reanchor": reanchor, "extract": extract, "ingest": ingest}
-    print(json.dumps(out), flush=True)
+    emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 

@@ -10,6 +10,8 @@ import os
 import sys
 import time
 
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")          # stdout = the JSON line only
+
 sys.path.insert(0, os.environ.get("GRAFT_REPO_ROOT", os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
