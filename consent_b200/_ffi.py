@@ -112,6 +112,15 @@ class cg_counters(C.Structure):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
 
 
+CG_N_KERNELS = 11
+KERNEL_NAMES = ("k_pack", "k_index", "k_chain", "k_split", "k_poa2<C1>", "k_poa2<G>", "k_poa2<W1>", "k_poa2<W2>", "k_poa", "k_polish", "k_out")
+
+
+class cg_kernel_stats(C.Structure):
+    _fields_ = [("ms", C.c_float * CG_N_KERNELS), ("launches", C.c_uint32 * CG_N_KERNELS),
+                ("poa_cells", C.c_uint64 * 4), ("poa_pred_cells", C.c_uint64 * 4)]
+
+
 class cg_synth_spec(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("first_window", C.c_uint32), ("n_windows", C.c_uint32),
                 ("n_seqs", C.c_uint32), ("truth_len", C.c_uint32),

@@ -103,6 +103,7 @@ struct CgPoaScratch {     // one per resident POA warp (global memory, L1/L2 res
 struct CgCountersDev {
     u64 anchors, regions, poa_graphs, alignments, dp_cells, dp_pred_cells, solid_kmers, consensus_bytes, fallback_windows;
     u64 sequences, bases, windows;
+    u64 tier_cells[4], tier_pred[4];      // k_poa2 tiers C1, G, W1, W2
 };
 
 struct CgChunk {

@@ -79,6 +79,8 @@ struct HostResults {
 
 // One timed stage = a pair of events on the lane's stream; collected after the final sync of cg_run.
 struct StageSpan { int stage; cudaEvent_t a, b; };
+// One timed kernel launch (or a short run of launches of one kind): events on the stream the kernel runs on.
+struct KernelSpan { int kind; cudaEvent_t a, b; u32 launches; };
 
 // A lane = everything one chunk needs while it is in flight: its stream(s), workspaces and pinned control words.
 // Two lanes alternate over the chunks of a batch (chunk i on lane i % 2, each driven by its own host thread), so the
@@ -103,6 +105,7 @@ struct Lane {
     float stage_ms[CG_N_STAGES]{};
     u32 stage_launches[CG_N_STAGES]{};
     std::vector<StageSpan> spans;
+    std::vector<KernelSpan> kspans;
     std::vector<cudaEvent_t> evpool;
     size_t pool_at = 0;
 };
@@ -137,6 +140,7 @@ struct cg_handle {
     std::vector<ChunkPlan> chunks;
     bool uploaded = false, ran = false, planned_ramp = false;
     // POA tiers
+    cg_kernel_stats kstats{};
     std::mutex tier_mu;                  // the last-resort scratch is shared by the lanes
     PoaTier tier[3];                     // k_poa.cuh: global-memory tiers without an in-degree limit (the last resort); [0] unused
     u32 c1_warps = 0, g_warps = 0, w1_warps = 0, w2_warps = 0;   // resident warps of the k_poa2.cuh tiers
@@ -323,6 +327,8 @@ int run_chunk(cg_handle* h, Lane& L, size_t ci) {
     };
     auto span_begin = [&](int stage) { StageSpan sp{stage, ev(), ev()}; cudaEventRecord(sp.a, st); L.spans.push_back(sp); };
     auto span_end = [&]() { cudaEventRecord(L.spans.back().b, st); };
+    auto kbegin = [&](int kind, cudaStream_t ks, u32 n = 1) { KernelSpan sp{kind, ev(), ev(), n}; cudaEventRecord(sp.a, ks); L.kspans.push_back(sp); };
+    auto kend = [&](cudaStream_t ks) { cudaEventRecord(L.kspans.back().b, ks); };
 
     // ---- workspaces
     CKL(L.pwords.ensure((cp.nwords + 16) * 4)); CKL(L.ptags.ensure((cp.nwords + 16) * 4));
@@ -383,14 +389,18 @@ int run_chunk(cg_handle* h, Lane& L, size_t ci) {
     }
     CKL(cudaMemsetAsync(L.pwords.as<u32>() + cp.nwords, 0, 16 * 4, st));
     CKL(cudaMemsetAsync(L.ptags.as<u32>() + cp.nwords, 0xff, 16 * 4, st));
+    kbegin(CG_K_PACK, st, 3);
     CG_LAUNCH(k_plan, (nwin + 127) / 128, 128, 0, st, c);
     CG_LAUNCH(k_scan, 5, 1024, 1024 * sizeof(u64), st, c.off_solid, c.off_slot, c.off_pos, c.off_reg, c.off_arena, nwin);
     CG_LAUNCH(k_pack, nwin, 256, 0, st, c);
+    kend(st);
     L.stage_launches[CG_STAGE_PACK] += 3;
     span_end();
 
     span_begin(CG_STAGE_INDEX);
+    kbegin(CG_K_INDEX, st);
     CG_LAUNCH(k_index, nwin, CG_IDX_THREADS, CG_IDX_SMEM_BYTES, st, c);
+    kend(st);
     L.stage_launches[CG_STAGE_INDEX] += 1;
     span_end();
 
@@ -398,13 +408,17 @@ int run_chunk(cg_handle* h, Lane& L, size_t ci) {
     const size_t smem_cap = (size_t)h->smem_optin;
     const size_t chain_full = std::min(cg_chain_smem(cp.max_tk, cp.max_n), smem_cap);     // windows that need more are flagged by the kernel
     const size_t chain_small = std::min(cg_chain_smem(std::min<u32>(cp.max_tk, 192u), cp.max_n), chain_full);
+    kbegin(CG_K_CHAIN, st, chain_full > chain_small ? 2 : 1);
     CG_LAUNCH(k_chain, nwin, CG_CHAIN_THREADS, chain_small, st, c, (u32)chain_small, 0u);
     if (chain_full > chain_small) CG_LAUNCH(k_chain, nwin, CG_CHAIN_THREADS, chain_full, st, c, (u32)chain_full, 1u);
+    kend(st);
     L.stage_launches[CG_STAGE_CHAIN] += chain_full > chain_small ? 2 : 1;
     span_end();
 
     span_begin(CG_STAGE_SPLIT);
+    kbegin(CG_K_SPLIT, st);
     CG_LAUNCH(k_split, nwin, CG_SPLIT_THREADS, 0, st, c);
+    kend(st);
     L.stage_launches[CG_STAGE_SPLIT] += 1;
     span_end();
 
@@ -419,8 +433,13 @@ int run_chunk(cg_handle* h, Lane& L, size_t ci) {
     CKL(L.w1_mem.ensure(CgPoa2Lay<CgPoa2W1>::scratch_per_warp * (size_t)h->w1_warps));
     CKL(L.w2_mem.ensure(CgPoa2Lay<CgPoa2W2>::scratch_per_warp * (size_t)h->w2_warps));
 #define CG_POA2_LAUNCH(TIER, mem, warps, stream, jin, qin, jout, qout)                                                          \
+    kbegin(TIER::VCAP <= 128 ? CG_K_POA_C1 : TIER::VCAP <= 254 ? CG_K_POA_G : TIER::VCAP <= 1024 ? CG_K_POA_W1 : CG_K_POA_W2, stream); \
     CG_LAUNCH(k_poa2<TIER>, ((warps) + TIER::WARPS - 1) / TIER::WARPS, TIER::WARPS * 32, CgPoa2Lay<TIER>::cta_bytes, stream, c, \
-              (mem), (warps), (const uint2*)(jin), q + 4 * (qin), (jout), q + 4 * (qout))
+              (mem), (warps), (const uint2*)(jin), q + 4 * (qin), (jout), q + 4 * (qout));                                      \
+    kend(stream)
+    // The three tiers side by side (the wide, long-running jobs are launched first so that they overlap the bulk of the small ones).
+    // (Measured and dropped: G first and ONE wide launch afterwards over its own queue plus G's overflow — the wide tier is latency
+    // bound and G's work hides inside it: 165 k -> 158 k windows/s at 20 sequences per window.)
     CKL(cudaEventRecord(L.ev_fork, st));
     for (int i = 0; i < 2; ++i) CKL(cudaStreamWaitEvent(L.s_poa[i], L.ev_fork, 0));
     CG_POA2_LAUNCH(CgPoa2W1, L.w1_mem.as<u8>(), h->w1_warps, L.s_poa[1], c.jobs_w, 2, jobs_q5, 5);
@@ -448,8 +467,8 @@ int run_chunk(cg_handle* h, Lane& L, size_t ci) {
     CKL(cudaMemcpyAsync(L.h_ctl, ctl, CTL_WORDS * sizeof(u32), cudaMemcpyDeviceToHost, st));
     CKL(cudaStreamSynchronize(st));
     if (getenv("CG_DEBUG"))
-        fprintf(stderr, "[consent_b200] chunk w0=%u nwin=%u POA jobs: C1 %u+%u, G %u+%u, W1 %u | re-queued: ->G %u, ->W1 %u, ->W2 %u, ->k_poa %u\n",
-                cp.w0, nwin, L.h_ctl[CTL_Q + 0], L.h_ctl[CTL_Q + 2], L.h_ctl[CTL_Q + 4], L.h_ctl[CTL_Q + 6], L.h_ctl[CTL_Q + 8],
+        fprintf(stderr, "[consent_b200] chunk w0=%u nwin=%u POA jobs: C1 %u+%u, G %u+%u, W1 %u+%u | re-queued: ->G %u, ->W1 %u, ->W2 %u, ->k_poa %u\n",
+                cp.w0, nwin, L.h_ctl[CTL_Q + 0], L.h_ctl[CTL_Q + 2], L.h_ctl[CTL_Q + 4], L.h_ctl[CTL_Q + 6], L.h_ctl[CTL_Q + 8], L.h_ctl[CTL_Q + 10],
                 L.h_ctl[CTL_Q + 12], L.h_ctl[CTL_Q + 16], L.h_ctl[CTL_Q + 20], L.h_ctl[CTL_Q + 24]);
     if (L.h_ctl[CTL_Q + 24]) {
         std::lock_guard<std::mutex> lk(h->tier_mu);         // one lane at a time on the shared last-resort scratch
@@ -460,9 +479,11 @@ int run_chunk(cg_handle* h, Lane& L, size_t ci) {
             if (h->tier[t].warps == 0) { L.err = "a POA job outgrew the largest enabled scratch tier"; return CG_ERR_CAPACITY; }
             { int rc = ensure_tier(L, h->tier[t]); if (rc) return rc; }
             span_begin(CG_STAGE_POA);
+            kbegin(CG_K_POA_LAST, st);
             CG_LAUNCH(k_poa, (h->tier[t].warps + CG_POA_WARPS_PER_CTA - 1) / CG_POA_WARPS_PER_CTA, CG_POA_THREADS, 0, st, c,
                       h->tier[t].desc.as<CgPoaScratch>(), h->tier[t].warps, (const uint2*)q_in, q + 4 * (t + 5), t < 2 ? q_out : (uint2*)nullptr,
                       q + 4 * (t + 6));
+            kend(st);
             L.stage_launches[CG_STAGE_POA] += 1;
             span_end();
             CKL(cudaMemcpyAsync(L.h_ctl, ctl, CTL_WORDS * sizeof(u32), cudaMemcpyDeviceToHost, st));
@@ -473,8 +494,10 @@ int run_chunk(cg_handle* h, Lane& L, size_t ci) {
 
     // ---- stitched lengths -> work slices
     span_begin(CG_STAGE_STITCH);
+    kbegin(CG_K_OUT, st, 2);
     CG_LAUNCH(k_stitch_len, (nwin + 127) / 128, 128, 0, st, c, off_fin);
     CG_LAUNCH(k_scan, 1, 1024, 1024 * sizeof(u64), st, off_fin, (u64*)nullptr, (u64*)nullptr, (u64*)nullptr, (u64*)nullptr, nwin);
+    kend(st);
     L.stage_launches[CG_STAGE_STITCH] += 2;
     span_end();
     u64 fin_total = 0;
@@ -484,13 +507,17 @@ int run_chunk(cg_handle* h, Lane& L, size_t ci) {
     c.fin = L.fin.as<u8>();
 
     span_begin(CG_STAGE_POLISH);
+    kbegin(CG_K_POLISH, st);
     CG_LAUNCH(k_polish, (nwin + CG_POLISH_WARPS_PER_CTA - 1) / CG_POLISH_WARPS_PER_CTA, CG_POLISH_THREADS, 0, st, c, (const u64*)off_fin);
+    kend(st);
     L.stage_launches[CG_STAGE_POLISH] += 1;
     span_end();
 
     span_begin(CG_STAGE_STITCH);
+    kbegin(CG_K_OUT, st, 2);
     CG_LAUNCH(k_out_sizes, (nwin + 127) / 128, 128, 0, st, c, cons_off, solid_off);
     CG_LAUNCH(k_scan, 2, 1024, 1024 * sizeof(u64), st, cons_off, solid_off, (u64*)nullptr, (u64*)nullptr, (u64*)nullptr, nwin);
+    kend(st);
     L.stage_launches[CG_STAGE_STITCH] += 2;
     span_end();
     u64 tot[2] = {0, 0};
@@ -518,9 +545,11 @@ int run_chunk(cg_handle* h, Lane& L, size_t ci) {
         }
     }
     span_begin(CG_STAGE_STITCH);
+    kbegin(CG_K_OUT, st);
     CG_LAUNCH(k_gather, nwin, 256, 0, st, c, (const u64*)off_fin, (const u64*)cons_off, (const u64*)solid_off,
               h->o_cons.as<u8>() + h->o_cons_n, h->o_sk.as<u32>() + h->o_solid_n, h->o_sc.as<u32>() + h->o_solid_n,
               h->o_status.as<u8>() + cp.w0, h->o_cons_n, h->o_solid_n, h->o_len.as<u64>() + cp.w0, h->o_nsol.as<u64>() + cp.w0);
+    kend(st);
     L.stage_launches[CG_STAGE_STITCH] += 1;
     span_end();
     if (h->stream_out) { int rc = stream_out_chunk(h, L, st, cp, tot[0], tot[1]); if (rc) return rc; }
@@ -621,6 +650,29 @@ extern "C" {
 
 int cg_abi_version(void) { return CG_ABI_VERSION; }
 
+#ifdef CG_POA_TIMING
+// debug builds only: per-job phase clocks of the POA tiers, as text
+int cg_debug_dump_jobs(const char* path) {
+    u32 n = 0;
+    cudaMemcpyFromSymbol(&n, cg_dbg_njobs, sizeof n);
+    n = std::min<u32>(n, 1u << 16);
+    std::vector<CgJobTiming> J(n);
+    if (n) cudaMemcpyFromSymbol(J.data(), cg_dbg_jobs, sizeof(CgJobTiming) * n);
+    FILE* f = fopen(path, "w");
+    if (!f) return -1;
+    fprintf(f, "tier w rg nseg V maxL t0 t1 dp maxtie traceback update splice dfs setup vote\n");
+    for (const CgJobTiming& j : J) {
+        fprintf(f, "%u %u %u %u %u %u %lld %lld", j.tier, j.w, j.rg, j.nseg, j.V, j.maxL, j.t0, j.t1);
+        for (int q = 0; q < 8; ++q) fprintf(f, " %lld", j.ph[q]);
+        fprintf(f, "\n");
+    }
+    fclose(f);
+    u32 zero = 0;
+    cudaMemcpyToSymbol(cg_dbg_njobs, &zero, sizeof zero);
+    return (int)n;
+}
+#endif
+
 int cg_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
@@ -670,7 +722,9 @@ int cg_create(int device, const cg_params* params, cg_handle** out) {
     ok = ok && cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin) == cudaSuccess;
     if (!ok) { g_create_err = std::string("CUDA initialisation failed: ") + cudaGetErrorString(cudaGetLastError()); cg_destroy(h); return CG_ERR_CUDA; }
     ok = cudaFuncSetAttribute(k_poa2<CgPoa2C1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CgPoa2Lay<CgPoa2C1>::cta_bytes) == cudaSuccess &&
-         cudaFuncSetAttribute(k_poa2<CgPoa2GT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CgPoa2Lay<CgPoa2GT>::cta_bytes) == cudaSuccess;
+         cudaFuncSetAttribute(k_poa2<CgPoa2GT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CgPoa2Lay<CgPoa2GT>::cta_bytes) == cudaSuccess &&
+         cudaFuncSetAttribute(k_poa2<CgPoa2W1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CgPoa2Lay<CgPoa2W1>::cta_bytes) == cudaSuccess &&
+         cudaFuncSetAttribute(k_poa2<CgPoa2W2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CgPoa2Lay<CgPoa2W2>::cta_bytes) == cudaSuccess;
     if (!ok) { g_create_err = std::string("CUDA initialisation failed: ") + cudaGetErrorString(cudaGetLastError()); cg_destroy(h); return CG_ERR_CUDA; }
     // POA tiers: resident warps of the k_poa2.cuh tiers; k_poa.cuh's global-memory tiers {nodes, edges, max segment length,
     // matrix cells, resident warps} are the last resort.
@@ -858,7 +912,7 @@ int run_impl(cg_handle* h) {
     CK(cudaEventRecord(h->ev_run0, h->lane[0].stream));
     for (int li = 0; li < n_lanes; ++li) {
         Lane& L = h->lane[li];
-        L.spans.clear(); L.pool_at = 0; L.err.clear(); L.rc = CG_OK; L.tail_recorded = false;
+        L.spans.clear(); L.kspans.clear(); L.pool_at = 0; L.err.clear(); L.rc = CG_OK; L.tail_recorded = false;
         memset(L.stage_ms, 0, sizeof L.stage_ms); memset(L.stage_launches, 0, sizeof L.stage_launches);
         CK(cudaMemsetAsync(L.ctl.p, 0, CTL_WORDS * sizeof(u32) + sizeof(CgCountersDev), L.stream));
         if (li) CK(cudaStreamWaitEvent(L.stream, h->ev_run0, 0));      // nothing of this run starts before its first event
@@ -894,6 +948,7 @@ int run_impl(cg_handle* h) {
         }
     }
     h->run_ms = 0;
+    memset(&h->kstats, 0, sizeof h->kstats);
     CgCountersDev sum{};
     for (int li = 0; li < n_lanes; ++li) {
         Lane& L = h->lane[li];
@@ -902,8 +957,10 @@ int run_impl(cg_handle* h) {
         h->run_ms = std::max(h->run_ms, ms);
         for (const StageSpan& sp : L.spans) { float m2 = 0; cudaEventElapsedTime(&m2, sp.a, sp.b); h->stage_ms[sp.stage] += m2; }
         for (int i = 0; i < CG_N_STAGES; ++i) h->stage_launches[i] += L.stage_launches[i];
+        for (const KernelSpan& sp : L.kspans) { float m2 = 0; cudaEventElapsedTime(&m2, sp.a, sp.b); h->kstats.ms[sp.kind] += m2; h->kstats.launches[sp.kind] += sp.launches; }
         CgCountersDev cd{};
         CK(cudaMemcpy(&cd, L.ctl.as<u32>() + CTL_WORDS, sizeof cd, cudaMemcpyDeviceToHost));
+        for (int t = 0; t < 4; ++t) { h->kstats.poa_cells[t] += cd.tier_cells[t]; h->kstats.poa_pred_cells[t] += cd.tier_pred[t]; }
         sum.anchors += cd.anchors; sum.regions += cd.regions; sum.poa_graphs += cd.poa_graphs; sum.alignments += cd.alignments;
         sum.dp_cells += cd.dp_cells; sum.dp_pred_cells += cd.dp_pred_cells; sum.solid_kmers += cd.solid_kmers;
         sum.consensus_bytes += cd.consensus_bytes; sum.fallback_windows += cd.fallback_windows;
@@ -1579,6 +1636,12 @@ int cg_extract_stats(const cg_handle* h, float* kernel_ms, float* copy_ms, uint6
 int cg_stage_ms(const cg_handle* h, float ms[CG_N_STAGES], uint32_t launches[CG_N_STAGES]) {
     if (!h) return CG_ERR_INVALID_ARG;
     for (int i = 0; i < CG_N_STAGES; ++i) { if (ms) ms[i] = h->stage_ms[i]; if (launches) launches[i] = h->stage_launches[i]; }
+    return CG_OK;
+}
+
+int cg_get_kernel_stats(const cg_handle* h, cg_kernel_stats* out) {
+    if (!h || !out) return CG_ERR_INVALID_ARG;
+    *out = h->kstats;
     return CG_OK;
 }
 

@@ -92,11 +92,18 @@ template <class IdT_, int STORE_, u32 VCAP_, u32 HCELLS_, u32 LCAP_, u32 SEGCAP_
     static constexpr u32 VCAP = VCAP_, HCELLS = HCELLS_, LCAP = LCAP_, SEGCAP = SEGCAP_, WARPS = WARPS_, CTAS_PER_SM = CTAS_;
     static constexpr u32 SCAP = 3 * VCAP_ + 8, ALNCAP = VCAP_ + LCAP_;
     static constexpr u32 SEQCAP = LCAP_ < 512u ? LCAP_ : 512u;        // segments up to this long are staged next to the graph
+    // all-global ("wide") tiers: score rows are stored lane-contiguous (k_poa2 wide layout below); segments of up to 64 * CHF - 1
+    // bases run the register-resident DP with the query profile in shared memory, longer ones the any-length variant
+    static constexpr u32 CHF = 10;
+    static constexpr u32 CHMAX = (LCAP_ + 64u) / 64u;                  // 64-column blocks of the longest segment
 };
 typedef CgPoa2Tier<u8, CG_P2_ALL_SMEM, 128, 2048, 64, 192, 4, 5> CgPoa2C1;
 typedef CgPoa2Tier<u8, CG_P2_H_GLOBAL, 254, 30976, 120, 192, 4, 5> CgPoa2GT;
-typedef CgPoa2Tier<u16, CG_P2_ALL_GLOBAL, 1024, 512u << 10, 1024, 1024, 4, 4> CgPoa2W1;    // 16 warps per SM: +36 % at N = 20, +21 % at N = 40 over 8 (tools/poa_tier_sweep.py)
-typedef CgPoa2Tier<u16, CG_P2_ALL_GLOBAL, 4096, 4u << 20, 2048, 4096, 4, 2> CgPoa2W2;
+#ifndef CG_W1_CTAS
+#define CG_W1_CTAS 6
+#endif
+typedef CgPoa2Tier<u16, CG_P2_ALL_GLOBAL, 1024, 672u << 10, 1024, 1024, 4, CG_W1_CTAS> CgPoa2W1;    // 24 warps per SM (9 KB of shared memory per warp); 1025 rows x 640 columns
+typedef CgPoa2Tier<u16, CG_P2_ALL_GLOBAL, 4096, 4u << 20, 2048, 4096, 4, 1> CgPoa2W2;    // 42 KB of shared memory per warp
 
 template <class T> struct CgPoa2Lay {
     typedef CgIdPack<typename T::IdT> Pk;
@@ -115,7 +122,13 @@ template <class T> struct CgPoa2Lay {
                             h_bytes = r16(2 * (size_t)T::HCELLS + 16),
                             per_warp = T::STORE == CG_P2_H_GLOBAL ? o_H : o_H + h_bytes,         // the graph slice (+ matrix unless it is apart)
                             scratch_per_warp = T::STORE == CG_P2_ALL_SMEM ? 0 : T::STORE == CG_P2_H_GLOBAL ? h_bytes : per_warp;
-    static constexpr size_t cta_bytes = T::SMEM ? per_warp * T::WARPS : 0;
+    // wide tiers, shared memory per warp: the row descriptors' low words (letter | in-degree << 8 | first predecessor row << 16) and
+    // the query profile (4 letters x CHF blocks x 32 lanes of packed scores)
+    // (k_poa2_wide.cuh: CgWideRd).  The profile's bytes double as the DFS's marks / check flags and the top of its stack.
+    static constexpr size_t RDB = T::VCAP <= 1024 ? 4 : 8, DFS_STK = 512;
+    static constexpr size_t o_wrd = 0, o_wprof = RDB * (size_t)T::VCAP,
+                            wide_bytes = o_wprof + mx(512 * (size_t)T::CHF, 2 * (size_t)T::VCAP + sizeof(typename Pk::Item) * DFS_STK);
+    static constexpr size_t cta_bytes = T::SMEM ? per_warp * T::WARPS : wide_bytes * T::WARPS;
 };
 
 // meta word of a node: low field = nal (bits 0-1) | "sequence 0 passes here" (bit 2) | in-degree (bits 3-7); then 3 aligned ids
@@ -125,6 +138,9 @@ template <class T> struct CgPoa2G {
     typedef typename T::IdT IdT;
     u32 wo;                     // graph in shared memory: byte offset of this warp's slice (every access an LDS/STS with an immediate offset)
     u8* base;                   // this warp's global scratch slice: everything (all-global tiers) or the matrix alone
+    u32 ws;                     // wide tiers: byte offset of this warp's shared-memory slice (row descriptors, query profile)
+    __device__ __forceinline__ u8* wrd() const { return cg_smem_base() + ws + Lay::o_wrd; }
+    __device__ __forceinline__ u32* prof() const { return (u32*)(cg_smem_base() + ws + Lay::o_wprof); }
     __device__ __forceinline__ u8* b() const { return T::SMEM ? cg_smem_base() + wo : base; }
     __device__ __forceinline__ typename Pk::Vec& pred(u32 i) const { return ((typename Pk::Vec*)(b() + Lay::o_pred))[i]; }
     __device__ __forceinline__ typename Pk::Vec& prow(u32 i) const { return ((typename Pk::Vec*)(b() + Lay::o_prow))[i]; }
@@ -134,8 +150,12 @@ template <class T> struct CgPoa2G {
     __device__ __forceinline__ typename Pk::Seg& seg(u32 i) const { return ((typename Pk::Seg*)(b() + Lay::o_seg))[i]; }
     __device__ __forceinline__ u16& nseq(u32 i) const { return ((u16*)(b() + Lay::o_nseq))[i]; }
     __device__ __forceinline__ typename Pk::Item& work(u32 i) const { return ((typename Pk::Item*)(b() + Lay::o_work))[i]; }
-    __device__ __forceinline__ u8& marks(u32 i) const { return b()[Lay::o_tmp + i]; }
-    __device__ __forceinline__ u8& check(u32 i) const { return b()[Lay::o_tmp + T::VCAP + i]; }
+    __device__ __forceinline__ u8& marks(u32 i) const { return T::STORE == CG_P2_ALL_GLOBAL ? ((u8*)prof())[i] : b()[Lay::o_tmp + i]; }
+    __device__ __forceinline__ u8& check(u32 i) const { return T::STORE == CG_P2_ALL_GLOBAL ? ((u8*)prof())[T::VCAP + i] : b()[Lay::o_tmp + T::VCAP + i]; }
+    __device__ __forceinline__ typename Pk::Item& stk(u32 i) const {         // DFS stack: its top lives in shared memory on the wide tiers
+        if (T::STORE == CG_P2_ALL_GLOBAL && i < Lay::DFS_STK) return ((typename Pk::Item*)((u8*)prof() + 2 * T::VCAP))[i];
+        return work(i);
+    }
     __device__ __forceinline__ IdT& nodeq(u32 i) const { return ((IdT*)(b() + Lay::o_tmp))[i]; }
     __device__ __forceinline__ IdT& posq(u32 i) const { return ((IdT*)(b() + Lay::o_tmp))[T::LCAP + i]; }
     __device__ __forceinline__ IdT& anchq(u32 i) const { return ((IdT*)(b() + Lay::o_tmp))[2 * T::LCAP + i]; }
@@ -162,15 +182,15 @@ __device__ __forceinline__ u32 cg_lt_mask() { return (1u << cg_lane()) - 1u; }
 
 // ------------------------------------------------------------------ exact order: spoa's DFS (graph.cpp:294-354), lane 0
 // Same walk as cg_poa_toposort (k_poa.cuh) on the packed records.  marks/check are pre-initialised (0 / 1) by the warp.
-template <class T> __device__ __forceinline__ bool cg_poa2_dfs(const CgPoa2G<T>& s, u32 V) {
+template <class T> __device__ CG_NOINLINE bool cg_poa2_dfs(const CgPoa2G<T>& s, u32 V) {
     CG_P2_TYPES;
     constexpr u32 FIN = 1u << W;
     u32 nrank = 0, sp = 0;
     for (u32 i = 0; i < V; ++i) {
         if (s.marks(i) != 0) continue;
-        s.work(sp++) = (ItemT)i;
+        s.stk(sp++) = (ItemT)i;
         while (sp != 0) {
-            const u32 top = s.work(sp - 1);
+            const u32 top = s.stk(sp - 1);
             const u32 id = top & IDNONE;
             bool finish = (top & FIN) != 0;
             const MetaT m = s.meta(id);
@@ -183,16 +203,16 @@ template <class T> __device__ __forceinline__ bool cg_poa2_dfs(const CgPoa2G<T>&
                 if (sp + deg + 3 > T::SCAP) return false;
                 for (u32 e = 0; e < deg; ++e) {
                     const u32 b = Pk::get(P, e);
-                    if (s.marks(b) != 2) s.work(sp++) = (ItemT)b;
+                    if (s.marks(b) != 2) s.stk(sp++) = (ItemT)b;
                 }
                 if (s.check(id)) {
                     for (u32 a = 0; a < nal; ++a) {
                         const u32 aid = (u32)((m >> (W * (a + 1))) & IDMASK);
-                        if (s.marks(aid) != 2) { s.work(sp++) = (ItemT)aid; s.check(aid) = 0; }
+                        if (s.marks(aid) != 2) { s.stk(sp++) = (ItemT)aid; s.check(aid) = 0; }
                     }
                 }
                 if (sp == sp0) finish = true;
-                else { s.marks(id) = 1; s.work(sp0 - 1) = (ItemT)(id | FIN); }
+                else { s.marks(id) = 1; s.stk(sp0 - 1) = (ItemT)(id | FIN); }
             }
             if (finish) {
                 s.marks(id) = 2;
@@ -496,66 +516,7 @@ __device__ __forceinline__ i32 cg_poa2_dp2(const CgPoa2G<T>& s, u32 V, const u8*
     return lo > hi ? lo : hi;
 }
 
-// Any length: packed chunks of 64 columns, every row read back from the stored matrix (the wide tiers' long segments).
-template <class T>
-__device__ __forceinline__ i32 cg_poa2_dp_any(const CgPoa2G<T>& s, u32 V, const u8* seq, u32 L, u32 Ws, CgPoa2Max& trk) {
-    CG_P2_TYPES;
-    static_assert(9u * T::LCAP + 64u < 32767u, "packed 16-bit DP: score (<= 5 L) + 4 j must fit a signed halfword");
-    const u32 lane = cg_lane(), Wd = L + 1;
-    i16* H = s.H();
-    for (u32 j = lane; j < Ws; j += 32) H[j] = 0;
-    __syncwarp();
-    u32 bv2 = 0;
-    for (u32 r = 0; r < V; ++r) {
-        const u32 d = (u32)s.rdesc(r);
-        const u32 ch = d & 0xffu;
-        const u32 deg = (d >> 8) & 0xffu, np = deg ? deg : 1u;
-        const VecT pr = s.prow(r);
-        u32* row = (u32*)(H + (size_t)(r + 1) * Ws);
-        u32 carry = 0, rowmax = 0;
-        for (u32 jb = 0; jb < Wd; jb += 64) {
-            const u32 j0 = jb + 2 * lane, j1 = j0 + 1;
-            const bool act = j0 < Wd;
-            u32 val = 0;
-            if (act) {
-                const u32 q0 = j0 >= 1 ? seq[j0 - 1] : 0u, q1 = j1 < Wd ? seq[j1 - 1] : 0u;
-                const u32 sc = (q0 == ch ? 5u : 0xfff6u) | (q1 == ch ? 0x00050000u : 0xfff60000u);
-#pragma unroll 1
-                for (u32 e = 0; e < np; ++e) {
-                    const i16* prow = H + (size_t)(deg ? Pk::get(pr, e) : 0u) * Ws + j0;
-                    const u32 h01 = *(const u32*)prow;
-                    const u32 hm1 = j0 == 0 ? 0u : (u32)(u16)prow[-1];
-                    val = cg_vmax2(val, cg_viaddmax2_relu(hm1 | (h01 << 16), sc, cg_vadd2(h01, 0xfffcfffcu)));
-                }
-            }
-            const u32 keep = j0 == 0 ? 0xffff0000u : 0xffffffffu;
-            const u32 j4 = (4 * j0) | ((4 * j1) << 16), nj4 = ((0u - 4 * j0) & 0xffffu) | ((0u - 4 * j1) << 16);
-            u32 u = cg_vadd2(val & keep, j4);
-            u = cg_vmax2(u, u << 16);
-            u32 x = __byte_perm(u, 0, 0x3232);
-#pragma unroll
-            for (int dd = 1; dd < 32; dd <<= 1) x = cg_vmax2(x, __shfl_up_sync(CG_FULL, x, dd));
-            u32 e2 = __shfl_up_sync(CG_FULL, x, 1);
-            if (lane == 0) e2 = 0;
-            e2 = cg_vmax2(e2, carry);
-            carry = cg_vmax2(carry, __shfl_sync(CG_FULL, x, 31));
-            const u32 h = cg_vadd2(cg_vmax2(u, e2), nj4) & keep;
-            if (act) {
-                row[jb / 2 + lane] = h;
-                const u32 hm = h & ((j0 < Wd ? 0xffffu : 0u) | (j1 < Wd ? 0xffff0000u : 0u));
-                if (T::POSTPASS_MAX) bv2 = cg_vmax2(bv2, hm); else rowmax = cg_vmax2(rowmax, hm);
-            }
-        }
-        if (!T::POSTPASS_MAX) {
-            const u32 lo = rowmax & 0xffffu, hi = rowmax >> 16;
-            const i32 m = cg_poa2_track(trk, (i32)(lo > hi ? lo : hi), r + 1);
-            CG_P2_KEEP_ROWMAX(T, s, m, r + 1);
-        }
-        __syncwarp();
-    }
-    const i32 lo = (i32)(i16)(bv2 & 0xffffu), hi = (i32)(i16)(bv2 >> 16);
-    return lo > hi ? lo : hi;
-}
+#include "k_poa2_wide.cuh"
 
 // Where is the maximum M (> 0)?  Lanes over rows, each scanning its row.  Returns the number of rows that hold M; if it is
 // exactly one, (*bi, *bj) is the first cell of that row equal to M (simd_alignment_engine_impl.hpp:860-862).
@@ -583,6 +544,22 @@ __device__ __forceinline__ u32 cg_poa2_find_max(const CgPoa2G<T>& s, u32 V, u32 
     *bi = frow; *bj = fcol;
     return nrows;
 }
+
+// ------------------------------------------------------------------ debug builds (-DCG_POA_TIMING): per-job phase clocks
+#ifdef CG_POA_TIMING
+struct CgJobTiming { u32 tier, w, rg, nseg, V, maxL; long long t0, t1, ph[8]; };   // ph: dp, max/tie, traceback, update, splice+rows, dfs, setup, vote
+__device__ CgJobTiming cg_dbg_jobs[1 << 16];
+__device__ u32 cg_dbg_njobs;
+#define CG_T_DECL long long tph_[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long tlast_ = clock64(); const long long tjob0_ = tlast_
+#define CG_T_MARK(i) do { const long long now_ = clock64(); tph_[i] += now_ - tlast_; tlast_ = now_; } while (0)
+#define CG_T_DONE(a_, b_, c_, d_, e_, f_) do { if (cg_lane() == 0) { const u32 k_ = atomicAdd(&cg_dbg_njobs, 1u); if (k_ < (1u << 16)) { \
+        CgJobTiming& J = cg_dbg_jobs[k_]; J.tier = a_; J.w = b_; J.rg = c_; J.nseg = d_; J.V = e_; J.maxL = f_; J.t0 = tjob0_; J.t1 = clock64(); \
+        for (int q_ = 0; q_ < 8; ++q_) J.ph[q_] = tph_[q_]; } } } while (0)
+#else
+#define CG_T_DECL
+#define CG_T_MARK(i)
+#define CG_T_DONE(a_, b_, c_, d_, e_, f_)
+#endif
 
 // ------------------------------------------------------------------ one job
 // Returns the consensus length, or CG_NONE32 if the tier was outgrown (nothing is committed).
@@ -616,6 +593,8 @@ __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s
 
     u32 V = 0, nseqs = 0, cur = 0, sumdeg = 0;
     bool dfs_valid = false;
+    CG_T_DECL;
+    CG_T_MARK(6);
     u64 j_aln = 0, j_cells = 0, j_pred = 0;
 
     for (u32 si = 0; si < nseg; ++si) {
@@ -630,21 +609,37 @@ __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s
             __syncwarp();
             seq = sb;
         }
-        const u32 Wd = L + 1, Ws = (L + 2) & ~1u;              // columns 0..L; rows are stored with an even stride
+        constexpr bool WIDE = T::STORE == CG_P2_ALL_GLOBAL;    // lane-contiguous rows of 64 CH columns (k_poa2_wide.cuh)
+        u32 CHw = (L + 64u) / 64u;
+#ifdef CG_W1_ONE_CH
+        if (WIDE) CHw = CHw <= 10 ? 10u : CHw;
+#else
+        if (WIDE) CHw = CHw <= 4 ? 4u : CHw <= 7 ? 7u : CHw <= 10 ? 10u : CHw;
+#endif
+        const u32 Wd = L + 1, Ws = WIDE ? 64u * CHw : (L + 2) & ~1u;   // columns 0..L; rows are stored with an even stride
         u32 n_aln = 0;
         if (V != 0) {
             if ((u64)(V + 1) * Ws > (u64)T::HCELLS) return CG_NONE32;
-            i32 bv;
+            i32 bv = 0;
             CgPoa2Max trk;
             trk.M = 0; trk.row = 0; trk.nrows = 0;
-            if (L <= 32 && T::H_SMEM) bv = cg_poa2_dp<1>(s, V, seq, L, Ws);
+            if constexpr (WIDE) {
+                // three block counts only (rows of 256 / 448 / 640 columns): every variant is ~3 KB of code that 24 warps share
+#ifndef CG_W1_ONE_CH
+                if (CHw <= 4) { cg_poa2w_profile(s.prof(), seq, L, 4); cg_poa2w_dp<4>(s, V, trk); }
+                else if (CHw <= 7) { cg_poa2w_profile(s.prof(), seq, L, 7); cg_poa2w_dp<7>(s, V, trk); }
+                else
+#endif
+                if (CHw <= 10) { cg_poa2w_profile(s.prof(), seq, L, 10); cg_poa2w_dp<10>(s, V, trk); }
+                else cg_poa2w_dp_any(s, V, seq, L, CHw, trk);
+            }
+            else if (L <= 32 && T::H_SMEM) bv = cg_poa2_dp<1>(s, V, seq, L, Ws);
             else if (L <= 63) bv = cg_poa2_dp2<1>(s, V, seq, L, Ws, trk);
             else if (T::LCAP > 63 && L <= 127) bv = cg_poa2_dp2<(T::LCAP > 63 ? 2 : 1)>(s, V, seq, L, Ws, trk);
             else if (T::LCAP > 127 && L <= 255) bv = cg_poa2_dp2<(T::LCAP > 127 ? 4 : 1)>(s, V, seq, L, Ws, trk);
             else if (T::LCAP > 255 && L <= 511) bv = cg_poa2_dp2<(T::LCAP > 255 ? 8 : 1)>(s, V, seq, L, Ws, trk);
-            else if (T::LCAP > 511 && L <= 575) bv = cg_poa2_dp2<(T::LCAP > 511 ? 9 : 1)>(s, V, seq, L, Ws, trk);    // a 500-base PB window: 522 +- 8
-            else if (T::LCAP > 511) bv = cg_poa2_dp_any(s, V, seq, L, Ws, trk);
             else bv = 0;
+            CG_T_MARK(0);
             j_aln += 1; j_cells += (u64)(V + 1) * L; j_pred += (u64)sumdeg * L;
             i32 M;
             u32 bi = 0, bj = 0, nrows;
@@ -653,7 +648,8 @@ __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s
                 nrows = M > 0 ? cg_poa2_find_max(s, V, Wd, Ws, M, &bi, &bj) : 0u;
             } else {
                 M = trk.M; nrows = trk.nrows; bi = trk.row;
-                if (M > 0 && nrows == 1) {                   // first cell of that row equal to M
+                if constexpr (WIDE) { if (M > 0 && nrows == 1) bj = cg_poa2w_rowfirst(s, bi, CHw, Wd, M); }
+                else if (M > 0 && nrows == 1) {              // first cell of that row equal to M
                     const i16* hr = s.H() + (size_t)bi * Ws;
                     for (u32 jb = 1; jb < Wd; jb += 32) {
                         const u32 j = jb + lane;
@@ -665,6 +661,7 @@ __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s
             if (M > 0 && nrows > 1) {
                 // several rows reach the maximum: the winner is the first of them in spoa's own order (simd...impl.hpp:828-833)
                 if (!dfs_valid) {
+                    CG_T_MARK(1);
                     for (u32 i = lane; i < V; i += 32) { s.marks(i) = 0; s.check(i) = 1; }
                     __syncwarp();
                     bool ok = true;
@@ -673,6 +670,7 @@ __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s
                     if (!ok) return CG_NONE32;
                     dfs_valid = true;
                     __syncwarp();
+                    CG_T_MARK(5);
                 }
                 const i16* H = s.H();
                 u32 row = 0;
@@ -692,19 +690,29 @@ __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s
                     if (bal) { row = __shfl_sync(CG_FULL, myrow, __ffs((int)bal) - 1); break; }
                 }
                 bi = row; bj = 0;
-                const i16* hr = H + (size_t)row * Ws;
-                for (u32 jb = 1; jb < Wd; jb += 32) {
-                    const u32 j = jb + lane;
-                    const u32 bal = __ballot_sync(CG_FULL, j < Wd && (i32)hr[j] == M);
-                    if (bal) { bj = jb + (u32)__ffs((int)bal) - 1; break; }
+                if constexpr (WIDE) bj = cg_poa2w_rowfirst(s, row, CHw, Wd, M);
+                else {
+                    const i16* hr = H + (size_t)row * Ws;
+                    for (u32 jb = 1; jb < Wd; jb += 32) {
+                        const u32 j = jb + lane;
+                        const u32 bal = __ballot_sync(CG_FULL, j < Wd && (i32)hr[j] == M);
+                        if (bal) { bj = jb + (u32)__ffs((int)bal) - 1; break; }
+                    }
                 }
             }
             bool bad = false;
-            if (lane == 0 && M > 0) n_aln = cg_poa2_traceback(s, seq, Ws, bi, bj, &bad);
-            n_aln = __shfl_sync(CG_FULL, n_aln, 0);
-            if (__shfl_sync(CG_FULL, (u32)bad, 0)) return CG_NONE32;
+            CG_T_MARK(1);
+            if constexpr (WIDE) {
+                if (M > 0) n_aln = cg_poa2w_traceback(s, seq, CHw, bi, bj, M, &bad);     // the whole warp
+                if (bad) return CG_NONE32;
+            } else {
+                if (lane == 0 && M > 0) n_aln = cg_poa2_traceback(s, seq, Ws, bi, bj, &bad);
+                n_aln = __shfl_sync(CG_FULL, n_aln, 0);
+                if (__shfl_sync(CG_FULL, (u32)bad, 0)) return CG_NONE32;
+            }
         }
         __syncwarp();
+        CG_T_MARK(2);
 
         // ---- graph update, all lanes (graph.cpp:155-272).  Pair t in path order = work[n_aln - 1 - t].
         u32 first_valid = L, last_valid = 0;
@@ -825,9 +833,10 @@ __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s
         }
         nseqs++;
         if (__any_sync(CG_FULL, ovf)) return CG_NONE32;
-        if (!__any_sync(CG_FULL, changed)) { __syncwarp(); continue; }      // same nodes, same edges: same order, same rows
+        if (!__any_sync(CG_FULL, changed)) { __syncwarp(); CG_T_MARK(3); continue; }      // same nodes, same edges: same order, same rows
         dfs_valid = false;
         __syncwarp();
+        CG_T_MARK(3);
 
         // ---- the incremental order: splice the new nodes into the old order (columns stay contiguous)
         // U3a: position (in the old order) in front of which each new node goes
@@ -874,7 +883,11 @@ __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s
             const u32 q = qb + lane;
             const bool isnew = q < L && s.kindq(q) != 0;
             const u32 bal = __ballot_sync(CG_FULL, isnew);
-            if (isnew) s.work(K + __popc(bal & cg_lt_mask())) = (ItemT)((u32)s.posq(q) | ((u32)s.nodeq(q) << W));
+            if (isnew) {
+                const u32 at = K + __popc(bal & cg_lt_mask()), ps = s.posq(q);
+                s.work(at) = (ItemT)(ps | ((u32)s.nodeq(q) << W));
+                if constexpr (T::STORE == CG_P2_ALL_GLOBAL) ((u16*)s.prof())[at] = (u16)ps;    // wide tiers: the search keys of U3c in shared memory
+            }
             K += __popc(bal);
         }
         __syncwarp();
@@ -885,7 +898,11 @@ __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s
             if (p < V0) {
                 u32 lo = 0, hi = K;                                   // first k with pos_k > p
 #pragma unroll 1
-                while (lo < hi) { const u32 mid = (lo + hi) >> 1; if (((u32)s.work(mid) & IDNONE) <= p) lo = mid + 1; else hi = mid; }
+                while (lo < hi) {
+                    const u32 mid = (lo + hi) >> 1;
+                    const u32 key = T::STORE == CG_P2_ALL_GLOBAL ? (u32)((const u16*)s.prof())[mid] : ((u32)s.work(mid) & IDNONE);
+                    if (key <= p) lo = mid + 1; else hi = mid;
+                }
                 const u32 node = s.r2n(cur, p);
                 s.r2n(nxt, p + lo) = (IdT)node;
                 s.rank_of(node) = (IdT)(p + lo);
@@ -914,12 +931,16 @@ __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s
 #pragma unroll 1
                 for (u32 e = 0; e < deg; ++e) rows = Pk::set(rows, e, (u32)s.rank_of(Pk::get(P, e)) + 1u);
                 s.prow(r) = rows;
-                s.rdesc(r) = (typename Pk::Rdesc)((u32)s.letter(node) | (deg << 8) | (Pk::first(rows) << 16)) | ((typename Pk::Rdesc)node << (16 + W));
+                const u32 rd_lo = (u32)s.letter(node) | (deg << 8) | (Pk::first(rows) << 16);
+                s.rdesc(r) = (typename Pk::Rdesc)rd_lo | ((typename Pk::Rdesc)node << (16 + W));
+                if constexpr (T::STORE == CG_P2_ALL_GLOBAL)
+                    CgWideRd<T>::at(s)[r] = CgWideRd<T>::pack((u32)s.letter(node), deg, Pk::first(rows), deg > 1 ? Pk::get(rows, 1) : 0u);
                 sd += deg ? deg : 1u;
             }
         }
         sumdeg = cg_warp_sum(sd);
         __syncwarp();
+        CG_T_MARK(4);
     }
 
     // ---- exact column order for the vote
@@ -933,6 +954,7 @@ __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s
         __syncwarp();
     }
 
+    CG_T_MARK(5);
     // ---- column vote (bmean.cpp:649-694) straight off the graph: a column = a leader and its aligned nodes
     u8* out = c.arena + c.off_arena[w] + R->arena_off;
     u32 outn = 0;
@@ -966,6 +988,8 @@ __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s
         outn += __popc(bal);
     }
     *cnt_aln += j_aln; *cnt_cells += j_cells; *cnt_pred += j_pred;
+    CG_T_MARK(7);
+    CG_T_DONE((u32)T::VCAP, w, rg, nseg, V, R->max_len);
     return outn;
 }
 
@@ -978,6 +1002,7 @@ __global__ void __launch_bounds__(T::WARPS * 32, T::CTAS_PER_SM) k_poa2(CgChunk 
     if (gw >= nwarps) return;                       // warp-uniform; no block-wide barrier in this kernel
     CgPoa2G<T> s;
     s.wo = (u32)CgPoa2Lay<T>::per_warp * cg_warp();
+    s.ws = (u32)CgPoa2Lay<T>::wide_bytes * cg_warp();
     s.base = T::STORE == CG_P2_ALL_SMEM ? nullptr : scratch + CgPoa2Lay<T>::scratch_per_warp * (size_t)gw;
     const u32 lane = cg_lane();
     const u32 nfront = qctl[0], nback = qctl[2], cap = qctl[3];
@@ -999,5 +1024,8 @@ __global__ void __launch_bounds__(T::WARPS * 32, T::CTAS_PER_SM) k_poa2(CgChunk 
         atomicAdd((unsigned long long*)&c.counters->alignments, (unsigned long long)cnt_aln);
         atomicAdd((unsigned long long*)&c.counters->dp_cells, (unsigned long long)cnt_cells);
         atomicAdd((unsigned long long*)&c.counters->dp_pred_cells, (unsigned long long)cnt_pred);
+        constexpr u32 tier = T::VCAP <= 128 ? 0u : T::VCAP <= 254 ? 1u : T::VCAP <= 1024 ? 2u : 3u;
+        atomicAdd((unsigned long long*)&c.counters->tier_cells[tier], (unsigned long long)cnt_cells);
+        atomicAdd((unsigned long long*)&c.counters->tier_pred[tier], (unsigned long long)cnt_pred);
     }
 }

@@ -17,7 +17,7 @@
 #define CG_SPLIT_WARPS (CG_SPLIT_THREADS / 32u)
 // POA job routing.  The final graph size of a region is predicted from its longest segment L and its depth n
 // (fit on PacBio-profile piles: V ~ 1.52 L + 0.022 L n - 7, +12 % margin); a wrong guess only costs a re-queue.
-// class 0/1: tier C1 (heavy / light), 2/3: tier G (heavy / light), 4: wide tiers.  Capacities mirror k_poa2.cuh.
+// class 0/1: tier C1 (heavy / light), 2/3: tier G (heavy / light), 4/5: wide tiers (heavy / light).  Capacities mirror k_poa2.cuh.
 #define CG_POA_C1_LCAP 64u
 #define CG_POA_C1_VCAP 128u
 #define CG_POA_C1_CELLS 2048u
@@ -26,14 +26,15 @@
 #define CG_POA_C_SEGCAP 192u
 #define CG_POA_C1_HEAVY 24000u     // sequences x predicted cells: front of the queue (drained first)
 #define CG_POA_G_HEAVY 400000u
-#define CG_POA_NCLASS 5u
+#define CG_POA_W_HEAVY 3000000u    // wide tiers: the long jobs first, so that the short ones fill the tail of the launch
+#define CG_POA_NCLASS 6u
 __device__ __forceinline__ u32 cg_poa_class(u32 n, u32 L) {
     u32 vhat = (L * (1557u + 23u * n)) >> 10;
     vhat = vhat > 8u ? vhat - 7u : 1u;
     vhat += vhat >> 3;
     const u32 cells = (vhat + 1u) * (L + 1u);
     const u32 cost = n * cells;
-    if (n > CG_POA_C_SEGCAP || L > CG_POA_G_LCAP || vhat > CG_POA_G_VCAP) return 4u;
+    if (n > CG_POA_C_SEGCAP || L > CG_POA_G_LCAP || vhat > CG_POA_G_VCAP) return (u64)n * cells >= CG_POA_W_HEAVY ? 4u : 5u;
     if (L <= CG_POA_C1_LCAP && vhat <= CG_POA_C1_VCAP && cells <= CG_POA_C1_CELLS) return cost >= CG_POA_C1_HEAVY ? 0u : 1u;
     return cost >= CG_POA_G_HEAVY ? 2u : 3u;
 }
@@ -219,16 +220,16 @@ __global__ void __launch_bounds__(CG_SPLIT_THREADS) k_split(CgChunk c) {
     u32 njobs = 0;
 #pragma unroll
     for (u32 q = 0; q < CG_POA_NCLASS; ++q) njobs += cnt[q];
-    // class -> (queue, end): 0 q0 front, 1 q0 back, 2 q1 front, 3 q1 back, 4 q2 front
+    // class -> (queue, end): 0 q0 front, 1 q0 back, 2 q1 front, 3 q1 back, 4 q2 front, 5 q2 back
     u32 base[CG_POA_NCLASS];
 #pragma unroll
     for (u32 q = 0; q < CG_POA_NCLASS; ++q) {
         base[q] = 0;
-        const u32 ctl = q < 4 ? 4u * (q >> 1) + 2u * (q & 1u) : 4u * (q - 2u);
+        const u32 ctl = 4u * (q >> 1) + 2u * (q & 1u);
         if (lane == 0 && cnt[q]) base[q] = atomicAdd(&c.qctl[ctl], cnt[q]);
         base[q] = __shfl_sync(CG_FULL, base[q], 0);
     }
-    const u32 cap_s = c.qctl[3], cap_m = c.qctl[7];
+    const u32 cap_s = c.qctl[3], cap_m = c.qctl[7], cap_w = c.qctl[11];
     u32 run_off = 0;
     for (u32 gb = 0; gb < nreg; gb += 32) {
         const u32 g = gb + lane;
@@ -251,7 +252,8 @@ __global__ void __launch_bounds__(CG_SPLIT_THREADS) k_split(CgChunk c) {
             else if (cls == 1) c.jobs_s[cap_s - 1 - my] = job;
             else if (cls == 2) c.jobs_m[my] = job;
             else if (cls == 3) c.jobs_m[cap_m - 1 - my] = job;
-            else c.jobs_w[my] = job;
+            else if (cls == 4) c.jobs_w[my] = job;
+            else c.jobs_w[cap_w - 1 - my] = job;
         }
         run_off += __shfl_sync(CG_FULL, inc, 31);
     }

@@ -14,7 +14,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-from ._ffi import (Batch, CG_N_STAGES, Corrected, PKG_DIR, Params, Piles, PileSet, ReadNames, Reads, Results, STAGE_NAMES,
+from ._ffi import (Batch, CG_N_STAGES, KERNEL_NAMES, cg_kernel_stats, Corrected, PKG_DIR, Params, Piles, PileSet, ReadNames, Reads, Results, STAGE_NAMES,
                    STATUS_NAMES, cg_batch, cg_corrected, cg_counters, cg_params, cg_pile_set, cg_piles, cg_read_names, cg_reads,
                    cg_results, cg_window_set, load_library, results_to_c, window_set_to_py)
 
@@ -22,7 +22,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libconsent_b200.so")
 
 EXPORTS = ("cg_abi_version", "cg_device_count", "cg_create", "cg_destroy", "cg_last_error", "cg_set_option",
            "cg_correct_windows", "cg_free_results", "cg_upload", "cg_run", "cg_download", "cg_stage_ms",
-           "cg_get_counters", "cg_run_ms", "cg_chunk_count", "cg_reanchor_reads", "cg_free_corrected", "cg_reanchor_stats",
+           "cg_get_counters", "cg_get_kernel_stats", "cg_run_ms", "cg_chunk_count", "cg_reanchor_reads", "cg_free_corrected", "cg_reanchor_stats",
            "cg_upload_piles", "cg_download_windows", "cg_free_window_set", "cg_extract_stats",
            "cg_ingest_paf", "cg_free_pile_set", "cg_ingest_stats", "cg_finish_reads", "cg_finish_stats", "cg_finish_resident")
 
@@ -63,6 +63,8 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.cg_chunk_count.argtypes = [H]
     lib.cg_get_counters.restype = C.c_int
     lib.cg_get_counters.argtypes = [H, C.POINTER(cg_counters)]
+    lib.cg_get_kernel_stats.restype = C.c_int
+    lib.cg_get_kernel_stats.argtypes = [H, C.POINTER(cg_kernel_stats)]
     lib.cg_reanchor_reads.restype = C.c_int
     lib.cg_reanchor_reads.argtypes = [H, C.POINTER(cg_batch), C.POINTER(cg_results), C.POINTER(cg_reads), C.POINTER(cg_corrected)]
     lib.cg_free_corrected.argtypes = [C.POINTER(cg_corrected)]
@@ -235,6 +237,16 @@ class Corrector:
         n = (C.c_uint32 * CG_N_STAGES)()
         self._check(self.lib.cg_stage_ms(self._h, ms, n))
         return {name: {"ms": float(ms[i]), "launches": int(n[i])} for i, name in enumerate(STAGE_NAMES)}
+
+    def kernel_stats(self) -> dict:
+        """Per kernel of the last run(): summed launch durations (own CUDA events on the launching stream), launches, and for the
+        POA tiers the score-matrix / predecessor-row cells they computed."""
+        k = cg_kernel_stats()
+        self._check(self.lib.cg_get_kernel_stats(self._h, C.byref(k)))
+        out = {name: {"ms": float(k.ms[i]), "launches": int(k.launches[i])} for i, name in enumerate(KERNEL_NAMES)}
+        for t, name in enumerate(KERNEL_NAMES[4:8]):
+            out[name]["dp_cells"] = int(k.poa_cells[t]); out[name]["dp_pred_cells"] = int(k.poa_pred_cells[t])
+        return out
 
     def run_ms(self) -> float:
         """CUDA-event time of the whole last run() on the library's stream."""

@@ -311,6 +311,30 @@ int  cg_run_ms(const cg_handle* h, float* ms);
 /* Number of chunks the uploaded batch is processed in (each chunk = one launch of every kernel of the path). */
 int  cg_chunk_count(const cg_handle* h);
 
+/* Per-kernel timing of the last cg_run.  Every launch of the kernels below is bracketed by its own pair of CUDA events ON THE
+ * STREAM IT IS LAUNCHED ON (the POA tiers of a chunk run side by side on three streams, and two chunks are in flight at a
+ * time, so a stage span on one stream — cg_stage_ms — also contains other kernels' time; these do not).
+ * ms = sum of the launch durations, launches = their number; poa_cells / poa_pred_cells = the score-matrix cells (V+1)*L and
+ * predecessor-row cells E*L each POA tier computed (the algorithmic-bytes model of SURVEY §8d, per kernel). */
+#define CG_K_PACK      0   /* k_plan + k_scan + k_pack                  */
+#define CG_K_INDEX     1   /* k_index                                   */
+#define CG_K_CHAIN     2   /* k_chain (both shared-memory sizes)        */
+#define CG_K_SPLIT     3   /* k_split                                   */
+#define CG_K_POA_C1    4   /* k_poa2<C1>: graph + matrix in shared memory */
+#define CG_K_POA_G     5   /* k_poa2<G>: graph in shared memory, matrix in L2 */
+#define CG_K_POA_W1    6   /* k_poa2<W1>: wide tier, <= 1024 nodes      */
+#define CG_K_POA_W2    7   /* k_poa2<W2>: wide tier, <= 4096 nodes      */
+#define CG_K_POA_LAST  8   /* k_poa: the last resort                    */
+#define CG_K_POLISH    9   /* k_polish                                  */
+#define CG_K_OUT      10   /* k_stitch_len, k_out_sizes, k_scan, k_gather */
+#define CG_N_KERNELS  11
+typedef struct cg_kernel_stats {
+    float    ms[CG_N_KERNELS];
+    uint32_t launches[CG_N_KERNELS];
+    uint64_t poa_cells[4], poa_pred_cells[4];      /* C1, G, W1, W2 */
+} cg_kernel_stats;
+int  cg_get_kernel_stats(const cg_handle* h, cg_kernel_stats* out);
+
 /* Work counters of the last cg_run, the inputs of the algorithmic-bytes model
  * (SURVEY §8d): alignments, score-matrix cells sum (V+1)*L, predecessor-row cells
  * sum E*L, POA graphs, anchors in chains, solid k-mers, packed input bytes,
