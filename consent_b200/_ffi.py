@@ -106,7 +106,7 @@ class cg_synth_read_spec(C.Structure):
 class cg_counters(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "windows", "sequences", "bases", "anchors", "regions", "poa_graphs", "alignments",
-        "dp_cells", "dp_pred_cells", "solid_kmers", "consensus_bytes", "fallback_windows")]
+        "dp_cells", "dp_pred_cells", "solid_kmers", "consensus_bytes", "fallback_windows", "error_windows")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}

@@ -104,6 +104,7 @@ struct CgCountersDev {
     u64 anchors, regions, poa_graphs, alignments, dp_cells, dp_pred_cells, solid_kmers, consensus_bytes, fallback_windows;
     u64 sequences, bases, windows;
     u64 tier_cells[4], tier_pred[4];      // k_poa2 tiers C1, G, W1, W2
+    u64 error_windows;                    // windows over a limit of this build (status CG_WINDOW_ERROR)
 };
 
 struct CgChunk {

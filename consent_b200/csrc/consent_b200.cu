@@ -141,6 +141,8 @@ struct cg_handle {
     bool uploaded = false, ran = false, planned_ramp = false;
     // POA tiers
     cg_kernel_stats kstats{};
+    bool store_resident = false;         // cg_set_read_store: the read store of cg_upload_piles stays on the device across batches
+    u32 store_n = 0;
     std::mutex tier_mu;                  // the last-resort scratch is shared by the lanes
     PoaTier tier[3];                     // k_poa.cuh: global-memory tiers without an in-degree limit (the last resort); [0] unused
     u32 c1_warps = 0, g_warps = 0, w1_warps = 0, w2_warps = 0;   // resident warps of the k_poa2.cuh tiers
@@ -255,11 +257,13 @@ int plan_chunks(cg_handle* h, bool ramp = false) {
         size_t bytes = 0;
         const u32 max_windows = (ramp && w == 0 && h->W > h->chunk_max_windows) ? std::max<u32>(1u, h->chunk_max_windows / 4) : h->chunk_max_windows;
         while (w < h->W && c.nwin < max_windows) {
-            const u32 s0 = h->h_wsb[w], s1 = h->h_wsb[w + 1], N = s1 - s0;
-            const u64 nb = h->h_wbase[w + 1] - h->h_wbase[w];
-            const u64 nocc = nb;
+            const u32 s0 = h->h_wsb[w], s1 = h->h_wsb[w + 1];
+            u32 N = s1 - s0;
+            u64 nb = h->h_wbase[w + 1] - h->h_wbase[w];
             const u64 tlen = h->h_tlen[w];
-            const u64 tk = tlen >= k ? tlen - k + 1 : 0;
+            u64 tk = tlen >= k ? tlen - k + 1 : 0;
+            if (N > CG_N_MAX || tlen > CG_LEN_MAX || tk > CG_TK_MAX) { N = 1; tk = 0; nb = tlen; }     // k_plan: CG_WINDOW_ERROR, template only
+            const u64 nocc = nb;
             const u64 a_solid = round_up(nocc / h->p.solid_thresh, 4), a_slot = round_up(tk, 8), a_pos = round_up(tk * N, 8),
                       a_reg = tk + 2, a_arena = round_up(nb + N, 16);
             const u64 words = ((h->h_wbase[w + 1] >> 4) + s1) - ((h->h_wbase[w] >> 4) + s0);
@@ -605,16 +609,16 @@ int host_results_acquire(cg_handle* h, u32 W, HostResults** out) {
 }
 
 // Make room for `need_c` consensus bytes and `need_s` solid k-mers, keeping what has already been downloaded.
-int host_results_reserve(cg_handle* h, HostResults* r, u64 need_c, u64 need_s, u64 keep_c, u64 keep_s) {
+int host_results_reserve(cg_handle* h, std::string& err, HostResults* r, u64 need_c, u64 need_s, u64 keep_c, u64 keep_s) {
     if (need_c > r->capC || !r->cons) {
-        CK(cudaStreamSynchronize(h->s_d2h));
-        CK(pinned_ensure(r->cons, r->capC, (size_t)need_c, (size_t)keep_c));
+        CK_TO(err, cudaStreamSynchronize(h->s_d2h));
+        CK_TO(err, pinned_ensure(r->cons, r->capC, (size_t)need_c, (size_t)keep_c));
     }
     if (need_s > r->capS || !r->sk) {
-        CK(cudaStreamSynchronize(h->s_d2h));
+        CK_TO(err, cudaStreamSynchronize(h->s_d2h));
         size_t cap2 = r->capS;
-        CK(pinned_ensure(r->sk, r->capS, (size_t)need_s, (size_t)keep_s));
-        CK(pinned_ensure(r->sc, cap2, (size_t)need_s, (size_t)keep_s));
+        CK_TO(err, pinned_ensure(r->sk, r->capS, (size_t)need_s, (size_t)keep_s));
+        CK_TO(err, pinned_ensure(r->sc, cap2, (size_t)need_s, (size_t)keep_s));
         r->capS = std::min(r->capS, cap2);
     }
     return CG_OK;
@@ -627,20 +631,20 @@ int stream_out_chunk(cg_handle* h, Lane& L, cudaStream_t st, const ChunkPlan& cp
     const u64 need_c = h->o_cons_n + cons_n + 1, need_s = h->o_solid_n + solid_n + 1;
     if (need_c > r->capC || need_s > r->capS || !r->cons || !r->sk) {
         const u64 est_c = (u64)((double)need_c / frac * 1.05) + 4096, est_s = (u64)((double)need_s / frac * 1.05) + 4096;
-        int rc = host_results_reserve(h, r, std::max(need_c, est_c), std::max(need_s, est_s), h->o_cons_n, h->o_solid_n);
+        int rc = host_results_reserve(h, L.err, r, std::max(need_c, est_c), std::max(need_s, est_s), h->o_cons_n, h->o_solid_n);
         if (rc) return rc;
     }
-    CK(cudaEventRecord(L.ev_gather, st));
-    CK(cudaStreamWaitEvent(h->s_d2h, L.ev_gather, 0));
+    CKL(cudaEventRecord(L.ev_gather, st));
+    CKL(cudaStreamWaitEvent(h->s_d2h, L.ev_gather, 0));
     cudaStream_t sd = h->s_d2h;
-    if (cons_n) CK(cudaMemcpyAsync(r->cons + h->o_cons_n, h->o_cons.as<u8>() + h->o_cons_n, cons_n, cudaMemcpyDeviceToHost, sd));
+    if (cons_n) CKL(cudaMemcpyAsync(r->cons + h->o_cons_n, h->o_cons.as<u8>() + h->o_cons_n, cons_n, cudaMemcpyDeviceToHost, sd));
     if (solid_n) {
-        CK(cudaMemcpyAsync(r->sk + h->o_solid_n, h->o_sk.as<u32>() + h->o_solid_n, solid_n * 4, cudaMemcpyDeviceToHost, sd));
-        CK(cudaMemcpyAsync(r->sc + h->o_solid_n, h->o_sc.as<u32>() + h->o_solid_n, solid_n * 4, cudaMemcpyDeviceToHost, sd));
+        CKL(cudaMemcpyAsync(r->sk + h->o_solid_n, h->o_sk.as<u32>() + h->o_solid_n, solid_n * 4, cudaMemcpyDeviceToHost, sd));
+        CKL(cudaMemcpyAsync(r->sc + h->o_solid_n, h->o_sc.as<u32>() + h->o_solid_n, solid_n * 4, cudaMemcpyDeviceToHost, sd));
     }
-    CK(cudaMemcpyAsync(r->cons_off + cp.w0, h->o_len.as<u64>() + cp.w0, cp.nwin * sizeof(u64), cudaMemcpyDeviceToHost, sd));
-    CK(cudaMemcpyAsync(r->solid_off + cp.w0, h->o_nsol.as<u64>() + cp.w0, cp.nwin * sizeof(u64), cudaMemcpyDeviceToHost, sd));
-    CK(cudaMemcpyAsync(r->status + cp.w0, h->o_status.as<u8>() + cp.w0, cp.nwin, cudaMemcpyDeviceToHost, sd));
+    CKL(cudaMemcpyAsync(r->cons_off + cp.w0, h->o_len.as<u64>() + cp.w0, cp.nwin * sizeof(u64), cudaMemcpyDeviceToHost, sd));
+    CKL(cudaMemcpyAsync(r->solid_off + cp.w0, h->o_nsol.as<u64>() + cp.w0, cp.nwin * sizeof(u64), cudaMemcpyDeviceToHost, sd));
+    CKL(cudaMemcpyAsync(r->status + cp.w0, h->o_status.as<u8>() + cp.w0, cp.nwin, cudaMemcpyDeviceToHost, sd));
     return CG_OK;
 }
 
@@ -823,14 +827,12 @@ int upload_impl(cg_handle* h, const cg_batch* in, bool wait) {
     for (u32 w = 0; w < W; ++w) {
         const u32 s0 = in->win_seq_begin[w], s1 = in->win_seq_begin[w + 1];
         if (s1 <= s0) { h->err = "empty pile (window without a template)"; return CG_ERR_INVALID_ARG; }
-        if (s1 - s0 > CG_N_MAX) { h->err = "more than 4095 sequences in one window"; return CG_ERR_CAPACITY; }
         h->h_wbase[w] = in->seq_off[s0];
         const u64 t1 = in->seq_off[s0 + 1];
         if (t1 < h->h_wbase[w]) { h->err = "seq_off must be non-decreasing"; return CG_ERR_INVALID_ARG; }
         const u64 tlen = t1 - h->h_wbase[w];
-        if (tlen > CG_LEN_MAX) { h->err = "a sequence is longer than 6000 bases"; return CG_ERR_CAPACITY; }
-        if (tlen >= k && tlen - k + 1 > CG_TK_MAX) { h->err = "template longer than 2047 k-mers"; return CG_ERR_CAPACITY; }
-        h->h_tlen[w] = (u32)tlen;
+        if (tlen >= (1ull << 31)) { h->err = "a template longer than 2^31 bases"; return CG_ERR_INVALID_ARG; }
+        h->h_tlen[w] = (u32)tlen;                   // windows over a limit of this build are flagged by k_plan (CG_WINDOW_ERROR), not refused
     }
     const u64 n_bases = n_seqs ? in->seq_off[n_seqs] : 0;
     h->h_wbase[W] = n_bases;
@@ -856,7 +858,6 @@ int upload_impl(cg_handle* h, const cg_batch* in, bool wait) {
     }
     CK(cudaStreamSynchronize(sc));
     if (h->lane[0].h_ctl[HCTL_VFLAGS] & CG_FLAG_BAD_OFFSETS) { h->err = "seq_off must be non-decreasing"; return CG_ERR_INVALID_ARG; }
-    if (h->lane[0].h_ctl[HCTL_VFLAGS] & CG_FLAG_CAPACITY) { h->err = "a sequence is longer than 6000 bases"; return CG_ERR_CAPACITY; }
     for (size_t ci = 0; ci < h->chunks.size(); ++ci) {
         const ChunkPlan& cp = h->chunks[ci];
         const u64 b0 = h->h_wbase[cp.w0], b1 = h->h_wbase[cp.w0 + cp.nwin];
@@ -930,7 +931,7 @@ int run_impl(cg_handle* h) {
         cudaStreamSynchronize(h->lane[li].stream);
         cudaStreamSynchronize(h->lane[li].s_tail);
         for (int i = 0; i < 3; ++i) cudaStreamSynchronize(h->lane[li].s_poa[i]);
-        if (rc == CG_OK && h->lane[li].rc != CG_OK) { rc = h->lane[li].rc; h->err = h->lane[li].err; }
+        if (rc == CG_OK && h->lane[li].rc != CG_OK) { rc = h->lane[li].rc; if (!h->lane[li].err.empty()) h->err = h->lane[li].err; }
     }
     if (rc != CG_OK) { cudaStreamSynchronize(h->s_h2d); cudaStreamSynchronize(h->s_d2h); return rc; }
     if (getenv("CG_TIMELINE")) {
@@ -963,13 +964,13 @@ int run_impl(cg_handle* h) {
         for (int t = 0; t < 4; ++t) { h->kstats.poa_cells[t] += cd.tier_cells[t]; h->kstats.poa_pred_cells[t] += cd.tier_pred[t]; }
         sum.anchors += cd.anchors; sum.regions += cd.regions; sum.poa_graphs += cd.poa_graphs; sum.alignments += cd.alignments;
         sum.dp_cells += cd.dp_cells; sum.dp_pred_cells += cd.dp_pred_cells; sum.solid_kmers += cd.solid_kmers;
-        sum.consensus_bytes += cd.consensus_bytes; sum.fallback_windows += cd.fallback_windows;
+        sum.consensus_bytes += cd.consensus_bytes; sum.fallback_windows += cd.fallback_windows; sum.error_windows += cd.error_windows;
     }
     cg_counters& o = h->counters;
     o.windows = h->W; o.sequences = h->n_seqs; o.bases = h->n_bases;
     o.anchors = sum.anchors; o.regions = sum.regions; o.poa_graphs = sum.poa_graphs; o.alignments = sum.alignments;
     o.dp_cells = sum.dp_cells; o.dp_pred_cells = sum.dp_pred_cells; o.solid_kmers = sum.solid_kmers;
-    o.consensus_bytes = sum.consensus_bytes; o.fallback_windows = sum.fallback_windows;
+    o.consensus_bytes = sum.consensus_bytes; o.fallback_windows = sum.fallback_windows; o.error_windows = sum.error_windows;
     h->ran = true;
     return CG_OK;
 }
@@ -1010,7 +1011,7 @@ int cg_download(cg_handle* h, cg_results* out) {
     const u32 W = h->W;
     HostResults* r = nullptr;
     { int rc = host_results_acquire(h, W, &r); if (rc) { if (r) give_back(h, r); return rc; } }
-    { int rc = host_results_reserve(h, r, h->o_cons_n + 1, h->o_solid_n + 1, 0, 0); if (rc) { give_back(h, r); return rc; } }
+    { int rc = host_results_reserve(h, h->err, r, h->o_cons_n + 1, h->o_solid_n + 1, 0, 0); if (rc) { give_back(h, r); return rc; } }
     cudaError_t e = cudaSuccess;
     cudaStream_t sd = h->s_d2h;
     if (W) {
@@ -1049,7 +1050,7 @@ int cg_correct_windows(cg_handle* h, const cg_batch* in, cg_results* out) {
     h->h2d_pending = false;
     cudaError_t e1 = cudaStreamSynchronize(h->s_h2d), e2 = cudaStreamSynchronize(h->s_d2h);
     if (rc == CG_OK && (e1 != cudaSuccess || e2 != cudaSuccess)) { h->err = "transfer stream failed"; rc = CG_ERR_CUDA; }
-    if (rc == CG_OK && (!r->cons || !r->sk)) rc = host_results_reserve(h, r, 1, 1, 0, 0);      // zero windows
+    if (rc == CG_OK && (!r->cons || !r->sk)) rc = host_results_reserve(h, h->err, r, 1, 1, 0, 0);      // zero windows
     if (rc != CG_OK) { give_back(h, r); return rc; }
     fill_results(h, r, out);
     return CG_OK;
@@ -1174,8 +1175,12 @@ static int reanchor_impl(cg_handle* h, const cg_batch* windows, const cg_results
     A.lines_in_smem = smem <= 72 * 1024 ? 1u : 0u;                           // 3 CTAs per SM keep their lines on chip
     if (!A.lines_in_smem) smem = smem_ref;
     CK(cudaFuncSetAttribute(k_reanchor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
-    cudaEvent_t e0, e1;
-    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    struct Events {                                         // destroyed on every return path, CK's included
+        cudaEvent_t e[4] = {nullptr, nullptr, nullptr, nullptr};
+        ~Events() { for (cudaEvent_t x : e) if (x) cudaEventDestroy(x); }
+    } evs;
+    for (cudaEvent_t& x : evs.e) CK(cudaEventCreate(&x));
+    cudaEvent_t e0 = evs.e[0], e1 = evs.e[1], f0 = evs.e[2], f1 = evs.e[3];
     CK(cudaEventRecord(e0, st));
     if (R) CG_LAUNCH(k_reanchor, ctas, CG_RA_WARPS * 32, smem, st, A);
     CK(cudaEventRecord(e1, st));
@@ -1183,16 +1188,13 @@ static int reanchor_impl(cg_handle* h, const cg_batch* windows, const cg_results
     // ---- post-filters in place: trimRead + dropRead rewrite the lengths and give the first kept base
     h->fin_ms = 0;
     if (trim_mer) {
-        cudaEvent_t f0, f1;
         CK(h->ra_skip.ensure(((size_t)R + 1) * 4));
-        CK(cudaEventCreate(&f0)); CK(cudaEventCreate(&f1));
         CK(cudaEventRecord(f0, st));
         if (R) CG_LAUNCH(k_finish_reads, std::min<u32>(R, (u32)h->sms * 8), 256, 128, st, (const char*)h->ra_head.as<char>(), (const u64*)h->ra_head_off.as<u64>(),
                          h->ra_len.as<u32>(), h->ra_skip.as<u32>(), R, trim_mer);
         CK(cudaEventRecord(f1, st));
         CK(cudaEventSynchronize(f1));
         CK(cudaEventElapsedTime(&h->fin_ms, f0, f1));
-        cudaEventDestroy(f0); cudaEventDestroy(f1);
     }
     // ---- lengths -> dense offsets -> gather -> host
     std::vector<u32> len((size_t)R + 1, 0);
@@ -1201,7 +1203,6 @@ static int reanchor_impl(cg_handle* h, const cg_batch* windows, const cg_results
     CK(cudaMemcpyAsync(ctl, h->ra_ctl.p, sizeof ctl, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaEventElapsedTime(&h->ra_ms, e0, e1));
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
     memcpy(&h->ra_cells, ctl + 2, 8);
     if (ctl[1]) {
         h->err = (ctl[1] & CG_RA_FLAG_CAPACITY) ? "re-anchoring: a window exceeds a capacity limit of this build (alignment region, consensus length or banded sub-alignment)"
@@ -1428,18 +1429,42 @@ int cg_ingest_stats(const cg_handle* h, float* kernel_ms, float* parse_ms, uint6
 }
 
 // ---- window extraction: phase A of processRead on the device, into the resident batch ----------------------
+int cg_set_read_store(cg_handle* h, uint32_t n_store, const uint64_t* store_off, const char* store_bases) {
+    if (!h) return CG_ERR_INVALID_ARG;
+    if (!store_off || (n_store && store_off[n_store] && !store_bases)) { h->err = "null argument"; return CG_ERR_INVALID_ARG; }
+    for (u32 i = 0; i < n_store; ++i) if (store_off[i + 1] < store_off[i]) { h->err = "store_off must be non-decreasing"; return CG_ERR_INVALID_ARG; }
+    cudaSetDevice(h->device);
+    h->store_resident = false; h->ex_valid = false;
+    const u64 nb = store_off[n_store];
+    cudaStream_t st = h->lane[0].stream;
+    CK(h->ex_store.ensure(nb + 16)); CK(h->ex_store_off.ensure(((size_t)n_store + 1) * 8));
+    if (nb) CK(cudaMemcpyAsync(h->ex_store.p, store_bases, nb, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->ex_store_off.p, store_off, ((size_t)n_store + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (nb) CG_LAUNCH(k_ex_normalise, (u32)std::min<u64>((nb + 255) / 256, (u64)h->sms * 16), 256, 0, st, h->ex_store.as<char>(), nb);
+    CK(cudaStreamSynchronize(st));
+    h->ex_store_off_h.assign(store_off, store_off + n_store + 1);
+    h->store_n = n_store;
+    h->store_resident = true;
+    return CG_OK;
+}
+
 int cg_upload_piles(cg_handle* h, const cg_piles* P) {
     if (!h) return CG_ERR_INVALID_ARG;
-    if (!P || !P->store_off || !P->pile_ov_begin || (P->n_piles && (!P->pile_read || !P->pile_qlen)) || (P->n_store && !P->store_bases)) {
+    const bool resident = P && !P->store_off && !P->store_bases;     // the store cg_set_read_store left on the device
+    if (!P || !P->pile_ov_begin || (P->n_piles && (!P->pile_read || !P->pile_qlen)) ||
+        (!resident && (!P->store_off || (P->n_store && !P->store_bases)))) {
         h->err = "null argument"; return CG_ERR_INVALID_ARG;
     }
+    if (resident && (!h->store_resident || P->n_store != h->store_n)) { h->err = "cg_upload_piles without a store: cg_set_read_store first (same n_store)"; return CG_ERR_STATE; }
+    if (!resident) h->store_resident = false;               // the call's own store replaces whatever was there
     if (P->window_size == 0 || P->window_overlap >= P->window_size) { h->err = "window_overlap must be smaller than window_size"; return CG_ERR_INVALID_ARG; }
     if (P->window_size > CG_LEN_MAX) { h->err = "window_size above 6000"; return CG_ERR_CAPACITY; }
     cudaSetDevice(h->device);
     h->uploaded = h->ran = false; h->h2d_pending = false; h->ex_valid = false;
     h->run_gen++;
     const u32 NP = P->n_piles, NS = P->n_store;
-    const u64 n_store_bases = P->store_off[NS];
+    const u64* store_off_h = resident ? h->ex_store_off_h.data() : P->store_off;
+    const u64 n_store_bases = store_off_h[NS];
     const u64 n_ov = P->pile_ov_begin[NP];
     if (n_ov && !P->overlaps) { h->err = "null argument"; return CG_ERR_INVALID_ARG; }
     // per pile: coverage scratch and an upper bound of its windows (a window every ws - ovl bases, plus the last one)
@@ -1448,19 +1473,20 @@ int cg_upload_piles(cg_handle* h, const cg_piles* P) {
     for (u32 p = 0; p < NP; ++p) {
         if (P->pile_read[p] >= NS) { h->err = "pile_read out of range"; return CG_ERR_INVALID_ARG; }
         if (P->pile_ov_begin[p + 1] < P->pile_ov_begin[p]) { h->err = "pile_ov_begin must be non-decreasing"; return CG_ERR_INVALID_ARG; }
-        if (P->pile_ov_begin[p + 1] - P->pile_ov_begin[p] + 1 > CG_N_MAX) { h->err = "more than 4094 overlaps in one pile"; return CG_ERR_CAPACITY; }
         cov_off[p + 1] = cov_off[p] + round_up((u64)P->pile_qlen[p] + 2, 4);
         cap_off[p + 1] = cap_off[p] + (u64)P->pile_qlen[p] / step + 2;
     }
     cudaStream_t st = h->lane[0].stream;
-    CK(h->ex_store.ensure(n_store_bases + 16)); CK(h->ex_store_off.ensure(((size_t)NS + 1) * 8));
+    if (!resident) { CK(h->ex_store.ensure(n_store_bases + 16)); CK(h->ex_store_off.ensure(((size_t)NS + 1) * 8)); }
     CK(h->ex_pile_read.ensure(((size_t)NP + 1) * 4)); CK(h->ex_pile_qlen.ensure(((size_t)NP + 1) * 4)); CK(h->ex_pile_ovb.ensure(((size_t)NP + 1) * 4));
     CK(h->ex_ov.ensure((n_ov + 1) * sizeof(CgOverlapDev)));
     CK(h->ex_cov.ensure((cov_off[NP] + 4) * 4)); CK(h->ex_cov_off.ensure(((size_t)NP + 1) * 8)); CK(h->ex_cap_off.ensure(((size_t)NP + 1) * 8));
     CK(h->ex_cap_beg.ensure((cap_off[NP] + 1) * 4)); CK(h->ex_cap_end.ensure((cap_off[NP] + 1) * 4)); CK(h->ex_nwin.ensure(((size_t)NP + 1) * 4));
     CK(h->ex_flags.ensure(16));
-    if (n_store_bases) CK(cudaMemcpyAsync(h->ex_store.p, P->store_bases, n_store_bases, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(h->ex_store_off.p, P->store_off, ((size_t)NS + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (!resident) {
+        if (n_store_bases) CK(cudaMemcpyAsync(h->ex_store.p, P->store_bases, n_store_bases, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(h->ex_store_off.p, P->store_off, ((size_t)NS + 1) * 8, cudaMemcpyHostToDevice, st));
+    }
     if (NP) {
         CK(cudaMemcpyAsync(h->ex_pile_read.p, P->pile_read, (size_t)NP * 4, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(h->ex_pile_qlen.p, P->pile_qlen, (size_t)NP * 4, cudaMemcpyHostToDevice, st));
@@ -1478,10 +1504,14 @@ int cg_upload_piles(cg_handle* h, const cg_piles* P) {
     A.cov = h->ex_cov.as<u32>(); A.cov_off = h->ex_cov_off.as<u64>(); A.win_cap_off = h->ex_cap_off.as<u64>();
     A.cap_beg = h->ex_cap_beg.as<u32>(); A.cap_end = h->ex_cap_end.as<u32>(); A.n_win = h->ex_nwin.as<u32>();
     A.flags = h->ex_flags.as<u32>();
-    cudaEvent_t e0, e1, e2, e2b, e2c, e3;
-    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreate(&e2)); CK(cudaEventCreate(&e2b)); CK(cudaEventCreate(&e2c)); CK(cudaEventCreate(&e3));
+    struct Events {                                         // destroyed on every return path, CK's included
+        cudaEvent_t e[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+        ~Events() { for (cudaEvent_t x : e) if (x) cudaEventDestroy(x); }
+    } evs;
+    for (cudaEvent_t& x : evs.e) CK(cudaEventCreate(&x));
+    cudaEvent_t e0 = evs.e[0], e1 = evs.e[1], e2 = evs.e[2], e2b = evs.e[3], e2c = evs.e[4], e3 = evs.e[5], e2d = evs.e[6];
     CK(cudaEventRecord(e0, st));
-    if (n_store_bases) CG_LAUNCH(k_ex_normalise, (u32)std::min<u64>((n_store_bases + 255) / 256, (u64)h->sms * 16), 256, 0, st, h->ex_store.as<char>(), n_store_bases);
+    if (n_store_bases && !resident) CG_LAUNCH(k_ex_normalise, (u32)std::min<u64>((n_store_bases + 255) / 256, (u64)h->sms * 16), 256, 0, st, h->ex_store.as<char>(), n_store_bases);
     if (NP) CG_LAUNCH(k_ex_positions, (NP + 3) / 4, 128, 0, st, A);
     CK(cudaEventRecord(e1, st));
     // ---- window counts -> dense windows (host prefix; a few bytes per window)
@@ -1509,26 +1539,21 @@ int cg_upload_piles(cg_handle* h, const cg_piles* P) {
     const u32 W = (u32)Wtot;
     h->ex_wpos.resize(W); h->ex_wend.resize(W);
     std::vector<u32> win_pile(W);
-    std::vector<u64> slot_base((size_t)W + 1, 0);
     for (u32 p = 0, w = 0; p < NP; ++p)
         for (u32 i = 0; i < nwin[p]; ++i, ++w) {
             h->ex_wpos[w] = cap_beg[cap_off[p] + i]; h->ex_wend[w] = cap_end[cap_off[p] + i]; win_pile[w] = p;
-            slot_base[w + 1] = slot_base[w] + (P->pile_ov_begin[p + 1] - P->pile_ov_begin[p]) + 1;
         }
-    const u64 S = slot_base[W];
     CK(h->ex_win_pile.ensure(((size_t)W + 1) * 4)); CK(h->ex_win_beg.ensure(((size_t)W + 1) * 4)); CK(h->ex_win_end.ensure(((size_t)W + 1) * 4));
-    CK(h->ex_slot_base.ensure(((size_t)W + 1) * 8)); CK(h->ex_slot_len.ensure((S + 1) * 4)); CK(h->ex_slot_src.ensure((S + 1) * 8));
-    CK(h->ex_slot_loc.ensure((S + 1) * 4)); CK(h->ex_win_nseq.ensure(((size_t)W + 1) * 4)); CK(h->ex_win_nbytes.ensure(((size_t)W + 1) * 4));
+    CK(h->ex_win_nseq.ensure(((size_t)W + 1) * 4)); CK(h->ex_win_nbytes.ensure(((size_t)W + 1) * 4));
     CK(h->ex_win_base.ensure(((size_t)W + 1) * 8));
     if (W) {
         CK(cudaMemcpyAsync(h->ex_win_pile.p, win_pile.data(), (size_t)W * 4, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(h->ex_win_beg.p, h->ex_wpos.data(), (size_t)W * 4, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(h->ex_win_end.p, h->ex_wend.data(), (size_t)W * 4, cudaMemcpyHostToDevice, st));
     }
-    CK(cudaMemcpyAsync(h->ex_slot_base.p, slot_base.data(), ((size_t)W + 1) * 8, cudaMemcpyHostToDevice, st));
     A.n_windows = W; A.win_pile = h->ex_win_pile.as<u32>(); A.win_beg = h->ex_win_beg.as<u32>(); A.win_end = h->ex_win_end.as<u32>();
-    A.slot_base = h->ex_slot_base.as<u64>(); A.slot_len = h->ex_slot_len.as<u32>(); A.slot_src = h->ex_slot_src.as<u64>();
-    A.slot_loc = h->ex_slot_loc.as<u32>(); A.win_nseq = h->ex_win_nseq.as<u32>(); A.win_nbytes = h->ex_win_nbytes.as<u32>();
+    A.win_nseq = h->ex_win_nseq.as<u32>(); A.win_nbytes = h->ex_win_nbytes.as<u32>();
+    A.mode = 0;                                             // count the kept pieces of every window
     CK(cudaEventRecord(e2, st));
     if (W) CG_LAUNCH(k_ex_sizes, (W + 3) / 4, 128, 0, st, A);
     CK(cudaEventRecord(e2b, st));
@@ -1549,7 +1574,6 @@ int cg_upload_piles(cg_handle* h, const cg_piles* P) {
         h->h_wsb[w + 1] = (u32)ns;
         h->h_wbase[w + 1] = h->h_wbase[w] + nbytes[w];
         h->h_tlen[w] = h->ex_wend[w] - h->ex_wpos[w] + 1;
-        if (h->h_tlen[w] >= k && h->h_tlen[w] - k + 1 > CG_TK_MAX) { h->err = "template longer than 2047 k-mers"; return CG_ERR_CAPACITY; }
     }
     const u64 n_seqs = h->h_wsb[W], n_bases = h->h_wbase[W];
     h->W = W; h->n_seqs = n_seqs; h->n_bases = n_bases;
@@ -1557,7 +1581,12 @@ int cg_upload_piles(cg_handle* h, const cg_piles* P) {
     CK(cudaMemcpyAsync(h->d_wsb.p, h->h_wsb.data(), ((size_t)W + 1) * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->ex_win_base.p, h->h_wbase.data(), ((size_t)W + 1) * 8, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->d_seq_off.as<u64>() + n_seqs, &h->h_wbase[W], 8, cudaMemcpyHostToDevice, st));
+    CK(h->ex_slot_len.ensure((n_seqs + 1) * 4)); CK(h->ex_slot_src.ensure((n_seqs + 1) * 8)); CK(h->ex_slot_loc.ensure((n_seqs + 1) * 4));
+    A.slot_len = h->ex_slot_len.as<u32>(); A.slot_src = h->ex_slot_src.as<u64>(); A.slot_loc = h->ex_slot_loc.as<u32>();
     A.win_seq_begin = h->d_wsb.as<u32>(); A.win_base = h->ex_win_base.as<u64>(); A.seq_off = h->d_seq_off.as<u64>(); A.bases = h->d_bases.as<char>();
+    A.mode = 1;                                             // the pieces themselves, one record per kept piece
+    CK(cudaEventRecord(e2d, st));
+    if (W) CG_LAUNCH(k_ex_sizes, (W + 3) / 4, 128, 0, st, A);
     CK(cudaEventRecord(e2c, st));
     if (W) CG_LAUNCH(k_ex_copy, std::min<u32>(W, (u32)h->sms * 16), 256, 0, st, A);
     CK(cudaEventRecord(e3, st));
@@ -1569,12 +1598,12 @@ int cg_upload_piles(cg_handle* h, const cg_piles* P) {
         h->ev_h2d.push_back(e);
     }
     CK(cudaStreamSynchronize(st));
-    float m1 = 0, m2 = 0, m3 = 0;
-    CK(cudaEventElapsedTime(&m1, e0, e1)); CK(cudaEventElapsedTime(&m2, e2, e2b)); CK(cudaEventElapsedTime(&m3, e2c, e3));
-    for (cudaEvent_t e : {e0, e1, e2, e2b, e2c, e3}) cudaEventDestroy(e);
-    h->ex_ms = m1 + m2 + m3; h->ex_copy_ms = m3; h->ex_bytes = n_bases;
+    float m1 = 0, m2 = 0, m2w = 0, m3 = 0;
+    CK(cudaEventElapsedTime(&m1, e0, e1)); CK(cudaEventElapsedTime(&m2, e2, e2b)); CK(cudaEventElapsedTime(&m2w, e2d, e2c));
+    CK(cudaEventElapsedTime(&m3, e2c, e3));
+    h->ex_ms = m1 + m2 + m2w + m3; h->ex_copy_ms = m3; h->ex_bytes = n_bases;
     h->ex_pile_read_h.assign(P->pile_read, P->pile_read + NP);
-    h->ex_store_off_h.assign(P->store_off, P->store_off + NS + 1);
+    if (!resident) h->ex_store_off_h.assign(P->store_off, P->store_off + NS + 1);
     h->ex_ws = P->window_size; h->ex_ovl = P->window_overlap;
     h->ex_valid = true;
     h->uploaded = true;

@@ -32,6 +32,7 @@ __global__ void __launch_bounds__(CG_CHAIN_THREADS) k_chain(CgChunk c, u32 smem_
     const u32 w = blockIdx.x, tid = threadIdx.x, lane = cg_lane(), warp = cg_warp();
     const CgWin W = c.win[w];
     const u32 A = W.n_alive, N = W.n_seqs, C = W.n_cand, S = W.S;
+    if (W.bad) return;
     if (pass == 1 && W.n_chain != CG_CHAIN_DEFERRED) return;
     if (A == 0) {
         if (tid == 0) c.win[w].n_chain = 0;
@@ -40,7 +41,7 @@ __global__ void __launch_bounds__(CG_CHAIN_THREADS) k_chain(CgChunk c, u32 smem_
     if (cg_chain_smem(A, N) > smem_bytes) {
         if (tid == 0) {
             if (pass == 0) c.win[w].n_chain = CG_CHAIN_DEFERRED;
-            else { c.win[w].n_chain = 0; c.win[w].bad = 1; atomicOr(c.flags, (u32)CG_FLAG_CAPACITY); }
+            else { c.win[w].n_chain = 0; c.win[w].bad = 1; }      // -> raw template, status CG_WINDOW_ERROR
         }
         return;
     }

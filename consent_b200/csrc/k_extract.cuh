@@ -30,9 +30,14 @@ struct CgExtractArgs {
     // k_ex_positions: coverage scratch (pile p owns cov[cov_off[p] .. +qlen+1)), windows of pile p at slots win_cap_off[p] ..
     u32* cov; const u64* cov_off; const u64* win_cap_off; u32* cap_beg; u32* cap_end; u32* n_win;
     // dense windows (after the host's prefix over n_win)
-    u32 n_windows; const u32* win_pile; const u32* win_beg; const u32* win_end; const u64* slot_base;   // slot_base[w]: first slot of window w
-    // per slot (slot 0 of a window = the template): piece length (0: not in the pile), first source base, step (+1 / -1 = revcomp)
-    u32* slot_len; u64* slot_src; u32* slot_loc;       // slot_loc: byte offset of the piece inside its window
+    u32 n_windows; const u32* win_pile; const u32* win_beg; const u32* win_end;
+    // per KEPT piece (sequence s of the batch: the slots of window w start at win_seq_begin[w], its first one is the template):
+    // piece length, first source base (bit 63: walk backwards + complement), byte offset of the piece inside its window.
+    // k_ex_sizes runs twice: mode 0 only counts (win_nseq, win_nbytes), mode 1 writes the pieces once win_seq_begin is known —
+    // memory is per kept piece, not per (window, overlap of its pile): a contig's pile may hold tens of thousands of overlaps
+    // of which a window sees its local coverage (CONSENT-polish: maxSupport 20000, CONSENT-polish:43).
+    u32 mode;
+    u32* slot_len; u64* slot_src; u32* slot_loc;
     u32* win_nseq; u32* win_nbytes;
     // outputs
     const u32* win_seq_begin; const u64* win_base; u64* seq_off; char* bases;
@@ -115,7 +120,7 @@ __global__ void k_ex_sizes(CgExtractArgs A) {
     const u32 p = A.win_pile[w];
     const u32 qBeg = A.win_beg[w], end = A.win_end[w];
     const u32 o0 = A.pile_ov_begin[p], nal = A.pile_ov_begin[p + 1] - o0;
-    const u64 sb = A.slot_base[w];
+    const u64 sb = A.mode ? (u64)A.win_seq_begin[w] : 0ull;
     const u32 q = A.pile_read[p];
     u32 bad = 0, rank_base = 0, byte_base = 0;
     for (u32 s0 = 0; s0 < nal + 1; s0 += 32) {
@@ -174,18 +179,18 @@ __global__ void k_ex_sizes(CgExtractArgs A) {
             const u32 ro = __shfl_up_sync(CG_FULL, r, d), bo = __shfl_up_sync(CG_FULL, b, d);
             if (lane >= d) { r += ro; b += bo; }
         }
-        if (s <= nal) {
-            A.slot_len[sb + s] = len;
-            A.slot_src[sb + s] = src;
-            A.slot_loc[sb + s] = byte_base + b - len;
+        if (A.mode && len) {
+            const u64 at = sb + rank_base + r - 1;
+            A.slot_len[at] = len;
+            A.slot_src[at] = src;
+            A.slot_loc[at] = byte_base + b - len;
         }
         rank_base += __shfl_sync(CG_FULL, r, 31);
         byte_base += __shfl_sync(CG_FULL, b, 31);
     }
     bad = cg_ex_warp_or(bad);
     if (lane == 0) {
-        A.win_nseq[w] = rank_base;
-        A.win_nbytes[w] = byte_base;
+        if (!A.mode) { A.win_nseq[w] = rank_base; A.win_nbytes[w] = byte_base; }
         if (bad) atomicOr(A.flags, bad);
     }
 }
@@ -235,29 +240,15 @@ __device__ __forceinline__ void cg_ex_copy_piece(char* dst, const char* store, u
 // One CTA per window: every kept piece copied from the store into the window's slice of the batch, seq_off filled.
 __global__ void __launch_bounds__(256) k_ex_copy(CgExtractArgs A) {
     for (u32 w = blockIdx.x; w < A.n_windows; w += gridDim.x) {
-        const u32 p = A.win_pile[w];
-        const u32 nslot = A.pile_ov_begin[p + 1] - A.pile_ov_begin[p] + 1;
-        const u64 sb = A.slot_base[w];
+        const u32 seq0 = A.win_seq_begin[w], nslot = A.win_seq_begin[w + 1] - seq0;
         const u64 wbase = A.win_base[w];
-        const u32 seq0 = A.win_seq_begin[w];
         const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31u, nwarps = blockDim.x >> 5;
-        // seq_off: the rank of a kept slot = number of kept slots before it (recomputed per 32 slots by warp 0)
-        if (warp == 0) {
-            u32 rank = 0;
-            for (u32 s0 = 0; s0 < nslot; s0 += 32) {
-                const u32 s = s0 + lane;
-                const u32 len = s < nslot ? A.slot_len[sb + s] : 0u;
-                const u32 m = __ballot_sync(CG_FULL, len != 0);
-                if (len) A.seq_off[seq0 + rank + __popc(m & ((1u << lane) - 1u))] = wbase + A.slot_loc[sb + s];
-                rank += __popc(m);
-            }
-        }
+        for (u32 s = threadIdx.x; s < nslot; s += blockDim.x) A.seq_off[seq0 + s] = wbase + A.slot_loc[seq0 + s];
         // pieces: one warp per piece
         for (u32 s = warp; s < nslot; s += nwarps) {
-            const u32 len = A.slot_len[sb + s];
-            if (!len) continue;
-            const u64 src = A.slot_src[sb + s];
-            cg_ex_copy_piece(A.bases + wbase + A.slot_loc[sb + s], A.store, src & ~(1ull << 63), (src >> 63) != 0, len, lane);
+            const u32 len = A.slot_len[seq0 + s];
+            const u64 src = A.slot_src[seq0 + s];
+            cg_ex_copy_piece(A.bases + wbase + A.slot_loc[seq0 + s], A.store, src & ~(1ull << 63), (src >> 63) != 0, len, lane);
         }
     }
 }

@@ -43,6 +43,7 @@ __global__ void __launch_bounds__(CG_IDX_THREADS, 1) k_index(CgChunk c) {
     const u32 w = blockIdx.x, tid = threadIdx.x, lane = cg_lane(), warp = cg_warp();
     const u32 T = CG_IDX_THREADS, NWARPS = CG_IDX_THREADS / 32;
     const CgWin W = c.win[w];
+    if (W.bad) return;                               // k_plan left n_cand = n_alive = n_solid = 0
     const u32 k = c.k, N = W.n_seqs, tk = W.tk, S = W.S;
 
     const u64 g0 = cg_pword(c.seq_off, W.seq_begin) - c.pword_base;

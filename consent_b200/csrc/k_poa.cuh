@@ -575,7 +575,7 @@ __device__ __forceinline__ void cg_poa_drain(const CgChunk& c, const G& s, const
         if (lane == 0) {
             if (n == CG_NONE32) {
                 if (jobs_next) cg_queue_push_front(jobs_next, qnext, job);
-                else { c.win[job.x].bad = 1; atomicOr(c.flags, (u32)CG_FLAG_CAPACITY); }
+                else c.win[job.x].bad = 1;            // outgrew the last tier: raw template, status CG_WINDOW_ERROR
             } else {
                 c.regions[c.off_reg[job.x] + job.y].cons_len = n;
             }

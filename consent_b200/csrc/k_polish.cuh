@@ -311,11 +311,12 @@ __global__ void __launch_bounds__(CG_POLISH_THREADS) k_polish(CgChunk c, const u
     u8* P = buf + cap;
     const u32 n = W.stitched_len, k = c.k;
     if (n == 0) {                                   // "could not build a consensus": the raw template (correctionMSA.cpp:34-36)
-        const u8* t = bases + soff[0];
+        const u8* t = bases + soff[0];              // (also what a window over a limit of this build comes back as: status 2)
         for (u32 i = lane; i < W.tlen; i += 32) buf[i] = t[i];
         if (lane == 0) {
-            c.win[w].final_len = W.tlen; c.win[w].final_beg = 0; c.win[w].status = 1;
-            atomicAdd((unsigned long long*)&c.counters->fallback_windows, 1ull);
+            c.win[w].final_len = W.tlen; c.win[w].final_beg = 0; c.win[w].status = W.bad ? 2u : 1u;
+            if (W.bad) atomicAdd((unsigned long long*)&c.counters->error_windows, 1ull);
+            else atomicAdd((unsigned long long*)&c.counters->fallback_windows, 1ull);
             atomicAdd((unsigned long long*)&c.counters->consensus_bytes, (unsigned long long)W.tlen);
         }
         return;
@@ -356,10 +357,21 @@ __global__ void __launch_bounds__(CG_POLISH_THREADS) k_polish(CgChunk c, const u
         if (lane == 0) {
             bool ovf = false;
             cg_polish(d, buf, cap, n, P, cap, &fbeg, &fn, &ovf);
-            if (ovf) { c.win[w].bad = 1; atomicOr(c.flags, (u32)CG_FLAG_CAPACITY); }
+            if (ovf) c.win[w].bad = 1;
         }
         fbeg = __shfl_sync(CG_FULL, fbeg, 0);
         fn = __shfl_sync(CG_FULL, fn, 0);
+        if (__shfl_sync(CG_FULL, (u32)c.win[w].bad, 0)) {       // the polish outgrew its work slice: raw template, status CG_WINDOW_ERROR
+            const u8* t = bases + soff[0];
+            __syncwarp();
+            for (u32 i = lane; i < W.tlen; i += 32) buf[i] = t[i];
+            if (lane == 0) {
+                c.win[w].final_len = W.tlen; c.win[w].final_beg = 0; c.win[w].status = 2;
+                atomicAdd((unsigned long long*)&c.counters->error_windows, 1ull);
+                atomicAdd((unsigned long long*)&c.counters->consensus_bytes, (unsigned long long)W.tlen);
+            }
+            return;
+        }
     }
     if (lane == 0) {
         c.win[w].final_len = fn; c.win[w].final_beg = fbeg; c.win[w].status = 0;

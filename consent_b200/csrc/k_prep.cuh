@@ -23,19 +23,25 @@ __global__ void k_plan(CgChunk c) {
     u32 s0 = c.win_seq_begin[gw], s1 = c.win_seq_begin[gw + 1];
     u32 N = s1 - s0, k = c.k;
     u64 nocc = 0;
+    bool bad = N > CG_N_MAX;
     for (u32 s = s0; s < s1; ++s) {
-        u32 len = (u32)(c.seq_off[s + 1] - c.seq_off[s]);
+        u64 len = c.seq_off[s + 1] - c.seq_off[s];
+        if (len > CG_LEN_MAX) bad = true;
         if (len >= k) nocc += len - k + 1;
     }
     u32 tlen = (u32)(c.seq_off[s0 + 1] - c.seq_off[s0]);
     u32 tk = tlen >= k ? tlen - k + 1 : 0;
     u64 nb = c.seq_off[s1] - c.seq_off[s0];
+    if (tk > CG_TK_MAX) bad = true;
+    // A window over a limit of this build is not processed: it comes back as its raw template with status CG_WINDOW_ERROR
+    // (the reference has no such limits; the batch goes on).  Every later kernel sees a pile of one sequence without k-mers.
+    if (bad) { N = 1; tk = 0; nocc = 0; nb = tlen; }
     CgWin W;
     W.seq_begin = s0; W.n_seqs = N; W.tlen = tlen; W.tk = tk;
     int S = (int)c.common < (int)N / 2 ? (int)c.common : (int)N / 2;     // src/correctionMSA.cpp:31
     W.S = (u32)S;
     W.n_cand = W.n_alive = W.n_chain = W.n_regions = W.n_solid = 0;
-    W.stitched_len = W.final_len = W.final_beg = 0; W.status = 0; W.bad = 0;
+    W.stitched_len = W.final_len = W.final_beg = 0; W.status = 0; W.bad = bad ? 1u : 0u;
     W.n_occ = (u32)nocc; W.n_bases = (u32)nb;
     c.win[w] = W;
     c.off_solid[w] = cg_round_up(nocc / c.solid, 4);
@@ -74,6 +80,7 @@ __global__ void k_scan(u64* a0, u64* a1, u64* a2, u64* a3, u64* a4, u32 n) {
 // tag : (read index in the window) << 16 | (word index in the read) << 4 | (k-mer starts in the word - 1); ~0 = none
 __global__ void __launch_bounds__(256) k_pack(CgChunk c) {
     const CgWin W = c.win[blockIdx.x];
+    if (W.bad) return;                               // over a limit: untouched (k_plan)
     u32 lane = cg_lane(), nwarps = blockDim.x >> 5;
     u32 bad = 0;
     for (u32 r = cg_warp(); r < W.n_seqs; r += nwarps) {

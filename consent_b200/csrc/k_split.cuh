@@ -80,6 +80,7 @@ __device__ __forceinline__ u32 cg_select_distance_reg(const u32 (&d)[CG_SPLIT_RE
 __global__ void __launch_bounds__(CG_SPLIT_THREADS) k_split(CgChunk c) {
     const u32 w = blockIdx.x, lane = cg_lane(), warp = cg_warp();
     const CgWin W = c.win[w];
+    if (W.bad) return;                               // n_regions stays 0: no POA jobs, nothing to stitch
     const u32 N = W.n_seqs, C = W.n_cand, nA = W.n_chain;
     const u64 slot_base = c.off_slot[w];
     const u16* chain = c.chain + slot_base;

@@ -23,7 +23,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libconsent_b200.so")
 EXPORTS = ("cg_abi_version", "cg_device_count", "cg_create", "cg_destroy", "cg_last_error", "cg_set_option",
            "cg_correct_windows", "cg_free_results", "cg_upload", "cg_run", "cg_download", "cg_stage_ms",
            "cg_get_counters", "cg_get_kernel_stats", "cg_run_ms", "cg_chunk_count", "cg_reanchor_reads", "cg_free_corrected", "cg_reanchor_stats",
-           "cg_upload_piles", "cg_download_windows", "cg_free_window_set", "cg_extract_stats",
+           "cg_upload_piles", "cg_set_read_store", "cg_download_windows", "cg_free_window_set", "cg_extract_stats",
            "cg_ingest_paf", "cg_free_pile_set", "cg_ingest_stats", "cg_finish_reads", "cg_finish_stats", "cg_finish_resident")
 
 
@@ -72,6 +72,8 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.cg_reanchor_stats.argtypes = [H, C.POINTER(C.c_float), C.POINTER(C.c_uint64)]
     lib.cg_upload_piles.restype = C.c_int
     lib.cg_upload_piles.argtypes = [H, C.POINTER(cg_piles)]
+    lib.cg_set_read_store.restype = C.c_int
+    lib.cg_set_read_store.argtypes = [H, C.c_uint32, C.POINTER(C.c_uint64), C.c_char_p]
     lib.cg_download_windows.restype = C.c_int
     lib.cg_download_windows.argtypes = [H, C.c_int, C.POINTER(cg_window_set)]
     lib.cg_free_window_set.argtypes = [C.POINTER(cg_window_set)]
@@ -202,6 +204,21 @@ class Corrector:
         """Read store + read piles (overlaps per query read) in, the window batch cut on the device and left resident:
         run() / download() follow as after upload()."""
         cp = piles.c()
+        self._check(self.lib.cg_upload_piles(self._h, C.byref(cp)))
+
+    def set_read_store(self, store_off, store_bases):
+        """Ship the read store once (cg_set_read_store); later upload_piles(..., resident_store=True) calls cut from it."""
+        import numpy as np
+        off = np.ascontiguousarray(store_off, dtype=np.uint64)
+        bases = np.ascontiguousarray(store_bases, dtype=np.uint8)
+        self._check(self.lib.cg_set_read_store(self._h, len(off) - 1, off.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                               C.cast(bases.ctypes.data, C.c_char_p)))
+
+    def upload_piles_resident(self, piles: Piles):
+        """upload_piles against the store cg_set_read_store left on the device (the piles' own store is not sent)."""
+        cp = piles.c()
+        cp.store_off = None
+        cp.store_bases = None
         self._check(self.lib.cg_upload_piles(self._h, C.byref(cp)))
 
     def download_windows(self, with_bases: bool = True):

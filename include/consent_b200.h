@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define CG_ABI_VERSION 4
+#define CG_ABI_VERSION 5
 
 typedef enum cg_status {
     CG_OK                 =  0,
@@ -83,6 +83,10 @@ typedef struct cg_batch {
 
 #define CG_WINDOW_CONSENSUS   0   /* MSABMAAC produced a consensus                      */
 #define CG_WINDOW_TEMPLATE    1   /* fell back to the raw template (correctionMSA.cpp:34-36) */
+#define CG_WINDOW_ERROR       2   /* the window is over a limit of this build (more than 4095 sequences, a sequence over 6000
+                                     bases, a template over 2047 k-mers, an anchor table or POA graph beyond the largest
+                                     workspace): it comes back as its raw template and an empty solid list, the rest of the
+                                     batch is unaffected (the reference has no such limits and never fails a window)      */
 
 /* Results for W windows, owned by the library until cg_free_results(). */
 typedef struct cg_results {
@@ -225,6 +229,11 @@ typedef struct cg_window_set {
 /* Extracts every window of every pile into the handle's resident batch (what cg_upload would have received from a host
  * running phase A).  Blocking.  Piles without a window yield reads without windows. */
 int  cg_upload_piles(cg_handle* h, const cg_piles* piles);
+/* A host that streams the PAF in bounded batches of piles (the reference's ring of 100 000 jobs,
+ * src/CONSENT-correction.cpp:76-127) ships the read store once: after cg_set_read_store, cg_upload_piles calls whose
+ * cg_piles has store_off == NULL and store_bases == NULL (n_store unchanged) cut their windows from the resident store.
+ * The store is what indexReads holds (src/utils.cpp:166-204), normalised on the device like cg_upload_piles does. */
+int  cg_set_read_store(cg_handle* h, uint32_t n_store, const uint64_t* store_off, const char* store_bases);
 int  cg_download_windows(cg_handle* h, int with_bases, cg_window_set* out);
 void cg_free_window_set(cg_window_set* s);
 /* CUDA-event time (ms) of the extraction kernels of the last cg_upload_piles (host round trips for the window counts
@@ -344,6 +353,7 @@ typedef struct cg_counters {
     uint64_t anchors, regions, poa_graphs, alignments;
     uint64_t dp_cells, dp_pred_cells;
     uint64_t solid_kmers, consensus_bytes, fallback_windows;
+    uint64_t error_windows;          /* windows returned with CG_WINDOW_ERROR */
 } cg_counters;
 int  cg_get_counters(const cg_handle* h, cg_counters* out);
 

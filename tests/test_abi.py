@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol(gpu_lib):
         assert hasattr(lib, fn), f"{fn} declared in include/consent_b200.h but not exported"
     assert set(header_functions()) == set(engine.EXPORTS)
     lib.cg_abi_version.restype = C.c_int
-    assert lib.cg_abi_version() == 4
+    assert lib.cg_abi_version() == 5
 
 
 def test_cuda_library_holds_sm100a_kernels(gpu_lib):

@@ -156,3 +156,53 @@ def test_dropin_binary_polishes_like_the_reference_on_the_gpu(polish, gpu_lib, m
     d, args, want = polish
     out = subprocess.run([_binary("consent_correction_b200")] + mode + args + FLAGS, check=True, capture_output=True).stdout
     assert out == want
+
+
+# ---------------------------------------------------------------------------------------------------- the product's own host programs
+# consent_b200/bin/CONSENT-correction / CONSENT-polishing (consent_b200/host/*.cpp): own FASTA reader, PAF streamed in bounded
+# batches of whole piles, one host thread + handle per GPU, records written in input order.  No reference code is linked.
+def _product(entry, name="CONSENT-correction"):
+    entry.build_bin()
+    return os.path.join(ROOT, "consent_b200", "bin", name)
+
+
+def _emu_env(d, entry, **extra):
+    emu = entry.build_emu()
+    libdir = d / "emulib"
+    libdir.mkdir(exist_ok=True)
+    link = libdir / "libconsent_b200.so"
+    if not link.exists():
+        os.symlink(emu, link)
+    return dict(os.environ, LD_LIBRARY_PATH=str(libdir), **extra)
+
+
+@pytest.mark.parametrize("batch_bytes", ["100000000", "20000", "1"])
+def test_product_corrector_on_emulated_kernels_prints_the_reference_fasta(small, entry, batch_bytes):
+    """One batch, a handful of batches, one pile per batch: always the unmodified reference binary's FASTA, byte for byte."""
+    d, paf, fa, want = small
+    out = subprocess.run([_product(entry), "-a", paf, "-r", fa, "-j", "4", "-p", "/nonexistent"] + FLAGS, check=True, capture_output=True,
+                         env=_emu_env(d, entry, CONSENT_BATCH_BYTES=batch_bytes)).stdout
+    assert out == want
+
+
+def test_product_polisher_on_emulated_kernels_prints_the_reference_fasta(polish, entry):
+    d, args, want = polish
+    out = subprocess.run([_product(entry, "CONSENT-polishing")] + args + FLAGS, check=True, capture_output=True,
+                         env=_emu_env(d, entry, CONSENT_BATCH_BYTES="30000")).stdout
+    assert out == want
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("batch_bytes", ["100000000", "20000"])
+def test_product_corrector_on_the_gpu_prints_the_reference_fasta(small, gpu_lib, entry, batch_bytes):
+    d, paf, fa, want = small
+    out = subprocess.run([_product(entry), "-a", paf, "-r", fa] + FLAGS, check=True, capture_output=True,
+                         env=dict(os.environ, CONSENT_BATCH_BYTES=batch_bytes)).stdout
+    assert out == want
+
+
+@pytest.mark.gpu
+def test_product_polisher_on_the_gpu_prints_the_reference_fasta(polish, gpu_lib, entry):
+    d, args, want = polish
+    out = subprocess.run([_product(entry, "CONSENT-polishing")] + args + FLAGS, check=True, capture_output=True).stdout
+    assert out == want

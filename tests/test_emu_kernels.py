@@ -118,3 +118,27 @@ def test_emulated_kernels_on_real_piles(emu, example_golden):
     res = emu().correct_windows(Batch.from_piles(piles))
     case = {k: (v[:60] if isinstance(v, list) else v) for k, v in example_golden.items()}
     assert_matches_golden(res, case)
+
+
+def test_emulated_window_over_a_limit_comes_back_as_its_template_and_the_batch_goes_on(emu, oracle):
+    """CG_WINDOW_ERROR: a window over a limit of this build (here: 4200 sequences > 4095, and a 2100-base template > 2047 k-mers) is
+    returned as its raw template with status 2; its neighbours are corrected as if it were not there (the reference never fails a
+    window: src/correctionMSA.cpp:29-49)."""
+    import numpy as np
+    good1, good2 = synth_windows(2, 8, seed=51), synth_windows(2, 20, seed=52)
+    rng = np.random.default_rng(3)
+    deep = Batch.from_piles([["".join("ACGT"[i] for i in rng.integers(0, 4, 40))] + ["ACGTACGTACGTAAC"] * 4199])
+    long_tpl = Batch.from_piles([["".join("ACGT"[i] for i in rng.integers(0, 4, 2100)), "ACGTACGTACGTAAC", "ACGTTTGACGTACGTAAC"]])
+    batch = concat([good1, deep, good2, long_tpl])
+    cor = emu()
+    got = cor.correct_windows(batch)
+    want, _ = oracle.correct_windows(concat([good1, good2]), threads=4)
+    idx_good = [0, 1, 3, 4]
+    for i, w in enumerate(idx_good):
+        assert got.consensus(w) == want.consensus(i) and int(got.status[w]) == int(want.status[i])
+        assert got.solid(w) == want.solid(i)
+    for w, b in ((2, deep), (5, long_tpl)):
+        assert int(got.status[w]) == 2
+        assert got.consensus(w) == bytes(b.bases[:int(b.seq_off[1])]).decode()
+        assert got.solid(w) == []
+    assert cor.counters()["error_windows"] == 2

@@ -184,3 +184,53 @@ def test_gpu_chain_piles_to_corrected_reads(gpu, oracle):
     assert res.equals(ores)
     assert got.equals(want)
     assert batch.n_windows > 4000
+
+
+# ------------------------------------------------------------------------------------------------ polishing-shaped piles
+def contig_pile(n_reads: int, contig_len: int, read_len: int, seed: int) -> Piles:
+    """ONE pile whose query is a long 'contig' with n_reads short reads mapped all along it (CONSENT-polish: a contig's pile holds
+    thousands of overlaps, a window sees its local coverage; maxSupport 20000, reference CONSENT-polish:43)."""
+    rng = np.random.default_rng(seed)
+    contig = rng.integers(0, 4, contig_len)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    store, off, ov = [acgt[contig]], [0, contig_len], []
+    for r in range(n_reads):
+        beg = int(rng.integers(0, contig_len - read_len))
+        seq = contig[beg:beg + read_len].copy()
+        flip = rng.random(read_len) < 0.08
+        seq[flip] = (seq[flip] + rng.integers(1, 4, int(flip.sum()))) % 4
+        strand = int(rng.integers(0, 2))
+        bases = acgt[seq]
+        if strand:
+            bases = acgt[3 - seq][::-1]
+        store.append(bases); off.append(off[-1] + read_len)
+        ov.append((r + 1, strand, beg, beg + read_len - 1, 0, read_len - 1, read_len))
+    return Piles(np.array(off, np.uint64), np.concatenate(store), np.array([0], np.uint32), np.array([contig_len], np.uint32),
+                 np.array([0, n_reads], np.uint32), np.array(ov, np.uint32), 1, 500, 50)
+
+
+def test_emulated_kernels_cut_a_pile_of_more_overlaps_than_a_window_may_hold(emu, oracle):
+    """5000 overlaps in one pile (> CG_N_MAX = 4095 sequences per WINDOW): every window only sees ~40 of them and must extract."""
+    p = contig_pile(5000, 60000, 500, seed=21)
+    cor = emu()
+    cor.upload_piles(p)
+    got = cor.download_windows()
+    assert_same_windows(got, oracle.extract_windows(p), "deep contig pile")
+    assert got[0].n_windows > 100 and got[0].n_seqs / got[0].n_windows < 200
+
+
+def test_emulated_resident_store_gives_the_same_windows(emu, oracle):
+    p = synth_piles(n_reads=40, genome_len=12000, read_len=2000, seed=8)
+    cor = emu()
+    cor.set_read_store(p.store_off, p.store_bases)
+    half = p.n_piles // 2
+    want = oracle.extract_windows(p)
+    for lo, hi in ((0, half), (half, p.n_piles)):                       # two batches of piles against one resident store
+        o0, o1 = int(p.pile_ov_begin[lo]), int(p.pile_ov_begin[hi])
+        sub = Piles(p.store_off, p.store_bases, p.pile_read[lo:hi], p.pile_qlen[lo:hi], p.pile_ov_begin[lo:hi + 1] - o0, p.overlaps[o0:o1],
+                    p.min_support, p.window_size, p.window_overlap)
+        cor.upload_piles_resident(sub)
+        assert_same_windows(cor.download_windows(), oracle.extract_windows(sub), f"resident store, piles {lo}..{hi}")
+    assert want[0].n_windows > 0
+    with pytest.raises(ConsentError):
+        emu().upload_piles_resident(p)                                   # no store set on that handle
