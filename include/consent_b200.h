@@ -85,8 +85,8 @@ typedef struct cg_batch {
 #define CG_WINDOW_TEMPLATE    1   /* fell back to the raw template (correctionMSA.cpp:34-36) */
 #define CG_WINDOW_ERROR       2   /* the window is over a limit of this build (more than 4095 sequences, a sequence over 6000
                                      bases, a template over 2047 k-mers, an anchor table or POA graph beyond the largest
-                                     workspace): it comes back as its raw template and an empty solid list, the rest of the
-                                     batch is unaffected (the reference has no such limits and never fails a window)      */
+                                     workspace): it comes back as its raw template (with the solid k-mers counted before the
+                                     limit was met, none if it was met at once), the rest of the batch is unaffected (the reference has no such limits and never fails a window)      */
 
 /* Results for W windows, owned by the library until cg_free_results(). */
 typedef struct cg_results {

@@ -70,9 +70,9 @@ def test_emulated_poa_tier_overflow_requeues_jobs(emu, oracle):
     want, _ = oracle.correct_windows(long_pile, threads=1)
     assert_same(emu().correct_windows(long_pile), want, "last-resort tier 1")
     assert_same(emu(poa_tier1_cells=1 << 20).correct_windows(long_pile), want, "last-resort tier 1 -> 2")
-    with pytest.raises(ConsentError) as e:
-        emu(poa_tier1_cells=1 << 20, poa_tier2_cells=1 << 20).correct_windows(long_pile)
-    assert e.value.code == -6
+    # no tier can hold it: the window comes back as its raw template with status CG_WINDOW_ERROR, the call succeeds
+    got = emu(poa_tier1_cells=1 << 20, poa_tier2_cells=1 << 20).correct_windows(long_pile)
+    assert int(got.status[0]) == 2 and got.consensus(0) == bytes(long_pile.bases[:int(long_pile.seq_off[1])]).decode()      # (its solid k-mer list was already counted and is returned)
 
 
 def test_emulated_deep_piles(emu, oracle):
@@ -90,9 +90,8 @@ def test_emulated_errors(emu):
     with pytest.raises(ConsentError) as e:
         cor.run() if False else emu().run()
     assert e.value.code == -7                               # CG_ERR_STATE: run before upload
-    with pytest.raises(ConsentError) as e:
-        cor.correct_windows(Batch.from_piles([["A" * 7000, "ACGT"]]))
-    assert e.value.code == -6                               # CG_ERR_CAPACITY: stated limit
+    got = cor.correct_windows(Batch.from_piles([["A" * 7000, "ACGT"]]))            # over a stated limit (6000 bases): not corrected, not fatal
+    assert int(got.status[0]) == 2 and got.consensus(0) == "A" * 7000              # CG_WINDOW_ERROR: the raw template
 
 
 def test_emulated_lifetime_and_empty_batch(emu):
