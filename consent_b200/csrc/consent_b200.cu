@@ -141,6 +141,9 @@ struct cg_handle {
     bool uploaded = false, ran = false, planned_ramp = false;
     // POA tiers
     cg_kernel_stats kstats{};
+    bool input_2bit = false;             // cg_upload / cg_correct_windows: `bases` is 2 bits per base (cg_pack_bases_2bit), unpacked on the device
+    bool results_with_solid = true;      // false: the solid k-mer lists stay on the device (cg_reanchor_reads / cg_finish_reads read them there)
+    DevBuf d_packed;
     bool store_resident = false;         // cg_set_read_store: the read store of cg_upload_piles stays on the device across batches
     u32 store_n = 0;
     std::mutex tier_mu;                  // the last-resort scratch is shared by the lanes
@@ -638,7 +641,7 @@ int stream_out_chunk(cg_handle* h, Lane& L, cudaStream_t st, const ChunkPlan& cp
     CKL(cudaStreamWaitEvent(h->s_d2h, L.ev_gather, 0));
     cudaStream_t sd = h->s_d2h;
     if (cons_n) CKL(cudaMemcpyAsync(r->cons + h->o_cons_n, h->o_cons.as<u8>() + h->o_cons_n, cons_n, cudaMemcpyDeviceToHost, sd));
-    if (solid_n) {
+    if (solid_n && h->results_with_solid) {
         CKL(cudaMemcpyAsync(r->sk + h->o_solid_n, h->o_sk.as<u32>() + h->o_solid_n, solid_n * 4, cudaMemcpyDeviceToHost, sd));
         CKL(cudaMemcpyAsync(r->sc + h->o_solid_n, h->o_sc.as<u32>() + h->o_solid_n, solid_n * 4, cudaMemcpyDeviceToHost, sd));
     }
@@ -776,10 +779,39 @@ void cg_destroy(cg_handle* h) {
                       &h->ex_win_end, &h->ex_slot_base, &h->ex_slot_len, &h->ex_slot_src, &h->ex_slot_loc, &h->ex_win_nseq, &h->ex_win_nbytes,
                       &h->ex_win_base, &h->ex_flags, &h->in_text, &h->in_tile, &h->in_nl, &h->in_names, &h->in_name_off, &h->in_slots, &h->in_rec,
                       &h->in_head, &h->in_pfirst, &h->in_plast, &h->in_keep, &h->in_scratch, &h->in_pread, &h->in_pqlen, &h->in_ov, &h->in_res,
-                      &h->in_ctl, &h->in_htile, &h->ra_skip};
+                      &h->in_ctl, &h->in_htile, &h->ra_skip, &h->d_packed};
     for (DevBuf* b : bufs) b->release();
     for (auto& t : h->tier) { t.mem.release(); t.desc.release(); }
     delete h;
+}
+
+// Host helper for "input_2bit": ASCII -> 2 bits per base (A 0, C 1, G 2, anything else 3 = T, upper or lower case: the mapping of the
+// reference's read index, src/utils.cpp:21-32,189), base i at bits 2 (i & 3) of byte i >> 2.  `out` holds (n + 3) / 4 bytes.
+void cg_pack_bases_2bit(const char* ascii, uint64_t n, uint8_t* out, int threads) {
+    if (!ascii || !out || !n) return;
+    const u64 nbytes = (n + 3) / 4;
+    const int T = std::max(1, std::min(threads, 64));
+    auto work = [&](u64 q0, u64 q1) {
+        for (u64 q = q0; q < q1; ++q) {
+            u32 v = 0;
+            for (u32 j = 0; j < 4; ++j) {
+                const u64 i = 4 * q + j;
+                if (i >= n) break;
+                const char c = ascii[i] & ~0x20;
+                v |= (c == 'A' ? 0u : c == 'C' ? 1u : c == 'G' ? 2u : 3u) << (2 * j);
+            }
+            out[q] = (u8)v;
+        }
+    };
+#ifndef CG_EMU
+    std::vector<std::thread> th;
+    const u64 per = (nbytes + T - 1) / T;
+    for (int t = 1; t < T; ++t) { const u64 a = std::min(nbytes, per * t), b = std::min(nbytes, per * (t + 1)); if (b > a) th.emplace_back(work, a, b); }
+    work(0, std::min(nbytes, per));
+    for (std::thread& x : th) x.join();
+#else
+    work(0, nbytes);
+#endif
 }
 
 int cg_set_option(cg_handle* h, const char* key, long long value) {
@@ -787,6 +819,8 @@ int cg_set_option(cg_handle* h, const char* key, long long value) {
     const std::string k(key);
     if (k == "chunk_budget_bytes") h->chunk_budget = (size_t)value;
     else if (k == "chunk_max_windows") h->chunk_max_windows = (u32)std::max<long long>(1, value);
+    else if (k == "input_2bit") h->input_2bit = value != 0;
+    else if (k == "results_with_solid") h->results_with_solid = value != 0;
     else if (k == "lanes") h->n_lanes = (int)std::max<long long>(1, std::min<long long>(value, CG_NLANES));
     else if (k == "poa_c1_warps") h->c1_warps = (u32)std::max<long long>(1, value);
     else if (k == "poa_g_warps") h->g_warps = (u32)std::max<long long>(1, value);
@@ -840,6 +874,7 @@ int upload_impl(cg_handle* h, const cg_batch* in, bool wait) {
         if (h->h_wbase[w + 1] < h->h_wbase[w]) { h->err = "seq_off must be non-decreasing"; return CG_ERR_INVALID_ARG; }
     h->W = W; h->n_seqs = n_seqs; h->n_bases = n_bases;
     CK(h->d_bases.ensure(n_bases + 64));
+    if (h->input_2bit) CK(h->d_packed.ensure(n_bases / 4 + 64));
     CK(h->d_seq_off.ensure((n_seqs + 1) * sizeof(u64)));
     CK(h->d_wsb.ensure((W + 1) * sizeof(u32)));
     cudaStream_t sc = h->s_h2d;
@@ -861,7 +896,12 @@ int upload_impl(cg_handle* h, const cg_batch* in, bool wait) {
     for (size_t ci = 0; ci < h->chunks.size(); ++ci) {
         const ChunkPlan& cp = h->chunks[ci];
         const u64 b0 = h->h_wbase[cp.w0], b1 = h->h_wbase[cp.w0 + cp.nwin];
-        if (b1 > b0) CK(cudaMemcpyAsync(h->d_bases.as<char>() + b0, in->bases + b0, b1 - b0, cudaMemcpyHostToDevice, sc));
+        if (b1 > b0 && !h->input_2bit) CK(cudaMemcpyAsync(h->d_bases.as<char>() + b0, in->bases + b0, b1 - b0, cudaMemcpyHostToDevice, sc));
+        if (b1 > b0 && h->input_2bit) {                     // a quarter of the bytes over the bus, expanded to the ASCII the kernels read
+            const u64 p0 = b0 >> 2, p1 = (b1 + 3) >> 2;
+            CK(cudaMemcpyAsync(h->d_packed.as<u8>() + p0, (const u8*)in->bases + p0, p1 - p0, cudaMemcpyHostToDevice, sc));
+            CG_LAUNCH(k_unpack_2bit, (u32)std::min<u64>((b1 - b0 + 1023) / 1024, (u64)h->sms * 8), 256, 0, sc, (const u8*)h->d_packed.as<u8>(), h->d_bases.as<char>(), b0, b1);
+        }
         CK(cudaEventRecord(h->ev_h2d[ci], sc));
     }
     if (wait) CK(cudaStreamSynchronize(sc));
@@ -979,6 +1019,7 @@ void fill_results(cg_handle* h, HostResults* r, cg_results* out) {
     const u32 W = h->W;
     r->cons_off[W] = h->o_cons_n; r->solid_off[W] = h->o_solid_n;
     out->n_windows = W; out->cons_off = r->cons_off; out->cons = r->cons; out->status = r->status;
+    if (!h->results_with_solid) memset(r->solid_off, 0, ((size_t)W + 1) * sizeof(u64));     // the lists stayed on the device
     out->solid_off = r->solid_off; out->solid_kmer = r->sk; out->solid_count = r->sc; out->owner_ = r;
     r->gen = h->run_gen;
 }
@@ -1019,8 +1060,8 @@ int cg_download(cg_handle* h, cg_results* out) {
         if (e == cudaSuccess) e = cudaMemcpyAsync(r->solid_off, h->o_nsol.p, W * sizeof(u64), cudaMemcpyDeviceToHost, sd);
         if (e == cudaSuccess) e = cudaMemcpyAsync(r->status, h->o_status.p, W, cudaMemcpyDeviceToHost, sd);
         if (e == cudaSuccess && h->o_cons_n) e = cudaMemcpyAsync(r->cons, h->o_cons.p, h->o_cons_n, cudaMemcpyDeviceToHost, sd);
-        if (e == cudaSuccess && h->o_solid_n) e = cudaMemcpyAsync(r->sk, h->o_sk.p, h->o_solid_n * 4, cudaMemcpyDeviceToHost, sd);
-        if (e == cudaSuccess && h->o_solid_n) e = cudaMemcpyAsync(r->sc, h->o_sc.p, h->o_solid_n * 4, cudaMemcpyDeviceToHost, sd);
+        if (e == cudaSuccess && h->o_solid_n && h->results_with_solid) e = cudaMemcpyAsync(r->sk, h->o_sk.p, h->o_solid_n * 4, cudaMemcpyDeviceToHost, sd);
+        if (e == cudaSuccess && h->o_solid_n && h->results_with_solid) e = cudaMemcpyAsync(r->sc, h->o_sc.p, h->o_solid_n * 4, cudaMemcpyDeviceToHost, sd);
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(sd);
     if (e != cudaSuccess) { h->err = std::string("download: ") + cudaGetErrorString(e); give_back(h, r); return CG_ERR_CUDA; }

@@ -15,6 +15,27 @@ __global__ void k_validate(const u64* seq_off, u64 n_seqs, u32* flags) {
     if (f) atomicOr(flags, f);
 }
 
+// 2-bit input (cg_set_option "input_2bit"): base i of the batch is bits 2 (i & 3) .. of byte i >> 2, A 0 C 1 G 2 T 3 (cg_pack_bases_2bit,
+// the way the reference's own read index holds reads: src/utils.cpp:21-54).  Expanded to the ASCII the kernels read; 4 bases per
+// thread and step for the aligned body (one byte in, one 32-bit word out).
+__global__ void k_unpack_2bit(const u8* packed, char* bases, u64 b0, u64 b1) {
+    const u64 a0 = (b0 + 3) & ~(u64)3, a1 = b1 & ~(u64)3;              // aligned body [a0, a1)
+    const u64 tid = (u64)blockIdx.x * blockDim.x + threadIdx.x, nth = (u64)gridDim.x * blockDim.x;
+    if (a1 > a0)
+        for (u64 q = (a0 >> 2) + tid; q < (a1 >> 2); q += nth) {
+            const u32 v = packed[q];
+            const u32 lut = 0x54474341u;                              // 'A' 'C' 'G' 'T' as bytes 0..3
+            const u32 w = ((lut >> (8 * (v & 3u))) & 0xffu) | (((lut >> (8 * ((v >> 2) & 3u))) & 0xffu) << 8) |
+                          (((lut >> (8 * ((v >> 4) & 3u))) & 0xffu) << 16) | (((lut >> (8 * ((v >> 6) & 3u))) & 0xffu) << 24);
+            *(u32*)(bases + 4 * q) = w;
+        }
+    if (tid < 8) {                                                     // ragged head / tail (also the whole range when it is tiny)
+        const u64 h1 = a1 > a0 ? a0 : b1, t0 = a1 > a0 ? a1 : b1;
+        for (u64 i = b0 + tid; i < h1; i += 8) bases[i] = "ACGT"[(packed[i >> 2] >> (2 * (i & 3))) & 3u];
+        for (u64 i = t0 + tid; i < b1; i += 8) bases[i] = "ACGT"[(packed[i >> 2] >> (2 * (i & 3))) & 3u];
+    }
+}
+
 // One thread per window: sizes and arena capacities (written into the off_* arrays, scanned by k_scan).
 __global__ void k_plan(CgChunk c) {
     u32 w = blockIdx.x * blockDim.x + threadIdx.x;

@@ -20,7 +20,7 @@ from ._ffi import (Batch, CG_N_STAGES, KERNEL_NAMES, cg_kernel_stats, Corrected,
 
 LIB_PATH = os.path.join(PKG_DIR, "libconsent_b200.so")
 
-EXPORTS = ("cg_abi_version", "cg_device_count", "cg_create", "cg_destroy", "cg_last_error", "cg_set_option",
+EXPORTS = ("cg_abi_version", "cg_device_count", "cg_create", "cg_destroy", "cg_last_error", "cg_set_option", "cg_pack_bases_2bit",
            "cg_correct_windows", "cg_free_results", "cg_upload", "cg_run", "cg_download", "cg_stage_ms",
            "cg_get_counters", "cg_get_kernel_stats", "cg_run_ms", "cg_chunk_count", "cg_reanchor_reads", "cg_free_corrected", "cg_reanchor_stats",
            "cg_upload_piles", "cg_set_read_store", "cg_download_windows", "cg_free_window_set", "cg_extract_stats",
@@ -42,6 +42,8 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.cg_destroy.argtypes = [H]
     lib.cg_last_error.restype = C.c_char_p
     lib.cg_last_error.argtypes = [H]
+    lib.cg_pack_bases_2bit.restype = None
+    lib.cg_pack_bases_2bit.argtypes = [C.c_char_p, C.c_uint64, C.POINTER(C.c_uint8), C.c_int]
     lib.cg_set_option.restype = C.c_int
     lib.cg_set_option.argtypes = [H, C.c_char_p, C.c_longlong]
     for name in ("cg_correct_windows",):
@@ -254,6 +256,22 @@ class Corrector:
         n = (C.c_uint32 * CG_N_STAGES)()
         self._check(self.lib.cg_stage_ms(self._h, ms, n))
         return {name: {"ms": float(ms[i]), "launches": int(n[i])} for i, name in enumerate(STAGE_NAMES)}
+
+    def pack_2bit(self, batch: Batch, threads: int = 8, pinned: bool = False) -> Batch:
+        """The batch with its bases packed 2 bits per base (cg_pack_bases_2bit) — input of a handle with set_option("input_2bit", 1)."""
+        import numpy as np
+        n = int(batch.n_bases)
+        if pinned:
+            import torch
+            keep = torch.empty((n + 3) // 4 + 8, dtype=torch.uint8).pin_memory()
+            out = keep.numpy()
+        else:
+            keep, out = None, np.empty((n + 3) // 4 + 8, np.uint8)
+        self.lib.cg_pack_bases_2bit(C.cast(batch.bases.ctypes.data, C.c_char_p), n, out.ctypes.data_as(C.POINTER(C.c_uint8)), threads)
+        nb = Batch.__new__(Batch)
+        nb.win_seq_begin, nb.seq_off, nb.bases = batch.win_seq_begin, batch.seq_off, out
+        nb._keep = (keep, getattr(batch, "_keep", None))
+        return nb
 
     def kernel_stats(self) -> dict:
         """Per kernel of the last run(): summed launch durations (own CUDA events on the launching stream), launches, and for the

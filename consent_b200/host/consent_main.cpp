@@ -17,6 +17,7 @@
 // as in the reference's hot path, without effect on the output: -j sizes the reference's thread pool, here the GPUs do the work).
 // Extra options: -g LIST  CUDA devices, e.g. "0,1,2,3" or "all" (default: device 0; also CONSENT_GPUS)
 //                -B MB    PAF text per batch (default 48)
+//                -W N     host threads (each with its own handle) per GPU (default 2: one batch's host phases run under the other's kernels)
 // The binary is the polisher when it is called as *polishing* (or with -P): it never trims (src/CONSENT-polishing.cpp:19).
 // Reads are sharded over the GPUs batch by batch; nothing is exchanged between GPUs during the computation, the corrected reads of a
 // batch come back to this process over PCIe and are written in input order.  (A multi-PROCESS run — one rank per GPU under torchrun —
@@ -24,6 +25,7 @@
 #include <getopt.h>
 
 #include <algorithm>
+#include <chrono>
 #include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
@@ -46,6 +48,7 @@ struct Options {
     unsigned minSupport = 3, maxSupport = 1000, windowSize = 500, merSize = 9, commonKMers = 8, minAnchors = 10, solidThresh = 4,
              windowOverlap = 50;                                                    // src/main.cpp:17-26
     std::vector<int> gpus;
+    unsigned workers_per_gpu = 2;       // host threads (each with its own handle) per GPU: one batch's host phases overlap the other's kernels
     size_t batch_mb = 48;
     bool polishing = false, verbose = false;
 };
@@ -112,6 +115,9 @@ struct Shared {
     std::mutex err_mu;
     std::string error;
     unsigned long long windows = 0, error_windows = 0, piles = 0;
+    double t_first = -1, t_last = 0;                 // seconds since start: first batch taken by a GPU, last batch written
+    std::chrono::steady_clock::time_point t0;
+    double now() const { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
 };
 
 void fail(Shared* sh, const std::string& what) {
@@ -136,6 +142,10 @@ void gpu_main(Shared* sh, int device) {
     const bool trim = !o.polishing && o.proof.empty();                               // doTrimRead, CONSENT-correction.cpp:17,70-73
     Batch b;
     while (sh->queue->pop(&b)) {
+        {
+            std::lock_guard<std::mutex> lk(sh->err_mu);
+            if (sh->t_first < 0) sh->t_first = sh->now();
+        }
         cg_pile_set ps;
         cg_corrected cor;
         if (cg_ingest_paf(h, b.text.data(), b.text.size(), &names, o.maxSupport, &ps) != CG_OK) { fail(sh, std::string("cg_ingest_paf: ") + cg_last_error(h)); break; }
@@ -164,6 +174,10 @@ void gpu_main(Shared* sh, int device) {
         cg_free_corrected(&cor);
         cg_free_pile_set(&ps);
         sh->writer->put(b.seq, std::move(fasta));
+        {
+            std::lock_guard<std::mutex> lk(sh->err_mu);
+            sh->t_last = sh->now();
+        }
     }
     cg_destroy(h);
 }
@@ -198,7 +212,7 @@ int main(int argc, char* argv[]) {
     const char* genv = getenv("CONSENT_GPUS");
     if (genv) o.gpus = parse_gpus(genv);
     int opt;
-    while ((opt = getopt(argc, argv, "a:A:d:k:s:S:M:l:f:e:p:c:m:j:w:r:R:n:i:g:B:Pv")) != -1) {
+    while ((opt = getopt(argc, argv, "a:A:d:k:s:S:M:l:f:e:p:c:m:j:w:r:R:n:i:g:B:W:Pv")) != -1) {
         switch (opt) {
             case 'a': o.alignments = optarg; break;
             case 's': o.minSupport = atoi(optarg); break;
@@ -213,6 +227,7 @@ int main(int argc, char* argv[]) {
             case 'R': o.proof = optarg; break;
             case 'g': o.gpus = parse_gpus(optarg); break;
             case 'B': o.batch_mb = (size_t)std::max(1, atoi(optarg)); break;
+            case 'W': o.workers_per_gpu = (unsigned)std::max(1, atoi(optarg)); break;
             case 'P': o.polishing = true; break;
             case 'v': o.verbose = true; break;
             case 'M': case 'p': case 'j': case 'i': case 'd': case 'e': case 'w': case 'n': break;     // accepted, unused by the path
@@ -224,6 +239,8 @@ int main(int argc, char* argv[]) {
     if (o.alignments.empty() || o.reads.empty()) { fprintf(stderr, "%s: -a and -r are required\n", self); return EXIT_FAILURE; }
     if (o.gpus.empty()) o.gpus.push_back(0);
 
+    Shared sh;
+    sh.t0 = std::chrono::steady_clock::now();
     consent::ReadStore store;
     std::string err;
     if (!store.load(o.reads, &err)) { fprintf(stderr, "%s: %s\n", self, err.c_str()); return EXIT_FAILURE; }
@@ -235,12 +252,13 @@ int main(int argc, char* argv[]) {
     consent::PafStream paf(o.alignments, batch_bytes);
     if (!paf.ok()) { fprintf(stderr, "%s: cannot open %s\n", self, o.alignments.c_str()); return EXIT_FAILURE; }
 
-    BatchQueue queue(2 * o.gpus.size());
+    const double t_loaded = sh.now();
+    BatchQueue queue(2 * o.gpus.size() * o.workers_per_gpu);
     OrderedWriter writer;
-    Shared sh;
     sh.opt = &o; sh.store = &store; sh.queue = &queue; sh.writer = &writer;
     std::vector<std::thread> workers;
-    for (int g : o.gpus) workers.emplace_back(gpu_main, &sh, g);
+    for (unsigned w = 0; w < o.workers_per_gpu; ++w)
+        for (int g : o.gpus) workers.emplace_back(gpu_main, &sh, g);
     size_t seq = 0;
     {
         Batch b;
@@ -258,5 +276,12 @@ int main(int argc, char* argv[]) {
     if (o.verbose || sh.error_windows)
         fprintf(stderr, "%s: %zu batches, %llu piles, %llu windows on %zu GPU(s)%s\n", self, seq, sh.piles, sh.windows, o.gpus.size(),
                 sh.error_windows ? (", " + std::to_string(sh.error_windows) + " windows over a limit of this build were left uncorrected").c_str() : "");
+    if (o.verbose) {
+        const double span = sh.t_last - sh.t_first;
+        fprintf(stderr, "{\"gpus\": %zu, \"batches\": %zu, \"piles\": %llu, \"windows\": %llu, \"load_s\": %.3f, \"first_batch_at_s\": %.3f, "
+                        "\"processing_s\": %.3f, \"total_s\": %.3f, \"windows_per_s_processing\": %.0f, \"windows_per_s_total\": %.0f}\n",
+                o.gpus.size(), seq, sh.piles, sh.windows, t_loaded, sh.t_first, span, sh.now(), span > 0 ? sh.windows / span : 0.0,
+                sh.windows / sh.now());
+    }
     return EXIT_SUCCESS;
 }

@@ -69,10 +69,11 @@ _PINNED = {}          # (tag, device index) -> pinned host staging tensor, grown
 
 def _pinned(tag: str, nbytes: int):
     import torch
-    t = _PINNED.get(tag)
+    key = (tag, torch.cuda.current_device() if torch.cuda.is_available() else -1)
+    t = _PINNED.get(key)
     if t is None or t.numel() < nbytes:
         t = torch.empty(max(nbytes, 1) + max(nbytes, 1) // 4, dtype=torch.uint8, pin_memory=True)
-        _PINNED[tag] = t
+        _PINNED[key] = t
     return t
 
 
@@ -137,6 +138,10 @@ def gather_results(local: Results, device=None, group=None, with_solid: bool = T
         o += len(c)
     gathered = [torch.empty(max_len, dtype=torch.uint8, device=device) for _ in range(world)] if rank == 0 else None
     dist.gather(buf, gathered, dst=0, group=group)
+    if on_gpu:
+        # the send buffer was filled by non-blocking copies out of library-owned pinned result buffers: they must have been read
+        # before the caller may drop `local` (cg_free_results hands them back to the pool for the next call's downloads)
+        torch.cuda.current_stream().synchronize()
     if rank != 0:
         return None
     parts = []

@@ -115,6 +115,13 @@ const char* cg_last_error(const cg_handle* h);   /* h may be NULL: last create e
  * "chunk_max_windows", "lanes"), resident warps of the POA tiers ("poa_c1_warps", "poa_g_warps", "poa_wide{1,2}_warps"),
  * last-resort POA scratch ("poa_tier{1,2}_{warps,nodes,cells}"). */
 int         cg_set_option(cg_handle* h, const char* key, long long value);
+/* Two more options change what crosses the bus, not what is computed:
+ *   "input_2bit" 1          cg_upload / cg_correct_windows read `bases` as 2 bits per base (base i of the batch at bits 2 (i & 3) of byte
+ *                           i >> 2; A 0 C 1 G 2 T 3 — cg_pack_bases_2bit), the form the reference's own read index keeps reads in
+ *                           (src/utils.cpp:21-54): a quarter of the bytes over PCIe, expanded on the device.  seq_off stays in bases.
+ *   "results_with_solid" 0  the solid k-mer lists are not downloaded (solid_off reads all zeros); they stay in HBM, where
+ *                           cg_reanchor_reads / cg_finish_reads given the live results read them. */
+void        cg_pack_bases_2bit(const char* ascii, uint64_t n, uint8_t* out, int threads);
 
 /* One-shot call: host buffers in, host buffers out (H2D, kernels, D2H inside).
  * This is the batched equivalent of calling computeConsensusReadCorrection on

@@ -141,3 +141,21 @@ def test_emulated_window_over_a_limit_comes_back_as_its_template_and_the_batch_g
         assert got.consensus(w) == bytes(b.bases[:int(b.seq_off[1])]).decode()
         assert got.solid(w) == []
     assert cor.counters()["error_windows"] == 2
+
+
+def test_emulated_2bit_input_and_resident_solid_lists_do_not_change_results(emu, oracle):
+    """"input_2bit": a quarter of the bytes over the bus; "results_with_solid" 0: the solid lists stay in HBM, where the
+    re-anchoring reads them.  Neither changes a byte of what is computed."""
+    from consent_b200.synth import synth_reads
+    batch, reads = synth_reads(5, 8, truth_len=2300, seed=77)
+    want, _ = oracle.correct_windows(batch, threads=4)
+    want_reads, _ = oracle.reanchor_reads(batch, want, reads, threads=4)
+    cor = emu(chunk_max_windows=7)                          # several chunks: their base ranges do not start on 4-base boundaries
+    cor.set_option("input_2bit", 1)
+    got = cor.correct_windows(cor.pack_2bit(batch))
+    assert_same(got, want, "2-bit packed input")
+    cor.set_option("results_with_solid", 0)
+    live = cor.correct_windows(cor.pack_2bit(batch))
+    assert all(live.consensus(w) == want.consensus(w) for w in range(want.n_windows))
+    assert int(live.solid_off[-1]) == 0
+    assert cor.reanchor_reads(batch, live, reads).equals(want_reads)
