@@ -39,7 +39,10 @@ typedef int32_t i32;
 #define CG_NONE16 0xffffu
 
 // ---- limits of this build (exceeding one -> CG_ERR_CAPACITY, never a silent wrong answer)
-#define CG_KMAX 9u            // direct-addressed count table: 4^k <= 2^18
+#define CG_KMAX 9u            // k_index counts k-mers of up to this length in a direct-addressed table (4^k <= 2^18); longer ones
+                              // (k <= CG_KMAX_HASHED, the reference's own limit: 1 << 2k, BMEAN/bmean.cpp:46) in a hash table
+#define CG_KMAX_HASHED 15u
+#define CG_IDX_SOLID_CAP 32768u   // hashed path: solid k-mers of one window that can be sorted in shared memory
 #define CG_TAB_BITS 15u       // 32768 u32 counters (128 KB of shared memory) per pass
 #define CG_TK_MAX 2047u       // template k-mers per window (anchor hash has 4096 slots)
 #define CG_N_MAX 4095u        // sequences per window
@@ -133,6 +136,8 @@ struct CgChunk {
     // the back, capacity of the array.  A job that outgrows a tier is pushed to the front of that tier's overflow queue.
     u32* qctl;
     uint2* jobs_s; uint2* jobs_m; uint2* jobs_w;
+    // k_index, k > CG_KMAX: open-addressing count tables in global memory, one per SM (slot = %smid), idx_cap entries each (power of two)
+    u32* idx_keys; u32* idx_counts; u32 idx_cap, idx_slots;
     // status
     u32* flags;
     CgCountersDev* counters;

@@ -24,6 +24,20 @@
 #include "k_split.cuh"
 #include "k_poa.cuh"
 #include "k_poa2.cuh"
+#ifndef CG_EMU
+#include <nvtx3/nvToolsExt.h>          // header-only NVTX 3: ranges per ABI call and per stage / lane (nsys, ncu --nvtx)
+struct CgNvtxRange {
+    explicit CgNvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~CgNvtxRange() { nvtxRangePop(); }
+};
+#define CG_NVTX(name) CgNvtxRange cg_nvtx_range_##__LINE__(name)
+#define CG_NVTX_PUSH(name) nvtxRangePushA(name)
+#define CG_NVTX_POP() nvtxRangePop()
+#else
+#define CG_NVTX(name)
+#define CG_NVTX_PUSH(name)
+#define CG_NVTX_POP()
+#endif
 #include "k_polish.cuh"
 #include "k_reanchor.cuh"
 #include "k_extract.cuh"
@@ -56,6 +70,7 @@ struct ChunkPlan {
     u64 pword_base, nwords;
     u64 solid_tot, slot_tot, pos_tot, reg_tot, arena_tot;
     u32 max_tk, max_n;
+    u64 max_occ;                        // largest pile (bases: an upper bound of its k-mer occurrences)
 };
 
 struct PoaTier {
@@ -99,6 +114,7 @@ struct Lane {
     DevBuf pwords, ptags, win, offs, solid_k, solid_c, slot_tpos, slot_kmer, anchors, chain, rel, pos, regions, arena, fin, visited;
     DevBuf jobs_s, jobs_m, jobs_3, jobs_w, jobs_r, jobs_x, ctl, off_fin, out_off;
     DevBuf g_mem, w1_mem, w2_mem; // per-warp global scratch of the POA tiers G (matrix only), W1 and W2
+    DevBuf idx_keys, idx_counts;  // k_index, k > 9: one open-addressing count table per SM
     u32* h_ctl = nullptr;        // pinned: flags + queue control + totals
     std::string err;
     int rc = 0;
@@ -276,6 +292,7 @@ int plan_chunks(cg_handle* h, bool ramp = false) {
             bytes += wbytes;
             c.solid_tot += a_solid; c.slot_tot += a_slot; c.pos_tot += a_pos; c.reg_tot += a_reg; c.arena_tot += a_arena;
             c.max_tk = std::max<u32>(c.max_tk, (u32)tk); c.max_n = std::max<u32>(c.max_n, N);
+            c.max_occ = std::max<u64>(c.max_occ, nocc);
             c.nwin++; ++w;
         }
         c.nwords = ((h->h_wbase[w] >> 4) + h->h_wsb[w]) - c.pword_base;
@@ -332,8 +349,9 @@ int run_chunk(cg_handle* h, Lane& L, size_t ci) {
         if (L.pool_at == L.evpool.size()) { cudaEvent_t e; cudaEventCreate(&e); L.evpool.push_back(e); }
         return L.evpool[L.pool_at++];
     };
-    auto span_begin = [&](int stage) { StageSpan sp{stage, ev(), ev()}; cudaEventRecord(sp.a, st); L.spans.push_back(sp); };
-    auto span_end = [&]() { cudaEventRecord(L.spans.back().b, st); };
+    static const char* const stage_names[CG_N_STAGES] = {"cg:pack", "cg:index", "cg:chain", "cg:split", "cg:poa", "cg:stitch", "cg:polish"};
+    auto span_begin = [&](int stage) { CG_NVTX_PUSH(stage_names[stage]); StageSpan sp{stage, ev(), ev()}; cudaEventRecord(sp.a, st); L.spans.push_back(sp); };
+    auto span_end = [&]() { cudaEventRecord(L.spans.back().b, st); CG_NVTX_POP(); };
     auto kbegin = [&](int kind, cudaStream_t ks, u32 n = 1) { KernelSpan sp{kind, ev(), ev(), n}; cudaEventRecord(sp.a, ks); L.kspans.push_back(sp); };
     auto kend = [&](cudaStream_t ks) { cudaEventRecord(L.kspans.back().b, ks); };
 
@@ -404,6 +422,18 @@ int run_chunk(cg_handle* h, Lane& L, size_t ci) {
     L.stage_launches[CG_STAGE_PACK] += 3;
     span_end();
 
+    if (h->p.mer_size > CG_KMAX) {                          // hashed k-mer counting: tables of >= 2 x the deepest pile's occurrences
+        u64 cap = 1024;
+        while (cap < 2 * cp.max_occ) cap <<= 1;
+        if (cap > (1ull << 26)) cap = 1ull << 26;           // deeper piles are flagged by the kernel (CG_WINDOW_ERROR)
+#ifndef CG_EMU
+        const u32 slots = 192;                              // indexed by %smid (B200: 148 SMs enabled, ids below 160)
+#else
+        const u32 slots = nwin;                             // the emulator has no SM ids: one table per window
+#endif
+        CKL(L.idx_keys.ensure((size_t)slots * cap * 4)); CKL(L.idx_counts.ensure((size_t)slots * cap * 4));
+        c.idx_keys = L.idx_keys.as<u32>(); c.idx_counts = L.idx_counts.as<u32>(); c.idx_cap = (u32)cap; c.idx_slots = slots;
+    }
     span_begin(CG_STAGE_INDEX);
     kbegin(CG_K_INDEX, st);
     CG_LAUNCH(k_index, nwin, CG_IDX_THREADS, CG_IDX_SMEM_BYTES, st, c);
@@ -692,7 +722,6 @@ int cg_create(int device, const cg_params* params, cg_handle** out) {
     if (!params || !out) { g_create_err = "null argument"; return CG_ERR_INVALID_ARG; }
     *out = nullptr;
     if (params->mer_size < 2 || params->mer_size > 15 || params->solid_thresh < 1) { g_create_err = "mer_size must be 2..15, solid_thresh >= 1"; return CG_ERR_INVALID_ARG; }
-    if (params->mer_size > CG_KMAX) { g_create_err = "mer_size > 9 is not supported by this build (direct-addressed k-mer table)"; return CG_ERR_CAPACITY; }
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) {
         g_create_err = "no usable CUDA device (this library has no CPU path)";
@@ -764,7 +793,7 @@ void cg_destroy(cg_handle* h) {
     for (Lane& L : h->lane) {
         DevBuf* lb[] = {&L.pwords, &L.ptags, &L.win, &L.offs, &L.solid_k, &L.solid_c, &L.slot_tpos, &L.slot_kmer, &L.anchors, &L.chain, &L.rel,
                         &L.pos, &L.regions, &L.arena, &L.fin, &L.visited, &L.jobs_s, &L.jobs_m, &L.jobs_3, &L.jobs_w, &L.jobs_r, &L.jobs_x,
-                        &L.ctl, &L.off_fin, &L.out_off, &L.g_mem, &L.w1_mem, &L.w2_mem};
+                        &L.ctl, &L.off_fin, &L.out_off, &L.g_mem, &L.w1_mem, &L.w2_mem, &L.idx_keys, &L.idx_counts};
         for (DevBuf* b : lb) b->release();
         for (cudaEvent_t e : L.evpool) cudaEventDestroy(e);
         for (cudaEvent_t e : {L.ev_fork, L.ev_gather, L.ev_end, L.ev_tail, L.ev_join[0], L.ev_join[1], L.ev_join[2]}) if (e) cudaEventDestroy(e);
@@ -912,6 +941,7 @@ int upload_impl(cg_handle* h, const cg_batch* in, bool wait) {
 
 // Chunks ci = lane, lane + n_lanes, ... on lane `li` (its own host thread when there are two lanes).
 void lane_main(cg_handle* h, int li, int n_lanes) {
+    CG_NVTX(li == 0 ? "cg:lane0" : "cg:lane1");
     Lane& L = h->lane[li];
     cudaSetDevice(h->device);
     L.rc = CG_OK;
@@ -1035,11 +1065,13 @@ extern "C" {
 
 int cg_upload(cg_handle* h, const cg_batch* in) {
     if (!h) return CG_ERR_INVALID_ARG;
+    CG_NVTX("cg_upload");
     return upload_impl(h, in, true);
 }
 
 int cg_run(cg_handle* h) {
     if (!h) return CG_ERR_INVALID_ARG;
+    CG_NVTX("cg_run");
     if (!h->uploaded) { h->err = "cg_run before cg_upload"; return CG_ERR_STATE; }
     h->stream_out = nullptr;
     return run_impl(h);
@@ -1047,6 +1079,7 @@ int cg_run(cg_handle* h) {
 
 int cg_download(cg_handle* h, cg_results* out) {
     if (!h || !out) return CG_ERR_INVALID_ARG;
+    CG_NVTX("cg_download");
     if (!h->ran) { h->err = "cg_download before a successful cg_run"; return CG_ERR_STATE; }
     cudaSetDevice(h->device);
     const u32 W = h->W;
@@ -1080,6 +1113,7 @@ void cg_free_results(cg_results* r) {
 // H2D of chunk i+1, the kernels of chunk i and D2H of chunk i-1 overlap (three streams).
 int cg_correct_windows(cg_handle* h, const cg_batch* in, cg_results* out) {
     if (!h || !out) return CG_ERR_INVALID_ARG;
+    CG_NVTX("cg_correct_windows");
     int rc = upload_impl(h, in, false);
     if (rc != CG_OK) return rc;
     HostResults* r = nullptr;
@@ -1103,6 +1137,7 @@ int cg_correct_windows(cg_handle* h, const cg_batch* in, cg_results* out) {
 static int reanchor_impl(cg_handle* h, const cg_batch* windows, const cg_results* cons, const cg_reads* reads, u32 trim_mer, cg_corrected* out,
                          bool on_device = false) {
     if (!h || !out) return CG_ERR_INVALID_ARG;
+    CG_NVTX("cg_reanchor_reads");
     if (!windows || !cons || !reads || !reads->read_win_begin || !reads->read_off || !windows->win_seq_begin || (!on_device && !windows->seq_off)) {
         h->err = "null argument"; return CG_ERR_INVALID_ARG;
     }
@@ -1284,6 +1319,7 @@ int cg_finish_reads(cg_handle* h, const cg_batch* windows, const cg_results* con
 // The tail of the chain cg_upload_piles -> cg_run on one handle without taking the windows, the results or the reads through the host.
 int cg_finish_resident(cg_handle* h, uint32_t trim_mer, cg_corrected* out) {
     if (!h || !out) return CG_ERR_INVALID_ARG;
+    CG_NVTX("cg_finish_resident");
     if (!h->uploaded || !h->ran || !h->ex_valid) { h->err = "cg_finish_resident needs cg_upload_piles and cg_run on this handle"; return CG_ERR_STATE; }
     cudaSetDevice(h->device);
     cudaStream_t st = h->lane[0].stream;
@@ -1329,6 +1365,7 @@ struct HostPileSet { std::vector<u32> pile_read, pile_qlen, ovb, res; std::vecto
 
 int cg_ingest_paf(cg_handle* h, const char* paf, uint64_t nbytes, const cg_read_names* names, uint32_t max_support, cg_pile_set* out) {
     if (!h || !out) return CG_ERR_INVALID_ARG;
+    CG_NVTX("cg_ingest_paf");
     if (!names || !names->name_off || (nbytes && !paf) || (names->n_reads && !names->names)) { h->err = "null argument"; return CG_ERR_INVALID_ARG; }
     if (max_support == 0) { h->err = "max_support must be at least 1"; return CG_ERR_INVALID_ARG; }
     if (nbytes && paf[nbytes - 1] != '\n') {
@@ -1491,6 +1528,7 @@ int cg_set_read_store(cg_handle* h, uint32_t n_store, const uint64_t* store_off,
 
 int cg_upload_piles(cg_handle* h, const cg_piles* P) {
     if (!h) return CG_ERR_INVALID_ARG;
+    CG_NVTX("cg_upload_piles");
     const bool resident = P && !P->store_off && !P->store_bases;     // the store cg_set_read_store left on the device
     if (!P || !P->pile_ov_begin || (P->n_piles && (!P->pile_read || !P->pile_qlen)) ||
         (!resident && (!P->store_off || (P->n_store && !P->store_bases)))) {

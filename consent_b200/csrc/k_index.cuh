@@ -54,8 +54,90 @@ __global__ void __launch_bounds__(CG_IDX_THREADS, 1) k_index(CgChunk c) {
     u32 nsolid = 0;
     const u32* pw;
     const u32* pt;
-    const bool bucketed = W.n_occ <= CG_IDX_BUCKET_CAP && 2 * k > CG_IDX_BKT_BITS;
-    if (bucketed) {
+    const bool hashed = k > CG_KMAX;
+    const bool bucketed = !hashed && W.n_occ <= CG_IDX_BUCKET_CAP && 2 * k > CG_IDX_BKT_BITS;
+    if (hashed) {
+        // ---- k = 10 .. 15: 4^k keys do not fit a direct table.  Every occurrence goes into an open-addressing table in global
+        // memory (one table per SM, L2-resident: atomicCAS claims the key, atomicAdd counts), the template's k-mers are looked up,
+        // the solid keys are collected, sorted in shared memory (bitonic, <= 32768 keys) and written in key order with their counts.
+        pw = c.pwords + g0;
+        pt = c.ptags + g0;
+        u32 slot;
+#ifndef CG_EMU
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(slot));
+#else
+        slot = blockIdx.x;
+#endif
+        const u32 cap = c.idx_cap, hmask = cap - 1u;
+        bool ovf = slot >= c.idx_slots || (u64)2 * W.n_occ > (u64)cap;
+        u32* hk = c.idx_keys + (size_t)(ovf ? 0u : slot) * cap;
+        u32* hc = c.idx_counts + (size_t)(ovf ? 0u : slot) * cap;
+        if (!ovf) {
+            for (u32 i = tid; i < cap; i += T) { hk[i] = CG_NONE32; hc[i] = 0; }
+            for (u32 p = tid; p < tk; p += T) { tkmer[p] = cg_kmer_at(pw[p >> 4], pw[(p >> 4) + 1], p & 15u, k); tcount[p] = 0; }
+            if (tid == 0) misc[0] = 0;
+            __syncthreads();
+            for (u32 g = tid; g < nw; g += T) {
+                const u32 tag = pt[g];
+                if (tag == CG_NONE32) continue;
+                const u32 nv = (tag & 15u) + 1;
+                const u32 w0 = pw[g], w1 = pw[g + 1];
+                for (u32 b = 0; b < nv; ++b) {
+                    const u32 km = cg_kmer_at(w0, w1, b, k);
+                    u32 hh = (km * 2654435761u) & hmask;
+                    for (;;) {
+                        const u32 old = atomicCAS(&hk[hh], CG_NONE32, km);
+                        if (old == CG_NONE32 || old == km) { atomicAdd(&hc[hh], 1u); break; }
+                        hh = (hh + 1) & hmask;
+                    }
+                }
+            }
+            __syncthreads();
+            for (u32 p = tid; p < tk; p += T) {
+                const u32 km = tkmer[p];
+                u32 hh = (km * 2654435761u) & hmask;
+                while (hk[hh] != km) hh = (hh + 1) & hmask;               // the template's own k-mers are all in the table
+                tcount[p] = hc[hh];
+            }
+            // solid keys -> tab[] (any order), then sorted
+            for (u32 i = tid; i < cap; i += T) {
+                if (hk[i] != CG_NONE32 && hc[i] >= solid_thr) {
+                    const u32 at = atomicAdd(&misc[0], 1u);
+                    if (at < CG_IDX_SOLID_CAP) tab[at] = hk[i];
+                }
+            }
+            __syncthreads();
+            nsolid = misc[0];
+            if (nsolid > CG_IDX_SOLID_CAP) ovf = true;
+        }
+        if (ovf) {                                   // more k-mers than this path holds: the window is left uncorrected (CG_WINDOW_ERROR)
+            if (tid == 0) { CgWin* Wg = &c.win[w]; Wg->bad = 1; Wg->n_solid = 0; Wg->n_cand = 0; Wg->n_alive = 0; }
+            return;
+        }
+        u32 npow = 1;
+        while (npow < nsolid) npow <<= 1;
+        for (u32 i = nsolid + tid; i < npow; i += T) tab[i] = CG_NONE32;
+        __syncthreads();
+        for (u32 kk = 2; kk <= npow; kk <<= 1)
+            for (u32 j = kk >> 1; j > 0; j >>= 1) {
+                for (u32 i = tid; i < npow; i += T) {
+                    const u32 l = i ^ j;
+                    if (l > i) {
+                        const u32 a = tab[i], b = tab[l];
+                        if (((i & kk) == 0) == (a > b)) { tab[i] = b; tab[l] = a; }
+                    }
+                }
+                __syncthreads();
+            }
+        for (u32 i = tid; i < nsolid; i += T) {
+            const u32 km = tab[i];
+            u32 hh = (km * 2654435761u) & hmask;
+            while (hk[hh] != km) hh = (hh + 1) & hmask;
+            c.solid_k[solid_base + i] = km;
+            c.solid_c[solid_base + i] = hc[hh];
+        }
+        __syncthreads();
+    } else if (bucketed) {
         // shared memory: [table 8192 u32][histogram + cursors 2 x 512 u32][bucket store CAP u16][tkmer][tcount][misc]
         u32* whist = tab + 8192;                  // [warp][bucket] counts, then the bucket bases at [512 ..]
         u32* cursor = whist + 512;
@@ -266,7 +348,7 @@ __global__ void __launch_bounds__(CG_IDX_THREADS, 1) k_index(CgChunk c) {
     u32* hkey = tab + 8192;                 // 4096 keys
     u16* hval = (u16*)(tab + 12288);        // 4096 slots
     u32* scnt = tab + 14336;                // count by slot
-    const u32 bm_words = (1u << (2 * k)) >= 32 ? (1u << (2 * k)) / 32 : 1;
+    const u32 bm_words = hashed ? 0u : ((1u << (2 * k)) >= 32 ? (1u << (2 * k)) / 32 : 1);      // pre-filter of the position sweep (4^k bits)
     for (u32 i = tid; i < bm_words; i += T) bitmap[i] = 0;
     for (u32 i = tid; i < 4096; i += T) hkey[i] = CG_NONE32;
     const u64 slot_base = c.off_slot[w];
@@ -288,7 +370,7 @@ __global__ void __launch_bounds__(CG_IDX_THREADS, 1) k_index(CgChunk c) {
             scnt[slot] = tcount[p];
             c.slot_tpos[slot_base + slot] = (u16)p;
             c.slot_kmer[slot_base + slot] = km;
-            atomicOr(&bitmap[km >> 5], 1u << (km & 31u));
+            if (!hashed) atomicOr(&bitmap[km >> 5], 1u << (km & 31u));
             u32 h = (km * 2654435761u) >> 20;
             for (;;) {
                 const u32 old = atomicCAS(&hkey[h], CG_NONE32, km);
@@ -316,10 +398,10 @@ __global__ void __launch_bounds__(CG_IDX_THREADS, 1) k_index(CgChunk c) {
             const u32 w0 = pw[g], w1 = pw[g + 1];
             for (u32 b = 0; b < nv; ++b) {
                 const u32 km = cg_kmer_at(w0, w1, b, k);
-                if (!((bitmap[km >> 5] >> (km & 31u)) & 1u)) continue;
+                if (!hashed && !((bitmap[km >> 5] >> (km & 31u)) & 1u)) continue;
                 u32 h = (km * 2654435761u) >> 20;
-                while (hkey[h] != km) h = (h + 1) & 4095u;
-                pos[(size_t)r * C + hval[h]] = (u16)(16 * wi + b + 1);
+                while (hkey[h] != km && hkey[h] != CG_NONE32) h = (h + 1) & 4095u;
+                if (hkey[h] == km) pos[(size_t)r * C + hval[h]] = (u16)(16 * wi + b + 1);
             }
         }
     }

@@ -16,7 +16,7 @@
 // Same command line as the reference binaries (getopt string of src/main.cpp:29; -M, -p, -j, -i, -d, -e, -w, -n are accepted and,
 // as in the reference's hot path, without effect on the output: -j sizes the reference's thread pool, here the GPUs do the work).
 // Extra options: -g LIST  CUDA devices, e.g. "0,1,2,3" or "all" (default: device 0; also CONSENT_GPUS)
-//                -B MB    PAF text per batch (default 48)
+//                -B MB    PAF text per batch (default: file size / (6 x workers), between 256 KB and 48 MB; always whole piles)
 //                -W N     host threads (each with its own handle) per GPU (default 2: one batch's host phases run under the other's kernels)
 // The binary is the polisher when it is called as *polishing* (or with -P): it never trims (src/CONSENT-polishing.cpp:19).
 // Reads are sharded over the GPUs batch by batch; nothing is exchanged between GPUs during the computation, the corrected reads of a
@@ -49,7 +49,7 @@ struct Options {
              windowOverlap = 50;                                                    // src/main.cpp:17-26
     std::vector<int> gpus;
     unsigned workers_per_gpu = 2;       // host threads (each with its own handle) per GPU: one batch's host phases overlap the other's kernels
-    size_t batch_mb = 48;
+    size_t batch_mb = 0;                // 0: sized from the PAF file so that every worker gets several batches (at most 48 MB)
     bool polishing = false, verbose = false;
 };
 
@@ -248,6 +248,12 @@ int main(int argc, char* argv[]) {
     store.finish();
 
     size_t batch_bytes = o.batch_mb << 20;
+    if (!batch_bytes) {                                                     // ~6 batches per worker, between 256 KB and 48 MB (a batch
+        size_t fsize = 0;                                                   // always holds whole piles: at least one)
+        if (FILE* pf = fopen(o.alignments.c_str(), "rb")) { fseek(pf, 0, SEEK_END); const long e = ftell(pf); fsize = e > 0 ? (size_t)e : 0; fclose(pf); }
+        const size_t workers = o.gpus.size() * o.workers_per_gpu;
+        batch_bytes = std::min<size_t>((size_t)48 << 20, std::max<size_t>((size_t)256 << 10, fsize / (6 * workers)));
+    }
     if (const char* bb = getenv("CONSENT_BATCH_BYTES")) batch_bytes = (size_t)std::max(1ll, atoll(bb));      // tests: many small batches
     consent::PafStream paf(o.alignments, batch_bytes);
     if (!paf.ok()) { fprintf(stderr, "%s: cannot open %s\n", self, o.alignments.c_str()); return EXIT_FAILURE; }

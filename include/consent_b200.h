@@ -64,7 +64,8 @@ typedef enum cg_status {
  * Defaults of the CONSENT-correct wrapper: k=9, solid=4, commonKMers=8,
  * minAnchors=2 (reference CONSENT-correct:42-50). */
 typedef struct cg_params {
-    uint32_t mer_size;      /* -k  merSize      : k-mer length, 2..15 (reference: 1<<(2k) overflows at 16, bmean.cpp:46) */
+    uint32_t mer_size;      /* -k  merSize      : k-mer length, 2..15 (reference: 1<<(2k) overflows at 16, bmean.cpp:46);
+                               up to 9 the k-mers are counted in a direct-addressed table, 10..15 in a hash table */
     uint32_t solid_thresh;  /* -f  solidThresh  : min occurrences for a solid k-mer     */
     uint32_t common_kmers;  /* -c  commonKMers  : anchor support cap; S = min(c, N/2)   */
     uint32_t min_anchors;   /* -A  minAnchors   : MSABMAAC bails out if regions < this  */

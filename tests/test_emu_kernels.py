@@ -159,3 +159,12 @@ def test_emulated_2bit_input_and_resident_solid_lists_do_not_change_results(emu,
     assert all(live.consensus(w) == want.consensus(w) for w in range(want.n_windows))
     assert int(live.solid_off[-1]) == 0
     assert cor.reanchor_reads(batch, live, reads).equals(want_reads)
+
+
+@pytest.mark.parametrize("k", [11, 15])
+def test_emulated_long_kmers_hashed_index(emu, oracle, k):
+    """k = 10 .. 15: the hash-table path of k_index (the direct table holds 4^k <= 2^18 keys)."""
+    p = Params(mer_size=k)
+    batch = concat([synth_windows(3, 20, seed=91), synth_windows(1, 150, seed=92), synth_windows(3, 12, seed=93, profile="ONT")])
+    want, _ = oracle.correct_windows(batch, p, threads=4)
+    assert_same(emu(p).correct_windows(batch), want, f"k = {k}")

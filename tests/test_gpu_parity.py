@@ -52,6 +52,25 @@ def test_gpu_parameter_variants(gpu, oracle):
         assert_same(gpu(p).correct_windows(batch), want, str(p))
 
 
+@pytest.mark.parametrize("k", [10, 11, 13, 15])
+def test_gpu_long_kmers_hashed_index(gpu, oracle, k):
+    """merSize 10 .. 15 (--merSize is a user flag, CONSENT-correct:60-151; the reference allows k <= 15, BMEAN/bmean.cpp:46): k-mers
+    counted in the hash table of k_index instead of the direct table; every stage downstream (anchors, polish, re-anchoring) sees
+    longer k-mers."""
+    from consent_b200.synth import synth_reads
+    p = Params(mer_size=k)
+    cor = gpu(p)
+    batch = concat([synth_windows(24, 20, seed=91), synth_windows(6, 150, seed=92), synth_windows(16, 12, seed=93, profile="ONT"),
+                    synth_windows(8, 60, seed=94, profile="ONT"), edge_batch(4)])
+    want, _ = oracle.correct_windows(batch, p, threads=32)
+    assert_same(cor.correct_windows(batch), want, f"k = {k}")
+    rb, reads = synth_reads(12, 15, truth_len=3000, seed=95, profile="ONT")
+    live = cor.correct_windows(rb)
+    wres, _ = oracle.correct_windows(rb, p, threads=32)
+    wreads, _ = oracle.reanchor_reads(rb, wres, reads, p, threads=16)
+    assert cor.reanchor_reads(rb, live, reads).equals(wreads)
+
+
 def test_gpu_mixed_depth_batch_and_chunking(gpu, oracle):
     batch = concat([synth_windows(40, 8, seed=62), synth_windows(30, 3, seed=63), synth_windows(6, 150, seed=64),
                     synth_windows(20, 20, seed=65), edge_batch(4)])
