@@ -342,6 +342,20 @@ def bench_ingest(cor, n_reads: int, cores: int, steps: int, hbm_peak: float) -> 
     return out
 
 
+def full_stream_parity(res, name: str, n_windows: int, n_seqs: int) -> dict:
+    """The WHOLE output of a run against the unmodified reference's: stream digests committed under tests/golden/stream_digests.json
+    (made once with oracle/_ref by tests/golden/make_stream_digests.py) — every window of the batch, not a sample."""
+    try:
+        gold = json.load(open(os.path.join(ROOT, "tests", "golden", "stream_digests.json")))[name]
+    except Exception as e:
+        return {"checked": False, "why": f"no golden digest: {e!r}"}
+    if gold["windows"] != n_windows or gold["seqs_per_window"] != n_seqs:
+        return {"checked": False, "why": f"golden digest is for {gold['windows']} x {gold['seqs_per_window']}, this run is {n_windows} x {n_seqs}"}
+    hc, hs = res.stream_digests()
+    return {"checked": True, "windows": n_windows, "consensus_equal_to_reference": hc.hexdigest() == gold["consensus_sha256"],
+            "solid_lists_equal_to_reference": hs.hexdigest() == gold["solid_sha256"], "golden": "tests/golden/stream_digests.json"}
+
+
 def kernel_table(acc: dict, steps: int, ab_by_kernel: dict) -> dict:
     """Per kernel: ms per step (sum of its launches' own CUDA-event durations), launches per step, algorithmic GB/s."""
     out = {}
@@ -410,12 +424,14 @@ def bench_config2(cor, cores: int, steps: int, warmup: int, peak: float, peak_sr
         res = cor.correct_windows(batch)
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / steps
+    parity = full_stream_parity(res, "config2", W, N)
     out = {"workload": "config2: 10000 synthetic 500 bp windows x 20 seqs/pile, PB 15% error, seed 42 (steps re-run the same 100 MB batch: it fits L2 "
                        "once, the 3.6 MB score matrices per window do not)",
            "windows": W, "value": W * steps / (dev_ms / 1e3), "unit": "windows/s", "ms_per_step": dev_ms / steps,
            "e2e": {"value": W / e2e_s, "unit": "windows/s", "h2d_bytes_per_step": int(batch.n_bases + batch.seq_off.nbytes + batch.win_seq_begin.nbytes),
                    "d2h_bytes_per_step": int(res.cons.nbytes + res.status.nbytes + res.cons_off.nbytes + res.solid_off.nbytes + res.solid_kmer.nbytes + res.solid_count.nbytes)},
            "roofline": roofline_row(ktab, peak, peak_src, traffic_json, dev_ms / steps),
+           "parity_full_stream": parity,
            "counters_per_step": counters}
     try:
         checker, kind = cpu_reference(batch, cores)
@@ -572,6 +588,7 @@ def main():
     h2d_ascii = int(batch.n_bases + batch.seq_off.nbytes + batch.win_seq_begin.nbytes)
     d2h_ascii = int(res.cons.nbytes + res.status.nbytes + res.cons_off.nbytes + res.solid_off.nbytes + res.solid_kmer.nbytes + res.solid_count.nbytes)
     res_ascii = res
+    parity_full = full_stream_parity(res_ascii, "config3", args.windows, args.seqs) if rank == 0 else None
     packed = cor.pack_2bit(batch, threads=max(1, min(cores // max(world, 1), 32)), pinned=True)
     cor.set_option("input_2bit", 1)
     cor.set_option("results_with_solid", 0)
@@ -665,7 +682,7 @@ def main():
                               "d2h_bytes_per_step": d2h_ascii, "input": "ASCII piles (1 byte per base), pinned",
                               "output": "consensus + solid k-mer lists (round 1's e2e)"},
            "gpu_launches": launches, "wall_ms_per_step": wall_ms / args.steps,
-           "roofline": roofline, "cpu_baseline": cpu,
+           "roofline": roofline, "cpu_baseline": cpu, "parity_full_stream": parity_full,
            "counters_per_step": counters, "config2": config2, "reanchor": reanchor, "extract": extract, "ingest": ingest}
     emit(json.dumps(out))
     if world > 1:

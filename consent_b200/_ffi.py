@@ -468,6 +468,18 @@ class Results:
                 return w
         return None if self.n_windows == other.n_windows else min(self.n_windows, other.n_windows)
 
+    def stream_digests(self, running=None):
+        """Slice-invariant digests of a window stream: per window (length, consensus bytes, status) into one sha256 and
+        (count, k-mers, counts) of its solid list into another.  Feeding the slices of a stream in order (pass the returned
+        objects back in) gives the digest of the whole stream: tests/golden/stream_digests.json holds the reference's."""
+        import hashlib
+        hc, hs = running if running is not None else (hashlib.sha256(), hashlib.sha256())
+        lens = np.diff(self.cons_off.astype(np.int64)).astype(np.uint32)
+        hc.update(lens.tobytes()); hc.update(np.ascontiguousarray(self.cons).tobytes()); hc.update(np.ascontiguousarray(self.status).tobytes())
+        ns = np.diff(self.solid_off.astype(np.int64)).astype(np.uint32)
+        hs.update(ns.tobytes()); hs.update(np.ascontiguousarray(self.solid_kmer).tobytes()); hs.update(np.ascontiguousarray(self.solid_count).tobytes())
+        return hc, hs
+
     def digest(self) -> str:
         """sha256 over every output byte in a canonical order ("checksum of checksums" for big runs)."""
         import hashlib

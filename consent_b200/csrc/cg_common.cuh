@@ -206,7 +206,7 @@ __device__ __forceinline__ u32 cg_block_scan(u32 v, u32* scratch, u32* total) {
 }
 
 // comparable(x, mean)  BMEAN/bmean.cpp:286-295 (fp64 on purpose: mean may be 0 -> inf/NaN semantics)
-__device__ __forceinline__ bool cg_comparable_mean(double x, double mean) {
+__host__ __device__ __forceinline__ bool cg_comparable_mean(double x, double mean) {
     if (fabs(x - mean) < 5) return true;
     if (x / mean < 0.5 || x / mean > 2) return false;
     return true;
@@ -231,10 +231,10 @@ struct CgWinView {
     const u32* rel;       // integer means (average_distance_next_anchor)
     u32 N, C, nA;
 };
-__device__ __forceinline__ u32 cg_seq_len(const CgWinView& v, u32 r) { return (u32)(v.seq_off[r + 1] - v.seq_off[r]); }
+__host__ __device__ __forceinline__ u32 cg_seq_len(const CgWinView& v, u32 r) { return (u32)(v.seq_off[r + 1] - v.seq_off[r]); }
 
 // -> kept?  start/len of read r's piece in region g.
-__device__ __forceinline__ bool cg_eval_segment(const CgWinView& v, u32 g, u32 r, u32* start, u32* len) {
+__host__ __device__ __forceinline__ bool cg_eval_segment(const CgWinView& v, u32 g, u32 r, u32* start, u32* len) {
     u32 len_r = cg_seq_len(v, r);
     if (v.nA == 0) {                                  // bmean.cpp:477-481 : [ [], Reads ]
         if (g != 1) return false;

@@ -1747,6 +1747,80 @@ int cg_stage_ms(const cg_handle* h, float ms[CG_N_STAGES], uint32_t launches[CG_
     return CG_OK;
 }
 
+// Per-stage text dump of window w of the batch cg_run just processed, in the format of the oracle's / the reference harness's
+// dump (oracle/consent_oracle.h): S, M (solid list), T (template k-mers that survive fill + filter), A (chain), R (mean distances),
+// G (regions), g (their segments), c (their consensuses), C (the stitched consensus).  Test instrumentation: the workspaces of a
+// chunk are reused by the next one, so the batch must have been a single chunk.  *text is malloc'ed (free() it).
+int cg_debug_dump_window(cg_handle* h, uint32_t w, char** text) {
+    if (!h || !text) return CG_ERR_INVALID_ARG;
+    if (!h->ran || h->chunks.size() != 1 || w >= h->W) { h->err = "cg_debug_dump_window: needs a finished single-chunk run and a window of it"; return CG_ERR_STATE; }
+    cudaSetDevice(h->device);
+    Lane& L = h->lane[0];
+    const u32 nwin = h->chunks[0].nwin;
+    auto get = [&](void* dst, const void* src, size_t n) { return n ? cudaMemcpy(dst, src, n, cudaMemcpyDeviceToHost) : cudaSuccess; };
+    CgWin W;
+    CK(get(&W, L.win.as<CgWin>() + w, sizeof W));
+    u64 off[5][2];
+    for (int a = 0; a < 5; ++a) CK(get(off[a], L.offs.as<u64>() + (size_t)a * (nwin + 1) + w, 16));
+    const u64 o_solid = off[0][0], o_slot = off[1][0], o_pos = off[2][0], o_reg = off[3][0], o_arena = off[4][0];
+    const u32 N = W.n_seqs, C = W.n_cand, nA = W.n_chain, k = h->p.mer_size;
+    std::vector<u32> sk(W.n_solid), sc(W.n_solid), slot_kmer(C), rel(nA ? nA : 1);
+    std::vector<u16> anchors(W.n_alive), chain(nA), pos((size_t)N * C);
+    CK(get(sk.data(), L.solid_k.as<u32>() + o_solid, 4 * (size_t)W.n_solid)); CK(get(sc.data(), L.solid_c.as<u32>() + o_solid, 4 * (size_t)W.n_solid));
+    CK(get(slot_kmer.data(), L.slot_kmer.as<u32>() + o_slot, 4 * (size_t)C));
+    CK(get(anchors.data(), L.anchors.as<u16>() + o_slot, 2 * (size_t)W.n_alive)); CK(get(chain.data(), L.chain.as<u16>() + o_slot, 2 * (size_t)nA));
+    CK(get(rel.data(), L.rel.as<u32>() + o_slot, 4 * (size_t)(nA ? nA - 1 : 0)));
+    CK(get(pos.data(), L.pos.as<u16>() + o_pos, 2 * (size_t)N * C));
+    std::vector<u64> soff(N + 1);
+    CK(get(soff.data(), h->d_seq_off.as<u64>() + W.seq_begin, 8 * (size_t)(N + 1)));
+    std::vector<char> bases((size_t)(soff[N] - soff[0]) + 1);
+    CK(get(bases.data(), h->d_bases.as<char>() + soff[0], (size_t)(soff[N] - soff[0])));
+    const u64 base0 = soff[0];
+    for (u64& x : soff) x -= base0;
+    const u32 n_regions = nA ? nA + 1 : 2;
+    std::vector<CgRegion> regs(W.n_regions);
+    CK(get(regs.data(), L.regions.as<CgRegion>() + o_reg, sizeof(CgRegion) * (size_t)W.n_regions));
+    std::vector<char> arena((size_t)(off[4][1] - off[4][0]) + 1);
+    CK(get(arena.data(), L.arena.as<u8>() + o_arena, (size_t)(off[4][1] - off[4][0])));
+    std::string t;
+    char line[64];
+    const int S = (int)h->p.common_kmers < (int)N / 2 ? (int)h->p.common_kmers : (int)N / 2;
+    snprintf(line, sizeof line, "S %d\nM %u", S, W.n_solid); t += line;
+    for (u32 i = 0; i < W.n_solid; ++i) { snprintf(line, sizeof line, " %u:%u", sk[i], sc[i]); t += line; }
+    snprintf(line, sizeof line, "\nT %u", W.n_alive); t += line;
+    for (u32 i = 0; i < W.n_alive; ++i) { snprintf(line, sizeof line, " %u", slot_kmer[anchors[i]]); t += line; }
+    snprintf(line, sizeof line, "\nA %u", nA); t += line;
+    for (u32 i = 0; i < nA; ++i) { snprintf(line, sizeof line, " %u", slot_kmer[chain[i]]); t += line; }
+    snprintf(line, sizeof line, "\nR %u", nA ? nA - 1 : 0u); t += line;
+    for (u32 i = 0; i + 1 < nA; ++i) { snprintf(line, sizeof line, " %lld", (long long)rel[i]); t += line; }
+    snprintf(line, sizeof line, "\nG %u\n", n_regions); t += line;
+    std::string stacked;
+    if (W.n_regions) {                                      // 0: MSABMAAC bailed out (regions < minAnchors), nothing is dumped per region
+        CgWinView v;
+        v.seq_off = soff.data(); v.pos = pos.data(); v.chain = chain.data(); v.rel = rel.data(); v.N = N; v.C = C; v.nA = nA;
+        for (u32 g = 0; g < W.n_regions; ++g) {
+            std::string segs;
+            u32 n = 0;
+            for (u32 r = 0; r < N; ++r) {
+                u32 st = 0, ln = 0;
+                if (cg_eval_segment(v, g, r, &st, &ln)) { segs += ' '; segs.append(bases.data() + soff[r] + st, ln); ++n; }
+            }
+            snprintf(line, sizeof line, "g %u %u", g, n); t += line; t += segs; t += '\n';
+            const CgRegion& R = regs[g];
+            if (R.kind == CG_REG_EMPTY) continue;
+            std::string cons = R.kind == CG_REG_COPY ? std::string(bases.data() + soff[R.read] + R.start, R.len) : std::string(arena.data() + R.arena_off, R.cons_len);
+            snprintf(line, sizeof line, "c %u ", g); t += line; t += cons; t += '\n';
+            stacked += cons;
+        }
+    }
+    t += "C "; t += stacked; t += '\n';
+    (void)k;
+    *text = (char*)malloc(t.size() + 1);
+    if (!*text) return CG_ERR_OUT_OF_MEMORY;
+    memcpy(*text, t.c_str(), t.size() + 1);
+    return CG_OK;
+}
+
 int cg_get_kernel_stats(const cg_handle* h, cg_kernel_stats* out) {
     if (!h || !out) return CG_ERR_INVALID_ARG;
     *out = h->kstats;

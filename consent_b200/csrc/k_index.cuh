@@ -374,8 +374,9 @@ __global__ void __launch_bounds__(CG_IDX_THREADS, 1) k_index(CgChunk c) {
             u32 h = (km * 2654435761u) >> 20;
             for (;;) {
                 const u32 old = atomicCAS(&hkey[h], CG_NONE32, km);
-                if (old == CG_NONE32 || old == km) { hval[h] = (u16)slot; break; }
-                h = (h + 1) & 4095u;
+                if (old == CG_NONE32) { hval[h] = (u16)slot; break; }    // one writer per entry.  A k-mer that occurs twice in the template
+                if (old == km) break;                                     // keeps its first claimant's slot: neither slot can be alive
+                h = (h + 1) & 4095u;                                      // (count > reads holding it), whichever it is
             }
             ++slot;
         }

@@ -194,12 +194,14 @@ template <class T> __device__ CG_NOINLINE bool cg_poa2_dfs(const CgPoa2G<T>& s, 
             const u32 id = top & IDNONE;
             bool finish = (top & FIN) != 0;
             const MetaT m = s.meta(id);
+            VecT P = Pk::zero();
+            if (T::STORE == CG_P2_ALL_GLOBAL && !finish) P = s.pred(id);     // global graph: both loads of the node leave together
             const u32 nal = (u32)m & 3u;
             if (!finish) {
                 if (s.marks(id) == 2) { --sp; continue; }
                 const u32 sp0 = sp;
                 const u32 deg = ((u32)m >> 3) & 31u;
-                const VecT P = s.pred(id);
+                if (T::STORE != CG_P2_ALL_GLOBAL) P = s.pred(id);
                 if (sp + deg + 3 > T::SCAP) return false;
                 for (u32 e = 0; e < deg; ++e) {
                     const u32 b = Pk::get(P, e);
@@ -236,51 +238,104 @@ template <class T> __device__ CG_NOINLINE bool cg_poa2_dfs(const CgPoa2G<T>& s, 
 #define CG_P2_PREFETCH(p) ((void)(p))
 #endif
 
-// ------------------------------------------------------------------ traceback (lane 0)
+// ------------------------------------------------------------------ traceback (compact tiers), by the whole warp
 // simd_alignment_engine_impl.hpp:968-1004: diagonal over the predecessors in in-edge order, then vertical over them,
 // then horizontal.  Pairs are written in traceback order (last pair first) as node | qpos << W (all ones = none).
-template <class T> __device__ __forceinline__ u32 cg_poa2_traceback(const CgPoa2G<T>& s, const u8* seq, u32 Ws, u32 bi, u32 bj, bool* bad) {
+// Lane t looks at the cell the path reaches after t diagonal steps along the first-predecessor chain (row descriptors are in
+// shared memory), all lanes fetch their cell and its neighbours at once, a ballot finds how far the guess holds: those steps are
+// committed together, the first lane that disagrees decides the next cell.  A run of matches costs one round (~50 warp
+// instructions) instead of ~25 single-lane instructions per step (the wide tiers' version: k_poa2_wide.cuh).
+template <class T> __device__ CG_NOINLINE u32 cg_poa2_traceback(const CgPoa2G<T>& s, const u8* seq, u32 Ws, u32 bi, u32 bj, i32 M, bool* bad) {
     CG_P2_TYPES;
+    enum { STOP = 0, DIAG = 1, DIAG1 = 2, VERT = 3, VERT1 = 4, HORIZ = 5, MULTI = 6 };
+    const u32 lane = cg_lane();
     const i16* H = s.H();
     u32 i = bi, j = bj, n = 0;
-    i32 Hij = H[(size_t)i * Ws + j];
-    while (Hij != 0) {                                   // column 0 is all zeros, so j >= 1 in here
-        const typename Pk::Rdesc d = s.rdesc(i - 1);
-        const u32 deg = ((u32)d >> 8) & 0xffu;
-        const i32 sc = ((u32)d & 0xffu) == seq[j - 1] ? 5 : -10;
-        const i16* hl = H + (size_t)i * Ws + (j - 1);
-        u32 pi_ = i, pj_ = j - 1;
-        i32 Hp;
-        if (deg <= 1) {                                  // one predecessor row (row 0 if the node has no in-edge)
-            const u32 p = ((u32)d >> 16) & IDNONE;
-            const i16* hp = H + (size_t)p * Ws + (j - 1);
-            const i32 hd = hp[0], hv = hp[1], hh = hl[0];
-            if (Hij == hd + sc) { pi_ = p; Hp = hd; }
-            else if (Hij == hv - 4) { pi_ = p; pj_ = j; Hp = hv; }
-            else { Hp = hh; if (Hij != hh - 4) { *bad = true; return 0; } }
-        } else {
-            const VecT pr = s.prow(i - 1);
-            u32 pd = IDNONE, pv = IDNONE;
-            i32 hd_ = 0, hv_ = 0;
+    i32 Hij = M;
+    while (Hij != 0) {
+        u32 row = i >= lane ? i - lane : 0u;
+        u32 d = row ? (u32)s.rdesc(row - 1) : 0u;
+        u32 start = 0, nvalid = 32;
 #pragma unroll 1
-            for (u32 e = 0; e < deg && pd == IDNONE; ++e) {
-                const u32 p = Pk::get(pr, e);
-                const i16* hp = H + (size_t)p * Ws + (j - 1);
-                const i32 hd = hp[0], hv = hp[1];
-                if (Hij == hd + sc) { pd = p; hd_ = hd; }
-                if (pv == IDNONE && Hij == hv - 4) { pv = p; hv_ = hv; }
+        for (u32 it = 0;; ++it) {
+            const u32 brk = __ballot_sync(CG_FULL, row != 0 && ((d >> 16) & IDNONE) != row - 1) & (0xffffffffu << start);
+            if (!brk) break;
+            const u32 b = (u32)__ffs((int)brk) - 1u;
+            if (it == 3 || b == 31) { nvalid = b + 1; break; }
+            const u32 pb = __shfl_sync(CG_FULL, (d >> 16) & IDNONE, (int)b);
+            if (lane > b) {
+                const u32 back = lane - b - 1;
+                row = pb >= back ? pb - back : 0u;
+                d = row ? (u32)s.rdesc(row - 1) : 0u;
             }
-            if (pd != IDNONE) { pi_ = pd; Hp = hd_; }
-            else if (pv != IDNONE) { pi_ = pv; pj_ = j; Hp = hv_; }
-            else { Hp = hl[0]; if (Hij != Hp - 4) { *bad = true; return 0; } }
+            start = b + 1;
         }
-        if (n >= T::ALNCAP) { *bad = true; return 0; }  // cannot happen: a path visits a cell once
-        const u32 node = (u32)(d >> (16 + W)) & IDNONE;
-        s.work(n) = (ItemT)((i == pi_ ? IDNONE : node) | ((j == pj_ ? IDNONE : (j - 1)) << W));
+        const u32 col = j >= lane ? j - lane : 0u;
+        const bool live = row != 0 && col != 0;
+        const u32 p0 = (d >> 16) & IDNONE, deg = (d >> 8) & 0xffu;
+        u32 p1 = 0;
+        i32 own = 0, hl = 0, hd = 0, hv = 0, hd1 = -1, hv1 = -1, sc = 0;
+        if (live) {
+            const i16* hr = H + (size_t)row * Ws + col;
+            const i16* hp = H + (size_t)p0 * Ws + col;
+            own = hr[0]; hl = hr[-1]; hd = hp[-1]; hv = hp[0];
+            if (deg >= 2) { p1 = Pk::get(s.prow(row - 1), 1); const i16* hq = H + (size_t)p1 * Ws + col; hd1 = hq[-1]; hv1 = hq[0]; }
+            sc = (d & 0xffu) == seq[col - 1] ? 5 : -10;
+        }
+        const u32 node = (d >> (16 + W)) & IDNONE;
+        u32 code = STOP;
+        if (live && own != 0) {
+            if (own == hd + sc) code = DIAG;
+            else if (deg >= 2 && own == hd1 + sc) code = DIAG1;
+            else if (deg > 2) code = MULTI;
+            else if (own == hv - 4) code = VERT;
+            else if (deg == 2 && own == hv1 - 4) code = VERT1;
+            else code = HORIZ;
+        }
+        u32 stopm = __ballot_sync(CG_FULL, code != DIAG);
+        if (nvalid < 32) stopm |= 0xffffffffu << nvalid;
+        const u32 run = stopm ? (u32)__ffs((int)stopm) - 1u : 32u;
+        if (n + run + 1 > T::ALNCAP) { *bad = true; return 0; }          // cannot happen: a path visits a cell once
+        if (lane < run) s.work(n + lane) = (ItemT)(node | ((col - 1) << W));
+        n += run;
+        if (run == 32 || run == nvalid) {
+            const int src = (int)run - 1;
+            i = __shfl_sync(CG_FULL, p0, src); j = __shfl_sync(CG_FULL, col, src) - 1u; Hij = __shfl_sync(CG_FULL, hd, src);
+            continue;
+        }
+        const int src = (int)run;
+        const u32 xcode = __shfl_sync(CG_FULL, code, src);
+        if (xcode == STOP) break;
+        const u32 xrow = __shfl_sync(CG_FULL, row, src), xcol = __shfl_sync(CG_FULL, col, src), xnode = __shfl_sync(CG_FULL, node, src);
+        const i32 xown = __shfl_sync(CG_FULL, own, src), xhl = __shfl_sync(CG_FULL, hl, src);
+        u32 ni = xrow, nj = xcol;
+        i32 nH = 0;
+        if (xcode == DIAG1) { ni = __shfl_sync(CG_FULL, p1, src); nj = xcol - 1; nH = __shfl_sync(CG_FULL, hd1, src); }
+        else if (xcode == VERT) { ni = __shfl_sync(CG_FULL, p0, src); nH = __shfl_sync(CG_FULL, hv, src); }
+        else if (xcode == VERT1) { ni = __shfl_sync(CG_FULL, p1, src); nH = __shfl_sync(CG_FULL, hv1, src); }
+        else if (xcode == HORIZ) { nj = xcol - 1; nH = xhl; if (xown != xhl - 4) { *bad = true; return 0; } }
+        else {                                                            // three or more predecessors, no diagonal match among the first two
+            const u32 xdeg = __shfl_sync(CG_FULL, deg, src);
+            const i32 xsc = __shfl_sync(CG_FULL, sc, src);
+            const VecT pr = s.prow(xrow - 1);
+            u32 pe = 0;
+            i32 ed = -1, ev = -1;
+            if (lane < xdeg) {
+                pe = Pk::get(pr, lane);
+                const i16* hp = H + (size_t)pe * Ws + xcol;
+                ed = hp[-1]; ev = hp[0];
+            }
+            const u32 md = __ballot_sync(CG_FULL, lane < xdeg && xown == ed + xsc);
+            const u32 mv = __ballot_sync(CG_FULL, lane < xdeg && xown == ev - 4);
+            if (md) { const int e = __ffs((int)md) - 1; ni = __shfl_sync(CG_FULL, pe, e); nj = xcol - 1; nH = __shfl_sync(CG_FULL, ed, e); }
+            else if (mv) { const int e = __ffs((int)mv) - 1; ni = __shfl_sync(CG_FULL, pe, e); nH = __shfl_sync(CG_FULL, ev, e); }
+            else { nj = xcol - 1; nH = xhl; if (xown != xhl - 4) { *bad = true; return 0; } }
+        }
+        if (lane == 0) s.work(n) = (ItemT)((ni == xrow ? IDNONE : xnode) | ((nj == xcol ? IDNONE : (xcol - 1)) << W));
         ++n;
-        i = pi_; j = pj_;
-        Hij = Hp;
+        i = ni; j = nj; Hij = nH;
     }
+    __syncwarp();
     return n;
 }
 
@@ -706,9 +761,8 @@ __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s
                 if (M > 0) n_aln = cg_poa2w_traceback(s, seq, CHw, bi, bj, M, &bad);     // the whole warp
                 if (bad) return CG_NONE32;
             } else {
-                if (lane == 0 && M > 0) n_aln = cg_poa2_traceback(s, seq, Ws, bi, bj, &bad);
-                n_aln = __shfl_sync(CG_FULL, n_aln, 0);
-                if (__shfl_sync(CG_FULL, (u32)bad, 0)) return CG_NONE32;
+                if (M > 0) n_aln = cg_poa2_traceback(s, seq, Ws, bi, bj, M, &bad);           // the whole warp
+                if (bad) return CG_NONE32;
             }
         }
         __syncwarp();

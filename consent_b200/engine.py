@@ -22,7 +22,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libconsent_b200.so")
 
 EXPORTS = ("cg_abi_version", "cg_device_count", "cg_create", "cg_destroy", "cg_last_error", "cg_set_option", "cg_pack_bases_2bit",
            "cg_correct_windows", "cg_free_results", "cg_upload", "cg_run", "cg_download", "cg_stage_ms",
-           "cg_get_counters", "cg_get_kernel_stats", "cg_run_ms", "cg_chunk_count", "cg_reanchor_reads", "cg_free_corrected", "cg_reanchor_stats",
+           "cg_get_counters", "cg_get_kernel_stats", "cg_debug_dump_window", "cg_run_ms", "cg_chunk_count", "cg_reanchor_reads", "cg_free_corrected", "cg_reanchor_stats",
            "cg_upload_piles", "cg_set_read_store", "cg_download_windows", "cg_free_window_set", "cg_extract_stats",
            "cg_ingest_paf", "cg_free_pile_set", "cg_ingest_stats", "cg_finish_reads", "cg_finish_stats", "cg_finish_resident")
 
@@ -65,6 +65,8 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.cg_chunk_count.argtypes = [H]
     lib.cg_get_counters.restype = C.c_int
     lib.cg_get_counters.argtypes = [H, C.POINTER(cg_counters)]
+    lib.cg_debug_dump_window.restype = C.c_int
+    lib.cg_debug_dump_window.argtypes = [H, C.c_uint32, C.POINTER(C.c_void_p)]
     lib.cg_get_kernel_stats.restype = C.c_int
     lib.cg_get_kernel_stats.argtypes = [H, C.POINTER(cg_kernel_stats)]
     lib.cg_reanchor_reads.restype = C.c_int
@@ -272,6 +274,14 @@ class Corrector:
         nb.win_seq_begin, nb.seq_off, nb.bases = batch.win_seq_begin, batch.seq_off, out
         nb._keep = (keep, getattr(batch, "_keep", None))
         return nb
+
+    def dump_window(self, w: int) -> str:
+        """Per-stage dump of window w of the last (single-chunk) run, in the oracle's format (lines S M T A R G g c C)."""
+        p = C.c_void_p()
+        self._check(self.lib.cg_debug_dump_window(self._h, w, C.byref(p)))
+        text = C.string_at(p).decode()
+        C.CDLL(None).free(p)
+        return text
 
     def kernel_stats(self) -> dict:
         """Per kernel of the last run(): summed launch durations (own CUDA events on the launching stream), launches, and for the

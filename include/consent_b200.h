@@ -352,6 +352,12 @@ typedef struct cg_kernel_stats {
 } cg_kernel_stats;
 int  cg_get_kernel_stats(const cg_handle* h, cg_kernel_stats* out);
 
+/* Test instrumentation: per-stage text dump (solid list, surviving template k-mers, anchor chain, mean distances, regions with their
+ * segments and consensuses, stitched consensus) of window w of the batch the last cg_run processed as ONE chunk — the format of
+ * oracle_dump_window / ref_dump_window, so that every stage of the CUDA path can be compared with the reference's, not only the end
+ * result.  *text is malloc'ed. */
+int  cg_debug_dump_window(cg_handle* h, uint32_t w, char** text);
+
 /* Work counters of the last cg_run, the inputs of the algorithmic-bytes model
  * (SURVEY §8d): alignments, score-matrix cells sum (V+1)*L, predecessor-row cells
  * sum E*L, POA graphs, anchors in chains, solid k-mers, packed input bytes,

@@ -168,3 +168,21 @@ def test_emulated_long_kmers_hashed_index(emu, oracle, k):
     batch = concat([synth_windows(3, 20, seed=91), synth_windows(1, 150, seed=92), synth_windows(3, 12, seed=93, profile="ONT")])
     want, _ = oracle.correct_windows(batch, p, threads=4)
     assert_same(emu(p).correct_windows(batch), want, f"k = {k}")
+
+
+def _stage_lines(dump: str):
+    return [ln for ln in dump.split("\n") if ln[:2] in ("S ", "M ", "T ", "A ", "R ", "G ", "g ", "c ", "C ")]
+
+
+def test_emulated_kernels_match_the_oracle_stage_by_stage(emu, oracle):
+    """Not only the end result: solid list, surviving template k-mers, anchor chain, mean distances, every region's segments and
+    consensus, and the stitched consensus of the CUDA path equal the oracle's dump line for line (cg_debug_dump_window)."""
+    from tests.cases import edge_piles
+    batch = concat([synth_windows(3, 20, seed=71), synth_windows(1, 150, seed=72), synth_windows(3, 8, seed=73),
+                    Batch.from_piles([p for n, p in edge_piles(3) if n in ("two_haplotypes", "unrelated_short_no_anchor", "weak_ends")])])
+    for params in (Params(), Params(min_anchors=50)):
+        cor = emu(params)
+        cor.upload(batch)
+        cor.run()
+        for w in range(batch.n_windows):
+            assert _stage_lines(cor.dump_window(w)) == _stage_lines(oracle.dump_window(batch, w, params)), f"window {w}, {params}"
