@@ -469,16 +469,28 @@ class Results:
         return None if self.n_windows == other.n_windows else min(self.n_windows, other.n_windows)
 
     def stream_digests(self, running=None):
-        """Slice-invariant digests of a window stream: per window (length, consensus bytes, status) into one sha256 and
-        (count, k-mers, counts) of its solid list into another.  Feeding the slices of a stream in order (pass the returned
-        objects back in) gives the digest of the whole stream: tests/golden/stream_digests.json holds the reference's."""
+        """Slice-invariant digests of a window stream.  Six running sha256 (consensus lengths, consensus bytes, status; solid-list
+        lengths, k-mers, counts): each is the hash of one array of the whole stream, so feeding the slices of a stream in order (pass
+        the returned list back in) gives the same values as hashing the stream at once.  stream_digest_pair() folds them into the two
+        values tests/golden/stream_digests.json holds for the reference's output."""
         import hashlib
-        hc, hs = running if running is not None else (hashlib.sha256(), hashlib.sha256())
-        lens = np.diff(self.cons_off.astype(np.int64)).astype(np.uint32)
-        hc.update(lens.tobytes()); hc.update(np.ascontiguousarray(self.cons).tobytes()); hc.update(np.ascontiguousarray(self.status).tobytes())
-        ns = np.diff(self.solid_off.astype(np.int64)).astype(np.uint32)
-        hs.update(ns.tobytes()); hs.update(np.ascontiguousarray(self.solid_kmer).tobytes()); hs.update(np.ascontiguousarray(self.solid_count).tobytes())
-        return hc, hs
+        hs = running if running is not None else [hashlib.sha256() for _ in range(6)]
+        n = self.n_windows
+        lens = np.diff(self.cons_off[:n + 1].astype(np.int64)).astype(np.uint32)
+        c0, c1 = int(self.cons_off[0]), int(self.cons_off[n])
+        hs[0].update(lens.tobytes()); hs[1].update(np.ascontiguousarray(self.cons[c0:c1]).tobytes()); hs[2].update(np.ascontiguousarray(self.status[:n]).tobytes())
+        ns = np.diff(self.solid_off[:n + 1].astype(np.int64)).astype(np.uint32)
+        s0, s1 = int(self.solid_off[0]), int(self.solid_off[n])
+        hs[3].update(ns.tobytes()); hs[4].update(np.ascontiguousarray(self.solid_kmer[s0:s1]).tobytes()); hs[5].update(np.ascontiguousarray(self.solid_count[s0:s1]).tobytes())
+        return hs
+
+    @staticmethod
+    def stream_digest_pair(hs):
+        """(consensus digest, solid-list digest) of a finished stream_digests() list."""
+        import hashlib
+        cons = hashlib.sha256("".join(h.hexdigest() for h in hs[:3]).encode()).hexdigest()
+        solid = hashlib.sha256("".join(h.hexdigest() for h in hs[3:]).encode()).hexdigest()
+        return cons, solid
 
     def digest(self) -> str:
         """sha256 over every output byte in a canonical order ("checksum of checksums" for big runs)."""

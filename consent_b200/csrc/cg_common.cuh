@@ -47,7 +47,7 @@ typedef int32_t i32;
 #define CG_TK_MAX 2047u       // template k-mers per window (anchor hash has 4096 slots)
 #define CG_N_MAX 4095u        // sequences per window
 #define CG_LEN_MAX 6000u      // bases per sequence (int16 score matrix: 5*L < 32767)
-#define CG_PW_CAP 9216u       // packed words (and tags) of one pile staged in shared memory
+#define CG_PW_CAP 8192u       // packed words (and tags) of one pile staged in shared memory
 
 // ---- error / event flags (device -> host), OR-ed into CgChunk::flags[0]
 enum {

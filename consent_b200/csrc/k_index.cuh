@@ -6,27 +6,31 @@
 // are ever read from it: (1) merCounts = total occurrences of k-mers seen >= solid times (:72-76) and
 // (2) the location lists of k-mers that occur in the template, are never repeated inside one read (:58-60,
 // 66-68, 78-82) and are present in >= S reads (:101).  So this kernel
-//   - counts all k-mers of the pile in a direct-addressed shared-memory table, 2^15 keys per pass
-//     (8 passes for k=9); after each pass the solid entries are compacted *in key order* (the sorted list
-//     the ABI returns) and the counts of the template's k-mers are picked up;
+//   - counts all k-mers of the pile in a direct-addressed shared-memory table; the solid entries are compacted
+//     *in key order* (the sorted list the ABI returns) and the counts of the template's k-mers are picked up;
 //   - keeps template positions with S <= count <= N (necessary for "alive"), gives each a slot, and in one
 //     more sweep over the pile records pos[read][slot] = position + 1;
-//   - a slot is alive iff (#reads holding it) == count, i.e. no read holds it twice.
+//   - a slot is alive iff no read holds its k-mer twice (every occurrence sets one bit per (read, slot) in shared memory;
+//     finding it set is a second occurrence).
 //
-// One CTA (512 threads) per window.  The 2-bit pile (words + tags, <= 72 KB) is bulk-copied HBM -> shared
-// memory by the TMA engine (cp.async.bulk + mbarrier); bigger piles are read through L1/L2.
+// One CTA (1024 threads) per window.  The 2-bit pile (words + tags, <= 64 KB) is bulk-copied HBM -> shared memory by the
+// TMA engine (cp.async.bulk + mbarrier) while the counters are zeroed; every sweep then reads it from there.  Bigger piles
+// (polishing depth) are read through L1/L2.
+//
+// Counting, k <= 9, pile staged (every window of the BASELINE configs): BYTE counters, 2^17 keys per pass in the 128 KB table
+// (two passes for k = 9, one below), one shared-memory atomic per occurrence (the add lands in the key's byte of its 32-bit
+// word and returns the old value).  The occurrence that lifts a counter to `solid` sets the key's bit in a 16 KB bitmap, so
+// the solid list of a pass is read off 4096 words instead of 131072 counters.  A counter that reaches 255 raises a flag and
+// the window is counted again in 32 bits (8 passes of 2^15 keys, the path of the deeper piles), so the result never depends
+// on the counter width; a k-mer seen 255 times in one window means a low-complexity pile.
+// k = 10 .. 15: an open-addressing table per SM in global memory (below).
 #pragma once
 #include "cg_common.cuh"
 
-#define CG_IDX_THREADS 512u
-#define CG_IDX_SMEM_BYTES (131072u + 8u * CG_PW_CAP + 2u * 2048u * 4u + 64u * 4u + 16u)
-// Bucketed counting (piles of up to CG_IDX_BUCKET_CAP k-mer occurrences, 2k > 13): the k-mers are extracted ONCE and
-// scattered, as their low 13 bits, into 2^(2k-13) buckets by their high bits (two sweeps over the pile: histogram, then
-// scatter); each counting pass then only touches its own bucket.  The 8-pass direct count below re-extracts every k-mer
-// in every pass and stays for deeper piles.
-#define CG_IDX_BUCKET_CAP 81920u
-#define CG_IDX_BKT_BITS 13u
-
+#ifndef CG_IDX_THREADS
+#define CG_IDX_THREADS 1024u
+#endif
+#define CG_IDX_SMEM_BYTES (131072u + 8u * CG_PW_CAP + 2u * 2048u * 4u + 16384u + 64u * 4u + 16u)     // table | pile words, tags | template k-mers, counts | solid bitmap | misc, barrier
 #ifndef CG_EMU
 __device__ __forceinline__ u32 cg_smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
 #endif
@@ -38,7 +42,8 @@ __global__ void __launch_bounds__(CG_IDX_THREADS, 1) k_index(CgChunk c) {
     u32* tags_s = pile_s + CG_PW_CAP;
     u32* tkmer = tags_s + CG_PW_CAP;
     u32* tcount = tkmer + 2048;
-    u32* misc = tcount + 2048;
+    u32* sbm = tcount + 2048;                        // byte-counter path: one bit per key of the pass, set when the key turns solid
+    u32* misc = sbm + 4096;
 
     const u32 w = blockIdx.x, tid = threadIdx.x, lane = cg_lane(), warp = cg_warp();
     const u32 T = CG_IDX_THREADS, NWARPS = CG_IDX_THREADS / 32;
@@ -55,7 +60,132 @@ __global__ void __launch_bounds__(CG_IDX_THREADS, 1) k_index(CgChunk c) {
     const u32* pw;
     const u32* pt;
     const bool hashed = k > CG_KMAX;
-    const bool bucketed = !hashed && W.n_occ <= CG_IDX_BUCKET_CAP && 2 * k > CG_IDX_BKT_BITS;
+    // ---- stage the 2-bit pile in shared memory (TMA bulk copy), if it fits
+    bool staged = false;
+    if (!hashed) {
+        const u64 ga = g0 & ~3ull;                    // 16-byte aligned source
+        const u32 shift = (u32)(g0 - ga);
+        const u32 ncopy = (shift + nw + 1 + 3) & ~3u; // + the look-ahead word; multiple of 16 bytes
+        if (ncopy <= CG_PW_CAP) {
+#ifndef CG_EMU
+            u64* bar = (u64*)(misc + 64);
+            const u32 bar_a = cg_smem_addr(bar);
+            if (tid == 0) {
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+                const u32 bytes = ncopy * 4u;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(2u * bytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(cg_smem_addr(pile_s)), "l"(c.pwords + ga), "r"(bytes), "r"(bar_a) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(cg_smem_addr(tags_s)), "l"(c.ptags + ga), "r"(bytes), "r"(bar_a) : "memory");
+            }
+            for (u32 i = tid; i < 32768; i += T) tab[i] = 0;         // the first pass's counters, while the copy is in flight
+            if (tid == 0) misc[0] = 0;
+            __syncthreads();                                          // the barrier's init is visible to every waiter
+            asm volatile(
+                "{\n"
+                ".reg .pred p;\n"
+                "CG_WAIT:\n"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+                "@p bra CG_DONE;\n"
+                "bra CG_WAIT;\n"
+                "CG_DONE:\n"
+                "}\n" ::"r"(bar_a) : "memory");
+#else
+            for (u32 i = tid; i < ncopy; i += T) { pile_s[i] = c.pwords[ga + i]; tags_s[i] = c.ptags[ga + i]; }
+            for (u32 i = tid; i < 32768; i += T) tab[i] = 0;
+            if (tid == 0) misc[0] = 0;
+            __syncthreads();
+#endif
+            pw = pile_s + shift;
+            pt = tags_s + shift;
+            staged = true;
+        }
+    }
+    bool counted = false;
+    if (staged) {
+        // ---- byte counters: 2^17 keys per pass
+        for (u32 p = tid; p < tk; p += T) {
+            tkmer[p] = cg_kmer_at(pw[p >> 4], pw[(p >> 4) + 1], p & 15u, k);
+            tcount[p] = 0;
+        }
+        const u32 key_bits = 2 * k < 17u ? 2 * k : 17u;
+        const u32 key_mask = (1u << key_bits) - 1u;
+        const u32 npass = 1u << (2 * k - key_bits);
+        const u32 nbw = ((1u << key_bits) + 31u) / 32u;        // words of the solid bitmap
+        const u32 per_warp = (nbw + NWARPS - 1) / NWARPS;
+        const u32 vb = warp * per_warp < nbw ? warp * per_warp : nbw;
+        const u32 ve = vb + per_warp < nbw ? vb + per_warp : nbw;
+        const u32 thrm1 = solid_thr - 1u;                      // a key turns solid when its counter leaves this value (solid >= 1)
+        const u8* tab8 = (const u8*)tab;
+        bool ok = true;
+        for (u32 pass = 0; pass < npass && ok; ++pass) {
+            if (pass)
+                for (u32 i = tid; i < 32768; i += T) tab[i] = 0;
+            for (u32 i = tid; i < nbw; i += T) sbm[i] = 0;
+            __syncthreads();
+            u32 top = 0;
+            for (u32 g = tid; g < nw; g += T) {
+                const u32 tag = pt[g];
+                if (tag == CG_NONE32) continue;
+                const u32 nv = (tag & 15u) + 1;
+                const u32 w0 = pw[g], w1 = pw[g + 1];
+#pragma unroll
+                for (u32 b = 0; b < 16; ++b) {
+                    if (b < nv) {
+                        const u32 km = cg_kmer_at(w0, w1, b, k);
+                        if ((km >> key_bits) == pass) {
+                            const u32 key = km & key_mask;
+                            const u32 old = atomicAdd(&tab[key >> 2], 1u << (8u * (key & 3u)));
+                            const u32 ob = __byte_perm(old, 0, 0x4440u | (key & 3u));     // the key's byte before the add
+                            top = ob > top ? ob : top;
+                            if (ob == thrm1) atomicOr(&sbm[key >> 5], 1u << (key & 31u));
+                        }
+                    }
+                }
+            }
+            if (top == 255u) misc[0] = 1;                      // a counter wrapped: recount in 32 bits
+            __syncthreads();
+            if (misc[0]) { ok = false; break; }
+            for (u32 p = tid; p < tk; p += T) {
+                const u32 km = tkmer[p];
+                if ((km >> key_bits) == pass) tcount[p] = tab8[km & key_mask];
+            }
+            // solid entries of this pass, in key order: count per warp range, scan, write
+            u32 wc = 0;
+            for (u32 v = vb + lane; v < ve; v += 32) wc += (u32)__popc(sbm[v]);
+            wc = cg_warp_sum(wc);
+            if (lane == 0) misc[1 + warp] = wc;
+            __syncthreads();
+            u32 woff = 0, total = 0;
+            for (u32 i = 0; i < NWARPS; ++i) { const u32 v = misc[1 + i]; if (i < warp) woff += v; total += v; }
+            if (wc) {
+                u64 run = solid_base + nsolid + woff;
+                for (u32 v0 = vb; v0 < ve; v0 += 32) {
+                    const u32 v = v0 + lane;
+                    u32 mm = v < ve ? sbm[v] : 0u;
+                    const u32 n = (u32)__popc(mm);
+                    const u32 inc = cg_warp_scan(n);
+                    u64 idx = run + inc - n;
+                    while (mm) {
+                        const u32 key = 32u * v + (u32)__ffs((int)mm) - 1u;
+                        mm &= mm - 1u;
+                        c.solid_k[idx] = (pass << key_bits) | key;
+                        c.solid_c[idx] = tab8[key];
+                        ++idx;
+                    }
+                    run += __shfl_sync(CG_FULL, inc, 31);
+                }
+            }
+            nsolid += total;
+            __syncthreads();
+        }
+        counted = ok;
+        if (!ok) nsolid = 0;
+    }
+    if (counted) {
+    } else
     if (hashed) {
         // ---- k = 10 .. 15: 4^k keys do not fit a direct table.  Every occurrence goes into an open-addressing table in global
         // memory (one table per SM, L2-resident: atomicCAS claims the key, atomicAdd counts), the template's k-mers are looked up,
@@ -137,146 +267,10 @@ __global__ void __launch_bounds__(CG_IDX_THREADS, 1) k_index(CgChunk c) {
             c.solid_c[solid_base + i] = hc[hh];
         }
         __syncthreads();
-    } else if (bucketed) {
-        // shared memory: [table 8192 u32][histogram + cursors 2 x 512 u32][bucket store CAP u16][tkmer][tcount][misc]
-        u32* whist = tab + 8192;                  // [warp][bucket] counts, then the bucket bases at [512 ..]
-        u32* cursor = whist + 512;
-        u16* bstore = (u16*)(cursor + 512);
-        tkmer = (u32*)(bstore + CG_IDX_BUCKET_CAP);
-        tcount = tkmer + 2048;
-        misc = tcount + 2048;
+    } else {
+    if (!staged) {
         pw = c.pwords + g0;
         pt = c.ptags + g0;
-        const u32 nbkt = 1u << (2 * k - CG_IDX_BKT_BITS);      // <= 32
-        const u32 lowmask = (1u << CG_IDX_BKT_BITS) - 1u;
-        for (u32 p = tid; p < tk; p += T) {
-            tkmer[p] = cg_kmer_at(pw[p >> 4], pw[(p >> 4) + 1], p & 15u, k);
-            tcount[p] = 0;
-        }
-        for (u32 i = tid; i < 1024; i += T) whist[i] = 0;
-        __syncthreads();
-        // sweep 1: per-warp histogram of the buckets
-        for (u32 g = tid; g < nw; g += T) {
-            const u32 tag = pt[g];
-            if (tag == CG_NONE32) continue;
-            const u32 nv = (tag & 15u) + 1;
-            const u32 w0 = pw[g], w1 = pw[g + 1];
-#pragma unroll
-            for (u32 b = 0; b < 16; ++b)
-                if (b < nv) atomicAdd(&whist[warp * 32 + (cg_kmer_at(w0, w1, b, k) >> CG_IDX_BKT_BITS)], 1u);
-        }
-        __syncthreads();
-        // bucket bases (exclusive scan over buckets) and the per-warp cursors inside each bucket
-        if (tid < 32) {
-            u32 tot = 0;
-            if (tid < nbkt) for (u32 x = 0; x < NWARPS; ++x) tot += whist[x * 32 + tid];
-            const u32 inc = cg_warp_scan(tot);
-            misc[40 + tid] = inc - tot;               // base of bucket tid
-            if (tid == 31) misc[39] = inc;           // all occurrences
-        }
-        __syncthreads();
-        {
-            const u32 x = tid >> 5, b = tid & 31u;    // 16 warps x 32 buckets = 512 threads
-            u32 off = misc[40 + b];
-            for (u32 y = 0; y < x; ++y) off += whist[y * 32 + b];
-            cursor[x * 32 + b] = off;
-        }
-        __syncthreads();
-        // sweep 2: scatter the low bits into the buckets
-        for (u32 g = tid; g < nw; g += T) {
-            const u32 tag = pt[g];
-            if (tag == CG_NONE32) continue;
-            const u32 nv = (tag & 15u) + 1;
-            const u32 w0 = pw[g], w1 = pw[g + 1];
-#pragma unroll
-            for (u32 b = 0; b < 16; ++b) {
-                if (b < nv) {
-                    const u32 km = cg_kmer_at(w0, w1, b, k);
-                    bstore[atomicAdd(&cursor[warp * 32 + (km >> CG_IDX_BKT_BITS)], 1u)] = (u16)(km & lowmask);
-                }
-            }
-        }
-        __syncthreads();
-        // one counting pass per bucket: 8192 keys, only the bucket's own occurrences
-        const u32 tab_n = 1u << CG_IDX_BKT_BITS;
-        const u32 per_warp = tab_n / NWARPS;          // 512 keys per warp, in key order
-        const u32 wb = warp * per_warp;
-        for (u32 bkt = 0; bkt < nbkt; ++bkt) {
-            for (u32 i = tid; i < tab_n; i += T) tab[i] = 0;
-            __syncthreads();
-            const u32 b0 = misc[40 + bkt], b1 = bkt + 1 < 32 ? (bkt + 1 < nbkt ? misc[40 + bkt + 1] : misc[39]) : misc[39];
-            for (u32 i = b0 + tid; i < b1; i += T) atomicAdd(&tab[bstore[i]], 1u);
-            __syncthreads();
-            for (u32 p = tid; p < tk; p += T) {
-                const u32 km = tkmer[p];
-                if ((km >> CG_IDX_BKT_BITS) == bkt) tcount[p] = tab[km & lowmask];
-            }
-            // solid entries of this bucket, in key order: count per warp range, scan, write
-            u32 wc = 0;
-            for (u32 b = wb; b < wb + per_warp; b += 32) wc += __popc(__ballot_sync(CG_FULL, tab[b + lane] >= solid_thr));
-            if (lane == 0) misc[warp] = wc;
-            __syncthreads();
-            u32 woff = 0, total = 0;
-            for (u32 i = 0; i < NWARPS; ++i) { const u32 v = misc[i]; if (i < warp) woff += v; total += v; }
-            if (wc) {
-                u64 run = solid_base + nsolid + woff;
-                for (u32 b = wb; b < wb + per_warp; b += 32) {
-                    const u32 cnt = tab[b + lane];
-                    const bool f = cnt >= solid_thr;
-                    const u32 m = __ballot_sync(CG_FULL, f);
-                    if (f) {
-                        const u64 idx = run + __popc(m & ((1u << lane) - 1u));
-                        c.solid_k[idx] = (bkt << CG_IDX_BKT_BITS) | (b + lane);
-                        c.solid_c[idx] = cnt;
-                    }
-                    run += __popc(m);
-                }
-            }
-            nsolid += total;
-            __syncthreads();
-        }
-    } else {
-    // ---- stage the 2-bit pile in shared memory (TMA bulk copy), if it fits
-    {
-        const u64 ga = g0 & ~3ull;                    // 16-byte aligned source
-        const u32 shift = (u32)(g0 - ga);
-        const u32 ncopy = (shift + nw + 1 + 3) & ~3u; // + the look-ahead word; multiple of 16 bytes
-        if (ncopy <= CG_PW_CAP) {
-#ifndef CG_EMU
-            u64* bar = (u64*)(misc + 64);
-            const u32 bar_a = cg_smem_addr(bar);
-            if (tid == 0) {
-                asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
-                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            }
-            __syncthreads();
-            if (tid == 0) {
-                const u32 bytes = ncopy * 4u;
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(2u * bytes) : "memory");
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                             ::"r"(cg_smem_addr(pile_s)), "l"(c.pwords + ga), "r"(bytes), "r"(bar_a) : "memory");
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                             ::"r"(cg_smem_addr(tags_s)), "l"(c.ptags + ga), "r"(bytes), "r"(bar_a) : "memory");
-            }
-            asm volatile(
-                "{\n"
-                ".reg .pred p;\n"
-                "CG_WAIT:\n"
-                "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
-                "@p bra CG_DONE;\n"
-                "bra CG_WAIT;\n"
-                "CG_DONE:\n"
-                "}\n" ::"r"(bar_a) : "memory");
-#else
-            for (u32 i = tid; i < ncopy; i += T) { pile_s[i] = c.pwords[ga + i]; tags_s[i] = c.ptags[ga + i]; }
-            __syncthreads();
-#endif
-            pw = pile_s + shift;
-            pt = tags_s + shift;
-        } else {
-            pw = c.pwords + g0;
-            pt = c.ptags + g0;
-        }
     }
 
     // ---- template k-mers (read 0 starts at word 0 of the pile)
@@ -348,9 +342,12 @@ __global__ void __launch_bounds__(CG_IDX_THREADS, 1) k_index(CgChunk c) {
     u32* hkey = tab + 8192;                 // 4096 keys
     u16* hval = (u16*)(tab + 12288);        // 4096 slots
     u32* scnt = tab + 14336;                // count by slot
+    u32* filled = tab + 16384;              // reads holding the slot | "some read holds it twice"
+    u32* pairs = tab + 18432;               // one bit per (read, slot): 14336 words
     const u32 bm_words = hashed ? 0u : ((1u << (2 * k)) >= 32 ? (1u << (2 * k)) / 32 : 1);      // pre-filter of the position sweep (4^k bits)
     for (u32 i = tid; i < bm_words; i += T) bitmap[i] = 0;
     for (u32 i = tid; i < 4096; i += T) hkey[i] = CG_NONE32;
+    for (u32 i = tid; i < 2048; i += T) filled[i] = 0;
     const u64 slot_base = c.off_slot[w];
     u32 flags4 = 0, nloc = 0;
 #pragma unroll
@@ -363,6 +360,10 @@ __global__ void __launch_bounds__(CG_IDX_THREADS, 1) k_index(CgChunk c) {
     }
     u32 C = 0;
     u32 slot = cg_block_scan(nloc, misc, &C);
+    // A slot is alive iff no read holds its k-mer twice.  Small tables: one bit per (read, slot) in shared memory tells a second
+    // occurrence apart as it is recorded; big ones: the reads holding each slot are counted from the position table afterwards.
+    const bool pair_bits = (u64)C * N <= 14336ull * 32ull;
+    if (pair_bits) for (u32 i = tid; i < (C * N + 31u) / 32u; i += T) pairs[i] = 0;
 #pragma unroll
     for (u32 q = 0; q < 4; ++q) {
         if (flags4 & (1u << q)) {
@@ -375,7 +376,7 @@ __global__ void __launch_bounds__(CG_IDX_THREADS, 1) k_index(CgChunk c) {
             for (;;) {
                 const u32 old = atomicCAS(&hkey[h], CG_NONE32, km);
                 if (old == CG_NONE32) { hval[h] = (u16)slot; break; }    // one writer per entry.  A k-mer that occurs twice in the template
-                if (old == km) break;                                     // keeps its first claimant's slot: neither slot can be alive
+                if (old == km) { if (pair_bits) filled[slot] = 1; break; }   // keeps its first claimant's slot: neither slot can be alive
                 h = (h + 1) & 4095u;                                      // (count > reads holding it), whichever it is
             }
             ++slot;
@@ -397,34 +398,41 @@ __global__ void __launch_bounds__(CG_IDX_THREADS, 1) k_index(CgChunk c) {
             if (tag == CG_NONE32) continue;
             const u32 nv = (tag & 15u) + 1, r = tag >> 16, wi = (tag >> 4) & 0xfffu;
             const u32 w0 = pw[g], w1 = pw[g + 1];
-            for (u32 b = 0; b < nv; ++b) {
-                const u32 km = cg_kmer_at(w0, w1, b, k);
-                if (!hashed && !((bitmap[km >> 5] >> (km & 31u)) & 1u)) continue;
-                u32 h = (km * 2654435761u) >> 20;
-                while (hkey[h] != km && hkey[h] != CG_NONE32) h = (h + 1) & 4095u;
-                if (hkey[h] == km) pos[(size_t)r * C + hval[h]] = (u16)(16 * wi + b + 1);
+#pragma unroll
+            for (u32 b = 0; b < 16; ++b) {
+                if (b < nv) {
+                    const u32 km = cg_kmer_at(w0, w1, b, k);
+                    if (hashed || ((bitmap[km >> 5] >> (km & 31u)) & 1u)) {
+                        u32 h = (km * 2654435761u) >> 20;
+                        while (hkey[h] != km && hkey[h] != CG_NONE32) h = (h + 1) & 4095u;
+                        if (hkey[h] == km) {
+                            const u32 sl = hval[h], cell = r * C + sl;
+                            pos[cell] = (u16)(16 * wi + b + 1);
+                            if (pair_bits && ((atomicOr(&pairs[cell >> 5], 1u << (cell & 31u)) >> (cell & 31u)) & 1u)) filled[sl] = 1;
+                        }
+                    }
+                }
             }
         }
     }
     __syncthreads();
 
     // ---- alive <=> every occurrence is in a different read; anchors = alive slots in template order
-    u32* filled = tab + 16384;              // reads holding the slot
-    for (u32 i = tid; i < C; i += T) filled[i] = 0;
-    __syncthreads();
-    for (u32 r = warp; r < N; r += NWARPS) {
-        const u16* prow = pos + (size_t)r * C;
-        for (u32 sb = 0; sb < C; sb += 32) {
-            const u32 s = sb + lane;
-            if (s < C && prow[s] != 0) atomicAdd(&filled[s], 1u);
+    if (!pair_bits) {
+        for (u32 r = warp; r < N; r += NWARPS) {
+            const u16* prow = pos + (size_t)r * C;
+            for (u32 sb = 0; sb < C; sb += 32) {
+                const u32 s = sb + lane;
+                if (s < C && prow[s] != 0) atomicAdd(&filled[s], 1u);
+            }
         }
+        __syncthreads();
     }
-    __syncthreads();
     flags4 = 0; nloc = 0;
 #pragma unroll
     for (u32 q = 0; q < 4; ++q) {
         const u32 s = tid * 4 + q;
-        if (s < C && filled[s] == scnt[s]) { flags4 |= 1u << q; ++nloc; }
+        if (s < C && (pair_bits ? filled[s] == 0 : filled[s] == scnt[s])) { flags4 |= 1u << q; ++nloc; }
     }
     u32 A = 0;
     u32 a = cg_block_scan(nloc, misc, &A);

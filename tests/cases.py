@@ -56,6 +56,25 @@ def edge_piles(seed: int = 1):
     return cases
 
 
+def counter_width_piles(seed: int = 11):
+    """Piles around the width of k_index's byte counters: a 9-mer seen exactly 255 times (stays on the byte path), 256 and 257 times
+    (the window is counted again with 32-bit counters), and one seen 255 times next to one seen 300 times in the other pass's key range."""
+    rng = random.Random(seed)
+    truth = _rand_seq(rng, 300)
+
+    def pile(runs):                       # runs: list of (base, run length, number of reads); a run of n gives n - 8 9-mers
+        reads = [truth]
+        for base, run, n in runs:
+            for _ in range(n):
+                cut = rng.randrange(20, 280)
+                reads.append(_mutate(rng, truth[:cut], 0.05) + "CG"[base == "C"] + base * run + "CG"[base == "C"] + _mutate(rng, truth[cut:], 0.05))
+        return reads
+    return [("kmer_255_times", pile([("A", 13, 51)])),                       # 51 x 5
+            ("kmer_256_times", pile([("A", 16, 32)])),                       # 32 x 8
+            ("kmer_257_times", pile([("A", 16, 32), ("A", 9, 1)])),
+            ("kmer_255_and_300_times_two_passes", pile([("A", 13, 51), ("T", 18, 30)]))]
+
+
 def edge_batch(seed: int = 1) -> Batch:
     return Batch.from_piles([p for _, p in edge_piles(seed)])
 

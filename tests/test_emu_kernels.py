@@ -82,6 +82,15 @@ def test_emulated_deep_piles(emu, oracle):
     assert_same(emu().correct_windows(batch), want, "300-deep pile")
 
 
+def test_emulated_kmer_counts_around_the_byte_counter_width(emu, oracle):
+    from tests.cases import counter_width_piles
+    for name, pile in counter_width_piles():
+        batch = Batch.from_piles([pile])
+        want, _ = oracle.correct_windows(batch, threads=2)
+        assert max(c for _, c in want.solid(0)) >= 255, name
+        assert_same(emu().correct_windows(batch), want, name)
+
+
 def test_emulated_errors(emu):
     cor = emu()
     with pytest.raises(ConsentError) as e:

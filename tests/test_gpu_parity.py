@@ -213,6 +213,17 @@ def test_gpu_polishing_depth_piles(gpu, oracle):
     assert_same(gpu().correct_windows(deep), want, "1200-deep pile")
 
 
+def test_gpu_kmer_counts_around_the_byte_counter_width(gpu, oracle):
+    """k_index counts in bytes and recounts a window in 32 bits when a k-mer passes 255 occurrences: 255 / 256 / 257 and both key ranges."""
+    from tests.cases import counter_width_piles
+    cases = counter_width_piles()
+    batch = Batch.from_piles([p for _, p in cases])
+    want, _ = oracle.correct_windows(batch, threads=4)
+    for w, (name, _) in enumerate(cases):
+        assert max(c for _, c in want.solid(w)) >= 255, name
+    assert_same(gpu().correct_windows(batch), want, "k-mer counts of 255 / 256 / 257")
+
+
 def test_gpu_two_handles_in_two_threads(gpu, oracle):
     """The ABI is re-entrant per handle (the reference call is made from --nproc threads, src/CONSENT-correction.cpp:76-111)."""
     import threading
