@@ -200,6 +200,32 @@ def test_gpu_config3_stream_is_invariant_under_scheduling(gpu, oracle, reference
         assert gc[key] == oc[key], key
 
 
+def _stream_against_golden(gpu, name, step):
+    import json
+    import os
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "stream_digests.json")))[name]
+    W, N = gold["windows"], gold["seqs_per_window"]
+    cor, run = gpu(), None
+    for w0 in range(0, W, step):
+        res = cor.correct_windows(synth_windows(min(step, W - w0), N, seed=gold["seed"], profile=gold["profile"], first_window=w0))
+        assert int((res.status == 2).sum()) == 0
+        run = res.stream_digests(run)
+    cons, solid = res.stream_digest_pair(run)
+    assert cons == gold["consensus_sha256"], f"{name}: consensus stream differs from the reference's"
+    assert solid == gold["solid_sha256"], f"{name}: solid k-mer stream differs from the reference's"
+
+
+def test_gpu_config2_whole_stream_equals_the_reference(gpu):
+    """BASELINE config 2, all 10 000 windows x 20 sequences: every consensus byte, status and solid (k-mer, count) pair against the digests
+    of the unmodified reference's output (tests/golden/stream_digests.json, made by tests/golden/make_stream_digests.py)."""
+    _stream_against_golden(gpu, "config2", 4000)
+
+
+def test_gpu_config3_whole_stream_equals_the_reference(gpu):
+    """BASELINE config 3, all 100 000 windows x 150 sequences (the headline workload), fed in slices of 12 500 windows."""
+    _stream_against_golden(gpu, "config3", 12500)
+
+
 def test_gpu_polishing_depth_piles(gpu, oracle):
     """CONSENT-polish piles are far deeper than the corrector's 150 (maxSupport 20000, CONSENT-polish:42-43): more than
     256 sequences (k_split's general path), more than 81 920 k-mer occurrences (k_index's direct-count path, pile too big
