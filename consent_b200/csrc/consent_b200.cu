@@ -417,7 +417,7 @@ int run_chunk(cg_handle* h, Lane& L, size_t ci) {
     kbegin(CG_K_PACK, st, 3);
     CG_LAUNCH(k_plan, (nwin + 127) / 128, 128, 0, st, c);
     CG_LAUNCH(k_scan, 5, 1024, 1024 * sizeof(u64), st, c.off_solid, c.off_slot, c.off_pos, c.off_reg, c.off_arena, nwin);
-    CG_LAUNCH(k_pack, nwin, 256, 0, st, c);
+    CG_LAUNCH(k_pack, nwin, CG_PACK_THREADS, CG_PACK_SMEM_BYTES, st, c);
     kend(st);
     L.stage_launches[CG_STAGE_PACK] += 3;
     span_end();

@@ -96,38 +96,60 @@ __global__ void k_scan(u64* a0, u64* a1, u64* a2, u64* a3, u64* a4, u32 n) {
     }
 }
 
-// One CTA per window, one warp per sequence, one lane per 16-base word.
+// One CTA per window, one thread per 16-base word of the pile (the words of a window are contiguous: sequence s starts at word
+// (seq_off[s] >> 4) + s; a binary search over the window's sequence table, staged in shared memory, finds a word's sequence).
+// A thread reads its 16 bases as five aligned 32-bit words, re-aligns them with funnel shifts and converts four bases at a
+// time: code = ((b >> 1) & 3) ^ (its own high bit) maps A C G T to 0 1 2 3, anything else is caught by mapping the code back to
+// its letter; a multiply gathers the four 2-bit codes into one byte.
 // word: base i of the word at bits [31-2i, 30-2i] (so a k-mer read off the word is BMEAN's code, utils.cpp:18-30)
 // tag : (read index in the window) << 16 | (word index in the read) << 4 | (k-mer starts in the word - 1); ~0 = none
-__global__ void __launch_bounds__(256) k_pack(CgChunk c) {
+#define CG_PACK_THREADS 256u
+#define CG_PACK_SMEM_BYTES (4u * (CG_N_MAX + 2u))
+__global__ void __launch_bounds__(CG_PACK_THREADS) k_pack(CgChunk c) {
+    CG_DYN_SMEM(smem);
+    u32* s_w0 = (u32*)smem;                          // first word of each sequence, relative to the window's first word
     const CgWin W = c.win[blockIdx.x];
     if (W.bad) return;                               // over a limit: untouched (k_plan)
-    u32 lane = cg_lane(), nwarps = blockDim.x >> 5;
+    const u32 N = W.n_seqs, tid = threadIdx.x;
+    const u64 gw0 = cg_pword(c.seq_off, W.seq_begin);
+    for (u32 s = tid; s <= N; s += CG_PACK_THREADS) s_w0[s] = (u32)(cg_pword(c.seq_off, W.seq_begin + s) - gw0);
+    __syncthreads();
+    const u32 nw = s_w0[N];
+    const u8* base = (const u8*)c.bases;
     u32 bad = 0;
-    for (u32 r = cg_warp(); r < W.n_seqs; r += nwarps) {
-        u32 s = W.seq_begin + r;
-        u64 off = c.seq_off[s];
-        u32 len = (u32)(c.seq_off[s + 1] - off);
-        u64 g0 = cg_pword(c.seq_off, s) - c.pword_base;
-        u32 nw = (u32)(cg_pword(c.seq_off, s + 1) - c.pword_base - g0);
-        u32 nkm = len >= c.k ? len - c.k + 1 : 0;
-        const u8* src = (const u8*)c.bases + off;
-        for (u32 wi = lane; wi < nw; wi += 32) {
-            u32 word = 0;
+    for (u32 g = tid; g < nw; g += CG_PACK_THREADS) {
+        u32 lo = 0, hi = N;                          // last sequence whose first word is <= g
+        while (hi - lo > 1) { const u32 mid = (lo + hi) >> 1; if (s_w0[mid] <= g) lo = mid; else hi = mid; }
+        const u32 r = lo, wi = g - s_w0[r];
+        const u64 off = c.seq_off[W.seq_begin + r];
+        const u32 len = (u32)(c.seq_off[W.seq_begin + r + 1] - off);
+        const u32 nkm = len >= c.k ? len - c.k + 1 : 0;
+        const u32 left = len > 16 * wi ? len - 16 * wi : 0;        // bases of the sequence from this word on
+        u32 word = 0;
+        if (left) {
+            const u64 a = off + 16ull * wi;
+            const u32* p = (const u32*)(base + (a & ~3ull));
+            const u32 sh = 8u * (u32)(a & 3ull);
+            u32 raw[5];
 #pragma unroll
-            for (u32 b = 0; b < 16; ++b) {
-                u32 idx = 16 * wi + b;
-                if (idx < len) {
-                    u32 code = cg_base_code(src[idx]);
-                    bad |= code >> 2;
-                    word |= (code & 3u) << (30 - 2 * b);
-                }
+            for (u32 i = 0; i < 5; ++i) raw[i] = (4 * i < left + (u32)(a & 3ull)) ? p[i] : 0x41414141u;     // words holding none of the bases are not read
+#pragma unroll
+            for (u32 i = 0; i < 4; ++i) {
+                u32 x = __funnelshift_r(raw[i], raw[i + 1], sh);                               // bases 4i .. 4i + 3 of the word, first base lowest
+                const u32 have = left > 4 * i ? (left - 4 * i < 4 ? left - 4 * i : 4u) : 0u;
+                const u32 keep = have >= 4 ? 0xffffffffu : (1u << (8u * have)) - 1u;
+                x = (x & keep) | (0x41414141u & ~keep);                                        // past the end: 'A' (code 0), never flagged
+                u32 t = (x >> 1) & 0x03030303u;
+                t ^= (t >> 1) & 0x01010101u;
+                const u32 y = (t | (t >> 4)) & 0x00ff00ffu;
+                const u32 sel = (y | (y >> 8)) & 0xffffu;
+                bad |= __byte_perm(0x54474341u, 0u, sel) ^ x;                                  // 'A' 'C' 'G' 'T' by code against what was read
+                word |= ((t * 0x40100401u) >> 24) << (24u - 8u * i);
             }
-            u32 nv = nkm > 16 * wi ? (nkm - 16 * wi < 16 ? nkm - 16 * wi : 16) : 0;
-            u32 tag = nv ? ((r << 16) | (wi << 4) | (nv - 1)) : CG_NONE32;
-            c.pwords[g0 + wi] = word;
-            c.ptags[g0 + wi] = tag;
         }
+        const u32 nv = nkm > 16 * wi ? (nkm - 16 * wi < 16 ? nkm - 16 * wi : 16) : 0;
+        c.pwords[gw0 - c.pword_base + g] = word;
+        c.ptags[gw0 - c.pword_base + g] = nv ? ((r << 16) | (wi << 4) | (nv - 1)) : CG_NONE32;
     }
     if (bad) atomicOr(c.flags, (u32)CG_FLAG_BAD_BASE);
 }
