@@ -112,7 +112,7 @@ struct Lane {
     cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr}, ev_gather = nullptr, ev_end = nullptr, ev_tail = nullptr;
     bool tail_recorded = false;
     DevBuf pwords, ptags, win, offs, solid_k, solid_c, slot_tpos, slot_kmer, anchors, chain, rel, pos, regions, arena, fin, visited;
-    DevBuf jobs_s, jobs_m, jobs_3, jobs_w, jobs_r, jobs_x, ctl, off_fin, out_off;
+    DevBuf jobs_s, jobs_m, jobs_3, jobs_w, jobs_ws, jobs_r, jobs_x, ctl, off_fin, out_off;
     DevBuf g_mem, w1_mem, w2_mem; // per-warp global scratch of the POA tiers G (matrix only), W1 and W2
     DevBuf idx_keys, idx_counts;  // k_index, k > 9: one open-addressing count table per SM
     u32* h_ctl = nullptr;        // pinned: flags + queue control + totals
@@ -366,7 +366,7 @@ int run_chunk(cg_handle* h, Lane& L, size_t ci) {
     CKL(L.regions.ensure(cp.reg_tot * sizeof(CgRegion) + 16));
     CKL(L.arena.ensure(cp.arena_tot + 16));
     CKL(L.visited.ensure((cp.solid_tot / 32 + nwin + 2) * 4));
-    for (DevBuf* jb : {&L.jobs_s, &L.jobs_m, &L.jobs_3, &L.jobs_w, &L.jobs_r, &L.jobs_x}) CKL(jb->ensure(cp.reg_tot * sizeof(uint2) + 16));
+    for (DevBuf* jb : {&L.jobs_s, &L.jobs_m, &L.jobs_3, &L.jobs_w, &L.jobs_ws, &L.jobs_r, &L.jobs_x}) CKL(jb->ensure(cp.reg_tot * sizeof(uint2) + 16));
     CKL(L.off_fin.ensure(sizeof(u64) * (nwin + 1)));
     CKL(L.out_off.ensure(sizeof(u64) * 2 * (nwin + 1)));
 
@@ -477,9 +477,12 @@ int run_chunk(cg_handle* h, Lane& L, size_t ci) {
     // The three tiers side by side (the wide, long-running jobs are launched first so that they overlap the bulk of the small ones).
     // (Measured and dropped: G first and ONE wide launch afterwards over its own queue plus G's overflow — the wide tier is latency
     // bound and G's work hides inside it: 165 k -> 158 k windows/s at 20 sequences per window.)
+    // The wide tier's few long jobs go longest (predicted) first: k_split.cuh: k_poa_sort_queue.  On the main stream, before the fork: the
+    // wide launch has to reach the SMs ahead of the bulk tiers (sorted on its own stream it started behind them: 72 -> 81 ms per 16 384 windows).
+    CG_LAUNCH(k_poa_sort_queue, 1, CG_QSORT_THREADS, (CG_QSORT_BUCKETS + 64) * sizeof(u32), st, c, (const uint2*)c.jobs_w, q + 4 * 2, L.jobs_ws.as<uint2>());
     CKL(cudaEventRecord(L.ev_fork, st));
     for (int i = 0; i < 2; ++i) CKL(cudaStreamWaitEvent(L.s_poa[i], L.ev_fork, 0));
-    CG_POA2_LAUNCH(CgPoa2W1, L.w1_mem.as<u8>(), h->w1_warps, L.s_poa[1], c.jobs_w, 2, jobs_q5, 5);
+    CG_POA2_LAUNCH(CgPoa2W1, L.w1_mem.as<u8>(), h->w1_warps, L.s_poa[1], L.jobs_ws.as<uint2>(), 2, jobs_q5, 5);
     CG_POA2_LAUNCH(CgPoa2GT, L.g_mem.as<u8>(), h->g_warps, L.s_poa[0], c.jobs_m, 1, jobs_q4, 4);
     CG_POA2_LAUNCH(CgPoa2C1, (u8*)nullptr, h->c1_warps, st, c.jobs_s, 0, jobs_q3, 3);
     for (int i = 0; i < 2; ++i) CKL(cudaEventRecord(L.ev_join[i], L.s_poa[i]));
@@ -545,7 +548,7 @@ int run_chunk(cg_handle* h, Lane& L, size_t ci) {
 
     span_begin(CG_STAGE_POLISH);
     kbegin(CG_K_POLISH, st);
-    CG_LAUNCH(k_polish, (nwin + CG_POLISH_WARPS_PER_CTA - 1) / CG_POLISH_WARPS_PER_CTA, CG_POLISH_THREADS, 0, st, c, (const u64*)off_fin);
+    CG_LAUNCH(k_polish, (nwin + CG_POLISH_WARPS_PER_CTA - 1) / CG_POLISH_WARPS_PER_CTA, CG_POLISH_THREADS, CG_POLISH_SMEM_BYTES, st, c, (const u64*)off_fin);
     kend(st);
     L.stage_launches[CG_STAGE_POLISH] += 1;
     span_end();
@@ -792,7 +795,7 @@ void cg_destroy(cg_handle* h) {
     if (h->ev_run0) cudaEventDestroy(h->ev_run0);
     for (Lane& L : h->lane) {
         DevBuf* lb[] = {&L.pwords, &L.ptags, &L.win, &L.offs, &L.solid_k, &L.solid_c, &L.slot_tpos, &L.slot_kmer, &L.anchors, &L.chain, &L.rel,
-                        &L.pos, &L.regions, &L.arena, &L.fin, &L.visited, &L.jobs_s, &L.jobs_m, &L.jobs_3, &L.jobs_w, &L.jobs_r, &L.jobs_x,
+                        &L.pos, &L.regions, &L.arena, &L.fin, &L.visited, &L.jobs_s, &L.jobs_m, &L.jobs_3, &L.jobs_w, &L.jobs_ws, &L.jobs_r, &L.jobs_x,
                         &L.ctl, &L.off_fin, &L.out_off, &L.g_mem, &L.w1_mem, &L.w2_mem, &L.idx_keys, &L.idx_counts};
         for (DevBuf* b : lb) b->release();
         for (cudaEvent_t e : L.evpool) cudaEventDestroy(e);

@@ -229,6 +229,105 @@ template <class T> __device__ CG_NOINLINE bool cg_poa2_dfs(const CgPoa2G<T>& s, 
     return true;
 }
 
+// The same walk for the first wide tier (ids of 10 bits, graph in global memory), where chasing every node's two records through L2
+// on one lane cost an eighth of the tier's time: the warp first packs what the walk needs into ONE word per node in shared memory
+// (first two in-edges | in-degree << 20 | aligned nodes << 25 | mark << 27 | check << 29: 4 KB over the idle query profile, plus a
+// 512-entry stack of 16-bit items); only nodes with more than two in-edges or with aligned nodes (~5 %) still read their global records.
+template <class T> struct CgDfsCompact {
+    static constexpr bool USE = T::STORE == CG_P2_ALL_GLOBAL && T::VCAP <= 1024;
+    static constexpr u32 STK = 512;
+    __device__ __forceinline__ static u32* nt(const CgPoa2G<T>& s) { return s.prof(); }
+    __device__ __forceinline__ static u16* stk(const CgPoa2G<T>& s) { return (u16*)(s.prof() + T::VCAP); }
+};
+template <class T> __device__ __forceinline__ void cg_poa2_dfs_prepare(const CgPoa2G<T>& s, u32 V) {
+    CG_P2_TYPES;
+    const u32 lane = cg_lane();
+    if constexpr (CgDfsCompact<T>::USE) {
+        u32* nt = CgDfsCompact<T>::nt(s);
+        for (u32 i = lane; i < V; i += 32) {
+            const MetaT m = s.meta(i);
+            const VecT P = s.pred(i);
+            const u32 deg = ((u32)m >> 3) & 31u;
+            nt[i] = (deg > 0 ? Pk::get(P, 0) : 0u) | ((deg > 1 ? Pk::get(P, 1) : 0u) << 10) | (deg << 20) | (((u32)m & 3u) << 25) | (1u << 29);
+        }
+    } else {
+        for (u32 i = lane; i < V; i += 32) { s.marks(i) = 0; s.check(i) = 1; }
+    }
+    __syncwarp();
+}
+template <class T> __device__ CG_NOINLINE bool cg_poa2_dfs_compact(const CgPoa2G<T>& s, u32 V) {
+    CG_P2_TYPES;
+    typedef CgDfsCompact<T> C;
+    constexpr u32 FIN = 1u << 10, ID = 0x3ffu, MARK = 27, CHECK = 1u << 29;
+    u32* nt = C::nt(s);
+    u16* st16 = C::stk(s);
+#define CG_DFS_PUSH(x) do { if (sp < C::STK) st16[sp] = (u16)(x); else s.work(sp) = (ItemT)(x); ++sp; } while (0)
+#define CG_DFS_AT(i) ((i) < C::STK ? (u32)st16[i] : (u32)s.work(i))
+    u32 nrank = 0, sp = 0;
+    for (u32 i = 0; i < V; ++i) {
+        if (((nt[i] >> MARK) & 3u) != 0) continue;
+        CG_DFS_PUSH(i);
+        while (sp != 0) {
+            const u32 top = CG_DFS_AT(sp - 1);
+            const u32 id = top & ID;
+            bool finish = (top & FIN) != 0;
+            const u32 e = nt[id];
+            const u32 deg = (e >> 20) & 31u, nal = (e >> 25) & 3u;
+            if (!finish) {
+                if (((e >> MARK) & 3u) == 2) { --sp; continue; }
+                const u32 sp0 = sp;
+                if (sp + deg + 3 > T::SCAP) return false;
+                if (deg <= 2) {
+                    if (deg >= 1) { const u32 b = e & ID; if (((nt[b] >> MARK) & 3u) != 2) CG_DFS_PUSH(b); }
+                    if (deg == 2) { const u32 b = (e >> 10) & ID; if (((nt[b] >> MARK) & 3u) != 2) CG_DFS_PUSH(b); }
+                } else {
+                    const VecT P = s.pred(id);
+                    for (u32 q = 0; q < deg; ++q) { const u32 b = Pk::get(P, q); if (((nt[b] >> MARK) & 3u) != 2) CG_DFS_PUSH(b); }
+                }
+                if ((e & CHECK) && nal) {
+                    const MetaT m = s.meta(id);
+                    for (u32 a = 0; a < nal; ++a) {
+                        const u32 aid = (u32)((m >> (W * (a + 1))) & IDMASK);
+                        if (((nt[aid] >> MARK) & 3u) != 2) { CG_DFS_PUSH(aid); nt[aid] &= ~CHECK; }
+                    }
+                }
+                if (sp == sp0) finish = true;
+                else {
+                    nt[id] = (nt[id] & ~(3u << MARK)) | (1u << MARK);
+                    if (sp0 - 1 < C::STK) st16[sp0 - 1] = (u16)(id | FIN); else s.work(sp0 - 1) = (ItemT)(id | FIN);
+                }
+            }
+            if (finish) {
+                const u32 e2 = nt[id];
+                nt[id] = (e2 & ~(3u << MARK)) | (2u << MARK);
+                if (e2 & CHECK) {
+                    s.xr2n(nrank) = (IdT)id; s.xlead(nrank) = 1; ++nrank;
+                    if (nal) {
+                        const MetaT m = s.meta(id);
+                        for (u32 a = 0; a < nal; ++a) { s.xr2n(nrank) = (IdT)((m >> (W * (a + 1))) & IDMASK); s.xlead(nrank) = 0; ++nrank; }
+                    }
+                }
+                --sp;
+            }
+        }
+    }
+#undef CG_DFS_PUSH
+#undef CG_DFS_AT
+    return true;
+}
+// marks / check (or the packed table) by the warp, the walk by lane 0, the verdict to every lane
+template <class T> __device__ __forceinline__ bool cg_poa2_dfs_run(const CgPoa2G<T>& s, u32 V) {
+    cg_poa2_dfs_prepare(s, V);
+    bool ok = true;
+    if (cg_lane() == 0) {
+        if constexpr (CgDfsCompact<T>::USE) ok = cg_poa2_dfs_compact(s, V);
+        else ok = cg_poa2_dfs(s, V);
+    }
+    ok = __shfl_sync(CG_FULL, (u32)ok, 0) != 0;
+    __syncwarp();
+    return ok;
+}
+
 // A line into L1 ahead of its use (no registers held): the next row's predecessor vector during the DP.  (Prefetching the matrix
 // rows a traceback is about to reach — four rows ~7 steps ahead, or one row 8 steps ahead along the first-predecessor chain —
 // measured no gain on the wide tiers and was dropped.)
@@ -717,14 +816,8 @@ __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s
                 // several rows reach the maximum: the winner is the first of them in spoa's own order (simd...impl.hpp:828-833)
                 if (!dfs_valid) {
                     CG_T_MARK(1);
-                    for (u32 i = lane; i < V; i += 32) { s.marks(i) = 0; s.check(i) = 1; }
-                    __syncwarp();
-                    bool ok = true;
-                    if (lane == 0) ok = cg_poa2_dfs(s, V);
-                    ok = __shfl_sync(CG_FULL, (u32)ok, 0) != 0;
-                    if (!ok) return CG_NONE32;
+                    if (!cg_poa2_dfs_run(s, V)) return CG_NONE32;
                     dfs_valid = true;
-                    __syncwarp();
                     CG_T_MARK(5);
                 }
                 const i16* H = s.H();
@@ -999,13 +1092,7 @@ __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s
 
     // ---- exact column order for the vote
     if (!dfs_valid && V != 0) {
-        for (u32 i = lane; i < V; i += 32) { s.marks(i) = 0; s.check(i) = 1; }
-        __syncwarp();
-        bool ok = true;
-        if (lane == 0) ok = cg_poa2_dfs(s, V);
-        ok = __shfl_sync(CG_FULL, (u32)ok, 0) != 0;
-        if (!ok) return CG_NONE32;
-        __syncwarp();
+        if (!cg_poa2_dfs_run(s, V)) return CG_NONE32;
     }
 
     CG_T_MARK(5);

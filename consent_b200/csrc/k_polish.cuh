@@ -24,10 +24,13 @@
 __device__ __forceinline__ bool cg_is_upper(u8 ch) { return ch >= 'A' && ch <= 'Z'; }
 __device__ __forceinline__ u8 cg_to_upper(u8 ch) { return (ch >= 'a' && ch <= 'z') ? (u8)(ch - 32) : ch; }
 __device__ __forceinline__ u8 cg_to_lower(u8 ch) { return (ch >= 'A' && ch <= 'Z') ? (u8)(ch + 32) : ch; }
-// str2num of an upper-cased character (BMEAN/utils.cpp:18-30): A0 C1 G2, anything else 3
-__device__ __forceinline__ u32 cg_char_code(u8 ch) { ch = cg_to_upper(ch); return ch == 'A' ? 0u : ch == 'C' ? 1u : ch == 'G' ? 2u : 3u; }
+// str2num of an upper-cased character (BMEAN/utils.cpp:18-30): A0 C1 G2, anything else 3.  Every byte this kernel looks at is one of
+// ACGTacgt (the input is validated, k_prep.cuh: k_pack; the consensus is built from input bases; weightConsensus only changes case), and
+// for those eight ((ch >> 1) & 3) ^ its own high bit is exactly that code.
+__device__ __forceinline__ u32 cg_char_code(u8 ch) { const u32 x = ((u32)ch >> 1) & 3u; return x ^ (x >> 1); }
 __device__ __forceinline__ u32 cg_code_of(const u8* p, u32 k) {
     u32 r = 0;
+#pragma unroll 1
     for (u32 i = 0; i < k; ++i) r = (r << 2) | cg_char_code(p[i]);
     return r;
 }
@@ -36,22 +39,68 @@ struct CgDbg {
     const u32* sk; const u32* sc; u32 ns;
     u32 k, mask;
     u32* visited;
+    const u32* bstart; u32 shift;        // bstart[b] = first list entry whose k-mer's top 10 bits are >= b (1025 entries, shared memory)
 };
-__device__ __forceinline__ i32 cg_dbg_find(const CgDbg& d, u32 code) {
-    u32 lo = 0, hi = d.ns;
+#define CG_DBG_BUCKETS 1024u
+#define CG_DBG_BUCKET_BITS 10u
+// The bucket index of a window's solid list, by the whole warp: one coalesced pass over the list marks where the top bits change, a
+// suffix minimum fills the empty buckets.  A lookup then bisects ~ns / 1024 entries instead of ns (the walk is a chain of dependent lookups).
+__device__ __forceinline__ void cg_dbg_build_index(const u32* sk, u32 ns, u32 shift, u32* bstart) {
+    const u32 lane = cg_lane();
+    for (u32 b = lane; b <= CG_DBG_BUCKETS; b += 32) bstart[b] = ns;
+    __syncwarp();
+    for (u32 ib = 0; ib < ns; ib += 32) {
+        const u32 i = ib + lane;
+        if (i < ns) {
+            const u32 b = sk[i] >> shift;
+            if (i == 0 || (sk[i - 1] >> shift) != b) bstart[b] = i;
+        }
+    }
+    __syncwarp();
+    // suffix minimum: lane l owns the buckets [PER l, PER (l + 1))
+    constexpr u32 PER = CG_DBG_BUCKETS / 32u;
+    u32 m = ns;
+    for (int q = (int)PER - 1; q >= 0; --q) { const u32 x = bstart[PER * lane + q]; m = x < m ? x : m; }
+    u32 sm = m;                                           // minimum over this lane's buckets and every later lane's
+#pragma unroll
+    for (int dlt = 1; dlt < 32; dlt <<= 1) { const u32 o = __shfl_down_sync(CG_FULL, sm, dlt); if (lane + (u32)dlt < 32u) sm = o < sm ? o : sm; }
+    u32 run = __shfl_down_sync(CG_FULL, sm, 1);          // ... over the later lanes only
+    if (lane == 31) run = ns;
+    for (int q = (int)PER - 1; q >= 0; --q) { const u32 x = bstart[PER * lane + q]; run = x < run ? x : run; bstart[PER * lane + q] = run; }
+    __syncwarp();
+}
+// first entry >= code
+__device__ __forceinline__ u32 cg_dbg_lower(const CgDbg& d, u32 code) {
+    const u32 b = code >> d.shift;
+    u32 lo = d.bstart[b], hi = d.bstart[b + 1];
     while (lo < hi) { const u32 m = (lo + hi) >> 1; if (d.sk[m] < code) lo = m + 1; else hi = m; }
+    return lo;
+}
+__device__ __forceinline__ i32 cg_dbg_find(const CgDbg& d, u32 code) {
+    const u32 lo = cg_dbg_lower(d, code);
     return (lo < d.ns && d.sk[lo] == code) ? (i32)lo : -1;
 }
 struct CgNb { u32 code[4]; u32 cnt[4]; u32 idx[4]; u32 n; };
 // getNeighbours (DBG.cpp:18-54): successors generated in A,C,G,T order; predecessors (left) through the reverse
 // complement trick, i.e. with first letter T,G,C,A; then sorted by count, descending — std::sort on <= 4 elements
-// is an insertion sort, i.e. stable.
-__device__ __forceinline__ void cg_dbg_neighbours(const CgDbg& d, u32 code, bool left, CgNb& nb) {
+// is an insertion sort, i.e. stable.  The four successors are consecutive keys: one lookup, then the entries that follow it.
+__device__ CG_NOINLINE void cg_dbg_neighbours(const CgDbg& d, u32 code, bool left, CgNb& nb) {
     nb.n = 0;
-    for (u32 i = 0; i < 4; ++i) {
-        const u32 cand = left ? (((3u - i) << (2 * (d.k - 1))) | (code >> 2)) : (((code << 2) & d.mask) | i);
-        const i32 ix = cg_dbg_find(d, cand);
-        if (ix >= 0) { nb.code[nb.n] = cand; nb.cnt[nb.n] = d.sc[ix]; nb.idx[nb.n] = (u32)ix; nb.n++; }
+    if (!left) {
+        const u32 base4 = (code << 2) & d.mask;
+        const u32 lo = cg_dbg_lower(d, base4);
+        u32 key[4];
+#pragma unroll
+        for (u32 j = 0; j < 4; ++j) key[j] = lo + j < d.ns ? d.sk[lo + j] : 0xffffffffu;
+#pragma unroll
+        for (u32 j = 0; j < 4; ++j)
+            if (key[j] - base4 < 4u) { nb.code[nb.n] = key[j]; nb.cnt[nb.n] = d.sc[lo + j]; nb.idx[nb.n] = lo + j; nb.n++; }
+    } else {
+        for (u32 i = 0; i < 4; ++i) {
+            const u32 cand = ((3u - i) << (2 * (d.k - 1))) | (code >> 2);
+            const i32 ix = cg_dbg_find(d, cand);
+            if (ix >= 0) { nb.code[nb.n] = cand; nb.cnt[nb.n] = d.sc[ix]; nb.idx[nb.n] = (u32)ix; nb.n++; }
+        }
     }
     for (u32 i = 1; i < nb.n; ++i) {
         const u32 cc = nb.code[i], ct = nb.cnt[i], ci = nb.idx[i];
@@ -299,7 +348,9 @@ __global__ void k_stitch_len(CgChunk c, u64* off_fin) {
     off_fin[w] = ((u64)2 * m + 64 + 15) / 16 * 16 * 2;          // two slices: consensus, path
 }
 
+#define CG_POLISH_SMEM_BYTES (CG_POLISH_WARPS_PER_CTA * (CG_DBG_BUCKETS + 8u) * 4u)
 __global__ void __launch_bounds__(CG_POLISH_THREADS) k_polish(CgChunk c, const u64* off_fin) {
+    CG_DYN_SMEM(smem);
     const u32 lane = cg_lane();
     const u32 w = blockIdx.x * CG_POLISH_WARPS_PER_CTA + cg_warp();
     if (w >= c.nwin) return;                        // warp-uniform
@@ -342,6 +393,10 @@ __global__ void __launch_bounds__(CG_POLISH_THREADS) k_polish(CgChunk c, const u
         d.sk = c.solid_k + c.off_solid[w]; d.sc = c.solid_c + c.off_solid[w]; d.ns = W.n_solid;
         d.k = k; d.mask = (k >= 16) ? 0xffffffffu : ((1u << (2 * k)) - 1u);
         d.visited = c.visited + (c.off_solid[w] / 32 + w);
+        u32* bstart = (u32*)smem + cg_warp() * (CG_DBG_BUCKETS + 8u);
+        d.shift = 2 * k > CG_DBG_BUCKET_BITS ? 2 * k - CG_DBG_BUCKET_BITS : 0u;
+        cg_dbg_build_index(d.sk, d.ns, d.shift, bstart);
+        d.bstart = bstart;
         const u32 last = n - k;                     // positions beyond the last k-mer follow it
         const u32 solid_last = cg_dbg_find(d, cg_code_of(buf + last, k)) >= 0 ? 1u : 0u;
         __syncwarp();

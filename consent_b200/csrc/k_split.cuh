@@ -265,3 +265,46 @@ __global__ void __launch_bounds__(CG_SPLIT_THREADS) k_split(CgChunk c) {
         atomicAdd((unsigned long long*)&c.counters->poa_graphs, (unsigned long long)njobs);
     }
 }
+
+// The wide tier's queue in descending order of predicted cost.  Its jobs are long (a warp spends milliseconds on a whole-window
+// graph) and few per warp (config-2 shape: 16 700 jobs on 3 552 resident warps), so the launch ends when the unluckiest warp does:
+// two classes (heavy first, light last) left a fifth of the launch as tail; longest-first over 512 cost buckets (16 per octave)
+// brings it within a few percent of the mean (the order has no influence on any result: jobs are independent).
+// One CTA: histogram of the buckets, exclusive scan, scatter.  ctl = the queue's four control words (front count, cursor, back count, capacity).
+#define CG_QSORT_THREADS 1024u
+#define CG_QSORT_BUCKETS 512u
+__global__ void __launch_bounds__(CG_QSORT_THREADS) k_poa_sort_queue(CgChunk c, const uint2* jobs, u32* ctl, uint2* sorted) {
+    CG_DYN_SMEM(smem);
+    u32* hist = (u32*)smem;                          // CG_QSORT_BUCKETS + 64 words
+    u32* scratch = hist + CG_QSORT_BUCKETS;
+    const u32 tid = threadIdx.x;
+    const u32 nfront = ctl[0], nback = ctl[2], cap = ctl[3], n = nfront + nback;
+    if (tid < CG_QSORT_BUCKETS) hist[tid] = 0;
+    __syncthreads();
+    for (u32 pass = 0; pass < 2; ++pass) {
+        for (u32 j = tid; j < n; j += CG_QSORT_THREADS) {
+            const uint2 job = j < nfront ? jobs[j] : jobs[cap - 1 - (j - nfront)];
+            const CgRegion& R = c.regions[c.off_reg[job.x] + job.y];
+            const u32 L = R.max_len, ns = R.n;
+            u32 vhat = (L * (1557u + 23u * ns)) >> 10;            // the predicted graph size of cg_poa_class
+            vhat = vhat > 8u ? vhat - 7u : 1u;
+            vhat += vhat >> 3;
+            const float cost = (float)ns * (float)(vhat + 1u) * (float)(L + 1u);
+            const u32 key = __float_as_uint(cost) >> 19;          // exponent and four mantissa bits: 16 buckets per octave
+            const u32 lo = 127u << 4;                              // cost >= 1
+            u32 b = key > lo ? key - lo : 0u;
+            b = b < CG_QSORT_BUCKETS ? CG_QSORT_BUCKETS - 1u - b : 0u;                     // heaviest first
+            const u32 at = atomicAdd(&hist[b], 1u);
+            if (pass) sorted[at] = job;
+        }
+        __syncthreads();
+        if (pass == 0) {
+            u32 total = 0;
+            const u32 v = tid < CG_QSORT_BUCKETS ? hist[tid] : 0u;
+            const u32 ex = cg_block_scan(v, scratch, &total);
+            if (tid < CG_QSORT_BUCKETS) hist[tid] = ex;
+            __syncthreads();
+        }
+    }
+    if (tid == 0) { ctl[0] = n; ctl[2] = 0; }
+}

@@ -301,6 +301,7 @@ static inline int __all_sync(unsigned mask, int pred) {
 
 // ------------------------------------------------------------------ integer intrinsics
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
+static inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
 static inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
 static inline int __clz(int x) { return x == 0 ? 32 : __builtin_clz((unsigned)x); }
 static inline int __ffs(int x) { return __builtin_ffs(x); }
