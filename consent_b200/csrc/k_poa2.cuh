@@ -679,6 +679,7 @@ __device__ __forceinline__ u32 cg_poa2_find_max(const CgPoa2G<T>& s, u32 V, u32 
     const u32 lane = cg_lane();
     const i16* H = s.H();
     u32 nrows = 0, frow = 0, fcol = 0;
+#pragma unroll 1
     for (u32 rb = 0; rb < V; rb += 32) {
         const u32 r = rb + lane;
         u32 col = 0;
@@ -731,6 +732,7 @@ __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s
 
     // ---- the region's segments, in read order (split_reads)
     u32 nseg = 0;
+#pragma unroll 1
     for (u32 rb = 0; rb < v.N; rb += 32) {
         const u32 r = rb + lane;
         u32 st = 0, ln = 0;
@@ -805,6 +807,7 @@ __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s
                 if constexpr (WIDE) { if (M > 0 && nrows == 1) bj = cg_poa2w_rowfirst(s, bi, CHw, Wd, M); }
                 else if (M > 0 && nrows == 1) {              // first cell of that row equal to M
                     const i16* hr = s.H() + (size_t)bi * Ws;
+#pragma unroll 1
                     for (u32 jb = 1; jb < Wd; jb += 32) {
                         const u32 j = jb + lane;
                         const u32 bal = __ballot_sync(CG_FULL, j < Wd && (i32)hr[j] == M);
@@ -822,6 +825,7 @@ __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s
                 }
                 const i16* H = s.H();
                 u32 row = 0;
+#pragma unroll 1
                 for (u32 ib = 0; ib < V; ib += 32) {
                     const u32 i = ib + lane;
                     bool hit = false;
@@ -841,6 +845,7 @@ __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s
                 if constexpr (WIDE) bj = cg_poa2w_rowfirst(s, row, CHw, Wd, M);
                 else {
                     const i16* hr = H + (size_t)row * Ws;
+#pragma unroll 1
                     for (u32 jb = 1; jb < Wd; jb += 32) {
                         const u32 j = jb + lane;
                         const u32 bal = __ballot_sync(CG_FULL, j < Wd && (i32)hr[j] == M);
@@ -865,6 +870,7 @@ __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s
         u32 first_valid = L, last_valid = 0;
         {
             u32 mn = 0xffffffffu, mxq = 0;
+#pragma unroll 1
             for (u32 t = lane; t < n_aln; t += 32) {
                 const u32 qp = (u32)s.work(t) >> W;
                 if (qp != IDNONE) { mn = qp < mn ? qp : mn; mxq = qp > mxq ? qp : mxq; }
@@ -883,6 +889,7 @@ __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s
         bool ovf = false;
         u32 n_mid_new = 0;
         // U1: the aligned part — which node does each consumed pair resolve to?
+#pragma unroll 1
         for (u32 tb = 0; tb < n_aln; tb += 32) {
             const u32 t = tb + lane;
             u32 kind = 3, nn = 0, an = IDNONE, qp = IDNONE;
@@ -938,6 +945,7 @@ __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s
         if (__any_sync(CG_FULL, ovf)) return CG_NONE32;
         __syncwarp();
         // U2a: every query position -> its node; new unaligned nodes are initialised here
+#pragma unroll 1
         for (u32 qb = 0; qb < L; qb += 32) {
             const u32 q = qb + lane;
             if (q < L) {
@@ -952,6 +960,7 @@ __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s
         __syncwarp();
         // U2b: one visit per position, one edge node(q-1) -> node(q) (an existing edge is reused, graph.cpp:105-110)
         bool changed = V != V0;
+#pragma unroll 1
         for (u32 qb = 0; qb < L; qb += 32) {
             const u32 q = qb + lane;
             if (q < L) {
@@ -988,6 +997,7 @@ __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s
         // ---- the incremental order: splice the new nodes into the old order (columns stay contiguous)
         // U3a: position (in the old order) in front of which each new node goes
         u32 carry_min = IDNONE;                                       // smallest column start among the anchored positions behind
+#pragma unroll 1
         for (int qb = (int)((L - 1) & ~31u); qb >= 0; qb -= 32) {
             const u32 q = (u32)qb + lane;
             u32 cs = IDNONE, ce = 0;
@@ -1026,6 +1036,7 @@ __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s
         __syncwarp();
         // U3b: the new nodes in q order -> work[k] = pos | node << W
         u32 K = 0;
+#pragma unroll 1
         for (u32 qb = 0; qb < L; qb += 32) {
             const u32 q = qb + lane;
             const bool isnew = q < L && s.kindq(q) != 0;
@@ -1040,6 +1051,7 @@ __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s
         __syncwarp();
         // U3c: old entry p moves up by the number of new nodes placed at or before it; new node k lands at pos_k + k
         const u32 nxt = cur ^ 1u;
+#pragma unroll 1
         for (u32 pb = 0; pb < V0; pb += 32) {
             const u32 p = pb + lane;
             if (p < V0) {
@@ -1055,6 +1067,7 @@ __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s
                 s.rank_of(node) = (IdT)(p + lo);
             }
         }
+#pragma unroll 1
         for (u32 kb2 = 0; kb2 < K; kb2 += 32) {
             const u32 k = kb2 + lane;
             if (k < K) {
@@ -1068,6 +1081,7 @@ __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s
         __syncwarp();
         // U4: row descriptors and the predecessor rows
         u32 sd = 0;
+#pragma unroll 1
         for (u32 rb = 0; rb < V; rb += 32) {
             const u32 r = rb + lane;
             if (r < V) {
@@ -1099,6 +1113,7 @@ __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s
     // ---- column vote (bmean.cpp:649-694) straight off the graph: a column = a leader and its aligned nodes
     u8* out = c.arena + c.off_arena[w] + R->arena_off;
     u32 outn = 0;
+#pragma unroll 1
     for (u32 ib = 0; ib < V; ib += 32) {
         const u32 i = ib + lane;
         u8 emit = 0;
