@@ -84,58 +84,86 @@ struct CgRaEnd { int score, col, row; };
 // lane, all in registers.  The only loop-carried chain inside a lane is F: with hp = max(diag + s, E) and g = max(hp - 3, 0),
 //   F' = max(F - 1, max(H - 3, 0)) = max(F - 1, g)          (H = max(hp, F), and F - 3 < F - 1)
 // so a column costs RPL dependent VIADDMNMX and everything else (hp, g, H, E, the column maximum) is independent work.
+//
+// TWO CELLS PER INSTRUCTION (round 2; scores <= 2 * CG_RA_QMAX fit a signed halfword).  The rows of a lane cannot be paired in one
+// register — the F chain runs down them — so a lane is split into two VIRTUAL lanes of RPL / 2 rows, A (low halves) and B (high
+// halves), B one step behind A in the wavefront: at step t virtual lane v = 2 lane + half works on column t - v.  A's first row is
+// fed by the previous lane's B (the shuffle, as before), B's first row by the same lane's A of the step before (registers).  H, E,
+// F, the diagonal and the column maximum are packed pairs: VIADDMNMX.S16x2 / VIMNMX.S16x2 do both cells; the match score comes from
+// the packed codes by exclusive-or (codes are < 8: (x + 7) >> 3 is "x != 0" in both halves without a carry between them).
+// Columns outside [0, nr) are computed too — before the first column the inputs are zeros and a code that matches nothing, which
+// leaves the all-zero state untouched; after the last one nobody reads the state — only the maximum tracking and the band-boundary
+// store look at the column index.  The running maximum is per virtual lane and found by compare on the rare step that raises it.
 template <int RPL>
 __device__ __forceinline__ void cg_ra_band(const char* qsrc, int qfirst, int qstep, int nq, int row0, const u8* refc, int rfirst, int rstep,
                                            int nr, const u32* in_msgs, u32* out_msgs, bool first_band, bool last_band,
                                            int& best, int& bcol, int& brow) {
+    static_assert(RPL % 2 == 0, "two virtual lanes per lane");
+    constexpr int R2 = RPL / 2;
+    constexpr u32 NOMATCH = 6u;                                    // matches no query code (0..3, 5 = N, 7 = padding)
     const int lane = (int)(threadIdx.x & 31u);
-    int H[RPL], E[RPL];
-    u32 qc[RPL];
+    u32 H2[R2], E2[R2], Q2[R2];
     const int my0 = row0 + lane * RPL;
 #pragma unroll
-    for (int i = 0; i < RPL; ++i) {
-        H[i] = 0; E[i] = 0;
-        u32 code = 7u;                                             // padding row: matches nothing
-        if (my0 + i < nq) {
-            code = cg_ra_code(qsrc[qfirst + qstep * (my0 + i)]);
-            if (code == 4u) code = 5u;                             // N never matches, not even N (ssw_cpp.cpp:47-55)
-        }
-        qc[i] = code;
+    for (int i = 0; i < R2; ++i) {
+        u32 ca = 7u, cb = 7u;                                      // padding row: matches nothing
+        if (my0 + i < nq) { ca = cg_ra_code(qsrc[qfirst + qstep * (my0 + i)]); if (ca == 4u) ca = 5u; }      // N never matches, not even N (ssw_cpp.cpp:47-55)
+        if (my0 + R2 + i < nq) { cb = cg_ra_code(qsrc[qfirst + qstep * (my0 + R2 + i)]); if (cb == 4u) cb = 5u; }
+        Q2[i] = ca | (cb << 16);
+        H2[i] = 0; E2[i] = 0;
     }
-    int diag_in = 0;
-    u32 out_msg = 0;
-    const int n_steps = nr + 31;
+    int bestA = best, bcolA = bcol, browA = brow, bestB = best, bcolB = bcol, browB = brow;
+    u32 dA = 0, dB = 0, a_h = 0, a_f = 0, a_rc = NOMATCH;          // diagonals of the two first rows; A's last row of the step before
+    u32 out_msg = NOMATCH;
+    const int n_steps = nr + 63;
     for (int t = 0; t < n_steps; ++t) {
-        // lane 0 is fed from shared memory (every lane reads the same word: a broadcast), the others from their neighbour
-        const int tt = min(t, nr - 1);
-        const u32 feed = first_band ? (u32)refc[rfirst + rstep * tt] : in_msgs[tt];
+        // lane 0 is fed from shared memory (every lane reads the same word: a broadcast), the others from their neighbour's B
+        u32 feed = NOMATCH;
+        if (t < nr) feed = first_band ? (u32)refc[rfirst + rstep * t] : in_msgs[t];
         const u32 up_msg = __shfl_up_sync(CG_FULL, out_msg, 1);
         const u32 in_msg = lane == 0 ? feed : up_msg;
-        const int c = t - lane;
-        if (c >= 0 && c < nr) {
-            const u32 rc = in_msg & 7u;
-            int f = (int)((in_msg >> 4) & 0x3fffu);
-            int d = diag_in;
-            diag_in = (int)(in_msg >> 18);
-            int colkey = 0, h = 0;                                 // max over rows of (h << 5 | RPL - 1 - i): maximum and its first row
+        const int cA = t - 2 * lane, cB = cA - 1;
+        const u32 rcA = in_msg & 7u, hA_in = in_msg >> 18;
+        const u32 rc2 = rcA | (a_rc << 16);
+        u32 f2 = ((in_msg >> 4) & 0x3fffu) | (a_f << 16);
+        u32 d2 = dA | (dB << 16);
+        u32 h2 = 0, cm2 = 0;
 #pragma unroll
-            for (int i = 0; i < RPL; ++i) {
-                const int hp = max(d + (qc[i] == rc ? 2 : -2), E[i]);      // E, f >= 0: the floor at 0 is implied
-                const int g = max(hp - 3, 0);
-                h = max(hp, f);
-                f = max(f - 1, g);
-                d = H[i]; H[i] = h;
-                colkey = max(colkey, h * 32 + (RPL - 1 - i));
-                E[i] = max(E[i] - 1, max(h - 3, 0));
-            }
-            out_msg = ((u32)h << 18) | ((u32)f << 4) | rc;
-            if (!last_band && lane == 31) out_msgs[c] = out_msg;
-            const int colmax = colkey >> 5;
-            if (colmax > best || (colmax == best && c < bcol && colmax > 0)) {
-                best = colmax; bcol = c; brow = my0 + (RPL - 1 - (colkey & 31));
-            }
+        for (int i = 0; i < R2; ++i) {
+            const u32 x = Q2[i] ^ rc2;
+            const u32 nz = ((x + 0x00070007u) >> 3) & 0x00010001u;                 // 1 per half that differs
+            const u32 sc = 0x00020002u ^ ((nz * 0xffffu) & 0xfffcfffcu);           // +2 / -2
+            const u32 hp = cg_viaddmax2(d2, sc, E2[i]);                            // E, f >= 0: the floor at 0 is implied
+            const u32 g = cg_viaddmax2_relu(hp, 0xfffdfffdu, 0u);
+            h2 = cg_vmax2(hp, f2);
+            f2 = cg_viaddmax2(f2, 0xffffffffu, g);
+            d2 = H2[i]; H2[i] = h2;
+            cm2 = cg_vmax2(cm2, h2);
+            E2[i] = cg_viaddmax2(E2[i], 0xffffffffu, cg_viaddmax2_relu(h2, 0xfffdfffdu, 0u));
+        }
+        // hand-over: B's last row to the next lane, A's last row to this lane's B
+        const u32 hB = h2 >> 16, fB = f2 >> 16;
+        out_msg = (hB << 18) | (fB << 4) | a_rc;
+        if (!last_band && lane == 31 && cB >= 0 && cB < nr) out_msgs[cB] = out_msg;
+        dA = hA_in; dB = a_h;
+        a_h = h2 & 0xffffu; a_f = f2 & 0xffffu; a_rc = rcA;
+        const int cmA = (int)(cm2 & 0xffffu), cmB = (int)(cm2 >> 16);
+        if (cA >= 0 && cA < nr && (cmA > bestA || (cmA == bestA && cA < bcolA && cmA > 0))) {
+            int r = 0;
+#pragma unroll
+            for (int i = R2 - 1; i >= 0; --i) if ((int)(H2[i] & 0xffffu) == cmA) r = i;
+            bestA = cmA; bcolA = cA; browA = my0 + r;
+        }
+        if (cB >= 0 && cB < nr && (cmB > bestB || (cmB == bestB && cB < bcolB && cmB > 0))) {
+            int r = 0;
+#pragma unroll
+            for (int i = R2 - 1; i >= 0; --i) if ((int)(H2[i] >> 16) == cmB) r = i;
+            bestB = cmB; bcolB = cB; browB = my0 + R2 + r;
         }
     }
+    // the lane's (score, first column, first row) = the better of its two virtual lanes (A's rows are the smaller ones)
+    const bool takeB = bestB > bestA || (bestB == bestA && bcolB < bcolA);
+    best = takeB ? bestB : bestA; bcol = takeB ? bcolB : bcolA; brow = takeB ? browB : browA;
 }
 
 // One scan of the local-alignment matrix by a warp.  Query row j = qsrc[qfirst + qstep * j], j in [0, nq); column c =
