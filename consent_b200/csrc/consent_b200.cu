@@ -1146,6 +1146,7 @@ static int reanchor_impl(cg_handle* h, const cg_batch* windows, const cg_results
     }
     cudaSetDevice(h->device);
     const u32 W = cons->n_windows, R = reads->n_reads;
+    if (R >> 31) { h->err = "more than 2^31 reads"; return CG_ERR_CAPACITY; }          // (k_reanchor also takes its opaque zero from this)
     if (windows->n_windows != W || reads->read_win_begin[0] != 0 || reads->read_win_begin[R] != W) {
         h->err = "windows, results and reads do not describe the same windows"; return CG_ERR_INVALID_ARG;
     }
@@ -1236,7 +1237,7 @@ static int reanchor_impl(cg_handle* h, const cg_batch* windows, const cg_results
         A.tpl = h->ra_tpl.as<char>(); A.tpl_off = h->ra_tpl_off.as<u64>();
     }
     // ---- scratch: resident warps, each with its buffers and a direction matrix for the banded sub-alignment
-    u32 ctas = std::min<u32>((R + CG_RA_WARPS - 1) / CG_RA_WARPS, (u32)h->sms * 4);
+    u32 ctas = std::min<u32>((R + CG_RA_WARPS - 1) / CG_RA_WARPS, (u32)h->sms * CG_RA_CTAS_PER_SM);
     if (ctas == 0) ctas = 1;
     u64 dir_cap = std::min<u64>((u64)maxL * maxL, 4ull << 20);
     const u64 budget = 6ull << 30;
@@ -1249,9 +1250,9 @@ static int reanchor_impl(cg_handle* h, const cg_batch* windows, const cg_results
     A.head = h->ra_head.as<char>(); A.head_off = h->ra_head_off.as<u64>(); A.out_len = h->ra_len.as<u32>();
     A.scratch = h->ra_scratch.as<u8>(); A.scratch_stride = stride; A.maxL = maxL; A.rmax = rmax; A.dir_cap = dir_cap;
     A.ctl = h->ra_ctl.as<u32>();
-    const size_t smem_ref = (size_t)CG_RA_WARPS * ((rmax + 15u) & ~15u);
-    size_t smem = smem_ref + (size_t)CG_RA_WARPS * 3 * cg_ra_line_bytes(maxL);
-    A.lines_in_smem = smem <= 72 * 1024 ? 1u : 0u;                           // 3 CTAs per SM keep their lines on chip
+    const size_t smem_ref = (size_t)CG_RA_WARPS * cg_ra_smem_per_warp(rmax, maxL, false);
+    size_t smem = (size_t)CG_RA_WARPS * cg_ra_smem_per_warp(rmax, maxL, true);
+    A.lines_in_smem = smem <= (224 / CG_RA_CTAS_PER_SM) * 1024 ? 1u : 0u;   // CG_RA_CTAS_PER_SM CTAs per SM keep their lines on chip
     if (!A.lines_in_smem) smem = smem_ref;
     CK(cudaFuncSetAttribute(k_reanchor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
     struct Events {                                         // destroyed on every return path, CK's included

@@ -25,6 +25,7 @@
 
 #define CG_RA_RPL 20u            // query rows per lane and band (640 rows per band)
 #define CG_RA_WARPS 4u           // warps per CTA
+#define CG_RA_PROF_BYTES (5u * (CG_RA_RPL / 2u) * 32u * 4u)      // query profile of one band: 5 reference letters x RPL / 2 row pairs x 32 lanes
 #define CG_RA_QMAX 8000          // H must fit 14 bits of the wavefront message: 2 * rows <= 16383
 
 enum { CG_RA_FLAG_DEGENERATE = 16u, CG_RA_FLAG_CAPACITY = 32u, CG_RA_FLAG_TRACEBACK = 64u };
@@ -50,6 +51,10 @@ __host__ __device__ inline u64 cg_ra_align16(u64 v) { return (v + 15) & ~(u64)15
 __host__ __device__ inline u64 cg_ra_buf_bytes(u32 maxL) { return cg_ra_align16(2ull * maxL + 32); }
 __host__ __device__ inline u64 cg_ra_bnd_bytes(u32 rmax) { return cg_ra_align16(8ull * rmax + 16); }
 __host__ __device__ inline u64 cg_ra_line_bytes(u32 maxL) { return cg_ra_align16(4ull * (maxL + 8)); }
+__host__ __device__ inline size_t cg_ra_smem_per_warp(u32 rmax, u32 maxL, bool lines_in_smem) {
+    const size_t lines = lines_in_smem ? 3 * (size_t)cg_ra_line_bytes(maxL) : 0;
+    return ((rmax + 15u) & ~15u) + (lines > CG_RA_PROF_BYTES ? lines : (size_t)CG_RA_PROF_BYTES);
+}
 __host__ __device__ inline u64 cg_ra_fixed_bytes(u32 maxL, u32 rmax) {
     return 3 * cg_ra_buf_bytes(maxL) + cg_ra_bnd_bytes(rmax) + 3 * cg_ra_line_bytes(maxL);
 }
@@ -80,6 +85,17 @@ __device__ __forceinline__ int cg_ra_wsum(int v) {
 
 struct CgRaEnd { int score, col, row; };
 
+// a * b + c on the FMA pipe (as a shift-add it would be one more instruction for the ALU pipe, which bounds the scan)
+__device__ __forceinline__ u32 cg_ra_mad(u32 a, u32 b, u32 c) {
+#ifndef CG_EMU
+    u32 r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+#else
+    return a * b + c;
+#endif
+}
+
 // One band of a scan: query rows [row0, row0 + 32 * RPL) (rows >= nq are padding), every reference column.  RPL rows per
 // lane, all in registers.  The only loop-carried chain inside a lane is F: with hp = max(diag + s, E) and g = max(hp - 3, 0),
 //   F' = max(F - 1, max(H - 3, 0)) = max(F - 1, g)          (H = max(hp, F), and F - 3 < F - 1)
@@ -89,29 +105,41 @@ struct CgRaEnd { int score, col, row; };
 // register — the F chain runs down them — so a lane is split into two VIRTUAL lanes of RPL / 2 rows, A (low halves) and B (high
 // halves), B one step behind A in the wavefront: at step t virtual lane v = 2 lane + half works on column t - v.  A's first row is
 // fed by the previous lane's B (the shuffle, as before), B's first row by the same lane's A of the step before (registers).  H, E,
-// F, the diagonal and the column maximum are packed pairs: VIADDMNMX.S16x2 / VIMNMX.S16x2 do both cells; the match score comes from
-// the packed codes by exclusive-or (codes are < 8: (x + 7) >> 3 is "x != 0" in both halves without a carry between them).
+// F, the diagonal and the column maximum are packed pairs: VIADDMNMX.S16x2 / VIMNMX.S16x2 do both cells; the match scores come from a
+// query profile in shared memory (below).
 // Columns outside [0, nr) are computed too — before the first column the inputs are zeros and a code that matches nothing, which
 // leaves the all-zero state untouched; after the last one nobody reads the state — only the maximum tracking and the band-boundary
-// store look at the column index.  The running maximum is per virtual lane and found by compare on the rare step that raises it.
-template <int RPL>
+// store look at the column index.  Column maximum and its first row: when every score of the scan stays below 2^11 (KEY16: alignments
+// of up to 959 bases, i.e. every window of the usual sizes) the pair (h, row) is one halfword key h * 16 + (15 - i), maximised with the
+// same packed instruction; otherwise the maximum alone is tracked and the row is found by compare on the steps that raise it (some lane
+// of the warp does at nearly every step, so that path is only for the long alignments).
+template <int RPL, bool KEY16>
 __device__ __forceinline__ void cg_ra_band(const char* qsrc, int qfirst, int qstep, int nq, int row0, const u8* refc, int rfirst, int rstep,
                                            int nr, const u32* in_msgs, u32* out_msgs, bool first_band, bool last_band,
-                                           int& best, int& bcol, int& brow) {
+                                           int& best, int& bcol, int& brow, u32* prof, const u32 zero) {
     static_assert(RPL % 2 == 0, "two virtual lanes per lane");
     constexpr int R2 = RPL / 2;
     constexpr u32 NOMATCH = 6u;                                    // matches no query code (0..3, 5 = N, 7 = padding)
     const int lane = (int)(threadIdx.x & 31u);
-    u32 H2[R2], E2[R2], Q2[R2];
+    u32 H2[R2], E2[R2];
     const int my0 = row0 + lane * RPL;
+    // Query profile of the band in shared memory: prof[(a * R2 + i) * 32 + lane] = score of reference letter a against row i of A (low
+    // half) and against row i of B (high half); a = 4: a reference N / nothing, every row scores -2.  A cell pair's scores are then
+    // two LDS and one byte permute instead of seven integer instructions (the ALU pipe is what bounds this kernel).
+    __syncwarp();
 #pragma unroll
     for (int i = 0; i < R2; ++i) {
         u32 ca = 7u, cb = 7u;                                      // padding row: matches nothing
         if (my0 + i < nq) { ca = cg_ra_code(qsrc[qfirst + qstep * (my0 + i)]); if (ca == 4u) ca = 5u; }      // N never matches, not even N (ssw_cpp.cpp:47-55)
         if (my0 + R2 + i < nq) { cb = cg_ra_code(qsrc[qfirst + qstep * (my0 + R2 + i)]); if (cb == 4u) cb = 5u; }
-        Q2[i] = ca | (cb << 16);
+#pragma unroll
+        for (u32 a = 0; a < 5; ++a) prof[(a * R2 + i) * 32 + lane] = (ca == a ? 2u : 0xfffeu) | ((cb == a ? 2u : 0xfffeu) << 16);
         H2[i] = 0; E2[i] = 0;
     }
+    __syncwarp();
+    const u32* pl = prof + lane;
+    // `zero`: 0 in a register the compiler cannot fold (the kernel derives it from an argument): VIADDMNMX.S16x2 wants its third operand
+    // in a register, and a literal 0 is re-materialised by a PRMT in front of every use (two more ALU-pipe instructions per cell pair)
     int bestA = best, bcolA = bcol, browA = brow, bestB = best, bcolB = bcol, browB = brow;
     u32 dA = 0, dB = 0, a_h = 0, a_f = 0, a_rc = NOMATCH;          // diagonals of the two first rows; A's last row of the step before
     u32 out_msg = NOMATCH;
@@ -124,22 +152,21 @@ __device__ __forceinline__ void cg_ra_band(const char* qsrc, int qfirst, int qst
         const u32 in_msg = lane == 0 ? feed : up_msg;
         const int cA = t - 2 * lane, cB = cA - 1;
         const u32 rcA = in_msg & 7u, hA_in = in_msg >> 18;
-        const u32 rc2 = rcA | (a_rc << 16);
+        const u32* pa = pl + (rcA < 4u ? rcA : 4u) * (R2 * 32);
+        const u32* pb = pl + (a_rc < 4u ? a_rc : 4u) * (R2 * 32);
         u32 f2 = ((in_msg >> 4) & 0x3fffu) | (a_f << 16);
         u32 d2 = dA | (dB << 16);
-        u32 h2 = 0, cm2 = 0;
+        u32 h2 = 0, cm2 = 0;                                         // cm2: packed column maxima, or packed keys (KEY16)
 #pragma unroll
         for (int i = 0; i < R2; ++i) {
-            const u32 x = Q2[i] ^ rc2;
-            const u32 nz = ((x + 0x00070007u) >> 3) & 0x00010001u;                 // 1 per half that differs
-            const u32 sc = 0x00020002u ^ ((nz * 0xffffu) & 0xfffcfffcu);           // +2 / -2
+            const u32 sc = __byte_perm(pa[32 * i], pb[32 * i], 0x7610);            // A's score for its column | B's for its own
             const u32 hp = cg_viaddmax2(d2, sc, E2[i]);                            // E, f >= 0: the floor at 0 is implied
-            const u32 g = cg_viaddmax2_relu(hp, 0xfffdfffdu, 0u);
+            const u32 g = cg_viaddmax2(hp, 0xfffdfffdu, zero);
             h2 = cg_vmax2(hp, f2);
             f2 = cg_viaddmax2(f2, 0xffffffffu, g);
             d2 = H2[i]; H2[i] = h2;
-            cm2 = cg_vmax2(cm2, h2);
-            E2[i] = cg_viaddmax2(E2[i], 0xffffffffu, cg_viaddmax2_relu(h2, 0xfffdfffdu, 0u));
+            cm2 = cg_vmax2(cm2, KEY16 ? cg_ra_mad(h2, 16u, (u32)(15 - i) * 0x00010001u) : h2);
+            E2[i] = cg_viaddmax2(E2[i], 0xffffffffu, cg_viaddmax2(h2, 0xfffdfffdu, zero));
         }
         // hand-over: B's last row to the next lane, A's last row to this lane's B
         const u32 hB = h2 >> 16, fB = f2 >> 16;
@@ -147,18 +174,25 @@ __device__ __forceinline__ void cg_ra_band(const char* qsrc, int qfirst, int qst
         if (!last_band && lane == 31 && cB >= 0 && cB < nr) out_msgs[cB] = out_msg;
         dA = hA_in; dB = a_h;
         a_h = h2 & 0xffffu; a_f = f2 & 0xffffu; a_rc = rcA;
-        const int cmA = (int)(cm2 & 0xffffu), cmB = (int)(cm2 >> 16);
-        if (cA >= 0 && cA < nr && (cmA > bestA || (cmA == bestA && cA < bcolA && cmA > 0))) {
-            int r = 0;
+        if (KEY16) {
+            const int kA = (int)(cm2 & 0xffffu), kB = (int)(cm2 >> 16);
+            const int cmA = kA >> 4, cmB = kB >> 4;
+            if (cA >= 0 && cA < nr && (cmA > bestA || (cmA == bestA && cA < bcolA && cmA > 0))) { bestA = cmA; bcolA = cA; browA = my0 + 15 - (kA & 15); }
+            if (cB >= 0 && cB < nr && (cmB > bestB || (cmB == bestB && cB < bcolB && cmB > 0))) { bestB = cmB; bcolB = cB; browB = my0 + R2 + 15 - (kB & 15); }
+        } else {
+            const int cmA = (int)(cm2 & 0xffffu), cmB = (int)(cm2 >> 16);
+            if (cA >= 0 && cA < nr && (cmA > bestA || (cmA == bestA && cA < bcolA && cmA > 0))) {
+                int r = 0;
 #pragma unroll
-            for (int i = R2 - 1; i >= 0; --i) if ((int)(H2[i] & 0xffffu) == cmA) r = i;
-            bestA = cmA; bcolA = cA; browA = my0 + r;
-        }
-        if (cB >= 0 && cB < nr && (cmB > bestB || (cmB == bestB && cB < bcolB && cmB > 0))) {
-            int r = 0;
+                for (int i = R2 - 1; i >= 0; --i) if ((int)(H2[i] & 0xffffu) == cmA) r = i;
+                bestA = cmA; bcolA = cA; browA = my0 + r;
+            }
+            if (cB >= 0 && cB < nr && (cmB > bestB || (cmB == bestB && cB < bcolB && cmB > 0))) {
+                int r = 0;
 #pragma unroll
-            for (int i = R2 - 1; i >= 0; --i) if ((int)(H2[i] >> 16) == cmB) r = i;
-            bestB = cmB; bcolB = cB; browB = my0 + R2 + r;
+                for (int i = R2 - 1; i >= 0; --i) if ((int)(H2[i] >> 16) == cmB) r = i;
+                bestB = cmB; bcolB = cB; browB = my0 + R2 + r;
+            }
         }
     }
     // the lane's (score, first column, first row) = the better of its two virtual lanes (A's rows are the smaller ones)
@@ -171,10 +205,11 @@ __device__ __forceinline__ void cg_ra_band(const char* qsrc, int qfirst, int qst
 // reaches it and the smallest row holding it there.  bnd: 2 * rmax u32 of per-warp scratch (the wavefront messages of a
 // band's last row, read back by lane 0 of the next band, when nq > 32 * CG_RA_RPL).
 __device__ CG_NOINLINE CgRaEnd cg_ra_scan(const char* qsrc, int qfirst, int qstep, int nq, const u8* refc, int rfirst, int rstep,
-                                          int nr, u32* bnd, u32 rmax) {
+                                          int nr, u32* bnd, u32 rmax, u32* prof, const u32 zero) {
     int best = 0, bcol = 0x7fffffff, brow = 0x7fffffff;
     const int band_rows = 32 * (int)CG_RA_RPL;
     const int n_bands = (nq + band_rows - 1) / band_rows;
+    const bool key16 = 2 * min(nq, nr) + 128 < 2048;
     for (int b = 0; b < n_bands; ++b) {
         const int row0 = b * band_rows;
         const int rows = min(band_rows, nq - row0);
@@ -182,13 +217,16 @@ __device__ CG_NOINLINE CgRaEnd cg_ra_scan(const char* qsrc, int qfirst, int qste
         const bool last_band = b + 1 == n_bands;
         const u32* in_msgs = bnd + (size_t)((b + 1) & 1) * rmax;    // written by band b - 1
         u32* out_msgs = bnd + (size_t)(b & 1) * rmax;
-#define CG_RA_BAND(R) cg_ra_band<R>(qsrc, qfirst, qstep, nq, row0, refc, rfirst, rstep, nr, in_msgs, out_msgs, b == 0, last_band, best, bcol, brow)
-        if (rpl <= 4) CG_RA_BAND(4);
-        else if (rpl <= 8) CG_RA_BAND(8);
-        else if (rpl <= 12) CG_RA_BAND(12);
-        else if (rpl <= 16) CG_RA_BAND(16);
-        else if (rpl <= 18) CG_RA_BAND(18);
-        else CG_RA_BAND(20);
+#define CG_RA_BAND(R, K) cg_ra_band<R, K>(qsrc, qfirst, qstep, nq, row0, refc, rfirst, rstep, nr, in_msgs, out_msgs, b == 0, last_band, best, bcol, brow, prof, zero)
+        if (key16) {                                               // every score of the scan (and of its 64 run-out columns) below 2^11
+            if (rpl <= 4) CG_RA_BAND(4, true);
+            else if (rpl <= 8) CG_RA_BAND(8, true);
+            else if (rpl <= 12) CG_RA_BAND(12, true);
+            else if (rpl <= 16) CG_RA_BAND(16, true);
+            else if (rpl <= 18) CG_RA_BAND(18, true);
+            else CG_RA_BAND(20, true);
+        } else if (rpl <= 10) CG_RA_BAND(10, false);
+        else CG_RA_BAND(20, false);
 #undef CG_RA_BAND
         __syncwarp();
     }
@@ -319,12 +357,18 @@ __device__ void cg_ra_move(char* base, u32 dst, u32 src, u32 n) {
     }
 }
 
+// 128 registers: 4 CTAs (16 warps) per SM.  No min-blocks clause: with it (4, 5 or 6 CTAs: 128 / 96 / 80 registers) ptxas schedules the
+// unrolled row loop worse and the kernel loses 12 % (1 598 -> 1 400 GCUPS at 4; the extra warps of 5 and 6 do not win it back).
+#define CG_RA_CTAS_PER_SM 4
 __global__ void __launch_bounds__(CG_RA_WARPS * 32) k_reanchor(CgReanchorArgs P) {
     CG_DYN_SMEM(smem_raw);
     const u32 lane = threadIdx.x & 31u, wip = threadIdx.x >> 5;
     const u32 rpad = (P.rmax + 15u) & ~15u;
-    const size_t smem_per_warp = rpad + (P.lines_in_smem ? 3 * (size_t)cg_ra_line_bytes(P.maxL) : 0);
+    // per warp: the reference codes, then ONE region shared by the scans' query profile and the three rolling lines of the banded
+    // sub-alignment (lane 0 runs it between scans, every scan rebuilds its profile): a second region would cost a resident CTA
+    const size_t smem_per_warp = cg_ra_smem_per_warp(P.rmax, P.maxL, P.lines_in_smem != 0);
     u8* refc = (u8*)smem_raw + (size_t)wip * smem_per_warp;
+    u32* prof = (u32*)(refc + rpad);
     const u32 gw = blockIdx.x * CG_RA_WARPS + wip;
     u8* sc = P.scratch + (size_t)gw * P.scratch_stride;
     char* bufs[3];
@@ -336,6 +380,7 @@ __global__ void __launch_bounds__(CG_RA_WARPS * 32) k_reanchor(CgReanchorArgs P)
     u8* dir = (u8*)bnd + cg_ra_bnd_bytes(P.rmax) + 3 * cg_ra_line_bytes(P.maxL);
     u64 cells = 0;
     u32 flags = 0;
+    const u32 zero = P.n_reads >> 31;                             // 0 (n_reads < 2^31), opaque to the compiler: cg_ra_band
 
     for (;;) {
         u32 slot = 0;
@@ -381,10 +426,10 @@ __global__ void __launch_bounds__(CG_RA_WARPS * 32) k_reanchor(CgReanchorArgs P)
             __syncwarp();
             for (u32 i = lane; i < (u32)sizeAl; i += 32) refc[i] = (u8)cg_ra_code(head[alPos + i]);
             __syncwarp();
-            const CgRaEnd fw = cg_ra_scan(cur, 0, 1, (int)n, refc, 0, 1, sizeAl, bnd, P.rmax);                          // :87
+            const CgRaEnd fw = cg_ra_scan(cur, 0, 1, (int)n, refc, 0, 1, sizeAl, bnd, P.rmax, prof, zero);                          // :87
             cells += (u64)n * (u64)sizeAl;
             if (fw.score <= 0) { flags |= CG_RA_FLAG_DEGENERATE; break; }
-            const CgRaEnd bw = cg_ra_scan(cur, fw.row, -1, fw.row + 1, refc, fw.col, -1, fw.col + 1, bnd, P.rmax);
+            const CgRaEnd bw = cg_ra_scan(cur, fw.row, -1, fw.row + 1, refc, fw.col, -1, fw.col + 1, bnd, P.rmax, prof, zero);
             cells += (u64)(fw.row + 1) * (u64)(bw.col + 1);
             const u32 beg = (u32)(fw.col - bw.col + alPos), end = (u32)(fw.col + alPos);                                  // :88-89
             const char* curp = cur + (fw.row - bw.row);                                                                   // :90
@@ -412,12 +457,12 @@ __global__ void __launch_bounds__(CG_RA_WARPS * 32) k_reanchor(CgReanchorArgs P)
                             __syncwarp();
                             for (u32 i = lane; i < overlap; i += 32) refc[i] = (u8)cg_ra_code(s2[i]);
                             __syncwarp();
-                            const CgRaEnd f2 = cg_ra_scan(s1, 0, 1, (int)overlap, refc, 0, 1, (int)overlap, bnd, P.rmax);
+                            const CgRaEnd f2 = cg_ra_scan(s1, 0, 1, (int)overlap, refc, 0, 1, (int)overlap, bnd, P.rmax, prof, zero);
                             cells += (u64)overlap * (u64)overlap;
                             int ins = 0, del = 0;
                             u32 bad = 0;
                             if (f2.score > 0) {
-                                const CgRaEnd b2 = cg_ra_scan(s1, f2.row, -1, f2.row + 1, refc, f2.col, -1, f2.col + 1, bnd, P.rmax);
+                                const CgRaEnd b2 = cg_ra_scan(s1, f2.row, -1, f2.row + 1, refc, f2.col, -1, f2.col + 1, bnd, P.rmax, prof, zero);
                                 cells += (u64)(f2.row + 1) * (u64)(b2.col + 1);
                                 const int rb = f2.col - b2.col, qb = f2.row - b2.row;
                                 const int refLen = b2.col + 1, readLen = b2.row + 1;

@@ -105,6 +105,22 @@ def test_emulated_kernel_matches_oracle_and_golden(emu, oracle, reanchor_golden,
         assert cor.reanchor_stats()["dp_cells"] == int(oracle.lib.oracle_reanchor_cells())
 
 
+def _very_long_windows():
+    # windows of 1 100 bases: alignments of more than 959 bases leave the halfword (score, row) keys of k_reanchor's scan (KEY16) for
+    # the compare path, and need two bands of rows
+    return synth_reads(2, 4, truth_len=3600, seed=21, profile="PB", window_size=1100, window_overlap=80)
+
+
+def test_emulated_kernel_on_alignments_too_long_for_halfword_keys(emu, oracle, reference):
+    batch, reads = _very_long_windows()
+    res, _ = oracle.correct_windows(batch, Params(), threads=8, with_status=False)
+    want, _ = oracle.reanchor_reads(batch, res, reads, Params(), threads=4)
+    if reference is not None:
+        ref, _ = reference.reanchor_reads(batch, res, reads, Params())
+        assert_same_reads(want, ref, "oracle vs reference, 1100-base windows")
+    assert_same_reads(emu().reanchor_reads(batch, res, reads), want, "emulated kernel, 1100-base windows")
+
+
 def test_emulated_resident_results_are_reused(emu, oracle):
     """results of correct_windows on the same handle: the device copies are used, same reads as with host copies."""
     batch, reads = synth_reads(3, 4, truth_len=1700, seed=12, thin_every=4, thin_seqs=1)
@@ -147,6 +163,14 @@ def test_gpu_matches_reference_if_present(gpu, reference):
     res, _ = reference.correct_windows(batch, Params(), threads=os.cpu_count() or 4, with_status=False)
     want, _ = reference.reanchor_reads(batch, res, reads, threads=8)
     assert_same_reads(cor.reanchor_reads(batch, res, reads), want, "GPU vs the unmodified reference")
+
+
+@pytest.mark.gpu
+def test_gpu_alignments_too_long_for_halfword_keys(gpu, oracle):
+    batch, reads = _very_long_windows()
+    res, _ = oracle.correct_windows(batch, Params(), threads=8, with_status=False)
+    want, _ = oracle.reanchor_reads(batch, res, reads, Params(), threads=4)
+    assert_same_reads(gpu().reanchor_reads(batch, res, reads), want, "1100-base windows")
 
 
 @pytest.mark.gpu
