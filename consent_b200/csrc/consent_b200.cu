@@ -1752,7 +1752,7 @@ int cg_stage_ms(const cg_handle* h, float ms[CG_N_STAGES], uint32_t launches[CG_
 }
 
 // Per-stage text dump of window w of the batch cg_run just processed, in the format of the oracle's / the reference harness's
-// dump (oracle/consent_oracle.h): S, M (solid list), T (template k-mers that survive fill + filter), A (chain), R (mean distances),
+// dump (the per-stage text the test oracle prints): S, M (solid list), T (template k-mers that survive fill + filter), A (chain), R (mean distances),
 // G (regions), g (their segments), c (their consensuses), C (the stitched consensus).  Test instrumentation: the workspaces of a
 // chunk are reused by the next one, so the batch must have been a single chunk.  *text is malloc'ed (free() it).
 int cg_debug_dump_window(cg_handle* h, uint32_t w, char** text) {

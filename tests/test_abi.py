@@ -70,5 +70,12 @@ def test_invalid_parameters_are_rejected(gpu_lib):
     h = C.c_void_p()
     for bad in (cg_params(1, 4, 8, 2), cg_params(16, 4, 8, 2), cg_params(9, 0, 8, 2)):
         assert lib.cg_create(0, C.byref(bad), C.byref(h)) == -1
+    # k = 10 .. 15 are valid since round 2 (hashed k-mer index): on a box without a GPU the only possible outcome is CG_ERR_NO_DEVICE —
+    # the product has no CPU path
     k12 = cg_params(12, 4, 8, 2)
-    assert lib.cg_create(0, C.byref(k12), C.byref(h)) == -6          # CG_ERR_CAPACITY: stated limit of this build
+    rc = lib.cg_create(0, C.byref(k12), C.byref(h))
+    assert rc in (0, -2)
+    if rc == 0:
+        lib.cg_destroy(h)
+    else:
+        assert b"no CPU path" in lib.cg_last_error(None)
