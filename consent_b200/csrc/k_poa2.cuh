@@ -749,6 +749,8 @@ __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s
 
     u32 V = 0, nseqs = 0, cur = 0, sumdeg = 0;
     bool dfs_valid = false;
+    bool cache_ok = false;                                           // the previous sequence's alignment can be applied again (below)
+    u32 cache_len = 0, cache_naln = 0;
     CG_T_DECL;
     CG_T_MARK(6);
     u64 j_aln = 0, j_cells = 0, j_pred = 0;
@@ -758,11 +760,19 @@ __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s
         const u32 L = Pk::seg_len(sg);
         if (L == 0) continue;                                        // graph.cpp:160 — not a row of the MSA
         const u8* seq = bases + v.seq_off[Pk::seg_read(sg)] + Pk::seg_start(sg);
-        if (L <= T::SEQCAP) {                                        // stage the segment next to the graph
+        // The same string as the sequence before it, whose alignment left the graph as it was (same nodes, same edges, hence the same row
+        // order)?  Then the score matrix, the winning cell, the tie order and the traceback would all come out the same: the alignment
+        // pairs of that sequence are still in `work` and are applied again.  In regions of up to 16 bases (half the jobs of the config-3
+        // shape) two thirds of the sequences repeat an earlier one, and 45 % of their alignments are such repeats.
+        bool reuse = false;
+        if (L <= T::SEQCAP) {                                        // stage the segment next to the graph (where the previous one still is)
             u8* sb = s.seqbuf();
+            const bool cand = T::SMEM && cache_ok && L == cache_len;
+            bool same = true;
             __syncwarp();
-            for (u32 i = lane; i < L; i += 32) sb[i] = seq[i];
+            for (u32 i = lane; i < L; i += 32) { const u8 ch = seq[i]; if (T::SMEM) same = same && ch == sb[i]; sb[i] = ch; }
             __syncwarp();
+            reuse = cand && __all_sync(CG_FULL, same);
             seq = sb;
         }
         constexpr bool WIDE = T::STORE == CG_P2_ALL_GLOBAL;    // lane-contiguous rows of 64 CH columns (k_poa2_wide.cuh)
@@ -774,7 +784,10 @@ __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s
 #endif
         const u32 Wd = L + 1, Ws = WIDE ? 64u * CHw : (L + 2) & ~1u;   // columns 0..L; rows are stored with an even stride
         u32 n_aln = 0;
-        if (V != 0) {
+        if (reuse) {
+            n_aln = cache_naln;
+            j_aln += 1; j_cells += (u64)(V + 1) * L; j_pred += (u64)sumdeg * L;      // the work counters describe the algorithm, not this shortcut
+        } else if (V != 0) {
             if ((u64)(V + 1) * Ws > (u64)T::HCELLS) return CG_NONE32;
             i32 bv = 0;
             CgPoa2Max trk;
@@ -989,7 +1002,11 @@ __device__ __forceinline__ u32 cg_poa2_job(const CgChunk& c, const CgPoa2G<T>& s
         }
         nseqs++;
         if (__any_sync(CG_FULL, ovf)) return CG_NONE32;
-        if (!__any_sync(CG_FULL, changed)) { __syncwarp(); CG_T_MARK(3); continue; }      // same nodes, same edges: same order, same rows
+        if (!__any_sync(CG_FULL, changed)) {                         // same nodes, same edges: same order, same rows
+            cache_ok = V0 != 0 && L <= T::SEQCAP; cache_len = L; cache_naln = n_aln;
+            __syncwarp(); CG_T_MARK(3); continue;
+        }
+        cache_ok = false;
         dfs_valid = false;
         __syncwarp();
         CG_T_MARK(3);
