@@ -116,6 +116,7 @@ struct Shared {
     std::string error;
     unsigned long long windows = 0, error_windows = 0, piles = 0;
     double t_first = -1, t_last = 0;                 // seconds since start: first batch taken by a GPU, last batch written
+    double t_created = 0, t_store = 0, t_first_done = -1;   // last handle created, last read store shipped, first batch finished
     std::chrono::steady_clock::time_point t0;
     double now() const { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
 };
@@ -134,10 +135,12 @@ void gpu_main(Shared* sh, int device) {
     cg_params prm = {o.merSize, o.solidThresh, o.commonKMers, o.minAnchors};
     cg_handle* h = nullptr;
     if (cg_create(device, &prm, &h) != CG_OK) { fail(sh, std::string("cg_create: ") + cg_last_error(nullptr)); return; }
+    { std::lock_guard<std::mutex> lk(sh->err_mu); sh->t_created = sh->now(); }
     const char dummy = 'A';
     if (cg_set_read_store(h, st.size(), st.off.data(), st.bases.empty() ? &dummy : st.bases.data()) != CG_OK) {
         fail(sh, std::string("cg_set_read_store: ") + cg_last_error(h)); cg_destroy(h); return;
     }
+    { std::lock_guard<std::mutex> lk(sh->err_mu); sh->t_store = sh->now(); }
     const cg_read_names names = {st.size(), st.name_off.data(), st.name_bytes.empty() ? &dummy : st.name_bytes.data()};
     const bool trim = !o.polishing && o.proof.empty();                               // doTrimRead, CONSENT-correction.cpp:17,70-73
     Batch b;
@@ -177,6 +180,7 @@ void gpu_main(Shared* sh, int device) {
         {
             std::lock_guard<std::mutex> lk(sh->err_mu);
             sh->t_last = sh->now();
+            if (sh->t_first_done < 0) sh->t_first_done = sh->t_last;
         }
     }
     cg_destroy(h);
@@ -285,8 +289,9 @@ int main(int argc, char* argv[]) {
     if (o.verbose) {
         const double span = sh.t_last - sh.t_first;
         fprintf(stderr, "{\"gpus\": %zu, \"batches\": %zu, \"piles\": %llu, \"windows\": %llu, \"load_s\": %.3f, \"first_batch_at_s\": %.3f, "
+                        "\"handles_created_at_s\": %.3f, \"read_store_shipped_at_s\": %.3f, \"first_batch_done_at_s\": %.3f, "
                         "\"processing_s\": %.3f, \"total_s\": %.3f, \"windows_per_s_processing\": %.0f, \"windows_per_s_total\": %.0f}\n",
-                o.gpus.size(), seq, sh.piles, sh.windows, t_loaded, sh.t_first, span, sh.now(), span > 0 ? sh.windows / span : 0.0,
+                o.gpus.size(), seq, sh.piles, sh.windows, t_loaded, sh.t_first, sh.t_created, sh.t_store, sh.t_first_done, span, sh.now(), span > 0 ? sh.windows / span : 0.0,
                 sh.windows / sh.now());
     }
     return EXIT_SUCCESS;
