@@ -23,6 +23,7 @@
 #include "k_extract.cuh"      // CgOverlapDev
 
 enum { CG_IN_FLAG_COLUMNS = 1u, CG_IN_FLAG_NUMBER = 2u, CG_IN_FLAG_NAME = 4u };
+#define CG_IN_SAME_Q 0xfffffffeu   // CgPafRec::q of a line whose qName is the previous line's (same pile): not looked up again
 #define CG_IN_TILE 4096u      // bytes of text per CTA of k_paf_count / k_paf_lines: 256 threads x 16 bytes
 
 struct CgPafRec { u32 q, qlen, res; CgOverlapDev o; };            // 10 x u32; q == CG_NONE32: an empty line
@@ -201,7 +202,24 @@ __global__ void __launch_bounds__(256) k_paf_parse(CgIngestArgs A) {
     if (ntabs < 11u) { if (lane == 0) { atomicOr(A.ctl, (u32)CG_IN_FLAG_COLUMNS); out[0] = CG_NONE32; } return; }
     // the two names, by the whole warp
     const u32 t4 = tab[4] + 1u;
-    const u32 qid = cg_in_lookup_warp(A, line, tab[0], lane);
+    // Consecutive lines of a pile share their qName (a 150-deep pile: 150 lines, one name): a line that repeats the previous line's name
+    // — the same bytes up to and including the tab — skips the hash, the probe and the compare against the table and is marked instead;
+    // the pile takes its read from its first line.  (An empty line in between ends the pile, src/alignmentPiles.cpp:29-37: it has no name.)
+    bool same_q = false;
+    if (i > 0) {
+        const u64 pb = i > 1 ? A.nl_pos[i - 2] + 1u : 0u;
+        const u32 plen = (u32)(A.nl_pos[i - 1] - pb), n0 = tab[0];
+        if (plen > n0) {
+            const char* pl = A.text + pb;
+            u32 diff = 0;
+            for (u32 base = 0; base <= n0 && !diff; base += 32u) {
+                const u32 x = base + lane;
+                diff = __ballot_sync(CG_FULL, x <= n0 && pl[x] != line[x]);
+            }
+            same_q = diff == 0u;
+        }
+    }
+    const u32 qid = same_q ? CG_IN_SAME_Q : cg_in_lookup_warp(A, line, tab[0], lane);
     const u32 tid = cg_in_lookup_warp(A, line + t4, tab[5] - t4, lane);
     // the other columns: lane f owns column f = [st, en)
     u32 st = 0, en = len;
@@ -247,7 +265,7 @@ __global__ void __launch_bounds__(256) k_paf_heads(CgIngestArgs A) {
     u32 hd = 0;
     if (i < A.n_lines) {
         const u32 q = A.rec[i].q;
-        if (q != CG_NONE32) { hd = 1; if (i) { const u32 pq = A.rec[i - 1].q; if (pq == q) hd = 0; } }
+        if (q != CG_NONE32 && q != CG_IN_SAME_Q) { hd = 1; if (i) { const u32 pq = A.rec[i - 1].q; if (pq == q) hd = 0; } }
     }
     u32 total;
     const u32 before = cg_block_scan(hd, scratch, &total);
@@ -376,7 +394,7 @@ __global__ void __launch_bounds__(32) k_paf_select(CgIngestArgs A) {
             const CgPafRec r = A.rec[first + (u32)a[n - 1u - j]];
             A.ov[o0 + j] = r.o;
             A.res[o0 + j] = r.res;
-            if (j == 0) { A.pile_read[p] = r.q; A.pile_qlen[p] = r.qlen; }      // alignments.begin()
+            if (j == 0) { A.pile_read[p] = A.rec[first].q; A.pile_qlen[p] = r.qlen; }      // alignments.begin(); the pile's read: its first line's (k_paf_parse)
         }
         __syncwarp();
     }
