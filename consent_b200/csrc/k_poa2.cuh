@@ -250,6 +250,14 @@ template <class T> __device__ __forceinline__ void cg_poa2_dfs_prepare(const CgP
             const u32 deg = ((u32)m >> 3) & 31u;
             nt[i] = (deg > 0 ? Pk::get(P, 0) : 0u) | ((deg > 1 ? Pk::get(P, 1) : 0u) << 10) | (deg << 20) | (((u32)m & 3u) << 25) | (1u << 29);
         }
+    } else if constexpr (T::SMEM) {
+        static_assert(!T::SMEM || (sizeof(typename T::IdT) == 1 && 2 * T::VCAP <= CgPoa2Lay<T>::TMP0), "halfword node table over the marks / check bytes");
+        u16* nt = (u16*)(s.b() + CgPoa2Lay<T>::o_tmp);
+        for (u32 i = lane; i < V; i += 32) {
+            const u32 m = (u32)s.meta(i);
+            const u32 deg = (m >> 3) & 31u;
+            nt[i] = (u16)((deg ? Pk::first(s.pred(i)) : 0u) | ((deg < 7u ? deg : 7u) << 8) | ((m & 3u) << 11) | 0x8000u);
+        }
     } else {
         for (u32 i = lane; i < V; i += 32) { s.marks(i) = 0; s.check(i) = 1; }
     }
@@ -315,12 +323,69 @@ template <class T> __device__ CG_NOINLINE bool cg_poa2_dfs_compact(const CgPoa2G
 #undef CG_DFS_AT
     return true;
 }
+// The compact tiers (byte ids, graph in shared memory) keep one HALFWORD per node over the marks / check bytes: first in-edge |
+// in-degree << 8 (7 = "7 or 8") | aligned nodes << 11 | mark << 13 | check << 15.  Nine nodes in ten have at most one in-edge and no
+// aligned node: their visit reads that halfword and nothing else (the walk is one lane: every instruction saved is a whole issue slot).
+template <class T> __device__ CG_NOINLINE bool cg_poa2_dfs_small(const CgPoa2G<T>& s, u32 V) {
+    CG_P2_TYPES;
+    constexpr u32 FIN = 1u << W, MK = 13, MKM = 3u << MK, CHECK = 0x8000u;
+    u16* nt = (u16*)(s.b() + CgPoa2Lay<T>::o_tmp);
+    u32 nrank = 0, sp = 0;
+    for (u32 i = 0; i < V; ++i) {
+        if ((nt[i] & MKM) != 0) continue;
+        s.stk(sp++) = (ItemT)i;
+        while (sp != 0) {
+            const u32 top = s.stk(sp - 1);
+            const u32 id = top & IDNONE;
+            bool finish = (top & FIN) != 0;
+            const u32 e = nt[id];
+            const u32 degc = (e >> 8) & 7u, nal = (e >> 11) & 3u;
+            if (!finish) {
+                if ((e & MKM) == (2u << MK)) { --sp; continue; }
+                const u32 sp0 = sp;
+                if (degc <= 1) {
+                    if (sp + degc + 3 > T::SCAP) return false;
+                    if (degc) { const u32 b = e & 0xffu; if ((nt[b] & MKM) != (2u << MK)) s.stk(sp++) = (ItemT)b; }
+                } else {
+                    const u32 deg = degc < 7u ? degc : (((u32)s.meta(id) >> 3) & 31u);
+                    if (sp + deg + 3 > T::SCAP) return false;
+                    const VecT P = s.pred(id);
+                    for (u32 q = 0; q < deg; ++q) { const u32 b = Pk::get(P, q); if ((nt[b] & MKM) != (2u << MK)) s.stk(sp++) = (ItemT)b; }
+                }
+                if ((e & CHECK) && nal) {
+                    const MetaT m = s.meta(id);
+                    for (u32 a = 0; a < nal; ++a) {
+                        const u32 aid = (u32)((m >> (W * (a + 1))) & IDMASK);
+                        if ((nt[aid] & MKM) != (2u << MK)) { s.stk(sp++) = (ItemT)aid; nt[aid] = (u16)(nt[aid] & ~CHECK); }
+                    }
+                }
+                if (sp == sp0) finish = true;
+                else { nt[id] = (u16)((nt[id] & ~MKM) | (1u << MK)); s.stk(sp0 - 1) = (ItemT)(id | FIN); }
+            }
+            if (finish) {
+                const u32 e2 = nt[id];
+                nt[id] = (u16)((e2 & ~MKM) | (2u << MK));
+                if (e2 & CHECK) {
+                    s.xr2n(nrank) = (IdT)id; s.xlead(nrank) = 1; ++nrank;
+                    if (nal) {
+                        const MetaT m = s.meta(id);
+                        for (u32 a = 0; a < nal; ++a) { s.xr2n(nrank) = (IdT)((m >> (W * (a + 1))) & IDMASK); s.xlead(nrank) = 0; ++nrank; }
+                    }
+                }
+                --sp;
+            }
+        }
+    }
+    return true;
+}
+
 // marks / check (or the packed table) by the warp, the walk by lane 0, the verdict to every lane
 template <class T> __device__ __forceinline__ bool cg_poa2_dfs_run(const CgPoa2G<T>& s, u32 V) {
     cg_poa2_dfs_prepare(s, V);
     bool ok = true;
     if (cg_lane() == 0) {
         if constexpr (CgDfsCompact<T>::USE) ok = cg_poa2_dfs_compact(s, V);
+        else if constexpr (T::SMEM) ok = cg_poa2_dfs_small(s, V);
         else ok = cg_poa2_dfs(s, V);
     }
     ok = __shfl_sync(CG_FULL, (u32)ok, 0) != 0;
