@@ -24,9 +24,9 @@
 //
 // Tiers (one template, T = ids x storage x capacities).  What decides a tier's speed is how many warps an SM holds
 // (every warp is a chain of dependent steps), i.e. shared memory per warp, so only small matrices live there:
-//   C1 : byte ids (<= 128 nodes), graph AND matrix (<= 2048 cells) in shared memory             20 warps / SM
+//   C1 : byte ids (<= 128 nodes, segments <= 32: one column per lane), graph AND matrix (<= 2048 cells) in shared memory   20 warps / SM
 //   G  : byte ids (<= 254 nodes), graph in shared memory, matrix in global memory (L2)            20 warps / SM
-//   W1 : 16-bit ids (<= 1024 nodes, 1024-base segments), everything in global memory (L2)         8 warps / SM
+//   W1 : 16-bit ids (<= 1024 nodes, 1024-base segments), everything in global memory (L2)         24 warps / SM
 //   W2 : 16-bit ids (<= 4096 nodes, 2048-base segments, 4 M cells), global memory                 2 warps / SM
 // A job that outgrows its tier (nodes, cells, in-degree, segment length) is re-queued for the next one before anything
 // is committed; in-degree > 16 and anything bigger end in k_poa (k_poa.cuh), which has no such limits.
@@ -97,7 +97,7 @@ template <class IdT_, int STORE_, u32 VCAP_, u32 HCELLS_, u32 LCAP_, u32 SEGCAP_
     static constexpr u32 CHF = 10;
     static constexpr u32 CHMAX = (LCAP_ + 64u) / 64u;                  // 64-column blocks of the longest segment
 };
-typedef CgPoa2Tier<u8, CG_P2_ALL_SMEM, 128, 2048, 64, 192, 4, 5> CgPoa2C1;
+typedef CgPoa2Tier<u8, CG_P2_ALL_SMEM, 128, 2048, 32, 192, 4, 5> CgPoa2C1;
 typedef CgPoa2Tier<u8, CG_P2_H_GLOBAL, 254, 30976, 120, 192, 4, 5> CgPoa2GT;
 #ifndef CG_W1_CTAS
 #define CG_W1_CTAS 6

@@ -18,7 +18,7 @@
 // POA job routing.  The final graph size of a region is predicted from its longest segment L and its depth n
 // (fit on PacBio-profile piles: V ~ 1.52 L + 0.022 L n - 7, +12 % margin); a wrong guess only costs a re-queue.
 // class 0/1: tier C1 (heavy / light), 2/3: tier G (heavy / light), 4/5: wide tiers (heavy / light).  Capacities mirror k_poa2.cuh.
-#define CG_POA_C1_LCAP 64u
+#define CG_POA_C1_LCAP 32u
 #define CG_POA_C1_VCAP 128u
 #define CG_POA_C1_CELLS 2048u
 #define CG_POA_G_LCAP 120u
