@@ -222,6 +222,23 @@ __device__ __forceinline__ bool cg_comparable_dec(double x, double lo, double hi
         return true;
     }
 }
+// The same two tests in integers, for the integer-valued arguments the path only ever has (lengths, positions, integer means; all below
+// 2^31).  Exactly the fp64 results: |x - m| < 5 is exact; x / m < 0.5 <=> 2 x < m and x / m > 2 <=> x > 2 m, because a quotient of two
+// such integers that is not exactly 0.5 (or 2) differs from it by at least 1 / (2 m) >= 2^-32, far more than the rounding of the
+// division (2^-53 relative); m = 0: x / 0 = inf (> 2: not comparable) for x > 0 and |0 - 0| < 5 for x = 0, which the integer tests
+// reproduce.  (One fp64 division per call was ~100 instructions of slow path on every read of every region.)
+__host__ __device__ __forceinline__ bool cg_comparable_mean_u(u32 x, u32 m) {
+    const u32 d = x > m ? x - m : m - x;
+    if (d < 5u) return true;
+    return !(2ull * x < (u64)m || (u64)x > 2ull * m);
+}
+__device__ __forceinline__ bool cg_comparable_dec_u(u32 x, u32 lo, u32 hi) {
+    if ((u64)x < (u64)hi + 5u) {
+        if ((u64)x + 5u > (u64)lo) return true;
+        return !(2ull * x < (u64)lo);
+    }
+    return !((u64)x > 2ull * hi);
+}
 
 // Window view used by k_split / k_poa to evaluate split_reads (bmean.cpp:476-554) for one (region, read).
 struct CgWinView {
@@ -248,9 +265,10 @@ __host__ __device__ __forceinline__ bool cg_eval_segment(const CgWinView& v, u32
         if (!ap) return false;
         u32 a = ap - 1;
         u32 l = a > len_r ? len_r : a;
-        double m = (double)((i32)trow[v.chain[0]] - 1);
+        const i32 mi = (i32)trow[v.chain[0]] - 1;
         *start = 0; *len = l;
-        return cg_comparable_mean((double)l, m) && l != 0;
+        if (mi < 0) return cg_comparable_mean((double)l, (double)mi) && l != 0;       // (the template holds every chain anchor: not reached)
+        return cg_comparable_mean_u(l, (u32)mi) && l != 0;
     }
     if (g == v.nA) {                                  // :497-503
         u32 ap = prow[v.chain[v.nA - 1]];
@@ -258,13 +276,16 @@ __host__ __device__ __forceinline__ bool cg_eval_segment(const CgWinView& v, u32
         u32 a = ap - 1;
         u32 l = len_r - a;
         u32 len0 = cg_seq_len(v, 0);
-        double m = (double)(size_t)((size_t)len0 - (size_t)(int64_t)((i32)trow[v.chain[v.nA - 1]] - 1));
+        const size_t ms = (size_t)len0 - (size_t)(int64_t)((i32)trow[v.chain[v.nA - 1]] - 1);
         *start = a; *len = l;
-        return cg_comparable_mean((double)l, m) && l != 0;
+        if (ms >> 31) return cg_comparable_mean((double)l, (double)ms) && l != 0;      // (an anchor beyond the template's end: not reached)
+        return cg_comparable_mean_u(l, (u32)ms) && l != 0;
     }
     u32 p1 = prow[v.chain[g - 1]], p2 = prow[v.chain[g]];   // :506-520
     if (!p1 || !p2) return false;
     u32 l = p2 - p1;
     *start = p1 - 1; *len = l;
-    return cg_comparable_mean((double)l, (double)v.rel[g - 1]) && l != 0;
+    const u32 mr = v.rel[g - 1];
+    if (mr >> 31) return cg_comparable_mean((double)l, (double)mr) && l != 0;
+    return cg_comparable_mean_u(l, mr) && l != 0;
 }

@@ -113,12 +113,12 @@ __global__ void __launch_bounds__(CG_SPLIT_THREADS) k_split(CgChunk c) {
             const u32 nbits = 32u - (u32)__clz((int)mx);
             const u32 ilo = (u32)floor((double)(n - 1) * 0.2);     // deciles, bmean.cpp:324-327
             const u32 ihi = (u32)ceil((double)(n - 1) * 0.8);
-            const double lo = (double)cg_select_distance_reg(d, nbits, ilo);
-            const double hi = (double)cg_select_distance_reg(d, nbits, ihi);
+            const u32 lo = cg_select_distance_reg(d, nbits, ilo);
+            const u32 hi = cg_select_distance_reg(d, nbits, ihi);
             u32 sum = 0, cnt = 0;
 #pragma unroll
             for (u32 t = 0; t < CG_SPLIT_REG_READS; ++t)
-                if (d[t] != 0xffffffffu && cg_comparable_dec((double)d[t], lo, hi)) { sum += d[t]; ++cnt; }
+                if (d[t] != 0xffffffffu && cg_comparable_dec_u(d[t], lo, hi)) { sum += d[t]; ++cnt; }      // distances are < 2^16
             sum = cg_warp_sum(sum);
             cnt = cg_warp_sum(cnt);
             if (lane == 0) rel[i] = cnt ? sum / cnt : 0u;           // integer division, bmean.cpp:401
