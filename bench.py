@@ -378,7 +378,7 @@ def acc_kernels(acc: dict, ks: dict) -> None:
         a["dp_cells"] = v.get("dp_cells", 0); a["dp_pred_cells"] = v.get("dp_pred_cells", 0)      # per run, identical every step
 
 
-def roofline_row(ktab: dict, peak: float, peak_src: str, traffic_json: dict, ms_per_step: float) -> dict:
+def roofline_row(ktab: dict, peak: float, peak_src: str, traffic_json: dict, ms_per_step: float, windows_per_step: int) -> dict:
     """The dominant kernel = the one that does most of the path's algorithmic work per step (the wide POA tier's few long jobs run
     for a long time in the background of a 150-sequence step without doing much of its work, so the longest-running kernel would
     be the wrong pick there)."""
@@ -388,8 +388,14 @@ def roofline_row(ktab: dict, peak: float, peak_src: str, traffic_json: dict, ms_
     per_launch = v["algorithmic_bytes_per_step"] / v["launches_per_step"]
     achieved = per_launch / (v["ms_per_launch"] / 1e3) / 1e9
     tr = traffic_json.get(dom, {})
+    traffic = None
+    if tr.get("dram_bytes_per_window") is not None:       # per launch like `achieved`: bytes per window x windows of a step / launches per step
+        traffic = int(tr["dram_bytes_per_window"] * windows_per_step / v["launches_per_step"])
     return {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": tr.get("dram_bytes_per_launch"), "traffic_source": tr.get("source", "none: no ncu capture of this kernel committed"),
+            "traffic": traffic,
+            "traffic_source": (tr["source"] + f"; {tr['dram_bytes_per_window']:.0f} DRAM bytes per window ({tr.get('shape', '')}) x the step's windows / "
+                               "launches per step — a constant from an ncu capture, not measured in this run") if traffic is not None
+            else "none: no ncu capture of this kernel committed",
             "peak_source": peak_src, "algorithmic_bytes_per_launch": per_launch, "launches_per_step": v["launches_per_step"],
             "ms_per_launch": v["ms_per_launch"],
             "timing": "each launch bracketed by its own CUDA events on the stream it runs on (cg_get_kernel_stats); kernels of "
@@ -430,7 +436,7 @@ def bench_config2(cor, cores: int, steps: int, warmup: int, peak: float, peak_sr
            "windows": W, "value": W * steps / (dev_ms / 1e3), "unit": "windows/s", "ms_per_step": dev_ms / steps,
            "e2e": {"value": W / e2e_s, "unit": "windows/s", "h2d_bytes_per_step": int(batch.n_bases + batch.seq_off.nbytes + batch.win_seq_begin.nbytes),
                    "d2h_bytes_per_step": int(res.cons.nbytes + res.status.nbytes + res.cons_off.nbytes + res.solid_off.nbytes + res.solid_kmer.nbytes + res.solid_count.nbytes)},
-           "roofline": roofline_row(ktab, peak, peak_src, traffic_json, dev_ms / steps),
+           "roofline": roofline_row(ktab, peak, peak_src, traffic_json, dev_ms / steps, W),
            "parity_full_stream": parity,
            "counters_per_step": counters}
     try:
@@ -622,7 +628,7 @@ def main():
     abk = {name: 2 * (kacc[name]["dp_cells"] + kacc[name]["dp_pred_cells"]) for name in ("k_poa2<C1>", "k_poa2<G>", "k_poa2<W1>", "k_poa2<W2>") if name in kacc}
     abk["k_index"] = ab["index"]
     ktab = kernel_table(kacc, args.steps, abk)
-    roofline = roofline_row(ktab, peak, peak_src, traffic_json, dev_ms / args.steps)
+    roofline = roofline_row(ktab, peak, peak_src, traffic_json, dev_ms / args.steps, args.windows)
     roofline["whole_path_GBps"] = ab["window_total"] / (dev_ms / args.steps / 1e3) / 1e9
     roofline["poa_all_tiers"] = {"algorithmic_bytes_per_step": ab["poa"], "note": "tiers run side by side; see kernels[*] for each"}
     roofline["stage_ms_per_step"] = {k: round(v, 3) for k, v in stage_avg.items()}
