@@ -195,3 +195,13 @@ def test_emulated_kernels_match_the_oracle_stage_by_stage(emu, oracle):
         cor.run()
         for w in range(batch.n_windows):
             assert _stage_lines(cor.dump_window(w)) == _stage_lines(oracle.dump_window(batch, w, params)), f"window {w}, {params}"
+
+
+def test_integer_comparable_tests_equal_the_fp64_ones(entry):
+    """cg_common.cuh evaluates comparable(x, mean) (bmean.cpp:286-295) and comparable(x, deciles) (:264-282) in integers on the device;
+    the product's own functions, compiled for the host, agree with the fp64 forms on every argument of a dense grid and around powers of two."""
+    import ctypes as C
+    lib = C.CDLL(entry.build_emu())
+    lib.emu_comparable_selfcheck.restype = C.c_uint64
+    lib.emu_comparable_selfcheck.argtypes = [C.c_uint32, C.c_uint32]
+    assert lib.emu_comparable_selfcheck(1500, 1500) == 0
