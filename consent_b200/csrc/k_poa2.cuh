@@ -630,11 +630,7 @@ __device__ __forceinline__ i32 cg_poa2_dp(const CgPoa2G<T>& s, u32 V, const u8* 
 // Column 0 is lane 0's low half: it is forced to 0 in every row.  Rows have an even stride, so the pairs are aligned.
 __device__ __forceinline__ u32 cg_vadd2(u32 a, u32 b) { return __vadd2(a, b); }
 __device__ __forceinline__ u32 cg_vmax2(u32 a, u32 b) { return __vmaxs2(a, b); }
-#ifndef CG_EMU
 __device__ __forceinline__ u32 cg_viaddmax2_relu(u32 a, u32 b, u32 c) { return __viaddmax_s16x2_relu(a, b, c); }
-#else
-__device__ __forceinline__ u32 cg_viaddmax2_relu(u32 a, u32 b, u32 c) { return __vmaxs2(__vmaxs2(__vadd2(a, b), c), 0u); }
-#endif
 template <int CH, class T>
 __device__ __forceinline__ i32 cg_poa2_dp2(const CgPoa2G<T>& s, u32 V, const u8* seq, u32 L, u32 Ws, CgPoa2Max& trk) {
     CG_P2_TYPES;

@@ -23,13 +23,7 @@
 #pragma once
 #include <type_traits>
 
-__device__ __forceinline__ u32 cg_viaddmax2(u32 a, u32 b, u32 c) {
-#ifndef CG_EMU
-    return __viaddmax_s16x2(a, b, c);
-#else
-    return __vmaxs2(__vadd2(a, b), c);
-#endif
-}
+__device__ __forceinline__ u32 cg_viaddmax2(u32 a, u32 b, u32 c) { return __viaddmax_s16x2(a, b, c); }
 __device__ __forceinline__ u32 cg_pcode(u32 ch) { return (ch >> 1) & 3u; }       // A 0, C 1, T 2, G 3: row of the query profile
 
 // Row descriptor of the wide tiers (shared memory, one word per matrix row - 1): letter code | in-degree << 2 | first predecessor

@@ -275,13 +275,7 @@ __device__ CG_NOINLINE void cg_polish(const CgDbg& d, u8* buf, u32 cap, u32 n_in
                     u32 curBranches = 0;
                     const u32 gap = tmpDstBeg - tmpSrcEnd - 1;
                     // 15.0 / 100.0 * 2.0 * gap + gap + merSize, evaluated left to right in fp64, no FMA  (:163)
-#ifdef CG_EMU
-                    volatile double t0 = (15.0 / 100.0 * 2.0) * (double)gap;
-                    volatile double t1 = t0 + (double)gap;
-                    const double t2 = t1 + (double)k;
-#else
                     const double t2 = __dadd_rn(__dadd_rn(__dmul_rn(15.0 / 100.0 * 2.0, (double)gap), (double)gap), (double)k);
-#endif
                     const u32 maxSize = (u32)t2;
                     for (u32 q = 0; q < k; ++q) P[q] = cg_to_upper(cr[tmpSrcBeg + q]);
                     u32 pl = k;

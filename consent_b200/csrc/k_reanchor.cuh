@@ -85,17 +85,6 @@ __device__ __forceinline__ int cg_ra_wsum(int v) {
 
 struct CgRaEnd { int score, col, row; };
 
-// a * b + c on the FMA pipe (as a shift-add it would be one more instruction for the ALU pipe, which bounds the scan)
-__device__ __forceinline__ u32 cg_ra_mad(u32 a, u32 b, u32 c) {
-#ifndef CG_EMU
-    u32 r;
-    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
-    return r;
-#else
-    return a * b + c;
-#endif
-}
-
 // One band of a scan: query rows [row0, row0 + 32 * RPL) (rows >= nq are padding), every reference column.  RPL rows per
 // lane, all in registers.  The only loop-carried chain inside a lane is F: with hp = max(diag + s, E) and g = max(hp - 3, 0),
 //   F' = max(F - 1, max(H - 3, 0)) = max(F - 1, g)          (H = max(hp, F), and F - 3 < F - 1)
@@ -165,7 +154,7 @@ __device__ __forceinline__ void cg_ra_band(const char* qsrc, int qfirst, int qst
             h2 = cg_vmax2(hp, f2);
             f2 = cg_viaddmax2(f2, 0xffffffffu, g);
             d2 = H2[i]; H2[i] = h2;
-            cm2 = cg_vmax2(cm2, KEY16 ? cg_ra_mad(h2, 16u, (u32)(15 - i) * 0x00010001u) : h2);
+            cm2 = cg_vmax2(cm2, KEY16 ? h2 * 16u + (u32)(15 - i) * 0x00010001u : h2);
             E2[i] = cg_viaddmax2(E2[i], 0xffffffffu, cg_viaddmax2(h2, 0xfffdfffdu, zero));
         }
         // hand-over: B's last row to the next lane, A's last row to this lane's B

@@ -313,6 +313,10 @@ static inline unsigned __vmaxs2(unsigned a, unsigned b) {         // per-halfwor
     const short al = (short)(a & 0xffffu), bl = (short)(b & 0xffffu), ah = (short)(a >> 16), bh = (short)(b >> 16);
     return (unsigned)(unsigned short)(al > bl ? al : bl) | ((unsigned)(unsigned short)(ah > bh ? ah : bh) << 16);
 }
+static inline unsigned __viaddmax_s16x2(unsigned a, unsigned b, unsigned c) { return __vmaxs2(__vadd2(a, b), c); }            // per halfword max(a + b, c)
+static inline unsigned __viaddmax_s16x2_relu(unsigned a, unsigned b, unsigned c) { return __vmaxs2(__vmaxs2(__vadd2(a, b), c), 0u); }
+static inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }                                      // one rounding each, no contraction
+static inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
 static inline unsigned __byte_perm(unsigned x, unsigned y, unsigned sel) {
     const unsigned long long v = ((unsigned long long)y << 32) | x;
     unsigned r = 0;
