@@ -23,6 +23,27 @@
 #define CG_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #define CG_DYN_SMEM(name) extern __shared__ __align__(128) unsigned char name[]
 #define CG_NOINLINE __noinline__
+// sm_100a-only pieces (the emulator header defines the same names for the CPU suite): SM id, L1 prefetch, TMA bulk copies.
+__device__ __forceinline__ unsigned cg_smid() { unsigned r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cg_prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+// Two bulk copies HBM -> shared memory by the TMA engine (cp.async.bulk -> UBLKCP), `bytes` each (a multiple of 16; both sides 16-byte
+// aligned), completing on one mbarrier.  cg_bulk_issue2: ONE thread; cg_bulk_wait: every thread, after a __syncthreads() behind the issue.
+__device__ __forceinline__ void cg_bulk_issue2(void* dst0, const void* src0, void* dst1, const void* src1, unsigned bytes, uint64_t* bar) {
+    const unsigned bar_a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(2u * bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"((unsigned)__cvta_generic_to_shared(dst0)), "l"(src0), "r"(bytes), "r"(bar_a) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"((unsigned)__cvta_generic_to_shared(dst1)), "l"(src1), "r"(bytes), "r"(bar_a) : "memory");
+}
+__device__ __forceinline__ void cg_bulk_wait(uint64_t* bar) {
+    const unsigned bar_a = (unsigned)__cvta_generic_to_shared(bar);
+    unsigned done = 0;
+    while (!done)
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(bar_a) : "memory");
+}
 #else
 #define CG_NOINLINE __attribute__((noinline))
 #endif

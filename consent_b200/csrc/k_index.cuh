@@ -31,10 +31,6 @@
 #define CG_IDX_THREADS 1024u
 #endif
 #define CG_IDX_SMEM_BYTES (131072u + 8u * CG_PW_CAP + 2u * 2048u * 4u + 16384u + 64u * 4u + 16u)     // table | pile words, tags | template k-mers, counts | solid bitmap | misc, barrier
-#ifndef CG_EMU
-__device__ __forceinline__ u32 cg_smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
-#endif
-
 __global__ void __launch_bounds__(CG_IDX_THREADS, 1) k_index(CgChunk c) {
     CG_DYN_SMEM(smem);
     u32* tab = (u32*)smem;
@@ -67,37 +63,12 @@ __global__ void __launch_bounds__(CG_IDX_THREADS, 1) k_index(CgChunk c) {
         const u32 shift = (u32)(g0 - ga);
         const u32 ncopy = (shift + nw + 1 + 3) & ~3u; // + the look-ahead word; multiple of 16 bytes
         if (ncopy <= CG_PW_CAP) {
-#ifndef CG_EMU
             u64* bar = (u64*)(misc + 64);
-            const u32 bar_a = cg_smem_addr(bar);
-            if (tid == 0) {
-                asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
-                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-                const u32 bytes = ncopy * 4u;
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(2u * bytes) : "memory");
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                             ::"r"(cg_smem_addr(pile_s)), "l"(c.pwords + ga), "r"(bytes), "r"(bar_a) : "memory");
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                             ::"r"(cg_smem_addr(tags_s)), "l"(c.ptags + ga), "r"(bytes), "r"(bar_a) : "memory");
-            }
+            if (tid == 0) cg_bulk_issue2(pile_s, c.pwords + ga, tags_s, c.ptags + ga, ncopy * 4u, bar);
             for (u32 i = tid; i < 32768; i += T) tab[i] = 0;         // the first pass's counters, while the copy is in flight
             if (tid == 0) misc[0] = 0;
             __syncthreads();                                          // the barrier's init is visible to every waiter
-            asm volatile(
-                "{\n"
-                ".reg .pred p;\n"
-                "CG_WAIT:\n"
-                "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
-                "@p bra CG_DONE;\n"
-                "bra CG_WAIT;\n"
-                "CG_DONE:\n"
-                "}\n" ::"r"(bar_a) : "memory");
-#else
-            for (u32 i = tid; i < ncopy; i += T) { pile_s[i] = c.pwords[ga + i]; tags_s[i] = c.ptags[ga + i]; }
-            for (u32 i = tid; i < 32768; i += T) tab[i] = 0;
-            if (tid == 0) misc[0] = 0;
-            __syncthreads();
-#endif
+            cg_bulk_wait(bar);
             pw = pile_s + shift;
             pt = tags_s + shift;
             staged = true;
@@ -192,12 +163,7 @@ __global__ void __launch_bounds__(CG_IDX_THREADS, 1) k_index(CgChunk c) {
         // the solid keys are collected, sorted in shared memory (bitonic, <= 32768 keys) and written in key order with their counts.
         pw = c.pwords + g0;
         pt = c.ptags + g0;
-        u32 slot;
-#ifndef CG_EMU
-        asm volatile("mov.u32 %0, %%smid;" : "=r"(slot));
-#else
-        slot = blockIdx.x;
-#endif
+        const u32 slot = cg_smid();                  // one table per SM (the emulator: per CTA)
         const u32 cap = c.idx_cap, hmask = cap - 1u;
         bool ovf = slot >= c.idx_slots || (u64)2 * W.n_occ > (u64)cap;
         u32* hk = c.idx_keys + (size_t)(ovf ? 0u : slot) * cap;

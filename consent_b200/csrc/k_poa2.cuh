@@ -396,11 +396,7 @@ template <class T> __device__ __forceinline__ bool cg_poa2_dfs_run(const CgPoa2G
 // A line into L1 ahead of its use (no registers held): the next row's predecessor vector during the DP.  (Prefetching the matrix
 // rows a traceback is about to reach — four rows ~7 steps ahead, or one row 8 steps ahead along the first-predecessor chain —
 // measured no gain on the wide tiers and was dropped.)
-#if !defined(CG_EMU)
-#define CG_P2_PREFETCH(p) asm volatile("prefetch.global.L1 [%0];" ::"l"(p))
-#else
-#define CG_P2_PREFETCH(p) ((void)(p))
-#endif
+#define CG_P2_PREFETCH(p) cg_prefetch_l1(p)
 
 // ------------------------------------------------------------------ traceback (compact tiers), by the whole warp
 // simd_alignment_engine_impl.hpp:968-1004: diagonal over the predecessors in in-edge order, then vertical over them,

@@ -411,3 +411,8 @@ static inline cudaError_t cudaMemGetInfo(size_t* fr, size_t* tot) { *fr = (size_
 #define CG_LAUNCH(kernel, grid, block, smem, stream, ...) \
     cg_emu::launch(dim3(grid), dim3(block), (smem), [=]() { kernel(__VA_ARGS__); })
 #define CG_DYN_SMEM(name) unsigned char* name = cg_emu::cur->blk->dyn_smem
+// the sm_100a-only helpers of cg_common.cuh: one count table per CTA instead of per SM, no prefetch, the bulk copies as plain copies
+static inline unsigned cg_smid() { return blockIdx.x; }
+static inline void cg_prefetch_l1(const void*) {}
+static inline void cg_bulk_issue2(void* dst0, const void* src0, void* dst1, const void* src1, unsigned bytes, uint64_t*) { memcpy(dst0, src0, bytes); memcpy(dst1, src1, bytes); }
+static inline void cg_bulk_wait(uint64_t*) {}
