@@ -1,4 +1,4 @@
-"""Debug: per-job phase clocks of the POA tiers (needs alt/libconsent_timing.so built with -DCG_POA_TIMING).
+"""Debug: per-job phase clocks of the POA tiers (builds alt/libconsent_timing.so with -DCG_POA_TIMING if it is not there; run from the repo root).
 python tools/poa_job_timing.py [windows] [n_seqs]"""
 import ctypes as C, os, sys
 sys.path.insert(0, os.environ.get("GRAFT_REPO_ROOT", os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
@@ -10,6 +10,12 @@ import numpy as np  # noqa: E402
 W = int(sys.argv[1]) if len(sys.argv) > 1 else 4000
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 lib = "alt/libconsent_timing.so"
+if not os.path.exists(lib):                              # the instrumented build (per-job phase clocks): not part of build()
+    import subprocess
+    os.makedirs("alt", exist_ok=True)
+    subprocess.run([os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc"), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+                    "-fmad=false", "-DCG_POA_TIMING", "-Xcompiler", "-fPIC", "-shared", "-I", "include", "-I", "consent_b200/csrc", "-o", lib,
+                    "consent_b200/csrc/consent_b200.cu", "-ldl"], check=True)
 cor = Corrector(Params(), lib_path=lib)
 cor.upload(synth_windows(W, N, seed=42))
 cor.run()
