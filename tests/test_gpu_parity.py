@@ -250,6 +250,24 @@ def test_gpu_kmer_counts_around_the_byte_counter_width(gpu, oracle):
     assert_same(gpu().correct_windows(batch), want, "k-mer counts of 255 / 256 / 257")
 
 
+def test_gpu_position_table_too_big_for_the_pair_bits(gpu, oracle):
+    """k_index tells a k-mer held twice by one read from one bit per (read, candidate) in shared memory while reads x candidates fit
+    458 752 bits; a deep low-error pile (1 500 reads, ~340 candidates) exceeds that and takes the sweep over the position table."""
+    import random
+    from tests.cases import _mutate, _rand_seq
+    rng = random.Random(17)
+    truth = _rand_seq(rng, 500)
+    pile = [_mutate(rng, truth, 0.04) for _ in range(1500)]
+    batch = Batch.from_piles([pile, pile[:40]])
+    want, _ = oracle.correct_windows(batch, threads=8)
+    cor = gpu()
+    got = cor.correct_windows(batch)
+    assert_same(got, want, "1500-deep low-error pile")
+    one = gpu()
+    one.correct_windows(Batch.from_piles([pile]))
+    assert one.counters()["anchors"] * 1500 > 458752          # the deep window's chain alone is longer than the bit table allows candidates for
+
+
 def test_gpu_two_handles_in_two_threads(gpu, oracle):
     """The ABI is re-entrant per handle (the reference call is made from --nproc threads, src/CONSENT-correction.cpp:76-111)."""
     import threading
